@@ -1,0 +1,160 @@
+"""TEST INFRASTRUCTURE ONLY -- generate tests/golden/*.npz from the UNMODIFIED reference source.
+
+Run in the development container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+What comes from where:
+  * env trajectories, prior dynamics, obs<->state maps, prior disturbance, constraint assembly (P,q,G,h) and the
+    CascadeCBFLayer assembly are outputs of the reference's own code (imported via oracle/ref_loader.py).
+  * `safe_action` / `grad_action` are outputs of the reference's own CBFQPLayer.get_safe_action with
+    ``qpth.qp.QPFunction`` bound to oracle/qpth_pdipm.py (qpth itself is not installed anywhere in this image, so
+    the solve step is a restatement -- parity for it is unpinned, see that file's header).
+  * `x_exact` is oracle/exact_qp.py on the reference-assembled, reference-normalised (G~, h~).
+Seeds: 12345 (the reference's default --seed, main.py:223).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import exact_qp, ref_loader, rcbf_oracle as O  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+tt = torch.from_numpy
+
+
+def layer_fixture(ref, mode, B, gamma_b):
+    args = ref_loader.make_args()
+    env = ref.UnicycleEnv() if mode == "Unicycle" else ref.SimulatedCarsEnv()
+    layer = ref.CBFQPLayer(env, args, gamma_b=gamma_b, k_d=3.0, l_p=0.03)
+    if mode == "Unicycle":
+        st, ac, mu, sg = O.synth_unicycle(B, seed=12345)
+        t = np.zeros(B, np.float32)
+    else:
+        st, ac, mu, sg, t = O.synth_cars(B, seed=12345)
+    P, q, G, h = layer.get_cbf_qp_constraints(tt(st), tt(ac), tt(mu), tt(sg))
+    # reference normalisation lines replayed verbatim in spirit (diff_cbf_qp.py:103-106)
+    Gh = torch.cat((G, h.unsqueeze(2)), -1)
+    n = torch.max(torch.abs(Gh), dim=2, keepdim=True)[0]
+    Gn, hn = G / n, h / n.squeeze(-1)
+    a = tt(ac).clone().requires_grad_(True)
+    final = layer.get_safe_action(tt(st), a, tt(mu), tt(sg))
+    # a fixed, seeded upstream gradient
+    w = torch.from_numpy(np.random.default_rng(777).normal(size=final.shape).astype(np.float32))
+    (final * w).sum().backward()
+    xe, lam, act, viol = exact_qp.solve_exact(P.double().numpy(), q.double().numpy(), Gn.double().numpy(),
+                                              hn.double().numpy())
+    # 1-D call contract (diff_cbf_qp.py:64-69,79)
+    final_1d = layer.get_safe_action(tt(st[0]), tt(ac[0]), tt(mu[0]), tt(sg[0]))
+    return dict(state=st, action=ac, mean=mu, sigma=sg, t=t, gamma_b=np.float32(gamma_b),
+                P=P.numpy(), q=q.numpy(), G=G.numpy(), h=h.numpy(), Gn=Gn.numpy(), hn=hn.numpy(),
+                safe_action=final.detach().numpy(), grad_w=w.numpy(), grad_action=a.grad.numpy(),
+                x_exact=xe, lam_exact=lam, active_exact=act, viol_exact=viol, safe_action_1d=final_1d.numpy())
+
+
+def unicycle_traj(ref, T=900):
+    env = ref.UnicycleEnv()
+    rng = np.random.default_rng(12345)
+    obs0 = env.reset()
+    acts = rng.uniform(-1.5, 1.5, (T, 2))      # beyond [-1,1] on purpose: exercises the clip (unicycle_env.py:62)
+    # steer through a hazard and to the goal so cost / goal_met / done all occur
+    obs, rew, done, cost, goal, states = [], [], [], [], [], []
+    for k in range(T):
+        a = acts[k].copy()
+        if k >= 50:                            # P-controller toward the goal, like the reference's demo controller
+            o = obs[-1]
+            a = np.array([1.0, 2.0 * np.arctan2(o[5], o[4])]) + 0.1 * acts[k]
+            acts[k] = a
+        o, r, d, info = env.step(a)
+        obs.append(o.copy()); rew.append(r); done.append(d); cost.append(info.get("cost", 0.0))
+        goal.append(bool(info.get("goal_met", False))); states.append(env.state.copy())
+        if d:
+            acts = acts[:k + 1]
+            break
+    return dict(obs0=obs0, actions=acts, obs=np.array(obs), reward=np.array(rew), done=np.array(done),
+                cost=np.array(cost), goal_met=np.array(goal), state=np.array(states))
+
+
+def cars_traj(ref, T=300):
+    np.random.seed(0)
+    env = ref.SimulatedCarsEnv()
+    np.random.seed(0)
+    obs0 = env.reset()
+    v_noise = env.state[1] - 30.0
+    rng = np.random.default_rng(12345)
+    acts = rng.uniform(-1.0, 1.0, (T, 1)) * np.linspace(0.2, 3.0, T)[:, None]
+    obs, rew, done, cost, states, ts = [], [], [], [], [], []
+    for k in range(T):
+        o, r, d, info = env.step(acts[k].copy())
+        obs.append(o.copy()); rew.append(r); done.append(d); cost.append(info["cost"]); states.append(env.state.copy())
+        ts.append(env.t)
+    return dict(obs0=obs0, v_noise=np.float64(v_noise), actions=acts, obs=np.array(obs), reward=np.array(rew),
+                done=np.array(done), cost=np.array(cost), state=np.array(states), t=np.array(ts))
+
+
+def dynamics_fixture(ref, B=64):
+    args = ref_loader.make_args()
+    out = {}
+    for mode, envc in (("Unicycle", ref.UnicycleEnv), ("SimulatedCars", ref.SimulatedCarsEnv)):
+        env = envc()
+        dm = ref.DynamicsModel(env, args)
+        if mode == "Unicycle":
+            st, ac, _, _ = O.synth_unicycle(B, seed=4242)
+            t = None
+        else:
+            st, ac, _, _, t = O.synth_cars(B, seed=4242)
+            t = t.astype(np.float64)
+        st = st.astype(np.float64); ac = ac.astype(np.float64)
+        nxt, std, tn = dm.predict_next_state(st, ac, t_batch=t)
+        obs = dm.get_obs(st)
+        st_back = dm.get_state(obs)
+        mean, fstd = dm.predict_disturbance(st)
+        k = mode.lower()
+        out.update({k + "_state": st, k + "_action": ac, k + "_next": nxt, k + "_std_dt": std, k + "_obs": obs,
+                    k + "_state_from_obs": st_back, k + "_dist_mean": mean, k + "_dist_std": fstd})
+        if t is not None:
+            out[k + "_t"] = t
+            out[k + "_t_next"] = tn
+    return out
+
+
+def cascade_fixture(ref, B=16):
+    env = ref.UnicycleEnv()
+    lay = ref.CascadeCBFLayer(env, gamma_b=100, k_d=1.5, l_p=0.03)
+    st, ac, mu, sg = (a.astype(np.float64) for a in O.synth_unicycle(B, seed=99))
+    Gs, hs, Ps = [], [], []
+    for i in range(B):
+        P, q, G, h = lay.get_cbf_qp_constraints(ac[i], st[i], mu[i], sg[i])
+        Gs.append(G); hs.append(h); Ps.append(P)
+    envc = ref.SimulatedCarsEnv()
+    layc = ref.CascadeCBFLayer(envc, gamma_b=100, k_d=1.5)
+    stc, acc, muc, sgc, _ = (a.astype(np.float64) for a in O.synth_cars(B, seed=99))
+    Gc, hc = [], []
+    for i in range(B):
+        P, q, G, h = layc.get_cbf_qp_constraints(acc[i], stc[i], muc[i], sgc[i])
+        Gc.append(G); hc.append(np.asarray(h, np.float64))
+    return dict(state=st, action=ac, mean=mu, sigma=sg, G=np.array(Gs), h=np.array(hs), P=np.array(Ps),
+                cars_state=stc, cars_action=acc, cars_sigma=sgc, cars_G=np.array(Gc), cars_h=np.array(hc))
+
+
+def main():
+    ref = ref_loader.load_reference()
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(12345)
+    np.savez_compressed(os.path.join(OUT, "unicycle_layer_b256.npz"), **layer_fixture(ref, "Unicycle", 256, 20.0))
+    np.savez_compressed(os.path.join(OUT, "cars_layer_b512.npz"), **layer_fixture(ref, "SimulatedCars", 512, 20.0))
+    np.savez_compressed(os.path.join(OUT, "unicycle_env_traj.npz"), **unicycle_traj(ref))
+    np.savez_compressed(os.path.join(OUT, "cars_env_traj.npz"), **cars_traj(ref))
+    np.savez_compressed(os.path.join(OUT, "dynamics_prior.npz"), **dynamics_fixture(ref))
+    np.savez_compressed(os.path.join(OUT, "cascade_layer.npz"), **cascade_fixture(ref))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
