@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- safe env-steps/s of the SAC-RCBF safety hot path (dynamics + RCBF-QP) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference's CPU path: oracle port, host cores)
+
+Workload (BASELINE.json configs[3], "Unicycle with GP-robust constraints", sized for one GPU): every rank owns
+`--instances` (default 4 Mi = 4x config 4's 1 Mi, so that one step's inputs exceed the 126 MB L2) persistent Unicycle
+env instances with auto-reset; one "step" = ONE fused launch (assemble RCBF constraints from the GP mean/std tensors,
+solve the QP, clamp, env.step, write obs/reward/done/cost) over all of them with a fresh synthetic (u_RL, mean, std)
+batch.  Instances shard by rank; there is no collective on the step path (weak scaling).
+
+JSON keys beyond the base contract: roofline (HBM bytes model + FP32 flop model, both measured live), cpu_baseline
+(oracle port on the host cores), e2e (same step through the public env API with pinned HOST buffers, H2D + D2H inside
+the timed region), clocks, gpu_launches, extra (solver statistics + secondary workloads).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic bytes of one Unicycle safe step (DESIGN.md section "Roofline"):
+#   in : state4 16 + step 4 + u_rl 8 + mean 12 + sigma 12 = 52      out: state4 16 + step 4 + u_safe 8 + obs 28 +
+#   reward 4 + done 1 + cost 4 + goal_met 1 = 66
+UNI_BYTES_PER_STEP = 52 + 66
+# flop model of SURVEY.md 8(d): F_asm + (K + 1/2) F_iter + F_dyn, F_iter(3,9) = 918, F_asm = 260, F_dyn = 110;
+# K = executed interior-point iterations (0 for instances certified trivially feasible: those skip the init solve too)
+F_ITER_UNI, F_ASM_UNI, F_DYN_UNI = 918.0, 260.0, 110.0
+CERT_FLOPS_UNI = 250.0  # one float64 KKT certificate attempt, counted per executed iteration
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=1 << 22, help="env instances per GPU")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="budget of the cpu_baseline sample")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference's CPU path
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_step(O, batch, st, ac, mu, sg):
+    """One pass of the reference's CPU path over `len(st)` instances, in batches of `batch` like sac_cbf.py does:
+    f32 torch assembly (diff_cbf_qp.py:146-379) + row normalisation (:103-106) + qpth PDIPM in f64 (:139, restated) +
+    clamp (:77) + UnicycleEnv.step arithmetic in numpy f64 (envs/unicycle_env.py:46-111)."""
+    tt = torch.from_numpy
+    n = st.shape[0]
+    for lo in range(0, n, batch):
+        sl = slice(lo, min(n, lo + batch))
+        ua = O.safe_action("Unicycle", tt(st[sl]), tt(ac[sl]), tt(mu[sl]), tt(sg[sl]), gamma_b=20.0).numpy()
+        s64 = st[sl].astype(np.float64)
+        O.unicycle_env_step(s64, ua.astype(np.float64), np.zeros(s64.shape[0], np.int64), O.unicycle_goal_dist(s64))
+
+
+def time_cpu_reference(seconds, batch=512):
+    from oracle import rcbf_oracle as O
+
+    st, ac, mu, sg = O.synth_unicycle(batch * 8, seed=12345)
+    cpu_reference_step(O, batch, st[:batch], ac[:batch], mu[:batch], sg[:batch])   # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        cpu_reference_step(O, batch, st, ac, mu, sg)
+        done += st.shape[0]
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return done / el, done, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import rcbf_oracle as O
+
+    batch, per_step = 512, 4096
+    st, ac, mu, sg = O.synth_unicycle(per_step, seed=12345)
+    for _ in range(args.warmup):
+        cpu_reference_step(O, batch, st[:batch], ac[:batch], mu[:batch], sg[:batch])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_step(O, batch, st, ac, mu, sg)
+    el = time.perf_counter() - t0
+    v = per_step * args.steps / el
+    cores = torch.get_num_threads()
+    sample = "%d steps x %d Unicycle instances in batches of %d (reference batch size, sac_cbf.py)" % (
+        args.steps, per_step, batch)
+    print(json.dumps({
+        "impl": "reference", "metric": "safe env-steps/sec (dynamics+RCBF-QP)", "value": v, "unit": "env-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 assembly + f64 QP (qpth)",
+        "data": "synthetic", "config": {"workload": "config4-unicycle-gp-robust-safe-step", "instances_per_step": per_step},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def synth_inputs(n, device, seed, sets):
+    """`sets` rotating (u_rl, mean, sigma) batches + initial states, SURVEY 8(d) distributions incl. 20% hazard-heavy."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    U = lambda lo, hi, *s: lo + (hi - lo) * torch.rand(*s, generator=g, device=device)  # noqa: E731
+    st = torch.stack([U(-3, 3, n), U(-3, 3, n), U(-np.pi, np.pi, n)], 1)
+    nh = n // 5
+    hz = torch.tensor([[0., 0.], [-1.5, 1.5], [-1.5, -1.5], [1.5, -1.5], [1.5, 1.5]], device=device)
+    idx = torch.randint(0, 5, (nh,), generator=g, device=device)
+    sel = torch.randperm(n, generator=g, device=device)[:nh]
+    r, phi = U(0.3, 1.1, nh), U(-np.pi, np.pi, nh)
+    st[sel, 0] = hz[idx, 0] + r * torch.cos(phi)
+    st[sel, 1] = hz[idx, 1] + r * torch.sin(phi)
+    batches = [(U(-1, 1, n, 2).contiguous(), U(-0.1, 0.1, n, 3).contiguous(), U(0, 0.2, n, 3).contiguous())
+               for _ in range(sets)]
+    return st.contiguous(), batches
+
+
+def fma_probe_tflops(lib, _lib, device):
+    sink = torch.zeros(4, device=device)
+    blocks, threads, iters = 148 * 16, 256, 4096
+    s = _lib.stream_ptr(device)
+    for _ in range(2):
+        lib.rcbf_fp32_fma_probe(_lib.ptr(sink), blocks, threads, iters, s)
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(5):
+        e0.record()
+        lib.rcbf_fp32_fma_probe(_lib.ptr(sink), blocks, threads, iters, s)
+        e1.record()
+        torch.cuda.synchronize(device)
+        best = min(best, e0.elapsed_time(e1))
+    return 2.0 * 8 * iters * blocks * threads / (best * 1e-3) / 1e12
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=device)
+
+    import sac_rcbf_b200 as S
+    from sac_rcbf_b200 import _lib
+
+    lib = S.load_library()
+    n = args.instances
+    ns = types.SimpleNamespace(cuda=True, gp_model_size=2000, l_p=0.03, device_num=local)
+    env = S.UnicycleEnv(num_envs=n, device=device, auto_reset=True)
+    layer = S.CBFQPLayer(env, ns, gamma_b=20, k_d=3.0, l_p=0.03)
+    SETS = 2
+    st0, batches = synth_inputs(n, device, 12345 + rank, SETS)
+    env.state = st0
+    env._counters = torch.zeros(8, dtype=torch.int64, device=device)
+    env._safe_action = torch.empty((n, 2), dtype=torch.float32, device=device)
+
+    def step(k):
+        u, mu, sg = batches[k % SETS]
+        env.safe_step(layer, u, mu, sg)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    barrier()
+    env._counters.zero_()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        step(k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    counters = env._counters.clone()
+    if dist is not None:
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)   # optional rollout statistics gather: off the timed path
+    c = counters.cpu().tolist()
+    total_steps = float(n) * world * args.steps
+    value = total_steps / (ms * 1e-3)
+    kernel_ms = ms / args.steps                      # one fused launch per step
+    iters_mean = c[4] / total_steps
+    nontrivial = 1.0 - c[3] / total_steps
+
+    # ---------------------------------------------------------------- e2e: public env API with pinned host buffers
+    e2e = None
+    extra = {}
+    if True:
+        CH = 8
+        per = (n + CH - 1) // CH
+        h_in = [tuple(b.cpu().pin_memory() for b in batches[k]) for k in range(SETS)]
+        d_in = (torch.empty_like(batches[0][0]), torch.empty_like(batches[0][1]), torch.empty_like(batches[0][2]))
+        h_out = dict(u=torch.empty((n, 2)).pin_memory(), obs=torch.empty((n, 7)).pin_memory(),
+                     rew=torch.empty((n,)).pin_memory(), cost=torch.empty((n,)).pin_memory(),
+                     done=torch.empty((n,), dtype=torch.uint8).pin_memory())
+        streams = [torch.cuda.Stream(device) for _ in range(3)]
+        p_layer, p_env = layer._params(), env._env_params()
+
+        def e2e_step(k):
+            hi = h_in[k % SETS]
+            for cidx in range(CH):
+                lo, up = cidx * per, min(n, (cidx + 1) * per)
+                if lo >= up:
+                    break
+                s = streams[cidx % 3]
+                with torch.cuda.stream(s):
+                    for dst, src in zip(d_in, hi):
+                        dst[lo:up].copy_(src[lo:up], non_blocking=True)
+                    rc = lib.rcbf_unicycle_safe_step(
+                        _lib.ptr(env._state4[lo:up]), _lib.ptr(env._step[lo:up]), _lib.ptr(d_in[0][lo:up]),
+                        _lib.ptr(d_in[1][lo:up]), _lib.ptr(d_in[2][lo:up]), up - lo, p_layer, p_env,
+                        _lib.ptr(env._safe_action[lo:up]), _lib.ptr(env._obs[lo:up]), _lib.ptr(env._reward[lo:up]),
+                        _lib.ptr(env._done[lo:up]), _lib.ptr(env._cost[lo:up]), _lib.ptr(env._goal[lo:up]), None,
+                        _lib.ptr(env._counters), s.cuda_stream)
+                    assert rc == 0
+                    h_out["u"][lo:up].copy_(env._safe_action[lo:up], non_blocking=True)
+                    h_out["obs"][lo:up].copy_(env._obs[lo:up], non_blocking=True)
+                    h_out["rew"][lo:up].copy_(env._reward[lo:up], non_blocking=True)
+                    h_out["cost"][lo:up].copy_(env._cost[lo:up], non_blocking=True)
+                    h_out["done"][lo:up].copy_(env._done[lo:up], non_blocking=True)
+            for s in streams:
+                s.synchronize()
+
+        k_e2e = max(3, min(args.steps, 10))
+        for k in range(3):
+            e2e_step(k)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(k_e2e):
+            e2e_step(k)
+        torch.cuda.synchronize(device)
+        el = time.perf_counter() - t0
+        te = torch.tensor([el], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        el = float(te.item())
+        h2d = n * (8 + 12 + 12)
+        d2h = n * (8 + 28 + 4 + 4 + 1)
+        e2e = {"value": float(n) * world * k_e2e / el, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": k_e2e, "chunks": CH,
+               "api": "UnicycleEnv.safe_step (rcbf_unicycle_safe_step) with pinned host u_rl/mean/sigma in and "
+                      "u_safe/obs/reward/cost/done out"}
+        assert float(h_out["rew"].abs().sum()) >= 0.0   # the result is read on the host
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        hbm_peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        fp32_peak = fma_probe_tflops(lib, _lib, device)
+        gbs = UNI_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
+        flops_per_step = F_ASM_UNI + F_DYN_UNI + nontrivial * 0.5 * F_ITER_UNI + iters_mean * (F_ITER_UNI + CERT_FLOPS_UNI)
+        tfl = flops_per_step * n / (kernel_ms * 1e-3) / 1e12
+        roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                    "kernel": "k_unicycle_safe_step", "kernel_ms": kernel_ms, "bytes_per_unit": UNI_BYTES_PER_STEP,
+                    "fp32": {"achieved_tflops": tfl, "peak_tflops": fp32_peak, "frac": tfl / fp32_peak,
+                             "peak_source": "rcbf_fp32_fma_probe measured in this run",
+                             "flops_per_unit": flops_per_step, "ipm_iters_mean": iters_mean,
+                             "nontrivial_frac": nontrivial},
+                    "note": "path is FP32-pipe bound (SURVEY 8d): the hbm fraction is reported per contract, the fp32 "
+                            "fraction is the binding one"}
+        v, done_n, el = time_cpu_reference(args.cpu_seconds)
+        cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "%d Unicycle instances in batches of 512 over %.1f s (oracle: reference-order f32 "
+                                  "assembly + restated qpth f64 + numpy f64 env step)" % (done_n, el)}
+        extra["solver"] = {"nan": c[0], "uncertified": c[1], "f64_passes": c[2], "trivial": c[3],
+                           "ipm_iters_mean": iters_mean}
+        out = {
+            "metric": "safe env-steps/sec (dynamics+RCBF-QP)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (f64 KKT certificate)",
+            "data": "synthetic",
+            "config": {"workload": "config4-unicycle-gp-robust-safe-step", "instances_per_gpu": n,
+                       "l2": "inputs larger than L2 (%.0f MB read per step per GPU, 2 rotating input sets)"
+                             % (52 * n / 1e6), "gamma_b": 20, "parallelism": "instances sharded by rank, no collective"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": args.steps, "extra": extra,
+        }
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

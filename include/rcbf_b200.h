@@ -1,0 +1,180 @@
+/* rcbf_b200.h -- C ABI of librcbf_b200.so: the sm_100a implementation of SAC-RCBF's per-step safety hot path.
+ *
+ * Drop-in boundary.  The reference (yemam3/SAC-RCBF) is pure Python; the functions below are what a ctypes / torch
+ * binding replaces in it (see INTEGRATION.md for the stubs):
+ *
+ *   rcbf_*_assemble          CBFQPLayer.get_cbf_qp_constraints          rcbf_sac/diff_cbf_qp.py:146-379
+ *   rcbf_qp_solve            CBFQPLayer.cbf_layer / solve_qp (qpth)     rcbf_sac/diff_cbf_qp.py:81-144
+ *   rcbf_*_safe_action       CBFQPLayer.get_safe_action (forward)       rcbf_sac/diff_cbf_qp.py:44-79
+ *   rcbf_*_safe_action_bwd   autograd of the above (qpth backward)      rcbf_sac/diff_cbf_qp.py:139 + :103-106,:77
+ *   rcbf_*_env_step_*        UnicycleEnv.step / SimulatedCarsEnv.step   envs/unicycle_env.py:46-111 ; envs/simulated_cars_env.py:38-87
+ *   rcbf_*_env_reset_*       .reset()                                   envs/unicycle_env.py:125-143 ; envs/simulated_cars_env.py:108-125
+ *   rcbf_*_predict_next_*    DynamicsModel.predict_next_state (prior)   rcbf_sac/dynamics.py:60-105
+ *   rcbf_*_safe_step         get_safe_action + env.step fused           rcbf_sac/sac_cbf.py:218-238 + main.py:93-95
+ *   (CascadeCBFLayer.get_u_safe, rcbf_sac/cbf_qp.py:29-53, is rcbf_unicycle_safe_action with sigma_scale = k_d,
+ *    abs_sigma_map = 0, p_diag = (10, 1e-4, 1e7) and the unclamped correction read from `x`.)
+ *
+ * Conventions: every pointer is a DEVICE pointer unless its name ends in _host; arrays are row-major (n, feat) like
+ * the reference's tensors; `n` instances; `stream` is a cudaStream_t passed as void*; nullable outputs are marked.
+ * Every call is asynchronous on `stream`, allocates nothing and returns 0 or the cudaError_t of the launch.
+ */
+#ifndef RCBF_B200_H
+#define RCBF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RCBF_UNI_HAZ 5 /* envs/unicycle_env.py:26 */
+#define RCBF_UNI_M 9   /* 5 CBF rows + 4 actuator rows, diff_cbf_qp.py:42 */
+#define RCBF_UNI_NZ 3  /* (u_v, u_w, eps) */
+#define RCBF_CARS_M 4
+#define RCBF_CARS_NZ 2
+
+/* per-instance status written by the solvers */
+#define RCBF_OK_TRIVIAL 0   /* x = 0 feasible */
+#define RCBF_OK_CERTIFIED 1 /* exact KKT certificate */
+#define RCBF_OK_IPM 2       /* interior-point residual < tol (float64 pass) */
+#define RCBF_MAXITER 3      /* iteration limit: best iterate returned (what qpth does) */
+#define RCBF_NAN 4          /* -> Python raises Exception('QP Failed to solve'), diff_cbf_qp.py:141-143 */
+
+typedef struct {
+  float hazards[RCBF_UNI_HAZ][2];
+  float collision_radius_sq; /* float((1.2*hazards_radius)^2) diff_cbf_qp.py:207,246 */
+  float gamma_b;
+  float l_p;
+  float sigma_scale;  /* 1 (CBFQPLayer: k_d is dead, :261) or k_d (CascadeCBFLayer, cbf_qp.py:141) */
+  int abs_sigma_map;  /* 1: |g_p| (diff_cbf_qp.py:241); 0: signed (cbf_qp.py:119) */
+  float u_min[2], u_max[2];
+  float p_diag[3];
+} rcbf_unicycle_params;
+
+typedef struct {
+  float gamma_2, gamma_sq; /* float(gamma_b+gamma_b), float(gamma_b*gamma_b) diff_cbf_qp.py:348 */
+  float kp, k_brake;
+  float collision_radius_sq;
+  float sigma_scale;
+  float u_min, u_max;
+  float p_diag[2];
+  float slack_coeff;
+} rcbf_cars_params;
+
+typedef struct {
+  double hazards[RCBF_UNI_HAZ][2];
+  double hazards_radius;
+  double dt, goal_x, goal_y, goal_size, reward_goal;
+  double init_x, init_y, init_theta;
+  int max_episode_steps;
+  int auto_reset;
+} rcbf_unicycle_env_params;
+
+typedef struct {
+  double dt, kp, k_brake;
+  int max_episode_steps;
+  int auto_reset;
+} rcbf_cars_env_params;
+
+/* counters[0]=#NaN  [1]=#uncertified(max-iter)  [2]=#float64 straggler passes  [3]=#trivial  [4]=sum of IPM iterations
+ * [5..7] reserved.  Accumulated with atomics; zero them before the call.  Nullable. */
+typedef unsigned long long rcbf_counters_t;
+
+/* ---- constraint assembly (raw P,q are constants: P = diag(p_diag), q = 0) ------------------------------------- */
+int rcbf_unicycle_assemble(const float* state, const float* action, const float* mean, const float* sigma, int64_t n,
+                           const rcbf_unicycle_params* p_host, float* G /* n*9*3 */, float* h /* n*9 */, void* stream);
+int rcbf_cars_assemble(const float* state, const float* action, const float* sigma, int64_t n,
+                       const rcbf_cars_params* p_host, float* G /* n*4*2 */, float* h /* n*4 */, void* stream);
+
+/* ---- get_safe_action forward.  x/lam/slack (float32, saved for the backward), status, iters: nullable ---------- */
+int rcbf_unicycle_safe_action(const float* state, const float* action, const float* mean, const float* sigma,
+                              int64_t n, const rcbf_unicycle_params* p_host, float* safe_action /* n*2 */,
+                              float* x /* n*3 */, float* lam /* n*9 */, float* slack /* n*9 */, int32_t* status,
+                              int32_t* iters, rcbf_counters_t* counters, void* stream);
+int rcbf_cars_safe_action(const float* state, const float* action, const float* sigma, int64_t n,
+                          const rcbf_cars_params* p_host, float* safe_action /* n*1 */, float* x /* n*2 */,
+                          float* lam /* n*4 */, float* slack /* n*4 */, int32_t* status, int32_t* iters,
+                          rcbf_counters_t* counters, void* stream);
+
+/* ---- get_safe_action backward: d loss / d action given d loss / d safe_action -------------------------------- */
+int rcbf_unicycle_safe_action_bwd(const float* state, const float* action, const float* mean, const float* sigma,
+                                  const float* x, const float* lam, const float* slack, const float* grad_out,
+                                  int64_t n, const rcbf_unicycle_params* p_host, float* grad_action, void* stream);
+int rcbf_cars_safe_action_bwd(const float* state, const float* action, const float* sigma, const float* x,
+                              const float* lam, const float* slack, const float* grad_out, int64_t n,
+                              const rcbf_cars_params* p_host, float* grad_action, void* stream);
+
+/* ---- generic small QP  min 1/2 x'Qx + p'x  s.t. Gx <= h  (cbf_layer / solve_qp), float64 tensors like qpth sees ---
+ * (nz, m) in {(3,9), (2,4)}.  normalise != 0 applies the [G|h] row normalisation of solve_qp first. */
+int rcbf_qp_solve(const double* Q /* n*nz*nz */, const double* p /* n*nz */, const double* G /* n*m*nz */,
+                  const double* h /* n*m */, int64_t n, int nz, int m, double* x /* n*nz */, double* lam /* n*m */,
+                  double* slack /* n*m */, int32_t* status, int32_t* iters, rcbf_counters_t* counters, void* stream);
+int rcbf_qp_solve_bwd(const double* Q, const double* G, const double* x, const double* lam, const double* slack,
+                      const double* grad_x, int64_t n, int nz, int m, double* dQ, double* dp, double* dG, double* dh,
+                      void* stream);
+
+/* ---- environments.  *_f32: throughput layout; *_f64: bit-faithful to the numpy reference ----------------------
+ * Unicycle state: 4 values per instance (x, y, theta, last_goal_dist) -> one 16-byte load in the f32 layout.
+ * Cars state: 10 values per instance + t + episode_step. */
+int rcbf_unicycle_env_reset_f32(float* state4, int32_t* step, const uint8_t* mask /* nullable: all */, int64_t n,
+                                const rcbf_unicycle_env_params* e_host, float* obs /* n*7 nullable */, void* stream);
+int rcbf_unicycle_env_reset_f64(double* state4, int32_t* step, const uint8_t* mask, int64_t n,
+                                const rcbf_unicycle_env_params* e_host, double* obs, void* stream);
+int rcbf_unicycle_env_step_f32(float* state4, int32_t* step, const float* action, int64_t n,
+                               const rcbf_unicycle_env_params* e_host, float* obs /* n*7 */, float* reward,
+                               uint8_t* done, float* cost, uint8_t* goal_met, void* stream);
+int rcbf_unicycle_env_step_f64(double* state4, int32_t* step, const double* action, int64_t n,
+                               const rcbf_unicycle_env_params* e_host, double* obs, double* reward, uint8_t* done,
+                               double* cost, uint8_t* goal_met, void* stream);
+int rcbf_cars_env_reset_f32(float* state, float* t, int32_t* step, const float* v_noise, const uint8_t* mask,
+                            int64_t n, float* obs /* nullable */, void* stream);
+int rcbf_cars_env_reset_f64(double* state, double* t, int32_t* step, const double* v_noise, const uint8_t* mask,
+                            int64_t n, double* obs, void* stream);
+int rcbf_cars_env_step_f32(float* state, float* t, int32_t* step, const float* action, int64_t n,
+                           const rcbf_cars_env_params* e_host, float* obs /* n*10 */, float* reward, uint8_t* done,
+                           float* cost, void* stream);
+int rcbf_cars_env_step_f64(double* state, double* t, int32_t* step, const double* action, int64_t n,
+                           const rcbf_cars_env_params* e_host, double* obs, double* reward, uint8_t* done,
+                           double* cost, void* stream);
+
+/* ---- prior model (DynamicsModel.predict_next_state): next = s + dt (f + g u) + dt*mean ; mean nullable (= 0) ---- */
+int rcbf_unicycle_predict_next_f32(const float* state, const float* action, const float* mean, int64_t n, double dt,
+                                   float* next, void* stream);
+int rcbf_unicycle_predict_next_f64(const double* state, const double* action, const double* mean, int64_t n,
+                                   double dt, double* next, void* stream);
+int rcbf_cars_predict_next_f32(const float* state, const float* action, const float* t, const float* mean, int64_t n,
+                               double dt, double kp, double k_brake, float* next, void* stream);
+int rcbf_cars_predict_next_f64(const double* state, const double* action, const double* t, const double* mean,
+                               int64_t n, double dt, double kp, double k_brake, double* next, void* stream);
+
+/* ---- fused safe step: assemble + QP + clamp + env.step in ONE launch (float32 env layout) --------------------- */
+int rcbf_unicycle_safe_step(float* state4, int32_t* step, const float* action_rl, const float* mean,
+                            const float* sigma, int64_t n, const rcbf_unicycle_params* p_host,
+                            const rcbf_unicycle_env_params* e_host, float* safe_action /* n*2 */, float* obs /* n*7 */,
+                            float* reward, uint8_t* done, float* cost, uint8_t* goal_met, int32_t* status /* nullable */,
+                            rcbf_counters_t* counters, void* stream);
+int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* action_rl, const float* sigma, int64_t n,
+                        const rcbf_cars_params* p_host, const rcbf_cars_env_params* e_host, float* safe_action,
+                        float* obs /* n*10 */, float* reward, uint8_t* done, float* cost, int32_t* status,
+                        rcbf_counters_t* counters, void* stream);
+
+/* ---- host-buffer entry points (the e2e path): pinned or pageable HOST arrays in, HOST arrays out; the library
+ * stages through its own device scratch and pipelines H2D / compute / D2H over `chunks` slices on internal streams.
+ * Synchronous (returns when the outputs are valid). */
+int rcbf_unicycle_safe_action_host(const float* state_host, const float* action_host, const float* mean_host,
+                                   const float* sigma_host, int64_t n, const rcbf_unicycle_params* p_host,
+                                   float* safe_action_host, int32_t* n_failed_host, int device, int chunks);
+int rcbf_cars_safe_action_host(const float* state_host, const float* action_host, const float* sigma_host, int64_t n,
+                               const rcbf_cars_params* p_host, float* safe_action_host, int32_t* n_failed_host,
+                               int device, int chunks);
+
+/* ---- measurement helpers --------------------------------------------------------------------------------------
+ * FP32 FMA throughput probe: `iters` dependent-chain FMAs x 8 chains per thread; returns nothing, time it outside.
+ * flops per launch = 2 * 8 * iters * blocks * threads. */
+int rcbf_fp32_fma_probe(float* sink, int blocks, int threads, int iters, void* stream);
+const char* rcbf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RCBF_B200_H */

@@ -83,9 +83,10 @@ def assemble_unicycle(state, action, mean, sigma, gamma_b=20.0, l_p=0.03, hazard
     G[:, :K, 0] = -Lg0
     G[:, :K, 1] = -Lg1
     G[:, :K, 2] = -1.0                                                      # :260
-    h[:, :K] = (gamma_b * hcbf ** 3 + (dx * mpx[:, None] + dy * mpy[:, None])
-                - (dx.abs() * spx[:, None] + dy.abs() * spy[:, None])
-                + (Lg0 * action[:, 0:1] + Lg1 * action[:, 1:2]))            # :261 (k_d NOT applied)
+    # association as in :261 :  gamma*h^3 + ((dhdp.mu_p - |dhdp|.sigma_p) + Lg.u)      (k_d NOT applied)
+    h[:, :K] = gamma_b * (hcbf * hcbf * hcbf) + (((dx * mpx[:, None] + dy * mpy[:, None])
+                                                  - (dx.abs() * spx[:, None] + dy.abs() * spy[:, None]))
+                                                 + (Lg0 * action[:, 0:1] + Lg1 * action[:, 1:2]))
     r = K
     for cidx in range(2):                                                   # :365-377
         G[:, r, cidx] = 1.0
@@ -141,8 +142,8 @@ def assemble_cars(state, action, mean, sigma, gamma_b=20.0, kp=4.0, k_brake=20.0
     # f = (v0,a0,...,v4,a4): idx4=v2, idx5=a2, idx6=v3, idx7=a3, idx8=v4, idx9=a4
     Lff13 = a4 * vel[:, 2] + a5 * acc[:, 2] + a6 * vel[:, 3] + a7 * acc[:, 3]        # :319
     LfD13 = a5.abs() * sg[:, 2] + a7.abs() * sg[:, 3]                                  # :320
-    Lff15 = b8 * vel[:, 4] + b9 * acc[:, 4] + b6 * vel[:, 3] + b7 * acc[:, 3]        # :327
-    LfD15 = b9.abs() * sg[:, 4] + b7.abs() * sg[:, 3]                                  # :328
+    Lff15 = b6 * vel[:, 3] + b7 * acc[:, 3] + b8 * vel[:, 4] + b9 * acc[:, 4]        # :327 (state-index order)
+    LfD15 = b7.abs() * sg[:, 3] + b9.abs() * sg[:, 4]                                  # :328
     Lg13 = 50.0 * a7                                                                   # :331 (g = 50 e_7, :303)
     Lg15 = 50.0 * b7                                                                   # :332
     u = action[:, 0]

@@ -1,0 +1,123 @@
+"""ctypes mirrors of the plain-C parameter structs in include/rcbf_b200.h (== csrc/rcbf_core.cuh)."""
+import ctypes as C
+
+import numpy as np
+
+UNI_HAZ = 5
+
+
+class UnicycleParams(C.Structure):
+    _fields_ = [
+        ("hazards", (C.c_float * 2) * UNI_HAZ),
+        ("collision_radius_sq", C.c_float),
+        ("gamma_b", C.c_float),
+        ("l_p", C.c_float),
+        ("sigma_scale", C.c_float),
+        ("abs_sigma_map", C.c_int),
+        ("u_min", C.c_float * 2),
+        ("u_max", C.c_float * 2),
+        ("p_diag", C.c_float * 3),
+    ]
+
+
+class CarsParams(C.Structure):
+    _fields_ = [
+        ("gamma_2", C.c_float),
+        ("gamma_sq", C.c_float),
+        ("kp", C.c_float),
+        ("k_brake", C.c_float),
+        ("collision_radius_sq", C.c_float),
+        ("sigma_scale", C.c_float),
+        ("u_min", C.c_float),
+        ("u_max", C.c_float),
+        ("p_diag", C.c_float * 2),
+        ("slack_coeff", C.c_float),
+    ]
+
+
+class UnicycleEnvParams(C.Structure):
+    _fields_ = [
+        ("hazards", (C.c_double * 2) * UNI_HAZ),
+        ("hazards_radius", C.c_double),
+        ("dt", C.c_double),
+        ("goal_x", C.c_double),
+        ("goal_y", C.c_double),
+        ("goal_size", C.c_double),
+        ("reward_goal", C.c_double),
+        ("init_x", C.c_double),
+        ("init_y", C.c_double),
+        ("init_theta", C.c_double),
+        ("max_episode_steps", C.c_int),
+        ("auto_reset", C.c_int),
+    ]
+
+
+class CarsEnvParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_double),
+        ("kp", C.c_double),
+        ("k_brake", C.c_double),
+        ("max_episode_steps", C.c_int),
+        ("auto_reset", C.c_int),
+    ]
+
+
+DEFAULT_HAZARDS = np.array([[0., 0.], [-1., 1.], [-1., -1.], [1., -1.], [1., 1.]]) * 1.5  # envs/unicycle_env.py:26
+
+
+def _check_hazards(hazards_locations):
+    hz = np.asarray(DEFAULT_HAZARDS if hazards_locations is None else hazards_locations, np.float64)
+    if hz.shape != (UNI_HAZ, 2):
+        raise ValueError("the sm_100a kernels are specialised for %d hazards (reference: unicycle_env.py:26), got %r"
+                         % (UNI_HAZ, hz.shape))
+    return hz
+
+
+def unicycle_params(hazards_locations=None, hazards_radius=0.6, gamma_b=100.0, l_p=0.03, u_min=(-2.5, -2.5),
+                    u_max=(2.5, 2.5), p_diag=(1.0, 1e-2, 1e5), sigma_scale=1.0, abs_sigma_map=True):
+    """Defaults = envs/unicycle_env.py:21-26 and rcbf_sac/diff_cbf_qp.py:12,207,265."""
+    hz = _check_hazards(hazards_locations)
+    p = UnicycleParams()
+    for i in range(UNI_HAZ):
+        p.hazards[i][0], p.hazards[i][1] = float(hz[i, 0]), float(hz[i, 1])
+    p.collision_radius_sq = (1.2 * hazards_radius) ** 2  # squared in double, rounded once (diff_cbf_qp.py:207,246)
+    p.gamma_b, p.l_p, p.sigma_scale, p.abs_sigma_map = gamma_b, l_p, sigma_scale, int(abs_sigma_map)
+    for c in range(2):
+        p.u_min[c], p.u_max[c] = float(u_min[c]), float(u_max[c])
+    for j in range(3):
+        p.p_diag[j] = float(p_diag[j])
+    return p
+
+
+def cars_params(gamma_b=100.0, kp=4.0, k_brake=20.0, u_min=-10.0, u_max=10.0, p_diag=(0.1, 10.0), sigma_scale=1.0,
+                slack_coeff=200.0):
+    """Defaults = envs/simulated_cars_env.py:18-26 and rcbf_sac/diff_cbf_qp.py:272,352,356."""
+    p = CarsParams()
+    p.gamma_2, p.gamma_sq = gamma_b + gamma_b, gamma_b * gamma_b  # python-double scalars of diff_cbf_qp.py:348
+    p.kp, p.k_brake, p.collision_radius_sq, p.sigma_scale = kp, k_brake, 3.5 ** 2, sigma_scale
+    p.u_min, p.u_max = float(u_min), float(u_max)
+    p.p_diag[0], p.p_diag[1] = float(p_diag[0]), float(p_diag[1])
+    p.slack_coeff = slack_coeff
+    return p
+
+
+def unicycle_env_params(hazards_locations=None, hazards_radius=0.6, dt=0.02, goal_pos=(2.5, 2.5), goal_size=0.3,
+                        reward_goal=1.0, init_state=(-2.5, -2.5, 0.0), max_episode_steps=1000, auto_reset=False):
+    """Defaults = envs/unicycle_env.py:24-33,137."""
+    hz = _check_hazards(hazards_locations)
+    e = UnicycleEnvParams()
+    for i in range(UNI_HAZ):
+        e.hazards[i][0], e.hazards[i][1] = float(hz[i, 0]), float(hz[i, 1])
+    e.hazards_radius, e.dt, e.goal_x, e.goal_y = hazards_radius, dt, float(goal_pos[0]), float(goal_pos[1])
+    e.goal_size, e.reward_goal = goal_size, reward_goal
+    e.init_x, e.init_y, e.init_theta = (float(v) for v in init_state)
+    e.max_episode_steps, e.auto_reset = int(max_episode_steps), int(auto_reset)
+    return e
+
+
+def cars_env_params(dt=0.02, kp=4.0, k_brake=20.0, max_episode_steps=300, auto_reset=False):
+    """Defaults = envs/simulated_cars_env.py:21-26."""
+    e = CarsEnvParams()
+    e.dt, e.kp, e.k_brake = dt, kp, k_brake
+    e.max_episode_steps, e.auto_reset = int(max_episode_steps), int(auto_reset)
+    return e

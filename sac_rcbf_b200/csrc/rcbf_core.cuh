@@ -1,0 +1,747 @@
+// rcbf_core.cuh -- per-instance arithmetic of the SAC-RCBF safety hot path.
+//
+// Everything here is a small, fully unrolled, register-resident function of ONE
+// environment instance / ONE QP.  The __global__ kernels in rcbf_kernels.cu map one
+// CUDA thread to one instance and call these.  The functions are also compilable
+// for the host (RCBF_HD expands to nothing under g++) so the numerics of the exact
+// same source can be exercised on a CPU-only box by tests/hostsim -- that build is
+// test infrastructure and is never loaded by the product package.
+//
+// Reference being re-implemented (yemam3/SAC-RCBF):
+//   constraint assembly   rcbf_sac/diff_cbf_qp.py:202-266 (Unicycle), :268-357 (SimulatedCars), :362-377 (box rows)
+//   row normalisation     rcbf_sac/diff_cbf_qp.py:103-106
+//   QP                    qpth PDIPM via rcbf_sac/diff_cbf_qp.py:107,139   (see DESIGN.md for the solver design)
+//   clamp                 rcbf_sac/diff_cbf_qp.py:77
+//   env steps             envs/unicycle_env.py:46-111,215-280 ; envs/simulated_cars_env.py:38-158
+//   prior dynamics        rcbf_sac/dynamics.py:60-105,125-188
+#pragma once
+
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/rcbf_b200.h"
+
+#if defined(__CUDACC__)
+#define RCBF_HD __host__ __device__ __forceinline__
+#define RCBF_UNROLL _Pragma("unroll")
+#else
+#define RCBF_HD inline __attribute__((always_inline))
+#define RCBF_UNROLL _Pragma("GCC unroll 16")
+#endif
+
+namespace rcbf {
+
+// ------------------------------------------------------------------------------------------------
+// scalar helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T> RCBF_HD T t_abs(T x) { return x < T(0) ? -x : x; }
+template <typename T> RCBF_HD T t_max(T a, T b) { return a > b ? a : b; }
+template <typename T> RCBF_HD T t_min(T a, T b) { return a < b ? a : b; }
+RCBF_HD float t_fma(float a, float b, float c) { return fmaf(a, b, c); }
+RCBF_HD double t_fma(double a, double b, double c) { return fma(a, b, c); }
+RCBF_HD float t_sqrt(float a) { return sqrtf(a); }
+RCBF_HD double t_sqrt(double a) { return sqrt(a); }
+
+// single-rounding float ops that the compiler may not contract into FMAs (reference-order assembly)
+RCBF_HD float mul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fmul_rn(a, b);
+#else
+  return a * b;  // host build uses -ffp-contract=off
+#endif
+}
+RCBF_HD float add_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fadd_rn(a, b);
+#else
+  return a + b;
+#endif
+}
+RCBF_HD float sub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __fsub_rn(a, b);
+#else
+  return a - b;
+#endif
+}
+
+// fast reciprocal used INSIDE the interior-point iteration only (search directions tolerate 1-2 ulp);
+// the certificate / outputs use IEEE division.
+RCBF_HD float t_rcp_fast(float a) {
+#if defined(__CUDA_ARCH__)
+  return __frcp_rn(a);
+#else
+  return 1.0f / a;
+#endif
+}
+RCBF_HD double t_rcp_fast(double a) { return 1.0 / a; }
+
+// per-instance status codes: RCBF_OK_TRIVIAL ... RCBF_NAN, see include/rcbf_b200.h
+
+// ------------------------------------------------------------------------------------------------
+// Least-norm point in a polytope:   minimise 1/2 |y|^2   s.t.  A y <= b        (NZ vars, M rows)
+//
+// Every QP of the path  (min 1/2 x'Px s.t. G~x <= h~, P diagonal, q = 0)  is brought to this form with
+// y = sqrt(P) x, A = G~ P^-1/2 (column equilibration).  A general SPD Q / non-zero p go through the Cholesky
+// factor of Q (rcbf_generic.cuh).  Duals and slacks are invariant under the change of variables.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int NZ, int M>
+struct LnpProblem {
+  T A[M][NZ];
+  T b[M];
+};
+
+template <typename T, int NZ, int M>
+struct LnpSolution {
+  T y[NZ];
+  T lam[M];
+  T s[M];
+  int status;
+  int iters;
+};
+
+// --- tiny SPD solves (closed-form Cholesky), NZ in {1,2,3} -------------------------------------------
+template <typename T>
+struct Sym3 {  // symmetric 3x3, lower part
+  T a00, a10, a11, a20, a21, a22;
+};
+
+template <typename T, int NZ>
+struct Chol {
+  // L (lower) with the diagonal stored as reciprocals
+  T i00, l10, i11, l20, l21, i22;
+  RCBF_HD void factor(const T S[NZ][NZ]) {
+    T l00 = t_sqrt(S[0][0]);
+    i00 = T(1) / l00;
+    if (NZ > 1) {
+      l10 = S[1][0] * i00;
+      T l11 = t_sqrt(S[1][1] - l10 * l10);
+      i11 = T(1) / l11;
+    }
+    if (NZ > 2) {
+      l20 = S[2][0] * i00;
+      l21 = (S[2][1] - l20 * l10) * i11;
+      T l22 = t_sqrt(S[2][2] - l20 * l20 - l21 * l21);
+      i22 = T(1) / l22;
+    }
+  }
+  RCBF_HD void fwd(const T r[NZ], T w[NZ]) const {  // L w = r
+    w[0] = r[0] * i00;
+    if (NZ > 1) w[1] = (r[1] - l10 * w[0]) * i11;
+    if (NZ > 2) w[2] = (r[2] - l20 * w[0] - l21 * w[1]) * i22;
+  }
+  RCBF_HD void bwd(const T w[NZ], T x[NZ]) const {  // L' x = w
+    if (NZ > 2) {
+      x[2] = w[2] * i22;
+      x[1] = (w[1] - l21 * x[2]) * i11;
+      x[0] = (w[0] - l10 * x[1] - l20 * x[2]) * i00;
+    } else if (NZ > 1) {
+      x[1] = w[1] * i11;
+      x[0] = (w[0] - l10 * x[1]) * i00;
+    } else {
+      x[0] = w[0] * i00;
+    }
+  }
+  RCBF_HD void solve(const T r[NZ], T x[NZ]) const {
+    T w[NZ];
+    fwd(r, w);
+    bwd(w, x);
+  }
+};
+
+// --- KKT certificate ----------------------------------------------------------------------------------
+// Given a guessed active set (bit mask, at most NZ rows), solve the equality-constrained problem
+//     (A_S A_S') lam_S = -b_S,   y = -A_S' lam_S
+// in precision C and accept iff  lam_S >= -tol_l,  b - A y >= -tol_s on every row and |b_S - A_S y| <= tol_s.
+// For a strictly convex QP a point passing this test IS the optimum (to tol), independent of how the guess
+// was obtained -- this is what lets the float32 interior-point iteration stop as soon as the active set is
+// identified instead of having to converge numerically.
+// CP supplies the problem data in precision C through a(i,j) / b(i) (compile-time indices after unrolling), so that
+// the certificate sees the *unrounded* scaled data even when the iteration runs on a float32 copy.
+template <typename C, typename CP, int NZ, int M>
+RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], C lam[M], C s[M]) {
+  // gather up to NZ active rows (unused slots: zero row, b = 0  ->  lam = 0 through the unit diagonal below)
+  C R[NZ][NZ];
+  C rb[NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) R[k][j] = C(0);
+    rb[k] = C(0);
+  }
+  int cnt = 0;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    const bool act = (mask >> i) & 1u;
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) {
+      const bool put = act && (cnt == k);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) R[k][j] = put ? P.a(i, j) : R[k][j];
+      rb[k] = put ? P.b(i) : rb[k];
+    }
+    cnt += act ? 1 : 0;
+  }
+  if (cnt > NZ) return false;
+  // Gram matrix (unit diagonal on unused slots)
+  C Gm[NZ][NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int l = 0; l <= k; ++l) {
+      C acc = C(0);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = t_fma(R[k][j], R[l][j], acc);
+      Gm[k][l] = acc;
+    }
+    Gm[k][k] = (k < cnt) ? Gm[k][k] : C(1);
+  }
+  Chol<C, NZ> ch;
+  ch.factor(Gm);
+  C nrb[NZ], lk[NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) nrb[k] = -rb[k];
+  ch.solve(nrb, lk);
+  bool ok = true;
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -tol_l);  // NaN (dependent rows) compares false
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    C acc = C(0);
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) acc = t_fma(-R[k][j], lk[k], acc);
+    y[j] = acc;
+  }
+  int c2 = 0;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    C acc = P.b(i);
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) acc = t_fma(-P.a(i, j), y[j], acc);
+    const bool act = (mask >> i) & 1u;
+    C li = C(0);
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) li = (act && c2 == k) ? lk[k] : li;
+    c2 += act ? 1 : 0;
+    lam[i] = li;
+    s[i] = acc;
+    ok = ok && (acc >= -tol_s) && (!act || acc <= tol_s);
+  }
+  return ok;
+}
+
+template <typename T> struct LnpTol;
+template <> struct LnpTol<float> {
+  static constexpr int kMaxIter = 16;
+  static constexpr int kFirstCert = 1;   // first iteration at which the certificate may be tried (if the mask repeats)
+  static constexpr int kAlwaysCert = 2;  // from here on it is tried every iteration
+  static constexpr float kResidTol = 0.0f;  // float32 never accepts on the IPM residual: certificate or straggler
+};
+template <> struct LnpTol<double> {
+  static constexpr int kMaxIter = 60;
+  static constexpr int kFirstCert = 1;
+  static constexpr int kAlwaysCert = 2;
+  static constexpr double kResidTol = 1e-11;
+};
+
+// --- primal-dual interior point (Mehrotra predictor-corrector) with certified early exit -------------------
+// T : precision of the iteration (float on the main path, double in the straggler pass)
+// C : precision of the certificate (double: ~100 DFMA, B200 runs FP64 at 1:2)
+template <typename T, typename C, typename CP, int NZ, int M>
+RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<C, NZ, M>& out, C tol_s, C tol_l) {
+  // 0. trivial certificate: y = 0 is feasible  <=>  b >= 0 on every row
+  {
+    bool triv = true;
+    bool nan = false;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      triv = triv && (P.b[i] >= T(0));
+      nan = nan || (P.b[i] != P.b[i]);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) nan = nan || (P.A[i][j] != P.A[i][j]);
+    }
+    if (triv || nan) {
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) out.y[j] = nan ? C(NAN) : C(0);
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i) {
+        out.lam[i] = C(0);
+        out.s[i] = C(P.b[i]);
+      }
+      out.status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
+      out.iters = 0;
+      return;
+    }
+  }
+
+  T y[NZ], s[M], z[M];
+  // 1. initial point (qpth): (I + A'A) y = A'b ; s = b - A y ; z = -s ; shift both to >= 1 if needed
+  {
+    T S[NZ][NZ], r[NZ];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      RCBF_UNROLL
+      for (int k = 0; k <= j; ++k) {
+        T acc = (j == k) ? T(1) : T(0);
+        RCBF_UNROLL
+        for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], P.A[i][k], acc);
+        S[j][k] = acc;
+      }
+      T acc = T(0);
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], P.b[i], acc);
+      r[j] = acc;
+    }
+    Chol<T, NZ> ch;
+    ch.factor(S);
+    ch.solve(r, y);
+    T smin = T(1e30), zmin = T(1e30);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      T acc = P.b[i];
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = t_fma(-P.A[i][j], y[j], acc);
+      s[i] = acc;
+      z[i] = -acc;
+      smin = t_min(smin, s[i]);
+      zmin = t_min(zmin, z[i]);
+    }
+    const T sshift = smin < T(0) ? (T(1) - smin) : T(0);
+    const T zshift = zmin < T(0) ? (T(1) - zmin) : T(0);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      s[i] += sshift;
+      z[i] += zshift;
+    }
+  }
+
+  T best_res = T(1e30);
+  T by[NZ], bs[M], bz[M];
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) by[j] = y[j];
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    bs[i] = s[i];
+    bz[i] = z[i];
+  }
+  uint32_t last_mask = 0xffffffffu;
+  int status = RCBF_MAXITER;
+  int it = 0;
+  for (; it < LnpTol<T>::kMaxIter; ++it) {
+    // residuals
+    T rx[NZ], rz[M];
+    T mu = T(0), nrx = T(0), nrz = T(0);
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      T acc = y[j];
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], z[i], acc);
+      rx[j] = acc;
+      nrx = t_fma(acc, acc, nrx);
+    }
+    uint32_t mask = 0;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      T acc = s[i] - P.b[i];
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = t_fma(P.A[i][j], y[j], acc);
+      rz[i] = acc;
+      nrz = t_fma(acc, acc, nrz);
+      mu = t_fma(s[i], z[i], mu);
+      mask |= (z[i] > s[i]) ? (1u << i) : 0u;
+    }
+    const T res = t_sqrt(nrx) + t_sqrt(nrz) + mu;  // qpth's resid: |rx| + |rz| + m*mu
+    if (!(res == res)) break;  // overflow / breakdown: keep the best iterate so far
+    if (res < best_res) {
+      best_res = res;
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) by[j] = y[j];
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i) {
+        bs[i] = s[i];
+        bz[i] = z[i];
+      }
+    }
+    // certified early exit: try the predicted active set whenever it is a candidate
+    if (it >= LnpTol<T>::kFirstCert && (mask == last_mask || it >= LnpTol<T>::kAlwaysCert)) {
+      if (lnp_certify<C, CP, NZ, M>(cp, mask, tol_s, tol_l, out.y, out.lam, out.s)) {
+        out.status = RCBF_OK_CERTIFIED;
+        out.iters = it;
+        return;
+      }
+    }
+    last_mask = mask;
+    if (res < LnpTol<T>::kResidTol) {
+      status = RCBF_OK_IPM;
+      break;
+    }
+    mu *= T(1.0 / M);
+
+    // scaling, normal matrix S = I + A' D A
+    T w[M], d[M];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      w[i] = t_rcp_fast(s[i] * z[i]);   // 1/(s z): 1/s = w z, 1/z = w s  (one reciprocal per row)
+      d[i] = z[i] * z[i] * w[i];
+    }
+    T S[NZ][NZ];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      RCBF_UNROLL
+      for (int k = 0; k <= j; ++k) {
+        T acc = (j == k) ? T(1) : T(0);
+        RCBF_UNROLL
+        for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j] * d[i], P.A[i][k], acc);
+        S[j][k] = acc;
+      }
+    }
+    Chol<T, NZ> ch;
+    ch.factor(S);
+
+    // affine direction: S dy = -rx + A'(z - d rz)
+    T r[NZ], dy[NZ], ds[M], dz[M];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      T acc = -rx[j];
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], t_fma(-d[i], rz[i], z[i]), acc);
+      r[j] = acc;
+    }
+    ch.solve(r, dy);
+    T rho = T(0);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      T acc = -rz[i];
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = t_fma(-P.A[i][j], dy[j], acc);
+      ds[i] = acc;
+      dz[i] = t_fma(-d[i], acc, -z[i]);
+      rho = t_max(rho, -ds[i] * (w[i] * z[i]));
+      rho = t_max(rho, -dz[i] * (w[i] * s[i]));
+    }
+    T alpha = rho > T(1) ? T(1) / rho : T(1);
+    T t3 = T(0), t4 = T(0);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      t3 = t_fma(t_fma(alpha, ds[i], s[i]), t_fma(alpha, dz[i], z[i]), t3);
+      t4 = t_fma(s[i], z[i], t4);
+    }
+    T sig = t3 / t4;
+    sig = sig * sig * sig;
+    const T musig = mu * sig;
+    // corrector folded into one combined solve: rs_tot = z + (-mu sig + ds_aff dz_aff)/s
+    T rsc[M];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) rsc[i] = (t_fma(ds[i], dz[i], -musig)) * (w[i] * z[i]);
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      T acc = r[j];
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], rsc[i], acc);
+      r[j] = acc;
+    }
+    ch.solve(r, dy);
+    rho = T(0);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      T acc = -rz[i];
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = t_fma(-P.A[i][j], dy[j], acc);
+      ds[i] = acc;
+      dz[i] = t_fma(-d[i], acc, -(z[i] + rsc[i]));
+      rho = t_max(rho, -ds[i] * (w[i] * z[i]));
+      rho = t_max(rho, -dz[i] * (w[i] * s[i]));
+    }
+    alpha = rho > T(0.999) ? T(0.999) / rho : T(1);
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) y[j] = t_fma(alpha, dy[j], y[j]);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      s[i] = t_fma(alpha, ds[i], s[i]);
+      z[i] = t_fma(alpha, dz[i], z[i]);
+    }
+  }
+  // not certified: hand back the best iterate by residual (what qpth returns)
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) out.y[j] = C(by[j]);
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    out.lam[i] = C(bz[i]);
+    out.s[i] = C(bs[i]);
+  }
+  out.status = (best_res < T(1e30)) ? status : RCBF_NAN;
+  out.iters = it;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Parameters (plain C structs; mirrored by include/rcbf_b200.h)
+// ------------------------------------------------------------------------------------------------
+constexpr int kUniHaz = 5;  // envs/unicycle_env.py:26 (the layer reads len(env.hazards_locations), diff_cbf_qp.py:35)
+constexpr int kUniM = kUniHaz + 4;
+constexpr int kUniNZ = 3;
+constexpr int kCarsM = 4;
+constexpr int kCarsNZ = 2;
+
+using UnicycleParams = rcbf_unicycle_params;  // include/rcbf_b200.h
+using CarsParams = rcbf_cars_params;
+
+// ------------------------------------------------------------------------------------------------
+// Assembly: raw (G, h) exactly as get_cbf_qp_constraints returns them (before normalisation)
+// ------------------------------------------------------------------------------------------------
+struct UniRaw {
+  float G[kUniM][kUniNZ];
+  float h[kUniM];
+  float Lg[kUniHaz][2];  // d h_i / d action  (= -G[i][:2]); kept for the backward chain
+};
+
+RCBF_HD void sincos_t(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+  sincosf(x, s, c);
+#else
+  *s = sinf(x);
+  *c = cosf(x);
+#endif
+}
+
+// The assembly mirrors the reference's float32 operation ORDER (one rounding per torch op, no FMA contraction, the
+// k-ordered accumulation of torch.bmm's small-matrix path) so that the QP data agree with the reference's to the
+// last bit up to the ulp of cos/sin: near-degenerate instances amplify 1e-7 data noise into >1e-4 action noise.
+RCBF_HD void assemble_unicycle(const UnicycleParams& p, const float st[3], const float u[2], const float mu[3],
+                               const float sg[3], UniRaw& o) {
+  float s, c;
+  sincos_t(st[2], &s, &c);                                 // :211-212
+  const float lp = p.l_p;
+  const float px = add_rn(st[0], mul_rn(lp, c));           // :216
+  const float py = add_rn(st[1], mul_rn(lp, s));           // :217
+  const float g01 = -mul_rn(s, lp), g11 = mul_rn(c, lp);   // g_p = R diag(1,l_p) = [[c, g01],[s, g11]]  :225-233
+  const float mpx = add_rn(mul_rn(g01, mu[2]), mu[0]);     // :236-238
+  const float mpy = add_rn(mul_rn(g11, mu[2]), mu[1]);
+  const float a01 = p.abs_sigma_map ? fabsf(g01) : g01;
+  const float a11 = p.abs_sigma_map ? fabsf(g11) : g11;
+  const float spx = mul_rn(p.sigma_scale, add_rn(mul_rn(a01, sg[2]), sg[0]));  // :239-241 (scale = 1 in this layer)
+  const float spy = mul_rn(p.sigma_scale, add_rn(mul_rn(a11, sg[2]), sg[1]));
+  RCBF_UNROLL
+  for (int i = 0; i < kUniHaz; ++i) {
+    const float dx = sub_rn(px, p.hazards[i][0]);          // :248
+    const float dy = sub_rn(py, p.hazards[i][1]);
+    const float hc = mul_rn(0.5f, sub_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), p.collision_radius_sq));  // :246
+    const float L0 = add_rn(mul_rn(dx, c), mul_rn(dy, s));      // dhdp' g_p   :259
+    const float L1 = add_rn(mul_rn(dx, g01), mul_rn(dy, g11));
+    o.Lg[i][0] = L0;
+    o.Lg[i][1] = L1;
+    o.G[i][0] = -L0;
+    o.G[i][1] = -L1;
+    o.G[i][2] = -1.0f;                                     // :260
+    const float t1 = add_rn(mul_rn(dx, mpx), mul_rn(dy, mpy));
+    const float t2 = add_rn(mul_rn(fabsf(dx), spx), mul_rn(fabsf(dy), spy));
+    const float t3 = add_rn(mul_rn(L0, u[0]), mul_rn(L1, u[1]));
+    o.h[i] = add_rn(mul_rn(p.gamma_b, mul_rn(mul_rn(hc, hc), hc)), add_rn(sub_rn(t1, t2), t3));  // :261
+  }
+  RCBF_UNROLL
+  for (int cc = 0; cc < 2; ++cc) {  // :365-377
+    const int r = kUniHaz + 2 * cc;
+    RCBF_UNROLL
+    for (int j = 0; j < 3; ++j) {
+      o.G[r][j] = (j == cc) ? 1.0f : 0.0f;
+      o.G[r + 1][j] = (j == cc) ? -1.0f : 0.0f;
+    }
+    o.h[r] = sub_rn(p.u_max[cc], u[cc]);
+    o.h[r + 1] = add_rn(-p.u_min[cc], u[cc]);
+  }
+}
+
+struct CarsRaw {
+  float G[kCarsM][kCarsNZ];
+  float h[kCarsM];
+  float Lg[2];
+};
+
+// prior accelerations shared by the layer (:284-290), the prior model (dynamics.py:171-177) and the env
+// (simulated_cars_env.py:58-64).  v0des = desired velocity of the lead car.  T = float (layer) or double (env/prior).
+template <typename T>
+RCBF_HD void cars_accels(T kp, T kb, const T pos[5], const T vel[5], T v0des, T acc[5]) {
+  acc[0] = kp * (v0des - vel[0]);
+  RCBF_UNROLL
+  for (int i = 1; i < 5; ++i) acc[i] = kp * (T(30) - vel[i]);
+  const T d01 = pos[0] - pos[1], d12 = pos[1] - pos[2], d24 = pos[2] - pos[4];
+  acc[1] -= (d01 < T(6)) ? kb * d01 : T(0);
+  acc[2] -= (d12 < T(6)) ? kb * d12 : T(0);
+  acc[4] -= (d24 < T(13)) ? kb * d24 : T(0);
+}
+
+RCBF_HD void assemble_cars(const CarsParams& p, const float st[10], float u, const float sg[10], CarsRaw& o) {
+  float pos[5], vel[5], acc[5];
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {
+    pos[i] = st[2 * i];
+    vel[i] = st[2 * i + 1];
+  }
+  // :284-290 (no lead-car sinusoid in the layer, :285); each op rounded once like the torch expression
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) acc[i] = mul_rn(p.kp, sub_rn(30.0f, vel[i]));
+  const float d01 = sub_rn(pos[0], pos[1]), d12 = sub_rn(pos[1], pos[2]), d24 = sub_rn(pos[2], pos[4]);
+  acc[1] = (d01 < 6.0f) ? sub_rn(acc[1], mul_rn(p.k_brake, d01)) : acc[1];
+  acc[2] = (d12 < 6.0f) ? sub_rn(acc[2], mul_rn(p.k_brake, d12)) : acc[2];
+  acc[4] = (d24 < 13.0f) ? sub_rn(acc[4], mul_rn(p.k_brake, d24)) : acc[4];
+  // acc[3] = 0 (:289): its products vanish below
+  const float d23 = sub_rn(pos[2], pos[3]), d43 = sub_rn(pos[4], pos[3]);
+  const float h13 = mul_rn(0.5f, sub_rn(mul_rn(d23, d23), p.collision_radius_sq));  // :306
+  const float h15 = mul_rn(0.5f, sub_rn(mul_rn(d43, d43), p.collision_radius_sq));  // :307
+  const float a7 = sub_rn(pos[3], pos[2]), b7 = sub_rn(pos[3], pos[4]);
+  const float a6 = sub_rn(vel[3], vel[2]), b6 = sub_rn(vel[3], vel[4]);
+  const float h13d = mul_rn(a7, a6);  // :310
+  const float h15d = mul_rn(b7, b6);  // :311
+  const float a4 = sub_rn(vel[2], vel[3]), a5 = d23;  // :314-318
+  const float b8 = sub_rn(vel[4], vel[3]), b9 = d43;  // :322-326
+  // bmm accumulates in state-index order; the a7*acc3 / b7*acc3 terms are exact zeros           :319,:327
+  const float Lff13 = add_rn(add_rn(mul_rn(a4, vel[2]), mul_rn(a5, acc[2])), mul_rn(a6, vel[3]));
+  const float Lff15 = add_rn(add_rn(mul_rn(b6, vel[3]), mul_rn(b8, vel[4])), mul_rn(b9, acc[4]));
+  const float ss = p.sigma_scale;
+  const float LfD13 = mul_rn(ss, add_rn(mul_rn(fabsf(a5), sg[5]), mul_rn(fabsf(a7), sg[7])));  // :320 (:299 odd entries)
+  const float LfD15 = mul_rn(ss, add_rn(mul_rn(fabsf(b7), sg[7]), mul_rn(fabsf(b9), sg[9])));  // :328
+  const float Lg13 = mul_rn(a7, 50.0f), Lg15 = mul_rn(b7, 50.0f);                              // :331-332 (g = 50 e_7)
+  o.Lg[0] = Lg13;
+  o.Lg[1] = Lg15;
+  // :348-349, evaluated left to right
+  o.h[0] = add_rn(add_rn(add_rn(sub_rn(Lff13, LfD13), mul_rn(p.gamma_2, h13d)), mul_rn(p.gamma_sq, h13)), mul_rn(Lg13, u));
+  o.h[1] = add_rn(add_rn(add_rn(sub_rn(Lff15, LfD15), mul_rn(p.gamma_2, h15d)), mul_rn(p.gamma_sq, h15)), mul_rn(Lg15, u));
+  o.G[0][0] = -Lg13;  // :350
+  o.G[1][0] = -Lg15;  // :351
+  o.G[0][1] = -p.slack_coeff;  // :352
+  o.G[1][1] = -p.slack_coeff;
+  o.G[2][0] = 1.0f;  // :369-370
+  o.G[2][1] = 0.0f;
+  o.h[2] = sub_rn(p.u_max, u);
+  o.G[3][0] = -1.0f;  // :375-376
+  o.G[3][1] = 0.0f;
+  o.h[3] = add_rn(-p.u_min, u);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row normalisation (diff_cbf_qp.py:103-106) + column equilibration -> least-norm problem
+// ------------------------------------------------------------------------------------------------
+template <int NZ, int M>
+struct Normalised {
+  float Gn[M][NZ];
+  float hn[M];
+  float n[M];
+  uint32_t h_is_max;  // bit i: |h_i| is the (strict) row maximum  -> routes d n_i / d h_i in the backward
+};
+
+template <int NZ, int M>
+RCBF_HD void normalise_rows(const float G[M][NZ], const float h[M], Normalised<NZ, M>& o) {
+  o.h_is_max = 0;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    float gm = 0.0f;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) gm = fmaxf(gm, fabsf(G[i][j]));
+    const float ha = fabsf(h[i]);
+    // torch.max returns the FIRST maximal index on ties; h is the last column (diff_cbf_qp.py:103-104)
+    if (ha > gm) o.h_is_max |= (1u << i);
+    const float n = (ha != ha) ? ha : fmaxf(gm, ha);  // propagate NaN like torch.max
+    o.n[i] = n;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) o.Gn[i][j] = G[i][j] / n;
+    o.hn[i] = h[i] / n;
+  }
+}
+
+template <typename T, int NZ, int M>
+RCBF_HD void to_lnp(const Normalised<NZ, M>& nrm, const T pis[NZ] /* P^-1/2 */, LnpProblem<T, NZ, M>& P) {
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) P.A[i][j] = T(nrm.Gn[i][j]) * pis[j];
+    P.b[i] = T(nrm.hn[i]);
+  }
+}
+
+// certificate data of a normalised, column-equilibrated QP in float64: a(i,j) = G~_ij * P_j^-1/2 (exact product of
+// the float32 datum the reference also sees and the float64 scale), b(i) = h~_i
+template <int NZ, int M>
+struct NormCert {
+  const Normalised<NZ, M>& nrm;
+  const double* pis;
+  RCBF_HD double a(int i, int j) const { return (double)nrm.Gn[i][j] * pis[j]; }
+  RCBF_HD double b(int i) const { return (double)nrm.hn[i]; }
+};
+
+// certificate tolerances (normalised rows have |entries| <= 1)
+constexpr double kTolSlack = 1e-9;
+constexpr double kTolDual = 1e-9;
+
+// Solve the normalised QP of one instance.  Main path: float32 interior point + float64 certificate; if that does
+// not certify, the float64 interior point runs (rare "straggler" lanes).  x = P^-1/2 y.
+template <int NZ, int M>
+RCBF_HD void solve_normalised(const Normalised<NZ, M>& nrm, const float p_diag[NZ], double x[NZ], double lam[M],
+                              double s[M], int& status, int& iters) {
+  double pisd[NZ];
+  float pisf[NZ];
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    pisd[j] = 1.0 / sqrt((double)p_diag[j]);
+    pisf[j] = (float)pisd[j];
+  }
+  LnpSolution<double, NZ, M> sol;
+  const NormCert<NZ, M> cp{nrm, pisd};
+  {
+    LnpProblem<float, NZ, M> Pf;
+    to_lnp<float, NZ, M>(nrm, pisf, Pf);
+    lnp_solve<float, double, NormCert<NZ, M>, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
+  }
+  if (sol.status >= RCBF_MAXITER) {  // straggler: repeat in float64 (NaN inputs were caught before, status NAN = overflow)
+    const int it0 = sol.iters;
+    LnpProblem<double, NZ, M> Pd;
+    to_lnp<double, NZ, M>(nrm, pisd, Pd);
+    lnp_solve<double, double, NormCert<NZ, M>, NZ, M>(Pd, cp, sol, kTolSlack, kTolDual);
+    sol.iters += it0 + 100;  // +100 flags the float64 pass in the iteration histogram
+  }
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) x[j] = sol.y[j] * pisd[j];
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    lam[i] = sol.lam[i];
+    s[i] = sol.s[i];
+  }
+  status = sol.status;
+  iters = sol.iters;
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_safe_action for one instance (diff_cbf_qp.py:44-79): assemble -> normalise -> solve -> clamp
+// ------------------------------------------------------------------------------------------------
+RCBF_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+struct UniSolve {
+  UniRaw raw;
+  Normalised<kUniNZ, kUniM> nrm;
+  double x[kUniNZ], lam[kUniM], s[kUniM];
+  int status, iters;
+};
+
+RCBF_HD void unicycle_safe_action(const UnicycleParams& p, const float st[3], const float u[2], const float mu[3],
+                                  const float sg[3], UniSolve& w, float u_safe[2]) {
+  assemble_unicycle(p, st, u, mu, sg, w.raw);
+  normalise_rows<kUniNZ, kUniM>(w.raw.G, w.raw.h, w.nrm);
+  solve_normalised<kUniNZ, kUniM>(w.nrm, p.p_diag, w.x, w.lam, w.s, w.status, w.iters);
+  RCBF_UNROLL
+  for (int c = 0; c < 2; ++c) u_safe[c] = clampf(u[c] + (float)w.x[c], p.u_min[c], p.u_max[c]);  // :77
+}
+
+struct CarsSolve {
+  CarsRaw raw;
+  Normalised<kCarsNZ, kCarsM> nrm;
+  double x[kCarsNZ], lam[kCarsM], s[kCarsM];
+  int status, iters;
+};
+
+RCBF_HD void cars_safe_action(const CarsParams& p, const float st[10], float u, const float sg[10], CarsSolve& w,
+                              float* u_safe) {
+  assemble_cars(p, st, u, sg, w.raw);
+  normalise_rows<kCarsNZ, kCarsM>(w.raw.G, w.raw.h, w.nrm);
+  solve_normalised<kCarsNZ, kCarsM>(w.nrm, p.p_diag, w.x, w.lam, w.s, w.status, w.iters);
+  *u_safe = clampf(u + (float)w.x[0], p.u_min, p.u_max);  // :77
+}
+
+}  // namespace rcbf

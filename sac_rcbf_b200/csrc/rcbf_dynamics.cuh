@@ -1,0 +1,204 @@
+// rcbf_dynamics.cuh -- per-instance environment steps and prior dynamics.
+//
+// Templated on the arithmetic/storage type T:
+//   T = float   the throughput path (float4-packed Unicycle state, north_star item (1))
+//   T = double  bit-faithful restatement of the reference's numpy float64 envs, used by the drop-in
+//               num_envs=1 gym-style wrappers so 1000-step trajectories track the reference to ~1e-13.
+//
+// Reference: envs/unicycle_env.py:46-143,215-280 ; envs/simulated_cars_env.py:38-158 ;
+//            rcbf_sac/dynamics.py:60-105,125-188 (prior model).
+#pragma once
+
+#include "rcbf_core.cuh"
+
+namespace rcbf {
+
+using UnicycleEnvParams = rcbf_unicycle_env_params;  // include/rcbf_b200.h
+using CarsEnvParams = rcbf_cars_env_params;
+
+RCBF_HD void sincos_t(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+  sincos(x, s, c);
+#else
+  *s = sin(x);
+  *c = cos(x);
+#endif
+}
+RCBF_HD float t_exp(float x) { return expf(x); }
+RCBF_HD double t_exp(double x) { return exp(x); }
+RCBF_HD float t_sin(float x) { return sinf(x); }
+RCBF_HD double t_sin(double x) { return sin(x); }
+
+template <typename T>
+struct UniEnvOut {
+  T obs[7];
+  T reward;
+  T cost;     // 0.1 inside a hazard, else 0 (the reference omits info['cost'] when 0, unicycle_env.py:106-110)
+  int done;
+  int goal_met;
+};
+
+// obs = [x, y, cos th, sin th, compass_x, compass_y, exp(-dist)]     unicycle_env.py:215-231,260-277
+template <typename T>
+RCBF_HD void unicycle_obs(const UnicycleEnvParams& p, const T st[3], T c, T s, T dist, T obs[7]) {
+  const T vx = T(p.goal_x) - st[0], vy = T(p.goal_y) - st[1];
+  const T cx = vx * c + vy * s;    // row-vector times R(theta)    :272-274
+  const T cy = vx * (-s) + vy * c;
+  const T nrm = t_sqrt(cx * cx + cy * cy) + T(0.001);  // :276
+  obs[0] = st[0];
+  obs[1] = st[1];
+  obs[2] = c;
+  obs[3] = s;
+  obs[4] = cx / nrm;
+  obs[5] = cy / nrm;
+  obs[6] = t_exp(-dist);
+}
+
+template <typename T>
+RCBF_HD T unicycle_goal_dist(const UnicycleEnvParams& p, const T st[3]) {
+  const T vx = T(p.goal_x) - st[0], vy = T(p.goal_y) - st[1];
+  return t_sqrt(vx * vx + vy * vy);
+}
+
+// UnicycleEnv.step (:46-111).  st, last_dist, step are updated in place.
+template <typename T>
+RCBF_HD void unicycle_env_step(const UnicycleEnvParams& p, T st[3], T& last_dist, int& step, const T a_in[2],
+                               UniEnvOut<T>& o) {
+  const T dt = T(p.dt);
+  const T a0 = t_min(t_max(a_in[0], T(-1)), T(1));  // :62
+  const T a1 = t_min(t_max(a_in[1], T(-1)), T(1));
+  T s, c;
+  sincos_t(st[2], &s, &c);
+  st[0] += dt * (c * a0);  // :86   state += dt * (f + g(state) @ action), f = 0
+  st[1] += dt * (s * a0);
+  st[2] += dt * a1;
+  sincos_t(st[2], &s, &c);  // :87 uses g() and cos() of the UPDATED theta
+  const T k = dt * T(0.1);
+  st[0] -= (k * c) * c;
+  st[1] -= (k * s) * c;
+  step += 1;  // :89
+  const T dist = unicycle_goal_dist(p, st);
+  T reward = last_dist - dist;  // :93-95
+  last_dist = dist;
+  const bool goal = dist <= T(p.goal_size);  // :97,113-123
+  if (goal) reward += T(p.reward_goal);
+  o.done = goal || (step >= p.max_episode_steps);  // :100-102
+  o.goal_met = goal;
+  bool hit = false;
+  const T r2 = T(p.hazards_radius) * T(p.hazards_radius);
+  RCBF_UNROLL
+  for (int i = 0; i < kUniHaz; ++i) {
+    const T dx = st[0] - T(p.hazards[i][0]), dy = st[1] - T(p.hazards[i][1]);
+    hit = hit || (dx * dx + dy * dy < r2);  // :106
+  }
+  o.cost = hit ? T(0.1) : T(0);
+  o.reward = reward;
+  unicycle_obs(p, st, c, s, dist, o.obs);
+}
+
+template <typename T>
+RCBF_HD void unicycle_reset(const UnicycleEnvParams& p, T st[3], T& last_dist, int& step) {  // :125-143
+  st[0] = T(p.init_x);
+  st[1] = T(p.init_y);
+  st[2] = T(p.init_theta);
+  step = 0;
+  last_dist = unicycle_goal_dist(p, st);
+}
+
+template <typename T>
+struct CarsEnvOut {
+  T obs[10];
+  T reward;
+  T cost;
+  int done;
+};
+
+template <typename T>
+RCBF_HD void cars_obs(const T st[10], T obs[10]) {  // simulated_cars_env.py:143-158
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {
+    obs[2 * i] = st[2 * i] / T(100);
+    obs[2 * i + 1] = st[2 * i + 1] / T(30);
+  }
+}
+
+// SimulatedCarsEnv.step (:38-106).  st, t, step updated in place.
+template <typename T>
+RCBF_HD void cars_env_step(const CarsEnvParams& p, T st[10], T& t, int& step, T a, CarsEnvOut<T>& o) {
+  T pos[5], vel[5], acc[5];
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {
+    pos[i] = st[2 * i];
+    vel[i] = st[2 * i + 1];
+  }
+  const T v0 = T(30) - T(10) * t_sin(T(0.2) * t);            // :59-60
+  cars_accels<T>(T(p.kp), T(p.k_brake), pos, vel, v0, acc);  // :61-64 (car 4 keeps its own P-term)
+  const T dt = T(p.dt);
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {
+    const T ai = acc[i] * T(1.1);  // :67
+    const T gi = (i == 3) ? T(50) * a : T(0);
+    st[2 * i] = pos[i] + dt * vel[i];          // :77  state += dt * (f + g * action)
+    st[2 * i + 1] = vel[i] + dt * (ai + gi);
+  }
+  t = t + dt;  // :79
+  step += 1;   // :81
+  o.done = step >= p.max_episode_steps;  // :83
+  T cost = T(0);
+  if (st[4] - st[6] < T(2.99)) cost -= T(0.1);  // :100-101
+  if (st[6] - st[8] < T(2.99)) cost -= T(0.1);  // :103-104
+  o.cost = cost;
+  const T a2 = a * a;
+  o.reward = T(-5) * (a2 < T(0) ? -a2 : a2) / T(p.max_episode_steps);  // :93
+  cars_obs(st, o.obs);
+}
+
+template <typename T>
+RCBF_HD void cars_reset(T st[10], T& t, int& step, T v_noise) {  // :108-125
+  const T p0[5] = {T(34), T(28), T(22), T(16), T(10)};
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {
+    st[2 * i] = p0[i];
+    st[2 * i + 1] = T(30) + v_noise;
+  }
+  st[7] = T(35);
+  t = T(0);
+  step = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// prior model  next = s + dt (f(s,t) + g(s) u) + dt * mean        rcbf_sac/dynamics.py:86-92
+// ---------------------------------------------------------------------------------------------------
+template <typename T>
+RCBF_HD void unicycle_prior_next(T dt, const T st[3], const T u[2], const T mean[3], T nxt[3]) {
+  T s, c;
+  sincos_t(st[2], &s, &c);
+  nxt[0] = st[0] + dt * (c * u[0]);  // dynamics.py:145-151 g = [[c,0],[s,0],[0,1]], f = 0
+  nxt[1] = st[1] + dt * (s * u[0]);
+  nxt[2] = st[2] + dt * u[1];
+  RCBF_UNROLL
+  for (int j = 0; j < 3; ++j) nxt[j] += dt * mean[j];  // :92
+}
+
+template <typename T>
+RCBF_HD void cars_prior_next(T dt, T kp, T kb, const T st[10], T u, T t, const T mean[10], T nxt[10]) {
+  T pos[5], vel[5], acc[5];
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {
+    pos[i] = st[2 * i];
+    vel[i] = st[2 * i + 1];
+  }
+  const T v0 = T(30) - T(10) * t_sin(T(0.2) * t);  // dynamics.py:172
+  cars_accels<T>(kp, kb, pos, vel, v0, acc);       // :173-177
+  acc[3] = T(0);                                   // :176 (and no x1.1: that gap is what the GP learns)
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {
+    const T gi = (i == 3) ? T(50) * u : T(0);  // :158-162
+    nxt[2 * i] = pos[i] + dt * vel[i];
+    nxt[2 * i + 1] = vel[i] + dt * (acc[i] + gi);
+  }
+  RCBF_UNROLL
+  for (int j = 0; j < 10; ++j) nxt[j] += dt * mean[j];
+}
+
+}  // namespace rcbf

@@ -1,0 +1,297 @@
+"""CBFQPLayer -- drop-in for rcbf_sac/diff_cbf_qp.py:10-395 backed by the sm_100a kernels.
+
+Same constructor, attributes, method names, argument order, shapes, dtypes and exceptions as the reference class;
+`get_safe_action` is differentiable w.r.t. `action_batch` (the only input that carries grad in the reference, see
+rcbf_sac/sac_cbf.py:233-236).  Compute always runs on the CUDA device; tensors that live elsewhere are copied in and
+the result is returned on the caller's device.  There is no CPU path.
+"""
+import numpy as np
+import torch
+
+from . import _lib, _params
+
+DYNAMICS_MODE = {"Unicycle": {"n_s": 3, "n_u": 2}, "SimulatedCars": {"n_s": 10, "n_u": 1}}  # dynamics.py:22-23
+
+
+def _f32c(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class _SafeActionFn(torch.autograd.Function):
+    """final = clamp(a + QP(a)) with the implicit-KKT backward kernel (K4)."""
+
+    @staticmethod
+    def forward(ctx, layer, state, action, mean, sigma):
+        dev = layer.device
+        st, ac, sg = _f32c(state, dev), _f32c(action, dev), _f32c(sigma, dev)
+        mu = _f32c(mean, dev)
+        n = st.shape[0]
+        need_grad = action.requires_grad and torch.is_grad_enabled()
+        out, x, lam, slack = layer._forward_raw(st, ac, mu, sg, save=need_grad)
+        ctx.layer = layer
+        ctx.in_device = action.device
+        ctx.in_dtype = action.dtype
+        if need_grad:
+            ctx.save_for_backward(st, ac, mu, sg, x, lam, slack)
+        return out.to(device=action.device, dtype=action.dtype) if (action.device != dev or action.dtype != torch.float32) else out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        layer = ctx.layer
+        st, ac, mu, sg, x, lam, slack = ctx.saved_tensors
+        go = _f32c(grad_out, layer.device)
+        ga = layer._backward_raw(st, ac, mu, sg, x, lam, slack, go)
+        return None, None, ga.to(device=ctx.in_device, dtype=ctx.in_dtype), None, None
+
+
+class _QPFn(torch.autograd.Function):
+    """Generic batched QP (cbf_layer API): float64 in, float64 out, qpth-style gradients for Q, p, G, h."""
+
+    @staticmethod
+    def forward(ctx, layer, Q, p, G, h):
+        lib = _lib.load()
+        dev = layer.device
+        n, m, nz = G.shape
+        Qd, pd, Gd, hd = (t.detach().to(device=dev, dtype=torch.float64).contiguous() for t in (Q, p, G, h))
+        x = torch.empty((n, nz), dtype=torch.float64, device=dev)
+        lam = torch.empty((n, m), dtype=torch.float64, device=dev)
+        slack = torch.empty((n, m), dtype=torch.float64, device=dev)
+        counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.rcbf_qp_solve(_lib.ptr(Qd), _lib.ptr(pd), _lib.ptr(Gd), _lib.ptr(hd), n, nz, m, _lib.ptr(x),
+                                   _lib.ptr(lam), _lib.ptr(slack), None, None, _lib.ptr(counters),
+                                   _lib.stream_ptr(dev))
+        if rc == -1:
+            raise NotImplementedError("generic QP kernel is instantiated for (nz, m) in {(3, 9), (2, 4)}, got (%d, %d)"
+                                      % (nz, m))
+        _lib.check(rc, "rcbf_qp_solve")
+        layer._last_counters = counters
+        ctx.layer = layer
+        ctx.save_for_backward(Qd, Gd, x, lam, slack)
+        ctx.in_devices = (Q.device, p.device, G.device, h.device)
+        return x.to(G.device)
+
+    @staticmethod
+    def backward(ctx, gx):
+        lib = _lib.load()
+        layer = ctx.layer
+        dev = layer.device
+        Qd, Gd, x, lam, slack = ctx.saved_tensors
+        n, m, nz = Gd.shape
+        g = gx.detach().to(device=dev, dtype=torch.float64).contiguous()
+        dQ = torch.empty_like(Qd)
+        dp = torch.empty((n, nz), dtype=torch.float64, device=dev)
+        dG = torch.empty_like(Gd)
+        dh = torch.empty((n, m), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = lib.rcbf_qp_solve_bwd(_lib.ptr(Qd), _lib.ptr(Gd), _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack),
+                                       _lib.ptr(g), n, nz, m, _lib.ptr(dQ), _lib.ptr(dp), _lib.ptr(dG), _lib.ptr(dh),
+                                       _lib.stream_ptr(dev))
+        _lib.check(rc, "rcbf_qp_solve_bwd")
+        d = ctx.in_devices
+        return None, dQ.to(d[0]), dp.to(d[1]), dG.to(d[2]), dh.to(d[3])
+
+
+class CBFQPLayer:
+
+    def __init__(self, env, args, gamma_b=100, k_d=1.5, l_p=0.03):
+        """Constructor of CBFLayer (signature of rcbf_sac/diff_cbf_qp.py:12).
+
+        Parameters
+        ----------
+        env : gym.env-like
+            must expose dynamics_mode, safe_action_space, action_space and, per mode, hazards_locations /
+            hazards_radius (Unicycle) or kp / k_brake (SimulatedCars)  (diff_cbf_qp.py:27-41,205-206,286)
+        args : namespace with `.cuda` (diff_cbf_qp.py:25); optional `.device_num`
+        gamma_b, k_d, l_p : as in the reference (k_d is stored but unused by this layer, like diff_cbf_qp.py:36/:261)
+        """
+        _lib.require_cuda()
+        _lib.load()
+        dev_num = getattr(args, "device_num", None)
+        self.device = torch.device("cuda", torch.cuda.current_device() if dev_num is None else int(dev_num))
+        # the reference computes on CPU when args.cuda is False; here the QP always runs on the GPU and results are
+        # returned on the caller's device
+        self.caller_device = self.device if getattr(args, "cuda", True) else torch.device("cpu")
+
+        self.env = env
+        self.u_min, self.u_max = self.get_control_bounds()
+        self.gamma_b = gamma_b
+
+        if self.env.dynamics_mode not in DYNAMICS_MODE:
+            raise Exception('Dynamics mode not supported.')
+
+        if self.env.dynamics_mode == 'Unicycle':
+            self.num_cbfs = len(env.hazards_locations)
+            self.k_d = k_d
+            self.l_p = l_p
+        elif self.env.dynamics_mode == 'SimulatedCars':
+            self.num_cbfs = 2
+
+        self.action_dim = env.action_space.shape[0]
+        self.num_ineq_constraints = self.num_cbfs + 2 * self.action_dim
+        self.check_nan = True       # reference behaviour: sync + raise on NaN (diff_cbf_qp.py:141-143)
+        self._last_counters = None  # device tensor [nan, uncertified, f64 passes, trivial, sum iters, ...]
+        self._params_cache = None
+
+    # ------------------------------------------------------------------------------------------------------ params
+    def _params(self):
+        """C parameter struct, rebuilt when a public attribute the reference reads at call time has changed."""
+        env = self.env
+        if env.dynamics_mode == 'Unicycle':
+            key = ('U', float(self.gamma_b), float(self.l_p), float(env.hazards_radius),
+                   np.asarray(env.hazards_locations, np.float64).tobytes(),
+                   self.u_min.cpu().numpy().tobytes(), self.u_max.cpu().numpy().tobytes())
+            if self._params_cache is None or self._params_cache[0] != key:
+                p = _params.unicycle_params(env.hazards_locations, env.hazards_radius, float(self.gamma_b),
+                                            float(self.l_p), self.u_min.cpu().numpy(), self.u_max.cpu().numpy())
+                self._params_cache = (key, p)
+        else:
+            key = ('C', float(self.gamma_b), float(env.kp), float(env.k_brake), self.u_min.cpu().numpy().tobytes(),
+                   self.u_max.cpu().numpy().tobytes())
+            if self._params_cache is None or self._params_cache[0] != key:
+                p = _params.cars_params(float(self.gamma_b), float(env.kp), float(env.k_brake),
+                                        float(self.u_min[0]), float(self.u_max[0]))
+                self._params_cache = (key, p)
+        return self._params_cache[1]
+
+    # ------------------------------------------------------------------------------------------------- raw launches
+    def _forward_raw(self, st, ac, mu, sg, save=False, want_status=False):
+        lib = _lib.load()
+        dev = self.device
+        n = st.shape[0]
+        mode = self.env.dynamics_mode
+        nz, m, nu = (3, 9, 2) if mode == 'Unicycle' else (2, 4, 1)
+        out = torch.empty((n, nu), dtype=torch.float32, device=dev)
+        x = lam = slack = status = iters = None
+        if save:
+            x = torch.empty((n, nz), dtype=torch.float32, device=dev)
+            lam = torch.empty((n, m), dtype=torch.float32, device=dev)
+            slack = torch.empty((n, m), dtype=torch.float32, device=dev)
+        if want_status:
+            status = torch.empty((n,), dtype=torch.int32, device=dev)
+            iters = torch.empty((n,), dtype=torch.int32, device=dev)
+        counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        p = self._params()
+        with torch.cuda.device(dev):
+            if mode == 'Unicycle':
+                rc = lib.rcbf_unicycle_safe_action(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
+                                                   _lib.ptr(out), _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack),
+                                                   _lib.ptr(status), _lib.ptr(iters), _lib.ptr(counters),
+                                                   _lib.stream_ptr(dev))
+            else:
+                rc = lib.rcbf_cars_safe_action(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), n, p, _lib.ptr(out),
+                                               _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack), _lib.ptr(status),
+                                               _lib.ptr(iters), _lib.ptr(counters), _lib.stream_ptr(dev))
+        _lib.check(rc, "rcbf_%s_safe_action" % mode)
+        self._last_counters = counters
+        self._last_status, self._last_iters = status, iters
+        if self.check_nan and int(counters[0].item()) > 0:
+            print('\033[91m QP Failed to solve - result is nan == True!\033[00m')
+            raise Exception('QP Failed to solve')
+        return out, x, lam, slack
+
+    def _backward_raw(self, st, ac, mu, sg, x, lam, slack, go):
+        lib = _lib.load()
+        dev = self.device
+        n = st.shape[0]
+        ga = torch.empty_like(ac)
+        p = self._params()
+        with torch.cuda.device(dev):
+            if self.env.dynamics_mode == 'Unicycle':
+                rc = lib.rcbf_unicycle_safe_action_bwd(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg),
+                                                       _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack), _lib.ptr(go), n, p,
+                                                       _lib.ptr(ga), _lib.stream_ptr(dev))
+            else:
+                rc = lib.rcbf_cars_safe_action_bwd(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), _lib.ptr(x),
+                                                   _lib.ptr(lam), _lib.ptr(slack), _lib.ptr(go), n, p, _lib.ptr(ga),
+                                                   _lib.stream_ptr(dev))
+        _lib.check(rc, "rcbf_safe_action_bwd")
+        return ga
+
+    # ------------------------------------------------------------------------------------------------- public API
+    def get_safe_action(self, state_batch, action_batch, mean_pred_batch, sigma_batch):
+        """Safe action = clamp(action + u_cbf) (diff_cbf_qp.py:44-79).  1-D inputs are accepted and return 1-D."""
+        expand_dims = len(state_batch.shape) == 1
+        if expand_dims:
+            action_batch = action_batch.unsqueeze(0)
+            state_batch = state_batch.unsqueeze(0)
+            mean_pred_batch = mean_pred_batch.unsqueeze(0)
+            sigma_batch = sigma_batch.unsqueeze(0)
+        assert len(state_batch.shape) == 2 and len(action_batch.shape) == 2 and len(mean_pred_batch.shape) == 2 and \
+            len(sigma_batch.shape) == 2, print(state_batch.shape, action_batch.shape, mean_pred_batch.shape,
+                                               sigma_batch.shape)
+        final_action = _SafeActionFn.apply(self, state_batch, action_batch, mean_pred_batch, sigma_batch)
+        return final_action if not expand_dims else final_action.squeeze(0)
+
+    def solve_qp(self, Ps, qs, Gs, hs):
+        """Row-normalise [G|h] and solve; returns x[:, :-1] (diff_cbf_qp.py:81-109).  Like the reference, Gs is
+        normalised IN PLACE."""
+        Ghs = torch.cat((Gs, hs.unsqueeze(2)), -1)
+        Ghs_norm = torch.max(torch.abs(Ghs), dim=2, keepdim=True)[0]
+        Gs /= Ghs_norm
+        hs = hs / Ghs_norm.squeeze(-1)
+        sol = self.cbf_layer(Ps, qs, Gs, hs,
+                             solver_args={"check_Q_spd": False, "maxIter": 100000, "notImprovedLim": 10, "eps": 1e-4})
+        safe_action_batch = sol[:, :-1]
+        return safe_action_batch
+
+    def cbf_layer(self, Qs, ps, Gs, hs, As=None, bs=None, solver_args=None):
+        """Batched QP  min 1/2 x'Qx + p'x  s.t. Gx <= h  -> float32 (B, nz)  (diff_cbf_qp.py:111-144).
+        solver_args are accepted for signature compatibility; the kernel converges every QP to its KKT point."""
+        if As is not None and bs is not None and (As.numel() > 0 or bs.numel() > 0):
+            raise NotImplementedError("equality constraints are never used by the reference (diff_cbf_qp.py:135-137)")
+        result = _QPFn.apply(self, Qs, ps, Gs, hs).float()
+        if torch.any(torch.isnan(result)):
+            print('\033[91m QP Failed to solve - result is nan == True!\033[00m')
+            raise Exception('QP Failed to solve')
+        return result
+
+    def get_cbf_qp_constraints(self, state_batch, action_batch, mean_pred_batch, sigma_pred_batch):
+        """P (B,nz,nz), q (B,nz), G (B,m,nz), h (B,m) as float32 (diff_cbf_qp.py:146-379)."""
+        assert len(state_batch.shape) == 2 and len(action_batch.shape) == 2 and len(mean_pred_batch.shape) == 2 and len(
+            sigma_pred_batch.shape) == 2, print(state_batch.shape, action_batch.shape, mean_pred_batch.shape,
+                                                sigma_pred_batch.shape)
+        lib = _lib.load()
+        dev = self.device
+        out_dev = state_batch.device
+        st, ac, sg = _f32c(state_batch, dev), _f32c(action_batch, dev), _f32c(sigma_pred_batch, dev)
+        mu = _f32c(mean_pred_batch, dev)
+        n = st.shape[0]
+        mode = self.env.dynamics_mode
+        p = self._params()
+        with torch.cuda.device(dev):
+            if mode == 'Unicycle':
+                G = torch.empty((n, 9, 3), dtype=torch.float32, device=dev)
+                h = torch.empty((n, 9), dtype=torch.float32, device=dev)
+                rc = lib.rcbf_unicycle_assemble(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
+                                                _lib.ptr(G), _lib.ptr(h), _lib.stream_ptr(dev))
+                P = torch.diag(torch.tensor([1.e0, 1.e-2, 1e5])).repeat(n, 1, 1).to(out_dev)
+            elif mode == 'SimulatedCars':
+                G = torch.empty((n, 4, 2), dtype=torch.float32, device=dev)
+                h = torch.empty((n, 4), dtype=torch.float32, device=dev)
+                rc = lib.rcbf_cars_assemble(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), n, p, _lib.ptr(G), _lib.ptr(h),
+                                            _lib.stream_ptr(dev))
+                P = torch.diag(torch.tensor([0.1, 1e1])).repeat(n, 1, 1).to(out_dev)
+            else:
+                raise Exception('Dynamics mode unknown!')
+        _lib.check(rc, "rcbf_assemble")
+        q = torch.zeros((n, self.action_dim + 1), device=out_dev)
+        return P, q, G.to(out_dev), h.to(out_dev)
+
+    def get_control_bounds(self):
+        """u_min, u_max tensors on the device (diff_cbf_qp.py:381-395)."""
+        u_min = torch.tensor(self.env.safe_action_space.low).to(self.device)
+        u_max = torch.tensor(self.env.safe_action_space.high).to(self.device)
+        return u_min, u_max
+
+    # ---------------------------------------------------------------------------------------------- diagnostics
+    def solver_stats(self):
+        """Counters of the last launch: dict(nan, uncertified, f64_passes, trivial, sum_iters)."""
+        if self._last_counters is None:
+            return None
+        c = self._last_counters.cpu().tolist()
+        return dict(nan=c[0], uncertified=c[1], f64_passes=c[2], trivial=c[3], sum_iters=c[4])
+
+
+# north_star names the class DiffCBFLayer; the reference only has CBFQPLayer (SURVEY.md "Naming note")
+DiffCBFLayer = CBFQPLayer

@@ -1,0 +1,142 @@
+"""Batched SimulatedCarsEnv on the GPU -- drop-in for envs/simulated_cars_env.py (gym old 4-tuple API).
+
+Front <- Car 1 <- Car 2 <- Car 3 <- Car 4 (controlled) <- Car 5.  num_envs == 1 reproduces the reference's
+single-instance contract on the float64 kernel (reset draws its velocity noise from numpy's global RNG exactly like
+simulated_cars_env.py:118); num_envs > 1 is device-resident float32.
+"""
+import numpy as np
+import torch
+
+from .. import _lib, _params
+from ..spaces import Box
+
+
+class SimulatedCarsEnv:
+    metadata = {'render.modes': ['human']}
+
+    def __init__(self, num_envs=1, device=None, precision=None, auto_reset=False, seed=None):
+        _lib.require_cuda()
+        self._lib = _lib.load()
+        self.num_envs = int(num_envs)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.precision = precision or ("f64" if self.num_envs == 1 else "f32")
+        self._dtype = torch.float64 if self.precision == "f64" else torch.float32
+        self.auto_reset = bool(auto_reset)
+
+        self.dynamics_mode = 'SimulatedCars'
+        self.action_space = Box(low=-1.0, high=1.0, shape=(1,))               # simulated_cars_env.py:18
+        self.safe_action_space = Box(low=-10.0, high=10.0, shape=(1,))        # :19
+        self.observation_space = Box(low=-1e10, high=1e10, shape=(10,))       # :20
+        self.max_episode_steps = 300
+        self.dt = 0.02
+        self.kp = 4.0
+        self.k_brake = 20.0
+        self.disturb_mean = np.zeros((1,))
+        self.disturb_covar = np.diag([0.2 ** 2])
+
+        n = self.num_envs
+        self._state = torch.zeros((n, 10), dtype=self._dtype, device=self.device)
+        self._t = torch.zeros((n,), dtype=self._dtype, device=self.device)
+        self._step = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        self._obs = torch.empty((n, 10), dtype=self._dtype, device=self.device)
+        self._reward = torch.empty((n,), dtype=self._dtype, device=self.device)
+        self._cost = torch.empty((n,), dtype=self._dtype, device=self.device)
+        self._done = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        self._gen = torch.Generator(device=self.device)
+        if seed is not None:
+            self._gen.manual_seed(int(seed))
+        self.reset()
+
+    @property
+    def unwrapped(self):
+        return self
+
+    def _env_params(self):
+        return _params.cars_env_params(self.dt, self.kp, self.k_brake, self.max_episode_steps, self.auto_reset)
+
+    def _fn(self, name):
+        return getattr(self._lib, "rcbf_cars_env_%s_%s" % (name, self.precision))
+
+    @property
+    def state(self):
+        return self._state[0].double().cpu().numpy() if self.num_envs == 1 else self._state
+
+    @state.setter
+    def state(self, value):
+        v = torch.as_tensor(np.asarray(value) if not torch.is_tensor(value) else value).to(self.device, self._dtype)
+        self._state[:] = v.reshape(-1, 10)
+
+    @property
+    def t(self):
+        return float(self._t[0].item()) if self.num_envs == 1 else self._t
+
+    @property
+    def episode_step(self):
+        return int(self._step[0].item()) if self.num_envs == 1 else self._step
+
+    def seed(self, s=None):
+        self.action_space.seed(s)
+        if s is not None:
+            self._gen.manual_seed(int(s))
+        return [s]
+
+    def close(self):
+        pass
+
+    def render(self, mode='human', close=False):
+        print('Ep_step = {}, \tState = {}'.format(self.episode_step, self.state))
+
+    def reset(self, mask=None, v_noise=None):
+        """All cars at (34, 28, 22, 16, 10), velocities 30 + ONE shared N(0, 0.5) draw per instance, car 4 at 35."""
+        n = self.num_envs
+        if v_noise is None:
+            if n == 1:
+                v_noise = torch.tensor([np.random.normal(0, 0.5)], dtype=self._dtype)   # global numpy RNG, like :118
+            else:
+                v_noise = 0.5 * torch.randn((n,), generator=self._gen, device=self.device, dtype=self._dtype)
+        vn = torch.as_tensor(v_noise).to(self.device, self._dtype).reshape(n).contiguous()
+        m = None if mask is None else mask.to(self.device, torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            rc = self._fn("reset")(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step), _lib.ptr(vn),
+                                   _lib.ptr(m), n, _lib.ptr(self._obs), _lib.stream_ptr(self.device))
+        _lib.check(rc, "rcbf_cars_env_reset")
+        return self._obs[0].double().cpu().numpy() if n == 1 else self._obs.clone()
+
+    def step(self, action):
+        if torch.is_tensor(action):
+            a = action.detach().to(self.device, self._dtype).reshape(self.num_envs).contiguous()
+        else:
+            a = torch.as_tensor(np.asarray(action, np.float64).reshape(self.num_envs)).to(self.device, self._dtype)
+        with torch.cuda.device(self.device):
+            rc = self._fn("step")(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step), _lib.ptr(a),
+                                  self.num_envs, self._env_params(), _lib.ptr(self._obs), _lib.ptr(self._reward),
+                                  _lib.ptr(self._done), _lib.ptr(self._cost), _lib.stream_ptr(self.device))
+        _lib.check(rc, "rcbf_cars_env_step")
+        if self.num_envs == 1:
+            info = {'cost': float(self._cost[0].item()), 'goal_met': False}     # simulated_cars_env.py:85
+            return (self._obs[0].double().cpu().numpy(), float(self._reward[0].item()), bool(self._done[0].item()),
+                    info)
+        info = {'cost': self._cost.clone(), 'goal_met': torch.zeros_like(self._done, dtype=torch.bool)}
+        return self._obs.clone(), self._reward.clone(), self._done.bool(), info
+
+    def safe_step(self, cbf_layer, action_rl, sigma_pred, want_status=False):
+        """Fused K5 (float32 layout): get_safe_action + step in one launch.  Returns (safe_action, obs, reward, done, info)."""
+        if self.precision != "f32":
+            raise ValueError("safe_step runs on the float32 env layout (precision='f32')")
+        dev = self.device
+        n = self.num_envs
+        ac = action_rl.detach().to(dev, torch.float32).reshape(n).contiguous()
+        sg = sigma_pred.detach().to(dev, torch.float32).contiguous()
+        if not hasattr(self, "_safe_action"):
+            self._safe_action = torch.empty((n, 1), dtype=torch.float32, device=dev)
+            self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None
+        with torch.cuda.device(dev):
+            rc = self._lib.rcbf_cars_safe_step(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step),
+                                               _lib.ptr(ac), _lib.ptr(sg), n, cbf_layer._params(), self._env_params(),
+                                               _lib.ptr(self._safe_action), _lib.ptr(self._obs), _lib.ptr(self._reward),
+                                               _lib.ptr(self._done), _lib.ptr(self._cost), _lib.ptr(status),
+                                               _lib.ptr(self._counters), _lib.stream_ptr(dev))
+        _lib.check(rc, "rcbf_cars_safe_step")
+        info = {'cost': self._cost, 'status': status}
+        return self._safe_action, self._obs, self._reward, self._done, info

@@ -1,0 +1,184 @@
+"""Batched UnicycleEnv on the GPU -- drop-in for envs/unicycle_env.py (gym old 4-tuple API).
+
+num_envs == 1 reproduces the single-instance contract of the reference exactly (ndarray obs, python float reward, bool
+done, info dict with 'goal_met' only when met and 'cost' only inside a hazard) and runs the float64 kernel, which
+follows the numpy arithmetic of the reference operation by operation.  num_envs > 1 keeps everything on the device
+(torch tensors in / out) and defaults to the float32 layout: state = one float4 (x, y, theta, last_goal_dist).
+Rendering (unicycle_env.py:145-213) is out of scope.
+"""
+import numpy as np
+import torch
+
+from .. import _lib, _params
+from ..spaces import Box
+
+
+class UnicycleEnv:
+    metadata = {'render.modes': ['human']}
+
+    def __init__(self, num_envs=1, device=None, precision=None, auto_reset=False):
+        _lib.require_cuda()
+        self._lib = _lib.load()
+        self.num_envs = int(num_envs)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.precision = precision or ("f64" if self.num_envs == 1 else "f32")
+        self._dtype = torch.float64 if self.precision == "f64" else torch.float32
+        self.auto_reset = bool(auto_reset)
+
+        self.dynamics_mode = 'Unicycle'
+        self.action_space = Box(low=-1.0, high=1.0, shape=(2,))               # unicycle_env.py:21
+        self.safe_action_space = Box(low=-2.5, high=2.5, shape=(2,))          # :22
+        self.observation_space = Box(low=-1e10, high=1e10, shape=(7,))        # :23
+        self.bds = np.array([[-3., -3.], [3., 3.]])                           # :24
+        self.hazards_radius = 0.6                                             # :25
+        self.hazards_locations = np.array([[0., 0.], [-1., 1.], [-1., -1.], [1., -1.], [1., 1.]]) * 1.5   # :26
+        self.dt = 0.02
+        self.max_episode_steps = 1000
+        self.reward_goal = 1.0
+        self.goal_size = 0.3
+        self.goal_pos = np.array([2.5, 2.5])
+        self.initial_state = np.array([-2.5, -2.5, 0.])                       # :137
+        self.viewer = None
+
+        n = self.num_envs
+        self._state4 = torch.zeros((n, 4), dtype=self._dtype, device=self.device)
+        self._step = torch.zeros((n,), dtype=torch.int32, device=self.device)
+        self._obs = torch.empty((n, 7), dtype=self._dtype, device=self.device)
+        self._reward = torch.empty((n,), dtype=self._dtype, device=self.device)
+        self._cost = torch.empty((n,), dtype=self._dtype, device=self.device)
+        self._done = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        self._goal = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        self.reset()
+
+    # -------------------------------------------------------------------------------------------- helpers
+    @property
+    def unwrapped(self):
+        return self
+
+    def _env_params(self):
+        return _params.unicycle_env_params(self.hazards_locations, self.hazards_radius, self.dt, self.goal_pos,
+                                           self.goal_size, self.reward_goal, self.initial_state,
+                                           self.max_episode_steps, self.auto_reset)
+
+    def _fn(self, name):
+        return getattr(self._lib, "rcbf_unicycle_env_%s_%s" % (name, self.precision))
+
+    @property
+    def state(self):
+        """(3,) float64 ndarray for num_envs == 1 (like the reference attribute), else a (N,3) device tensor view."""
+        if self.num_envs == 1:
+            return self._state4[0, :3].double().cpu().numpy()
+        return self._state4[:, :3]
+
+    @state.setter
+    def state(self, value):
+        v = torch.as_tensor(np.asarray(value) if not torch.is_tensor(value) else value).to(self.device, self._dtype)
+        self._state4[:, :3] = v.reshape(-1, 3)
+        gp = torch.as_tensor(self.goal_pos, dtype=self._dtype, device=self.device)
+        self._state4[:, 3] = torch.linalg.norm(gp - self._state4[:, :2], dim=1)
+
+    @property
+    def episode_step(self):
+        return int(self._step[0].item()) if self.num_envs == 1 else self._step
+
+    @property
+    def last_goal_dist(self):
+        return float(self._state4[0, 3].item()) if self.num_envs == 1 else self._state4[:, 3]
+
+    def seed(self, s=None):
+        self.action_space.seed(s)
+        return [s]
+
+    def close(self):
+        pass
+
+    def render(self, mode='human', close=False):
+        raise NotImplementedError("rendering (envs/unicycle_env.py:145-213) is outside the hot-path scope")
+
+    # -------------------------------------------------------------------------------------------- API
+    def reset(self, mask=None):
+        """Reset all instances (or those where mask != 0) to (-2.5, -2.5, 0); returns the observation."""
+        m = None if mask is None else mask.to(self.device, torch.uint8).contiguous()
+        e = self._env_params()
+        with torch.cuda.device(self.device):
+            rc = self._fn("reset")(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(m), self.num_envs, e,
+                                   _lib.ptr(self._obs), _lib.stream_ptr(self.device))
+        _lib.check(rc, "rcbf_unicycle_env_reset")
+        return self.get_obs_from_buffer()
+
+    def get_obs_from_buffer(self):
+        if self.num_envs == 1:
+            return self._obs[0].double().cpu().numpy()
+        return self._obs.clone()
+
+    def get_obs(self):
+        """Observation of the current state (unicycle_env.py:215-231)."""
+        e = self._env_params()
+        zero = torch.zeros((self.num_envs,), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            rc = self._fn("reset")(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(zero), self.num_envs, e,
+                                   _lib.ptr(self._obs), _lib.stream_ptr(self.device))
+        _lib.check(rc, "rcbf_unicycle_env_reset(obs only)")
+        return self.get_obs_from_buffer()
+
+    def step(self, action):
+        """(obs, reward, done, info).  The action is clipped to [-1, 1] inside the kernel (unicycle_env.py:62)."""
+        if torch.is_tensor(action):
+            a = action.detach().to(self.device, self._dtype).reshape(self.num_envs, 2).contiguous()
+        else:
+            a = torch.as_tensor(np.asarray(action, np.float64).reshape(self.num_envs, 2)).to(self.device, self._dtype)
+        e = self._env_params()
+        with torch.cuda.device(self.device):
+            rc = self._fn("step")(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(a), self.num_envs, e,
+                                  _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._done),
+                                  _lib.ptr(self._cost), _lib.ptr(self._goal), _lib.stream_ptr(self.device))
+        _lib.check(rc, "rcbf_unicycle_env_step")
+        return self._pack_step_outputs()
+
+    def _pack_step_outputs(self):
+        if self.num_envs == 1:
+            info = dict()
+            if bool(self._goal[0].item()):
+                info['goal_met'] = True                    # only present when met (unicycle_env.py:98)
+            c = float(self._cost[0].item())
+            if c != 0.0:
+                info['cost'] = c                           # only present inside a hazard (:106-110)
+            return (self._obs[0].double().cpu().numpy(), float(self._reward[0].item()), bool(self._done[0].item()),
+                    info)
+        info = {'cost': self._cost.clone(), 'goal_met': self._goal.bool()}
+        return self._obs.clone(), self._reward.clone(), self._done.bool(), info
+
+    def safe_step(self, cbf_layer, action_rl, mean_pred, sigma_pred, want_status=False):
+        """Fused K5: CBFQPLayer.get_safe_action + step in ONE kernel launch (float32 layout only).
+        Returns (safe_action, obs, reward, done, info)."""
+        if self.precision != "f32":
+            raise ValueError("safe_step runs on the float32 env layout (precision='f32')")
+        dev = self.device
+        ac = action_rl.detach().to(dev, torch.float32).contiguous()
+        mu = mean_pred.detach().to(dev, torch.float32).contiguous()
+        sg = sigma_pred.detach().to(dev, torch.float32).contiguous()
+        n = self.num_envs
+        if not hasattr(self, "_safe_action"):
+            self._safe_action = torch.empty((n, 2), dtype=torch.float32, device=dev)
+            self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None
+        with torch.cuda.device(dev):
+            rc = self._lib.rcbf_unicycle_safe_step(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(ac),
+                                                   _lib.ptr(mu), _lib.ptr(sg), n, cbf_layer._params(),
+                                                   self._env_params(), _lib.ptr(self._safe_action), _lib.ptr(self._obs),
+                                                   _lib.ptr(self._reward), _lib.ptr(self._done), _lib.ptr(self._cost),
+                                                   _lib.ptr(self._goal), _lib.ptr(status), _lib.ptr(self._counters),
+                                                   _lib.stream_ptr(dev))
+        _lib.check(rc, "rcbf_unicycle_safe_step")
+        info = {'cost': self._cost, 'goal_met': self._goal, 'status': status}
+        return self._safe_action, self._obs, self._reward, self._done, info
+
+    # kept for API parity with envs/unicycle_env.py:113,260
+    def goal_met(self):
+        d = torch.linalg.norm(torch.as_tensor(self.goal_pos, dtype=self._dtype, device=self.device)
+                              - self._state4[:, :2], dim=1) <= self.goal_size
+        return bool(d[0].item()) if self.num_envs == 1 else d
+
+    def obs_compass(self):
+        o = self.get_obs()
+        return o[4:6] if self.num_envs == 1 else o[:, 4:6]

@@ -1,0 +1,430 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the Python mirror of the reference API (which goes through
+the C ABI of include/rcbf_b200.h), against the CPU oracle and the golden fixtures generated from the reference source.
+
+Tolerances are the ones BASELINE.json's north_star states:
+    dynamics        1e-6 relative (fp32 vs the float64 oracle)
+    safe actions    1e-4 absolute vs the reference QP solve, every normalised row satisfied to -1e-6
+    gradients       1e-3 relative (norm-wise per batch)
+"""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import exact_qp, rcbf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ACT_TOL = 1e-4
+ROW_TOL = -1e-6
+GRAD_TOL = 1e-3
+DYN_RTOL = 1e-6
+
+tt = torch.from_numpy
+
+
+def _cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sac_rcbf_b200 as S_
+    S_.load_library()
+    return S_
+
+
+def _args():
+    return types.SimpleNamespace(cuda=True, gp_model_size=2000, l_p=0.03)
+
+
+@pytest.fixture(scope="module")
+def uni(S):
+    env = S.UnicycleEnv()
+    return env, S.CBFQPLayer(env, _args(), gamma_b=20, k_d=3.0, l_p=0.03)
+
+
+@pytest.fixture(scope="module")
+def cars(S):
+    env = S.SimulatedCarsEnv()
+    return env, S.CBFQPLayer(env, _args(), gamma_b=20, k_d=3.0, l_p=0.03)
+
+
+def _row_slack(Gn, hn, x):
+    return (hn.astype(np.float64) - np.einsum("bmj,bj->bm", Gn.astype(np.float64), x.astype(np.float64))).min()
+
+
+# ----------------------------------------------------------------------------------------------------- assembly
+@pytest.mark.parametrize("which,name", [("uni", "unicycle_layer_b256.npz"), ("cars", "cars_layer_b512.npz")])
+def test_assembly_vs_golden(request, golden, which, name):
+    env, layer = request.getfixturevalue(which)
+    g = golden(name)
+    P, q, G, h = layer.get_cbf_qp_constraints(*(_cuda(g[k]) for k in ("state", "action", "mean", "sigma")))
+    assert P.shape == g["P"].shape and q.shape == g["q"].shape and G.shape == g["G"].shape and h.shape == g["h"].shape
+    np.testing.assert_array_equal(P.cpu().numpy(), g["P"])
+    np.testing.assert_array_equal(q.cpu().numpy(), g["q"])
+    n = np.maximum(np.abs(g["G"]).max(2), np.abs(g["h"]))
+    # same op order as the reference: differences are the last ulp of cos/sin only
+    assert (np.abs(G.cpu().numpy() - g["G"]) / n[:, :, None]).max() < 5e-7
+    assert (np.abs(h.cpu().numpy() - g["h"]) / n).max() < 3e-6
+    if which == "cars":     # no transcendental on this path: bit exact
+        np.testing.assert_array_equal(G.cpu().numpy(), g["G"])
+        np.testing.assert_array_equal(h.cpu().numpy(), g["h"])
+
+
+# ----------------------------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize("which,name", [("uni", "unicycle_layer_b256.npz"), ("cars", "cars_layer_b512.npz")])
+def test_safe_action_vs_golden(request, golden, which, name):
+    env, layer = request.getfixturevalue(which)
+    g = golden(name)
+    out = layer.get_safe_action(*(_cuda(g[k]) for k in ("state", "action", "mean", "sigma")))
+    assert out.dtype == torch.float32 and out.is_cuda and out.shape == g["safe_action"].shape
+    err = np.abs(out.cpu().numpy() - g["safe_action"])
+    assert err.max() < ACT_TOL, err.max()
+    # vs the exact optimum of the reference-assembled QP
+    nu = g["action"].shape[1]
+    lo, hi = env.safe_action_space.low, env.safe_action_space.high
+    ex = np.clip(g["action"] + g["x_exact"][:, :nu].astype(np.float32), lo, hi)
+    assert np.abs(out.cpu().numpy() - ex).max() < ACT_TOL
+    st = layer.solver_stats()
+    assert st["nan"] == 0 and st["uncertified"] == 0
+    # 1-D contract (diff_cbf_qp.py:64-69,79)
+    o1 = layer.get_safe_action(*(_cuda(g[k][0]) for k in ("state", "action", "mean", "sigma")))
+    assert o1.shape == (nu,) and np.abs(o1.cpu().numpy() - g["safe_action_1d"]).max() < ACT_TOL
+
+
+def _forward_with_aux(layer, st, ac, mu, sg):
+    out, x, lam, slack = layer._forward_raw(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg), save=True, want_status=True)
+    return (out.cpu().numpy(), x.cpu().numpy(), lam.cpu().numpy(), slack.cpu().numpy(),
+            layer._last_status.cpu().numpy(), layer._last_iters.cpu().numpy())
+
+
+@pytest.mark.parametrize("mode", ["Unicycle", "SimulatedCars"])
+def test_safe_action_vs_oracle_synthetic(request, mode):
+    env, layer = request.getfixturevalue("uni" if mode == "Unicycle" else "cars")
+    B = 20000
+    if mode == "Unicycle":
+        st, ac, mu, sg = O.synth_unicycle(B, seed=2024)
+        keep = np.ones(B, bool)
+    else:
+        st, ac, mu, sg, _ = O.synth_cars(B, seed=2024)
+        keep = O.cars_threshold_margin(st) > 1e-4          # braking switches (SURVEY 'Discontinuities')
+    out, x, lam, slack, status, iters = _forward_with_aux(layer, st, ac, mu, sg)
+    assert not np.isnan(out).any()
+    assert (status <= 2).all(), np.bincount(status)
+    # oracle: reference-order f32 assembly + exact solve; and the same with f64 assembly to flag instances whose
+    # REFERENCE answer is not determined to 1e-4 by its own float32 data (last-ulp cos/sin sensitivity)
+    fe, aux = O.safe_action(mode, tt(st), tt(ac), tt(mu), tt(sg), solver="exact", return_aux=True, gamma_b=20.0)
+    f64 = O.safe_action(mode, tt(st), tt(ac), tt(mu), tt(sg), solver="exact", assembly_dtype=torch.float64, gamma_b=20.0)
+    illcond = (np.abs(fe.numpy() - f64.numpy()).max(1) > 2e-5)
+    ok = keep & ~illcond
+    err = np.abs(out - fe.numpy()).max(1)
+    assert illcond.mean() < 1e-3 and (~keep).mean() < 1e-3
+    assert err[ok].max() < ACT_TOL, (err[ok].max(), int(np.argmax(err * ok)))
+    assert err.max() < 5e-3                                  # even the ill-conditioned ones stay close
+    # every normalised row satisfied by OUR (u, eps) on OUR normalised data
+    Gn, hn = aux["Gn"].numpy(), aux["hn"].numpy()
+    assert _row_slack(Gn[ok], hn[ok], x[ok]) > ROW_TOL
+    # duals: non-negative, complementary
+    assert lam.min() >= 0 and np.abs(lam * slack).max() < 1e-5 * max(1.0, lam.max())
+
+
+def test_trivial_instances_pass_through(uni):
+    env, layer = uni
+    B = 4096
+    st = np.tile(np.array([[2.9, -0.1, 0.3]], np.float32), (B, 1))     # far from every hazard
+    rng = np.random.default_rng(0)
+    ac = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+    z = np.zeros((B, 3), np.float32)
+    out, x, lam, slack, status, iters = _forward_with_aux(layer, st, ac, z, z)
+    assert (status == 0).all() and (iters == 0).all()
+    np.testing.assert_array_equal(out, ac)
+
+
+def test_nan_raises_like_reference(uni):
+    env, layer = uni
+    st = torch.tensor([[float("nan"), 0.0, 0.0]], device="cuda")
+    with pytest.raises(Exception, match="QP Failed to solve"):
+        layer.get_safe_action(st, torch.zeros(1, 2, device="cuda"), torch.zeros(1, 3, device="cuda"),
+                              torch.zeros(1, 3, device="cuda"))
+    with pytest.raises(AssertionError):
+        layer.get_cbf_qp_constraints(torch.zeros(3, device="cuda"), torch.zeros(2, device="cuda"),
+                                     torch.zeros(3, device="cuda"), torch.zeros(3, device="cuda"))
+
+
+def test_unknown_dynamics_mode_raises(S):
+    env = types.SimpleNamespace(dynamics_mode="Quadrotor", safe_action_space=types.SimpleNamespace(
+        low=np.zeros(2, np.float32), high=np.ones(2, np.float32)), action_space=types.SimpleNamespace(shape=(2,)))
+    with pytest.raises(Exception, match="Dynamics mode not supported."):
+        S.CBFQPLayer(env, _args())
+
+
+def test_inputs_not_mutated_and_cpu_tensors_accepted(uni, golden):
+    env, layer = uni
+    g = golden("unicycle_layer_b256.npz")
+    ins = [tt(g[k].copy()) for k in ("state", "action", "mean", "sigma")]      # CPU tensors
+    copies = [t.clone() for t in ins]
+    out = layer.get_safe_action(*ins)
+    assert out.device.type == "cpu"
+    for a, b in zip(ins, copies):
+        assert torch.equal(a, b)
+    assert np.abs(out.numpy() - g["safe_action"]).max() < ACT_TOL
+
+
+# ----------------------------------------------------------------------------------------------------- backward
+@pytest.mark.parametrize("which,name", [("uni", "unicycle_layer_b256.npz"), ("cars", "cars_layer_b512.npz")])
+def test_gradient_vs_golden(request, golden, which, name):
+    env, layer = request.getfixturevalue(which)
+    g = golden(name)
+    a = _cuda(g["action"]).requires_grad_(True)
+    out = layer.get_safe_action(_cuda(g["state"]), a, _cuda(g["mean"]), _cuda(g["sigma"]))
+    (out * _cuda(g["grad_w"])).sum().backward()
+    gr = a.grad.cpu().numpy()
+    ref = g["grad_action"]
+    rel = np.linalg.norm(gr - ref) / max(np.linalg.norm(ref), 1e-6)
+    assert rel < GRAD_TOL, rel
+    # per-instance: all but clamp-saturated / weakly active rows agree tightly
+    e = np.abs(gr - ref).max(1)
+    assert np.quantile(e, 0.95) < 1e-3 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("mode", ["Unicycle", "SimulatedCars"])
+def test_gradient_vs_oracle_autograd(request, mode):
+    env, layer = request.getfixturevalue("uni" if mode == "Unicycle" else "cars")
+    B = 512
+    if mode == "Unicycle":
+        st, ac, mu, sg = O.synth_unicycle(B, seed=31, hazard_frac=0.5)
+    else:
+        st, ac, mu, sg, _ = O.synth_cars(B, seed=31)
+    w = np.random.default_rng(5).normal(size=ac.shape).astype(np.float32)
+    a_ref = tt(ac).clone().requires_grad_(True)
+    fo = O.safe_action(mode, tt(st), a_ref, tt(mu), tt(sg), gamma_b=20.0)       # reference f32 assembly + qpth (f64)
+    (fo * tt(w)).sum().backward()
+    a = _cuda(ac).requires_grad_(True)
+    out = layer.get_safe_action(_cuda(st), a, _cuda(mu), _cuda(sg))
+    (out * _cuda(w)).sum().backward()
+    gr, ref = a.grad.cpu().numpy(), a_ref.grad.numpy()
+    rel = np.linalg.norm(gr - ref) / max(np.linalg.norm(ref), 1e-6)
+    assert rel < GRAD_TOL, rel
+    # no-grad path allocates no saved tensors and matches the grad path bit for bit
+    with torch.no_grad():
+        out2 = layer.get_safe_action(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg))
+    assert torch.equal(out2, out.detach())
+
+
+# ----------------------------------------------------------------------------------------------------- generic QP API
+@pytest.mark.parametrize("which,name", [("uni", "unicycle_layer_b256.npz"), ("cars", "cars_layer_b512.npz")])
+def test_solve_qp_api(request, golden, which, name):
+    env, layer = request.getfixturevalue(which)
+    g = golden(name)
+    nu = g["action"].shape[1]
+    Gs = _cuda(g["G"].copy())
+    x = layer.solve_qp(_cuda(g["P"]), _cuda(g["q"]), Gs, _cuda(g["h"]))
+    assert x.shape == (g["G"].shape[0], nu) and x.dtype == torch.float32
+    assert np.abs(x.cpu().numpy() - g["x_exact"][:, :nu]).max() < ACT_TOL
+    # like the reference, Gs was normalised in place (diff_cbf_qp.py:105)
+    assert np.abs(Gs.cpu().numpy() - g["Gn"]).max() < 1e-6
+    # cbf_layer with gradients w.r.t. G and h vs the restated qpth backward
+    from oracle import qpth_pdipm
+    Gn = tt(g["Gn"]).double().requires_grad_(True); hn = tt(g["hn"]).double().requires_grad_(True)
+    P, q = tt(g["P"]).double(), tt(g["q"]).double()
+    e = torch.empty(0, dtype=torch.float64)
+    xr = qpth_pdipm.QPFunction(eps=1e-10, notImprovedLim=10, maxIter=100)(P, q, Gn, hn, e, e)
+    w = torch.from_numpy(np.random.default_rng(9).normal(size=tuple(xr.shape)))
+    (xr * w).sum().backward()
+    Gc = _cuda(g["Gn"]).double().requires_grad_(True); hc = _cuda(g["hn"]).double().requires_grad_(True)
+    xc = layer.cbf_layer(P.cuda(), q.cuda(), Gc, hc)
+    (xc.double() * w.cuda()).sum().backward()
+    assert np.abs(xc.detach().cpu().numpy() - xr.detach().numpy()).max() < 1e-5
+    for mine, ref in ((hc.grad.cpu(), hn.grad), (Gc.grad.cpu(), Gn.grad)):
+        rel = (mine - ref).norm() / ref.norm().clamp_min(1e-9)
+        assert rel < GRAD_TOL, rel
+
+
+# ----------------------------------------------------------------------------------------------------- dynamics
+def test_unicycle_env_f64_vs_golden_trajectory(S, golden):
+    g = golden("unicycle_env_traj.npz")
+    env = S.UnicycleEnv()
+    obs = env.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (7,)
+    np.testing.assert_allclose(obs, g["obs0"], rtol=0, atol=1e-14)
+    for k in range(len(g["reward"])):
+        obs, r, d, info = env.step(g["actions"][k])
+        assert isinstance(r, float) and isinstance(d, bool) and isinstance(info, dict)
+        np.testing.assert_allclose(obs, g["obs"][k], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(env.state, g["state"][k], rtol=1e-12, atol=1e-12)
+        assert abs(r - g["reward"][k]) < 1e-11
+        assert d == bool(g["done"][k])
+        assert ("goal_met" in info) == bool(g["goal_met"][k])
+        assert ("cost" in info) == (g["cost"][k] > 0) and abs(info.get("cost", 0.0) - g["cost"][k]) < 1e-15
+    assert env.episode_step == len(g["reward"])
+
+
+def test_cars_env_f64_vs_golden_trajectory(S, golden):
+    g = golden("cars_env_traj.npz")
+    np.random.seed(0)
+    env = S.SimulatedCarsEnv()
+    np.random.seed(0)
+    obs = env.reset()
+    np.testing.assert_allclose(obs, g["obs0"], rtol=0, atol=1e-15)
+    for k in range(len(g["reward"])):
+        obs, r, d, info = env.step(g["actions"][k])
+        np.testing.assert_allclose(obs, g["obs"][k], rtol=1e-12, atol=1e-12)
+        assert abs(r - g["reward"][k]) < 1e-15 and d == bool(g["done"][k])
+        assert abs(info["cost"] - g["cost"][k]) < 1e-15 and info["goal_met"] is False
+    assert abs(env.t - g["t"][-1]) < 1e-12
+
+
+def test_env_f32_single_step_vs_oracle(S):
+    B = 65536
+    rng = np.random.default_rng(77)
+    # Unicycle
+    env = S.UnicycleEnv(num_envs=B)
+    st = np.stack([rng.uniform(-3, 3, B), rng.uniform(-3, 3, B), rng.uniform(-np.pi, np.pi, B)], 1).astype(np.float32)
+    env.state = _cuda(st)
+    a = rng.uniform(-1.5, 1.5, (B, 2)).astype(np.float32)
+    last = O.unicycle_goal_dist(st.astype(np.float64))
+    ref = O.unicycle_env_step(st.astype(np.float64), a.astype(np.float64), np.zeros(B, np.int64), last)
+    obs, rew, done, info = env.step(_cuda(a))
+    new = env.state.cpu().numpy()
+    scale = np.maximum(np.abs(ref["state"]), 1.0)
+    assert (np.abs(new - ref["state"]) / scale).max() < DYN_RTOL
+    assert (np.abs(obs.cpu().numpy() - ref["obs"])).max() < 2e-6
+    # reward is a difference of two O(5) distances: float32 carries it to ~1e-6 absolute
+    assert np.abs(rew.cpu().numpy() - ref["reward"]).max() < 2e-6
+    near_goal = np.abs(ref["last_goal_dist"] - 0.3) < 1e-5
+    assert ((done.cpu().numpy() == ref["done"]) | near_goal).all()
+    d2 = ((ref["state"][:, None, :2] - O.UNICYCLE["hazards_locations"][None]) ** 2).sum(2)
+    near_hz = (np.abs(d2 - 0.36) < 1e-5).any(1)
+    assert ((np.abs(info["cost"].cpu().numpy() - ref["cost"]) < 1e-7) | near_hz).all()
+    # Cars
+    envc = S.SimulatedCarsEnv(num_envs=B)
+    stc, acc, _, _, t = O.synth_cars(B, seed=3)
+    envc.state = _cuda(stc)
+    envc._t.copy_(_cuda(t))
+    refc = O.cars_env_step(stc.astype(np.float64), acc.astype(np.float64), t.astype(np.float64), np.zeros(B, np.int64))
+    obs, rew, done, info = envc.step(_cuda(acc))
+    keep = O.cars_threshold_margin(stc) > 1e-4
+    newc = envc.state.cpu().numpy()
+    assert (np.abs(newc - refc["state"])[keep] / np.maximum(np.abs(refc["state"][keep]), 1.0)).max() < DYN_RTOL
+    assert (np.abs(obs.cpu().numpy() - refc["obs"])[keep] / np.maximum(np.abs(refc["obs"][keep]), 1.0)).max() < DYN_RTOL
+    assert np.abs(rew.cpu().numpy() - refc["reward"]).max() < 1e-8
+
+
+def test_predict_next_state_vs_golden(S, golden):
+    g = golden("dynamics_prior.npz")
+    for mode, envc, k in (("Unicycle", S.UnicycleEnv, "unicycle"), ("SimulatedCars", S.SimulatedCarsEnv, "simulatedcars")):
+        dm = S.DynamicsModel(envc(), _args())
+        t = g.get(k + "_t")
+        nxt, std, tn = dm.predict_next_state(g[k + "_state"], g[k + "_action"], t_batch=t)
+        assert isinstance(nxt, np.ndarray) and nxt.dtype == np.float64
+        np.testing.assert_allclose(nxt, g[k + "_next"], rtol=1e-13, atol=1e-12)
+        np.testing.assert_allclose(std, g[k + "_std_dt"], atol=1e-15)
+        if t is not None:
+            np.testing.assert_allclose(tn, g[k + "_t_next"])
+        np.testing.assert_allclose(dm.get_obs(g[k + "_state"]), g[k + "_obs"], atol=1e-14)
+        np.testing.assert_allclose(dm.get_state(g[k + "_obs"]), g[k + "_state_from_obs"], atol=1e-12)
+        m, s = dm.predict_disturbance(g[k + "_state"])
+        np.testing.assert_allclose(m, g[k + "_dist_mean"]); np.testing.assert_allclose(s, g[k + "_dist_std"])
+        # float32 device tensors stay on the device and meet the 1e-6 relative bar
+        st32 = _cuda(g[k + "_state"].astype(np.float32)); u32 = _cuda(g[k + "_action"].astype(np.float32))
+        t32 = None if t is None else _cuda(t.astype(np.float32))
+        n32, s32, _ = dm.predict_next_state(st32, u32, t_batch=t32)
+        assert n32.is_cuda and n32.dtype == torch.float32
+        keep = np.ones(len(nxt), bool) if t is None else O.cars_threshold_margin(g[k + "_state"]) > 1e-4
+        rel = np.abs(n32.cpu().numpy() - g[k + "_next"]) / np.maximum(np.abs(g[k + "_next"]), 1.0)
+        assert rel[keep].max() < 2 * DYN_RTOL
+
+
+# ----------------------------------------------------------------------------------------------------- fused step
+def test_fused_safe_step_equals_layer_then_env(S, uni, cars):
+    B = 32768
+    env_u, layer_u = uni
+    st, ac, mu, sg = O.synth_unicycle(B, seed=9)
+    a = S.UnicycleEnv(num_envs=B); b = S.UnicycleEnv(num_envs=B)
+    a.state = _cuda(st); b.state = _cuda(st)
+    us = layer_u.get_safe_action(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg))
+    o1, r1, d1, i1 = a.step(us)
+    us2, o2, r2, d2, i2 = b.safe_step(layer_u, _cuda(ac), _cuda(mu), _cuda(sg))
+    assert torch.equal(us, us2) and torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2.bool())
+    assert torch.equal(a.state, b.state) and torch.equal(i1["cost"], i2["cost"])
+    env_c, layer_c = cars
+    stc, acc, muc, sgc, t = O.synth_cars(B, seed=9)
+    a = S.SimulatedCarsEnv(num_envs=B); b = S.SimulatedCarsEnv(num_envs=B)
+    for e in (a, b):
+        e.state = _cuda(stc); e._t.copy_(_cuda(t))
+    us = layer_c.get_safe_action(_cuda(stc), _cuda(acc), _cuda(muc), _cuda(sgc))
+    o1, r1, d1, i1 = a.step(us)
+    us2, o2, r2, d2, i2 = b.safe_step(layer_c, _cuda(acc), _cuda(sgc))
+    assert torch.equal(us, us2) and torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(a.state, b.state)
+
+
+# ----------------------------------------------------------------------------------------------------- full size
+def test_full_size_properties(uni):
+    """BASELINE config 4 size (1M instances): size-independent properties instead of an oracle run."""
+    env, layer = uni
+    B = 1 << 20
+    st, ac, mu, sg = O.synth_unicycle(B, seed=12345)
+    out, x, lam, slack, status, iters = _forward_with_aux(layer, st, ac, mu, sg)
+    assert not np.isnan(out).any() and (status <= 2).all()
+    assert np.abs(out).max() <= 2.5
+    # slack the kernel certified is the row residual of its own normalised data: every row satisfied
+    assert slack.min() > ROW_TOL and lam.min() >= 0
+    # trivial instances are passed through untouched
+    triv = status == 0
+    np.testing.assert_array_equal(out[triv], ac[triv])
+    # permutation equivariance + determinism (no cross-instance coupling, unlike qpth's batch-global stop)
+    perm = np.random.default_rng(1).permutation(B)
+    out_p = _forward_with_aux(layer, st[perm], ac[perm], mu[perm], sg[perm])[0]
+    np.testing.assert_array_equal(out_p, out[perm])
+    # spot-check 4096 of them against the exact oracle
+    idx = np.random.default_rng(2).choice(B, 4096, replace=False)
+    fe = O.safe_action("Unicycle", tt(st[idx]), tt(ac[idx]), tt(mu[idx]), tt(sg[idx]), solver="exact", gamma_b=20.0)
+    f64 = O.safe_action("Unicycle", tt(st[idx]), tt(ac[idx]), tt(mu[idx]), tt(sg[idx]), solver="exact",
+                        assembly_dtype=torch.float64, gamma_b=20.0)
+    ok = np.abs(fe.numpy() - f64.numpy()).max(1) <= 2e-5
+    assert np.abs(out[idx] - fe.numpy())[ok].max() < ACT_TOL
+
+
+def test_host_buffer_entry_matches_device_entry(S, uni, cars):
+    import ctypes as C
+    from sac_rcbf_b200 import _lib
+    lib = _lib.load()
+    for (env, layer), synth in ((uni, O.synth_unicycle), (cars, O.synth_cars)):
+        B = 100003     # ragged on purpose
+        arrs = synth(B, seed=4)
+        st, ac, mu, sg = arrs[:4]
+        ref = layer.get_safe_action(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg)).cpu().numpy()
+        pin = [torch.from_numpy(a).pin_memory() for a in (st, ac, mu, sg)]
+        out = torch.empty(ref.shape, dtype=torch.float32).pin_memory()
+        nf = C.c_int32(-1)
+        if env.dynamics_mode == "Unicycle":
+            rc = lib.rcbf_unicycle_safe_action_host(_lib.ptr(pin[0]), _lib.ptr(pin[1]), _lib.ptr(pin[2]), _lib.ptr(pin[3]),
+                                                    B, layer._params(), _lib.ptr(out), C.byref(nf), 0, 7)
+        else:
+            rc = lib.rcbf_cars_safe_action_host(_lib.ptr(pin[0]), _lib.ptr(pin[1]), _lib.ptr(pin[3]), B, layer._params(),
+                                                _lib.ptr(out), C.byref(nf), 0, 7)
+        assert rc == 0 and nf.value == 0
+        np.testing.assert_array_equal(out.numpy(), ref)
+
+
+# ----------------------------------------------------------------------------------------------------- numpy layer shim
+def test_cascade_layer_vs_oracle(S, golden):
+    g = golden("cascade_layer.npz")
+    env = S.UnicycleEnv()
+    lay = S.CascadeCBFLayer(env, gamma_b=100, k_d=1.5, l_p=0.03)
+    for i in range(g["state"].shape[0]):
+        P, q, G, h = lay.get_cbf_qp_constraints(g["action"][i], g["state"][i], g["mean"][i], g["sigma"][i])
+        n = np.maximum(np.abs(g["G"][i]).max(1), np.abs(g["h"][i]))
+        assert (np.abs(G - g["G"][i]) / n[:, None]).max() < 2e-6 and (np.abs(h - g["h"][i]) / n).max() < 2e-6
+        np.testing.assert_allclose(P, g["P"][i])
+        u = lay.get_u_safe(g["action"][i], g["state"][i], g["mean"][i], g["sigma"][i])
+        ue, _ = O.cascade_u_safe("Unicycle", g["action"][i], g["state"][i], g["mean"][i], g["sigma"][i])
+        assert u.shape == (2,) and np.abs(u - ue).max() < 2e-3 * max(1.0, np.abs(ue).max())
+    envc = S.SimulatedCarsEnv()
+    layc = S.CascadeCBFLayer(envc, gamma_b=100, k_d=1.5)
+    for i in range(g["cars_state"].shape[0]):
+        u = layc.get_u_safe(g["cars_action"][i], g["cars_state"][i], np.zeros(10), g["cars_sigma"][i])
+        ue, _ = O.cascade_u_safe("SimulatedCars", g["cars_action"][i], g["cars_state"][i], np.zeros(10), g["cars_sigma"][i])
+        assert u.shape == (1,) and np.abs(u - ue).max() < 1e-3 * max(1.0, np.abs(ue).max())
