@@ -36,7 +36,9 @@ UNI_BYTES_PER_STEP = 52 + 66
 # flop model of SURVEY.md 8(d): F_asm + (K + 1/2) F_iter + F_dyn, F_iter(3,9) = 918, F_asm = 260, F_dyn = 110;
 # K = executed interior-point iterations (0 for instances certified trivially feasible: those skip the init solve too)
 F_ITER_UNI, F_ASM_UNI, F_DYN_UNI = 918.0, 260.0, 110.0
-CERT_FLOPS_UNI = 250.0  # one float64 KKT certificate attempt, counted per executed iteration
+CERT_FLOPS_UNI = 250.0  # one float64 KKT certificate
+GREEDY_ROUND_FLOPS_UNI = 170.0  # one presolve round: 9 slacks + worst-row pick + <=3x3 Gram/Cholesky + y
+GREEDY_SETUP_FLOPS_UNI = 60.0   # 9 row norms (rsqrt) + column scaling
 
 
 def parse():
@@ -198,6 +200,69 @@ def fma_probe_tflops(lib, _lib, device):
     return 2.0 * 8 * iters * blocks * threads / (best * 1e-3) / 1e12
 
 
+def _time_calls(fn, iters, device):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize(device)
+    return e0.elapsed_time(e1) / iters
+
+
+def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
+    """Other BASELINE.json configs, reported next to the headline line (rank 0 only, a few launches each)."""
+    out = {}
+    # (a) same workload, interior-point-only solver mode (north_star's PDIPM on every non-trivial QP)
+    layer.solver = "pdipm"
+    env._counters.zero_()
+    ms = _time_calls(lambda: env.safe_step(layer, *batches[0]), 5, device)
+    cc = env._counters.cpu().tolist()
+    layer.solver = "presolve"
+    tot = 8.0 * n
+    out["pdipm_mode"] = {"value": n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
+                         "ipm_iters_mean": cc[4] / tot, "f64_passes": cc[2], "uncertified": cc[1],
+                         "note": "every non-trivial QP through the float32 Mehrotra PDIPM + float64 certificate"}
+    # (b) QP solves/s: get_safe_action only (assembly + solve + clamp), Unicycle and SimulatedCars (config 5 sizes)
+    st = env._state4[:, :3].contiguous()
+    u, mu, sg = batches[0]
+    ms = _time_calls(lambda: layer._forward_raw(st, u, mu, sg), 5, device)
+    out["qp_solves_unicycle"] = {"value": n / (ms * 1e-3), "unit": "QP/s", "instances": n, "ms": ms}
+    from oracle import rcbf_oracle as O
+    nc = 1 << 22
+    stc, acc, muc, sgc, tc = (torch.from_numpy(a).to(device) for a in O.synth_cars(nc, seed=12345))
+    envc = S.SimulatedCarsEnv(num_envs=nc, device=device)
+    layc = S.CBFQPLayer(envc, ns, gamma_b=20, k_d=3.0, l_p=0.03)
+    layc.check_nan = False
+    ms = _time_calls(lambda: layc._forward_raw(stc, acc, muc, sgc), 5, device)
+    out["qp_solves_cars"] = {"value": nc / (ms * 1e-3), "unit": "QP/s", "instances": nc, "ms": ms}
+    envc.state = stc
+    envc._t.copy_(tc)
+    ms = _time_calls(lambda: envc.safe_step(layc, acc, sgc), 5, device)
+    out["cars_safe_step"] = {"value": nc / (ms * 1e-3), "unit": "env-steps/s", "instances": nc, "ms": ms,
+                             "bytes_per_unit": 40 + 4 + 4 + 4 + 40 + 40 + 4 + 4 + 40 + 4 + 1 + 4 + 4}
+    # (c) config 2/3 shapes: B=512 latency of the drop-in calls (launch-bound)
+    b = 512
+    s5, a5, m5, g5 = st[:b].clone(), u[:b].clone(), mu[:b].clone(), sg[:b].clone()
+    layer.check_nan = False
+    ms = _time_calls(lambda: layer.get_safe_action(s5, a5, m5, g5), 50, device)
+    out["config_unicycle_b512_fwd_us"] = 1e3 * ms
+
+    def fwd_bwd():
+        a = a5.clone().requires_grad_(True)
+        layer.get_safe_action(s5, a, m5, g5).sum().backward()
+
+    ms = _time_calls(fwd_bwd, 50, device)
+    out["config3_unicycle_b512_fwd_bwd_us"] = 1e3 * ms
+    ms = _time_calls(lambda: layc.get_safe_action(stc[:b], acc[:b], muc[:b], sgc[:b]), 50, device)
+    out["config2_cars_b512_fwd_us"] = 1e3 * ms
+    layer.check_nan = True
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -340,23 +405,34 @@ def main():
         hbm_peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp32_peak = fma_probe_tflops(lib, _lib, device)
         gbs = UNI_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
-        flops_per_step = F_ASM_UNI + F_DYN_UNI + nontrivial * 0.5 * F_ITER_UNI + iters_mean * (F_ITER_UNI + CERT_FLOPS_UNI)
+        # default solver mode: assembly + env step for everyone; setup + certificate per non-trivial instance; one
+        # presolve round per counted round (counters[4]); fallback interior point: counters[5], [6]
+        fb_frac, fb_iters = c[5] / total_steps, c[6] / total_steps
+        flops_per_step = (F_ASM_UNI + F_DYN_UNI + nontrivial * (GREEDY_SETUP_FLOPS_UNI + CERT_FLOPS_UNI)
+                          + iters_mean * GREEDY_ROUND_FLOPS_UNI + fb_frac * 0.5 * F_ITER_UNI
+                          + fb_iters * (F_ITER_UNI + CERT_FLOPS_UNI))
         tfl = flops_per_step * n / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                     "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                     "kernel": "k_unicycle_safe_step", "kernel_ms": kernel_ms, "bytes_per_unit": UNI_BYTES_PER_STEP,
                     "fp32": {"achieved_tflops": tfl, "peak_tflops": fp32_peak, "frac": tfl / fp32_peak,
                              "peak_source": "rcbf_fp32_fma_probe measured in this run",
-                             "flops_per_unit": flops_per_step, "ipm_iters_mean": iters_mean,
+                             "flops_per_unit": flops_per_step, "presolve_rounds_mean": iters_mean,
+                             "fallback_frac": fb_frac,
                              "nontrivial_frac": nontrivial},
                     "note": "path is FP32-pipe bound (SURVEY 8d): the hbm fraction is reported per contract, the fp32 "
                             "fraction is the binding one"}
-        v, done_n, el = time_cpu_reference(args.cpu_seconds)
-        cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
-                        "sample": "%d Unicycle instances in batches of 512 over %.1f s (oracle: reference-order f32 "
-                                  "assembly + restated qpth f64 + numpy f64 env step)" % (done_n, el)}
-        extra["solver"] = {"nan": c[0], "uncertified": c[1], "f64_passes": c[2], "trivial": c[3],
-                           "ipm_iters_mean": iters_mean}
+        if args.cpu_seconds > 0:
+            v, done_n, el = time_cpu_reference(args.cpu_seconds)
+            cpu_baseline = {"value": v, "unit": "env-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": "%d Unicycle instances in batches of 512 over %.1f s (oracle: reference-order "
+                                      "f32 assembly + restated qpth f64 + numpy f64 env step)" % (done_n, el)}
+        else:
+            cpu_baseline = None
+        extra["solver"] = {"mode": layer.solver, "nan": c[0], "uncertified": c[1], "f64_passes": c[2], "trivial": c[3],
+                           "presolve_rounds_mean": iters_mean, "fallback": c[5], "fallback_ipm_iters": c[6]}
+        if not args.no_extra:
+            extra.update(secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns))
         out = {
             "metric": "safe env-steps/sec (dynamics+RCBF-QP)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -366,7 +442,7 @@ def main():
                        "l2": "inputs larger than L2 (%.0f MB read per step per GPU, 2 rotating input sets)"
                              % (52 * n / 1e6), "gamma_b": 20, "parallelism": "instances sharded by rank, no collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": args.steps, "extra": extra,
+            "gpu_launches": 2 * args.steps, "extra": extra,
         }
         print(json.dumps(out))
     if dist is not None:

@@ -49,6 +49,8 @@ typedef struct {
   int abs_sigma_map;  /* 1: |g_p| (diff_cbf_qp.py:241); 0: signed (cbf_qp.py:119) */
   float u_min[2], u_max[2];
   float p_diag[3];
+  int solver_mode; /* 0: greedy active-set presolve + KKT certificate, interior point as fallback (default);
+                      1: "pdipm": every non-trivial QP goes through the primal-dual interior point */
 } rcbf_unicycle_params;
 
 typedef struct {
@@ -59,6 +61,7 @@ typedef struct {
   float u_min, u_max;
   float p_diag[2];
   float slack_coeff;
+  int solver_mode; /* as in rcbf_unicycle_params */
 } rcbf_cars_params;
 
 typedef struct {
@@ -76,8 +79,10 @@ typedef struct {
   int auto_reset;
 } rcbf_cars_env_params;
 
-/* counters[0]=#NaN  [1]=#uncertified(max-iter)  [2]=#float64 straggler passes  [3]=#trivial  [4]=sum of IPM iterations
- * [5..7] reserved.  Accumulated with atomics; zero them before the call.  Nullable. */
+/* counters[0]=#NaN  [1]=#uncertified(max-iter)  [2]=#float64 interior-point passes  [3]=#trivial
+ * [4]=sum over instances of pass-1 iterations (presolve rounds in mode 0, interior-point iterations in mode 1)
+ * [5]=#instances handed to the fallback pass  [6]=sum of fallback-pass interior-point iterations  [7] reserved.
+ * Accumulated with atomics; zero them before the call.  Nullable. */
 typedef unsigned long long rcbf_counters_t;
 
 /* ---- constraint assembly (raw P,q are constants: P = diag(p_diag), q = 0) ------------------------------------- */

@@ -17,6 +17,7 @@ class UnicycleParams(C.Structure):
         ("u_min", C.c_float * 2),
         ("u_max", C.c_float * 2),
         ("p_diag", C.c_float * 3),
+        ("solver_mode", C.c_int),
     ]
 
 
@@ -32,6 +33,7 @@ class CarsParams(C.Structure):
         ("u_max", C.c_float),
         ("p_diag", C.c_float * 2),
         ("slack_coeff", C.c_float),
+        ("solver_mode", C.c_int),
     ]
 
 
@@ -74,7 +76,8 @@ def _check_hazards(hazards_locations):
 
 
 def unicycle_params(hazards_locations=None, hazards_radius=0.6, gamma_b=100.0, l_p=0.03, u_min=(-2.5, -2.5),
-                    u_max=(2.5, 2.5), p_diag=(1.0, 1e-2, 1e5), sigma_scale=1.0, abs_sigma_map=True):
+                    u_max=(2.5, 2.5), p_diag=(1.0, 1e-2, 1e5), sigma_scale=1.0, abs_sigma_map=True,
+                    solver_mode=0):
     """Defaults = envs/unicycle_env.py:21-26 and rcbf_sac/diff_cbf_qp.py:12,207,265."""
     hz = _check_hazards(hazards_locations)
     p = UnicycleParams()
@@ -86,11 +89,12 @@ def unicycle_params(hazards_locations=None, hazards_radius=0.6, gamma_b=100.0, l
         p.u_min[c], p.u_max[c] = float(u_min[c]), float(u_max[c])
     for j in range(3):
         p.p_diag[j] = float(p_diag[j])
+    p.solver_mode = int(solver_mode)
     return p
 
 
 def cars_params(gamma_b=100.0, kp=4.0, k_brake=20.0, u_min=-10.0, u_max=10.0, p_diag=(0.1, 10.0), sigma_scale=1.0,
-                slack_coeff=200.0):
+                slack_coeff=200.0, solver_mode=0):
     """Defaults = envs/simulated_cars_env.py:18-26 and rcbf_sac/diff_cbf_qp.py:272,352,356."""
     p = CarsParams()
     p.gamma_2, p.gamma_sq = gamma_b + gamma_b, gamma_b * gamma_b  # python-double scalars of diff_cbf_qp.py:348
@@ -98,6 +102,7 @@ def cars_params(gamma_b=100.0, kp=4.0, k_brake=20.0, u_min=-10.0, u_max=10.0, p_
     p.u_min, p.u_max = float(u_min), float(u_max)
     p.p_diag[0], p.p_diag[1] = float(p_diag[0]), float(p_diag[1])
     p.slack_coeff = slack_coeff
+    p.solver_mode = int(solver_mode)
     return p
 
 

@@ -46,16 +46,17 @@ class CascadeCBFLayer:
             if mode == 'Unicycle':
                 out = torch.empty((1, 2), dtype=torch.float32, device=dev)
                 x = torch.empty((1, 3), dtype=torch.float32, device=dev)
-                rc = self._lib.rcbf_unicycle_safe_action(_lib.ptr(self._dev(s, 3)), _lib.ptr(self._dev(u_nom, 2)),
-                                                         _lib.ptr(self._dev(mean_pred, 3)), _lib.ptr(self._dev(sigma, 3)),
-                                                         1, p, _lib.ptr(out), _lib.ptr(x), None, None, None, None, None,
-                                                         _lib.stream_ptr(dev))
+                ts = (self._dev(s, 3), self._dev(u_nom, 2), self._dev(mean_pred, 3), self._dev(sigma, 3))  # keep alive
+                rc = self._lib.rcbf_unicycle_safe_action(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]),
+                                                         _lib.ptr(ts[3]), 1, p, _lib.ptr(out), _lib.ptr(x), None, None,
+                                                         None, None, None, _lib.stream_ptr(dev))
             else:
                 out = torch.empty((1, 1), dtype=torch.float32, device=dev)
                 x = torch.empty((1, 2), dtype=torch.float32, device=dev)
-                rc = self._lib.rcbf_cars_safe_action(_lib.ptr(self._dev(s, 10)), _lib.ptr(self._dev(u_nom, 1)),
-                                                     _lib.ptr(self._dev(sigma, 10)), 1, p, _lib.ptr(out), _lib.ptr(x),
-                                                     None, None, None, None, None, _lib.stream_ptr(dev))
+                ts = (self._dev(s, 10), self._dev(u_nom, 1), self._dev(sigma, 10))  # keep alive
+                rc = self._lib.rcbf_cars_safe_action(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]), 1, p,
+                                                     _lib.ptr(out), _lib.ptr(x), None, None, None, None, None,
+                                                     _lib.stream_ptr(dev))
         _lib.check(rc, "rcbf_safe_action")
         xs = x[0].double().cpu().numpy()
         if np.any(np.isnan(xs)):
@@ -73,17 +74,16 @@ class CascadeCBFLayer:
             if mode == 'Unicycle':
                 G = torch.empty((1, 9, 3), dtype=torch.float32, device=dev)
                 h = torch.empty((1, 9), dtype=torch.float32, device=dev)
-                rc = self._lib.rcbf_unicycle_assemble(_lib.ptr(self._dev(state, 3)), _lib.ptr(self._dev(u_nom, 2)),
-                                                      _lib.ptr(self._dev(mean_pred, 3)),
-                                                      _lib.ptr(self._dev(sigma_pred, 3)), 1, p, _lib.ptr(G), _lib.ptr(h),
-                                                      _lib.stream_ptr(dev))
+                ts = (self._dev(state, 3), self._dev(u_nom, 2), self._dev(mean_pred, 3), self._dev(sigma_pred, 3))
+                rc = self._lib.rcbf_unicycle_assemble(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]), _lib.ptr(ts[3]),
+                                                      1, p, _lib.ptr(G), _lib.ptr(h), _lib.stream_ptr(dev))
                 P = np.diag([1.e1, 1.e-4, 1e7])
             else:
                 G = torch.empty((1, 4, 2), dtype=torch.float32, device=dev)
                 h = torch.empty((1, 4), dtype=torch.float32, device=dev)
-                rc = self._lib.rcbf_cars_assemble(_lib.ptr(self._dev(state, 10)), _lib.ptr(self._dev(u_nom, 1)),
-                                                  _lib.ptr(self._dev(sigma_pred, 10)), 1, p, _lib.ptr(G), _lib.ptr(h),
-                                                  _lib.stream_ptr(dev))
+                ts = (self._dev(state, 10), self._dev(u_nom, 1), self._dev(sigma_pred, 10))
+                rc = self._lib.rcbf_cars_assemble(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]), 1, p, _lib.ptr(G),
+                                                  _lib.ptr(h), _lib.stream_ptr(dev))
                 P = np.diag([0.1, 1e1])
         _lib.check(rc, "rcbf_assemble")
         return P, np.zeros(P.shape[0]), G[0].double().cpu().numpy(), h[0].double().cpu().numpy()

@@ -230,6 +230,100 @@ RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], 
   return ok;
 }
 
+// --- greedy dual active-set presolve -----------------------------------------------------------------------
+// Starting from y = 0 (the unconstrained optimum), repeatedly add the most violated row (violation measured in
+// units of the row norm) and re-solve the equality-constrained least-norm problem on the chosen rows, at most NZ
+// times.  This is Goldfarb-Idnani without constraint dropping: it stops with `false` as soon as a multiplier turns
+// negative (a drop would be needed) or NZ rows do not make the point feasible -- those instances go to the
+// interior-point solver.  The returned mask is only a GUESS; the float64 certificate decides.
+template <int NZ, int M>
+RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& mask_out, int& rounds) {
+  float inv_norm[M];
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    float acc = 0.f;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) acc = fmaf(P.A[i][j], P.A[i][j], acc);
+#if defined(__CUDA_ARCH__)
+    inv_norm[i] = rsqrtf(acc);
+#else
+    inv_norm[i] = 1.0f / sqrtf(acc);
+#endif
+  }
+  float y[NZ], R[NZ][NZ], rb[NZ];
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    y[j] = 0.f;
+    rb[j] = 0.f;
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) R[j][k] = 0.f;
+  }
+  uint32_t mask = 0;
+  bool ok = true, feasible = false;
+  int r = 0;
+  RCBF_UNROLL
+  for (; r <= NZ; ++r) {
+    // most violated row at the current y
+    float worst = -1e-6f;
+    int wi = -1;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      float acc = P.b[i];
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = fmaf(-P.A[i][j], y[j], acc);
+      const float v = acc * inv_norm[i];
+      const bool take = !((mask >> i) & 1u) && (v < worst);
+      worst = take ? v : worst;
+      wi = take ? i : wi;
+    }
+    if (wi < 0) {
+      feasible = true;
+      break;
+    }
+    if (r == NZ) break;  // NZ rows and still infeasible
+    mask |= 1u << wi;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      const bool put = (i == wi);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) R[r][j] = put ? P.A[i][j] : R[r][j];
+      rb[r] = put ? P.b[i] : rb[r];
+    }
+    // (R R') lam = -rb on the first r+1 rows (unit diagonal on the unused slots)
+    float Gm[NZ][NZ];
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) {
+      RCBF_UNROLL
+      for (int l = 0; l <= k; ++l) {
+        float acc = 0.f;
+        RCBF_UNROLL
+        for (int j = 0; j < NZ; ++j) acc = fmaf(R[k][j], R[l][j], acc);
+        Gm[k][l] = acc;
+      }
+      Gm[k][k] = (k <= r) ? Gm[k][k] : 1.f;
+    }
+    Chol<float, NZ> ch;
+    ch.factor(Gm);
+    float nrb[NZ], lk[NZ];
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) nrb[k] = -rb[k];
+    ch.solve(nrb, lk);
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -1e-6f);  // NaN (dependent rows) -> false
+    if (!ok) break;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      float acc = 0.f;
+      RCBF_UNROLL
+      for (int k = 0; k < NZ; ++k) acc = fmaf(-R[k][j], lk[k], acc);
+      y[j] = acc;
+    }
+  }
+  mask_out = mask;
+  rounds = r;
+  return ok && feasible;
+}
+
 template <typename T> struct LnpTol;
 template <> struct LnpTol<float> {
   static constexpr int kMaxIter = 16;
@@ -671,41 +765,114 @@ struct NormCert {
 constexpr double kTolSlack = 1e-9;
 constexpr double kTolDual = 1e-9;
 
-// Solve the normalised QP of one instance.  Main path: float32 interior point + float64 certificate; if that does
-// not certify, the float64 interior point runs (rare "straggler" lanes).  x = P^-1/2 y.
+#define RCBF_PENDING 5  /* internal: not certified by the fast path, queued for the interior-point pass */
+
 template <int NZ, int M>
-RCBF_HD void solve_normalised(const Normalised<NZ, M>& nrm, const float p_diag[NZ], double x[NZ], double lam[M],
-                              double s[M], int& status, int& iters) {
-  double pisd[NZ];
-  float pisf[NZ];
+struct NormSolution {
+  double x[NZ], lam[M], s[M];
+  int status, iters;
+};
+
+template <int NZ, int M>
+RCBF_HD void pis_of(const float p_diag[NZ], double pisd[NZ], float pisf[NZ]) {
   RCBF_UNROLL
   for (int j = 0; j < NZ; ++j) {
     pisd[j] = 1.0 / sqrt((double)p_diag[j]);
     pisf[j] = (float)pisd[j];
   }
-  LnpSolution<double, NZ, M> sol;
+}
+
+// Fast path of one normalised QP: trivial test, greedy active-set presolve (float32) and the float64 KKT
+// certificate.  kPresolve = false skips the presolve and runs the float32 interior point inline instead
+// ("pdipm" solver mode).  Leaves status = RCBF_PENDING when it cannot certify: the fallback pass takes over.
+template <int NZ, int M, bool kPresolve>
+RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_diag[NZ], NormSolution<NZ, M>& o) {
+  double pisd[NZ];
+  float pisf[NZ];
+  pis_of<NZ, M>(p_diag, pisd, pisf);
+  bool triv = true, nan = false;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    triv = triv && (nrm.hn[i] >= 0.f);
+    nan = nan || (nrm.hn[i] != nrm.hn[i]);
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) nan = nan || (nrm.Gn[i][j] != nrm.Gn[i][j]);
+  }
+  if (triv || nan) {
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) o.x[j] = nan ? (double)NAN : 0.0;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      o.lam[i] = 0.0;
+      o.s[i] = (double)nrm.hn[i];
+    }
+    o.status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
+    o.iters = 0;
+    return;
+  }
   const NormCert<NZ, M> cp{nrm, pisd};
-  {
+  LnpProblem<float, NZ, M> Pf;
+  to_lnp<float, NZ, M>(nrm, pisf, Pf);
+  double y[NZ];
+  if (kPresolve) {
+    uint32_t mask;
+    int rounds;
+    const bool guess = lnp_greedy_active_set<NZ, M>(Pf, mask, rounds);
+    o.status = RCBF_PENDING;
+    o.iters = rounds;
+    if (guess && lnp_certify<double, NormCert<NZ, M>, NZ, M>(cp, mask, kTolSlack, kTolDual, y, o.lam, o.s)) {
+      o.status = RCBF_OK_CERTIFIED;
+    }
+  } else {
+    LnpSolution<double, NZ, M> sol;
+    lnp_solve<float, double, NormCert<NZ, M>, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
+    o.status = (sol.status >= RCBF_MAXITER) ? RCBF_PENDING : sol.status;
+    o.iters = sol.iters;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) y[j] = sol.y[j];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      o.lam[i] = sol.lam[i];
+      o.s[i] = sol.s[i];
+    }
+  }
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) o.x[j] = y[j] * pisd[j];
+}
+
+// Fallback pass for the (rare) instances the fast path left pending: float32 interior point + certificate, then the
+// float64 interior point (which may also accept on its residual test, like qpth).  iters += 100 flags the f64 pass.
+template <int NZ, int M>
+RCBF_HD void solve_normalised_full(const Normalised<NZ, M>& nrm, const float p_diag[NZ], bool skip_f32,
+                                   NormSolution<NZ, M>& o) {
+  double pisd[NZ];
+  float pisf[NZ];
+  pis_of<NZ, M>(p_diag, pisd, pisf);
+  LnpSolution<double, NZ, M> sol;
+  sol.status = RCBF_MAXITER;
+  sol.iters = 0;
+  const NormCert<NZ, M> cp{nrm, pisd};
+  if (!skip_f32) {
     LnpProblem<float, NZ, M> Pf;
     to_lnp<float, NZ, M>(nrm, pisf, Pf);
     lnp_solve<float, double, NormCert<NZ, M>, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
   }
-  if (sol.status >= RCBF_MAXITER) {  // straggler: repeat in float64 (NaN inputs were caught before, status NAN = overflow)
+  if (sol.status >= RCBF_MAXITER) {
     const int it0 = sol.iters;
     LnpProblem<double, NZ, M> Pd;
     to_lnp<double, NZ, M>(nrm, pisd, Pd);
     lnp_solve<double, double, NormCert<NZ, M>, NZ, M>(Pd, cp, sol, kTolSlack, kTolDual);
-    sol.iters += it0 + 100;  // +100 flags the float64 pass in the iteration histogram
+    sol.iters += it0 + 100;
   }
   RCBF_UNROLL
-  for (int j = 0; j < NZ; ++j) x[j] = sol.y[j] * pisd[j];
+  for (int j = 0; j < NZ; ++j) o.x[j] = sol.y[j] * pisd[j];
   RCBF_UNROLL
   for (int i = 0; i < M; ++i) {
-    lam[i] = sol.lam[i];
-    s[i] = sol.s[i];
+    o.lam[i] = sol.lam[i];
+    o.s[i] = sol.s[i];
   }
-  status = sol.status;
-  iters = sol.iters;
+  o.status = sol.status;
+  o.iters = sol.iters;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -716,32 +883,38 @@ RCBF_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), h
 struct UniSolve {
   UniRaw raw;
   Normalised<kUniNZ, kUniM> nrm;
-  double x[kUniNZ], lam[kUniM], s[kUniM];
-  int status, iters;
+  NormSolution<kUniNZ, kUniM> sol;
 };
 
+// kMode: 0 = fast path with presolve, 1 = fast path with inline float32 IPM ("pdipm" mode), 2 = fallback pass,
+//        3 = fallback pass that skips the float32 IPM (it already failed in mode 1)
+template <int kMode>
 RCBF_HD void unicycle_safe_action(const UnicycleParams& p, const float st[3], const float u[2], const float mu[3],
                                   const float sg[3], UniSolve& w, float u_safe[2]) {
   assemble_unicycle(p, st, u, mu, sg, w.raw);
   normalise_rows<kUniNZ, kUniM>(w.raw.G, w.raw.h, w.nrm);
-  solve_normalised<kUniNZ, kUniM>(w.nrm, p.p_diag, w.x, w.lam, w.s, w.status, w.iters);
+  if (kMode == 0) solve_normalised_fast<kUniNZ, kUniM, true>(w.nrm, p.p_diag, w.sol);
+  if (kMode == 1) solve_normalised_fast<kUniNZ, kUniM, false>(w.nrm, p.p_diag, w.sol);
+  if (kMode >= 2) solve_normalised_full<kUniNZ, kUniM>(w.nrm, p.p_diag, kMode == 3, w.sol);
   RCBF_UNROLL
-  for (int c = 0; c < 2; ++c) u_safe[c] = clampf(u[c] + (float)w.x[c], p.u_min[c], p.u_max[c]);  // :77
+  for (int c = 0; c < 2; ++c) u_safe[c] = clampf(u[c] + (float)w.sol.x[c], p.u_min[c], p.u_max[c]);  // :77
 }
 
 struct CarsSolve {
   CarsRaw raw;
   Normalised<kCarsNZ, kCarsM> nrm;
-  double x[kCarsNZ], lam[kCarsM], s[kCarsM];
-  int status, iters;
+  NormSolution<kCarsNZ, kCarsM> sol;
 };
 
+template <int kMode>
 RCBF_HD void cars_safe_action(const CarsParams& p, const float st[10], float u, const float sg[10], CarsSolve& w,
                               float* u_safe) {
   assemble_cars(p, st, u, sg, w.raw);
   normalise_rows<kCarsNZ, kCarsM>(w.raw.G, w.raw.h, w.nrm);
-  solve_normalised<kCarsNZ, kCarsM>(w.nrm, p.p_diag, w.x, w.lam, w.s, w.status, w.iters);
-  *u_safe = clampf(u + (float)w.x[0], p.u_min, p.u_max);  // :77
+  if (kMode == 0) solve_normalised_fast<kCarsNZ, kCarsM, true>(w.nrm, p.p_diag, w.sol);
+  if (kMode == 1) solve_normalised_fast<kCarsNZ, kCarsM, false>(w.nrm, p.p_diag, w.sol);
+  if (kMode >= 2) solve_normalised_full<kCarsNZ, kCarsM>(w.nrm, p.p_diag, kMode == 3, w.sol);
+  *u_safe = clampf(u + (float)w.sol.x[0], p.u_min, p.u_max);  // :77
 }
 
 }  // namespace rcbf

@@ -20,6 +20,11 @@ namespace {
 constexpr int kThreads = 128;
 
 inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+// the fallback pass is a grid-stride scan: cap the grid at a few waves of the 148 SMs
+inline int grid_scan(int64_t n) {
+  const int64_t g = (n + kThreads - 1) / kThreads;
+  return (int)(g < 148 * 16 ? g : 148 * 16);
+}
 
 #define RCBF_LAUNCH_CHECK()                 \
   do {                                      \
@@ -50,6 +55,7 @@ __device__ __forceinline__ void accumulate_counters(rcbf_counters_t* counters, b
   const int n_max = __syncthreads_count(valid && status == RCBF_MAXITER);
   const int n_f64 = __syncthreads_count(valid && iters >= 100);
   const int n_triv = __syncthreads_count(valid && status == RCBF_OK_TRIVIAL);
+  const int n_pend = __syncthreads_count(valid && status == RCBF_PENDING);
   __shared__ int s_it;
   if (threadIdx.x == 0) s_it = 0;
   __syncthreads();
@@ -63,7 +69,17 @@ __device__ __forceinline__ void accumulate_counters(rcbf_counters_t* counters, b
     if (n_f64) atomicAdd(&counters[2], (unsigned long long)n_f64);
     if (n_triv) atomicAdd(&counters[3], (unsigned long long)n_triv);
     if (s_it) atomicAdd(&counters[4], (unsigned long long)s_it);
+    if (n_pend) atomicAdd(&counters[5], (unsigned long long)n_pend);
   }
+}
+
+// per-thread variant for the fallback pass (a handful of instances per launch)
+__device__ __forceinline__ void accumulate_counters_thread(rcbf_counters_t* counters, int status, int iters) {
+  if (counters == nullptr) return;
+  if (status == RCBF_NAN) atomicAdd(&counters[0], 1ULL);
+  if (status == RCBF_MAXITER) atomicAdd(&counters[1], 1ULL);
+  if (iters >= 100) atomicAdd(&counters[2], 1ULL);
+  atomicAdd(&counters[6], (unsigned long long)(iters >= 100 ? iters - 100 : iters));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -109,8 +125,59 @@ __global__ void __launch_bounds__(kThreads) k_cars_assemble(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K2+K3: get_safe_action forward
+// K2+K3: get_safe_action forward.
+//   pass 1 (kMode 0: greedy presolve + float64 certificate; kMode 1: float32 interior point + certificate) handles every
+//   instance; the rare ones it cannot certify get a tagged-NaN sentinel in safe_action[i][0] and nothing else.
+//   pass 2 (k_*_fallback, a grid-stride scan for the sentinel) re-solves those with the interior-point chain
+//   (float32, then float64).  Keeping the float64 interior point out of pass 1 is what keeps its register count low.
 // ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
+
+__device__ __forceinline__ bool is_pending(const float* p) { return __float_as_uint(__ldcg(p)) == kPendingBits; }
+
+__device__ __forceinline__ void write_unicycle_solution(int64_t i, const UniSolve& w, const float us[2],
+                                                        float* __restrict__ out, float* __restrict__ x,
+                                                        float* __restrict__ lam, float* __restrict__ slack,
+                                                        int32_t* __restrict__ status, int32_t* __restrict__ iters) {
+  store_row<2>(out, i, us);
+  if (x != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kUniNZ; ++j) x[i * kUniNZ + j] = (float)w.sol.x[j];
+  }
+  if (lam != nullptr) {
+#pragma unroll
+    for (int r = 0; r < kUniM; ++r) lam[i * kUniM + r] = (float)w.sol.lam[r];
+  }
+  if (slack != nullptr) {
+#pragma unroll
+    for (int r = 0; r < kUniM; ++r) slack[i * kUniM + r] = (float)w.sol.s[r];
+  }
+  if (status != nullptr) status[i] = w.sol.status;
+  if (iters != nullptr) iters[i] = w.sol.iters;
+}
+
+__device__ __forceinline__ void write_cars_solution(int64_t i, const CarsSolve& w, float us, float* __restrict__ out,
+                                                    float* __restrict__ x, float* __restrict__ lam,
+                                                    float* __restrict__ slack, int32_t* __restrict__ status,
+                                                    int32_t* __restrict__ iters) {
+  out[i] = us;
+  if (x != nullptr) {
+#pragma unroll
+    for (int j = 0; j < kCarsNZ; ++j) x[i * kCarsNZ + j] = (float)w.sol.x[j];
+  }
+  if (lam != nullptr) {
+#pragma unroll
+    for (int r = 0; r < kCarsM; ++r) lam[i * kCarsM + r] = (float)w.sol.lam[r];
+  }
+  if (slack != nullptr) {
+#pragma unroll
+    for (int r = 0; r < kCarsM; ++r) slack[i * kCarsM + r] = (float)w.sol.s[r];
+  }
+  if (status != nullptr) status[i] = w.sol.status;
+  if (iters != nullptr) iters[i] = w.sol.iters;
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(kThreads)
 k_unicycle_safe_action(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
                        const float* __restrict__ sg, int64_t n, UnicycleParams p, float* __restrict__ out,
@@ -126,27 +193,36 @@ k_unicycle_safe_action(const float* __restrict__ st, const float* __restrict__ a
   load_row<3>(sg, i, g);
   UniSolve w;
   float us[2];
-  unicycle_safe_action(p, s, u, m, g, w, us);
+  unicycle_safe_action<kMode>(p, s, u, m, g, w, us);
   if (valid) {
-    store_row<2>(out, i, us);
-    if (x != nullptr) {
-#pragma unroll
-      for (int j = 0; j < kUniNZ; ++j) x[i * kUniNZ + j] = (float)w.x[j];
-    }
-    if (lam != nullptr) {
-#pragma unroll
-      for (int r = 0; r < kUniM; ++r) lam[i * kUniM + r] = (float)w.lam[r];
-    }
-    if (slack != nullptr) {
-#pragma unroll
-      for (int r = 0; r < kUniM; ++r) slack[i * kUniM + r] = (float)w.s[r];
-    }
-    if (status != nullptr) status[i] = w.status;
-    if (iters != nullptr) iters[i] = w.iters;
+    if (w.sol.status == RCBF_PENDING) out[i * 2] = __uint_as_float(kPendingBits);
+    else write_unicycle_solution(i, w, us, out, x, lam, slack, status, iters);
   }
-  accumulate_counters(counters, valid, w.status, w.iters);
+  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
 }
 
+template <int kMode>
+__global__ void __launch_bounds__(kThreads)
+k_unicycle_safe_action_fallback(const float* __restrict__ st, const float* __restrict__ ac,
+                                const float* __restrict__ mu, const float* __restrict__ sg, int64_t n, UnicycleParams p,
+                                float* out, float* __restrict__ x, float* __restrict__ lam, float* __restrict__ slack,
+                                int32_t* __restrict__ status, int32_t* __restrict__ iters, rcbf_counters_t* counters) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    if (!is_pending(out + i * 2)) continue;
+    float s[3], u[2], m[3], g[3];
+    load_row<3>(st, i, s);
+    load_row<2>(ac, i, u);
+    load_row<3>(mu, i, m);
+    load_row<3>(sg, i, g);
+    UniSolve w;
+    float us[2];
+    unicycle_safe_action<kMode>(p, s, u, m, g, w, us);
+    write_unicycle_solution(i, w, us, out, x, lam, slack, status, iters);
+    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
+  }
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(kThreads)
 k_cars_safe_action(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg, int64_t n,
                    CarsParams p, float* __restrict__ out, float* __restrict__ x, float* __restrict__ lam,
@@ -161,25 +237,32 @@ k_cars_safe_action(const float* __restrict__ st, const float* __restrict__ ac, c
   const float u = __ldg(ac + i);
   CarsSolve w;
   float us;
-  cars_safe_action(p, s, u, g, w, &us);
+  cars_safe_action<kMode>(p, s, u, g, w, &us);
   if (valid) {
-    out[i] = us;
-    if (x != nullptr) {
-#pragma unroll
-      for (int j = 0; j < kCarsNZ; ++j) x[i * kCarsNZ + j] = (float)w.x[j];
-    }
-    if (lam != nullptr) {
-#pragma unroll
-      for (int r = 0; r < kCarsM; ++r) lam[i * kCarsM + r] = (float)w.lam[r];
-    }
-    if (slack != nullptr) {
-#pragma unroll
-      for (int r = 0; r < kCarsM; ++r) slack[i * kCarsM + r] = (float)w.s[r];
-    }
-    if (status != nullptr) status[i] = w.status;
-    if (iters != nullptr) iters[i] = w.iters;
+    if (w.sol.status == RCBF_PENDING) out[i] = __uint_as_float(kPendingBits);
+    else write_cars_solution(i, w, us, out, x, lam, slack, status, iters);
   }
-  accumulate_counters(counters, valid, w.status, w.iters);
+  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreads)
+k_cars_safe_action_fallback(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg,
+                            int64_t n, CarsParams p, float* out, float* __restrict__ x, float* __restrict__ lam,
+                            float* __restrict__ slack, int32_t* __restrict__ status, int32_t* __restrict__ iters,
+                            rcbf_counters_t* counters) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    if (!is_pending(out + i)) continue;
+    float s[10], g[10];
+    load_row<10>(st, i, s);
+    load_row<10>(sg, i, g);
+    const float u = __ldg(ac + i);
+    CarsSolve w;
+    float us;
+    cars_safe_action<kMode>(p, s, u, g, w, &us);
+    write_cars_solution(i, w, us, out, x, lam, slack, status, iters);
+    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -400,8 +483,29 @@ k_cars_predict_next(const T* __restrict__ state, const T* __restrict__ action, c
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K5: fused safe step = assemble + QP + clamp + env.step, one launch
+// K5: fused safe step = assemble + QP + clamp + env.step, one launch (+ the sentinel-scan fallback pass)
 // ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void finish_unicycle_step(int64_t i, const UnicycleEnvParams& e, float v[4], int stp,
+                                                     const float us[2], int status_v, float* __restrict__ state4,
+                                                     int32_t* __restrict__ step, float* __restrict__ safe_action,
+                                                     float* __restrict__ obs, float* __restrict__ reward,
+                                                     uint8_t* __restrict__ done, float* __restrict__ cost,
+                                                     uint8_t* __restrict__ goal_met, int32_t* __restrict__ status) {
+  UniEnvOut<float> o;
+  unicycle_env_step<float>(e, v, v[3], stp, us, o);
+  store_row<2>(safe_action, i, us);
+  store_row<7>(obs, i, o.obs);
+  reward[i] = o.reward;
+  done[i] = (uint8_t)o.done;
+  cost[i] = o.cost;
+  goal_met[i] = (uint8_t)o.goal_met;
+  if (status != nullptr) status[i] = status_v;
+  if (e.auto_reset && o.done) unicycle_reset<float>(e, v, v[3], stp);
+  store_state4<float>(state4, i, v);
+  step[i] = stp;
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(kThreads)
 k_unicycle_safe_step(float* __restrict__ state4, int32_t* __restrict__ step, const float* __restrict__ ac,
                      const float* __restrict__ mu, const float* __restrict__ sg, int64_t n, UnicycleParams p,
@@ -416,27 +520,62 @@ k_unicycle_safe_step(float* __restrict__ state4, int32_t* __restrict__ step, con
   load_row<2>(ac, i, u);
   load_row<3>(mu, i, m);
   load_row<3>(sg, i, g);
-  int stp = step[i];
+  const int stp = step[i];
   UniSolve w;
   float us[2];
-  unicycle_safe_action(p, v, u, m, g, w, us);
-  UniEnvOut<float> o;
-  unicycle_env_step<float>(e, v, v[3], stp, us, o);
+  unicycle_safe_action<kMode>(p, v, u, m, g, w, us);
   if (valid) {
-    store_row<2>(safe_action, i, us);
-    store_row<7>(obs, i, o.obs);
-    reward[i] = o.reward;
-    done[i] = (uint8_t)o.done;
-    cost[i] = o.cost;
-    goal_met[i] = (uint8_t)o.goal_met;
-    if (status != nullptr) status[i] = w.status;
-    if (e.auto_reset && o.done) unicycle_reset<float>(e, v, v[3], stp);
-    store_state4<float>(state4, i, v);
-    step[i] = stp;
+    if (w.sol.status == RCBF_PENDING) safe_action[i * 2] = __uint_as_float(kPendingBits);
+    else finish_unicycle_step(i, e, v, stp, us, w.sol.status, state4, step, safe_action, obs, reward, done, cost,
+                              goal_met, status);
   }
-  accumulate_counters(counters, valid, w.status, w.iters);
+  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
 }
 
+template <int kMode>
+__global__ void __launch_bounds__(kThreads)
+k_unicycle_safe_step_fallback(float* __restrict__ state4, int32_t* __restrict__ step, const float* __restrict__ ac,
+                              const float* __restrict__ mu, const float* __restrict__ sg, int64_t n, UnicycleParams p,
+                              UnicycleEnvParams e, float* safe_action, float* __restrict__ obs,
+                              float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ cost,
+                              uint8_t* __restrict__ goal_met, int32_t* __restrict__ status, rcbf_counters_t* counters) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    if (!is_pending(safe_action + i * 2)) continue;
+    float v[4], u[2], m[3], g[3];
+    load_state4<float>(state4, i, v);
+    load_row<2>(ac, i, u);
+    load_row<3>(mu, i, m);
+    load_row<3>(sg, i, g);
+    const int stp = step[i];
+    UniSolve w;
+    float us[2];
+    unicycle_safe_action<kMode>(p, v, u, m, g, w, us);
+    finish_unicycle_step(i, e, v, stp, us, w.sol.status, state4, step, safe_action, obs, reward, done, cost, goal_met,
+                         status);
+    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
+  }
+}
+
+__device__ __forceinline__ void finish_cars_step(int64_t i, const CarsEnvParams& e, float s[10], float tt, int stp,
+                                                 float us, int status_v, float* __restrict__ state,
+                                                 float* __restrict__ t, int32_t* __restrict__ step,
+                                                 float* __restrict__ safe_action, float* __restrict__ obs,
+                                                 float* __restrict__ reward, uint8_t* __restrict__ done,
+                                                 float* __restrict__ cost, int32_t* __restrict__ status) {
+  CarsEnvOut<float> o;
+  cars_env_step<float>(e, s, tt, stp, us, o);
+  safe_action[i] = us;
+  store_row<10>(obs, i, o.obs);
+  reward[i] = o.reward;
+  done[i] = (uint8_t)o.done;
+  cost[i] = o.cost;
+  if (status != nullptr) status[i] = status_v;
+  store_row<10>(state, i, s);
+  t[i] = tt;
+  step[i] = stp;
+}
+
+template <int kMode>
 __global__ void __launch_bounds__(kThreads)
 k_cars_safe_step(float* __restrict__ state, float* __restrict__ t, int32_t* __restrict__ step,
                  const float* __restrict__ ac, const float* __restrict__ sg, int64_t n, CarsParams p, CarsEnvParams e,
@@ -450,25 +589,40 @@ k_cars_safe_step(float* __restrict__ state, float* __restrict__ t, int32_t* __re
   load_row<10>(state, i, s);
   load_row<10>(sg, i, g);
   const float u = __ldg(ac + i);
-  float tt = t[i];
-  int stp = step[i];
+  const float tt = t[i];
+  const int stp = step[i];
   CarsSolve w;
   float us;
-  cars_safe_action(p, s, u, g, w, &us);
-  CarsEnvOut<float> o;
-  cars_env_step<float>(e, s, tt, stp, us, o);
+  cars_safe_action<kMode>(p, s, u, g, w, &us);
   if (valid) {
-    safe_action[i] = us;
-    store_row<10>(obs, i, o.obs);
-    reward[i] = o.reward;
-    done[i] = (uint8_t)o.done;
-    cost[i] = o.cost;
-    if (status != nullptr) status[i] = w.status;
-    store_row<10>(state, i, s);
-    t[i] = tt;
-    step[i] = stp;
+    if (w.sol.status == RCBF_PENDING) safe_action[i] = __uint_as_float(kPendingBits);
+    else finish_cars_step(i, e, s, tt, stp, us, w.sol.status, state, t, step, safe_action, obs, reward, done, cost,
+                          status);
   }
-  accumulate_counters(counters, valid, w.status, w.iters);
+  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
+}
+
+template <int kMode>
+__global__ void __launch_bounds__(kThreads)
+k_cars_safe_step_fallback(float* __restrict__ state, float* __restrict__ t, int32_t* __restrict__ step,
+                          const float* __restrict__ ac, const float* __restrict__ sg, int64_t n, CarsParams p,
+                          CarsEnvParams e, float* safe_action, float* __restrict__ obs, float* __restrict__ reward,
+                          uint8_t* __restrict__ done, float* __restrict__ cost, int32_t* __restrict__ status,
+                          rcbf_counters_t* counters) {
+  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+    if (!is_pending(safe_action + i)) continue;
+    float s[10], g[10];
+    load_row<10>(state, i, s);
+    load_row<10>(sg, i, g);
+    const float u = __ldg(ac + i);
+    const float tt = t[i];
+    const int stp = step[i];
+    CarsSolve w;
+    float us;
+    cars_safe_action<kMode>(p, s, u, g, w, &us);
+    finish_cars_step(i, e, s, tt, stp, us, w.sol.status, state, t, step, safe_action, obs, reward, done, cost, status);
+    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -552,9 +706,18 @@ int rcbf_unicycle_safe_action(const float* state, const float* action, const flo
                               const rcbf_unicycle_params* p, float* safe_action, float* x, float* lam, float* slack,
                               int32_t* status, int32_t* iters, rcbf_counters_t* counters, void* stream) {
   if (n <= 0) return 0;
-  k_unicycle_safe_action<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, action, mean, sigma, n, *p,
-                                                                             safe_action, x, lam, slack, status, iters,
-                                                                             counters);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->solver_mode == 0) {
+    k_unicycle_safe_action<0><<<grid_for(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action, x, lam,
+                                                               slack, status, iters, counters);
+    k_unicycle_safe_action_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action,
+                                                                         x, lam, slack, status, iters, counters);
+  } else {
+    k_unicycle_safe_action<1><<<grid_for(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action, x, lam,
+                                                               slack, status, iters, counters);
+    k_unicycle_safe_action_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action,
+                                                                         x, lam, slack, status, iters, counters);
+  }
   RCBF_LAUNCH_CHECK();
   return 0;
 }
@@ -563,8 +726,18 @@ int rcbf_cars_safe_action(const float* state, const float* action, const float* 
                           const rcbf_cars_params* p, float* safe_action, float* x, float* lam, float* slack,
                           int32_t* status, int32_t* iters, rcbf_counters_t* counters, void* stream) {
   if (n <= 0) return 0;
-  k_cars_safe_action<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, action, sigma, n, *p, safe_action, x,
-                                                                         lam, slack, status, iters, counters);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->solver_mode == 0) {
+    k_cars_safe_action<0><<<grid_for(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam, slack,
+                                                           status, iters, counters);
+    k_cars_safe_action_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam,
+                                                                     slack, status, iters, counters);
+  } else {
+    k_cars_safe_action<1><<<grid_for(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam, slack,
+                                                           status, iters, counters);
+    k_cars_safe_action_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam,
+                                                                     slack, status, iters, counters);
+  }
   RCBF_LAUNCH_CHECK();
   return 0;
 }
@@ -677,8 +850,18 @@ int rcbf_unicycle_safe_step(float* state4, int32_t* step, const float* action_rl
                             float* safe_action, float* obs, float* reward, uint8_t* done, float* cost, uint8_t* goal_met,
                             int32_t* status, rcbf_counters_t* counters, void* stream) {
   if (n <= 0) return 0;
-  k_unicycle_safe_step<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(
-      state4, step, action_rl, mean, sigma, n, *p, *e, safe_action, obs, reward, done, cost, goal_met, status, counters);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->solver_mode == 0) {
+    k_unicycle_safe_step<0><<<grid_for(n), kThreads, 0, s>>>(state4, step, action_rl, mean, sigma, n, *p, *e, safe_action,
+                                                             obs, reward, done, cost, goal_met, status, counters);
+    k_unicycle_safe_step_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(
+        state4, step, action_rl, mean, sigma, n, *p, *e, safe_action, obs, reward, done, cost, goal_met, status, counters);
+  } else {
+    k_unicycle_safe_step<1><<<grid_for(n), kThreads, 0, s>>>(state4, step, action_rl, mean, sigma, n, *p, *e, safe_action,
+                                                             obs, reward, done, cost, goal_met, status, counters);
+    k_unicycle_safe_step_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(
+        state4, step, action_rl, mean, sigma, n, *p, *e, safe_action, obs, reward, done, cost, goal_met, status, counters);
+  }
   RCBF_LAUNCH_CHECK();
   return 0;
 }
@@ -688,9 +871,18 @@ int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* acti
                         float* reward, uint8_t* done, float* cost, int32_t* status, rcbf_counters_t* counters,
                         void* stream) {
   if (n <= 0) return 0;
-  k_cars_safe_step<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, t, step, action_rl, sigma, n, *p, *e,
-                                                                       safe_action, obs, reward, done, cost, status,
-                                                                       counters);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->solver_mode == 0) {
+    k_cars_safe_step<0><<<grid_for(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e, safe_action, obs,
+                                                         reward, done, cost, status, counters);
+    k_cars_safe_step_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e,
+                                                                   safe_action, obs, reward, done, cost, status, counters);
+  } else {
+    k_cars_safe_step<1><<<grid_for(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e, safe_action, obs,
+                                                         reward, done, cost, status, counters);
+    k_cars_safe_step_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e,
+                                                                   safe_action, obs, reward, done, cost, status, counters);
+  }
   RCBF_LAUNCH_CHECK();
   return 0;
 }

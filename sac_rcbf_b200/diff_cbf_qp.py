@@ -26,7 +26,7 @@ class _SafeActionFn(torch.autograd.Function):
         st, ac, sg = _f32c(state, dev), _f32c(action, dev), _f32c(sigma, dev)
         mu = _f32c(mean, dev)
         n = st.shape[0]
-        need_grad = action.requires_grad and torch.is_grad_enabled()
+        need_grad = bool(ctx.needs_input_grad[2])   # grad mode is off inside forward(); this is the reliable signal
         out, x, lam, slack = layer._forward_raw(st, ac, mu, sg, save=need_grad)
         ctx.layer = layer
         ctx.in_device = action.device
@@ -130,27 +130,36 @@ class CBFQPLayer:
         self.action_dim = env.action_space.shape[0]
         self.num_ineq_constraints = self.num_cbfs + 2 * self.action_dim
         self.check_nan = True       # reference behaviour: sync + raise on NaN (diff_cbf_qp.py:141-143)
+        # "presolve": greedy active-set guess + float64 KKT certificate, interior point only as fallback (default);
+        # "pdipm": every non-trivial QP runs the primal-dual interior point (the reference's algorithm family)
+        self.solver = "presolve"
         self._last_counters = None  # device tensor [nan, uncertified, f64 passes, trivial, sum iters, ...]
         self._params_cache = None
 
     # ------------------------------------------------------------------------------------------------------ params
+    def _solver_mode(self):
+        if self.solver not in ("presolve", "pdipm"):
+            raise ValueError("solver must be 'presolve' or 'pdipm', got %r" % (self.solver,))
+        return 0 if self.solver == "presolve" else 1
+
     def _params(self):
         """C parameter struct, rebuilt when a public attribute the reference reads at call time has changed."""
         env = self.env
         if env.dynamics_mode == 'Unicycle':
-            key = ('U', float(self.gamma_b), float(self.l_p), float(env.hazards_radius),
+            key = ('U', self.solver, float(self.gamma_b), float(self.l_p), float(env.hazards_radius),
                    np.asarray(env.hazards_locations, np.float64).tobytes(),
                    self.u_min.cpu().numpy().tobytes(), self.u_max.cpu().numpy().tobytes())
             if self._params_cache is None or self._params_cache[0] != key:
                 p = _params.unicycle_params(env.hazards_locations, env.hazards_radius, float(self.gamma_b),
-                                            float(self.l_p), self.u_min.cpu().numpy(), self.u_max.cpu().numpy())
+                                            float(self.l_p), self.u_min.cpu().numpy(), self.u_max.cpu().numpy(),
+                                            solver_mode=self._solver_mode())
                 self._params_cache = (key, p)
         else:
-            key = ('C', float(self.gamma_b), float(env.kp), float(env.k_brake), self.u_min.cpu().numpy().tobytes(),
+            key = ('C', self.solver, float(self.gamma_b), float(env.kp), float(env.k_brake), self.u_min.cpu().numpy().tobytes(),
                    self.u_max.cpu().numpy().tobytes())
             if self._params_cache is None or self._params_cache[0] != key:
                 p = _params.cars_params(float(self.gamma_b), float(env.kp), float(env.k_brake),
-                                        float(self.u_min[0]), float(self.u_max[0]))
+                                        float(self.u_min[0]), float(self.u_max[0]), solver_mode=self._solver_mode())
                 self._params_cache = (key, p)
         return self._params_cache[1]
 
@@ -290,7 +299,8 @@ class CBFQPLayer:
         if self._last_counters is None:
             return None
         c = self._last_counters.cpu().tolist()
-        return dict(nan=c[0], uncertified=c[1], f64_passes=c[2], trivial=c[3], sum_iters=c[4])
+        return dict(nan=c[0], uncertified=c[1], f64_passes=c[2], trivial=c[3], sum_iters=c[4], fallback=c[5],
+                    fallback_iters=c[6])
 
 
 # north_star names the class DiffCBFLayer; the reference only has CBFQPLayer (SURVEY.md "Naming note")

@@ -30,7 +30,7 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def unicycle_safe_action(st, ac, mu, sg, params):
+def unicycle_safe_action(st, ac, mu, sg, params, mode=0):
     n = st.shape[0]
     st, ac, mu, sg = (np.ascontiguousarray(a, np.float32) for a in (st, ac, mu, sg))
     o = dict(out=np.zeros((n, 2), np.float32), x=np.zeros((n, 3)), lam=np.zeros((n, 9)), s=np.zeros((n, 9)),
@@ -40,11 +40,11 @@ def unicycle_safe_action(st, ac, mu, sg, params):
                                   _p(sg, C.c_float), C.byref(params), _p(o["out"], C.c_float), _p(o["x"], C.c_double),
                                   _p(o["lam"], C.c_double), _p(o["s"], C.c_double), _p(o["status"], C.c_int),
                                   _p(o["iters"], C.c_int), _p(o["Gn"], C.c_float), _p(o["hn"], C.c_float),
-                                  _p(o["G"], C.c_float), _p(o["h"], C.c_float))
+                                  _p(o["G"], C.c_float), _p(o["h"], C.c_float), C.c_int(mode))
     return o
 
 
-def cars_safe_action(st, ac, sg, params):
+def cars_safe_action(st, ac, sg, params, mode=0):
     n = st.shape[0]
     st, ac, sg = (np.ascontiguousarray(a, np.float32) for a in (st, ac, sg))
     o = dict(out=np.zeros((n, 1), np.float32), x=np.zeros((n, 2)), lam=np.zeros((n, 4)), s=np.zeros((n, 4)),
@@ -54,5 +54,5 @@ def cars_safe_action(st, ac, sg, params):
                               _p(o["out"], C.c_float), _p(o["x"], C.c_double), _p(o["lam"], C.c_double),
                               _p(o["s"], C.c_double), _p(o["status"], C.c_int), _p(o["iters"], C.c_int),
                               _p(o["Gn"], C.c_float), _p(o["hn"], C.c_float), _p(o["G"], C.c_float),
-                              _p(o["h"], C.c_float))
+                              _p(o["h"], C.c_float), C.c_int(mode))
     return o

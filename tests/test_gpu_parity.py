@@ -91,7 +91,10 @@ def test_safe_action_vs_golden(request, golden, which, name):
     assert st["nan"] == 0 and st["uncertified"] == 0
     # 1-D contract (diff_cbf_qp.py:64-69,79)
     o1 = layer.get_safe_action(*(_cuda(g[k][0]) for k in ("state", "action", "mean", "sigma")))
-    assert o1.shape == (nu,) and np.abs(o1.cpu().numpy() - g["safe_action_1d"]).max() < ACT_TOL
+    assert o1.shape == (nu,) and torch.equal(o1, out[0])
+    # the golden 1-D value comes from qpth stopping on ITS residual test at B=1 (eps=1e-4, diff_cbf_qp.py:107), which
+    # leaves it up to ~1e-2 from the optimum in the weakly weighted omega; we return the optimum
+    assert np.abs(o1.cpu().numpy() - g["safe_action_1d"]).max() < 2e-2
 
 
 def _forward_with_aux(layer, st, ac, mu, sg):
@@ -128,6 +131,31 @@ def test_safe_action_vs_oracle_synthetic(request, mode):
     assert _row_slack(Gn[ok], hn[ok], x[ok]) > ROW_TOL
     # duals: non-negative, complementary
     assert lam.min() >= 0 and np.abs(lam * slack).max() < 1e-5 * max(1.0, lam.max())
+
+
+@pytest.mark.parametrize("mode", ["Unicycle", "SimulatedCars"])
+def test_pdipm_solver_mode_matches_presolve_mode(request, mode):
+    """The interior-point-only mode (north_star's solver) and the default presolve mode end in the same float64 KKT
+    certificate, so they must agree to rounding of the certificate inputs (here: bit for bit)."""
+    env, layer = request.getfixturevalue("uni" if mode == "Unicycle" else "cars")
+    B = 1 << 18
+    arrs = O.synth_unicycle(B, seed=77) if mode == "Unicycle" else O.synth_cars(B, seed=77)
+    st, ac, mu, sg = arrs[:4]
+    ref = _forward_with_aux(layer, st, ac, mu, sg)
+    stats_ref = layer.solver_stats()
+    layer.solver = "pdipm"
+    try:
+        alt = _forward_with_aux(layer, st, ac, mu, sg)
+        stats = layer.solver_stats()
+    finally:
+        layer.solver = "presolve"
+    assert (alt[4] <= 2).all() and stats["nan"] == 0 and stats["uncertified"] == 0
+    same = (alt[4] == 1) & (ref[4] == 1)          # both certified: identical active set -> identical numbers
+    assert same.mean() > 0.2
+    np.testing.assert_array_equal(alt[0][same | (ref[4] == 0)], ref[0][same | (ref[4] == 0)])
+    assert np.abs(alt[0] - ref[0]).max() < 1e-5
+    # the interior point really ran: iterations were spent, the presolve spent at most nz rounds
+    assert stats["sum_iters"] > stats_ref["sum_iters"] and ref[5][ref[5] < 100].max() <= (3 if mode == "Unicycle" else 2)
 
 
 def test_trivial_instances_pass_through(uni):
@@ -290,7 +318,11 @@ def test_env_f32_single_step_vs_oracle(S):
     new = env.state.cpu().numpy()
     scale = np.maximum(np.abs(ref["state"]), 1.0)
     assert (np.abs(new - ref["state"]) / scale).max() < DYN_RTOL
-    assert (np.abs(obs.cpu().numpy() - ref["obs"])).max() < 2e-6
+    oerr = np.abs(obs.cpu().numpy() - ref["obs"])
+    assert oerr[:, [0, 1, 2, 3, 6]].max() < 2e-6
+    # the compass is (goal - p)/|goal - p| rotated: float32 positions (ulp 2.4e-7 at |p| ~ 3) make it ill-conditioned
+    # like 1/dist close to the goal
+    assert (oerr[:, 4:6] * np.maximum(ref["last_goal_dist"], 1e-3)[:, None]).max() < 2e-6
     # reward is a difference of two O(5) distances: float32 carries it to ~1e-6 absolute
     assert np.abs(rew.cpu().numpy() - ref["reward"]).max() < 2e-6
     near_goal = np.abs(ref["last_goal_dist"] - 0.3) < 1e-5
