@@ -218,9 +218,9 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     out = {}
     # (a) same workload, interior-point-only solver mode (north_star's PDIPM on every non-trivial QP)
     layer.solver = "pdipm"
-    env._counters.zero_()
+    env._counters[:8].zero_()
     ms = _time_calls(lambda: env.safe_step(layer, *batches[0]), 5, device)
-    cc = env._counters.cpu().tolist()
+    cc = env._counters[:8].cpu().tolist()
     layer.solver = "presolve"
     tot = 8.0 * n
     out["pdipm_mode"] = {"value": n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
@@ -294,7 +294,7 @@ def main():
     SETS = 2
     st0, batches = synth_inputs(n, device, 12345 + rank, SETS)
     env.state = st0
-    env._counters = torch.zeros(8, dtype=torch.int64, device=device)
+    env._counters = torch.zeros(2048, dtype=torch.int64, device=device)   # RCBF_WS_WORDS
     env._safe_action = torch.empty((n, 2), dtype=torch.float32, device=device)
 
     def step(k):
@@ -309,7 +309,7 @@ def main():
     for k in range(max(args.warmup, 3)):
         step(k)
     barrier()
-    env._counters.zero_()
+    env._counters[:8].zero_()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -326,7 +326,7 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    counters = env._counters.clone()
+    counters = env._counters[:8].clone()
     if dist is not None:
         dist.all_reduce(counters, op=dist.ReduceOp.SUM)   # optional rollout statistics gather: off the timed path
     c = counters.cpu().tolist()
@@ -348,6 +348,7 @@ def main():
                      rew=torch.empty((n,)).pin_memory(), cost=torch.empty((n,)).pin_memory(),
                      done=torch.empty((n,), dtype=torch.uint8).pin_memory())
         streams = [torch.cuda.Stream(device) for _ in range(3)]
+        wss = [torch.zeros(2048, dtype=torch.int64, device=device) for _ in range(3)]   # one workspace per stream
         p_layer, p_env = layer._params(), env._env_params()
 
         def e2e_step(k):
@@ -365,7 +366,7 @@ def main():
                         _lib.ptr(d_in[1][lo:up]), _lib.ptr(d_in[2][lo:up]), up - lo, p_layer, p_env,
                         _lib.ptr(env._safe_action[lo:up]), _lib.ptr(env._obs[lo:up]), _lib.ptr(env._reward[lo:up]),
                         _lib.ptr(env._done[lo:up]), _lib.ptr(env._cost[lo:up]), _lib.ptr(env._goal[lo:up]), None,
-                        _lib.ptr(env._counters), s.cuda_stream)
+                        _lib.ptr(wss[cidx % 3]), s.cuda_stream)
                     assert rc == 0
                     h_out["u"][lo:up].copy_(env._safe_action[lo:up], non_blocking=True)
                     h_out["obs"][lo:up].copy_(env._obs[lo:up], non_blocking=True)

@@ -79,10 +79,14 @@ typedef struct {
   int auto_reset;
 } rcbf_cars_env_params;
 
-/* counters[0]=#NaN  [1]=#uncertified(max-iter)  [2]=#float64 interior-point passes  [3]=#trivial
- * [4]=sum over instances of pass-1 iterations (presolve rounds in mode 0, interior-point iterations in mode 1)
- * [5]=#instances handed to the fallback pass  [6]=sum of fallback-pass interior-point iterations  [7] reserved.
- * Accumulated with atomics; zero them before the call.  Nullable. */
+/* Solver workspace: RCBF_WS_WORDS 64-bit words owned by the caller, zero-initialised once, one per concurrent stream.
+ *   [0]=#NaN  [1]=#uncertified(max-iter)  [2]=#float64 interior-point passes  [3]=#trivial
+ *   [4]=sum over instances of pass-1 iterations (presolve rounds in mode 0, interior-point iterations in mode 1)
+ *   [5]=#instances handed to the fallback pass  [6]=sum of fallback-pass interior-point iterations  [7] reserved
+ *   [8..15] queue bookkeeping, [16..) indices of the instances queued for the fallback pass (reset by the library).
+ * The counters [0..7] accumulate with atomics across calls; zero them when you want per-call numbers.  Nullable: the
+ * fallback pass then scans safe_action for its pending sentinel instead of reading the queue (slower). */
+#define RCBF_WS_WORDS 2048
 typedef unsigned long long rcbf_counters_t;
 
 /* ---- constraint assembly (raw P,q are constants: P = diag(p_diag), q = 0) ------------------------------------- */
@@ -95,11 +99,11 @@ int rcbf_cars_assemble(const float* state, const float* action, const float* sig
 int rcbf_unicycle_safe_action(const float* state, const float* action, const float* mean, const float* sigma,
                               int64_t n, const rcbf_unicycle_params* p_host, float* safe_action /* n*2 */,
                               float* x /* n*3 */, float* lam /* n*9 */, float* slack /* n*9 */, int32_t* status,
-                              int32_t* iters, rcbf_counters_t* counters, void* stream);
+                              int32_t* iters, rcbf_counters_t* workspace, void* stream);
 int rcbf_cars_safe_action(const float* state, const float* action, const float* sigma, int64_t n,
                           const rcbf_cars_params* p_host, float* safe_action /* n*1 */, float* x /* n*2 */,
                           float* lam /* n*4 */, float* slack /* n*4 */, int32_t* status, int32_t* iters,
-                          rcbf_counters_t* counters, void* stream);
+                          rcbf_counters_t* workspace, void* stream);
 
 /* ---- get_safe_action backward: d loss / d action given d loss / d safe_action -------------------------------- */
 int rcbf_unicycle_safe_action_bwd(const float* state, const float* action, const float* mean, const float* sigma,
@@ -157,11 +161,11 @@ int rcbf_unicycle_safe_step(float* state4, int32_t* step, const float* action_rl
                             const float* sigma, int64_t n, const rcbf_unicycle_params* p_host,
                             const rcbf_unicycle_env_params* e_host, float* safe_action /* n*2 */, float* obs /* n*7 */,
                             float* reward, uint8_t* done, float* cost, uint8_t* goal_met, int32_t* status /* nullable */,
-                            rcbf_counters_t* counters, void* stream);
+                            rcbf_counters_t* workspace, void* stream);
 int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* action_rl, const float* sigma, int64_t n,
                         const rcbf_cars_params* p_host, const rcbf_cars_env_params* e_host, float* safe_action,
                         float* obs /* n*10 */, float* reward, uint8_t* done, float* cost, int32_t* status,
-                        rcbf_counters_t* counters, void* stream);
+                        rcbf_counters_t* workspace, void* stream);
 
 /* ---- host-buffer entry points (the e2e path): pinned or pageable HOST arrays in, HOST arrays out; the library
  * stages through its own device scratch and pipelines H2D / compute / D2H over `chunks` slices on internal streams.

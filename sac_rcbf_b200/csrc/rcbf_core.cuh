@@ -23,9 +23,11 @@
 
 #if defined(__CUDACC__)
 #define RCBF_HD __host__ __device__ __forceinline__
+#define RCBF_HDC __host__ __device__
 #define RCBF_UNROLL _Pragma("unroll")
 #else
 #define RCBF_HD inline __attribute__((always_inline))
+#define RCBF_HDC
 #define RCBF_UNROLL _Pragma("GCC unroll 16")
 #endif
 
@@ -89,6 +91,17 @@ template <typename T, int NZ, int M>
 struct LnpProblem {
   T A[M][NZ];
   T b[M];
+};
+
+// Compile-time sparsity pattern of A: the actuator rows of both layers touch a single control and never the slack
+// (diff_cbf_qp.py:365-377).  IEEE rules forbid the compiler from folding `0 * y`, so the structure is spelled out:
+// every A[i][j] product below is guarded by Pat::nz(i, j), a constexpr that the unroller resolves.
+struct DensePat {
+  RCBF_HDC static constexpr bool nz(int, int) { return true; }
+};
+template <int NCBF, int NU>
+struct CbfPat {  // rows [0, NCBF) dense; row NCBF + 2c and NCBF + 2c + 1 touch column c only
+  RCBF_HDC static constexpr bool nz(int i, int j) { return i < NCBF || j == (i - NCBF) / 2; }
 };
 
 template <typename T, int NZ, int M>
@@ -158,7 +171,7 @@ struct Chol {
 // identified instead of having to converge numerically.
 // CP supplies the problem data in precision C through a(i,j) / b(i) (compile-time indices after unrolling), so that
 // the certificate sees the *unrounded* scaled data even when the iteration runs on a float32 copy.
-template <typename C, typename CP, int NZ, int M>
+template <typename C, typename CP, typename Pat, int NZ, int M>
 RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], C lam[M], C s[M]) {
   // gather up to NZ active rows (unused slots: zero row, b = 0  ->  lam = 0 through the unit diagonal below)
   C R[NZ][NZ];
@@ -177,7 +190,7 @@ RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], 
     for (int k = 0; k < NZ; ++k) {
       const bool put = act && (cnt == k);
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) R[k][j] = put ? P.a(i, j) : R[k][j];
+      for (int j = 0; j < NZ; ++j) R[k][j] = put ? (Pat::nz(i, j) ? P.a(i, j) : C(0)) : R[k][j];
       rb[k] = put ? P.b(i) : rb[k];
     }
     cnt += act ? 1 : 0;
@@ -217,7 +230,8 @@ RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], 
   for (int i = 0; i < M; ++i) {
     C acc = P.b(i);
     RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) acc = t_fma(-P.a(i, j), y[j], acc);
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) acc = t_fma(-P.a(i, j), y[j], acc);
     const bool act = (mask >> i) & 1u;
     C li = C(0);
     RCBF_UNROLL
@@ -236,14 +250,15 @@ RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], 
 // times.  This is Goldfarb-Idnani without constraint dropping: it stops with `false` as soon as a multiplier turns
 // negative (a drop would be needed) or NZ rows do not make the point feasible -- those instances go to the
 // interior-point solver.  The returned mask is only a GUESS; the float64 certificate decides.
-template <int NZ, int M>
+template <typename Pat, int NZ, int M>
 RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& mask_out, int& rounds) {
   float inv_norm[M];
   RCBF_UNROLL
   for (int i = 0; i < M; ++i) {
     float acc = 0.f;
     RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) acc = fmaf(P.A[i][j], P.A[i][j], acc);
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) acc = fmaf(P.A[i][j], P.A[i][j], acc);
 #if defined(__CUDA_ARCH__)
     inv_norm[i] = rsqrtf(acc);
 #else
@@ -270,7 +285,8 @@ RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& 
     for (int i = 0; i < M; ++i) {
       float acc = P.b[i];
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) acc = fmaf(-P.A[i][j], y[j], acc);
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) acc = fmaf(-P.A[i][j], y[j], acc);
       const float v = acc * inv_norm[i];
       const bool take = !((mask >> i) & 1u) && (v < worst);
       worst = take ? v : worst;
@@ -286,7 +302,7 @@ RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& 
     for (int i = 0; i < M; ++i) {
       const bool put = (i == wi);
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) R[r][j] = put ? P.A[i][j] : R[r][j];
+      for (int j = 0; j < NZ; ++j) R[r][j] = put ? (Pat::nz(i, j) ? P.A[i][j] : 0.f) : R[r][j];
       rb[r] = put ? P.b[i] : rb[r];
     }
     // (R R') lam = -rb on the first r+1 rows (unit diagonal on the unused slots)
@@ -341,7 +357,7 @@ template <> struct LnpTol<double> {
 // --- primal-dual interior point (Mehrotra predictor-corrector) with certified early exit -------------------
 // T : precision of the iteration (float on the main path, double in the straggler pass)
 // C : precision of the certificate (double: ~100 DFMA, B200 runs FP64 at 1:2)
-template <typename T, typename C, typename CP, int NZ, int M>
+template <typename T, typename C, typename CP, typename Pat, int NZ, int M>
 RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<C, NZ, M>& out, C tol_s, C tol_l) {
   // 0. trivial certificate: y = 0 is feasible  <=>  b >= 0 on every row
   {
@@ -378,12 +394,14 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
       for (int k = 0; k <= j; ++k) {
         T acc = (j == k) ? T(1) : T(0);
         RCBF_UNROLL
-        for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], P.A[i][k], acc);
+        for (int i = 0; i < M; ++i)
+          if (Pat::nz(i, j) && Pat::nz(i, k)) acc = t_fma(P.A[i][j], P.A[i][k], acc);
         S[j][k] = acc;
       }
       T acc = T(0);
       RCBF_UNROLL
-      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], P.b[i], acc);
+      for (int i = 0; i < M; ++i)
+        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], P.b[i], acc);
       r[j] = acc;
     }
     Chol<T, NZ> ch;
@@ -394,7 +412,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     for (int i = 0; i < M; ++i) {
       T acc = P.b[i];
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) acc = t_fma(-P.A[i][j], y[j], acc);
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], y[j], acc);
       s[i] = acc;
       z[i] = -acc;
       smin = t_min(smin, s[i]);
@@ -429,7 +448,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     for (int j = 0; j < NZ; ++j) {
       T acc = y[j];
       RCBF_UNROLL
-      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], z[i], acc);
+      for (int i = 0; i < M; ++i)
+        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], z[i], acc);
       rx[j] = acc;
       nrx = t_fma(acc, acc, nrx);
     }
@@ -438,7 +458,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     for (int i = 0; i < M; ++i) {
       T acc = s[i] - P.b[i];
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) acc = t_fma(P.A[i][j], y[j], acc);
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], y[j], acc);
       rz[i] = acc;
       nrz = t_fma(acc, acc, nrz);
       mu = t_fma(s[i], z[i], mu);
@@ -458,7 +479,7 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     }
     // certified early exit: try the predicted active set whenever it is a candidate
     if (it >= LnpTol<T>::kFirstCert && (mask == last_mask || it >= LnpTol<T>::kAlwaysCert)) {
-      if (lnp_certify<C, CP, NZ, M>(cp, mask, tol_s, tol_l, out.y, out.lam, out.s)) {
+      if (lnp_certify<C, CP, Pat, NZ, M>(cp, mask, tol_s, tol_l, out.y, out.lam, out.s)) {
         out.status = RCBF_OK_CERTIFIED;
         out.iters = it;
         return;
@@ -485,7 +506,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
       for (int k = 0; k <= j; ++k) {
         T acc = (j == k) ? T(1) : T(0);
         RCBF_UNROLL
-        for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j] * d[i], P.A[i][k], acc);
+        for (int i = 0; i < M; ++i)
+          if (Pat::nz(i, j) && Pat::nz(i, k)) acc = t_fma(P.A[i][j] * d[i], P.A[i][k], acc);
         S[j][k] = acc;
       }
     }
@@ -498,7 +520,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     for (int j = 0; j < NZ; ++j) {
       T acc = -rx[j];
       RCBF_UNROLL
-      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], t_fma(-d[i], rz[i], z[i]), acc);
+      for (int i = 0; i < M; ++i)
+        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], t_fma(-d[i], rz[i], z[i]), acc);
       r[j] = acc;
     }
     ch.solve(r, dy);
@@ -507,7 +530,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     for (int i = 0; i < M; ++i) {
       T acc = -rz[i];
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) acc = t_fma(-P.A[i][j], dy[j], acc);
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], dy[j], acc);
       ds[i] = acc;
       dz[i] = t_fma(-d[i], acc, -z[i]);
       rho = t_max(rho, -ds[i] * (w[i] * z[i]));
@@ -531,7 +555,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     for (int j = 0; j < NZ; ++j) {
       T acc = r[j];
       RCBF_UNROLL
-      for (int i = 0; i < M; ++i) acc = t_fma(P.A[i][j], rsc[i], acc);
+      for (int i = 0; i < M; ++i)
+        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], rsc[i], acc);
       r[j] = acc;
     }
     ch.solve(r, dy);
@@ -540,7 +565,8 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     for (int i = 0; i < M; ++i) {
       T acc = -rz[i];
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) acc = t_fma(-P.A[i][j], dy[j], acc);
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], dy[j], acc);
       ds[i] = acc;
       dz[i] = t_fma(-d[i], acc, -(z[i] + rsc[i]));
       rho = t_max(rho, -ds[i] * (w[i] * z[i]));
@@ -575,6 +601,8 @@ constexpr int kUniM = kUniHaz + 4;
 constexpr int kUniNZ = 3;
 constexpr int kCarsM = 4;
 constexpr int kCarsNZ = 2;
+using UniPat = CbfPat<kUniHaz, 2>;
+using CarsPat = CbfPat<2, 1>;
 
 using UnicycleParams = rcbf_unicycle_params;  // include/rcbf_b200.h
 using CarsParams = rcbf_cars_params;
@@ -722,31 +750,54 @@ struct Normalised {
   uint32_t h_is_max;  // bit i: |h_i| is the (strict) row maximum  -> routes d n_i / d h_i in the backward
 };
 
-template <int NZ, int M>
+// a / n with r ~ 1/n: one multiply + one residual correction (the fast path of IEEE division; correctly rounded
+// whenever r is within an ulp of 1/n, i.e. outside the denormal/overflow corners that normalised rows never reach)
+RCBF_HD float div_by(float a, float n, float r) {
+#if defined(__CUDA_ARCH__)
+  const float q = a * r;
+  return fmaf(fmaf(-n, q, a), r, q);
+#else
+  (void)r;
+  return a / n;
+#endif
+}
+RCBF_HD float rcp_refined(float n) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
+  return fmaf(fmaf(-n, r, 1.0f), r, r);
+#else
+  return 1.0f / n;
+#endif
+}
+
+template <typename Pat, int NZ, int M>
 RCBF_HD void normalise_rows(const float G[M][NZ], const float h[M], Normalised<NZ, M>& o) {
   o.h_is_max = 0;
   RCBF_UNROLL
   for (int i = 0; i < M; ++i) {
     float gm = 0.0f;
     RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) gm = fmaxf(gm, fabsf(G[i][j]));
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) gm = fmaxf(gm, fabsf(G[i][j]));
     const float ha = fabsf(h[i]);
     // torch.max returns the FIRST maximal index on ties; h is the last column (diff_cbf_qp.py:103-104)
     if (ha > gm) o.h_is_max |= (1u << i);
     const float n = (ha != ha) ? ha : fmaxf(gm, ha);  // propagate NaN like torch.max
     o.n[i] = n;
+    const float r = rcp_refined(n);
     RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) o.Gn[i][j] = G[i][j] / n;
-    o.hn[i] = h[i] / n;
+    for (int j = 0; j < NZ; ++j) o.Gn[i][j] = Pat::nz(i, j) ? div_by(G[i][j], n, r) : 0.0f;
+    o.hn[i] = div_by(h[i], n, r);
   }
 }
 
-template <typename T, int NZ, int M>
+template <typename T, typename Pat, int NZ, int M>
 RCBF_HD void to_lnp(const Normalised<NZ, M>& nrm, const T pis[NZ] /* P^-1/2 */, LnpProblem<T, NZ, M>& P) {
   RCBF_UNROLL
   for (int i = 0; i < M; ++i) {
     RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) P.A[i][j] = T(nrm.Gn[i][j]) * pis[j];
+    for (int j = 0; j < NZ; ++j) P.A[i][j] = Pat::nz(i, j) ? T(nrm.Gn[i][j]) * pis[j] : T(0);
     P.b[i] = T(nrm.hn[i]);
   }
 }
@@ -785,7 +836,7 @@ RCBF_HD void pis_of(const float p_diag[NZ], double pisd[NZ], float pisf[NZ]) {
 // Fast path of one normalised QP: trivial test, greedy active-set presolve (float32) and the float64 KKT
 // certificate.  kPresolve = false skips the presolve and runs the float32 interior point inline instead
 // ("pdipm" solver mode).  Leaves status = RCBF_PENDING when it cannot certify: the fallback pass takes over.
-template <int NZ, int M, bool kPresolve>
+template <typename Pat, int NZ, int M, bool kPresolve>
 RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_diag[NZ], NormSolution<NZ, M>& o) {
   double pisd[NZ];
   float pisf[NZ];
@@ -812,20 +863,20 @@ RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_d
   }
   const NormCert<NZ, M> cp{nrm, pisd};
   LnpProblem<float, NZ, M> Pf;
-  to_lnp<float, NZ, M>(nrm, pisf, Pf);
+  to_lnp<float, Pat, NZ, M>(nrm, pisf, Pf);
   double y[NZ];
   if (kPresolve) {
     uint32_t mask;
     int rounds;
-    const bool guess = lnp_greedy_active_set<NZ, M>(Pf, mask, rounds);
+    const bool guess = lnp_greedy_active_set<Pat, NZ, M>(Pf, mask, rounds);
     o.status = RCBF_PENDING;
     o.iters = rounds;
-    if (guess && lnp_certify<double, NormCert<NZ, M>, NZ, M>(cp, mask, kTolSlack, kTolDual, y, o.lam, o.s)) {
+    if (guess && lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, mask, kTolSlack, kTolDual, y, o.lam, o.s)) {
       o.status = RCBF_OK_CERTIFIED;
     }
   } else {
     LnpSolution<double, NZ, M> sol;
-    lnp_solve<float, double, NormCert<NZ, M>, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
+    lnp_solve<float, double, NormCert<NZ, M>, Pat, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
     o.status = (sol.status >= RCBF_MAXITER) ? RCBF_PENDING : sol.status;
     o.iters = sol.iters;
     RCBF_UNROLL
@@ -842,7 +893,7 @@ RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_d
 
 // Fallback pass for the (rare) instances the fast path left pending: float32 interior point + certificate, then the
 // float64 interior point (which may also accept on its residual test, like qpth).  iters += 100 flags the f64 pass.
-template <int NZ, int M>
+template <typename Pat, int NZ, int M>
 RCBF_HD void solve_normalised_full(const Normalised<NZ, M>& nrm, const float p_diag[NZ], bool skip_f32,
                                    NormSolution<NZ, M>& o) {
   double pisd[NZ];
@@ -854,14 +905,14 @@ RCBF_HD void solve_normalised_full(const Normalised<NZ, M>& nrm, const float p_d
   const NormCert<NZ, M> cp{nrm, pisd};
   if (!skip_f32) {
     LnpProblem<float, NZ, M> Pf;
-    to_lnp<float, NZ, M>(nrm, pisf, Pf);
-    lnp_solve<float, double, NormCert<NZ, M>, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
+    to_lnp<float, Pat, NZ, M>(nrm, pisf, Pf);
+    lnp_solve<float, double, NormCert<NZ, M>, Pat, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
   }
   if (sol.status >= RCBF_MAXITER) {
     const int it0 = sol.iters;
     LnpProblem<double, NZ, M> Pd;
-    to_lnp<double, NZ, M>(nrm, pisd, Pd);
-    lnp_solve<double, double, NormCert<NZ, M>, NZ, M>(Pd, cp, sol, kTolSlack, kTolDual);
+    to_lnp<double, Pat, NZ, M>(nrm, pisd, Pd);
+    lnp_solve<double, double, NormCert<NZ, M>, Pat, NZ, M>(Pd, cp, sol, kTolSlack, kTolDual);
     sol.iters += it0 + 100;
   }
   RCBF_UNROLL
@@ -892,10 +943,10 @@ template <int kMode>
 RCBF_HD void unicycle_safe_action(const UnicycleParams& p, const float st[3], const float u[2], const float mu[3],
                                   const float sg[3], UniSolve& w, float u_safe[2]) {
   assemble_unicycle(p, st, u, mu, sg, w.raw);
-  normalise_rows<kUniNZ, kUniM>(w.raw.G, w.raw.h, w.nrm);
-  if (kMode == 0) solve_normalised_fast<kUniNZ, kUniM, true>(w.nrm, p.p_diag, w.sol);
-  if (kMode == 1) solve_normalised_fast<kUniNZ, kUniM, false>(w.nrm, p.p_diag, w.sol);
-  if (kMode >= 2) solve_normalised_full<kUniNZ, kUniM>(w.nrm, p.p_diag, kMode == 3, w.sol);
+  normalise_rows<UniPat, kUniNZ, kUniM>(w.raw.G, w.raw.h, w.nrm);
+  if (kMode == 0) solve_normalised_fast<UniPat, kUniNZ, kUniM, true>(w.nrm, p.p_diag, w.sol);
+  if (kMode == 1) solve_normalised_fast<UniPat, kUniNZ, kUniM, false>(w.nrm, p.p_diag, w.sol);
+  if (kMode >= 2) solve_normalised_full<UniPat, kUniNZ, kUniM>(w.nrm, p.p_diag, kMode == 3, w.sol);
   RCBF_UNROLL
   for (int c = 0; c < 2; ++c) u_safe[c] = clampf(u[c] + (float)w.sol.x[c], p.u_min[c], p.u_max[c]);  // :77
 }
@@ -910,10 +961,10 @@ template <int kMode>
 RCBF_HD void cars_safe_action(const CarsParams& p, const float st[10], float u, const float sg[10], CarsSolve& w,
                               float* u_safe) {
   assemble_cars(p, st, u, sg, w.raw);
-  normalise_rows<kCarsNZ, kCarsM>(w.raw.G, w.raw.h, w.nrm);
-  if (kMode == 0) solve_normalised_fast<kCarsNZ, kCarsM, true>(w.nrm, p.p_diag, w.sol);
-  if (kMode == 1) solve_normalised_fast<kCarsNZ, kCarsM, false>(w.nrm, p.p_diag, w.sol);
-  if (kMode >= 2) solve_normalised_full<kCarsNZ, kCarsM>(w.nrm, p.p_diag, kMode == 3, w.sol);
+  normalise_rows<CarsPat, kCarsNZ, kCarsM>(w.raw.G, w.raw.h, w.nrm);
+  if (kMode == 0) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, true>(w.nrm, p.p_diag, w.sol);
+  if (kMode == 1) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, false>(w.nrm, p.p_diag, w.sol);
+  if (kMode >= 2) solve_normalised_full<CarsPat, kCarsNZ, kCarsM>(w.nrm, p.p_diag, kMode == 3, w.sol);
   *u_safe = clampf(u + (float)w.sol.x[0], p.u_min, p.u_max);  // :77
 }
 

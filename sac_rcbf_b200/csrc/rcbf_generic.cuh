@@ -47,7 +47,7 @@ RCBF_HD void generic_qp_solve(const double* Q, const double* p, const double* G,
   }
   LnpSolution<double, NZ, M> sol;
   const DirectCert<NZ, M> cp{P};
-  lnp_solve<double, double, DirectCert<NZ, M>, NZ, M>(P, cp, sol, kTolSlack, kTolDual);
+  lnp_solve<double, double, DirectCert<NZ, M>, DensePat, NZ, M>(P, cp, sol, kTolSlack, kTolDual);
   double yv[NZ];
   RCBF_UNROLL
   for (int j = 0; j < NZ; ++j) yv[j] = sol.y[j] - v[j];

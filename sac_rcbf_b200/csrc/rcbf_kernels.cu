@@ -12,6 +12,7 @@
 #include "rcbf_core.cuh"
 #include "rcbf_dynamics.cuh"
 #include "rcbf_generic.cuh"
+#include "rcbf_safe_kernels.cuh"
 
 using namespace rcbf;
 
@@ -125,147 +126,6 @@ __global__ void __launch_bounds__(kThreads) k_cars_assemble(const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K2+K3: get_safe_action forward.
-//   pass 1 (kMode 0: greedy presolve + float64 certificate; kMode 1: float32 interior point + certificate) handles every
-//   instance; the rare ones it cannot certify get a tagged-NaN sentinel in safe_action[i][0] and nothing else.
-//   pass 2 (k_*_fallback, a grid-stride scan for the sentinel) re-solves those with the interior-point chain
-//   (float32, then float64).  Keeping the float64 interior point out of pass 1 is what keeps its register count low.
-// ------------------------------------------------------------------------------------------------------------
-constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
-
-__device__ __forceinline__ bool is_pending(const float* p) { return __float_as_uint(__ldcg(p)) == kPendingBits; }
-
-__device__ __forceinline__ void write_unicycle_solution(int64_t i, const UniSolve& w, const float us[2],
-                                                        float* __restrict__ out, float* __restrict__ x,
-                                                        float* __restrict__ lam, float* __restrict__ slack,
-                                                        int32_t* __restrict__ status, int32_t* __restrict__ iters) {
-  store_row<2>(out, i, us);
-  if (x != nullptr) {
-#pragma unroll
-    for (int j = 0; j < kUniNZ; ++j) x[i * kUniNZ + j] = (float)w.sol.x[j];
-  }
-  if (lam != nullptr) {
-#pragma unroll
-    for (int r = 0; r < kUniM; ++r) lam[i * kUniM + r] = (float)w.sol.lam[r];
-  }
-  if (slack != nullptr) {
-#pragma unroll
-    for (int r = 0; r < kUniM; ++r) slack[i * kUniM + r] = (float)w.sol.s[r];
-  }
-  if (status != nullptr) status[i] = w.sol.status;
-  if (iters != nullptr) iters[i] = w.sol.iters;
-}
-
-__device__ __forceinline__ void write_cars_solution(int64_t i, const CarsSolve& w, float us, float* __restrict__ out,
-                                                    float* __restrict__ x, float* __restrict__ lam,
-                                                    float* __restrict__ slack, int32_t* __restrict__ status,
-                                                    int32_t* __restrict__ iters) {
-  out[i] = us;
-  if (x != nullptr) {
-#pragma unroll
-    for (int j = 0; j < kCarsNZ; ++j) x[i * kCarsNZ + j] = (float)w.sol.x[j];
-  }
-  if (lam != nullptr) {
-#pragma unroll
-    for (int r = 0; r < kCarsM; ++r) lam[i * kCarsM + r] = (float)w.sol.lam[r];
-  }
-  if (slack != nullptr) {
-#pragma unroll
-    for (int r = 0; r < kCarsM; ++r) slack[i * kCarsM + r] = (float)w.sol.s[r];
-  }
-  if (status != nullptr) status[i] = w.sol.status;
-  if (iters != nullptr) iters[i] = w.sol.iters;
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_unicycle_safe_action(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
-                       const float* __restrict__ sg, int64_t n, UnicycleParams p, float* __restrict__ out,
-                       float* __restrict__ x, float* __restrict__ lam, float* __restrict__ slack,
-                       int32_t* __restrict__ status, int32_t* __restrict__ iters, rcbf_counters_t* counters) {
-  const int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool valid = i0 < n;
-  const int64_t i = valid ? i0 : n - 1;
-  float s[3], u[2], m[3], g[3];
-  load_row<3>(st, i, s);
-  load_row<2>(ac, i, u);
-  load_row<3>(mu, i, m);
-  load_row<3>(sg, i, g);
-  UniSolve w;
-  float us[2];
-  unicycle_safe_action<kMode>(p, s, u, m, g, w, us);
-  if (valid) {
-    if (w.sol.status == RCBF_PENDING) out[i * 2] = __uint_as_float(kPendingBits);
-    else write_unicycle_solution(i, w, us, out, x, lam, slack, status, iters);
-  }
-  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_unicycle_safe_action_fallback(const float* __restrict__ st, const float* __restrict__ ac,
-                                const float* __restrict__ mu, const float* __restrict__ sg, int64_t n, UnicycleParams p,
-                                float* out, float* __restrict__ x, float* __restrict__ lam, float* __restrict__ slack,
-                                int32_t* __restrict__ status, int32_t* __restrict__ iters, rcbf_counters_t* counters) {
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    if (!is_pending(out + i * 2)) continue;
-    float s[3], u[2], m[3], g[3];
-    load_row<3>(st, i, s);
-    load_row<2>(ac, i, u);
-    load_row<3>(mu, i, m);
-    load_row<3>(sg, i, g);
-    UniSolve w;
-    float us[2];
-    unicycle_safe_action<kMode>(p, s, u, m, g, w, us);
-    write_unicycle_solution(i, w, us, out, x, lam, slack, status, iters);
-    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
-  }
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_cars_safe_action(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg, int64_t n,
-                   CarsParams p, float* __restrict__ out, float* __restrict__ x, float* __restrict__ lam,
-                   float* __restrict__ slack, int32_t* __restrict__ status, int32_t* __restrict__ iters,
-                   rcbf_counters_t* counters) {
-  const int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool valid = i0 < n;
-  const int64_t i = valid ? i0 : n - 1;
-  float s[10], g[10];
-  load_row<10>(st, i, s);
-  load_row<10>(sg, i, g);
-  const float u = __ldg(ac + i);
-  CarsSolve w;
-  float us;
-  cars_safe_action<kMode>(p, s, u, g, w, &us);
-  if (valid) {
-    if (w.sol.status == RCBF_PENDING) out[i] = __uint_as_float(kPendingBits);
-    else write_cars_solution(i, w, us, out, x, lam, slack, status, iters);
-  }
-  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_cars_safe_action_fallback(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg,
-                            int64_t n, CarsParams p, float* out, float* __restrict__ x, float* __restrict__ lam,
-                            float* __restrict__ slack, int32_t* __restrict__ status, int32_t* __restrict__ iters,
-                            rcbf_counters_t* counters) {
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    if (!is_pending(out + i)) continue;
-    float s[10], g[10];
-    load_row<10>(st, i, s);
-    load_row<10>(sg, i, g);
-    const float u = __ldg(ac + i);
-    CarsSolve w;
-    float us;
-    cars_safe_action<kMode>(p, s, u, g, w, &us);
-    write_cars_solution(i, w, us, out, x, lam, slack, status, iters);
-    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // K4: backward (recomputes the cheap assembly, reads the saved x / lam / slack)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads)
@@ -287,7 +147,7 @@ k_unicycle_safe_action_bwd(const float* __restrict__ st, const float* __restrict
   UniRaw raw;
   assemble_unicycle(p, s, u, m, g, raw);
   Normalised<kUniNZ, kUniM> nrm;
-  normalise_rows<kUniNZ, kUniM>(raw.G, raw.h, nrm);
+  normalise_rows<UniPat, kUniNZ, kUniM>(raw.G, raw.h, nrm);
   float r[kUniM][2];
 #pragma unroll
   for (int k = 0; k < kUniHaz; ++k) {
@@ -323,7 +183,7 @@ k_cars_safe_action_bwd(const float* __restrict__ st, const float* __restrict__ a
   CarsRaw raw;
   assemble_cars(p, s, u, g, raw);
   Normalised<kCarsNZ, kCarsM> nrm;
-  normalise_rows<kCarsNZ, kCarsM>(raw.G, raw.h, nrm);
+  normalise_rows<CarsPat, kCarsNZ, kCarsM>(raw.G, raw.h, nrm);
   float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
   float ga[1];
   const float uu[1] = {u}, lo[1] = {p.u_min}, hi[1] = {p.u_max}, gg[1] = {go};
@@ -483,149 +343,6 @@ k_cars_predict_next(const T* __restrict__ state, const T* __restrict__ action, c
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K5: fused safe step = assemble + QP + clamp + env.step, one launch (+ the sentinel-scan fallback pass)
-// ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void finish_unicycle_step(int64_t i, const UnicycleEnvParams& e, float v[4], int stp,
-                                                     const float us[2], int status_v, float* __restrict__ state4,
-                                                     int32_t* __restrict__ step, float* __restrict__ safe_action,
-                                                     float* __restrict__ obs, float* __restrict__ reward,
-                                                     uint8_t* __restrict__ done, float* __restrict__ cost,
-                                                     uint8_t* __restrict__ goal_met, int32_t* __restrict__ status) {
-  UniEnvOut<float> o;
-  unicycle_env_step<float>(e, v, v[3], stp, us, o);
-  store_row<2>(safe_action, i, us);
-  store_row<7>(obs, i, o.obs);
-  reward[i] = o.reward;
-  done[i] = (uint8_t)o.done;
-  cost[i] = o.cost;
-  goal_met[i] = (uint8_t)o.goal_met;
-  if (status != nullptr) status[i] = status_v;
-  if (e.auto_reset && o.done) unicycle_reset<float>(e, v, v[3], stp);
-  store_state4<float>(state4, i, v);
-  step[i] = stp;
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_unicycle_safe_step(float* __restrict__ state4, int32_t* __restrict__ step, const float* __restrict__ ac,
-                     const float* __restrict__ mu, const float* __restrict__ sg, int64_t n, UnicycleParams p,
-                     UnicycleEnvParams e, float* __restrict__ safe_action, float* __restrict__ obs,
-                     float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ cost,
-                     uint8_t* __restrict__ goal_met, int32_t* __restrict__ status, rcbf_counters_t* counters) {
-  const int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool valid = i0 < n;
-  const int64_t i = valid ? i0 : n - 1;
-  float v[4], u[2], m[3], g[3];
-  load_state4<float>(state4, i, v);
-  load_row<2>(ac, i, u);
-  load_row<3>(mu, i, m);
-  load_row<3>(sg, i, g);
-  const int stp = step[i];
-  UniSolve w;
-  float us[2];
-  unicycle_safe_action<kMode>(p, v, u, m, g, w, us);
-  if (valid) {
-    if (w.sol.status == RCBF_PENDING) safe_action[i * 2] = __uint_as_float(kPendingBits);
-    else finish_unicycle_step(i, e, v, stp, us, w.sol.status, state4, step, safe_action, obs, reward, done, cost,
-                              goal_met, status);
-  }
-  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_unicycle_safe_step_fallback(float* __restrict__ state4, int32_t* __restrict__ step, const float* __restrict__ ac,
-                              const float* __restrict__ mu, const float* __restrict__ sg, int64_t n, UnicycleParams p,
-                              UnicycleEnvParams e, float* safe_action, float* __restrict__ obs,
-                              float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ cost,
-                              uint8_t* __restrict__ goal_met, int32_t* __restrict__ status, rcbf_counters_t* counters) {
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    if (!is_pending(safe_action + i * 2)) continue;
-    float v[4], u[2], m[3], g[3];
-    load_state4<float>(state4, i, v);
-    load_row<2>(ac, i, u);
-    load_row<3>(mu, i, m);
-    load_row<3>(sg, i, g);
-    const int stp = step[i];
-    UniSolve w;
-    float us[2];
-    unicycle_safe_action<kMode>(p, v, u, m, g, w, us);
-    finish_unicycle_step(i, e, v, stp, us, w.sol.status, state4, step, safe_action, obs, reward, done, cost, goal_met,
-                         status);
-    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
-  }
-}
-
-__device__ __forceinline__ void finish_cars_step(int64_t i, const CarsEnvParams& e, float s[10], float tt, int stp,
-                                                 float us, int status_v, float* __restrict__ state,
-                                                 float* __restrict__ t, int32_t* __restrict__ step,
-                                                 float* __restrict__ safe_action, float* __restrict__ obs,
-                                                 float* __restrict__ reward, uint8_t* __restrict__ done,
-                                                 float* __restrict__ cost, int32_t* __restrict__ status) {
-  CarsEnvOut<float> o;
-  cars_env_step<float>(e, s, tt, stp, us, o);
-  safe_action[i] = us;
-  store_row<10>(obs, i, o.obs);
-  reward[i] = o.reward;
-  done[i] = (uint8_t)o.done;
-  cost[i] = o.cost;
-  if (status != nullptr) status[i] = status_v;
-  store_row<10>(state, i, s);
-  t[i] = tt;
-  step[i] = stp;
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_cars_safe_step(float* __restrict__ state, float* __restrict__ t, int32_t* __restrict__ step,
-                 const float* __restrict__ ac, const float* __restrict__ sg, int64_t n, CarsParams p, CarsEnvParams e,
-                 float* __restrict__ safe_action, float* __restrict__ obs, float* __restrict__ reward,
-                 uint8_t* __restrict__ done, float* __restrict__ cost, int32_t* __restrict__ status,
-                 rcbf_counters_t* counters) {
-  const int64_t i0 = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  const bool valid = i0 < n;
-  const int64_t i = valid ? i0 : n - 1;
-  float s[10], g[10];
-  load_row<10>(state, i, s);
-  load_row<10>(sg, i, g);
-  const float u = __ldg(ac + i);
-  const float tt = t[i];
-  const int stp = step[i];
-  CarsSolve w;
-  float us;
-  cars_safe_action<kMode>(p, s, u, g, w, &us);
-  if (valid) {
-    if (w.sol.status == RCBF_PENDING) safe_action[i] = __uint_as_float(kPendingBits);
-    else finish_cars_step(i, e, s, tt, stp, us, w.sol.status, state, t, step, safe_action, obs, reward, done, cost,
-                          status);
-  }
-  accumulate_counters(counters, valid, w.sol.status, w.sol.iters);
-}
-
-template <int kMode>
-__global__ void __launch_bounds__(kThreads)
-k_cars_safe_step_fallback(float* __restrict__ state, float* __restrict__ t, int32_t* __restrict__ step,
-                          const float* __restrict__ ac, const float* __restrict__ sg, int64_t n, CarsParams p,
-                          CarsEnvParams e, float* safe_action, float* __restrict__ obs, float* __restrict__ reward,
-                          uint8_t* __restrict__ done, float* __restrict__ cost, int32_t* __restrict__ status,
-                          rcbf_counters_t* counters) {
-  for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-    if (!is_pending(safe_action + i)) continue;
-    float s[10], g[10];
-    load_row<10>(state, i, s);
-    load_row<10>(sg, i, g);
-    const float u = __ldg(ac + i);
-    const float tt = t[i];
-    const int stp = step[i];
-    CarsSolve w;
-    float us;
-    cars_safe_action<kMode>(p, s, u, g, w, &us);
-    finish_cars_step(i, e, s, tt, stp, us, w.sol.status, state, t, step, safe_action, obs, reward, done, cost, status);
-    accumulate_counters_thread(counters, w.sol.status, w.sol.iters);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
 // generic QP (cbf_layer / solve_qp API), float64
 // ------------------------------------------------------------------------------------------------------------
 template <int NZ, int M>
@@ -684,7 +401,7 @@ __global__ void k_fp32_fma_probe(float* sink, int iters) {
 // ================================================================================================================
 extern "C" {
 
-const char* rcbf_version(void) { return "rcbf_b200 0.1 (sm_100a)"; }
+const char* rcbf_version(void) { return "rcbf_b200 0.2 (sm_100a)"; }
 
 int rcbf_unicycle_assemble(const float* state, const float* action, const float* mean, const float* sigma, int64_t n,
                            const rcbf_unicycle_params* p, float* G, float* h, void* stream) {
@@ -704,42 +421,20 @@ int rcbf_cars_assemble(const float* state, const float* action, const float* sig
 
 int rcbf_unicycle_safe_action(const float* state, const float* action, const float* mean, const float* sigma, int64_t n,
                               const rcbf_unicycle_params* p, float* safe_action, float* x, float* lam, float* slack,
-                              int32_t* status, int32_t* iters, rcbf_counters_t* counters, void* stream) {
-  if (n <= 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (p->solver_mode == 0) {
-    k_unicycle_safe_action<0><<<grid_for(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action, x, lam,
-                                                               slack, status, iters, counters);
-    k_unicycle_safe_action_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action,
-                                                                         x, lam, slack, status, iters, counters);
-  } else {
-    k_unicycle_safe_action<1><<<grid_for(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action, x, lam,
-                                                               slack, status, iters, counters);
-    k_unicycle_safe_action_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(state, action, mean, sigma, n, *p, safe_action,
-                                                                         x, lam, slack, status, iters, counters);
-  }
-  RCBF_LAUNCH_CHECK();
-  return 0;
+                              int32_t* status, int32_t* iters, rcbf_counters_t* workspace, void* stream) {
+  UniArgs a{};
+  a.st = state; a.ac = action; a.mu = mean; a.sg = sigma;
+  a.out = safe_action; a.x = x; a.lam = lam; a.slack = slack; a.status = status; a.iters = iters;
+  return launch_safe<UniEnv<false>>(a, n, *p, rcbf_unicycle_env_params{}, workspace, (cudaStream_t)stream);
 }
 
 int rcbf_cars_safe_action(const float* state, const float* action, const float* sigma, int64_t n,
                           const rcbf_cars_params* p, float* safe_action, float* x, float* lam, float* slack,
-                          int32_t* status, int32_t* iters, rcbf_counters_t* counters, void* stream) {
-  if (n <= 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (p->solver_mode == 0) {
-    k_cars_safe_action<0><<<grid_for(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam, slack,
-                                                           status, iters, counters);
-    k_cars_safe_action_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam,
-                                                                     slack, status, iters, counters);
-  } else {
-    k_cars_safe_action<1><<<grid_for(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam, slack,
-                                                           status, iters, counters);
-    k_cars_safe_action_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(state, action, sigma, n, *p, safe_action, x, lam,
-                                                                     slack, status, iters, counters);
-  }
-  RCBF_LAUNCH_CHECK();
-  return 0;
+                          int32_t* status, int32_t* iters, rcbf_counters_t* workspace, void* stream) {
+  CarsArgs a{};
+  a.st = state; a.ac = action; a.sg = sigma;
+  a.out = safe_action; a.x = x; a.lam = lam; a.slack = slack; a.status = status; a.iters = iters;
+  return launch_safe<CarsEnv<false>>(a, n, *p, rcbf_cars_env_params{}, workspace, (cudaStream_t)stream);
 }
 
 int rcbf_unicycle_safe_action_bwd(const float* state, const float* action, const float* mean, const float* sigma,
@@ -848,43 +543,23 @@ RCBF_ENV_FUNCS(f64, double)
 int rcbf_unicycle_safe_step(float* state4, int32_t* step, const float* action_rl, const float* mean, const float* sigma,
                             int64_t n, const rcbf_unicycle_params* p, const rcbf_unicycle_env_params* e,
                             float* safe_action, float* obs, float* reward, uint8_t* done, float* cost, uint8_t* goal_met,
-                            int32_t* status, rcbf_counters_t* counters, void* stream) {
-  if (n <= 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (p->solver_mode == 0) {
-    k_unicycle_safe_step<0><<<grid_for(n), kThreads, 0, s>>>(state4, step, action_rl, mean, sigma, n, *p, *e, safe_action,
-                                                             obs, reward, done, cost, goal_met, status, counters);
-    k_unicycle_safe_step_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(
-        state4, step, action_rl, mean, sigma, n, *p, *e, safe_action, obs, reward, done, cost, goal_met, status, counters);
-  } else {
-    k_unicycle_safe_step<1><<<grid_for(n), kThreads, 0, s>>>(state4, step, action_rl, mean, sigma, n, *p, *e, safe_action,
-                                                             obs, reward, done, cost, goal_met, status, counters);
-    k_unicycle_safe_step_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(
-        state4, step, action_rl, mean, sigma, n, *p, *e, safe_action, obs, reward, done, cost, goal_met, status, counters);
-  }
-  RCBF_LAUNCH_CHECK();
-  return 0;
+                            int32_t* status, rcbf_counters_t* workspace, void* stream) {
+  UniArgs a{};
+  a.state4 = state4; a.step = step; a.ac = action_rl; a.mu = mean; a.sg = sigma;
+  a.out = safe_action; a.status = status;
+  a.obs = obs; a.reward = reward; a.done = done; a.cost = cost; a.goal_met = goal_met;
+  return launch_safe<UniEnv<true>>(a, n, *p, *e, workspace, (cudaStream_t)stream);
 }
 
 int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* action_rl, const float* sigma, int64_t n,
                         const rcbf_cars_params* p, const rcbf_cars_env_params* e, float* safe_action, float* obs,
-                        float* reward, uint8_t* done, float* cost, int32_t* status, rcbf_counters_t* counters,
+                        float* reward, uint8_t* done, float* cost, int32_t* status, rcbf_counters_t* workspace,
                         void* stream) {
-  if (n <= 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (p->solver_mode == 0) {
-    k_cars_safe_step<0><<<grid_for(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e, safe_action, obs,
-                                                         reward, done, cost, status, counters);
-    k_cars_safe_step_fallback<2><<<grid_scan(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e,
-                                                                   safe_action, obs, reward, done, cost, status, counters);
-  } else {
-    k_cars_safe_step<1><<<grid_for(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e, safe_action, obs,
-                                                         reward, done, cost, status, counters);
-    k_cars_safe_step_fallback<3><<<grid_scan(n), kThreads, 0, s>>>(state, t, step, action_rl, sigma, n, *p, *e,
-                                                                   safe_action, obs, reward, done, cost, status, counters);
-  }
-  RCBF_LAUNCH_CHECK();
-  return 0;
+  CarsArgs a{};
+  a.state = state; a.t = t; a.step = step; a.ac = action_rl; a.sg = sigma;
+  a.out = safe_action; a.status = status;
+  a.obs = obs; a.reward = reward; a.done = done; a.cost = cost;
+  return launch_safe<CarsEnv<true>>(a, n, *p, *e, workspace, (cudaStream_t)stream);
 }
 
 int rcbf_fp32_fma_probe(float* sink, int blocks, int threads, int iters, void* stream) {
@@ -904,14 +579,14 @@ struct HostPipe {
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
   float* scratch = nullptr;
   size_t scratch_floats = 0;
-  rcbf_counters_t* counters = nullptr;
+  rcbf_counters_t* counters = nullptr;  // 3 workspaces of RCBF_WS_WORDS words, one per stream
   int ensure(int dev, size_t floats) {
     cudaError_t e;
     if (device != dev) {
       if ((e = cudaSetDevice(dev)) != cudaSuccess) return (int)e;
       for (auto& s : streams)
         if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-      if ((e = cudaMalloc(&counters, 8 * sizeof(rcbf_counters_t))) != cudaSuccess) return (int)e;
+      if ((e = cudaMalloc(&counters, 3 * RCBF_WS_WORDS * sizeof(rcbf_counters_t))) != cudaSuccess) return (int)e;
       device = dev;
     }
     if (floats > scratch_floats) {
@@ -934,7 +609,7 @@ int run_host_pipe(const float* const* in_host, const int* in_width, int n_in, fl
   if (rc) return rc;
   cudaSetDevice(device);
   if (chunks < 1) chunks = 1;
-  cudaMemsetAsync(g_pipe.counters, 0, 8 * sizeof(rcbf_counters_t), g_pipe.streams[0]);
+  cudaMemsetAsync(g_pipe.counters, 0, 3 * RCBF_WS_WORDS * sizeof(rcbf_counters_t), g_pipe.streams[0]);
   cudaStreamSynchronize(g_pipe.streams[0]);
   float* dev_in[8];
   float* cur = g_pipe.scratch;
@@ -952,16 +627,20 @@ int run_host_pipe(const float* const* in_host, const int* in_width, int n_in, fl
     for (int k = 0; k < n_in; ++k)
       cudaMemcpyAsync(dev_in[k] + lo * in_width[k], in_host[k] + lo * in_width[k], cnt * in_width[k] * sizeof(float),
                       cudaMemcpyHostToDevice, s);
-    rc = launch(dev_in, dev_out, lo, cnt, g_pipe.counters, s);
+    rc = launch(dev_in, dev_out, lo, cnt, g_pipe.counters + (c % 3) * RCBF_WS_WORDS, s);
     if (rc) return rc;
     cudaMemcpyAsync(out_host + lo * out_width, dev_out + lo * out_width, cnt * out_width * sizeof(float),
                     cudaMemcpyDeviceToHost, s);
   }
-  rcbf_counters_t host_counters[8];
   for (auto& s : g_pipe.streams) cudaStreamSynchronize(s);
-  cudaError_t e = cudaMemcpy(host_counters, g_pipe.counters, sizeof(host_counters), cudaMemcpyDeviceToHost);
-  if (e != cudaSuccess) return (int)e;
-  if (n_failed_host) *n_failed_host = (int32_t)host_counters[0];
+  rcbf_counters_t nan_count = 0;
+  for (int k = 0; k < 3; ++k) {
+    rcbf_counters_t v = 0;
+    cudaError_t e = cudaMemcpy(&v, g_pipe.counters + k * RCBF_WS_WORDS, sizeof(v), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    nan_count += v;
+  }
+  if (n_failed_host) *n_failed_host = (int32_t)nan_count;
   return (int)cudaGetLastError();
 }
 }  // namespace

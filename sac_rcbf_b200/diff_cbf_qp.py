@@ -136,6 +136,15 @@ class CBFQPLayer:
         self._last_counters = None  # device tensor [nan, uncertified, f64 passes, trivial, sum iters, ...]
         self._params_cache = None
 
+    def _workspace(self):
+        """RCBF_WS_WORDS-word solver workspace (counters + fallback queue) with the counters zeroed for this call."""
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.device != self.device:
+            ws = self._ws = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=self.device)
+        else:
+            ws[:8].zero_()
+        return ws
+
     # ------------------------------------------------------------------------------------------------------ params
     def _solver_mode(self):
         if self.solver not in ("presolve", "pdipm"):
@@ -179,7 +188,7 @@ class CBFQPLayer:
         if want_status:
             status = torch.empty((n,), dtype=torch.int32, device=dev)
             iters = torch.empty((n,), dtype=torch.int32, device=dev)
-        counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        counters = self._workspace()
         p = self._params()
         with torch.cuda.device(dev):
             if mode == 'Unicycle':
@@ -298,7 +307,7 @@ class CBFQPLayer:
         """Counters of the last launch: dict(nan, uncertified, f64_passes, trivial, sum_iters)."""
         if self._last_counters is None:
             return None
-        c = self._last_counters.cpu().tolist()
+        c = self._last_counters[:8].cpu().tolist()
         return dict(nan=c[0], uncertified=c[1], f64_passes=c[2], trivial=c[3], sum_iters=c[4], fallback=c[5],
                     fallback_iters=c[6])
 

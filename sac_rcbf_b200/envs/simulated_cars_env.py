@@ -129,7 +129,7 @@ class SimulatedCarsEnv:
         sg = sigma_pred.detach().to(dev, torch.float32).contiguous()
         if not hasattr(self, "_safe_action"):
             self._safe_action = torch.empty((n, 1), dtype=torch.float32, device=dev)
-            self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+            self._counters = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=dev)
         status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None
         with torch.cuda.device(dev):
             rc = self._lib.rcbf_cars_safe_step(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step),

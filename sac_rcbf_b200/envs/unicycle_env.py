@@ -160,7 +160,7 @@ class UnicycleEnv:
         n = self.num_envs
         if not hasattr(self, "_safe_action"):
             self._safe_action = torch.empty((n, 2), dtype=torch.float32, device=dev)
-            self._counters = torch.zeros(8, dtype=torch.int64, device=dev)
+            self._counters = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=dev)
         status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None
         with torch.cuda.device(dev):
             rc = self._lib.rcbf_unicycle_safe_step(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(ac),

@@ -5,6 +5,6 @@ timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; 
 timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 PROF="python bench.py --steps 3 --warmup 3 --no-extra --cpu-seconds 0"
 $PROF > gpurun_out/plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_|probe" --csv --log-file gpurun_out/launches.csv $PROF > gpurun_out/ncu_launches.log 2>&1; echo "ncu launches rc=$?"
 $PROF > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_unicycle_safe_step -s 4 -c 2 -f -o gpurun_out/prof_unicycle_safe_step $PROF > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
+ncu --set full --clock-control none --import-source on -k regex:k_safe -s 6 -c 2 -f -o gpurun_out/prof_k_safe $PROF > gpurun_out/ncu_full.log 2>&1; echo "ncu full rc=$?"; tail -3 gpurun_out/ncu_full.log
