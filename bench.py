@@ -294,7 +294,7 @@ def main():
     SETS = 2
     st0, batches = synth_inputs(n, device, 12345 + rank, SETS)
     env.state = st0
-    env._counters = torch.zeros(2048, dtype=torch.int64, device=device)   # RCBF_WS_WORDS
+    env._counters = torch.zeros(32768, dtype=torch.int64, device=device)   # RCBF_WS_WORDS
     env._safe_action = torch.empty((n, 2), dtype=torch.float32, device=device)
 
     def step(k):
@@ -348,7 +348,7 @@ def main():
                      rew=torch.empty((n,)).pin_memory(), cost=torch.empty((n,)).pin_memory(),
                      done=torch.empty((n,), dtype=torch.uint8).pin_memory())
         streams = [torch.cuda.Stream(device) for _ in range(3)]
-        wss = [torch.zeros(2048, dtype=torch.int64, device=device) for _ in range(3)]   # one workspace per stream
+        wss = [torch.zeros(32768, dtype=torch.int64, device=device) for _ in range(3)]   # one workspace per stream
         p_layer, p_env = layer._params(), env._env_params()
 
         def e2e_step(k):

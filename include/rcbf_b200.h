@@ -86,7 +86,7 @@ typedef struct {
  *   [8..15] queue bookkeeping, [16..) indices of the instances queued for the fallback pass (reset by the library).
  * The counters [0..7] accumulate with atomics across calls; zero them when you want per-call numbers.  Nullable: the
  * fallback pass then scans safe_action for its pending sentinel instead of reading the queue (slower). */
-#define RCBF_WS_WORDS 2048
+#define RCBF_WS_WORDS 32768
 typedef unsigned long long rcbf_counters_t;
 
 /* ---- constraint assembly (raw P,q are constants: P = diag(p_diag), q = 0) ------------------------------------- */

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 UNI_HAZ = 5
-WS_WORDS = 2048  # RCBF_WS_WORDS: solver workspace (counters + fallback queue), 64-bit words
+WS_WORDS = 32768  # RCBF_WS_WORDS: solver workspace (counters + fallback queue), 64-bit words
 
 
 class UnicycleParams(C.Structure):

@@ -1,19 +1,21 @@
 // rcbf_safe_kernels.cuh -- the hot kernels: get_safe_action forward (K2+K3) and the fused safe step (K5).
 //
-// One CUDA thread owns one instance, 256 threads per block, three phases per block:
+// One lane owns one instance; warps are persistent and walk 32-instance tiles (coalesced row-major loads).
+// Per tile ("A-step") every lane assembles the constraints in the reference's float32 op order, normalises the rows
+// and runs the trivial test (h~ >= 0 on every row  <=>  x = 0 is optimal, ~2/3 of the synthetic instances); trivial
+// lanes finish right there (clamp, env.step, outputs).  Lanes whose instance needs a solve push its packed problem
+// (28 words Unicycle / 10 words SimulatedCars + the instance index) into a WARP-PRIVATE ring in shared memory.
+// Whenever the ring holds >= 32 problems the warp runs a "B-step": all 32 lanes solve one problem each (greedy
+// active-set presolve + float64 KKT certificate, or the float32 interior point in "pdipm" mode), reload the 28 bytes
+// of instance inputs they need and finish that instance.  So the expensive phase always runs with full warps (without
+// compaction it ran at ~35 % lane utilisation), and there is no block-wide barrier anywhere: warps never wait for
+// each other.
 //
-//   A  every thread: coalesced loads, constraint assembly in the reference's float32 op order, row normalisation,
-//      and the trivial test (h~ >= 0 on every row  <=>  x = 0 is optimal; ~2/3 of the synthetic instances).
-//      Threads whose instance needs a solve pack its 28 (Unicycle) / 10 (SimulatedCars) words into shared memory at a
-//      slot handed out with one ballot + one shared atomic per warp.
-//   B  the first `count` threads of the block solve the packed problems (greedy active-set presolve + float64 KKT
-//      certificate, or the float32 interior point in "pdipm" mode) and hand the correction back through shared memory.
-//      Compaction is what keeps the warps of this phase full: without it they run at ~35 % lane utilisation.
-//   C  every thread: clamp, and for the fused kernel env.step + all env outputs (one float4 state store).
-//
-// Instances phase B cannot certify get a tagged-NaN sentinel in safe_action[i][0] and are queued (workspace words
-// [16..), see include/rcbf_b200.h); k_safe_fallback re-solves them with the interior-point chain and finishes them.
-// If the caller passes no workspace, or the queue overflows, the fallback scans for the sentinel instead.
+// Instances a B-step cannot certify get a tagged-NaN sentinel in safe_action[i][0] and are queued in the caller's
+// workspace; pass 2 (k_safe_fallback_*) finishes them: one WARP per instance enumerates every active set of size
+// <= nz (129 / 10 candidates) with the same float64 certificate, the interior point being the last resort
+// ("presolve" mode), or one thread per instance runs the float64 interior point ("pdipm" mode).  Without a
+// workspace, or when its queue overflows, pass 2 scans for the sentinel instead.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -23,7 +25,6 @@
 
 namespace rcbf {
 
-constexpr int kBlock = 256;
 constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
 constexpr int kWsCounters = 8;                 // workspace words [0, 8): counters
 constexpr int kWsQueueCount = 8;               // [8]: number of queued instances
@@ -79,9 +80,7 @@ struct UniEnv {
     float u[2];
     int stp;
   };
-  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, Inst& in,
-                                                  Normalised<NZ, M>& nrm) {
-    float m[3], g[3];
+  __device__ static __forceinline__ void load_inst(const Args& a, int64_t i, Inst& in) {
     if (kFused) {
       const float4 q = reinterpret_cast<const float4*>(a.state4)[i];
       in.v[0] = q.x; in.v[1] = q.y; in.v[2] = q.z; in.v[3] = q.w;
@@ -92,6 +91,10 @@ struct UniEnv {
       in.stp = 0;
     }
     ld_row<2>(a.ac, i, in.u);
+  }
+  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
+                                                  Normalised<NZ, M>& nrm) {
+    float m[3], g[3];
     ld_row<3>(a.mu, i, m);
     ld_row<3>(a.sg, i, g);
     UniRaw raw;
@@ -151,7 +154,17 @@ struct CarsEnv {
     float tt;
     int stp;
   };
-  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, Inst& in,
+  __device__ static __forceinline__ void load_inst(const Args& a, int64_t i, Inst& in) {
+    in.u[0] = __ldg(a.ac + i);
+    if (kFused) {
+      in.tt = a.t[i];
+      in.stp = a.step[i];
+    } else {
+      in.tt = 0.f;
+      in.stp = 0;
+    }
+  }
+  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
                                                   Normalised<NZ, M>& nrm) {
     float s[10], g[10];
     const float2* sp = reinterpret_cast<const float2*>(kFused ? a.state : a.st) + i * 5;  // rows are 40 B: 8-aligned
@@ -162,14 +175,6 @@ struct CarsEnv {
       const float2 r = __ldg(gp + k);
       s[2 * k] = q.x; s[2 * k + 1] = q.y;
       g[2 * k] = r.x; g[2 * k + 1] = r.y;
-    }
-    in.u[0] = __ldg(a.ac + i);
-    if (kFused) {
-      in.tt = a.t[i];
-      in.stp = a.step[i];
-    } else {
-      in.tt = 0.f;
-      in.stp = 0;
     }
     CarsRaw raw;
     assemble_cars(p, s, in.u[0], g, raw);
@@ -251,139 +256,169 @@ __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i
   if (a.iters != nullptr) a.iters[i] = sol.iters;
 }
 
-__device__ __forceinline__ void block_counters(rcbf_counters_t* ws, bool valid, int status, int iters) {
-  if (ws == nullptr) return;
-  const int n_nan = __syncthreads_count(valid && status == RCBF_NAN);
-  const int n_triv = __syncthreads_count(valid && status == RCBF_OK_TRIVIAL);
-  const int n_pend = __syncthreads_count(valid && status == RCBF_PENDING);
-  __shared__ int s_it;
-  if (threadIdx.x == 0) s_it = 0;
-  __syncthreads();
-  int it = (valid && status != RCBF_PENDING) ? iters : 0;
-  it = __reduce_add_sync(0xffffffffu, it);
-  if ((threadIdx.x & 31) == 0 && it) atomicAdd(&s_it, it);
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    if (n_nan) atomicAdd(&ws[0], (unsigned long long)n_nan);
-    if (n_triv) atomicAdd(&ws[3], (unsigned long long)n_triv);
-    if (s_it) atomicAdd(&ws[4], (unsigned long long)s_it);
-    if (n_pend) atomicAdd(&ws[5], (unsigned long long)n_pend);
+// ---------------------------------------------------------------------------------------------------------------
+// pass 1: persistent warps, warp-private compaction ring
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWarps = 4;             // warps per block
+constexpr int kThreadsW = 32 * kWarps;
+constexpr int kRing = 64;             // ring capacity per warp: at most 31 left over + 32 new
+
+template <class E>
+struct WarpRing {
+  float w[E::NW][kRing];
+  int idx[kRing];
+};
+
+struct LaneCounters {
+  int nan = 0, triv = 0, pend = 0, iters = 0;
+};
+
+template <class E>
+__device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t i, rcbf_counters_t* ws) {
+  a.out[i * E::NU] = __uint_as_float(kPendingBits);
+  if (ws != nullptr) {
+    const unsigned long long slot = atomicAdd(&ws[kWsQueueCount], 1ULL);
+    if (slot < (unsigned long long)kWsQueueCap) ws[kWsQueueBase + slot] = (unsigned long long)i;
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// pass 1
-// ---------------------------------------------------------------------------------------------------------------
-template <class E, int kMode /* 0 presolve, 1 pdipm */>
-__global__ void __launch_bounds__(kBlock, kMode == 0 ? 2 : 1)
-k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
+template <class E, int kMode>
+__device__ __forceinline__ void solve_batch(const typename E::Args& a, const typename E::Params& p,
+                                            const typename E::EnvParams& e, rcbf_counters_t* ws, WarpRing<E>& ring,
+                                            int head, int cnt, int lane, LaneCounters& lc) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NW = E::NW;
-  __shared__ float s_prob[NW][kBlock];
-  __shared__ float s_res[NU][kBlock];
-  __shared__ int s_stat[kBlock];
-  __shared__ unsigned short s_owner[kBlock];
-  __shared__ int s_count;
-
-  const int tid = threadIdx.x;
-  const int64_t base = (int64_t)blockIdx.x * kBlock;
-  const bool valid = base + tid < n;
-  const int64_t i = valid ? base + tid : n - 1;
-  if (tid == 0) s_count = 0;
-
-  // ---- phase A
-  typename E::Inst in;
-  bool triv = true, nan = false;
-  {
-    Normalised<NZ, M> nrm;
-    E::assemble(a, p, i, in, nrm);
-#pragma unroll
-    for (int r = 0; r < M; ++r) {
-      triv = triv && (nrm.hn[r] >= 0.f);
-      nan = nan || (nrm.hn[r] != nrm.hn[r]);
-#pragma unroll
-      for (int j = 0; j < NZ; ++j)
-        if (E::Pat::nz(r, j)) nan = nan || (nrm.Gn[r][j] != nrm.Gn[r][j]);
-    }
-    const bool need = valid && !triv && !nan;
-    __syncthreads();  // s_count = 0 visible
-    const unsigned ballot = __ballot_sync(0xffffffffu, need);
-    int wbase = 0;
-    if ((tid & 31) == 0 && ballot) wbase = atomicAdd(&s_count, __popc(ballot));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (need) {
-      const int slot = wbase + __popc(ballot & ((1u << (tid & 31)) - 1u));
-      float w[NW];
-      pack_problem<E>(nrm, w);
-#pragma unroll
-      for (int k = 0; k < NW; ++k) s_prob[k][slot] = w[k];
-      s_owner[slot] = (unsigned short)tid;
-    }
-    if (valid && !need && (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr)) {
-      NormSolution<NZ, M> sol;  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) sol.x[j] = nan ? (double)NAN : 0.0;
-#pragma unroll
-      for (int r = 0; r < M; ++r) {
-        sol.lam[r] = 0.0;
-        sol.s[r] = (double)nrm.hn[r];
-      }
-      sol.iters = 0;
-      write_saved<E>(a, i, sol);
-    }
-  }
-  __syncthreads();
-
-  // ---- phase B: compacted solve
-  if (tid < s_count) {
+  if (lane < cnt) {
+    const int slot = (head + lane) & (kRing - 1);
     float w[NW];
 #pragma unroll
-    for (int k = 0; k < NW; ++k) w[k] = s_prob[k][tid];
+    for (int k = 0; k < NW; ++k) w[k] = ring.w[k][slot];
+    const int64_t i = ring.idx[slot];
     Normalised<NZ, M> nrm;
     unpack_problem<E>(w, nrm);
     NormSolution<NZ, M> sol;
     solve_normalised_fast<typename E::Pat, NZ, M, kMode == 0>(nrm, p.p_diag, sol);
-    const int owner = s_owner[tid];
-#pragma unroll
-    for (int c = 0; c < NU; ++c) s_res[c][owner] = (float)sol.x[c];
-    s_stat[owner] = sol.status | (sol.iters << 8);
-    if (sol.status != RCBF_PENDING) write_saved<E>(a, base + owner, sol);
-  }
-  __syncthreads();
-
-  // ---- phase C
-  float xs[NU];
-  int status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL, iters = 0;
-  if (valid && !triv && !nan) {
-#pragma unroll
-    for (int c = 0; c < NU; ++c) xs[c] = s_res[c][tid];
-    status = s_stat[tid] & 255;
-    iters = s_stat[tid] >> 8;
-  } else {
-#pragma unroll
-    for (int c = 0; c < NU; ++c) xs[c] = nan ? NAN : 0.f;
-  }
-  if (valid) {
-    if (status == RCBF_PENDING) {
-      a.out[i * NU] = __uint_as_float(kPendingBits);
-      if (ws != nullptr) {
-        const unsigned long long slot = atomicAdd(&ws[kWsQueueCount], 1ULL);
-        if (slot < (unsigned long long)kWsQueueCap) ws[kWsQueueBase + slot] = (unsigned long long)i;
-      }
+    if (sol.status == RCBF_PENDING) {
+      mark_pending<E>(a, i, ws);
+      lc.pend += 1;
     } else {
-      E::finish(a, p, e, i, in, xs, status);
+      typename E::Inst in;
+      E::load_inst(a, i, in);
+      float xs[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
+      write_saved<E>(a, i, sol);
+      E::finish(a, p, e, i, in, xs, sol.status);
+      lc.iters += sol.iters;
     }
   }
-  block_counters(ws, valid, status, iters);
+  __syncwarp();
+}
+
+template <class E, int kMode /* 0 presolve, 1 pdipm */>
+__global__ void __launch_bounds__(kThreadsW, kMode == 0 ? 4 : 2)
+k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
+  constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NW = E::NW;
+  __shared__ WarpRing<E> s_ring[kWarps];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpRing<E>& ring = s_ring[warp];
+  const int64_t ntiles = (n + 31) >> 5;
+  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  const bool want_saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr);
+  int head = 0, qn = 0;
+  LaneCounters lc;
+
+  for (int64_t tile = gw; tile < ntiles; tile += nw) {
+    // ---- A-step
+    const int64_t i0 = (tile << 5) + lane;
+    const bool valid = i0 < n;
+    const int64_t i = valid ? i0 : n - 1;
+    typename E::Inst in;
+    E::load_inst(a, i, in);
+    bool triv = true, nan = false;
+    unsigned ballot;
+    {
+      Normalised<NZ, M> nrm;
+      E::assemble(a, p, i, in, nrm);
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        triv = triv && (nrm.hn[r] >= 0.f);
+        nan = nan || (nrm.hn[r] != nrm.hn[r]);
+#pragma unroll
+        for (int j = 0; j < NZ; ++j)
+          if (E::Pat::nz(r, j)) nan = nan || (nrm.Gn[r][j] != nrm.Gn[r][j]);
+      }
+      const bool need = valid && !triv && !nan;
+      ballot = __ballot_sync(0xffffffffu, need);
+      if (need) {
+        const int slot = (head + qn + __popc(ballot & ((1u << lane) - 1u))) & (kRing - 1);
+        float w[NW];
+        pack_problem<E>(nrm, w);
+#pragma unroll
+        for (int k = 0; k < NW; ++k) ring.w[k][slot] = w[k];
+        ring.idx[slot] = (int)i;
+      }
+      if (valid && !need && want_saved) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
+        NormSolution<NZ, M> sol;
+#pragma unroll
+        for (int j = 0; j < NZ; ++j) sol.x[j] = nan ? (double)NAN : 0.0;
+#pragma unroll
+        for (int r = 0; r < M; ++r) {
+          sol.lam[r] = 0.0;
+          sol.s[r] = (double)nrm.hn[r];
+        }
+        sol.iters = 0;
+        write_saved<E>(a, i, sol);
+      }
+    }
+    if (valid && (triv || nan)) {
+      float xs[NU];
+#pragma unroll
+      for (int c = 0; c < NU; ++c) xs[c] = nan ? NAN : 0.f;
+      E::finish(a, p, e, i, in, xs, nan ? RCBF_NAN : RCBF_OK_TRIVIAL);
+      lc.nan += nan ? 1 : 0;
+      lc.triv += nan ? 0 : 1;
+    }
+    qn += __popc(ballot);
+    __syncwarp();
+    // ---- B-step whenever a full warp of problems is waiting
+    if (qn >= 32) {
+      solve_batch<E, kMode>(a, p, e, ws, ring, head, 32, lane, lc);
+      head = (head + 32) & (kRing - 1);
+      qn -= 32;
+    }
+  }
+  if (qn > 0) solve_batch<E, kMode>(a, p, e, ws, ring, head, qn, lane, lc);
+
+  if (ws != nullptr) {
+    const int c_nan = __reduce_add_sync(0xffffffffu, lc.nan), c_triv = __reduce_add_sync(0xffffffffu, lc.triv);
+    const int c_pend = __reduce_add_sync(0xffffffffu, lc.pend), c_it = __reduce_add_sync(0xffffffffu, lc.iters);
+    if (lane == 0) {
+      if (c_nan) atomicAdd(&ws[0], (unsigned long long)c_nan);
+      if (c_triv) atomicAdd(&ws[3], (unsigned long long)c_triv);
+      if (c_it) atomicAdd(&ws[4], (unsigned long long)c_it);
+      if (c_pend) atomicAdd(&ws[5], (unsigned long long)c_pend);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// pass 2: interior-point fallback for the queued (or sentinel-marked) instances
+// pass 2: the queued (or sentinel-marked) instances
 // ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fallback_counters(rcbf_counters_t* ws, int status, int iters) {
+  if (ws == nullptr) return;
+  if (status == RCBF_NAN) atomicAdd(&ws[0], 1ULL);
+  if (status == RCBF_MAXITER) atomicAdd(&ws[1], 1ULL);
+  if (iters >= 100) atomicAdd(&ws[2], 1ULL);
+  atomicAdd(&ws[6], (unsigned long long)(iters >= 100 ? iters - 100 : iters));
+}
+
+// thread-per-instance interior-point chain (float32 unless it already failed in pass 1, then float64)
 template <class E, bool kSkipF32>
-__device__ __forceinline__ void fallback_one(const typename E::Args& a, int64_t i, const typename E::Params& p,
+__device__ __forceinline__ void fallback_ipm(const typename E::Args& a, int64_t i, const typename E::Params& p,
                                              const typename E::EnvParams& e, rcbf_counters_t* ws) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU;
   typename E::Inst in;
+  E::load_inst(a, i, in);
   Normalised<NZ, M> nrm;
   E::assemble(a, p, i, in, nrm);
   NormSolution<NZ, M> sol;
@@ -393,33 +428,109 @@ __device__ __forceinline__ void fallback_one(const typename E::Args& a, int64_t 
   for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
   write_saved<E>(a, i, sol);
   E::finish(a, p, e, i, in, xs, sol.status);
-  if (ws != nullptr) {
-    if (sol.status == RCBF_NAN) atomicAdd(&ws[0], 1ULL);
-    if (sol.status == RCBF_MAXITER) atomicAdd(&ws[1], 1ULL);
-    if (sol.iters >= 100) atomicAdd(&ws[2], 1ULL);
-    atomicAdd(&ws[6], (unsigned long long)(sol.iters >= 100 ? sol.iters - 100 : sol.iters));
+  fallback_counters(ws, sol.status, sol.iters);
+}
+
+// warp-per-instance exhaustive active-set enumeration with the float64 certificate ("presolve" mode)
+template <class E>
+__device__ __forceinline__ void fallback_enum(const typename E::Args& a, int64_t i, const typename E::Params& p,
+                                              const typename E::EnvParams& e, rcbf_counters_t* ws,
+                                              const unsigned short* table, int ntable, int lane) {
+  constexpr int NZ = E::NZ, M = E::M, NU = E::NU;
+  typename E::Inst in;
+  E::load_inst(a, i, in);
+  Normalised<NZ, M> nrm;
+  E::assemble(a, p, i, in, nrm);  // every lane assembles the same instance: 32x redundant, a few hundred flops
+  double pisd[NZ];
+  float pisf[NZ];
+  pis_of<NZ, M>(p.p_diag, pisd, pisf);
+  const NormCert<NZ, M> cp{nrm, pisd};
+  NormSolution<NZ, M> sol;
+  bool found = false;
+  for (int base = 0; base < ntable && !__any_sync(0xffffffffu, found); base += 32) {
+    const int t = base + lane;
+    double y[NZ], lam[M], s[M];
+    const uint32_t mask = (t < ntable) ? table[t] : 0u;
+    const bool ok = (t < ntable) && lnp_certify<double, NormCert<NZ, M>, typename E::Pat, NZ, M>(cp, mask, kTolSlack,
+                                                                                                  kTolDual, y, lam, s);
+    if (ok && !found) {
+      found = true;
+#pragma unroll
+      for (int j = 0; j < NZ; ++j) sol.x[j] = y[j] * pisd[j];
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        sol.lam[r] = lam[r];
+        sol.s[r] = s[r];
+      }
+      sol.status = RCBF_OK_CERTIFIED;
+      sol.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
+    }
+  }
+  const unsigned winners = __ballot_sync(0xffffffffu, found);
+  if (winners == 0u) {
+    if (lane == 0) fallback_ipm<E, false>(a, i, p, e, ws);  // degenerate to working precision: interior point
+    return;
+  }
+  if (lane == __ffs(winners) - 1) {
+    float xs[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
+    write_saved<E>(a, i, sol);
+    E::finish(a, p, e, i, in, xs, sol.status);
+    fallback_counters(ws, sol.status, 0);
   }
 }
 
-template <class E, bool kSkipF32>
+template <class E, int kMode>
 __global__ void __launch_bounds__(128)
 k_safe_fallback(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t gsz = (int64_t)gridDim.x * blockDim.x;
-  bool scan = (ws == nullptr);
-  if (!scan) {
-    const unsigned long long cnt = ws[kWsQueueCount];
-    if (cnt > (unsigned long long)kWsQueueCap) {
-      scan = true;  // overflow: every pending instance still carries the sentinel
+  constexpr int NZ = E::NZ, M = E::M;
+  const int lane = threadIdx.x & 31;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  const int64_t gwarp = gtid >> 5, nwarp = gsz >> 5;
+  unsigned long long cnt = (ws != nullptr) ? ws[kWsQueueCount] : ~0ULL;
+  const bool scan = cnt > (unsigned long long)kWsQueueCap;  // no workspace, or overflow: sentinel scan
+  if (!scan && cnt == 0ULL) goto done;
+
+  if (kMode == 0) {
+    // table of every active set with 1..NZ rows, built once per warp (lane-parallel, ballot-compacted)
+    __shared__ unsigned short s_table[4][160];
+    unsigned short* table = s_table[threadIdx.x >> 5];
+    int ntable = 0;
+    for (int m0 = 0; m0 < (1 << M); m0 += 32) {
+      const int m = m0 + lane;
+      const int pc = __popc(m);
+      const bool keep = (m < (1 << M)) && pc >= 1 && pc <= NZ;
+      const unsigned b = __ballot_sync(0xffffffffu, keep);
+      if (keep) table[ntable + __popc(b & ((1u << lane) - 1u))] = (unsigned short)m;
+      ntable += __popc(b);
+    }
+    __syncwarp();
+    if (!scan) {
+      for (int64_t q = gwarp; q < (int64_t)cnt; q += nwarp)
+        fallback_enum<E>(a, (int64_t)ws[kWsQueueBase + q], p, e, ws, table, ntable, lane);
     } else {
-      for (int64_t q = gtid; q < (int64_t)cnt; q += gsz) fallback_one<E, kSkipF32>(a, (int64_t)ws[kWsQueueBase + q], p, e, ws);
+      for (int64_t i0 = gwarp * 32; i0 < n; i0 += nwarp * 32) {
+        const int64_t i = i0 + lane;
+        const bool pend = (i < n) && __float_as_uint(__ldcg(a.out + i * E::NU)) == kPendingBits;
+        unsigned b = __ballot_sync(0xffffffffu, pend);
+        while (b) {
+          const int src = __ffs(b) - 1;
+          b &= b - 1;
+          fallback_enum<E>(a, i0 + src, p, e, ws, table, ntable, lane);
+        }
+      }
+    }
+  } else {
+    if (!scan) {
+      for (int64_t q = gtid; q < (int64_t)cnt; q += gsz) fallback_ipm<E, true>(a, (int64_t)ws[kWsQueueBase + q], p, e, ws);
+    } else {
+      for (int64_t i = gtid; i < n; i += gsz)
+        if (__float_as_uint(__ldcg(a.out + i * E::NU)) == kPendingBits) fallback_ipm<E, true>(a, i, p, e, ws);
     }
   }
-  if (scan) {
-    for (int64_t i = gtid; i < n; i += gsz)
-      if (__float_as_uint(__ldcg(a.out + i * E::NU)) == kPendingBits) fallback_one<E, kSkipF32>(a, i, p, e, ws);
-  }
-  if (ws != nullptr) {  // last block resets the queue for the next call
+done:
+  if (ws != nullptr) {  // the last block to finish resets the queue for the next call
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();
@@ -437,15 +548,19 @@ template <class E>
 inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::Params& p, const typename E::EnvParams& e,
                        rcbf_counters_t* ws, cudaStream_t s) {
   if (n <= 0) return 0;
-  const int grid = (int)((n + kBlock - 1) / kBlock);
-  // fallback grid: the queue holds at most kWsQueueCap entries; without a workspace it must scan all n
-  const int fgrid = (ws != nullptr) ? 16 : (int)((n + 127) / 128 < 148 * 8 ? (n + 127) / 128 : 148 * 8);
+  if (n > 0x7fffffffLL) return -2;  // ring indices are 32-bit
+  const int64_t ntiles = (n + 31) / 32;
+  const int64_t want = (ntiles + kWarps - 1) / kWarps;
+  const int resident = 148 * (p.solver_mode == 0 ? 4 : 2);  // persistent: one wave of resident blocks
+  const int grid = (int)(want < resident ? want : resident);
+  const int64_t fb = (n + 127) / 128;
+  const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);
   if (p.solver_mode == 0) {
-    k_safe<E, 0><<<grid, kBlock, 0, s>>>(a, n, p, e, ws);
-    k_safe_fallback<E, false><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
+    k_safe<E, 0><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
+    k_safe_fallback<E, 0><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
   } else {
-    k_safe<E, 1><<<grid, kBlock, 0, s>>>(a, n, p, e, ws);
-    k_safe_fallback<E, true><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
+    k_safe<E, 1><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
+    k_safe_fallback<E, 1><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
   }
   return (int)cudaGetLastError();
 }

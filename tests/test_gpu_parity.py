@@ -158,6 +158,26 @@ def test_pdipm_solver_mode_matches_presolve_mode(request, mode):
     assert stats["sum_iters"] > stats_ref["sum_iters"]
 
 
+def test_fallback_pass_without_workspace_scans_for_the_sentinel(cars):
+    """SimulatedCars leaves ~0.1 % of the QPs to pass 2 (a constraint has to be dropped, which the greedy presolve
+    does not do).  With a workspace pass 2 reads the queue; with workspace = NULL it must find the same instances by
+    scanning for the sentinel.  Both must give identical results."""
+    from sac_rcbf_b200 import _lib
+    env, layer = cars
+    lib = _lib.load()
+    B = 1 << 20
+    st, ac, mu, sg, _ = O.synth_cars(B, seed=5)
+    ref = _forward_with_aux(layer, st, ac, mu, sg)
+    stats = layer.solver_stats()
+    assert stats["fallback"] > 100 and stats["uncertified"] == 0 and (ref[4] <= 2).all()
+    d = [_cuda(a) for a in (st, ac, sg)]
+    out = torch.empty((B, 1), dtype=torch.float32, device="cuda")
+    rc = lib.rcbf_cars_safe_action(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), B, layer._params(), _lib.ptr(out),
+                                   None, None, None, None, None, None, _lib.stream_ptr(layer.device))
+    assert rc == 0
+    np.testing.assert_array_equal(out.cpu().numpy(), ref[0])
+
+
 def test_trivial_instances_pass_through(uni):
     env, layer = uni
     B = 4096
