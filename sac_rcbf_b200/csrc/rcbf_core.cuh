@@ -43,6 +43,22 @@ RCBF_HD float t_fma(float a, float b, float c) { return fmaf(a, b, c); }
 RCBF_HD double t_fma(double a, double b, double c) { return fma(a, b, c); }
 RCBF_HD float t_sqrt(float a) { return sqrtf(a); }
 RCBF_HD double t_sqrt(double a) { return sqrt(a); }
+// reciprocal square root: one MUFU (+ Newton for double) instead of an IEEE sqrt and an IEEE division; the tiny
+// Cholesky factors below only ever need 1/l_kk
+RCBF_HD float t_rsqrt(float a) {
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(a);
+#else
+  return 1.0f / sqrtf(a);
+#endif
+}
+RCBF_HD double t_rsqrt(double a) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(a);
+#else
+  return 1.0 / sqrt(a);
+#endif
+}
 
 // single-rounding float ops that the compiler may not contract into FMAs (reference-order assembly)
 RCBF_HD float mul_rn(float a, float b) {
@@ -124,18 +140,15 @@ struct Chol {
   // L (lower) with the diagonal stored as reciprocals
   T i00, l10, i11, l20, l21, i22;
   RCBF_HD void factor(const T S[NZ][NZ]) {
-    T l00 = t_sqrt(S[0][0]);
-    i00 = T(1) / l00;
+    i00 = t_rsqrt(S[0][0]);
     if (NZ > 1) {
       l10 = S[1][0] * i00;
-      T l11 = t_sqrt(S[1][1] - l10 * l10);
-      i11 = T(1) / l11;
+      i11 = t_rsqrt(S[1][1] - l10 * l10);
     }
     if (NZ > 2) {
       l20 = S[2][0] * i00;
       l21 = (S[2][1] - l20 * l10) * i11;
-      T l22 = t_sqrt(S[2][2] - l20 * l20 - l21 * l21);
-      i22 = T(1) / l22;
+      i22 = t_rsqrt(S[2][2] - l20 * l20 - l21 * l21);
     }
   }
   RCBF_HD void fwd(const T r[NZ], T w[NZ]) const {  // L w = r
@@ -251,27 +264,30 @@ RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], 
 // negative (a drop would be needed) or NZ rows do not make the point feasible -- those instances go to the
 // interior-point solver.  The returned mask is only a GUESS; the float64 certificate decides.
 template <typename Pat, int NZ, int M>
-RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& mask_out, int& rounds) {
-  float inv_norm[M];
+RCBF_HD bool lnp_greedy_active_set(const float Gn[M][NZ], const float hn[M], const float pis[NZ], float Rg[NZ][NZ],
+                                   float rbg[NZ], uint32_t& mask_out, int& rounds) {
+  // scaled problem A = G~ P^-1/2 and the reciprocal row norms (violations are compared in units of |a_i|)
+  float A[M][NZ], inv_norm[M];
   RCBF_UNROLL
   for (int i = 0; i < M; ++i) {
     float acc = 0.f;
     RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j)
-      if (Pat::nz(i, j)) acc = fmaf(P.A[i][j], P.A[i][j], acc);
-#if defined(__CUDA_ARCH__)
-    inv_norm[i] = rsqrtf(acc);
-#else
-    inv_norm[i] = 1.0f / sqrtf(acc);
-#endif
+    for (int j = 0; j < NZ; ++j) {
+      A[i][j] = Pat::nz(i, j) ? Gn[i][j] * pis[j] : 0.f;
+      if (Pat::nz(i, j)) acc = fmaf(A[i][j], A[i][j], acc);
+    }
+    inv_norm[i] = t_rsqrt(acc);
   }
-  float y[NZ], R[NZ][NZ], rb[NZ];
+  float y[NZ], R[NZ][NZ];
   RCBF_UNROLL
   for (int j = 0; j < NZ; ++j) {
     y[j] = 0.f;
-    rb[j] = 0.f;
+    rbg[j] = 0.f;
     RCBF_UNROLL
-    for (int k = 0; k < NZ; ++k) R[j][k] = 0.f;
+    for (int k = 0; k < NZ; ++k) {
+      R[j][k] = 0.f;
+      Rg[j][k] = 0.f;
+    }
   }
   uint32_t mask = 0;
   bool ok = true, feasible = false;
@@ -283,10 +299,10 @@ RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& 
     int wi = -1;
     RCBF_UNROLL
     for (int i = 0; i < M; ++i) {
-      float acc = P.b[i];
+      float acc = hn[i];
       RCBF_UNROLL
       for (int j = 0; j < NZ; ++j)
-        if (Pat::nz(i, j)) acc = fmaf(-P.A[i][j], y[j], acc);
+        if (Pat::nz(i, j)) acc = fmaf(-A[i][j], y[j], acc);
       const float v = acc * inv_norm[i];
       const bool take = !((mask >> i) & 1u) && (v < worst);
       worst = take ? v : worst;
@@ -298,13 +314,16 @@ RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& 
     }
     if (r == NZ) break;  // NZ rows and still infeasible
     mask |= 1u << wi;
+    // gather the UNSCALED row (the float64 certificate rebuilds its data from it) and scale the NZ entries
     RCBF_UNROLL
     for (int i = 0; i < M; ++i) {
       const bool put = (i == wi);
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) R[r][j] = put ? (Pat::nz(i, j) ? P.A[i][j] : 0.f) : R[r][j];
-      rb[r] = put ? P.b[i] : rb[r];
+      for (int j = 0; j < NZ; ++j) Rg[r][j] = put ? (Pat::nz(i, j) ? Gn[i][j] : 0.f) : Rg[r][j];
+      rbg[r] = put ? hn[i] : rbg[r];
     }
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) R[r][j] = Rg[r][j] * pis[j];
     // (R R') lam = -rb on the first r+1 rows (unit diagonal on the unused slots)
     float Gm[NZ][NZ];
     RCBF_UNROLL
@@ -322,7 +341,7 @@ RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& 
     ch.factor(Gm);
     float nrb[NZ], lk[NZ];
     RCBF_UNROLL
-    for (int k = 0; k < NZ; ++k) nrb[k] = -rb[k];
+    for (int k = 0; k < NZ; ++k) nrb[k] = -rbg[k];
     ch.solve(nrb, lk);
     RCBF_UNROLL
     for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -1e-6f);  // NaN (dependent rows) -> false
@@ -338,6 +357,82 @@ RCBF_HD bool lnp_greedy_active_set(const LnpProblem<float, NZ, M>& P, uint32_t& 
   mask_out = mask;
   rounds = r;
   return ok && feasible;
+}
+
+// float64 KKT certificate on rows that are ALREADY gathered (Rg, rbg from the presolve; slot k <-> k-th set bit of
+// `mask` in selection order is irrelevant to the test).  Returns y and the compact multipliers lk.
+template <typename Pat, int NZ, int M>
+RCBF_HD bool lnp_certify_rows(const float Gn[M][NZ], const float hn[M], const double pis[NZ], const float Rg[NZ][NZ],
+                              const float rbg[NZ], int cnt, uint32_t mask, double tol_s, double tol_l, double y[NZ],
+                              double lk[NZ]) {
+  double R[NZ][NZ], Gm[NZ][NZ], nrb[NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) R[k][j] = (double)Rg[k][j] * pis[j];
+    nrb[k] = -(double)rbg[k];
+  }
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int l = 0; l <= k; ++l) {
+      double acc = 0.0;
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = fma(R[k][j], R[l][j], acc);
+      Gm[k][l] = acc;
+    }
+    Gm[k][k] = (k < cnt) ? Gm[k][k] : 1.0;
+  }
+  Chol<double, NZ> ch;
+  ch.factor(Gm);
+  ch.solve(nrb, lk);
+  bool ok = true;
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -tol_l);
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    double acc = 0.0;
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) acc = fma(-R[k][j], lk[k], acc);
+    y[j] = acc;
+  }
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    double acc = (double)hn[i];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) acc = fma(-((double)Gn[i][j] * pis[j]), y[j], acc);
+    const bool act = (mask >> i) & 1u;
+    ok = ok && (acc >= -tol_s) && (!act || acc <= tol_s);
+  }
+  return ok;
+}
+
+// multipliers / slacks in dense form, only when a caller wants them saved (backward pass, diagnostics)
+template <typename Pat, int NZ, int M>
+RCBF_HD void lnp_expand_aux(const float Gn[M][NZ], const float hn[M], const double pis[NZ], const float Rg[NZ][NZ],
+                            const float rbg[NZ], uint32_t mask, const double y[NZ], const double lk[NZ], double lam[M],
+                            double s[M]) {
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    double acc = (double)hn[i];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) acc = fma(-((double)Gn[i][j] * pis[j]), y[j], acc);
+    s[i] = acc;
+    // slot of row i: the gathered row that equals it (selection order is not the bit order)
+    double li = 0.0;
+    if ((mask >> i) & 1u) {
+      RCBF_UNROLL
+      for (int k = 0; k < NZ; ++k) {
+        bool same = (rbg[k] == hn[i]);
+        RCBF_UNROLL
+        for (int j = 0; j < NZ; ++j) same = same && (Rg[k][j] == (Pat::nz(i, j) ? Gn[i][j] : 0.f));
+        li = same ? lk[k] : li;
+      }
+    }
+    lam[i] = li;
+  }
 }
 
 template <typename T> struct LnpTol;
@@ -616,13 +711,30 @@ struct UniRaw {
   float Lg[kUniHaz][2];  // d h_i / d action  (= -G[i][:2]); kept for the backward chain
 };
 
-RCBF_HD void sincos_t(float x, float* s, float* c) {
-#if defined(__CUDA_ARCH__)
-  sincosf(x, s, c);
-#else
-  *s = sinf(x);
-  *c = cosf(x);
-#endif
+// sin and cos of a float32 angle, <= ~1.5 ulp for |x| < 1e5 (env headings stay below ~25 rad: theta drifts by at
+// most dt * 1 rad/s per step over 1000 steps).  Cody-Waite reduction by pi/2 in three float32 pieces + the classic
+// degree-7 / degree-8 minimax polynomials on [-pi/4, pi/4].  ~30 instructions, no slow path, no local memory (the
+// library sincosf carries a Payne-Hanek branch that costs code size and registers in every kernel that calls it).
+RCBF_HD void sincos_t(float x, float* sn, float* cs) {
+  const float j = rintf(x * 0.636619772f);             // nearest multiple of pi/2
+  float r = fmaf(j, -1.57079601e+00f, x);
+  r = fmaf(j, -3.13916473e-07f, r);
+  r = fmaf(j, -5.39030253e-15f, r);
+  const int q = (int)j;
+  const float z = r * r;
+  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  ps = fmaf(ps, z, -1.6666654611e-1f);
+  ps = fmaf(ps * z, r, r);                              // sin(r)
+  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  pc = fmaf(pc, z, 4.166664568298827e-2f);
+  pc = fmaf(pc * z, z, fmaf(z, -0.5f, 1.0f));           // cos(r)
+  const bool swap = q & 1;
+  float sv = swap ? pc : ps;
+  float cv = swap ? ps : pc;
+  sv = (q & 2) ? -sv : sv;
+  cv = ((q + 1) & 2) ? -cv : cv;
+  *sn = sv;
+  *cs = cv;
 }
 
 // The assembly mirrors the reference's float32 operation ORDER (one rounding per torch op, no FMA contraction, the
@@ -763,9 +875,9 @@ RCBF_HD float div_by(float a, float n, float r) {
 }
 RCBF_HD float rcp_refined(float n) {
 #if defined(__CUDA_ARCH__)
-  float r;
+  float r;  // MUFU.RCP is within one ulp: enough for the single-correction quotient in div_by to round correctly
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
-  return fmaf(fmaf(-n, r, 1.0f), r, r);
+  return r;
 #else
   return 1.0f / n;
 #endif
@@ -837,44 +949,28 @@ RCBF_HD void pis_of(const float p_diag[NZ], double pisd[NZ], float pisf[NZ]) {
 // certificate.  kPresolve = false skips the presolve and runs the float32 interior point inline instead
 // ("pdipm" solver mode).  Leaves status = RCBF_PENDING when it cannot certify: the fallback pass takes over.
 template <typename Pat, int NZ, int M, bool kPresolve>
-RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_diag[NZ], NormSolution<NZ, M>& o) {
+RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_diag[NZ], bool want_aux,
+                                   NormSolution<NZ, M>& o) {
   double pisd[NZ];
   float pisf[NZ];
   pis_of<NZ, M>(p_diag, pisd, pisf);
-  bool triv = true, nan = false;
-  RCBF_UNROLL
-  for (int i = 0; i < M; ++i) {
-    triv = triv && (nrm.hn[i] >= 0.f);
-    nan = nan || (nrm.hn[i] != nrm.hn[i]);
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) nan = nan || (nrm.Gn[i][j] != nrm.Gn[i][j]);
-  }
-  if (triv || nan) {
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) o.x[j] = nan ? (double)NAN : 0.0;
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      o.lam[i] = 0.0;
-      o.s[i] = (double)nrm.hn[i];
-    }
-    o.status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
-    o.iters = 0;
-    return;
-  }
-  const NormCert<NZ, M> cp{nrm, pisd};
-  LnpProblem<float, NZ, M> Pf;
-  to_lnp<float, Pat, NZ, M>(nrm, pisf, Pf);
   double y[NZ];
   if (kPresolve) {
     uint32_t mask;
     int rounds;
-    const bool guess = lnp_greedy_active_set<Pat, NZ, M>(Pf, mask, rounds);
+    float Rg[NZ][NZ], rbg[NZ];
+    const bool guess = lnp_greedy_active_set<Pat, NZ, M>(nrm.Gn, nrm.hn, pisf, Rg, rbg, mask, rounds);
     o.status = RCBF_PENDING;
     o.iters = rounds;
-    if (guess && lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, mask, kTolSlack, kTolDual, y, o.lam, o.s)) {
+    double lk[NZ];
+    if (guess && lnp_certify_rows<Pat, NZ, M>(nrm.Gn, nrm.hn, pisd, Rg, rbg, rounds, mask, kTolSlack, kTolDual, y, lk)) {
       o.status = RCBF_OK_CERTIFIED;
+      if (want_aux) lnp_expand_aux<Pat, NZ, M>(nrm.Gn, nrm.hn, pisd, Rg, rbg, mask, y, lk, o.lam, o.s);
     }
   } else {
+    const NormCert<NZ, M> cp{nrm, pisd};
+    LnpProblem<float, NZ, M> Pf;
+    to_lnp<float, Pat, NZ, M>(nrm, pisf, Pf);
     LnpSolution<double, NZ, M> sol;
     lnp_solve<float, double, NormCert<NZ, M>, Pat, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
     o.status = (sol.status >= RCBF_MAXITER) ? RCBF_PENDING : sol.status;
@@ -889,6 +985,18 @@ RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_d
   }
   RCBF_UNROLL
   for (int j = 0; j < NZ; ++j) o.x[j] = y[j] * pisd[j];
+}
+
+// trivial test on the RAW rows (n_i > 0, so h~_i >= 0 <=> h_i >= 0): x = 0 is optimal iff every h_i >= 0
+template <int M>
+RCBF_HD void classify_raw(const float h[M], bool& triv, bool& nan) {
+  triv = true;
+  nan = false;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    triv = triv && (h[i] >= 0.f);
+    nan = nan || (h[i] != h[i]);
+  }
 }
 
 // Fallback pass for the (rare) instances the fast path left pending: float32 interior point + certificate, then the
@@ -937,16 +1045,39 @@ struct UniSolve {
   NormSolution<kUniNZ, kUniM> sol;
 };
 
+template <typename Pat, int NZ, int M>
+RCBF_HD void trivial_solution(const Normalised<NZ, M>& nrm, bool nan, NormSolution<NZ, M>& o) {
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) o.x[j] = nan ? (double)NAN : 0.0;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    o.lam[i] = 0.0;
+    o.s[i] = (double)nrm.hn[i];
+  }
+  o.status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
+  o.iters = 0;
+}
+
 // kMode: 0 = fast path with presolve, 1 = fast path with inline float32 IPM ("pdipm" mode), 2 = fallback pass,
 //        3 = fallback pass that skips the float32 IPM (it already failed in mode 1)
+// (reference driver used by the host simulation and the backward kernels; the hot kernels in rcbf_safe_kernels.cuh
+//  call the same pieces but interleave them with the compaction ring)
 template <int kMode>
 RCBF_HD void unicycle_safe_action(const UnicycleParams& p, const float st[3], const float u[2], const float mu[3],
                                   const float sg[3], UniSolve& w, float u_safe[2]) {
   assemble_unicycle(p, st, u, mu, sg, w.raw);
   normalise_rows<UniPat, kUniNZ, kUniM>(w.raw.G, w.raw.h, w.nrm);
-  if (kMode == 0) solve_normalised_fast<UniPat, kUniNZ, kUniM, true>(w.nrm, p.p_diag, w.sol);
-  if (kMode == 1) solve_normalised_fast<UniPat, kUniNZ, kUniM, false>(w.nrm, p.p_diag, w.sol);
-  if (kMode >= 2) solve_normalised_full<UniPat, kUniNZ, kUniM>(w.nrm, p.p_diag, kMode == 3, w.sol);
+  bool triv, nan;
+  classify_raw<kUniM>(w.raw.h, triv, nan);
+  RCBF_UNROLL
+  for (int i = 0; i < kUniHaz; ++i) nan = nan || (w.raw.G[i][0] != w.raw.G[i][0]) || (w.raw.G[i][1] != w.raw.G[i][1]);
+  if (triv || nan) {
+    trivial_solution<UniPat, kUniNZ, kUniM>(w.nrm, nan, w.sol);
+  } else {
+    if (kMode == 0) solve_normalised_fast<UniPat, kUniNZ, kUniM, true>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode == 1) solve_normalised_fast<UniPat, kUniNZ, kUniM, false>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode >= 2) solve_normalised_full<UniPat, kUniNZ, kUniM>(w.nrm, p.p_diag, kMode == 3, w.sol);
+  }
   RCBF_UNROLL
   for (int c = 0; c < 2; ++c) u_safe[c] = clampf(u[c] + (float)w.sol.x[c], p.u_min[c], p.u_max[c]);  // :77
 }
@@ -962,9 +1093,16 @@ RCBF_HD void cars_safe_action(const CarsParams& p, const float st[10], float u, 
                               float* u_safe) {
   assemble_cars(p, st, u, sg, w.raw);
   normalise_rows<CarsPat, kCarsNZ, kCarsM>(w.raw.G, w.raw.h, w.nrm);
-  if (kMode == 0) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, true>(w.nrm, p.p_diag, w.sol);
-  if (kMode == 1) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, false>(w.nrm, p.p_diag, w.sol);
-  if (kMode >= 2) solve_normalised_full<CarsPat, kCarsNZ, kCarsM>(w.nrm, p.p_diag, kMode == 3, w.sol);
+  bool triv, nan;
+  classify_raw<kCarsM>(w.raw.h, triv, nan);
+  nan = nan || (w.raw.G[0][0] != w.raw.G[0][0]) || (w.raw.G[1][0] != w.raw.G[1][0]);
+  if (triv || nan) {
+    trivial_solution<CarsPat, kCarsNZ, kCarsM>(w.nrm, nan, w.sol);
+  } else {
+    if (kMode == 0) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, true>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode == 1) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, false>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode >= 2) solve_normalised_full<CarsPat, kCarsNZ, kCarsM>(w.nrm, p.p_diag, kMode == 3, w.sol);
+  }
   *u_safe = clampf(u + (float)w.sol.x[0], p.u_min, p.u_max);  // :77
 }
 

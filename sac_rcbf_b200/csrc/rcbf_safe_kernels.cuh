@@ -70,7 +70,7 @@ struct UniArgs {
 
 template <bool kFused>
 struct UniEnv {
-  static constexpr int NZ = kUniNZ, M = kUniM, NU = 2, NW = 28;
+  static constexpr int NZ = kUniNZ, M = kUniM, NU = 2;
   using Pat = UniPat;
   using Args = UniArgs;
   using Params = UnicycleParams;
@@ -92,14 +92,51 @@ struct UniEnv {
     }
     ld_row<2>(a.ac, i, in.u);
   }
-  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
-                                                  Normalised<NZ, M>& nrm) {
+  // raw rows in NWR = 19 words: (G[i][0], G[i][1]) of the 5 CBF rows + the 9 h; the rest of G is constant
+  static constexpr int NWR = 19;
+  __device__ static __forceinline__ void assemble_raw(const Args& a, const Params& p, int64_t i, const Inst& in,
+                                                      float w[NWR], bool& triv, bool& nan) {
     float m[3], g[3];
     ld_row<3>(a.mu, i, m);
     ld_row<3>(a.sg, i, g);
     UniRaw raw;
     assemble_unicycle(p, in.v, in.u, m, g, raw);
-    normalise_rows<Pat, NZ, M>(raw.G, raw.h, nrm);
+    classify_raw<M>(raw.h, triv, nan);
+#pragma unroll
+    for (int r = 0; r < kUniHaz; ++r) {
+      w[2 * r] = raw.G[r][0];
+      w[2 * r + 1] = raw.G[r][1];
+      nan = nan || (raw.G[r][0] != raw.G[r][0]) || (raw.G[r][1] != raw.G[r][1]);
+    }
+#pragma unroll
+    for (int r = 0; r < M; ++r) w[10 + r] = raw.h[r];
+  }
+  __device__ static __forceinline__ void normalise_packed(const float w[NWR], const Params& p, Normalised<NZ, M>& nrm) {
+    float G[M][NZ], h[M];
+#pragma unroll
+    for (int r = 0; r < kUniHaz; ++r) {
+      G[r][0] = w[2 * r];
+      G[r][1] = w[2 * r + 1];
+      G[r][2] = -1.0f;  // diff_cbf_qp.py:260
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {  // diff_cbf_qp.py:365-377
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        G[kUniHaz + 2 * c][j] = (j == c) ? 1.0f : 0.0f;
+        G[kUniHaz + 2 * c + 1][j] = (j == c) ? -1.0f : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < M; ++r) h[r] = w[10 + r];
+    normalise_rows<Pat, NZ, M>(G, h, nrm);
+  }
+  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
+                                                  Normalised<NZ, M>& nrm) {
+    float w[NWR];
+    bool triv, nan;
+    assemble_raw(a, p, i, in, w, triv, nan);
+    normalise_packed(w, p, nrm);
   }
   __device__ static __forceinline__ void finish(const Args& a, const Params& p, const EnvParams& e, int64_t i, Inst& in,
                                                 const float xs[NU], int status) {
@@ -144,7 +181,7 @@ struct CarsArgs {
 
 template <bool kFused>
 struct CarsEnv {
-  static constexpr int NZ = kCarsNZ, M = kCarsM, NU = 1, NW = 10;
+  static constexpr int NZ = kCarsNZ, M = kCarsM, NU = 1;
   using Pat = CarsPat;
   using Args = CarsArgs;
   using Params = CarsParams;
@@ -164,8 +201,9 @@ struct CarsEnv {
       in.stp = 0;
     }
   }
-  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
-                                                  Normalised<NZ, M>& nrm) {
+  static constexpr int NWR = 6;  // G[0][0], G[1][0] + the 4 h; the slack column and the actuator rows are constant
+  __device__ static __forceinline__ void assemble_raw(const Args& a, const Params& p, int64_t i, const Inst& in,
+                                                      float w[NWR], bool& triv, bool& nan) {
     float s[10], g[10];
     const float2* sp = reinterpret_cast<const float2*>(kFused ? a.state : a.st) + i * 5;  // rows are 40 B: 8-aligned
     const float2* gp = reinterpret_cast<const float2*>(a.sg) + i * 5;
@@ -178,7 +216,31 @@ struct CarsEnv {
     }
     CarsRaw raw;
     assemble_cars(p, s, in.u[0], g, raw);
-    normalise_rows<Pat, NZ, M>(raw.G, raw.h, nrm);
+    classify_raw<M>(raw.h, triv, nan);
+    w[0] = raw.G[0][0];
+    w[1] = raw.G[1][0];
+    nan = nan || (w[0] != w[0]) || (w[1] != w[1]);
+#pragma unroll
+    for (int r = 0; r < M; ++r) w[2 + r] = raw.h[r];
+  }
+  __device__ static __forceinline__ void normalise_packed(const float w[NWR], const Params& p, Normalised<NZ, M>& nrm) {
+    float G[M][NZ], h[M];
+    G[0][0] = w[0];
+    G[1][0] = w[1];
+    G[0][1] = -p.slack_coeff;  // diff_cbf_qp.py:352
+    G[1][1] = -p.slack_coeff;
+    G[2][0] = 1.0f;  G[2][1] = 0.0f;   // :369-370
+    G[3][0] = -1.0f; G[3][1] = 0.0f;   // :375-376
+#pragma unroll
+    for (int r = 0; r < M; ++r) h[r] = w[2 + r];
+    normalise_rows<Pat, NZ, M>(G, h, nrm);
+  }
+  __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
+                                                  Normalised<NZ, M>& nrm) {
+    float w[NWR];
+    bool triv, nan;
+    assemble_raw(a, p, i, in, w, triv, nan);
+    normalise_packed(w, p, nrm);
   }
   __device__ static __forceinline__ void finish(const Args& a, const Params& p, const EnvParams& e, int64_t i, Inst& in,
                                                 const float xs[NU], int status) {
@@ -215,31 +277,6 @@ struct CarsEnv {
 // shared helpers
 // ---------------------------------------------------------------------------------------------------------------
 template <class E>
-__device__ __forceinline__ void pack_problem(const Normalised<E::NZ, E::M>& nrm, float w[E::NW]) {
-  int k = 0;
-#pragma unroll
-  for (int i = 0; i < E::M; ++i) {
-#pragma unroll
-    for (int j = 0; j < E::NZ; ++j)
-      if (E::Pat::nz(i, j)) w[k++] = nrm.Gn[i][j];
-  }
-#pragma unroll
-  for (int i = 0; i < E::M; ++i) w[k++] = nrm.hn[i];
-}
-
-template <class E>
-__device__ __forceinline__ void unpack_problem(const float w[E::NW], Normalised<E::NZ, E::M>& nrm) {
-  int k = 0;
-#pragma unroll
-  for (int i = 0; i < E::M; ++i) {
-#pragma unroll
-    for (int j = 0; j < E::NZ; ++j) nrm.Gn[i][j] = E::Pat::nz(i, j) ? w[k++] : 0.f;
-  }
-#pragma unroll
-  for (int i = 0; i < E::M; ++i) nrm.hn[i] = w[k++];
-}
-
-template <class E>
 __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i, const NormSolution<E::NZ, E::M>& sol) {
   if (a.x != nullptr) {
 #pragma unroll
@@ -265,12 +302,8 @@ constexpr int kRing = 64;             // ring capacity per warp: at most 31 left
 
 template <class E>
 struct WarpRing {
-  float w[E::NW][kRing];
+  float w[E::NWR][kRing];
   int idx[kRing];
-};
-
-struct LaneCounters {
-  int nan = 0, triv = 0, pend = 0, iters = 0;
 };
 
 template <class E>
@@ -282,120 +315,119 @@ __device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t 
   }
 }
 
-template <class E, int kMode>
-__device__ __forceinline__ void solve_batch(const typename E::Args& a, const typename E::Params& p,
-                                            const typename E::EnvParams& e, rcbf_counters_t* ws, WarpRing<E>& ring,
-                                            int head, int cnt, int lane, LaneCounters& lc) {
-  constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NW = E::NW;
-  if (lane < cnt) {
-    const int slot = (head + lane) & (kRing - 1);
-    float w[NW];
-#pragma unroll
-    for (int k = 0; k < NW; ++k) w[k] = ring.w[k][slot];
-    const int64_t i = ring.idx[slot];
-    Normalised<NZ, M> nrm;
-    unpack_problem<E>(w, nrm);
-    NormSolution<NZ, M> sol;
-    solve_normalised_fast<typename E::Pat, NZ, M, kMode == 0>(nrm, p.p_diag, sol);
-    if (sol.status == RCBF_PENDING) {
-      mark_pending<E>(a, i, ws);
-      lc.pend += 1;
-    } else {
-      typename E::Inst in;
-      E::load_inst(a, i, in);
-      float xs[NU];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
-      write_saved<E>(a, i, sol);
-      E::finish(a, p, e, i, in, xs, sol.status);
-      lc.iters += sol.iters;
-    }
-  }
-  __syncwarp();
-}
-
 template <class E, int kMode /* 0 presolve, 1 pdipm */>
 __global__ void __launch_bounds__(kThreadsW, kMode == 0 ? 4 : 2)
 k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
-  constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NW = E::NW;
+  constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NWR = E::NWR;
+  using Inst = typename E::Inst;
   __shared__ WarpRing<E> s_ring[kWarps];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpRing<E>& ring = s_ring[warp];
   const int64_t ntiles = (n + 31) >> 5;
-  const int64_t gw = (int64_t)blockIdx.x * kWarps + warp, nw = (int64_t)gridDim.x * kWarps;
+  const int64_t nw = (int64_t)gridDim.x * kWarps;
+  int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
   const bool want_saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr);
   int head = 0, qn = 0;
-  LaneCounters lc;
+  int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
 
-  for (int64_t tile = gw; tile < ntiles; tile += nw) {
-    // ---- A-step
-    const int64_t i0 = (tile << 5) + lane;
-    const bool valid = i0 < n;
-    const int64_t i = valid ? i0 : n - 1;
-    typename E::Inst in;
-    E::load_inst(a, i, in);
-    bool triv = true, nan = false;
-    unsigned ballot;
-    {
-      Normalised<NZ, M> nrm;
-      E::assemble(a, p, i, in, nrm);
-#pragma unroll
-      for (int r = 0; r < M; ++r) {
-        triv = triv && (nrm.hn[r] >= 0.f);
-        nan = nan || (nrm.hn[r] != nrm.hn[r]);
-#pragma unroll
-        for (int j = 0; j < NZ; ++j)
-          if (E::Pat::nz(r, j)) nan = nan || (nrm.Gn[r][j] != nrm.Gn[r][j]);
-      }
+  for (;;) {
+    const bool have_tile = tile < ntiles;
+    // job A: this lane's own instance when it needs no solve; job B: the instance this lane solved in the B-step
+    bool onA = false, onB = false;
+    int64_t iA = 0, iB = 0;
+    Inst inA, inB;
+    float xsA[NU], xsB[NU];
+    int stA = RCBF_OK_TRIVIAL, stB = RCBF_OK_CERTIFIED;
+
+    if (have_tile) {  // ---- A-step: assemble, classify, queue
+      const int64_t i0 = (tile << 5) + lane;
+      const bool valid = i0 < n;
+      iA = valid ? i0 : n - 1;
+      E::load_inst(a, iA, inA);
+      float w[NWR];
+      bool triv, nan;
+      E::assemble_raw(a, p, iA, inA, w, triv, nan);
       const bool need = valid && !triv && !nan;
-      ballot = __ballot_sync(0xffffffffu, need);
+      const unsigned ballot = __ballot_sync(0xffffffffu, need);
       if (need) {
         const int slot = (head + qn + __popc(ballot & ((1u << lane) - 1u))) & (kRing - 1);
-        float w[NW];
-        pack_problem<E>(nrm, w);
 #pragma unroll
-        for (int k = 0; k < NW; ++k) ring.w[k][slot] = w[k];
-        ring.idx[slot] = (int)i;
+        for (int k = 0; k < NWR; ++k) ring.w[k][slot] = w[k];
+        ring.idx[slot] = (int)iA;
       }
-      if (valid && !need && want_saved) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
+      onA = valid && !need;
+      stA = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
+#pragma unroll
+      for (int c = 0; c < NU; ++c) xsA[c] = nan ? NAN : 0.f;
+      if (onA && want_saved) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
+        Normalised<NZ, M> nrm;
+        E::normalise_packed(w, p, nrm);
         NormSolution<NZ, M> sol;
+        trivial_solution<typename E::Pat, NZ, M>(nrm, nan, sol);
+        write_saved<E>(a, iA, sol);
+      }
+      c_nan += (onA && nan) ? 1 : 0;
+      c_triv += (onA && !nan) ? 1 : 0;
+      qn += __popc(ballot);
+      tile += nw;
+    }
+    __syncwarp();
+
+    // ---- B-step: a full warp of queued problems (or whatever is left once the tiles are exhausted)
+    const int take = (qn >= 32) ? 32 : (have_tile ? 0 : qn);
+    if (take > 0) {
+      if (lane < take) {
+        const int slot = (head + lane) & (kRing - 1);
+        float w[NWR];
 #pragma unroll
-        for (int j = 0; j < NZ; ++j) sol.x[j] = nan ? (double)NAN : 0.0;
+        for (int k = 0; k < NWR; ++k) w[k] = ring.w[k][slot];
+        iB = ring.idx[slot];
+        Normalised<NZ, M> nrm;
+        E::normalise_packed(w, p, nrm);
+        NormSolution<NZ, M> sol;
+        solve_normalised_fast<typename E::Pat, NZ, M, kMode == 0>(nrm, p.p_diag, want_saved, sol);
+        if (sol.status == RCBF_PENDING) {
+          mark_pending<E>(a, iB, ws);
+          c_pend += 1;
+        } else {
+          onB = true;
+          stB = sol.status;
 #pragma unroll
-        for (int r = 0; r < M; ++r) {
-          sol.lam[r] = 0.0;
-          sol.s[r] = (double)nrm.hn[r];
+          for (int c = 0; c < NU; ++c) xsB[c] = (float)sol.x[c];
+          E::load_inst(a, iB, inB);
+          if (want_saved) write_saved<E>(a, iB, sol);
+          c_iters += sol.iters;
         }
-        sol.iters = 0;
-        write_saved<E>(a, i, sol);
+      }
+      head = (head + take) & (kRing - 1);
+      qn -= take;
+      __syncwarp();
+    }
+
+    // ---- finish (clamp, env.step, outputs): ONE copy of the code, run for job A then job B
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      const bool on = j ? onB : onA;
+      if (on) {
+        Inst in = j ? inB : inA;
+        float xs[NU];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) xs[c] = j ? xsB[c] : xsA[c];
+        E::finish(a, p, e, j ? iB : iA, in, xs, j ? stB : stA);
       }
     }
-    if (valid && (triv || nan)) {
-      float xs[NU];
-#pragma unroll
-      for (int c = 0; c < NU; ++c) xs[c] = nan ? NAN : 0.f;
-      E::finish(a, p, e, i, in, xs, nan ? RCBF_NAN : RCBF_OK_TRIVIAL);
-      lc.nan += nan ? 1 : 0;
-      lc.triv += nan ? 0 : 1;
-    }
-    qn += __popc(ballot);
-    __syncwarp();
-    // ---- B-step whenever a full warp of problems is waiting
-    if (qn >= 32) {
-      solve_batch<E, kMode>(a, p, e, ws, ring, head, 32, lane, lc);
-      head = (head + 32) & (kRing - 1);
-      qn -= 32;
-    }
+    if (!have_tile && qn == 0) break;
   }
-  if (qn > 0) solve_batch<E, kMode>(a, p, e, ws, ring, head, qn, lane, lc);
 
   if (ws != nullptr) {
-    const int c_nan = __reduce_add_sync(0xffffffffu, lc.nan), c_triv = __reduce_add_sync(0xffffffffu, lc.triv);
-    const int c_pend = __reduce_add_sync(0xffffffffu, lc.pend), c_it = __reduce_add_sync(0xffffffffu, lc.iters);
+    c_nan = __reduce_add_sync(0xffffffffu, c_nan);
+    c_triv = __reduce_add_sync(0xffffffffu, c_triv);
+    c_pend = __reduce_add_sync(0xffffffffu, c_pend);
+    c_iters = __reduce_add_sync(0xffffffffu, c_iters);
     if (lane == 0) {
       if (c_nan) atomicAdd(&ws[0], (unsigned long long)c_nan);
       if (c_triv) atomicAdd(&ws[3], (unsigned long long)c_triv);
-      if (c_it) atomicAdd(&ws[4], (unsigned long long)c_it);
+      if (c_iters) atomicAdd(&ws[4], (unsigned long long)c_iters);
       if (c_pend) atomicAdd(&ws[5], (unsigned long long)c_pend);
     }
   }
