@@ -9,7 +9,7 @@ import os
 from . import _params as P
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "librcbf_b200.so")
+LIB_PATH = os.environ.get("RCBF_LIB_PATH", os.path.join(HERE, "librcbf_b200.so"))  # env override: A/B builds
 
 _f = C.POINTER(C.c_float)
 _d = C.POINTER(C.c_double)

@@ -37,6 +37,8 @@ __device__ __forceinline__ void ld_row(const float* __restrict__ base, int64_t i
 #pragma unroll
   for (int j = 0; j < K; ++j) out[j] = __ldg(base + i * K + j);
 }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 template <int K>
 __device__ __forceinline__ void st_row(float* __restrict__ base, int64_t i, const float in[K]) {
 #pragma unroll
@@ -94,13 +96,28 @@ struct UniEnv {
   }
   // raw rows in NWR = 19 words: (G[i][0], G[i][1]) of the 5 CBF rows + the 9 h; the rest of G is constant
   static constexpr int NWR = 19;
-  __device__ static __forceinline__ void assemble_raw(const Args& a, const Params& p, int64_t i, const Inst& in,
-                                                      float w[NWR], bool& triv, bool& nan) {
+  struct Aux {  // the inputs only the assembly reads (loaded one tile ahead by the persistent loop)
     float m[3], g[3];
-    ld_row<3>(a.mu, i, m);
-    ld_row<3>(a.sg, i, g);
+  };
+  __device__ static __forceinline__ void load_aux(const Args& a, int64_t i, Aux& x) {
+    ld_row<3>(a.mu, i, x.m);
+    ld_row<3>(a.sg, i, x.g);
+  }
+  __device__ static __forceinline__ void prefetch(const Args& a, int64_t i) {
+    if (kFused) {
+      prefetch_l1(a.state4 + i * 4);
+      prefetch_l1(a.step + i);
+    } else {
+      prefetch_l1(a.st + i * 3);
+    }
+    prefetch_l1(a.ac + i * 2);
+    prefetch_l1(a.mu + i * 3);
+    prefetch_l1(a.sg + i * 3);
+  }
+  __device__ static __forceinline__ void assemble_raw(const Params& p, const Inst& in, const Aux& x, float w[NWR],
+                                                      bool& triv, bool& nan) {
     UniRaw raw;
-    assemble_unicycle(p, in.v, in.u, m, g, raw);
+    assemble_unicycle(p, in.v, in.u, x.m, x.g, raw);
     classify_raw<M>(raw.h, triv, nan);
 #pragma unroll
     for (int r = 0; r < kUniHaz; ++r) {
@@ -135,7 +152,9 @@ struct UniEnv {
                                                   Normalised<NZ, M>& nrm) {
     float w[NWR];
     bool triv, nan;
-    assemble_raw(a, p, i, in, w, triv, nan);
+    Aux x;
+    load_aux(a, i, x);
+    assemble_raw(p, in, x, w, triv, nan);
     normalise_packed(w, p, nrm);
   }
   __device__ static __forceinline__ void finish(const Args& a, const Params& p, const EnvParams& e, int64_t i, Inst& in,
@@ -202,20 +221,36 @@ struct CarsEnv {
     }
   }
   static constexpr int NWR = 6;  // G[0][0], G[1][0] + the 4 h; the slack column and the actuator rows are constant
-  __device__ static __forceinline__ void assemble_raw(const Args& a, const Params& p, int64_t i, const Inst& in,
-                                                      float w[NWR], bool& triv, bool& nan) {
+  struct Aux {
     float s[10], g[10];
+  };
+  __device__ static __forceinline__ void load_aux(const Args& a, int64_t i, Aux& x) {
     const float2* sp = reinterpret_cast<const float2*>(kFused ? a.state : a.st) + i * 5;  // rows are 40 B: 8-aligned
     const float2* gp = reinterpret_cast<const float2*>(a.sg) + i * 5;
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
       const float2 q = kFused ? sp[k] : __ldg(sp + k);
       const float2 r = __ldg(gp + k);
-      s[2 * k] = q.x; s[2 * k + 1] = q.y;
-      g[2 * k] = r.x; g[2 * k + 1] = r.y;
+      x.s[2 * k] = q.x; x.s[2 * k + 1] = q.y;
+      x.g[2 * k] = r.x; x.g[2 * k + 1] = r.y;
     }
+  }
+  __device__ static __forceinline__ void prefetch(const Args& a, int64_t i) {
+    const float* sp = (kFused ? a.state : a.st) + i * 10;
+    prefetch_l1(sp);
+    prefetch_l1(sp + 8);
+    prefetch_l1(a.sg + i * 10);
+    prefetch_l1(a.sg + i * 10 + 8);
+    prefetch_l1(a.ac + i);
+    if (kFused) {
+      prefetch_l1(a.t + i);
+      prefetch_l1(a.step + i);
+    }
+  }
+  __device__ static __forceinline__ void assemble_raw(const Params& p, const Inst& in, const Aux& x, float w[NWR],
+                                                      bool& triv, bool& nan) {
     CarsRaw raw;
-    assemble_cars(p, s, in.u[0], g, raw);
+    assemble_cars(p, x.s, in.u[0], x.g, raw);
     classify_raw<M>(raw.h, triv, nan);
     w[0] = raw.G[0][0];
     w[1] = raw.G[1][0];
@@ -239,7 +274,9 @@ struct CarsEnv {
                                                   Normalised<NZ, M>& nrm) {
     float w[NWR];
     bool triv, nan;
-    assemble_raw(a, p, i, in, w, triv, nan);
+    Aux x;
+    load_aux(a, i, x);
+    assemble_raw(p, in, x, w, triv, nan);
     normalise_packed(w, p, nrm);
   }
   __device__ static __forceinline__ void finish(const Args& a, const Params& p, const EnvParams& e, int64_t i, Inst& in,
@@ -296,6 +333,9 @@ __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i
 // ---------------------------------------------------------------------------------------------------------------
 // pass 1: persistent warps, warp-private compaction ring
 // ---------------------------------------------------------------------------------------------------------------
+#ifndef RCBF_MINB
+#define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (register cap 128)
+#endif
 constexpr int kWarps = 4;             // warps per block
 constexpr int kThreadsW = 32 * kWarps;
 constexpr int kRing = 64;             // ring capacity per warp: at most 31 left over + 32 new
@@ -316,7 +356,7 @@ __device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t 
 }
 
 template <class E, int kMode /* 0 presolve, 1 pdipm */>
-__global__ void __launch_bounds__(kThreadsW, kMode == 0 ? 4 : 2)
+__global__ void __launch_bounds__(kThreadsW, kMode == 0 ? RCBF_MINB : 2)
 k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NWR = E::NWR;
   using Inst = typename E::Inst;
@@ -343,10 +383,16 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       const int64_t i0 = (tile << 5) + lane;
       const bool valid = i0 < n;
       iA = valid ? i0 : n - 1;
+      if (tile + nw < ntiles) {  // pull the NEXT tile's input lines towards L1 while this tile is being processed
+        const int64_t j0 = ((tile + nw) << 5) + lane;
+        E::prefetch(a, j0 < n ? j0 : n - 1);
+      }
       E::load_inst(a, iA, inA);
+      typename E::Aux aux;
+      E::load_aux(a, iA, aux);
       float w[NWR];
       bool triv, nan;
-      E::assemble_raw(a, p, iA, inA, w, triv, nan);
+      E::assemble_raw(p, inA, aux, w, triv, nan);
       const bool need = valid && !triv && !nan;
       const unsigned ballot = __ballot_sync(0xffffffffu, need);
       if (need) {
@@ -583,7 +629,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   if (n > 0x7fffffffLL) return -2;  // ring indices are 32-bit
   const int64_t ntiles = (n + 31) / 32;
   const int64_t want = (ntiles + kWarps - 1) / kWarps;
-  const int resident = 148 * (p.solver_mode == 0 ? 4 : 2);  // persistent: one wave of resident blocks
+  const int resident = 148 * (p.solver_mode == 0 ? RCBF_MINB : 2);  // persistent: one wave of resident blocks
   const int grid = (int)(want < resident ? want : resident);
   const int64_t fb = (n + 127) / 128;
   const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);
