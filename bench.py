@@ -326,9 +326,13 @@ def main():
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    # optional rollout-statistics reduction (the only collective of the design; off the timed path)
+    from sac_rcbf_b200 import sharding
+    stats = sharding.reduce_rollout_stats(sharding.local_rollout_stats(env._reward, env._cost, env._done, env._goal,
+                                                                       env._counters))
     counters = env._counters[:8].clone()
     if dist is not None:
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)   # optional rollout statistics gather: off the timed path
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
     c = counters.cpu().tolist()
     total_steps = float(n) * world * args.steps
     value = total_steps / (ms * 1e-3)
@@ -430,6 +434,7 @@ def main():
                                       "f32 assembly + restated qpth f64 + numpy f64 env step)" % (done_n, el)}
         else:
             cpu_baseline = None
+        extra["last_step_stats"] = stats
         extra["solver"] = {"mode": layer.solver, "nan": c[0], "uncertified": c[1], "f64_passes": c[2], "trivial": c[3],
                            "presolve_rounds_mean": iters_mean, "fallback": c[5], "fallback_ipm_iters": c[6]}
         if not args.no_extra:
