@@ -120,6 +120,8 @@ def cpu_reference_step(O, batch, st, ac, mu, sg):
 def time_cpu_reference(seconds, batch=512):
     from oracle import rcbf_oracle as O
 
+    torch.set_num_threads(max(1, os.cpu_count() or 1))   # torchrun pins OMP_NUM_THREADS=1: use every host core
+
     st, ac, mu, sg = O.synth_unicycle(batch * 8, seed=12345)
     cpu_reference_step(O, batch, st[:batch], ac[:batch], mu[:batch], sg[:batch])   # warm-up
     done, t0 = 0, time.perf_counter()
@@ -138,6 +140,7 @@ def run_reference(args):
         return
     from oracle import rcbf_oracle as O
 
+    torch.set_num_threads(max(1, os.cpu_count() or 1))   # all the host threads it can use
     batch, per_step = 512, 4096
     st, ac, mu, sg = O.synth_unicycle(per_step, seed=12345)
     for _ in range(args.warmup):

@@ -1037,7 +1037,8 @@ RCBF_HD void solve_normalised_full(const Normalised<NZ, M>& nrm, const float p_d
 // ------------------------------------------------------------------------------------------------
 // get_safe_action for one instance (diff_cbf_qp.py:44-79): assemble -> normalise -> solve -> clamp
 // ------------------------------------------------------------------------------------------------
-RCBF_HD float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+// torch.clamp propagates NaN (fminf/fmaxf would return the bound)
+RCBF_HD float clampf(float v, float lo, float hi) { return (v != v) ? v : fminf(fmaxf(v, lo), hi); }
 
 struct UniSolve {
   UniRaw raw;

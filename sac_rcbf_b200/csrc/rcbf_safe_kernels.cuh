@@ -39,6 +39,33 @@ __device__ __forceinline__ void ld_row(const float* __restrict__ base, int64_t i
 }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier): the input rows of a 32-instance
+// tile are contiguous spans, so each array of the NEXT tile is fetched by one asynchronous 1-D bulk copy issued by
+// lane 0 while the warp works on the current tile.  No registers are tied up and the latency is fully hidden.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 template <int K>
 __device__ __forceinline__ void st_row(float* __restrict__ base, int64_t i, const float in[K]) {
 #pragma unroll
@@ -102,6 +129,51 @@ struct UniEnv {
   __device__ static __forceinline__ void load_aux(const Args& a, int64_t i, Aux& x) {
     ld_row<3>(a.mu, i, x.m);
     ld_row<3>(a.sg, i, x.g);
+  }
+  struct alignas(16) Stage {  // one tile of inputs as the bulk copies land them (same row-major layout as HBM)
+    float st[32 * 4];      // fused: (x,y,th,last) x 32 ; plain: (x,y,th) x 32 in the first 96 words
+    float ac[32 * 2];
+    float mu[32 * 3];
+    float sg[32 * 3];
+    int step[32];
+  };
+  static constexpr uint32_t kStageBytes = (kFused ? 512 + 128 : 384) + 256 + 384 + 384;
+  __host__ __device__ static __forceinline__ bool aligned(const Args& a) {
+    auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return ok(kFused ? (const void*)a.state4 : (const void*)a.st) && ok(a.ac) && ok(a.mu) && ok(a.sg) &&
+           (!kFused || ok(a.step));
+  }
+  __device__ static __forceinline__ void issue(const Args& a, int64_t tile, Stage& sg_, uint64_t* bar) {
+    const int64_t i0 = tile << 5;
+    mbar_expect_tx(bar, kStageBytes);
+    if (kFused) {
+      bulk_g2s(sg_.st, a.state4 + i0 * 4, 512, bar);
+      bulk_g2s(sg_.step, a.step + i0, 128, bar);
+    } else {
+      bulk_g2s(sg_.st, a.st + i0 * 3, 384, bar);
+    }
+    bulk_g2s(sg_.ac, a.ac + i0 * 2, 256, bar);
+    bulk_g2s(sg_.mu, a.mu + i0 * 3, 384, bar);
+    bulk_g2s(sg_.sg, a.sg + i0 * 3, 384, bar);
+  }
+  __device__ static __forceinline__ void read_stage(const Stage& sg_, int lane, Inst& in, Aux& x) {
+    if (kFused) {
+      const float4 q = reinterpret_cast<const float4*>(sg_.st)[lane];
+      in.v[0] = q.x; in.v[1] = q.y; in.v[2] = q.z; in.v[3] = q.w;
+      in.stp = sg_.step[lane];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) in.v[j] = sg_.st[lane * 3 + j];
+      in.v[3] = 0.f;
+      in.stp = 0;
+    }
+    const float2 u2 = reinterpret_cast<const float2*>(sg_.ac)[lane];
+    in.u[0] = u2.x; in.u[1] = u2.y;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      x.m[j] = sg_.mu[lane * 3 + j];
+      x.g[j] = sg_.sg[lane * 3 + j];
+    }
   }
   __device__ static __forceinline__ void prefetch(const Args& a, int64_t i) {
     if (kFused) {
@@ -235,6 +307,43 @@ struct CarsEnv {
       x.g[2 * k] = r.x; x.g[2 * k + 1] = r.y;
     }
   }
+  struct alignas(16) Stage {
+    float st[32 * 10];
+    float sg[32 * 10];
+    float ac[32];
+    float t[32];
+    int step[32];
+  };
+  static constexpr uint32_t kStageBytes = 1280 + 1280 + 128 + (kFused ? 256 : 0);
+  __host__ __device__ static __forceinline__ bool aligned(const Args& a) {
+    auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    return ok(kFused ? (const void*)a.state : (const void*)a.st) && ok(a.ac) && ok(a.sg) &&
+           (!kFused || (ok(a.t) && ok(a.step)));
+  }
+  __device__ static __forceinline__ void issue(const Args& a, int64_t tile, Stage& sg_, uint64_t* bar) {
+    const int64_t i0 = tile << 5;
+    mbar_expect_tx(bar, kStageBytes);
+    bulk_g2s(sg_.st, (kFused ? a.state : a.st) + i0 * 10, 1280, bar);
+    bulk_g2s(sg_.sg, a.sg + i0 * 10, 1280, bar);
+    bulk_g2s(sg_.ac, a.ac + i0, 128, bar);
+    if (kFused) {
+      bulk_g2s(sg_.t, a.t + i0, 128, bar);
+      bulk_g2s(sg_.step, a.step + i0, 128, bar);
+    }
+  }
+  __device__ static __forceinline__ void read_stage(const Stage& sg_, int lane, Inst& in, Aux& x) {
+    const float2* sp = reinterpret_cast<const float2*>(sg_.st) + lane * 5;
+    const float2* gp = reinterpret_cast<const float2*>(sg_.sg) + lane * 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const float2 q = sp[k], r = gp[k];
+      x.s[2 * k] = q.x; x.s[2 * k + 1] = q.y;
+      x.g[2 * k] = r.x; x.g[2 * k + 1] = r.y;
+    }
+    in.u[0] = sg_.ac[lane];
+    in.tt = kFused ? sg_.t[lane] : 0.f;
+    in.stp = kFused ? sg_.step[lane] : 0;
+  }
   __device__ static __forceinline__ void prefetch(const Args& a, int64_t i) {
     const float* sp = (kFused ? a.state : a.st) + i * 10;
     prefetch_l1(sp);
@@ -334,7 +443,7 @@ __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i
 // pass 1: persistent warps, warp-private compaction ring
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef RCBF_MINB
-#define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (register cap 128)
+#define RCBF_MINB 3  // resident blocks per SM the presolve-mode kernel is compiled for (168 registers: no spills; A/B on B200: 3 > 4 > 2)
 #endif
 constexpr int kWarps = 4;             // warps per block
 constexpr int kThreadsW = 32 * kWarps;
@@ -355,12 +464,14 @@ __device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t 
   }
 }
 
-template <class E, int kMode /* 0 presolve, 1 pdipm */>
+template <class E, int kMode /* 0 presolve, 1 pdipm */, bool kBulk /* TMA bulk-copy input staging */>
 __global__ void __launch_bounds__(kThreadsW, kMode == 0 ? RCBF_MINB : 2)
 k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NWR = E::NWR;
   using Inst = typename E::Inst;
   __shared__ WarpRing<E> s_ring[kWarps];
+  __shared__ typename E::Stage s_stage[kBulk ? kWarps : 1][2];
+  __shared__ uint64_t s_bar[kBulk ? kWarps : 1][2];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpRing<E>& ring = s_ring[warp];
   const int64_t ntiles = (n + 31) >> 5;
@@ -369,27 +480,56 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
   const bool want_saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr);
   int head = 0, qn = 0;
   int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
+  int nbulk = 0;  // bulk-staged tiles consumed so far by this warp (buffer = nbulk & 1, mbarrier parity = (nbulk >> 1) & 1)
+  if (kBulk) {
+    if (lane == 0) {
+      mbar_init(&s_bar[warp][0], 1);
+      mbar_init(&s_bar[warp][1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0 && ((tile << 5) + 32 <= n)) E::issue(a, tile, s_stage[warp][0], &s_bar[warp][0]);
+  }
+
+  // job B = the instance this lane solved in the PREVIOUS iteration's B-step; it is finished after the next A-step so
+  // that nothing but (index, correction, status) is live across the register-hungry solve
+  bool onB = false;
+  int iB = 0, stB = RCBF_OK_CERTIFIED;
+  float xsB[NU];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) xsB[c] = 0.f;
 
   for (;;) {
     const bool have_tile = tile < ntiles;
-    // job A: this lane's own instance when it needs no solve; job B: the instance this lane solved in the B-step
-    bool onA = false, onB = false;
-    int64_t iA = 0, iB = 0;
-    Inst inA, inB;
-    float xsA[NU], xsB[NU];
-    int stA = RCBF_OK_TRIVIAL, stB = RCBF_OK_CERTIFIED;
+    // job A: this lane's own instance when it needs no solve
+    bool onA = false;
+    int64_t iA = 0;
+    Inst inA;
+    float xsA[NU];
+    int stA = RCBF_OK_TRIVIAL;
 
     if (have_tile) {  // ---- A-step: assemble, classify, queue
       const int64_t i0 = (tile << 5) + lane;
       const bool valid = i0 < n;
       iA = valid ? i0 : n - 1;
-      if (tile + nw < ntiles) {  // pull the NEXT tile's input lines towards L1 while this tile is being processed
-        const int64_t j0 = ((tile + nw) << 5) + lane;
-        E::prefetch(a, j0 < n ? j0 : n - 1);
-      }
-      E::load_inst(a, iA, inA);
       typename E::Aux aux;
-      E::load_aux(a, iA, aux);
+      if (kBulk && (tile << 5) + 32 <= n) {
+        // this tile's inputs were bulk-copied into shared memory one iteration ago; wait, read, then put the NEXT
+        // tile in flight into the other buffer (its last reader finished before the previous __syncwarp)
+        const int b = nbulk & 1;
+        mbar_wait(&s_bar[warp][b], (nbulk >> 1) & 1);
+        E::read_stage(s_stage[warp][b], lane, inA, aux);
+        __syncwarp();
+        if (lane == 0 && (((tile + nw) << 5) + 32 <= n)) E::issue(a, tile + nw, s_stage[warp][b ^ 1], &s_bar[warp][b ^ 1]);
+        ++nbulk;
+      } else {
+        if (!kBulk && tile + nw < ntiles) {  // pull the NEXT tile's input lines towards L1 meanwhile
+          const int64_t j0 = ((tile + nw) << 5) + lane;
+          E::prefetch(a, j0 < n ? j0 : n - 1);
+        }
+        E::load_inst(a, iA, inA);
+        E::load_aux(a, iA, aux);
+      }
       float w[NWR];
       bool triv, nan;
       E::assemble_raw(p, inA, aux, w, triv, nan);
@@ -419,6 +559,23 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
     }
     __syncwarp();
 
+    // ---- finish (clamp, env.step, outputs): ONE copy of the code, run for job A, then for last iteration's job B
+#pragma unroll 1
+    for (int j = 0; j < 2; ++j) {
+      const bool on = j ? onB : onA;
+      if (on) {
+        const int64_t i = j ? (int64_t)iB : iA;
+        Inst in;
+        if (j) E::load_inst(a, i, in);
+        else in = inA;
+        float xs[NU];
+#pragma unroll
+        for (int c = 0; c < NU; ++c) xs[c] = j ? xsB[c] : xsA[c];
+        E::finish(a, p, e, i, in, xs, j ? stB : stA);
+      }
+    }
+    onB = false;
+
     // ---- B-step: a full warp of queued problems (or whatever is left once the tiles are exhausted)
     const int take = (qn >= 32) ? 32 : (have_tile ? 0 : qn);
     if (take > 0) {
@@ -440,7 +597,6 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
           stB = sol.status;
 #pragma unroll
           for (int c = 0; c < NU; ++c) xsB[c] = (float)sol.x[c];
-          E::load_inst(a, iB, inB);
           if (want_saved) write_saved<E>(a, iB, sol);
           c_iters += sol.iters;
         }
@@ -449,20 +605,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       qn -= take;
       __syncwarp();
     }
-
-    // ---- finish (clamp, env.step, outputs): ONE copy of the code, run for job A then job B
-#pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-      const bool on = j ? onB : onA;
-      if (on) {
-        Inst in = j ? inB : inA;
-        float xs[NU];
-#pragma unroll
-        for (int c = 0; c < NU; ++c) xs[c] = j ? xsB[c] : xsA[c];
-        E::finish(a, p, e, j ? iB : iA, in, xs, j ? stB : stA);
-      }
-    }
-    if (!have_tile && qn == 0) break;
+    if (!have_tile && qn == 0 && !__any_sync(0xffffffffu, onB)) break;
   }
 
   if (ws != nullptr) {
@@ -633,11 +776,15 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   const int grid = (int)(want < resident ? want : resident);
   const int64_t fb = (n + 127) / 128;
   const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);
+  // TMA bulk staging needs 16-byte aligned array bases (row spans of a 32-instance tile are then 16-byte multiples)
+  const bool bulk = E::aligned(a) && n >= 32;
   if (p.solver_mode == 0) {
-    k_safe<E, 0><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
+    if (bulk) k_safe<E, 0, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
+    else k_safe<E, 0, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
     k_safe_fallback<E, 0><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
   } else {
-    k_safe<E, 1><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
+    if (bulk) k_safe<E, 1, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
+    else k_safe<E, 1, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
     k_safe_fallback<E, 1><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
   }
   return (int)cudaGetLastError();

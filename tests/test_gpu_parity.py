@@ -178,6 +178,47 @@ def test_fallback_pass_without_workspace_scans_for_the_sentinel(cars):
     np.testing.assert_array_equal(out.cpu().numpy(), ref[0])
 
 
+@pytest.mark.parametrize("mode", ["Unicycle", "SimulatedCars"])
+def test_ragged_empty_and_unaligned_batches(request, mode):
+    """Edge cases of the tiled kernel: empty batch, sizes around the 32-instance tile, and row slices whose base
+    address is not 16-byte aligned (the TMA bulk-copy staging must fall back to plain loads).  All must equal the
+    corresponding rows of one big aligned launch bit for bit."""
+    env, layer = request.getfixturevalue("uni" if mode == "Unicycle" else "cars")
+    B = 4099
+    arrs = O.synth_unicycle(B, seed=3, hazard_frac=0.6) if mode == "Unicycle" else O.synth_cars(B, seed=3)
+    d = [_cuda(a) for a in arrs[:4]]
+    ref = layer.get_safe_action(*d)
+    for n in (0, 1, 31, 32, 33, 63, 64, 65, 1000):
+        out = layer.get_safe_action(*(t[:n] for t in d))
+        assert out.shape == ref[:n].shape and torch.equal(out, ref[:n])
+    for off in (1, 2, 3, 5, 7):                 # 12/8/40-byte rows: most offsets break 16-byte alignment
+        sl = [t[off:off + 777] for t in d]
+        assert any(t.data_ptr() % 16 for t in sl)
+        out = layer.get_safe_action(*sl)
+        assert torch.equal(out, ref[off:off + 777])
+    # non-contiguous / float64 inputs are accepted like torch ops would
+    out = layer.get_safe_action(*(t.double() for t in d))
+    assert out.dtype == torch.float64 and torch.equal(out.float(), ref)
+
+
+def test_one_nan_instance_in_a_large_batch_raises_and_is_flagged(uni):
+    env, layer = uni
+    B = 100000
+    st, ac, mu, sg = O.synth_unicycle(B, seed=8)
+    st[54321, 1] = np.nan
+    d = [_cuda(a) for a in (st, ac, mu, sg)]
+    with pytest.raises(Exception, match="QP Failed to solve"):
+        layer.get_safe_action(*d)
+    layer.check_nan = False
+    try:
+        out, x, lam, slack = layer._forward_raw(*d, save=False, want_status=True)
+    finally:
+        layer.check_nan = True
+    status = layer._last_status.cpu().numpy()
+    assert status[54321] == 4 and (np.delete(status, 54321) <= 2).all()
+    assert torch.isnan(out[54321]).all() and not torch.isnan(out).sum().item() > 2
+
+
 def test_trivial_instances_pass_through(uni):
     env, layer = uni
     B = 4096
@@ -437,6 +478,33 @@ def test_full_size_properties(uni):
                         assembly_dtype=torch.float64, gamma_b=20.0)
     ok = np.abs(fe.numpy() - f64.numpy()).max(1) <= 2e-5
     assert np.abs(out[idx] - fe.numpy())[ok].max() < ACT_TOL
+
+
+def test_config5_cars_sweep_top_size_properties(cars):
+    """BASELINE config 5's largest size (16 Mi SimulatedCars QPs on one GPU): every row feasible, duals valid, and a
+    seeded sub-sample equal to the same rows solved in a small launch."""
+    env, layer = cars
+    B = 1 << 24
+    g = torch.Generator(device="cuda").manual_seed(5)
+    t = 6 * torch.rand(B, generator=g, device="cuda")
+    st = torch.zeros(B, 10, device="cuda")
+    st[:, 0::2] = torch.tensor([34., 28., 22., 16., 10.], device="cuda") + 30 * t[:, None] + 1.5 * torch.randn(B, 5, generator=g, device="cuda")
+    st[:, 1::2] = 30 + 2 * torch.randn(B, 5, generator=g, device="cuda")
+    st[:, 7] += 3
+    ac = 2 * torch.rand(B, 1, generator=g, device="cuda") - 1
+    sg = torch.zeros(B, 10, device="cuda")
+    sg[:, 1::2] = 0.2 * torch.rand(B, 5, generator=g, device="cuda")
+    mu = torch.zeros(B, 10, device="cuda")
+    out, x, lam, slack = layer._forward_raw(st, ac, mu, sg, save=True, want_status=True)
+    stats = layer.solver_stats()
+    assert stats["nan"] == 0 and stats["uncertified"] == 0
+    assert float(slack.min()) > ROW_TOL and float(lam.min()) >= 0 and float(out.abs().max()) <= 10.0
+    idx = torch.randperm(B, generator=g, device="cuda")[:5000]
+    small = layer.get_safe_action(st[idx], ac[idx], mu[idx], sg[idx])
+    assert torch.equal(small, out[idx])
+    fe = O.safe_action("SimulatedCars", st[idx].cpu(), ac[idx].cpu(), mu[idx].cpu(), sg[idx].cpu(), solver="exact", gamma_b=20.0)
+    keep = O.cars_threshold_margin(st[idx].cpu().numpy()) > 1e-4
+    assert np.abs(small.cpu().numpy() - fe.numpy())[keep].max() < ACT_TOL
 
 
 def test_host_buffer_entry_matches_device_entry(S, uni, cars):
