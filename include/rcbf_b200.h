@@ -11,6 +11,7 @@
  *   rcbf_*_env_reset_*       .reset()                                   envs/unicycle_env.py:125-143 ; envs/simulated_cars_env.py:108-125
  *   rcbf_*_predict_next_*    DynamicsModel.predict_next_state (prior)   rcbf_sac/dynamics.py:60-105
  *   rcbf_*_safe_step         get_safe_action + env.step fused           rcbf_sac/sac_cbf.py:218-238 + main.py:93-95
+ *   rcbf_*_rollout_step_*    one transition of generate_model_rollouts  rcbf_sac/generate_rollouts.py:29-66
  *   (CascadeCBFLayer.get_u_safe, rcbf_sac/cbf_qp.py:29-53, is rcbf_unicycle_safe_action with sigma_scale = k_d,
  *    abs_sigma_map = 0, p_diag = (10, 1e-4, 1e7) and the unclamped correction read from `x`.)
  *
@@ -155,6 +156,24 @@ int rcbf_cars_predict_next_f32(const float* state, const float* action, const fl
                                double dt, double kp, double k_brake, float* next, void* stream);
 int rcbf_cars_predict_next_f64(const double* state, const double* action, const double* t, const double* mean,
                                int64_t n, double dt, double kp, double k_brake, double* next, void* stream);
+
+/* ---- model-rollout transition (generate_model_rollouts, rcbf_sac/generate_rollouts.py:29-66): state = get_state(obs),
+ * next ~ N(prior_next(state, a) + dt*mean, (dt*std)^2) with the standard-normal draw `eps` supplied by the caller,
+ * next_obs / reward / done rebuilt like the reference (incl. its double reward_goal).  mean, std, eps nullable. ------ */
+int rcbf_unicycle_rollout_step_f32(const float* obs /* n*7 */, const float* action, const float* mean,
+                                   const float* std, const float* eps, int64_t n, double dt, double goal_x,
+                                   double goal_y, float* next_obs /* n*7 */, float* reward, uint8_t* done, void* stream);
+int rcbf_unicycle_rollout_step_f64(const double* obs, const double* action, const double* mean, const double* std,
+                                   const double* eps, int64_t n, double dt, double goal_x, double goal_y,
+                                   double* next_obs, double* reward, uint8_t* done, void* stream);
+int rcbf_cars_rollout_step_f32(const float* obs /* n*10 */, const float* action, const float* t, const float* mean,
+                               const float* std, const float* eps, int64_t n, double dt, double kp, double k_brake,
+                               int max_steps, float* next_obs, float* reward, uint8_t* done, float* next_t,
+                               void* stream);
+int rcbf_cars_rollout_step_f64(const double* obs, const double* action, const double* t, const double* mean,
+                               const double* std, const double* eps, int64_t n, double dt, double kp, double k_brake,
+                               int max_steps, double* next_obs, double* reward, uint8_t* done, double* next_t,
+                               void* stream);
 
 /* ---- fused safe step: assemble + QP + clamp + env.step in ONE launch (float32 env layout) --------------------- */
 int rcbf_unicycle_safe_step(float* state4, int32_t* step, const float* action_rl, const float* mean,

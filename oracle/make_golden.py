@@ -142,6 +142,61 @@ def cascade_fixture(ref, B=16):
                 cars_state=stc, cars_action=acc, cars_sigma=sgc, cars_G=np.array(Gc), cars_h=np.array(hc))
 
 
+def rollouts_fixture(ref, B=25):
+    """The reference's own generate_model_rollouts (rcbf_sac/generate_rollouts.py) driven with a stub agent / memory and
+    a recorded Gaussian draw; what it pushes to memory_model is the golden output."""
+    out = {}
+    args = ref_loader.make_args()
+    for mode, envc in (("Unicycle", ref.UnicycleEnv), ("SimulatedCars", ref.SimulatedCarsEnv)):
+        env = envc()
+        dm = ref.DynamicsModel(env, args)
+        rng = np.random.default_rng(4321)
+        if mode == "Unicycle":
+            st, ac, _, _ = O.synth_unicycle(B, seed=4321)
+            st = st.astype(np.float64)
+            st[:3, :2] = env.goal_pos + np.array([[0.05, -0.1], [0.2, 0.1], [-0.15, 0.05]])   # some reach the goal
+            obs = O.unicycle_obs(st)
+            t = np.arange(B) * 0.02
+            n_s, n_u = 3, 2
+        else:
+            st, ac, _, _, t = O.synth_cars(B, seed=4321)
+            st = st.astype(np.float64)
+            obs = O.cars_obs(st)
+            t = t.astype(np.float64)
+            t[:4] = 300 * 0.02 - 0.02 * np.array([0.5, 1.0, 1.5, 3.0])     # straddle the time horizon
+            n_s, n_u = 10, 1
+        actions = rng.uniform(-1, 1, (B, n_u)) * (2.5 if mode == "Unicycle" else 10.0)
+        eps = rng.normal(size=(B, n_s))
+
+        class Mem:
+            def __init__(self):
+                self.items = None
+
+            def sample(self, batch_size):
+                return obs.copy(), None, None, None, None, t.copy(), None
+
+            def batch_push(self, *a):
+                self.items = [np.array(x, copy=True) for x in a]
+
+        class Agent:
+            def select_action(self, o, dmodel, evaluate=False, warmup=False):
+                return actions.copy()
+
+        mm = Mem()
+        orig = np.random.normal
+        np.random.normal = lambda mu, sd, *a, **k: mu + sd * eps        # generate_rollouts.py:31
+        try:
+            ref.generate_model_rollouts(env, mm, Mem(), Agent(), dm, k_horizon=1, batch_size=B)
+        finally:
+            np.random.normal = orig
+        k = mode.lower()
+        names = ("obs", "action", "reward", "next_obs", "mask", "t", "next_t")
+        for nme, val in zip(names, mm.items):
+            out[k + "_" + nme] = np.asarray(val, np.float64) if val.dtype != bool else val
+        out[k + "_eps"] = eps
+    return out
+
+
 def main():
     ref = ref_loader.load_reference()
     os.makedirs(OUT, exist_ok=True)
@@ -152,6 +207,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "cars_env_traj.npz"), **cars_traj(ref))
     np.savez_compressed(os.path.join(OUT, "dynamics_prior.npz"), **dynamics_fixture(ref))
     np.savez_compressed(os.path.join(OUT, "cascade_layer.npz"), **cascade_fixture(ref))
+    np.savez_compressed(os.path.join(OUT, "model_rollouts.npz"), **rollouts_fixture(ref))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -411,6 +411,37 @@ def get_obs(mode, state):
 
 
 # --------------------------------------------------------------------------------------
+# model-rollout transition                                     rcbf_sac/generate_rollouts.py:29-66
+# --------------------------------------------------------------------------------------
+def rollout_step(mode, obs, action, t, eps, mean=None, std=None):
+    """One transition of generate_model_rollouts for a batch (numpy f64).  eps = standard-normal draw such that
+    np.random.normal(mu, sd) == mu + sd * eps (:31).  Returns next_obs, reward, done, next_t."""
+    obs = np.asarray(obs, np.float64)
+    action = np.asarray(action, np.float64)
+    B = obs.shape[0]
+    state = get_state(mode, obs)                                            # :29
+    mu, sd, next_t = predict_next_state(mode, state, action, t, mean=mean, std=std)   # :30
+    nxt = mu + sd * np.asarray(eps, np.float64)                             # :31
+    nobs = get_obs(mode, nxt)                                               # :32
+    if mode == "Unicycle":
+        dist_prev = -np.log(obs[:, -1])                                     # :37
+        goal_rel = UNICYCLE["goal_pos"][None, :] - nobs[:, :2]              # :38
+        dist = np.linalg.norm(goal_rel, axis=1)                             # :39
+        c, s = np.cos(nxt[:, 2]), np.sin(nxt[:, 2])
+        comp = np.stack([goal_rel[:, 0] * c + goal_rel[:, 1] * s, -goal_rel[:, 0] * s + goal_rel[:, 1] * c], 1)   # :42
+        comp = comp / (np.sqrt(np.sum(comp ** 2, axis=1, keepdims=True)) + 0.001)                                 # :43
+        nobs = np.hstack((nobs, comp, np.exp(-dist)[:, None]))              # :44
+        reached = dist <= 0.3
+        reward = (dist_prev - dist) * 1.0 + reached * 1.0                   # :50
+        reward = reward + 1.0 * reached                                     # :53 (added twice)
+        done = reached                                                      # :54
+    else:
+        reward = -5.0 * np.abs(action[:, 0] ** 2) / CARS["max_episode_steps"]   # :61
+        done = next_t >= CARS["max_episode_steps"] * CARS["dt"]                 # :64
+    return nobs, reward, done, next_t
+
+
+# --------------------------------------------------------------------------------------
 # Synthetic inputs (SURVEY.md section 8(d))
 # --------------------------------------------------------------------------------------
 def synth_unicycle(B, seed=12345, hazard_frac=0.2):

@@ -5,6 +5,7 @@ Public surface (mirrors the reference's names):
     CascadeCBFLayer             rcbf_sac/cbf_qp.py
     DynamicsModel               rcbf_sac/dynamics.py (prior paths)
     UnicycleEnv, SimulatedCarsEnv, build_env        envs/*.py, build_env.py
+    generate_model_rollouts, DeviceReplayMemory     rcbf_sac/generate_rollouts.py, replay_memory.py (device-resident)
 The compute lives in librcbf_b200.so (hand-written CUDA, C ABI in include/rcbf_b200.h).  No CPU fallback.
 """
 from ._lib import RcbfLibraryError, load as load_library  # noqa: F401
@@ -23,6 +24,12 @@ def __getattr__(name):  # lazy: importing the package must work on a box without
     if name in ("UnicycleEnv", "SimulatedCarsEnv"):
         from . import envs
         return getattr(envs, name)
+    if name == "DeviceReplayMemory":
+        from .replay_memory import DeviceReplayMemory
+        return DeviceReplayMemory
+    if name in ("generate_model_rollouts", "rollout_transition"):
+        from . import generate_rollouts
+        return getattr(generate_rollouts, name)
     if name == "build_env":
         from .build_env import build_env
         return build_env

@@ -46,6 +46,10 @@ for _suf in ("f32", "f64"):
     SIGNATURES["rcbf_cars_env_step_" + _suf] = [_vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsEnvParams), _vp, _vp, _vp,
                                                 _vp, _vp]
     SIGNATURES["rcbf_unicycle_predict_next_" + _suf] = [_vp, _vp, _vp, _i64, C.c_double, _vp, _vp]
+    SIGNATURES["rcbf_unicycle_rollout_step_" + _suf] = [_vp, _vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double,
+                                                        C.c_double, _vp, _vp, _vp, _vp]
+    SIGNATURES["rcbf_cars_rollout_step_" + _suf] = [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double,
+                                                    C.c_double, C.c_int, _vp, _vp, _vp, _vp, _vp]
     SIGNATURES["rcbf_cars_predict_next_" + _suf] = [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, C.c_double, _vp,
                                                     _vp]
 

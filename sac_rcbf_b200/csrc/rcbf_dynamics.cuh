@@ -201,4 +201,62 @@ RCBF_HD void cars_prior_next(T dt, T kp, T kb, const T st[10], T u, T t, const T
   for (int j = 0; j < 10; ++j) nxt[j] += dt * mean[j];
 }
 
+// ---------------------------------------------------------------------------------------------------
+// model rollouts: one transition of generate_model_rollouts        rcbf_sac/generate_rollouts.py:29-66
+//   state = get_state(obs) ; next ~ N(prior_next(state, a) + dt*mean, (dt*std)^2) ; next_obs, reward, done
+// `eps` is the standard-normal draw (np.random.normal(mu, std) == mu + std * eps), passed in so that the step is
+// deterministic given its inputs.
+// ---------------------------------------------------------------------------------------------------
+RCBF_HD float t_atan2(float y, float x) { return atan2f(y, x); }
+RCBF_HD double t_atan2(double y, double x) { return atan2(y, x); }
+RCBF_HD float t_log(float x) { return logf(x); }
+RCBF_HD double t_log(double x) { return log(x); }
+
+template <typename T>
+RCBF_HD void unicycle_rollout_step(T dt, T goal_x, T goal_y, const T obs[7], const T a[2], const T mean[3],
+                                   const T std[3], const T eps[3], T next_obs[7], T& reward, int& done) {
+  T st[3] = {obs[0], obs[1], t_atan2(obs[3], obs[2])};  // dynamics.py:216-221
+  T nx[3];
+  unicycle_prior_next<T>(dt, st, a, mean, nx);          // generate_rollouts.py:30 (dynamics.py:86-92)
+  RCBF_UNROLL
+  for (int j = 0; j < 3; ++j) nx[j] = nx[j] + (dt * std[j]) * eps[j];  // :31
+  T s, c;
+  sincos_t(nx[2], &s, &c);
+  const T dist_prev = -t_log(obs[6]);                   // :37  (obs[-1] = exp(-dist))
+  const T gx = goal_x - nx[0], gy = goal_y - nx[1];     // :38
+  const T dist = t_sqrt(gx * gx + gy * gy);             // :39
+  const T cx = gx * c + gy * s, cy = gx * (-s) + gy * c;  // :42 (row vector times R(theta'))
+  const T nrm = t_sqrt(cx * cx + cy * cy) + T(0.001);   // :43
+  next_obs[0] = nx[0];
+  next_obs[1] = nx[1];
+  next_obs[2] = c;
+  next_obs[3] = s;
+  next_obs[4] = cx / nrm;
+  next_obs[5] = cy / nrm;
+  next_obs[6] = t_exp(-dist);                           // :44
+  const bool reached = dist <= T(0.3);                  // :47,52
+  // :50 + :53 -- the reference adds reward_goal TWICE when the goal is reached
+  reward = (dist_prev - dist) * T(1) + (reached ? T(1) : T(0)) + (reached ? T(1) : T(0));
+  done = reached;                                       // :54
+}
+
+template <typename T>
+RCBF_HD void cars_rollout_step(T dt, T kp, T kb, int max_steps, const T obs[10], T a, T t, const T mean[10],
+                               const T std[10], const T eps[10], T next_obs[10], T& reward, int& done, T& next_t) {
+  T st[10], nx[10];
+  RCBF_UNROLL
+  for (int i = 0; i < 5; ++i) {                         // dynamics.py:222-225
+    st[2 * i] = obs[2 * i] * T(100);
+    st[2 * i + 1] = obs[2 * i + 1] * T(30);
+  }
+  cars_prior_next<T>(dt, kp, kb, st, a, t, mean, nx);   // generate_rollouts.py:30
+  RCBF_UNROLL
+  for (int j = 0; j < 10; ++j) nx[j] = nx[j] + (dt * std[j]) * eps[j];  // :31
+  cars_obs<T>(nx, next_obs);                            // :32
+  const T a2 = a * a;
+  reward = T(-5) * (a2 < T(0) ? -a2 : a2) / T(max_steps);  // :61
+  next_t = t + dt;                                      // dynamics.py:102
+  done = next_t >= T(max_steps) * dt;                   // :64
+}
+
 }  // namespace rcbf

@@ -343,6 +343,56 @@ k_cars_predict_next(const T* __restrict__ state, const T* __restrict__ action, c
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// model-rollout transition (generate_model_rollouts), one thread per instance
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_unicycle_rollout_step(const T* __restrict__ obs, const T* __restrict__ action, const T* __restrict__ mean,
+                        const T* __restrict__ std, const T* __restrict__ eps, int64_t n, T dt, T gx, T gy,
+                        T* __restrict__ next_obs, T* __restrict__ reward, uint8_t* __restrict__ done) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  T o[7], a[2], m[3] = {T(0), T(0), T(0)}, sd[3] = {T(0), T(0), T(0)}, e[3] = {T(0), T(0), T(0)}, no[7], r;
+  int d;
+  load_row<7>(obs, i, o);
+  load_row<2>(action, i, a);
+  if (mean != nullptr) load_row<3>(mean, i, m);
+  if (std != nullptr && eps != nullptr) {
+    load_row<3>(std, i, sd);
+    load_row<3>(eps, i, e);
+  }
+  unicycle_rollout_step<T>(dt, gx, gy, o, a, m, sd, e, no, r, d);
+  store_row<7>(next_obs, i, no);
+  reward[i] = r;
+  done[i] = (uint8_t)d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_cars_rollout_step(const T* __restrict__ obs, const T* __restrict__ action, const T* __restrict__ t,
+                    const T* __restrict__ mean, const T* __restrict__ std, const T* __restrict__ eps, int64_t n, T dt,
+                    T kp, T kb, int max_steps, T* __restrict__ next_obs, T* __restrict__ reward,
+                    uint8_t* __restrict__ done, T* __restrict__ next_t) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  T o[10], m[10], sd[10], e[10], no[10], r, nt;
+  int d;
+  load_row<10>(obs, i, o);
+#pragma unroll
+  for (int j = 0; j < 10; ++j) m[j] = sd[j] = e[j] = T(0);
+  if (mean != nullptr) load_row<10>(mean, i, m);
+  if (std != nullptr && eps != nullptr) {
+    load_row<10>(std, i, sd);
+    load_row<10>(eps, i, e);
+  }
+  cars_rollout_step<T>(dt, kp, kb, max_steps, o, action[i], t[i], m, sd, e, no, r, d, nt);
+  store_row<10>(next_obs, i, no);
+  reward[i] = r;
+  done[i] = (uint8_t)d;
+  next_t[i] = nt;
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // generic QP (cbf_layer / solve_qp API), float64
 // ------------------------------------------------------------------------------------------------------------
 template <int NZ, int M>
@@ -539,6 +589,29 @@ int rcbf_qp_solve_bwd(const double* Q, const double* G, const double* x, const d
 
 RCBF_ENV_FUNCS(f32, float)
 RCBF_ENV_FUNCS(f64, double)
+
+#define RCBF_ROLLOUT_FUNCS(SUF, T)                                                                                      \
+  int rcbf_unicycle_rollout_step_##SUF(const T* obs, const T* action, const T* mean, const T* std, const T* eps,       \
+                                       int64_t n, double dt, double goal_x, double goal_y, T* next_obs, T* reward,     \
+                                       uint8_t* done, void* stream) {                                                  \
+    if (n <= 0) return 0;                                                                                               \
+    k_unicycle_rollout_step<T><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(                                    \
+        obs, action, mean, std, eps, n, (T)dt, (T)goal_x, (T)goal_y, next_obs, reward, done);                          \
+    RCBF_LAUNCH_CHECK();                                                                                                \
+    return 0;                                                                                                           \
+  }                                                                                                                     \
+  int rcbf_cars_rollout_step_##SUF(const T* obs, const T* action, const T* t, const T* mean, const T* std,             \
+                                   const T* eps, int64_t n, double dt, double kp, double k_brake, int max_steps,       \
+                                   T* next_obs, T* reward, uint8_t* done, T* next_t, void* stream) {                   \
+    if (n <= 0) return 0;                                                                                               \
+    k_cars_rollout_step<T><<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(                                        \
+        obs, action, t, mean, std, eps, n, (T)dt, (T)kp, (T)k_brake, max_steps, next_obs, reward, done, next_t);       \
+    RCBF_LAUNCH_CHECK();                                                                                                \
+    return 0;                                                                                                           \
+  }
+
+RCBF_ROLLOUT_FUNCS(f32, float)
+RCBF_ROLLOUT_FUNCS(f64, double)
 
 int rcbf_unicycle_safe_step(float* state4, int32_t* step, const float* action_rl, const float* mean, const float* sigma,
                             int64_t n, const rcbf_unicycle_params* p, const rcbf_unicycle_env_params* e,

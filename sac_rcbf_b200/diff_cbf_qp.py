@@ -151,24 +151,31 @@ class CBFQPLayer:
             raise ValueError("solver must be 'presolve' or 'pdipm', got %r" % (self.solver,))
         return 0 if self.solver == "presolve" else 1
 
+    def _bounds_host(self):
+        """Host copies of u_min / u_max, refreshed only when the tensors are replaced or written (no per-call sync)."""
+        tag = (self.u_min.data_ptr(), self.u_min._version, self.u_max.data_ptr(), self.u_max._version)
+        if getattr(self, "_bounds_tag", None) != tag:
+            self._bounds_np = (self.u_min.detach().cpu().numpy().copy(), self.u_max.detach().cpu().numpy().copy())
+            self._bounds_tag = tag
+        return self._bounds_np
+
     def _params(self):
         """C parameter struct, rebuilt when a public attribute the reference reads at call time has changed."""
         env = self.env
+        lo, hi = self._bounds_host()
         if env.dynamics_mode == 'Unicycle':
-            key = ('U', self.solver, float(self.gamma_b), float(self.l_p), float(env.hazards_radius),
-                   np.asarray(env.hazards_locations, np.float64).tobytes(),
-                   self.u_min.cpu().numpy().tobytes(), self.u_max.cpu().numpy().tobytes())
+            hz = env.hazards_locations
+            key = ('U', self.solver, float(self.gamma_b), float(self.l_p), float(env.hazards_radius), id(hz),
+                   hz.tobytes() if isinstance(hz, np.ndarray) else None, self._bounds_tag)
             if self._params_cache is None or self._params_cache[0] != key:
-                p = _params.unicycle_params(env.hazards_locations, env.hazards_radius, float(self.gamma_b),
-                                            float(self.l_p), self.u_min.cpu().numpy(), self.u_max.cpu().numpy(),
+                p = _params.unicycle_params(hz, env.hazards_radius, float(self.gamma_b), float(self.l_p), lo, hi,
                                             solver_mode=self._solver_mode())
                 self._params_cache = (key, p)
         else:
-            key = ('C', self.solver, float(self.gamma_b), float(env.kp), float(env.k_brake), self.u_min.cpu().numpy().tobytes(),
-                   self.u_max.cpu().numpy().tobytes())
+            key = ('C', self.solver, float(self.gamma_b), float(env.kp), float(env.k_brake), self._bounds_tag)
             if self._params_cache is None or self._params_cache[0] != key:
-                p = _params.cars_params(float(self.gamma_b), float(env.kp), float(env.k_brake),
-                                        float(self.u_min[0]), float(self.u_max[0]), solver_mode=self._solver_mode())
+                p = _params.cars_params(float(self.gamma_b), float(env.kp), float(env.k_brake), float(lo[0]),
+                                        float(hi[0]), solver_mode=self._solver_mode())
                 self._params_cache = (key, p)
         return self._params_cache[1]
 

@@ -130,3 +130,90 @@ def test_generate_model_rollouts_contract(S, env_name):
         reward = -5.0 * np.abs(action_batch_.squeeze() ** 2) / env.max_episode_steps
         done = nxt_t >= env.max_episode_steps * env.dt
         assert reward.shape == (B,) and done.shape == (B,)
+
+
+# ----------------------------------------------------------------------------------------------------- next rows (8f)
+def test_rollout_transition_vs_golden_and_oracle(S, golden):
+    """the fused rollout-transition kernel vs the reference's own generate_model_rollouts output
+    (float64 host path) and vs the oracle at float32 on the device."""
+    g = golden("model_rollouts.npz")
+    for env_name, k in (("Unicycle", "unicycle"), ("SimulatedCars", "simulatedcars")):
+        args = _args(); args.env_name = env_name
+        env = S.build_env(args)
+        dm = S.DynamicsModel(env, args)
+        nobs, rew, done, nt = S.rollout_transition(env, dm, g[k + "_obs"], g[k + "_action"], g[k + "_t"], g[k + "_eps"])
+        assert isinstance(nobs, np.ndarray) and nobs.dtype == np.float64
+        np.testing.assert_allclose(nobs, g[k + "_next_obs"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(rew, g[k + "_reward"], rtol=1e-12, atol=1e-12)
+        np.testing.assert_array_equal(~done, g[k + "_mask"].astype(bool))
+        np.testing.assert_allclose(nt, g[k + "_next_t"], atol=1e-14)
+        # float32, device resident, 200k instances vs the oracle
+        B = 200000
+        if env_name == "Unicycle":
+            st, ac, _, _ = O.synth_unicycle(B, seed=6); obs = O.unicycle_obs(st.astype(np.float64)); t = np.zeros(B)
+        else:
+            st, ac, _, _, t = O.synth_cars(B, seed=6); obs = O.cars_obs(st.astype(np.float64)); t = t.astype(np.float64)
+        eps = np.random.default_rng(2).normal(size=(B, dm.n_s))
+        ro, rr, rd, rt = O.rollout_step(env_name, obs, ac.astype(np.float64), t, eps)
+        dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().cuda()  # noqa: E731
+        o32, r32, d32, t32 = S.rollout_transition(env, dm, dev(obs), dev(ac), dev(t), dev(eps))
+        assert o32.is_cuda and o32.dtype == torch.float32
+        keep = np.ones(B, bool) if env_name == "Unicycle" else O.cars_threshold_margin(st) > 1e-3
+        err = np.abs(o32.cpu().numpy() - ro) / np.maximum(np.abs(ro), 1.0)
+        if env_name == "Unicycle":      # compass ~ 1/dist conditioning, like the env observation
+            dist = -np.log(ro[:, 6])
+            err[:, 4:6] *= np.minimum(dist, 1.0)[:, None]
+        assert err[keep].max() < 3e-6, err[keep].max()
+        assert np.abs(r32.cpu().numpy() - rr)[keep].max() < 3e-6
+        near = np.abs(-np.log(np.maximum(ro[:, 6], 1e-30)) - 0.3) < 1e-5 if env_name == "Unicycle" else np.zeros(B, bool)
+        assert ((d32.cpu().numpy() == rd) | near).all()
+
+
+def test_generate_model_rollouts_host_and_device_memories(S):
+    """Same call as main.py:53-57, once with a host-side reference-style memory and once with DeviceReplayMemory."""
+    args = _args(); args.env_name = "Unicycle"
+    env = S.build_env(args)
+    agent = _Agent(env, args, S)
+    dm = S.DynamicsModel(env, args)
+    B = 25
+    st, _, _, _ = O.synth_unicycle(200, seed=33)
+    obs = O.unicycle_obs(st.astype(np.float64))
+
+    class HostMem:                               # rcbf_sac/replay_memory.py shape of things
+        def __init__(self):
+            self.rows = []
+
+        def sample(self, batch_size):
+            idx = np.arange(batch_size)
+            return obs[idx], None, None, None, None, np.zeros(batch_size), None
+
+        def batch_push(self, s, a, r, s2, m, t, t2):
+            for i in range(s.shape[0]):
+                self.rows.append((s[i], a[i], r[i], s2[i], m[i], t[i], t2[i]))
+
+        def __len__(self):
+            return len(self.rows)
+
+    np.random.seed(3)
+    mm = S.generate_model_rollouts(env, HostMem(), HostMem(), agent, dm, k_horizon=2, batch_size=B, warmup=True)
+    assert B <= len(mm) <= 2 * B
+    s, a, r, s2, m, t, t2 = mm.rows[0]
+    assert s.shape == (7,) and a.shape == (2,) and s2.shape == (7,) and abs(t2 - t - env.dt) < 1e-12
+    # device memories
+    mem = S.DeviceReplayMemory(1000, seed=0, obs_dim=7, action_dim=2)
+    x = torch.from_numpy(obs).float().cuda()
+    mem.batch_push(x, torch.zeros(200, 2), torch.zeros(200), x, torch.ones(200), torch.zeros(200), torch.zeros(200))
+    mem_model = S.DeviceReplayMemory(1000, seed=1, obs_dim=7, action_dim=2)
+
+    class DevAgent(_Agent):
+        def select_action(self, state, dynamics_model, evaluate=False, warmup=False):
+            if torch.is_tensor(state):
+                action = 2 * torch.rand((state.shape[0], 2), device=state.device) - 1
+                return self.get_safe_action(state, action, dynamics_model)
+            return super().select_action(state, dynamics_model, evaluate, warmup)
+
+    out = S.generate_model_rollouts(env, mem_model, mem, DevAgent(env, args, S), dm, k_horizon=1, batch_size=B)
+    assert out is mem_model and len(mem_model) == B
+    s, a, r, s2, m, t, t2 = mem_model.sample(B)
+    assert s.is_cuda and s2.shape == (B, 7) and torch.isfinite(s2).all() and torch.isfinite(r).all()
+    assert torch.allclose(t2, t + env.dt)

@@ -202,3 +202,18 @@ def test_oracle_vs_live_reference_envs():
         np.testing.assert_allclose(out["obs"][0], o, atol=1e-13)
         assert abs(out["reward"][0] - rew) < 1e-13
         st, step, last = out["state"], out["episode_step"], out["last_goal_dist"]
+
+
+def test_rollout_step_vs_golden(golden):
+    """oracle restatement of generate_model_rollouts' transition vs what the reference's own function pushed."""
+    g = golden("model_rollouts.npz")
+    for mode, k in (("Unicycle", "unicycle"), ("SimulatedCars", "simulatedcars")):
+        nobs, rew, done, nt = O.rollout_step(mode, g[k + "_obs"], g[k + "_action"], g[k + "_t"], g[k + "_eps"])
+        np.testing.assert_allclose(nobs, g[k + "_next_obs"], rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(rew, g[k + "_reward"], rtol=1e-13, atol=1e-13)
+        np.testing.assert_array_equal(~done, g[k + "_mask"].astype(bool))
+        np.testing.assert_allclose(nt, g[k + "_next_t"], rtol=0, atol=1e-15)
+        assert (~g[k + "_mask"].astype(bool)).sum() >= 2          # the fixture exercises done
+    # the reference's double reward_goal (generate_rollouts.py:50,53)
+    d = ~g["unicycle_mask"].astype(bool)
+    assert (g["unicycle_reward"][d] > 1.9).all()
