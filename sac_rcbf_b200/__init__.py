@@ -31,6 +31,6 @@ def __getattr__(name):  # lazy: importing the package must work on a box without
         from . import generate_rollouts
         return getattr(generate_rollouts, name)
     if name == "build_env":
-        from .build_env import build_env
+        from ._build_env import build_env
         return build_env
     raise AttributeError(name)

@@ -36,6 +36,8 @@ class DeviceReplayMemory:
             return
         if n > self.capacity:  # only the newest `capacity` items survive, exactly like pushing one by one
             sl = slice(n - self.capacity, n)
+            self.position = (self.position + n - self.capacity) % self.capacity
+            self.size = self.capacity
             return self.batch_push(state_batch[sl], action_batch[sl], reward_batch[sl], next_state_batch[sl],
                                    mask_batch[sl], None if t_batch is None else t_batch[sl],
                                    None if next_t_batch is None else next_t_batch[sl])
