@@ -740,10 +740,9 @@ RCBF_HD void sincos_t(float x, float* sn, float* cs) {
 // The assembly mirrors the reference's float32 operation ORDER (one rounding per torch op, no FMA contraction, the
 // k-ordered accumulation of torch.bmm's small-matrix path) so that the QP data agree with the reference's to the
 // last bit up to the ulp of cos/sin: near-degenerate instances amplify 1e-7 data noise into >1e-4 action noise.
-RCBF_HD void assemble_unicycle(const UnicycleParams& p, const float st[3], const float u[2], const float mu[3],
-                               const float sg[3], UniRaw& o) {
-  float s, c;
-  sincos_t(st[2], &s, &c);                                 // :211-212
+RCBF_HD void assemble_unicycle_sc(const UnicycleParams& p, const float st[3], float s, float c, const float u[2],
+                                  const float mu[3], const float sg[3], UniRaw& o) {
+  // s, c = sin / cos of st[2]                              // :211-212
   const float lp = p.l_p;
   const float px = add_rn(st[0], mul_rn(lp, c));           // :216
   const float py = add_rn(st[1], mul_rn(lp, s));           // :217
@@ -782,6 +781,13 @@ RCBF_HD void assemble_unicycle(const UnicycleParams& p, const float st[3], const
     o.h[r] = sub_rn(p.u_max[cc], u[cc]);
     o.h[r + 1] = add_rn(-p.u_min[cc], u[cc]);
   }
+}
+
+RCBF_HD void assemble_unicycle(const UnicycleParams& p, const float st[3], const float u[2], const float mu[3],
+                               const float sg[3], UniRaw& o) {
+  float s, c;
+  sincos_t(st[2], &s, &c);
+  assemble_unicycle_sc(p, st, s, c, u, mu, sg, o);
 }
 
 struct CarsRaw {

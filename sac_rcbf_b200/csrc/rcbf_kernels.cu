@@ -231,7 +231,13 @@ k_unicycle_env_step(T* __restrict__ state4, int32_t* __restrict__ step, const T*
   load_row<2>(action, i, a);
   int stp = step[i];
   UniEnvOut<T> o;
-  unicycle_env_step<T>(e, v, v[3], stp, a, o);
+  if constexpr (sizeof(T) == 4) {
+    float s0, c0;
+    sincos_t(v[2], &s0, &c0);
+    unicycle_env_step_sc(e, v, v[3], stp, a, s0, c0, o);
+  } else {
+    unicycle_env_step<T>(e, v, v[3], stp, a, o);
+  }
   store_row<7>(obs, i, o.obs);
   reward[i] = o.reward;
   done[i] = (uint8_t)o.done;

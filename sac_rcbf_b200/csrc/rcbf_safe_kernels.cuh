@@ -107,6 +107,7 @@ struct UniEnv {
   struct Inst {
     float v[4];  // x, y, theta, last_goal_dist (fused) / unused
     float u[2];
+    float sn, cs;  // sin / cos of theta: computed once, used by the assembly AND by env.step
     int stp;
   };
   __device__ static __forceinline__ void load_inst(const Args& a, int64_t i, Inst& in) {
@@ -120,6 +121,7 @@ struct UniEnv {
       in.stp = 0;
     }
     ld_row<2>(a.ac, i, in.u);
+    sincos_t(in.v[2], &in.sn, &in.cs);
   }
   // raw rows in NWR = 19 words: (G[i][0], G[i][1]) of the 5 CBF rows + the 9 h; the rest of G is constant
   static constexpr int NWR = 19;
@@ -169,6 +171,7 @@ struct UniEnv {
     }
     const float2 u2 = reinterpret_cast<const float2*>(sg_.ac)[lane];
     in.u[0] = u2.x; in.u[1] = u2.y;
+    sincos_t(in.v[2], &in.sn, &in.cs);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
       x.m[j] = sg_.mu[lane * 3 + j];
@@ -189,7 +192,7 @@ struct UniEnv {
   __device__ static __forceinline__ void assemble_raw(const Params& p, const Inst& in, const Aux& x, float w[NWR],
                                                       bool& triv, bool& nan) {
     UniRaw raw;
-    assemble_unicycle(p, in.v, in.u, x.m, x.g, raw);
+    assemble_unicycle_sc(p, in.v, in.sn, in.cs, in.u, x.m, x.g, raw);
     classify_raw<M>(raw.h, triv, nan);
 #pragma unroll
     for (int r = 0; r < kUniHaz; ++r) {
@@ -238,7 +241,7 @@ struct UniEnv {
     if (a.status != nullptr) a.status[i] = status;
     if (kFused) {
       UniEnvOut<float> o;
-      unicycle_env_step<float>(e, in.v, in.v[3], in.stp, us, o);
+      unicycle_env_step_sc(e, in.v, in.v[3], in.stp, us, in.sn, in.cs, o);
       st_row<7>(a.obs, i, o.obs);
       a.reward[i] = o.reward;
       a.done[i] = (uint8_t)o.done;
