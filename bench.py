@@ -185,6 +185,26 @@ def synth_inputs(n, device, seed, sets):
     return st.contiguous(), batches
 
 
+def ncu_traffic_bytes(n):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the hot kernel from the committed `ncu --set full` capture of this
+    same workload (profiles/r01_ncu_full_summary.txt, 4 Mi instances per launch); None for any other size."""
+    path = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.txt")
+    if n != (1 << 22) or not os.path.exists(path):
+        return None, None
+    rd = wr = None
+    for line in open(path):
+        if line.startswith("== ") and rd is not None:
+            break
+        f = line.split()
+        if len(f) >= 3 and f[0] == "dram__bytes_read.sum":
+            rd = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        if len(f) >= 3 and f[0] == "dram__bytes_write.sum":
+            wr = float(f[1]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+    if rd is None or wr is None:
+        return None, None
+    return rd + wr, "profiles/r01_ncu_full_summary.txt (k_safe<UniEnv<1>,0,1>, one launch)"
+
+
 def fma_probe_tflops(lib, _lib, device):
     sink = torch.zeros(4, device=device)
     blocks, threads, iters = 148 * 16, 256, 4096
@@ -413,6 +433,7 @@ def main():
         hbm_peak, which = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         fp32_peak = fma_probe_tflops(lib, _lib, device)
         gbs = UNI_BYTES_PER_STEP * n / (kernel_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic_bytes(n)
         # default solver mode: assembly + env step for everyone; setup + certificate per non-trivial instance; one
         # presolve round per counted round (counters[4]); fallback interior point: counters[5], [6]
         fb_frac, fb_iters = c[5] / total_steps, c[6] / total_steps
@@ -421,7 +442,8 @@ def main():
                           + fb_iters * (F_ITER_UNI + CERT_FLOPS_UNI))
         tfl = flops_per_step * n / (kernel_ms * 1e-3) / 1e12
         roofline = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
-                    "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)",
                     "kernel": "k_unicycle_safe_step", "kernel_ms": kernel_ms, "bytes_per_unit": UNI_BYTES_PER_STEP,
                     "fp32": {"achieved_tflops": tfl, "peak_tflops": fp32_peak, "frac": tfl / fp32_peak,
                              "peak_source": "rcbf_fp32_fma_probe measured in this run",

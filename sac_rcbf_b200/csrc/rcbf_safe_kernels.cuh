@@ -446,7 +446,7 @@ __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i
 // pass 1: persistent warps, warp-private compaction ring
 // ---------------------------------------------------------------------------------------------------------------
 #ifndef RCBF_MINB
-#define RCBF_MINB 3  // resident blocks per SM the presolve-mode kernel is compiled for (168 registers: no spills; A/B on B200: 3 > 4 > 2)
+#define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (128 registers; A/B on B200: 4 > 3 > 5)
 #endif
 constexpr int kWarps = 4;             // warps per block
 constexpr int kThreadsW = 32 * kWarps;
@@ -467,7 +467,8 @@ __device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t 
   }
 }
 
-template <class E, int kMode /* 0 presolve, 1 pdipm */, bool kBulk /* TMA bulk-copy input staging */>
+template <class E, int kMode /* 0 presolve, 1 pdipm */, bool kBulk /* TMA bulk-copy input staging */,
+          bool kSaved /* also write x / lam / slack / iters (backward pass, diagnostics) */>
 __global__ void __launch_bounds__(kThreadsW, kMode == 0 ? RCBF_MINB : 2)
 k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NWR = E::NWR;
@@ -480,7 +481,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
   const int64_t ntiles = (n + 31) >> 5;
   const int64_t nw = (int64_t)gridDim.x * kWarps;
   int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
-  const bool want_saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr);
+  constexpr bool want_saved = kSaved;  // separate instantiation: the dense multipliers / slacks cost ~40 registers
   int head = 0, qn = 0;
   int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
   int nbulk = 0;  // bulk-staged tiles consumed so far by this warp (buffer = nbulk & 1, mbarrier parity = (nbulk >> 1) & 1)
@@ -781,15 +782,18 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);
   // TMA bulk staging needs 16-byte aligned array bases (row spans of a 32-instance tile are then 16-byte multiples)
   const bool bulk = E::aligned(a) && n >= 32;
-  if (p.solver_mode == 0) {
-    if (bulk) k_safe<E, 0, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
-    else k_safe<E, 0, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
-    k_safe_fallback<E, 0><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
-  } else {
-    if (bulk) k_safe<E, 1, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
-    else k_safe<E, 1, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);
-    k_safe_fallback<E, 1><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);
-  }
+  const bool saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr);
+#define RCBF_LAUNCH_SAFE(MODE)                                                                       \
+  do {                                                                                               \
+    if (bulk && saved) k_safe<E, MODE, true, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);       \
+    else if (bulk) k_safe<E, MODE, true, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);          \
+    else if (saved) k_safe<E, MODE, false, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);         \
+    else k_safe<E, MODE, false, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);                   \
+    k_safe_fallback<E, MODE><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);                                  \
+  } while (0)
+  if (p.solver_mode == 0) RCBF_LAUNCH_SAFE(0);
+  else RCBF_LAUNCH_SAFE(1);
+#undef RCBF_LAUNCH_SAFE
   return (int)cudaGetLastError();
 }
 
