@@ -7,11 +7,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librcbf_b200.so")
-SOURCES = ["rcbf_kernels.cu"]
-HEADERS = ["rcbf_core.cuh", "rcbf_dynamics.cuh", "rcbf_backward.cuh", "rcbf_generic.cuh",
+SOURCES = ["rcbf_kernels.cu", "rcbf_safe_unicycle.cu", "rcbf_safe_cars.cu"]
+HEADERS = ["rcbf_core.cuh", "rcbf_dynamics.cuh", "rcbf_backward.cuh", "rcbf_generic.cuh", "rcbf_safe_kernels.cuh",
            os.path.join("..", "..", "include", "rcbf_b200.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-              "-shared"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def needs_build():
@@ -22,15 +21,29 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """Compile the translation units in parallel (nvcc -c), then link them into the shared library."""
     if not (force or needs_build()):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, f) for f in SOURCES] + ["-o", LIB]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    objs = []
+    for src, obj, pr in procs:
+        out, _ = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, out))
+        if verbose:
+            print(out)
+        objs.append(obj)
+    r = subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a"] + objs +
+                       ["-o", LIB], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout)
-    if verbose:
-        print(r.stdout)
+        raise RuntimeError("link failed:\n" + r.stdout)
     return LIB
 
 

@@ -12,7 +12,6 @@
 #include "rcbf_core.cuh"
 #include "rcbf_dynamics.cuh"
 #include "rcbf_generic.cuh"
-#include "rcbf_safe_kernels.cuh"
 
 using namespace rcbf;
 
@@ -475,23 +474,7 @@ int rcbf_cars_assemble(const float* state, const float* action, const float* sig
   return 0;
 }
 
-int rcbf_unicycle_safe_action(const float* state, const float* action, const float* mean, const float* sigma, int64_t n,
-                              const rcbf_unicycle_params* p, float* safe_action, float* x, float* lam, float* slack,
-                              int32_t* status, int32_t* iters, rcbf_counters_t* workspace, void* stream) {
-  UniArgs a{};
-  a.st = state; a.ac = action; a.mu = mean; a.sg = sigma;
-  a.out = safe_action; a.x = x; a.lam = lam; a.slack = slack; a.status = status; a.iters = iters;
-  return launch_safe<UniEnv<false>>(a, n, *p, rcbf_unicycle_env_params{}, workspace, (cudaStream_t)stream);
-}
 
-int rcbf_cars_safe_action(const float* state, const float* action, const float* sigma, int64_t n,
-                          const rcbf_cars_params* p, float* safe_action, float* x, float* lam, float* slack,
-                          int32_t* status, int32_t* iters, rcbf_counters_t* workspace, void* stream) {
-  CarsArgs a{};
-  a.st = state; a.ac = action; a.sg = sigma;
-  a.out = safe_action; a.x = x; a.lam = lam; a.slack = slack; a.status = status; a.iters = iters;
-  return launch_safe<CarsEnv<false>>(a, n, *p, rcbf_cars_env_params{}, workspace, (cudaStream_t)stream);
-}
 
 int rcbf_unicycle_safe_action_bwd(const float* state, const float* action, const float* mean, const float* sigma,
                                   const float* x, const float* lam, const float* slack, const float* grad_out, int64_t n,
@@ -619,27 +602,7 @@ RCBF_ENV_FUNCS(f64, double)
 RCBF_ROLLOUT_FUNCS(f32, float)
 RCBF_ROLLOUT_FUNCS(f64, double)
 
-int rcbf_unicycle_safe_step(float* state4, int32_t* step, const float* action_rl, const float* mean, const float* sigma,
-                            int64_t n, const rcbf_unicycle_params* p, const rcbf_unicycle_env_params* e,
-                            float* safe_action, float* obs, float* reward, uint8_t* done, float* cost, uint8_t* goal_met,
-                            int32_t* status, rcbf_counters_t* workspace, void* stream) {
-  UniArgs a{};
-  a.state4 = state4; a.step = step; a.ac = action_rl; a.mu = mean; a.sg = sigma;
-  a.out = safe_action; a.status = status;
-  a.obs = obs; a.reward = reward; a.done = done; a.cost = cost; a.goal_met = goal_met;
-  return launch_safe<UniEnv<true>>(a, n, *p, *e, workspace, (cudaStream_t)stream);
-}
 
-int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* action_rl, const float* sigma, int64_t n,
-                        const rcbf_cars_params* p, const rcbf_cars_env_params* e, float* safe_action, float* obs,
-                        float* reward, uint8_t* done, float* cost, int32_t* status, rcbf_counters_t* workspace,
-                        void* stream) {
-  CarsArgs a{};
-  a.state = state; a.t = t; a.step = step; a.ac = action_rl; a.sg = sigma;
-  a.out = safe_action; a.status = status;
-  a.obs = obs; a.reward = reward; a.done = done; a.cost = cost;
-  return launch_safe<CarsEnv<true>>(a, n, *p, *e, workspace, (cudaStream_t)stream);
-}
 
 int rcbf_fp32_fma_probe(float* sink, int blocks, int threads, int iters, void* stream) {
   k_fp32_fma_probe<<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters);

@@ -1,0 +1,32 @@
+// rcbf_safe_cars.cu -- C ABI entry points of the hot kernels for SimulatedCars (own translation unit so the three .cu files of the
+// library compile in parallel; the kernels live in rcbf_safe_kernels.cuh).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rcbf_safe_kernels.cuh"
+
+using namespace rcbf;
+
+extern "C" {
+
+int rcbf_cars_safe_action(const float* state, const float* action, const float* sigma, int64_t n,
+                          const rcbf_cars_params* p, float* safe_action, float* x, float* lam, float* slack,
+                          int32_t* status, int32_t* iters, rcbf_counters_t* workspace, void* stream) {
+  CarsArgs a{};
+  a.st = state; a.ac = action; a.sg = sigma;
+  a.out = safe_action; a.x = x; a.lam = lam; a.slack = slack; a.status = status; a.iters = iters;
+  return launch_safe<CarsEnv<false>>(a, n, *p, rcbf_cars_env_params{}, workspace, (cudaStream_t)stream);
+}
+
+int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* action_rl, const float* sigma, int64_t n,
+                        const rcbf_cars_params* p, const rcbf_cars_env_params* e, float* safe_action, float* obs,
+                        float* reward, uint8_t* done, float* cost, int32_t* status, rcbf_counters_t* workspace,
+                        void* stream) {
+  CarsArgs a{};
+  a.state = state; a.t = t; a.step = step; a.ac = action_rl; a.sg = sigma;
+  a.out = safe_action; a.status = status;
+  a.obs = obs; a.reward = reward; a.done = done; a.cost = cost;
+  return launch_safe<CarsEnv<true>>(a, n, *p, *e, workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"
