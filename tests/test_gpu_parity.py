@@ -219,6 +219,38 @@ def test_one_nan_instance_in_a_large_batch_raises_and_is_flagged(uni):
     assert torch.isnan(out[54321]).all() and not torch.isnan(out).sum().item() > 2
 
 
+@pytest.mark.parametrize("mode,gamma_b,l_p", [("Unicycle", 100.0, 0.03), ("Unicycle", 5.0, 0.1), ("SimulatedCars", 100.0, 0.03),
+                                              ("SimulatedCars", 3.0, 0.03)])
+def test_other_layer_parameters_vs_oracle(S, mode, gamma_b, l_p):
+    """The layer's constructor defaults (gamma_b=100, diff_cbf_qp.py:12) and other gamma_b / l_p / hazard layouts /
+    actuator bounds, not only the README's gamma_b=20."""
+    import types as _t
+    if mode == "Unicycle":
+        env = S.UnicycleEnv()
+        env.hazards_locations = np.array([[0.3, -0.2], [-1.2, 1.4], [-1.7, -0.9], [1.1, -1.6], [2.0, 0.7]])
+        env.hazards_radius = 0.45
+        env.safe_action_space = _t.SimpleNamespace(low=np.array([-1.5, -3.0], np.float32), high=np.array([2.0, 3.0], np.float32))
+        st, ac, mu, sg = O.synth_unicycle(20000, seed=17)
+        kw = dict(gamma_b=gamma_b, l_p=l_p, hazards=env.hazards_locations, hazards_radius=0.45,
+                  u_min=np.array([-1.5, -3.0]), u_max=np.array([2.0, 3.0]))
+    else:
+        env = S.SimulatedCarsEnv()
+        env.kp, env.k_brake = 3.0, 15.0
+        env.safe_action_space = _t.SimpleNamespace(low=np.array([-6.0], np.float32), high=np.array([8.0], np.float32))
+        st, ac, mu, sg, _ = O.synth_cars(20000, seed=17)
+        kw = dict(gamma_b=gamma_b, kp=3.0, k_brake=15.0, u_min=np.array([-6.0]), u_max=np.array([8.0]))
+    layer = S.CBFQPLayer(env, _args(), gamma_b=gamma_b, k_d=1.5, l_p=l_p)
+    out = layer.get_safe_action(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg)).cpu().numpy()
+    assert layer.solver_stats()["uncertified"] == 0
+    fe = O.safe_action(mode, tt(st), tt(ac), tt(mu), tt(sg), solver="exact", **kw).numpy()
+    f64 = O.safe_action(mode, tt(st), tt(ac), tt(mu), tt(sg), solver="exact", assembly_dtype=torch.float64, **kw).numpy()
+    ok = np.abs(fe - f64).max(1) <= 2e-5
+    if mode == "SimulatedCars":
+        ok &= O.cars_threshold_margin(st) > 1e-4
+    assert ok.mean() > 0.995
+    assert np.abs(out - fe)[ok].max() < ACT_TOL
+
+
 def test_trivial_instances_pass_through(uni):
     env, layer = uni
     B = 4096
