@@ -267,6 +267,18 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     ms = _time_calls(lambda: envc.safe_step(layc, acc, sgc), 5, device)
     out["cars_safe_step"] = {"value": nc / (ms * 1e-3), "unit": "env-steps/s", "instances": nc, "ms": ms,
                              "bytes_per_unit": 40 + 4 + 4 + 4 + 40 + 40 + 4 + 4 + 40 + 4 + 1 + 4 + 4}
+    # (b2) config 3 at scale: differentiable path, forward with saved tensors + implicit-KKT backward kernel
+    go = torch.ones_like(u)
+    saved = {}
+
+    def fwd_saved():
+        saved["t"] = layer._forward_raw(st, u, mu, sg, save=True)
+
+    ms_f = _time_calls(fwd_saved, 5, device)
+    out_s, x_s, lam_s, slack_s = saved["t"]
+    ms_b = _time_calls(lambda: layer._backward_raw(st, u, mu, sg, x_s, lam_s, slack_s, go), 5, device)
+    out["qp_fwd_bwd_unicycle"] = {"value": n / ((ms_f + ms_b) * 1e-3), "unit": "QP fwd+bwd/s", "instances": n,
+                                  "fwd_saved_ms": ms_f, "bwd_ms": ms_b}
     # (c) config 2/3 shapes: B=512 latency of the drop-in calls (launch-bound)
     b = 512
     s5, a5, m5, g5 = st[:b].clone(), u[:b].clone(), mu[:b].clone(), sg[:b].clone()

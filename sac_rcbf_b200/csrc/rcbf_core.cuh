@@ -449,6 +449,240 @@ template <> struct LnpTol<double> {
   static constexpr double kResidTol = 1e-11;
 };
 
+// ---- the interior point as a resumable state machine: ipm_init once, then ipm_step until it returns a final
+// status.  (The persistent "pdipm" kernel refills a lane with a new problem as soon as its QP is done, so the
+// iteration cannot be a closed loop.)
+constexpr int IPM_CONTINUE = -1;
+
+template <typename T, int NZ, int M>
+struct IpmState {
+  T y[NZ], s[M], z[M];
+  T best_res;
+  T by[NZ], bs[M], bz[M];  // best iterate by residual (only maintained when kTrackBest)
+  uint32_t last_mask;
+  int it;
+};
+
+template <typename T, typename C, int NZ, int M>
+RCBF_HD int ipm_finish_best(const IpmState<T, NZ, M>& st, LnpSolution<C, NZ, M>& out, int status) {
+  // not certified: hand back the best iterate by residual (what qpth returns)
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) out.y[j] = C(st.by[j]);
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    out.lam[i] = C(st.bz[i]);
+    out.s[i] = C(st.bs[i]);
+  }
+  out.status = (st.best_res < T(1e30)) ? status : RCBF_NAN;
+  out.iters = st.it;
+  return out.status;
+}
+
+template <typename T, typename Pat, int NZ, int M>
+RCBF_HD void ipm_init(const LnpProblem<T, NZ, M>& P, IpmState<T, NZ, M>& st) {
+  // initial point (qpth): (I + A'A) y = A'b ; s = b - A y ; z = -s ; shift both to >= 1 if needed
+  {
+    T S[NZ][NZ], r[NZ];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      RCBF_UNROLL
+      for (int k = 0; k <= j; ++k) {
+        T acc = (j == k) ? T(1) : T(0);
+        RCBF_UNROLL
+        for (int i = 0; i < M; ++i)
+          if (Pat::nz(i, j) && Pat::nz(i, k)) acc = t_fma(P.A[i][j], P.A[i][k], acc);
+        S[j][k] = acc;
+      }
+      T acc = T(0);
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i)
+        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], P.b[i], acc);
+      r[j] = acc;
+    }
+    Chol<T, NZ> ch;
+    ch.factor(S);
+    ch.solve(r, st.y);
+    T smin = T(1e30), zmin = T(1e30);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      T acc = P.b[i];
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], st.y[j], acc);
+      st.s[i] = acc;
+      st.z[i] = -acc;
+      smin = t_min(smin, st.s[i]);
+      zmin = t_min(zmin, st.z[i]);
+    }
+    const T sshift = smin < T(0) ? (T(1) - smin) : T(0);
+    const T zshift = zmin < T(0) ? (T(1) - zmin) : T(0);
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      st.s[i] += sshift;
+      st.z[i] += zshift;
+    }
+  }
+
+  st.best_res = T(1e30);
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) st.by[j] = st.y[j];
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    st.bs[i] = st.s[i];
+    st.bz[i] = st.z[i];
+  }
+  st.last_mask = 0xffffffffu;
+  st.it = 0;
+}
+
+// one Mehrotra predictor-corrector iteration (+ the certificate attempt).  Returns IPM_CONTINUE or the final status
+// (out is filled in the latter case).
+template <typename T, typename C, typename CP, typename Pat, int NZ, int M, bool kTrackBest>
+RCBF_HD int ipm_step(const LnpProblem<T, NZ, M>& P, const CP& cp, IpmState<T, NZ, M>& st, LnpSolution<C, NZ, M>& out,
+                     C tol_s, C tol_l) {
+  if (st.it >= LnpTol<T>::kMaxIter) return ipm_finish_best<T, C, NZ, M>(st, out, RCBF_MAXITER);
+  {
+  // residuals
+  T rx[NZ], rz[M];
+  T mu = T(0), nrx = T(0), nrz = T(0);
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    T acc = st.y[j];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i)
+      if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], st.z[i], acc);
+    rx[j] = acc;
+    nrx = t_fma(acc, acc, nrx);
+  }
+  uint32_t mask = 0;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    T acc = st.s[i] - P.b[i];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], st.y[j], acc);
+    rz[i] = acc;
+    nrz = t_fma(acc, acc, nrz);
+    mu = t_fma(st.s[i], st.z[i], mu);
+    mask |= (st.z[i] > st.s[i]) ? (1u << i) : 0u;
+  }
+  const T res = t_sqrt(nrx) + t_sqrt(nrz) + mu;  // qpth's resid: |rx| + |rz| + m*mu
+  if (!(res == res)) return ipm_finish_best<T, C, NZ, M>(st, out, RCBF_MAXITER);  // overflow / breakdown
+  if (kTrackBest && res < st.best_res) {
+    st.best_res = res;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) st.by[j] = st.y[j];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      st.bs[i] = st.s[i];
+      st.bz[i] = st.z[i];
+    }
+  }
+  // certified early exit: try the predicted active set whenever it is a candidate
+  if (st.it >= LnpTol<T>::kFirstCert && (mask == st.last_mask || st.it >= LnpTol<T>::kAlwaysCert)) {
+    if (lnp_certify<C, CP, Pat, NZ, M>(cp, mask, tol_s, tol_l, out.y, out.lam, out.s)) {
+      out.status = RCBF_OK_CERTIFIED;
+      out.iters = st.it;
+      return RCBF_OK_CERTIFIED;
+    }
+  }
+  st.last_mask = mask;
+  if (res < LnpTol<T>::kResidTol) return ipm_finish_best<T, C, NZ, M>(st, out, RCBF_OK_IPM);
+  mu *= T(1.0 / M);
+
+  // scaling, normal matrix S = I + A' D A
+  T w[M], d[M];
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    w[i] = t_rcp_fast(st.s[i] * st.z[i]);   // 1/(s z): 1/s = w z, 1/z = w s  (one reciprocal per row)
+    d[i] = st.z[i] * st.z[i] * w[i];
+  }
+  T S[NZ][NZ];
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    RCBF_UNROLL
+    for (int k = 0; k <= j; ++k) {
+      T acc = (j == k) ? T(1) : T(0);
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i)
+        if (Pat::nz(i, j) && Pat::nz(i, k)) acc = t_fma(P.A[i][j] * d[i], P.A[i][k], acc);
+      S[j][k] = acc;
+    }
+  }
+  Chol<T, NZ> ch;
+  ch.factor(S);
+
+  // affine direction: S dy = -rx + A'(z - d rz)
+  T r[NZ], dy[NZ], ds[M], dz[M];
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    T acc = -rx[j];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i)
+      if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], t_fma(-d[i], rz[i], st.z[i]), acc);
+    r[j] = acc;
+  }
+  ch.solve(r, dy);
+  T rho = T(0);
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    T acc = -rz[i];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], dy[j], acc);
+    ds[i] = acc;
+    dz[i] = t_fma(-d[i], acc, -st.z[i]);
+    rho = t_max(rho, -ds[i] * (w[i] * st.z[i]));
+    rho = t_max(rho, -dz[i] * (w[i] * st.s[i]));
+  }
+  T alpha = rho > T(1) ? T(1) / rho : T(1);
+  T t3 = T(0), t4 = T(0);
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    t3 = t_fma(t_fma(alpha, ds[i], st.s[i]), t_fma(alpha, dz[i], st.z[i]), t3);
+    t4 = t_fma(st.s[i], st.z[i], t4);
+  }
+  T sig = t3 / t4;
+  sig = sig * sig * sig;
+  const T musig = mu * sig;
+  // corrector folded into one combined solve: rs_tot = z + (-mu sig + ds_aff dz_aff)/s
+  T rsc[M];
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) rsc[i] = (t_fma(ds[i], dz[i], -musig)) * (w[i] * st.z[i]);
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    T acc = r[j];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i)
+      if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], rsc[i], acc);
+    r[j] = acc;
+  }
+  ch.solve(r, dy);
+  rho = T(0);
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    T acc = -rz[i];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], dy[j], acc);
+    ds[i] = acc;
+    dz[i] = t_fma(-d[i], acc, -(st.z[i] + rsc[i]));
+    rho = t_max(rho, -ds[i] * (w[i] * st.z[i]));
+    rho = t_max(rho, -dz[i] * (w[i] * st.s[i]));
+  }
+  alpha = rho > T(0.999) ? T(0.999) / rho : T(1);
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) st.y[j] = t_fma(alpha, dy[j], st.y[j]);
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    st.s[i] = t_fma(alpha, ds[i], st.s[i]);
+    st.z[i] = t_fma(alpha, dz[i], st.z[i]);
+  }
+  }
+  st.it += 1;
+  return IPM_CONTINUE;
+}
+
 // --- primal-dual interior point (Mehrotra predictor-corrector) with certified early exit -------------------
 // T : precision of the iteration (float on the main path, double in the straggler pass)
 // C : precision of the certificate (double: ~100 DFMA, B200 runs FP64 at 1:2)
@@ -479,213 +713,10 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
     }
   }
 
-  T y[NZ], s[M], z[M];
-  // 1. initial point (qpth): (I + A'A) y = A'b ; s = b - A y ; z = -s ; shift both to >= 1 if needed
-  {
-    T S[NZ][NZ], r[NZ];
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) {
-      RCBF_UNROLL
-      for (int k = 0; k <= j; ++k) {
-        T acc = (j == k) ? T(1) : T(0);
-        RCBF_UNROLL
-        for (int i = 0; i < M; ++i)
-          if (Pat::nz(i, j) && Pat::nz(i, k)) acc = t_fma(P.A[i][j], P.A[i][k], acc);
-        S[j][k] = acc;
-      }
-      T acc = T(0);
-      RCBF_UNROLL
-      for (int i = 0; i < M; ++i)
-        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], P.b[i], acc);
-      r[j] = acc;
-    }
-    Chol<T, NZ> ch;
-    ch.factor(S);
-    ch.solve(r, y);
-    T smin = T(1e30), zmin = T(1e30);
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      T acc = P.b[i];
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j)
-        if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], y[j], acc);
-      s[i] = acc;
-      z[i] = -acc;
-      smin = t_min(smin, s[i]);
-      zmin = t_min(zmin, z[i]);
-    }
-    const T sshift = smin < T(0) ? (T(1) - smin) : T(0);
-    const T zshift = zmin < T(0) ? (T(1) - zmin) : T(0);
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      s[i] += sshift;
-      z[i] += zshift;
-    }
+  IpmState<T, NZ, M> st;
+  ipm_init<T, Pat, NZ, M>(P, st);
+  while (ipm_step<T, C, CP, Pat, NZ, M, true>(P, cp, st, out, tol_s, tol_l) == IPM_CONTINUE) {
   }
-
-  T best_res = T(1e30);
-  T by[NZ], bs[M], bz[M];
-  RCBF_UNROLL
-  for (int j = 0; j < NZ; ++j) by[j] = y[j];
-  RCBF_UNROLL
-  for (int i = 0; i < M; ++i) {
-    bs[i] = s[i];
-    bz[i] = z[i];
-  }
-  uint32_t last_mask = 0xffffffffu;
-  int status = RCBF_MAXITER;
-  int it = 0;
-  for (; it < LnpTol<T>::kMaxIter; ++it) {
-    // residuals
-    T rx[NZ], rz[M];
-    T mu = T(0), nrx = T(0), nrz = T(0);
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) {
-      T acc = y[j];
-      RCBF_UNROLL
-      for (int i = 0; i < M; ++i)
-        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], z[i], acc);
-      rx[j] = acc;
-      nrx = t_fma(acc, acc, nrx);
-    }
-    uint32_t mask = 0;
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      T acc = s[i] - P.b[i];
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j)
-        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], y[j], acc);
-      rz[i] = acc;
-      nrz = t_fma(acc, acc, nrz);
-      mu = t_fma(s[i], z[i], mu);
-      mask |= (z[i] > s[i]) ? (1u << i) : 0u;
-    }
-    const T res = t_sqrt(nrx) + t_sqrt(nrz) + mu;  // qpth's resid: |rx| + |rz| + m*mu
-    if (!(res == res)) break;  // overflow / breakdown: keep the best iterate so far
-    if (res < best_res) {
-      best_res = res;
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) by[j] = y[j];
-      RCBF_UNROLL
-      for (int i = 0; i < M; ++i) {
-        bs[i] = s[i];
-        bz[i] = z[i];
-      }
-    }
-    // certified early exit: try the predicted active set whenever it is a candidate
-    if (it >= LnpTol<T>::kFirstCert && (mask == last_mask || it >= LnpTol<T>::kAlwaysCert)) {
-      if (lnp_certify<C, CP, Pat, NZ, M>(cp, mask, tol_s, tol_l, out.y, out.lam, out.s)) {
-        out.status = RCBF_OK_CERTIFIED;
-        out.iters = it;
-        return;
-      }
-    }
-    last_mask = mask;
-    if (res < LnpTol<T>::kResidTol) {
-      status = RCBF_OK_IPM;
-      break;
-    }
-    mu *= T(1.0 / M);
-
-    // scaling, normal matrix S = I + A' D A
-    T w[M], d[M];
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      w[i] = t_rcp_fast(s[i] * z[i]);   // 1/(s z): 1/s = w z, 1/z = w s  (one reciprocal per row)
-      d[i] = z[i] * z[i] * w[i];
-    }
-    T S[NZ][NZ];
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) {
-      RCBF_UNROLL
-      for (int k = 0; k <= j; ++k) {
-        T acc = (j == k) ? T(1) : T(0);
-        RCBF_UNROLL
-        for (int i = 0; i < M; ++i)
-          if (Pat::nz(i, j) && Pat::nz(i, k)) acc = t_fma(P.A[i][j] * d[i], P.A[i][k], acc);
-        S[j][k] = acc;
-      }
-    }
-    Chol<T, NZ> ch;
-    ch.factor(S);
-
-    // affine direction: S dy = -rx + A'(z - d rz)
-    T r[NZ], dy[NZ], ds[M], dz[M];
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) {
-      T acc = -rx[j];
-      RCBF_UNROLL
-      for (int i = 0; i < M; ++i)
-        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], t_fma(-d[i], rz[i], z[i]), acc);
-      r[j] = acc;
-    }
-    ch.solve(r, dy);
-    T rho = T(0);
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      T acc = -rz[i];
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j)
-        if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], dy[j], acc);
-      ds[i] = acc;
-      dz[i] = t_fma(-d[i], acc, -z[i]);
-      rho = t_max(rho, -ds[i] * (w[i] * z[i]));
-      rho = t_max(rho, -dz[i] * (w[i] * s[i]));
-    }
-    T alpha = rho > T(1) ? T(1) / rho : T(1);
-    T t3 = T(0), t4 = T(0);
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      t3 = t_fma(t_fma(alpha, ds[i], s[i]), t_fma(alpha, dz[i], z[i]), t3);
-      t4 = t_fma(s[i], z[i], t4);
-    }
-    T sig = t3 / t4;
-    sig = sig * sig * sig;
-    const T musig = mu * sig;
-    // corrector folded into one combined solve: rs_tot = z + (-mu sig + ds_aff dz_aff)/s
-    T rsc[M];
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) rsc[i] = (t_fma(ds[i], dz[i], -musig)) * (w[i] * z[i]);
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) {
-      T acc = r[j];
-      RCBF_UNROLL
-      for (int i = 0; i < M; ++i)
-        if (Pat::nz(i, j)) acc = t_fma(P.A[i][j], rsc[i], acc);
-      r[j] = acc;
-    }
-    ch.solve(r, dy);
-    rho = T(0);
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      T acc = -rz[i];
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j)
-        if (Pat::nz(i, j)) acc = t_fma(-P.A[i][j], dy[j], acc);
-      ds[i] = acc;
-      dz[i] = t_fma(-d[i], acc, -(z[i] + rsc[i]));
-      rho = t_max(rho, -ds[i] * (w[i] * z[i]));
-      rho = t_max(rho, -dz[i] * (w[i] * s[i]));
-    }
-    alpha = rho > T(0.999) ? T(0.999) / rho : T(1);
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) y[j] = t_fma(alpha, dy[j], y[j]);
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      s[i] = t_fma(alpha, ds[i], s[i]);
-      z[i] = t_fma(alpha, dz[i], z[i]);
-    }
-  }
-  // not certified: hand back the best iterate by residual (what qpth returns)
-  RCBF_UNROLL
-  for (int j = 0; j < NZ; ++j) out.y[j] = C(by[j]);
-  RCBF_UNROLL
-  for (int i = 0; i < M; ++i) {
-    out.lam[i] = C(bz[i]);
-    out.s[i] = C(bs[i]);
-  }
-  out.status = (best_res < T(1e30)) ? status : RCBF_NAN;
-  out.iters = it;
 }
 
 // ------------------------------------------------------------------------------------------------

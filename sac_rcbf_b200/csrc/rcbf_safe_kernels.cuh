@@ -450,12 +450,19 @@ __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i
 #endif
 constexpr int kWarps = 4;             // warps per block
 constexpr int kThreadsW = 32 * kWarps;
-constexpr int kRing = 64;             // ring capacity per warp: at most 31 left over + 32 new
-
-template <class E>
-struct WarpRing {
+// Per-warp shared memory.  Problem ring: raw rows + instance index of the QPs waiting for a solve.  Finish ring:
+// (index, correction, status) of solved instances waiting for clamp / env.step.  Stage: two TMA landing buffers.
+template <class E, int kMode>
+struct WarpShared {
+  static constexpr int kRing = kMode == 0 ? 64 : 128;  // presolve: <= 31 left over + 32 new; pdipm: engine starts at 64
+  static constexpr int kFin = kMode == 0 ? 64 : 256;   // <= 31 left over + one solve phase's output
   float w[E::NWR][kRing];
   int idx[kRing];
+  float fx[E::NU][kFin];
+  int fidx[kFin];
+  int fst[kFin];
+  typename E::Stage stage[2];
+  uint64_t bar[2];
 };
 
 template <class E>
@@ -473,35 +480,35 @@ __global__ void __launch_bounds__(kThreadsW, kMode == 0 ? RCBF_MINB : 2)
 k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NWR = E::NWR;
   using Inst = typename E::Inst;
-  __shared__ WarpRing<E> s_ring[kWarps];
-  __shared__ typename E::Stage s_stage[kBulk ? kWarps : 1][2];
-  __shared__ uint64_t s_bar[kBulk ? kWarps : 1][2];
+  using WS = WarpShared<E, kMode>;
+  constexpr int kRing = WS::kRing, kFin = WS::kFin;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  WarpRing<E>& ring = s_ring[warp];
+  WS& sh = reinterpret_cast<WS*>(smem_raw)[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int64_t ntiles = (n + 31) >> 5;
   const int64_t nw = (int64_t)gridDim.x * kWarps;
   int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
-  constexpr bool want_saved = kSaved;  // separate instantiation: the dense multipliers / slacks cost ~40 registers
-  int head = 0, qn = 0;
+  int head = 0, qn = 0;     // problem ring
+  int fhead = 0, fn = 0;    // finish ring
   int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
   int nbulk = 0;  // bulk-staged tiles consumed so far by this warp (buffer = nbulk & 1, mbarrier parity = (nbulk >> 1) & 1)
-  if (kBulk) {
-    if (lane == 0) {
-      mbar_init(&s_bar[warp][0], 1);
-      mbar_init(&s_bar[warp][1], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    if (lane == 0 && ((tile << 5) + 32 <= n)) E::issue(a, tile, s_stage[warp][0], &s_bar[warp][0]);
-  }
-
-  // job B = the instance this lane solved in the PREVIOUS iteration's B-step; it is finished after the next A-step so
-  // that nothing but (index, correction, status) is live across the register-hungry solve
+  // presolve mode: job B = the instance this lane solved in the previous B-step, finished after the next A-step so
+  // that only (index, correction, status) is live across the register-hungry solve.  (pdipm mode: finish ring.)
   bool onB = false;
   int iB = 0, stB = RCBF_OK_CERTIFIED;
   float xsB[NU];
 #pragma unroll
   for (int c = 0; c < NU; ++c) xsB[c] = 0.f;
+  if (kBulk) {
+    if (lane == 0) {
+      mbar_init(&sh.bar[0], 1);
+      mbar_init(&sh.bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (lane == 0 && ((tile << 5) + 32 <= n)) E::issue(a, tile, sh.stage[0], &sh.bar[0]);
+  }
 
   for (;;) {
     const bool have_tile = tile < ntiles;
@@ -521,10 +528,10 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
         // this tile's inputs were bulk-copied into shared memory one iteration ago; wait, read, then put the NEXT
         // tile in flight into the other buffer (its last reader finished before the previous __syncwarp)
         const int b = nbulk & 1;
-        mbar_wait(&s_bar[warp][b], (nbulk >> 1) & 1);
-        E::read_stage(s_stage[warp][b], lane, inA, aux);
+        mbar_wait(&sh.bar[b], (nbulk >> 1) & 1);
+        E::read_stage(sh.stage[b], lane, inA, aux);
         __syncwarp();
-        if (lane == 0 && (((tile + nw) << 5) + 32 <= n)) E::issue(a, tile + nw, s_stage[warp][b ^ 1], &s_bar[warp][b ^ 1]);
+        if (lane == 0 && (((tile + nw) << 5) + 32 <= n)) E::issue(a, tile + nw, sh.stage[b ^ 1], &sh.bar[b ^ 1]);
         ++nbulk;
       } else {
         if (!kBulk && tile + nw < ntiles) {  // pull the NEXT tile's input lines towards L1 meanwhile
@@ -540,16 +547,16 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       const bool need = valid && !triv && !nan;
       const unsigned ballot = __ballot_sync(0xffffffffu, need);
       if (need) {
-        const int slot = (head + qn + __popc(ballot & ((1u << lane) - 1u))) & (kRing - 1);
+        const int slot = (head + qn + __popc(ballot & lt_mask)) & (kRing - 1);
 #pragma unroll
-        for (int k = 0; k < NWR; ++k) ring.w[k][slot] = w[k];
-        ring.idx[slot] = (int)iA;
+        for (int k = 0; k < NWR; ++k) sh.w[k][slot] = w[k];
+        sh.idx[slot] = (int)iA;
       }
       onA = valid && !need;
       stA = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
 #pragma unroll
       for (int c = 0; c < NU; ++c) xsA[c] = nan ? NAN : 0.f;
-      if (onA && want_saved) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
+      if (kSaved && onA) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
         Normalised<NZ, M> nrm;
         E::normalise_packed(w, p, nrm);
         NormSolution<NZ, M> sol;
@@ -563,53 +570,152 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
     }
     __syncwarp();
 
-    // ---- finish (clamp, env.step, outputs): ONE copy of the code, run for job A, then for last iteration's job B
+    // ---- finish (clamp, env.step, outputs): ONE copy of the code.  Pass 0 = job A; later passes = job B of the
+    // previous iteration (presolve mode) or full warps popped from the finish ring (pdipm mode)
 #pragma unroll 1
-    for (int j = 0; j < 2; ++j) {
-      const bool on = j ? onB : onA;
-      if (on) {
-        const int64_t i = j ? (int64_t)iB : iA;
-        Inst in;
-        if (j) E::load_inst(a, i, in);
-        else in = inA;
-        float xs[NU];
+    for (int j = 0;; ++j) {
+      bool on;
+      int64_t i;
+      Inst in;
+      float xs[NU];
+      int stv;
+      if (j == 0) {
+        on = onA;
+        i = iA;
+        in = inA;
 #pragma unroll
-        for (int c = 0; c < NU; ++c) xs[c] = j ? xsB[c] : xsA[c];
-        E::finish(a, p, e, i, in, xs, j ? stB : stA);
+        for (int c = 0; c < NU; ++c) xs[c] = xsA[c];
+        stv = stA;
+      } else if (kMode == 0) {
+        if (j > 1) break;
+        on = onB;
+        i = iB;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) xs[c] = xsB[c];
+        stv = stB;
+        if (on) E::load_inst(a, i, in);
+        onB = false;
+      } else {
+        if (fn == 0 || (fn < 32 && (have_tile || qn > 0))) break;
+        const int take = fn < 32 ? fn : 32;
+        on = lane < take;
+        const int fs = (fhead + lane) & (kFin - 1);
+        i = on ? sh.fidx[fs] : 0;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) xs[c] = sh.fx[c][fs];
+        stv = sh.fst[fs];
+        if (on) E::load_inst(a, i, in);
+        fhead = (fhead + take) & (kFin - 1);
+        fn -= take;
       }
-    }
-    onB = false;
-
-    // ---- B-step: a full warp of queued problems (or whatever is left once the tiles are exhausted)
-    const int take = (qn >= 32) ? 32 : (have_tile ? 0 : qn);
-    if (take > 0) {
-      if (lane < take) {
-        const int slot = (head + lane) & (kRing - 1);
-        float w[NWR];
-#pragma unroll
-        for (int k = 0; k < NWR; ++k) w[k] = ring.w[k][slot];
-        iB = ring.idx[slot];
-        Normalised<NZ, M> nrm;
-        E::normalise_packed(w, p, nrm);
-        NormSolution<NZ, M> sol;
-        solve_normalised_fast<typename E::Pat, NZ, M, kMode == 0>(nrm, p.p_diag, want_saved, sol);
-        if (sol.status == RCBF_PENDING) {
-          mark_pending<E>(a, iB, ws);
-          c_pend += 1;
-        } else {
-          onB = true;
-          stB = sol.status;
-#pragma unroll
-          for (int c = 0; c < NU; ++c) xsB[c] = (float)sol.x[c];
-          if (want_saved) write_saved<E>(a, iB, sol);
-          c_iters += sol.iters;
-        }
-      }
-      head = (head + take) & (kRing - 1);
-      qn -= take;
+      if (on) E::finish(a, p, e, i, in, xs, stv);
       __syncwarp();
     }
-    if (!have_tile && qn == 0 && !__any_sync(0xffffffffu, onB)) break;
+
+    if (kMode == 0) {
+      // ---- B-step: a full warp of queued problems (or whatever is left once the tiles are exhausted)
+      const int take = (qn >= 32) ? 32 : (have_tile ? 0 : qn);
+      if (take > 0) {
+        if (lane < take) {
+          const int slot = (head + lane) & (kRing - 1);
+          float w[NWR];
+#pragma unroll
+          for (int k = 0; k < NWR; ++k) w[k] = sh.w[k][slot];
+          iB = sh.idx[slot];
+          Normalised<NZ, M> nrm;
+          E::normalise_packed(w, p, nrm);
+          NormSolution<NZ, M> sol;
+          solve_normalised_fast<typename E::Pat, NZ, M, true>(nrm, p.p_diag, kSaved, sol);
+          if (sol.status == RCBF_PENDING) {
+            mark_pending<E>(a, iB, ws);
+            c_pend += 1;
+          } else {
+            onB = true;
+            stB = sol.status;
+#pragma unroll
+            for (int c = 0; c < NU; ++c) xsB[c] = (float)sol.x[c];
+            if (kSaved) write_saved<E>(a, iB, sol);
+            c_iters += sol.iters;
+          }
+        }
+        head = (head + take) & (kRing - 1);
+        qn -= take;
+        __syncwarp();
+      }
+    } else {
+      // ---- interior-point engine: every lane holds one QP; a lane whose QP is done (certified, or given up ->
+      // pending) immediately takes the next problem from the ring, so the warp stays full although the iteration
+      // counts differ widely (1..16, mean ~2).  Runs when >= 64 problems wait (or at the end) and drains the ring.
+      if (qn >= 64 || (!have_tile && qn > 0)) {
+        int remaining = qn;
+        bool active = false;
+        int my_idx = 0;
+        Normalised<NZ, M> nrm;
+        LnpProblem<float, NZ, M> Pf;
+        IpmState<float, NZ, M> st;
+        double pisd[NZ];
+        float pisf[NZ];
+        pis_of<NZ, M>(p.p_diag, pisd, pisf);
+        for (;;) {
+          const unsigned wb = __ballot_sync(0xffffffffu, !active);
+          const int rank = __popc(wb & lt_mask);
+          if (!active && rank < remaining) {
+            const int slot = (head + (qn - remaining) + rank) & (kRing - 1);
+            float w[NWR];
+#pragma unroll
+            for (int k = 0; k < NWR; ++k) w[k] = sh.w[k][slot];
+            my_idx = sh.idx[slot];
+            E::normalise_packed(w, p, nrm);
+            to_lnp<float, typename E::Pat, NZ, M>(nrm, pisf, Pf);
+            ipm_init<float, typename E::Pat, NZ, M>(Pf, st);
+            active = true;
+          }
+          remaining -= min(remaining, __popc(wb));
+          if (!__any_sync(0xffffffffu, active)) break;
+          int status = IPM_CONTINUE;
+          LnpSolution<double, NZ, M> lsol;
+          if (active) {
+            const NormCert<NZ, M> cp{nrm, pisd};
+            status = ipm_step<float, double, NormCert<NZ, M>, typename E::Pat, NZ, M, false>(Pf, cp, st, lsol, kTolSlack,
+                                                                                             kTolDual);
+          }
+          const bool fin = active && status != IPM_CONTINUE;
+          const bool ok = fin && status < RCBF_MAXITER;
+          if (fin && !ok) {
+            mark_pending<E>(a, my_idx, ws);
+            c_pend += 1;
+          }
+          const unsigned fb = __ballot_sync(0xffffffffu, ok);
+          if (ok) {
+            const int fs = (fhead + fn + __popc(fb & lt_mask)) & (kFin - 1);
+            NormSolution<NZ, M> sol;
+#pragma unroll
+            for (int j = 0; j < NZ; ++j) sol.x[j] = lsol.y[j] * pisd[j];
+#pragma unroll
+            for (int c = 0; c < NU; ++c) sh.fx[c][fs] = (float)sol.x[c];
+            sh.fidx[fs] = my_idx;
+            sh.fst[fs] = status;
+            if (kSaved) {
+#pragma unroll
+              for (int r = 0; r < M; ++r) {
+                sol.lam[r] = lsol.lam[r];
+                sol.s[r] = lsol.s[r];
+              }
+              sol.iters = lsol.iters;
+              write_saved<E>(a, my_idx, sol);
+            }
+            c_iters += lsol.iters;
+          }
+          fn += __popc(fb);
+          if (fin) active = false;
+        }
+        head = (head + qn) & (kRing - 1);
+        qn = 0;
+        __syncwarp();
+      }
+    }
+
+    if (!have_tile && qn == 0 && fn == 0 && !__any_sync(0xffffffffu, onB)) break;
   }
 
   if (ws != nullptr) {
@@ -783,17 +889,29 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   // TMA bulk staging needs 16-byte aligned array bases (row spans of a 32-instance tile are then 16-byte multiples)
   const bool bulk = E::aligned(a) && n >= 32;
   const bool saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr);
+#define RCBF_LAUNCH_ONE(MODE, BULK, SAVED)                                                           \
+  do {                                                                                               \
+    constexpr size_t smem = sizeof(WarpShared<E, MODE>) * kWarps;                                    \
+    static bool configured = false; /* > 48 KB of dynamic shared memory needs the opt-in, once */    \
+    if (!configured) {                                                                               \
+      cudaFuncSetAttribute(k_safe<E, MODE, BULK, SAVED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                           (int)smem);                                                               \
+      configured = true;                                                                             \
+    }                                                                                                \
+    k_safe<E, MODE, BULK, SAVED><<<grid, kThreadsW, smem, s>>>(a, n, p, e, ws);                      \
+  } while (0)
 #define RCBF_LAUNCH_SAFE(MODE)                                                                       \
   do {                                                                                               \
-    if (bulk && saved) k_safe<E, MODE, true, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);       \
-    else if (bulk) k_safe<E, MODE, true, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);          \
-    else if (saved) k_safe<E, MODE, false, true><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);         \
-    else k_safe<E, MODE, false, false><<<grid, kThreadsW, 0, s>>>(a, n, p, e, ws);                   \
+    if (bulk && saved) RCBF_LAUNCH_ONE(MODE, true, true);                                            \
+    else if (bulk) RCBF_LAUNCH_ONE(MODE, true, false);                                               \
+    else if (saved) RCBF_LAUNCH_ONE(MODE, false, true);                                              \
+    else RCBF_LAUNCH_ONE(MODE, false, false);                                                        \
     k_safe_fallback<E, MODE><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);                                  \
   } while (0)
   if (p.solver_mode == 0) RCBF_LAUNCH_SAFE(0);
   else RCBF_LAUNCH_SAFE(1);
 #undef RCBF_LAUNCH_SAFE
+#undef RCBF_LAUNCH_ONE
   return (int)cudaGetLastError();
 }
 
