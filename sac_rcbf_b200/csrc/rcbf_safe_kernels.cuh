@@ -892,11 +892,13 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
 #define RCBF_LAUNCH_ONE(MODE, BULK, SAVED)                                                           \
   do {                                                                                               \
     constexpr size_t smem = sizeof(WarpShared<E, MODE>) * kWarps;                                    \
-    static bool configured = false; /* > 48 KB of dynamic shared memory needs the opt-in, once */    \
-    if (!configured) {                                                                               \
+    static bool configured[64] = {}; /* > 48 KB of dynamic shared memory needs the opt-in, once per device */ \
+    int dev_ = 0;                                                                                    \
+    cudaGetDevice(&dev_);                                                                            \
+    if (!configured[dev_ & 63]) {                                                                    \
       cudaFuncSetAttribute(k_safe<E, MODE, BULK, SAVED>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                            (int)smem);                                                               \
-      configured = true;                                                                             \
+      configured[dev_ & 63] = true;                                                                  \
     }                                                                                                \
     k_safe<E, MODE, BULK, SAVED><<<grid, kThreadsW, smem, s>>>(a, n, p, e, ws);                      \
   } while (0)

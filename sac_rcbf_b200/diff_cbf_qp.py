@@ -164,9 +164,9 @@ class CBFQPLayer:
         env = self.env
         lo, hi = self._bounds_host()
         if env.dynamics_mode == 'Unicycle':
-            hz = env.hazards_locations
-            key = ('U', self.solver, float(self.gamma_b), float(self.l_p), float(env.hazards_radius), id(hz),
-                   hz.tobytes() if isinstance(hz, np.ndarray) else None, self._bounds_tag)
+            hz = np.asarray(env.hazards_locations, np.float64)
+            key = ('U', self.solver, float(self.gamma_b), float(self.l_p), float(env.hazards_radius), hz.tobytes(),
+                   self._bounds_tag)
             if self._params_cache is None or self._params_cache[0] != key:
                 p = _params.unicycle_params(hz, env.hazards_radius, float(self.gamma_b), float(self.l_p), lo, hi,
                                             solver_mode=self._solver_mode())
