@@ -20,12 +20,6 @@ namespace {
 constexpr int kThreads = 128;
 
 inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
-// the fallback pass is a grid-stride scan: cap the grid at a few waves of the 148 SMs
-inline int grid_scan(int64_t n) {
-  const int64_t g = (n + kThreads - 1) / kThreads;
-  return (int)(g < 148 * 16 ? g : 148 * 16);
-}
-
 #define RCBF_LAUNCH_CHECK()                 \
   do {                                      \
     cudaError_t e_ = cudaGetLastError();    \
@@ -73,14 +67,6 @@ __device__ __forceinline__ void accumulate_counters(rcbf_counters_t* counters, b
   }
 }
 
-// per-thread variant for the fallback pass (a handful of instances per launch)
-__device__ __forceinline__ void accumulate_counters_thread(rcbf_counters_t* counters, int status, int iters) {
-  if (counters == nullptr) return;
-  if (status == RCBF_NAN) atomicAdd(&counters[0], 1ULL);
-  if (status == RCBF_MAXITER) atomicAdd(&counters[1], 1ULL);
-  if (iters >= 100) atomicAdd(&counters[2], 1ULL);
-  atomicAdd(&counters[6], (unsigned long long)(iters >= 100 ? iters - 100 : iters));
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // K2: constraint assembly (raw G, h of get_cbf_qp_constraints)

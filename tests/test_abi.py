@@ -56,6 +56,19 @@ def test_ctypes_structs_match_c_layout(tmp_path):
     assert got == want
 
 
+def test_header_is_plain_c_and_the_pure_c_driver_links(lib, tmp_path):
+    """include/rcbf_b200.h must compile as C (no C++/torch types) and every entry the C driver uses must resolve
+    against the built library (the driver itself runs in the GPU suite)."""
+    from sac_rcbf_b200 import build
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I",
+                           os.path.join(cuda, "include"), os.path.join(ROOT, "tests", "c_abi", "c_abi_smoke.c"), "-o",
+                           exe, "-L", os.path.dirname(build.LIB), "-lrcbf_b200", "-L", os.path.join(cuda, "lib64"),
+                           "-lcudart", "-lm"])
+    assert os.path.exists(exe)
+
+
 def test_params_mirror_reference_constants():
     from sac_rcbf_b200 import _params as P
     p = P.unicycle_params(gamma_b=20.0)
