@@ -394,41 +394,12 @@ def main():
     e2e = None
     extra = {}
     if True:
-        CH = 8
-        per = (n + CH - 1) // CH
+        CH = int(os.environ.get("RCBF_E2E_CHUNKS", "8"))
         h_in = [tuple(b.cpu().pin_memory() for b in batches[k]) for k in range(SETS)]
-        d_in = (torch.empty_like(batches[0][0]), torch.empty_like(batches[0][1]), torch.empty_like(batches[0][2]))
-        h_out = dict(u=torch.empty((n, 2)).pin_memory(), obs=torch.empty((n, 7)).pin_memory(),
-                     rew=torch.empty((n,)).pin_memory(), cost=torch.empty((n,)).pin_memory(),
-                     done=torch.empty((n,), dtype=torch.uint8).pin_memory())
-        streams = [torch.cuda.Stream(device) for _ in range(3)]
-        wss = [torch.zeros(32768, dtype=torch.int64, device=device) for _ in range(3)]   # one workspace per stream
-        p_layer, p_env = layer._params(), env._env_params()
+        h_out = env.safe_step_host(layer, *h_in[0], chunks=CH)          # allocates the pinned outputs once (+ warm-up)
 
         def e2e_step(k):
-            hi = h_in[k % SETS]
-            for cidx in range(CH):
-                lo, up = cidx * per, min(n, (cidx + 1) * per)
-                if lo >= up:
-                    break
-                s = streams[cidx % 3]
-                with torch.cuda.stream(s):
-                    for dst, src in zip(d_in, hi):
-                        dst[lo:up].copy_(src[lo:up], non_blocking=True)
-                    rc = lib.rcbf_unicycle_safe_step(
-                        _lib.ptr(env._state4[lo:up]), _lib.ptr(env._step[lo:up]), _lib.ptr(d_in[0][lo:up]),
-                        _lib.ptr(d_in[1][lo:up]), _lib.ptr(d_in[2][lo:up]), up - lo, p_layer, p_env,
-                        _lib.ptr(env._safe_action[lo:up]), _lib.ptr(env._obs[lo:up]), _lib.ptr(env._reward[lo:up]),
-                        _lib.ptr(env._done[lo:up]), _lib.ptr(env._cost[lo:up]), _lib.ptr(env._goal[lo:up]), None,
-                        _lib.ptr(wss[cidx % 3]), s.cuda_stream)
-                    assert rc == 0
-                    h_out["u"][lo:up].copy_(env._safe_action[lo:up], non_blocking=True)
-                    h_out["obs"][lo:up].copy_(env._obs[lo:up], non_blocking=True)
-                    h_out["rew"][lo:up].copy_(env._reward[lo:up], non_blocking=True)
-                    h_out["cost"][lo:up].copy_(env._cost[lo:up], non_blocking=True)
-                    h_out["done"][lo:up].copy_(env._done[lo:up], non_blocking=True)
-            for s in streams:
-                s.synchronize()
+            env.safe_step_host(layer, *h_in[k % SETS], out=h_out, chunks=CH)
 
         k_e2e = max(3, min(args.steps, 10))
         for k in range(3):
@@ -444,12 +415,13 @@ def main():
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         el = float(te.item())
         h2d = n * (8 + 12 + 12)
-        d2h = n * (8 + 28 + 4 + 4 + 1)
+        d2h = n * (8 + 28 + 4 + 4 + 1 + 1)
         e2e = {"value": float(n) * world * k_e2e / el, "unit": "env-steps/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": k_e2e, "chunks": CH,
-               "api": "UnicycleEnv.safe_step (rcbf_unicycle_safe_step) with pinned host u_rl/mean/sigma in and "
-                      "u_safe/obs/reward/cost/done out"}
-        assert float(h_out["rew"].abs().sum()) >= 0.0   # the result is read on the host
+               "api": "UnicycleEnv.safe_step_host -> rcbf_unicycle_safe_step_host: pinned HOST u_rl/mean/sigma in, "
+                      "HOST u_safe/obs/reward/done/cost/goal_met out, env state resident on the GPU; wall clock around "
+                      "the synchronous call"}
+        assert float(h_out["reward"].abs().sum()) >= 0.0   # the result is read on the host
 
     if rank == 0:
         peaks = {}

@@ -196,6 +196,18 @@ int rcbf_cars_safe_action_host(const float* state_host, const float* action_host
                                const rcbf_cars_params* p_host, float* safe_action_host, int32_t* n_failed_host,
                                int device, int chunks);
 
+/* fused step with HOST inputs/outputs: the env state (state4/state, t, step) stays on the DEVICE, the per-step inputs
+ * (u_rl, GP mean/std) come from host arrays and every per-step output goes back to host arrays.  Same pipeline. */
+int rcbf_unicycle_safe_step_host(float* state4, int32_t* step, const float* action_host, const float* mean_host,
+                                 const float* sigma_host, int64_t n, const rcbf_unicycle_params* p_host,
+                                 const rcbf_unicycle_env_params* e_host, float* safe_action_host, float* obs_host,
+                                 float* reward_host, uint8_t* done_host, float* cost_host, uint8_t* goal_met_host,
+                                 int32_t* n_failed_host, int device, int chunks);
+int rcbf_cars_safe_step_host(float* state, float* t, int32_t* step, const float* action_host, const float* sigma_host,
+                             int64_t n, const rcbf_cars_params* p_host, const rcbf_cars_env_params* e_host,
+                             float* safe_action_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                             float* cost_host, int32_t* n_failed_host, int device, int chunks);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------
  * FP32 FMA throughput probe: `iters` dependent-chain FMAs x 8 chains per thread; returns nothing, time it outside.
  * flops per launch = 2 * 8 * iters * blocks * threads. */

@@ -36,6 +36,11 @@ SIGNATURES = {
                                        C.POINTER(C.c_int32), C.c_int, C.c_int],
     "rcbf_cars_safe_action_host": [_vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, C.POINTER(C.c_int32), C.c_int,
                                    C.c_int],
+    "rcbf_unicycle_safe_step_host": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams),
+                                     C.POINTER(P.UnicycleEnvParams), _vp, _vp, _vp, _vp, _vp, _vp,
+                                     C.POINTER(C.c_int32), C.c_int, C.c_int],
+    "rcbf_cars_safe_step_host": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), C.POINTER(P.CarsEnvParams),
+                                 _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.c_int, C.c_int],
     "rcbf_fp32_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
 }
 for _suf in ("f32", "f64"):

@@ -646,7 +646,7 @@ int run_host_pipe(const float* const* in_host, const int* in_width, int n_in, fl
     cur += (size_t)n * in_width[k];
   }
   float* dev_out = cur;
-  const int64_t per = (n + chunks - 1) / chunks;
+  const int64_t per = (((n + chunks - 1) / chunks) + 31) & ~(int64_t)31;  // tile multiple: chunks stay 16-byte aligned
   for (int c = 0; c < chunks; ++c) {
     const int64_t lo = (int64_t)c * per;
     const int64_t cnt = (lo + per <= n) ? per : (n - lo);
@@ -671,9 +671,96 @@ int run_host_pipe(const float* const* in_host, const int* in_width, int n_in, fl
   if (n_failed_host) *n_failed_host = (int32_t)nan_count;
   return (int)cudaGetLastError();
 }
+// fused-step pipeline: `n_in` host input arrays and `n_out` host output arrays of given BYTE widths per instance; the
+// env state stays on the device.  launch(dev_in[], dev_out[], lo, cnt, ws, stream) runs the fused kernel on a slice.
+template <typename LaunchFn>
+int run_step_pipe(const void* const* in_host, const int* in_bytes, int n_in, void* const* out_host, const int* out_bytes,
+                  int n_out, int64_t n, int device, int chunks, int32_t* n_failed_host, LaunchFn launch) {
+  if (n <= 0) return 0;
+  size_t total = 0;
+  size_t off_in[8], off_out[8];
+  for (int k = 0; k < n_in; ++k) {
+    off_in[k] = total;
+    total += (((size_t)n * in_bytes[k]) + 255) & ~(size_t)255;
+  }
+  for (int k = 0; k < n_out; ++k) {
+    off_out[k] = total;
+    total += (((size_t)n * out_bytes[k]) + 255) & ~(size_t)255;
+  }
+  int rc = g_pipe.ensure(device, (total + 3) / 4);
+  if (rc) return rc;
+  cudaSetDevice(device);
+  if (chunks < 1) chunks = 1;
+  for (int k = 0; k < 3; ++k) cudaMemsetAsync(g_pipe.counters + k * RCBF_WS_WORDS, 0, 8 * sizeof(rcbf_counters_t), g_pipe.streams[k]);
+  char* base = reinterpret_cast<char*>(g_pipe.scratch);
+  void* dev_in[8];
+  void* dev_out[8];
+  const int64_t per = (((n + chunks - 1) / chunks) + 31) & ~(int64_t)31;
+  for (int c = 0; c < chunks; ++c) {
+    const int64_t lo = (int64_t)c * per;
+    const int64_t cnt = (lo + per <= n) ? per : (n - lo);
+    if (cnt <= 0) break;
+    cudaStream_t s = g_pipe.streams[c % 3];
+    for (int k = 0; k < n_in; ++k) {
+      dev_in[k] = base + off_in[k] + (size_t)lo * in_bytes[k];
+      cudaMemcpyAsync(dev_in[k], static_cast<const char*>(in_host[k]) + (size_t)lo * in_bytes[k], (size_t)cnt * in_bytes[k],
+                      cudaMemcpyHostToDevice, s);
+    }
+    for (int k = 0; k < n_out; ++k) dev_out[k] = base + off_out[k] + (size_t)lo * out_bytes[k];
+    rc = launch(dev_in, dev_out, lo, cnt, g_pipe.counters + (c % 3) * RCBF_WS_WORDS, s);
+    if (rc) return rc;
+    for (int k = 0; k < n_out; ++k)
+      cudaMemcpyAsync(static_cast<char*>(out_host[k]) + (size_t)lo * out_bytes[k], dev_out[k], (size_t)cnt * out_bytes[k],
+                      cudaMemcpyDeviceToHost, s);
+  }
+  for (auto& s : g_pipe.streams) cudaStreamSynchronize(s);
+  rcbf_counters_t nan_count = 0;
+  for (int k = 0; k < 3; ++k) {
+    rcbf_counters_t v = 0;
+    cudaError_t e = cudaMemcpy(&v, g_pipe.counters + k * RCBF_WS_WORDS, sizeof(v), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return (int)e;
+    nan_count += v;
+  }
+  if (n_failed_host) *n_failed_host = (int32_t)nan_count;
+  return (int)cudaGetLastError();
+}
 }  // namespace
 
 extern "C" {
+
+int rcbf_unicycle_safe_step_host(float* state4, int32_t* step, const float* action_host, const float* mean_host,
+                                 const float* sigma_host, int64_t n, const rcbf_unicycle_params* p,
+                                 const rcbf_unicycle_env_params* e, float* safe_action_host, float* obs_host,
+                                 float* reward_host, uint8_t* done_host, float* cost_host, uint8_t* goal_met_host,
+                                 int32_t* n_failed_host, int device, int chunks) {
+  const void* in[3] = {action_host, mean_host, sigma_host};
+  const int inb[3] = {8, 12, 12};
+  void* out[6] = {safe_action_host, obs_host, reward_host, done_host, cost_host, goal_met_host};
+  const int outb[6] = {8, 28, 4, 1, 4, 1};
+  return run_step_pipe(in, inb, 3, out, outb, 6, n, device, chunks, n_failed_host,
+                       [&](void** di, void** d_o, int64_t lo, int64_t cnt, rcbf_counters_t* ws, cudaStream_t s) {
+                         return rcbf_unicycle_safe_step(state4 + lo * 4, step + lo, (const float*)di[0],
+                                                        (const float*)di[1], (const float*)di[2], cnt, p, e,
+                                                        (float*)d_o[0], (float*)d_o[1], (float*)d_o[2], (uint8_t*)d_o[3],
+                                                        (float*)d_o[4], (uint8_t*)d_o[5], nullptr, ws, (void*)s);
+                       });
+}
+
+int rcbf_cars_safe_step_host(float* state, float* t, int32_t* step, const float* action_host, const float* sigma_host,
+                             int64_t n, const rcbf_cars_params* p, const rcbf_cars_env_params* e,
+                             float* safe_action_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                             float* cost_host, int32_t* n_failed_host, int device, int chunks) {
+  const void* in[2] = {action_host, sigma_host};
+  const int inb[2] = {4, 40};
+  void* out[5] = {safe_action_host, obs_host, reward_host, done_host, cost_host};
+  const int outb[5] = {4, 40, 4, 1, 4};
+  return run_step_pipe(in, inb, 2, out, outb, 5, n, device, chunks, n_failed_host,
+                       [&](void** di, void** d_o, int64_t lo, int64_t cnt, rcbf_counters_t* ws, cudaStream_t s) {
+                         return rcbf_cars_safe_step(state + lo * 10, t + lo, step + lo, (const float*)di[0],
+                                                    (const float*)di[1], cnt, p, e, (float*)d_o[0], (float*)d_o[1],
+                                                    (float*)d_o[2], (uint8_t*)d_o[3], (float*)d_o[4], nullptr, ws, (void*)s);
+                       });
+}
 
 int rcbf_unicycle_safe_action_host(const float* state_host, const float* action_host, const float* mean_host,
                                    const float* sigma_host, int64_t n, const rcbf_unicycle_params* p,

@@ -140,3 +140,28 @@ class SimulatedCarsEnv:
         _lib.check(rc, "rcbf_cars_safe_step")
         info = {'cost': self._cost, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
+
+    def safe_step_host(self, cbf_layer, action_rl, sigma_pred, out=None, chunks=8):
+        """Fused safe step with HOST tensors in and out (see UnicycleEnv.safe_step_host)."""
+        import ctypes as C
+        if self.precision != "f32":
+            raise ValueError("safe_step_host runs on the float32 env layout (precision='f32')")
+        n = self.num_envs
+        if out is None:
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+            out = dict(safe_action=mk((n, 1), torch.float32), obs=mk((n, 10), torch.float32),
+                       reward=mk((n,), torch.float32), done=mk((n,), torch.uint8), cost=mk((n,), torch.float32))
+        for t in (action_rl, sigma_pred):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("safe_step_host takes contiguous float32 CPU tensors")
+        nf = C.c_int32(0)
+        torch.cuda.current_stream(self.device).synchronize()
+        rc = self._lib.rcbf_cars_safe_step_host(
+            _lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step), _lib.ptr(action_rl), _lib.ptr(sigma_pred), n,
+            cbf_layer._params(), self._env_params(), _lib.ptr(out["safe_action"]), _lib.ptr(out["obs"]),
+            _lib.ptr(out["reward"]), _lib.ptr(out["done"]), _lib.ptr(out["cost"]), C.byref(nf), self.device.index or 0,
+            int(chunks))
+        _lib.check(rc, "rcbf_cars_safe_step_host")
+        if cbf_layer.check_nan and nf.value > 0:
+            raise Exception('QP Failed to solve')
+        return out

@@ -173,6 +173,35 @@ class UnicycleEnv:
         info = {'cost': self._cost, 'goal_met': self._goal, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
 
+    def safe_step_host(self, cbf_layer, action_rl, mean_pred, sigma_pred, out=None, chunks=8):
+        """Fused safe step with HOST tensors in and out (the end-to-end path): `action_rl (n,2)`, `mean_pred (n,3)`,
+        `sigma_pred (n,3)` float32 CPU tensors (pinned memory recommended); the env state stays on the GPU.  The C
+        library pipelines H2D / kernel / D2H over `chunks` slices on its own streams and returns when `out` is valid.
+        Returns dict(safe_action, obs, reward, done, cost, goal_met) of pinned CPU tensors (reused when passed back)."""
+        import ctypes as C
+        if self.precision != "f32":
+            raise ValueError("safe_step_host runs on the float32 env layout (precision='f32')")
+        n = self.num_envs
+        if out is None:
+            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
+            out = dict(safe_action=mk((n, 2), torch.float32), obs=mk((n, 7), torch.float32),
+                       reward=mk((n,), torch.float32), done=mk((n,), torch.uint8), cost=mk((n,), torch.float32),
+                       goal_met=mk((n,), torch.uint8))
+        for t in (action_rl, mean_pred, sigma_pred):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError("safe_step_host takes contiguous float32 CPU tensors")
+        nf = C.c_int32(0)
+        torch.cuda.current_stream(self.device).synchronize()      # the library uses its own streams
+        rc = self._lib.rcbf_unicycle_safe_step_host(
+            _lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(action_rl), _lib.ptr(mean_pred), _lib.ptr(sigma_pred),
+            n, cbf_layer._params(), self._env_params(), _lib.ptr(out["safe_action"]), _lib.ptr(out["obs"]),
+            _lib.ptr(out["reward"]), _lib.ptr(out["done"]), _lib.ptr(out["cost"]), _lib.ptr(out["goal_met"]),
+            C.byref(nf), self.device.index or 0, int(chunks))
+        _lib.check(rc, "rcbf_unicycle_safe_step_host")
+        if cbf_layer.check_nan and nf.value > 0:
+            raise Exception('QP Failed to solve')
+        return out
+
     # kept for API parity with envs/unicycle_env.py:113,260
     def goal_met(self):
         d = torch.linalg.norm(torch.as_tensor(self.goal_pos, dtype=self._dtype, device=self.device)

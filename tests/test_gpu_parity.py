@@ -561,6 +561,30 @@ def test_host_buffer_entry_matches_device_entry(S, uni, cars):
         np.testing.assert_array_equal(out.numpy(), ref)
 
 
+def test_fused_step_host_entry_matches_device_entry(S, uni, cars):
+    """rcbf_*_safe_step_host (pinned host tensors in/out, env state on the GPU) == the device-resident safe_step."""
+    B = 100003
+    env_u, layer_u = uni
+    st, ac, mu, sg = O.synth_unicycle(B, seed=12)
+    a = S.UnicycleEnv(num_envs=B); b = S.UnicycleEnv(num_envs=B)
+    a.state = _cuda(st); b.state = _cuda(st)
+    us, obs, rew, done, info = a.safe_step(layer_u, _cuda(ac), _cuda(mu), _cuda(sg))
+    pin = lambda x: torch.from_numpy(x).pin_memory()  # noqa: E731
+    out = b.safe_step_host(layer_u, pin(ac), pin(mu), pin(sg), chunks=5)
+    assert torch.equal(out["safe_action"], us.cpu()) and torch.equal(out["obs"], obs.cpu())
+    assert torch.equal(out["reward"], rew.cpu()) and torch.equal(out["done"], done.cpu())
+    assert torch.equal(out["cost"], info["cost"].cpu()) and torch.equal(a.state, b.state)
+    env_c, layer_c = cars
+    stc, acc, muc, sgc, t = O.synth_cars(B, seed=12)
+    a = S.SimulatedCarsEnv(num_envs=B); b = S.SimulatedCarsEnv(num_envs=B)
+    for e in (a, b):
+        e.state = _cuda(stc); e._t.copy_(_cuda(t))
+    us, obs, rew, done, info = a.safe_step(layer_c, _cuda(acc), _cuda(sgc))
+    out = b.safe_step_host(layer_c, pin(acc), pin(sgc), chunks=3)
+    assert torch.equal(out["safe_action"], us.cpu()) and torch.equal(out["obs"], obs.cpu())
+    assert torch.equal(out["reward"], rew.cpu()) and torch.equal(a.state, b.state)
+
+
 # ----------------------------------------------------------------------------------------------------- numpy layer shim
 def test_cascade_layer_vs_oracle(S, golden):
     g = golden("cascade_layer.npz")
