@@ -249,6 +249,41 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     out["pdipm_mode"] = {"value": n / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
                          "ipm_iters_mean": cc[4] / tot, "f64_passes": cc[2], "uncertified": cc[1],
                          "note": "every non-trivial QP through the float32 Mehrotra PDIPM + float64 certificate"}
+    # (a2) worst-case mix: EVERY instance sits in the 0.3..1.1 ring around a hazard (the 20 % stratum of the headline
+    # workload made 100 %), so nearly every QP needs a solve
+    g = torch.Generator(device=device)
+    g.manual_seed(99)
+    hz = torch.tensor([[0., 0.], [-1.5, 1.5], [-1.5, -1.5], [1.5, -1.5], [1.5, 1.5]], device=device)
+    idx = torch.randint(0, 5, (n,), generator=g, device=device)
+    r = 0.3 + 0.8 * torch.rand(n, generator=g, device=device)
+    phi = (2 * torch.rand(n, generator=g, device=device) - 1) * np.pi
+    sth = torch.stack([hz[idx, 0] + r * torch.cos(phi), hz[idx, 1] + r * torch.sin(phi),
+                       (2 * torch.rand(n, generator=g, device=device) - 1) * np.pi], 1).contiguous()
+    envh = S.UnicycleEnv(num_envs=n, device=device, auto_reset=True)
+    envh._counters = torch.zeros(32768, dtype=torch.int64, device=device)
+    envh._safe_action = torch.empty((n, 2), dtype=torch.float32, device=device)
+
+    def hz_step():
+        envh.state = sth                      # same hard states every launch
+        envh.safe_step(layer, *batches[0])
+
+    for _ in range(3):
+        hz_step()
+    envh._counters[:8].zero_()
+    torch.cuda.synchronize(device)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot_ms = 0.0
+    for _ in range(5):
+        envh.state = sth
+        e0.record()
+        envh.safe_step(layer, *batches[0])
+        e1.record()
+        torch.cuda.synchronize(device)
+        tot_ms += e0.elapsed_time(e1)
+    ch = envh._counters[:8].cpu().tolist()
+    out["hazard_heavy_100pct"] = {"value": n / (tot_ms / 5 * 1e-3), "unit": "env-steps/s", "ms_per_step": tot_ms / 5,
+                                  "nontrivial_frac": 1.0 - ch[3] / (5.0 * n), "fallback": ch[5]}
+    del envh
     # (b) QP solves/s: get_safe_action only (assembly + solve + clamp), Unicycle and SimulatedCars (config 5 sizes)
     st = env._state4[:, :3].contiguous()
     u, mu, sg = batches[0]
