@@ -363,6 +363,39 @@ def test_solve_qp_api(request, golden, which, name):
         assert rel < GRAD_TOL, rel
 
 
+@pytest.mark.parametrize("nz,m", [(3, 9), (2, 4)])
+def test_generic_qp_dense_Q_and_p_vs_exact_and_qpth_backward(uni, nz, m):
+    """cbf_layer on QPs the layer itself never builds: dense SPD Q, non-zero p, dense G (the Cholesky change of
+    variables and the dQ / dp gradients of the generic kernel)."""
+    from oracle import qpth_pdipm
+    env, layer = uni
+    B = 4000
+    rng = np.random.default_rng(nz * 100 + m)
+    L = rng.normal(size=(B, nz, nz)) * 0.5 + np.eye(nz)[None] * 1.5
+    Q = L @ L.transpose(0, 2, 1) + 0.1 * np.eye(nz)[None]
+    p = rng.normal(size=(B, nz))
+    G = rng.normal(size=(B, m, nz))
+    x0 = rng.normal(size=(B, nz))
+    h = np.einsum("bmj,bj->bm", G, x0) + rng.uniform(0.05, 2.0, size=(B, m))      # strictly feasible at x0
+    xe, lam, act, viol = exact_qp.solve_exact(Q, p, G, h)
+    assert viol.max() < 1e-8
+    Qc, pc, Gc, hc = (torch.from_numpy(a).cuda().requires_grad_(True) for a in (Q, p, G, h))
+    x = layer.cbf_layer(Qc, pc, Gc, hc)
+    assert x.dtype == torch.float32 and np.abs(x.detach().cpu().numpy() - xe).max() < 2e-5 * max(1.0, np.abs(xe).max())
+    assert layer.solver_stats()["nan"] == 0
+    # gradients of a random linear functional vs the restated qpth backward evaluated at the exact solution
+    w = rng.normal(size=(B, nz))
+    (x.double() * torch.from_numpy(w).cuda()).sum().backward()
+    slack = h - np.einsum("bmj,bj->bm", G, xe)
+    dQ, dp, dG, dh = qpth_pdipm.pdipm_backward(tt(Q), tt(G), tt(xe), tt(lam), tt(np.maximum(slack, 0.0)), tt(w))
+    for mine, ref in ((Qc.grad, dQ), (pc.grad, dp), (Gc.grad, dG), (hc.grad, dh)):
+        rel = (mine.cpu() - ref).norm() / ref.norm().clamp_min(1e-9)
+        assert rel < GRAD_TOL, rel
+    with pytest.raises(NotImplementedError):
+        layer.cbf_layer(torch.eye(4)[None].cuda().double(), torch.zeros(1, 4).cuda().double(),
+                        torch.zeros(1, 5, 4).cuda().double(), torch.ones(1, 5).cuda().double())
+
+
 # ----------------------------------------------------------------------------------------------------- dynamics
 def test_unicycle_env_f64_vs_golden_trajectory(S, golden):
     g = golden("unicycle_env_traj.npz")
