@@ -68,11 +68,20 @@ class CarsEnvParams(C.Structure):
 DEFAULT_HAZARDS = np.array([[0., 0.], [-1., 1.], [-1., -1.], [1., -1.], [1., 1.]]) * 1.5  # envs/unicycle_env.py:26
 
 
+FAR_HAZARD = 1.0e4  # padding hazard: h = gamma*(1/2 |d|^2)^3 ~ 1e24 > 0 always, so its row can never be active
+
+
 def _check_hazards(hazards_locations):
+    """(K,2) with 1 <= K <= 5 hazards -> (5,2): the kernels are specialised for the reference's 5 hazards
+    (unicycle_env.py:26); fewer are padded with hazards 1e4 m away whose CBF rows are inert."""
     hz = np.asarray(DEFAULT_HAZARDS if hazards_locations is None else hazards_locations, np.float64)
-    if hz.shape != (UNI_HAZ, 2):
-        raise ValueError("the sm_100a kernels are specialised for %d hazards (reference: unicycle_env.py:26), got %r"
-                         % (UNI_HAZ, hz.shape))
+    if hz.ndim != 2 or hz.shape[1] != 2 or not (1 <= hz.shape[0] <= UNI_HAZ):
+        raise ValueError("the sm_100a kernels support 1..%d hazards of shape (K, 2) (reference: unicycle_env.py:26), "
+                         "got %r" % (UNI_HAZ, hz.shape))
+    if hz.shape[0] < UNI_HAZ:
+        pad = np.full((UNI_HAZ - hz.shape[0], 2), FAR_HAZARD)
+        pad[:, 1] += np.arange(pad.shape[0]) * 10.0
+        hz = np.concatenate([hz, pad], 0)
     return hz
 
 

@@ -290,6 +290,9 @@ class CBFQPLayer:
                 h = torch.empty((n, 9), dtype=torch.float32, device=dev)
                 rc = lib.rcbf_unicycle_assemble(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
                                                 _lib.ptr(G), _lib.ptr(h), _lib.stream_ptr(dev))
+                if self.num_cbfs < 5:   # drop the inert rows of the padding hazards (see _params._check_hazards)
+                    rows = list(range(self.num_cbfs)) + [5, 6, 7, 8]
+                    G, h = G[:, rows, :].contiguous(), h[:, rows].contiguous()
                 P = torch.diag(torch.tensor([1.e0, 1.e-2, 1e5])).repeat(n, 1, 1).to(out_dev)
             elif mode == 'SimulatedCars':
                 G = torch.empty((n, 4, 2), dtype=torch.float32, device=dev)

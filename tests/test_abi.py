@@ -77,7 +77,9 @@ def test_params_mirror_reference_constants():
     c = P.cars_params(gamma_b=20.0)
     assert c.gamma_2 == 40.0 and c.gamma_sq == 400.0 and c.slack_coeff == 200.0 and c.collision_radius_sq == 12.25
     with pytest.raises(ValueError):
-        P.unicycle_params(hazards_locations=[[0, 0]] * 3)
+        P.unicycle_params(hazards_locations=[[0, 0]] * 6)
+    p3 = P.unicycle_params(hazards_locations=[[0, 0]] * 3)       # padded with inert far-away hazards
+    assert p3.hazards[3][0] == P.FAR_HAZARD and p3.hazards[4][1] > P.FAR_HAZARD
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")

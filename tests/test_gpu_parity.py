@@ -251,6 +251,31 @@ def test_other_layer_parameters_vs_oracle(S, mode, gamma_b, l_p):
     assert np.abs(out - fe)[ok].max() < ACT_TOL
 
 
+def test_fewer_than_five_hazards(S):
+    """The reference layer sizes itself from len(env.hazards_locations) (diff_cbf_qp.py:35); 1..5 hazards are supported
+    by padding with inert far-away hazards."""
+    env = S.UnicycleEnv()
+    env.hazards_locations = np.array([[0.4, 0.1], [-1.0, 1.2], [1.3, -0.8]])
+    layer = S.CBFQPLayer(env, _args(), gamma_b=20, k_d=3.0, l_p=0.03)
+    assert layer.num_cbfs == 3 and layer.num_ineq_constraints == 7
+    st, ac, mu, sg = O.synth_unicycle(20000, seed=23)
+    P, q, G, h = layer.get_cbf_qp_constraints(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg))
+    kw = dict(gamma_b=20.0, hazards=env.hazards_locations)
+    P2, q2, G2, h2 = O.assemble_unicycle(tt(st), tt(ac), tt(mu), tt(sg), **kw)
+    assert G.shape == (20000, 7, 3) and h.shape == (20000, 7)
+    n = np.maximum(np.abs(G2.numpy()).max(2), np.abs(h2.numpy()))
+    assert (np.abs(G.cpu().numpy() - G2.numpy()) / n[:, :, None]).max() < 5e-7
+    assert (np.abs(h.cpu().numpy() - h2.numpy()) / n).max() < 3e-6
+    out = layer.get_safe_action(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg)).cpu().numpy()
+    fe = O.safe_action("Unicycle", tt(st), tt(ac), tt(mu), tt(sg), solver="exact", **kw).numpy()
+    f64 = O.safe_action("Unicycle", tt(st), tt(ac), tt(mu), tt(sg), solver="exact", assembly_dtype=torch.float64, **kw).numpy()
+    ok = np.abs(fe - f64).max(1) <= 2e-5
+    assert ok.mean() > 0.995 and np.abs(out - fe)[ok].max() < ACT_TOL
+    with pytest.raises(ValueError):
+        env.hazards_locations = np.zeros((6, 2))
+        S.CBFQPLayer(env, _args()).get_safe_action(_cuda(st[:4]), _cuda(ac[:4]), _cuda(mu[:4]), _cuda(sg[:4]))
+
+
 def test_trivial_instances_pass_through(uni):
     env, layer = uni
     B = 4096
