@@ -13,11 +13,25 @@ HEADERS = ["rcbf_core.cuh", "rcbf_dynamics.cuh", "rcbf_backward.cuh", "rcbf_gene
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
+HASH_FILE = LIB + ".srchash"
+
+
+def _source_hash():
+    """Content hash of every source / header / flag: file mtimes do not survive a snapshot copy or a git checkout."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not (os.path.exists(LIB) and os.path.exists(HASH_FILE)):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(HASH_FILE) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
@@ -44,6 +58,8 @@ def build(force=False, verbose=False):
                        ["-o", LIB], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout)
+    with open(HASH_FILE, "w") as fh:
+        fh.write(_source_hash() + "\n")
     return LIB
 
 
