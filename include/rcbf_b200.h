@@ -208,10 +208,46 @@ int rcbf_cars_safe_step_host(float* state, float* t, int32_t* step, const float*
                              float* safe_action_host, float* obs_host, float* reward_host, uint8_t* done_host,
                              float* cost_host, int32_t* n_failed_host, int device, int chunks);
 
+/* ---- disturbance-GP posterior ----------------------------------------------------------
+ * Replaces GPyDisturbanceEstimator.predict (rcbf_sac/gp_model.py:86-114) + the fitted branch of
+ * DynamicsModel.predict_disturbance (rcbf_sac/dynamics.py:371-379) for all n_gp output dimensions in ONE launch:
+ *   z*      = test_x * inv_x_scale                              (dynamics.py:375)
+ *   k*_j    = outputscale_g * exp(-|z* - z_j|^2 * inv_2l2_g)    (ScaleKernel(RBFKernel), gp_model.py:17-20)
+ *   w       = F_g k*            F_g (rank_g x n) with  F_g^T F_g = (K_g + noise_g I)^-1  (exactly, or truncated to
+ *                               the numerical rank by the host side, which validates the truncation when it builds F)
+ *   mean    = y_scale_g * (w . proj_y_g)                        proj_y_g = F_g y_g          (gp_model.py:99, dynamics.py:378)
+ *   std     = y_scale_g * sqrt(max(outputscale_g - |w|^2 + include_noise * noise_g, min_variance))   (:100,:379)
+ * All arithmetic is float64 (outputscale - |w|^2 cancels ~ n outputscale / noise digits).
+ * Device arrays, caller-owned, read-only:
+ *   train_z     [n_pad][dim_pad]   normalised training inputs, zero padded; n_pad % 32 == 0, dim_pad in {4, 8, 12, 16}
+ *   inv_x_scale [dim_pad]          zero beyond n_in
+ *   hyp         [n_gp][4]          {inv_2l2, outputscale, noise, y_scale}
+ *   r_tiles     [n_gp]             number of tile_rows-wide row tiles of F_g actually used (<= max_tiles)
+ *   factor      [n_gp][max_tiles][n_pad][tile_rows]   F_g, tile-major and transposed (zero padded)
+ *   proj_y      [n_gp][max_tiles * tile_rows] */
+typedef struct {
+  const double* train_z;
+  const double* inv_x_scale;
+  const double* hyp;
+  const int32_t* r_tiles;
+  const double* factor;
+  const double* proj_y;
+  int32_t n_pad, n_in, dim_pad, n_gp, max_tiles, tile_rows; /* tile_rows in {16, 64} */
+  int32_t include_noise;                                    /* 1: 'f_var' as the reference returns it (gp_model.py:100) */
+  double min_variance;                                      /* gpytorch float32 clamp: 1e-6 */
+} rcbf_gp_posterior;
+
+/* test_x (n_test, n_in) row-major -> mean, std (n_test, n_gp) row-major, same scalar type as test_x. */
+int rcbf_gp_predict_f32(const float* test_x, int64_t n_test, const rcbf_gp_posterior* post_host, float* mean,
+                        float* std, void* stream);
+int rcbf_gp_predict_f64(const double* test_x, int64_t n_test, const rcbf_gp_posterior* post_host, double* mean,
+                        double* std, void* stream);
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------
  * FP32 FMA throughput probe: `iters` dependent-chain FMAs x 8 chains per thread; returns nothing, time it outside.
  * flops per launch = 2 * 8 * iters * blocks * threads. */
 int rcbf_fp32_fma_probe(float* sink, int blocks, int threads, int iters, void* stream);
+int rcbf_fp64_fma_probe(double* sink, int blocks, int threads, int iters, void* stream); /* same, float64 FMAs */
 const char* rcbf_version(void);
 
 #ifdef __cplusplus

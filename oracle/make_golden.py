@@ -197,8 +197,48 @@ def rollouts_fixture(ref, B=25):
     return out
 
 
+def gp_fixture(ref, n_uni=120, n_cars=96, n_test=40):
+    """Disturbance history = output of the REFERENCE's own envs + DynamicsModel.append_transition (random actions,
+    GP refits disabled: gpytorch is absent); hyper-parameters / posterior = oracle/gp_oracle.py (parity unpinned)."""
+    from oracle import gp_oracle
+    args = ref_loader.make_args()
+    args.gp_model_size = 100000          # never reaches the refit trigger (dynamics.py:303)
+    out = {}
+    rng = np.random.default_rng(777)
+    for mode, envc, n in (("Unicycle", ref.UnicycleEnv, n_uni), ("SimulatedCars", ref.SimulatedCarsEnv, n_cars)):
+        np.random.seed(12345)
+        env = envc()
+        dm = ref.DynamicsModel(env, args)
+        env.reset()
+        for _ in range(n):
+            state = np.copy(env.state if mode == "Unicycle" else env.state)
+            t = None if mode == "Unicycle" else np.array([env.t])
+            a = rng.uniform(-1, 1, env.action_space.shape[0])
+            _, _, done, _ = env.step(a)
+            if mode == "Unicycle":
+                a_used = np.clip(a, -1.0, 1.0)   # unicycle_env.py:62 clips before stepping
+                dm.append_transition(state, a_used, np.copy(env.state))
+            else:
+                dm.append_transition(state, a, np.copy(env.state), t_batch=t)
+            if done:
+                env.reset()
+        train_x = dm.disturbance_history['state'][:dm.history_counter].copy()
+        train_y = dm.disturbance_history['disturbance'][:dm.history_counter].copy()
+        gps = gp_oracle.DisturbanceGPs(train_x, train_y, ref.MAX_STD[mode], training_iter=70)
+        lo, hi = train_x.min(0), train_x.max(0)
+        test_x = rng.uniform(lo - 0.2 * (hi - lo + 1e-3), hi + 0.2 * (hi - lo + 1e-3), (n_test, train_x.shape[1]))
+        mean, std = gps.predict_disturbance(test_x)
+        k = mode.lower()
+        out.update({k + "_train_x": train_x, k + "_train_y": train_y, k + "_raw": np.stack([g.raw for g in gps.gps]),
+                    k + "_test_x": test_x, k + "_mean": mean, k + "_std": std})
+    return out
+
+
 def main():
     ref = ref_loader.load_reference()
+    if "--gp-only" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "gp_disturbance.npz"), **gp_fixture(ref))
+        return
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(12345)
     np.savez_compressed(os.path.join(OUT, "unicycle_layer_b256.npz"), **layer_fixture(ref, "Unicycle", 256, 20.0))
@@ -208,6 +248,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "dynamics_prior.npz"), **dynamics_fixture(ref))
     np.savez_compressed(os.path.join(OUT, "cascade_layer.npz"), **cascade_fixture(ref))
     np.savez_compressed(os.path.join(OUT, "model_rollouts.npz"), **rollouts_fixture(ref))
+    np.savez_compressed(os.path.join(OUT, "gp_disturbance.npz"), **gp_fixture(ref))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -3,7 +3,8 @@
 Public surface (mirrors the reference's names):
     CBFQPLayer / DiffCBFLayer   rcbf_sac/diff_cbf_qp.py
     CascadeCBFLayer             rcbf_sac/cbf_qp.py
-    DynamicsModel               rcbf_sac/dynamics.py (prior paths)
+    DynamicsModel               rcbf_sac/dynamics.py (prior paths + device disturbance GPs)
+    GPyDisturbanceEstimator, DisturbanceGPBank      rcbf_sac/gp_model.py (exact-GP fit + CUDA posterior kernel)
     UnicycleEnv, SimulatedCarsEnv, build_env        envs/*.py, build_env.py
     generate_model_rollouts, DeviceReplayMemory     rcbf_sac/generate_rollouts.py, replay_memory.py (device-resident)
 The compute lives in librcbf_b200.so (hand-written CUDA, C ABI in include/rcbf_b200.h).  No CPU fallback.
@@ -24,6 +25,9 @@ def __getattr__(name):  # lazy: importing the package must work on a box without
     if name in ("UnicycleEnv", "SimulatedCarsEnv"):
         from . import envs
         return getattr(envs, name)
+    if name in ("GPyDisturbanceEstimator", "DisturbanceGPBank"):
+        from . import gp_model
+        return getattr(gp_model, name)
     if name == "DeviceReplayMemory":
         from .replay_memory import DeviceReplayMemory
         return DeviceReplayMemory

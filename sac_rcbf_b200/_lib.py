@@ -42,6 +42,9 @@ SIGNATURES = {
     "rcbf_cars_safe_step_host": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), C.POINTER(P.CarsEnvParams),
                                  _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.c_int, C.c_int],
     "rcbf_fp32_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
+    "rcbf_fp64_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
+    "rcbf_gp_predict_f32": [_vp, _i64, C.POINTER(P.GpPosterior), _vp, _vp, _vp],
+    "rcbf_gp_predict_f64": [_vp, _i64, C.POINTER(P.GpPosterior), _vp, _vp, _vp],
 }
 for _suf in ("f32", "f64"):
     SIGNATURES["rcbf_unicycle_env_reset_" + _suf] = [_vp, _vp, _vp, _i64, C.POINTER(P.UnicycleEnvParams), _vp, _vp]

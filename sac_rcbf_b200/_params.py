@@ -22,6 +22,25 @@ class UnicycleParams(C.Structure):
     ]
 
 
+class GpPosterior(C.Structure):  # rcbf_gp_posterior
+    _fields_ = [
+        ("train_z", C.c_void_p),
+        ("inv_x_scale", C.c_void_p),
+        ("hyp", C.c_void_p),
+        ("r_tiles", C.c_void_p),
+        ("factor", C.c_void_p),
+        ("proj_y", C.c_void_p),
+        ("n_pad", C.c_int32),
+        ("n_in", C.c_int32),
+        ("dim_pad", C.c_int32),
+        ("n_gp", C.c_int32),
+        ("max_tiles", C.c_int32),
+        ("tile_rows", C.c_int32),
+        ("include_noise", C.c_int32),
+        ("min_variance", C.c_double),
+    ]
+
+
 class CarsParams(C.Structure):
     _fields_ = [
         ("gamma_2", C.c_float),

@@ -1,0 +1,37 @@
+// rcbf_tma.cuh -- cp.async.bulk (TMA, 1-D) + mbarrier helpers shared by the hot kernels and the GP posterior kernel.
+#pragma once
+
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+namespace rcbf {
+
+// ---- TMA bulk copies (cp.async.bulk, global -> shared, completion on an mbarrier): the input rows of a 32-instance
+// tile are contiguous spans, so each array of the NEXT tile is fetched by one asynchronous 1-D bulk copy issued by
+// lane 0 while the warp works on the current tile.  No registers are tied up and the latency is fully hidden.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
+}  // namespace rcbf

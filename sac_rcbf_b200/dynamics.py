@@ -1,9 +1,10 @@
 """DynamicsModel -- prior-dynamics part of rcbf_sac/dynamics.py behind the same method names.
 
-In scope: `predict_next_state` (prior f, g + dt * disturbance mean), `get_state`,
-`get_obs`, the zero-mean / MAX_STD prior branch of `predict_disturbance`, `append_transition` (history ring buffer).
-Out of scope: fitting / evaluating the GPyTorch disturbance GPs (dynamics.py:306-340,371-379) -- the kernels consume
-the (mean, std) tensors a GP produces; plug one in through `disturbance_fn`.
+SURVEY.md section 8a rows D3-D5: `predict_next_state` (prior f, g + dt * disturbance mean), `get_state`, `get_obs`,
+the zero-mean / MAX_STD prior branch of `predict_disturbance`, `append_transition` (history ring buffer).
+Section 8f row 1: `fit_gp_model` / the fitted branch of `predict_disturbance` / save + load run on the device through
+`gp_model.DisturbanceGPBank` (one CUDA launch for all state dimensions, no host round trip for tensor inputs).
+`disturbance_fn` still overrides everything when given.
 """
 import numpy as np
 import torch
@@ -149,7 +150,15 @@ class DynamicsModel:
         if self.disturbance_fn is not None:
             means, f_std = self.disturbance_fn(test_x)
         elif self.disturb_estimators:
-            raise NotImplementedError("fitted-GP prediction (dynamics.py:371-379) is out of scope; pass disturbance_fn")
+            # dynamics.py:371-379: x / std_x, every GP, mean * (std_y + 1e-8), sqrt(f_var) * (std_y + 1e-8) -- the
+            # scalings live in the bank and are applied inside the kernel
+            if is_tensor:
+                dt_ = test_x.dtype if test_x.dtype in (torch.float32, torch.float64) else torch.float32
+                means, f_std = self._gp_bank.predict(test_x.detach().to(self.device, dt_))
+                means, f_std = means.to(test_x.device, test_x.dtype), f_std.to(test_x.device, test_x.dtype)
+            else:
+                xs = torch.as_tensor(np.asarray(test_x, np.float64)).to(self.device)
+                means, f_std = (v.cpu().numpy() for v in self._gp_bank.predict(xs))
         else:
             max_std = MAX_STD[self.env.dynamics_mode]
             if is_tensor:
@@ -163,8 +172,8 @@ class DynamicsModel:
         return means, f_std
 
     def append_transition(self, state_batch, u_batch, next_state_batch, t_batch=None):
-        """Record (state, estimated disturbance) in the ring buffer (dynamics.py:263-304).  GP refits are delegated
-        to `fit_gp_model`, a no-op unless a subclass / hook provides one."""
+        """Record (state, estimated disturbance) in the ring buffer (dynamics.py:263-304) and refit the GPs every
+        max_history_count / 10 points, like the reference."""
         expand_dims = len(state_batch.shape) == 1
         if expand_dims:
             state_batch = np.expand_dims(state_batch, 0)
@@ -183,8 +192,54 @@ class DynamicsModel:
                 self.fit_gp_model()
 
     def fit_gp_model(self, training_iter=70):
-        """GP fitting (dynamics.py:306-340) is outside the hot-path scope: no-op."""
-        return None
+        """dynamics.py:306-340: normalise the history by its std (+1e-8), one GP per state dimension with the MAX_STD
+        prior outputscale, `training_iter` Adam steps on the exact marginal likelihood -- all dimensions as one batch
+        on the device -- then cache the posterior factors the predict kernel reads."""
+        if self.history_counter < self.max_history_count:
+            train_x = self.disturbance_history['state'][:self.history_counter]
+            train_y = self.disturbance_history['disturbance'][:self.history_counter]
+        else:
+            train_x = self.disturbance_history['state']
+            train_y = self.disturbance_history['disturbance']
+        self._install_gp_bank(np.array(train_x), np.array(train_y))
+        self._gp_bank.train(training_iter)
+        self._gp_bank.build_posterior()
+
+    def _install_gp_bank(self, train_x, train_y):
+        from .gp_model import DisturbanceGPBank, BankMember
+        train_x_std = np.std(train_x, axis=0)
+        train_y_std = np.std(train_y, axis=0)
+        with np.errstate(divide='ignore'):
+            x_scale = train_x_std + 0.0                      # predict divides by std_x WITHOUT the 1e-8 (dynamics.py:375)
+        self._gp_bank = DisturbanceGPBank(train_x / (train_x_std + 1e-8), train_y / (train_y_std + 1e-8),
+                                          MAX_STD[self.env.dynamics_mode], device=self.device, x_scale=x_scale,
+                                          y_scale=train_y_std + 1e-8)
+        self.disturb_estimators = [BankMember(self._gp_bank, i) for i in range(self.n_s)]
+        self.train_x = train_x
+        self.train_y = train_y
+
+    def load_disturbance_models(self, output):
+        """dynamics.py:393-410.  Reads this class's own files and the reference's (a list of gpytorch state dicts)."""
+        if output is None:
+            return
+        try:
+            weights = torch.load('{}/gp_models.pkl'.format(output), map_location='cpu')
+            train_x = torch.load('{}/gp_models_train_x.pkl'.format(output), weights_only=False)
+            train_y = torch.load('{}/gp_models_train_y.pkl'.format(output), weights_only=False)
+            self._install_gp_bank(np.asarray(train_x, np.float64), np.asarray(train_y, np.float64))
+            for i in range(self.n_s):
+                self.disturb_estimators[i].load_state_dict(weights[i])
+            self._gp_bank.build_posterior()
+        except Exception:
+            raise Exception('Could not load GP models from {}'.format(output))
+
+    def save_disturbance_models(self, output):
+        """dynamics.py:412-423 (same three files, same gpytorch parameter names)."""
+        if not self.disturb_estimators or self.train_x is None or self.train_y is None:
+            return
+        torch.save([est.state_dict() for est in self.disturb_estimators], '{}/gp_models.pkl'.format(output))
+        torch.save(self.train_x, '{}/gp_models_train_x.pkl'.format(output))
+        torch.save(self.train_y, '{}/gp_models_train_y.pkl'.format(output))
 
     def seed(self, s):
         torch.manual_seed(s)
