@@ -219,7 +219,7 @@ int rcbf_cars_safe_step_host(float* state, float* t, int32_t* step, const float*
  *   std     = y_scale_g * sqrt(max(outputscale_g - |w|^2 + include_noise * noise_g, min_variance))   (:100,:379)
  * All arithmetic is float64 (outputscale - |w|^2 cancels ~ n outputscale / noise digits).
  * Device arrays, caller-owned, read-only:
- *   train_z     [n_pad][dim_pad]   normalised training inputs, zero padded; n_pad % 32 == 0, dim_pad in {4, 8, 12, 16}
+ *   train_z     [n_pad][dim_pad]   normalised training inputs, zero padded; n_pad % 64 == 0, dim_pad in {4, 8, 12, 16}
  *   inv_x_scale [dim_pad]          zero beyond n_in
  *   hyp         [n_gp][4]          {inv_2l2, outputscale, noise, y_scale}
  *   r_tiles     [n_gp]             number of tile_rows-wide row tiles of F_g actually used (<= max_tiles)
@@ -232,7 +232,7 @@ typedef struct {
   const int32_t* r_tiles;
   const double* factor;
   const double* proj_y;
-  int32_t n_pad, n_in, dim_pad, n_gp, max_tiles, tile_rows; /* tile_rows in {16, 64} */
+  int32_t n_pad, n_in, dim_pad, n_gp, max_tiles, tile_rows; /* tile_rows in {4, 8, 16, 64} */
   int32_t include_noise;                                    /* 1: 'f_var' as the reference returns it (gp_model.py:100) */
   double min_variance;                                      /* gpytorch float32 clamp: 1e-6 */
 } rcbf_gp_posterior;

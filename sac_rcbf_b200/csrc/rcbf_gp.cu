@@ -11,7 +11,9 @@
 //      shared memory -- K* is never written to HBM;
 //   3. a register-tiled float64 rank-32 update  W[r][t] += F^T[c][r] * k[c][t]  ((tile_rows / 16) x 4 per thread).
 // After the last chunk the block reduces |W[:, t]|^2 and W[:, t] . proj_y and writes mean / std of its 32 test points.
-// Factors with more rows than one tile are walked tile by tile (the kernel block is recomputed per tile: with 64 rows
+// That kernel serves factors with 64-row tiles (kernels that are not numerically low rank); k_gp_predict_lowrank below
+// serves 4 / 8 / 16-row tiles.  Factors with more rows than one tile are walked tile by tile (the kernel block is
+// recomputed per tile: with 64 rows
 // per tile the exps cost about as much as the FMAs, so nothing is gained by spilling K* to HBM).
 #include <cstdint>
 
@@ -168,14 +170,133 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_predict(rcbf_gp_posterior p, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Low-rank variant (factor row tiles of R = 4 / 8 / 16 rows -- the reference's pinned lengthscale 1e5 gives rank <= 4
+// for the Unicycle and ~11 for SimulatedCars): no K* staging at all.  Block = 32 test points x 8 warps; each warp
+// takes 8 of the 64 training points of a chunk, a lane evaluates k(z_c, z*_lane) and immediately folds it into its
+// R private accumulators  w[r] += F^T[c][r] * k  (F^T[c][.] is a shared-memory broadcast).  One barrier per chunk
+// (stage release); the 8 partial w's are summed through shared memory once per row tile.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kLrWarps = 8;
+constexpr int kLrChunk = 64;
+constexpr int kLrPerWarp = kLrChunk / kLrWarps;
+
+template <int R, int DP>
+struct GpLrSmem {
+  double fac[2][kLrChunk * R];
+  double z[2][kLrChunk * DP];
+  double red[kLrWarps][R][kGpTile];
+  uint64_t bar[2];
+};
+
+template <int R, int DP, typename T>
+__global__ void __launch_bounds__(kLrWarps * 32) k_gp_predict_lowrank(rcbf_gp_posterior p, const T* __restrict__ test_x,
+                                                                      int64_t n_test, T* __restrict__ mean,
+                                                                      T* __restrict__ sd) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  GpLrSmem<R, DP>& sh = *reinterpret_cast<GpLrSmem<R, DP>*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gp = blockIdx.y;
+  const int64_t t0 = (int64_t)blockIdx.x * kGpTile;
+  const double inv_2l2 = p.hyp[gp * 4 + 0], os = p.hyp[gp * 4 + 1], noise = p.hyp[gp * 4 + 2],
+               y_scale = p.hyp[gp * 4 + 3];
+  const int n_chunks = p.n_pad / kLrChunk;
+  const int r_tiles = p.r_tiles[gp];
+  const int total = r_tiles * n_chunks;
+  const double* fac_gp = p.factor + (size_t)gp * p.max_tiles * p.n_pad * R;
+  const double* py_gp = p.proj_y + (size_t)gp * p.max_tiles * R;
+
+  if (tid == 0) {
+    mbar_init(&sh.bar[0], 1);
+    mbar_init(&sh.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int it) {  // thread 0 only
+    const int rt = it / n_chunks, ch = it - rt * n_chunks, s = it & 1;
+    constexpr uint32_t fac_bytes = kLrChunk * R * 8, z_bytes = kLrChunk * DP * 8;
+    mbar_expect_tx(&sh.bar[s], fac_bytes + z_bytes);
+    bulk_g2s(sh.fac[s], fac_gp + ((size_t)rt * p.n_pad + (size_t)ch * kLrChunk) * R, fac_bytes, &sh.bar[s]);
+    bulk_g2s(sh.z[s], p.train_z + (size_t)ch * kLrChunk * DP, z_bytes, &sh.bar[s]);
+  };
+  if (tid == 0 && total > 0) issue(0);
+
+  double zt[DP];
+  {
+    const int64_t t = t0 + lane;
+#pragma unroll
+    for (int k = 0; k < DP; ++k)
+      zt[k] = (k < p.n_in && t < n_test) ? (double)test_x[t * p.n_in + k] * p.inv_x_scale[k] : 0.0;
+  }
+  double w[R];
+  double q = 0.0, m = 0.0;  // meaningful in warp 0 only
+
+  for (int it = 0; it < total; ++it) {
+    const int rt = it / n_chunks, ch = it - rt * n_chunks, s = it & 1;
+    if (ch == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = 0.0;
+    }
+    if (tid == 0 && it + 1 < total) issue(it + 1);
+    mbar_wait(&sh.bar[s], (it >> 1) & 1);
+#pragma unroll
+    for (int j = 0; j < kLrPerWarp; ++j) {
+      const int c = warp * kLrPerWarp + j;
+      const double* zc = &sh.z[s][c * DP];
+      double d2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) {
+        const double d = zc[k] - zt[k];
+        d2 = fma(d, d, d2);
+      }
+      const double kv = os * exp(-d2 * inv_2l2);
+      const double* fc = &sh.fac[s][c * R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) w[r] = fma(fc[r], kv, w[r]);
+    }
+    if (ch == n_chunks - 1) {  // row tile finished: sum the 8 partial w's, fold into |w|^2 and w . proj_y
+#pragma unroll
+      for (int r = 0; r < R; ++r) sh.red[warp][r][lane] = w[r];
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          double ws = 0.0;
+#pragma unroll
+          for (int v = 0; v < kLrWarps; ++v) ws += sh.red[v][r][lane];
+          q = fma(ws, ws, q);
+          m = fma(ws, py_gp[rt * R + r], m);
+        }
+      }
+    }
+    __syncthreads();  // releases stage s (and sh.red) for reuse
+  }
+  if (warp == 0) {
+    const int64_t t = t0 + lane;
+    if (t < n_test) {
+      double var = os - q + (p.include_noise ? noise : 0.0);
+      var = var > p.min_variance ? var : p.min_variance;
+      if (q != q) var = q;  // keep a NaN visible instead of clamping it away
+      mean[t * p.n_gp + gp] = (T)(m * y_scale);
+      sd[t * p.n_gp + gp] = (T)(sqrt(var) * y_scale);
+    }
+  }
+}
+
 template <int RT, int DP, typename T>
 int launch_gp_one(const rcbf_gp_posterior& p, const T* test_x, int64_t n_test, T* mean, T* sd, cudaStream_t s) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  const int smem = (int)sizeof(GpSmem<RT, DP>);
+  constexpr bool kLowRank = RT <= 16;
+  const int smem = kLowRank ? (int)sizeof(GpLrSmem<kLowRank ? RT : 16, DP>) : (int)sizeof(GpSmem<RT, DP>);
   if (dev >= 0 && dev < 64 && !attr_done[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(k_gp_predict<RT, DP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e;
+    if constexpr (kLowRank)
+      e = cudaFuncSetAttribute(k_gp_predict_lowrank<RT, DP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    else
+      e = cudaFuncSetAttribute(k_gp_predict<RT, DP, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return (int)e;
     attr_done[dev] = true;
   }
@@ -185,8 +306,12 @@ int launch_gp_one(const rcbf_gp_posterior& p, const T* test_x, int64_t n_test, T
     const int64_t now = tiles - done < (1 << 24) ? tiles - done : (1 << 24);
     dim3 grid((unsigned)now, (unsigned)p.n_gp);
     const int64_t off = done * kGpTile;
-    k_gp_predict<RT, DP, T><<<grid, kGpThreads, smem, s>>>(p, test_x + off * p.n_in, n_test - off,
-                                                          mean + off * p.n_gp, sd + off * p.n_gp);
+    if constexpr (kLowRank)
+      k_gp_predict_lowrank<RT, DP, T><<<grid, kLrWarps * 32, smem, s>>>(p, test_x + off * p.n_in, n_test - off,
+                                                                       mean + off * p.n_gp, sd + off * p.n_gp);
+    else
+      k_gp_predict<RT, DP, T><<<grid, kGpThreads, smem, s>>>(p, test_x + off * p.n_in, n_test - off,
+                                                            mean + off * p.n_gp, sd + off * p.n_gp);
     done += now;
   }
   return (int)cudaGetLastError();
@@ -196,13 +321,21 @@ template <typename T>
 int launch_gp(const rcbf_gp_posterior* ph, const T* test_x, int64_t n_test, T* mean, T* sd, void* stream) {
   if (!ph || n_test < 0) return (int)cudaErrorInvalidValue;
   const rcbf_gp_posterior& p = *ph;
-  if (p.n_pad <= 0 || p.n_pad % kGpChunk || p.n_in <= 0 || p.n_in > p.dim_pad || p.n_gp <= 0 || p.n_gp > 65535 ||
+  if (p.n_pad <= 0 || p.n_pad % kLrChunk || p.n_in <= 0 || p.n_in > p.dim_pad || p.n_gp <= 0 || p.n_gp > 65535 ||
       p.max_tiles <= 0)
     return (int)cudaErrorInvalidValue;
   if (n_test == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;
 #define RCBF_GP_CASE(RT, DP) \
   if (p.tile_rows == RT && p.dim_pad == DP) return launch_gp_one<RT, DP, T>(p, test_x, n_test, mean, sd, s);
+  RCBF_GP_CASE(4, 4)
+  RCBF_GP_CASE(4, 8)
+  RCBF_GP_CASE(4, 12)
+  RCBF_GP_CASE(4, 16)
+  RCBF_GP_CASE(8, 4)
+  RCBF_GP_CASE(8, 8)
+  RCBF_GP_CASE(8, 12)
+  RCBF_GP_CASE(8, 16)
   RCBF_GP_CASE(16, 4)
   RCBF_GP_CASE(16, 8)
   RCBF_GP_CASE(16, 12)

@@ -28,7 +28,7 @@ NOISE_LOWER = 1e-4           # gpytorch GaussianLikelihood: GreaterThan(1e-4)
 MIN_VARIANCE = 1e-6          # gpytorch.settings.min_variance for float32 (the dtype the reference predicts in)
 LENGTHSCALE_INIT = 1e5       # gp_model.py:21
 PRIOR_SIGMA = 1e-5           # gp_model.py:18,20
-_CHUNK = 32                  # kGpChunk in csrc/rcbf_gp.cu
+_CHUNK = 64                  # kLrChunk in csrc/rcbf_gp.cu (a multiple of kGpChunk)
 
 
 def _inv_softplus(v):
@@ -177,7 +177,7 @@ class DisturbanceGPBank:
             factors.append(f)
             projs.append(f @ y)
         max_rank = max(f.shape[0] for f in factors)
-        tile_rows = 16 if max_rank <= 48 else 64
+        tile_rows = 4 if max_rank <= 4 else 8 if max_rank <= 8 else 16 if max_rank <= 48 else 64
         max_tiles = (max_rank + tile_rows - 1) // tile_rows
         factor = torch.zeros(self.n_gp, max_tiles, n_pad, tile_rows, **f64)
         proj_y = torch.zeros(self.n_gp, max_tiles * tile_rows, **f64)
