@@ -235,6 +235,18 @@ typedef struct {
   int32_t n_pad, n_in, dim_pad, n_gp, max_tiles, tile_rows; /* tile_rows in {4, 8, 16, 64} */
   int32_t include_noise;                                    /* 1: 'f_var' as the reference returns it (gp_model.py:100) */
   double min_variance;                                      /* gpytorch float32 clamp: 1e-6 */
+  /* far-field fast path (optional, ff_coef == NULL disables it; needs max_tiles == 1): when every
+   * a_j = |z* - z_j|^2 * inv_2l2 is tiny -- the reference pins the lengthscale at 1e5 (gp_model.py:18-21), a ~ 1e-8 --
+   * exp(-a) = 1 - a + a^2/2 to float64 accuracy and w = F k* collapses to a quadratic-in-(z*, |z*|^2) polynomial whose
+   * coefficients the host sums once:  O(rank * n_in^2) per test point instead of O(n * rank).
+   *   ff_coef [n_gp][tile_rows][3 + 2 dim_pad + dim_pad (dim_pad + 1) / 2]:  w_r = c0 + s (c1 + s c2)
+   *            + sum_k z*_k (lin_k + s slin_k) + sum_{k<=l} quad_kl z*_k z*_l,   s = |z*|^2
+   *   ff_amax [n_gp]: a test point may use the polynomial for GP g iff (|z*| + ff_zmax)^2 * inv_2l2_g <= ff_amax[g]
+   *            (the host derives it from the a^3/6 remainder so that mean / variance move by < 1e-9 relative);
+   *            other points are evaluated exactly by the same kernel (their warp sums over the training set). */
+  const double* ff_coef;
+  const double* ff_amax;
+  double ff_zmax; /* max_j |z_j| */
 } rcbf_gp_posterior;
 
 /* test_x (n_test, n_in) row-major -> mean, std (n_test, n_gp) row-major, same scalar type as test_x. */

@@ -38,6 +38,9 @@ class GpPosterior(C.Structure):  # rcbf_gp_posterior
         ("tile_rows", C.c_int32),
         ("include_noise", C.c_int32),
         ("min_variance", C.c_double),
+        ("ff_coef", C.c_void_p),
+        ("ff_amax", C.c_void_p),
+        ("ff_zmax", C.c_double),
     ]
 
 

@@ -284,12 +284,119 @@ __global__ void __launch_bounds__(kLrWarps * 32) k_gp_predict_lowrank(rcbf_gp_po
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Far-field fast path (see rcbf_gp_posterior::ff_coef): one lane per test point, no loop over the training set.
+// Lanes whose point fails the validity bound are finished exactly by their warp: the 32 lanes split the training
+// set, evaluate the kernel and F k* for that one point and shuffle-reduce -- same float64 arithmetic as the kernels
+// above, so a bank whose test points are all "near" is merely slower, never wrong.
+// ---------------------------------------------------------------------------------------------------------------
+template <int R, int DP, typename T>
+__global__ void __launch_bounds__(128) k_gp_farfield(rcbf_gp_posterior p, const T* __restrict__ test_x, int64_t n_test,
+                                                     T* __restrict__ mean, T* __restrict__ sd) {
+  constexpr int NC = 3 + 2 * DP + DP * (DP + 1) / 2;
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int64_t n_tiles = (n_test + 31) / 32;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
+    const int64_t t = tile * 32 + lane;
+    const bool valid = t < n_test;
+    double zt[DP];
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DP; ++k) {
+      zt[k] = (k < p.n_in && valid) ? (double)test_x[t * p.n_in + k] * __ldg(p.inv_x_scale + k) : 0.0;
+      s = fma(zt[k], zt[k], s);
+    }
+    const double reach = sqrt(s) + p.ff_zmax;
+    for (int g = 0; g < p.n_gp; ++g) {
+      const double inv_2l2 = __ldg(p.hyp + g * 4 + 0), os = __ldg(p.hyp + g * 4 + 1), noise = __ldg(p.hyp + g * 4 + 2),
+                   y_scale = __ldg(p.hyp + g * 4 + 3);
+      const double* py = p.proj_y + (size_t)g * R;
+      const bool far = reach * reach * inv_2l2 <= __ldg(p.ff_amax + g);
+      double q = 0.0, m = 0.0;
+      const double* cf = p.ff_coef + (size_t)g * R * NC;
+      for (int r = 0; r < R; ++r) {
+        const double* c = cf + r * NC;
+        double w = fma(s, fma(s, __ldg(c + 2), __ldg(c + 1)), __ldg(c));
+#pragma unroll
+        for (int k = 0; k < DP; ++k) w = fma(zt[k], fma(s, __ldg(c + 3 + DP + k), __ldg(c + 3 + k)), w);
+        int idx = 3 + 2 * DP;
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          double row = 0.0;
+#pragma unroll
+          for (int l = k; l < DP; ++l) row = fma(zt[l], __ldg(c + idx++), row);
+          w = fma(zt[k], row, w);
+        }
+        q = fma(w, w, q);
+        m = fma(w, __ldg(py + r), m);
+      }
+      unsigned near = __ballot_sync(kFull, valid && !far);
+      while (near) {  // exact evaluation of one point by the whole warp
+        const int src = __ffs(near) - 1;
+        near &= near - 1;
+        double zs[DP];
+#pragma unroll
+        for (int k = 0; k < DP; ++k) zs[k] = __shfl_sync(kFull, zt[k], src);
+        double w[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) w[r] = 0.0;
+        const double* fac = p.factor + (size_t)g * p.max_tiles * p.n_pad * R;
+        for (int j = lane; j < p.n_pad; j += 32) {
+          double d2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < DP; ++k) {
+            const double d = __ldg(p.train_z + (size_t)j * DP + k) - zs[k];
+            d2 = fma(d, d, d2);
+          }
+          const double kv = os * exp(-d2 * inv_2l2);
+#pragma unroll
+          for (int r = 0; r < R; ++r) w[r] = fma(__ldg(fac + (size_t)j * R + r), kv, w[r]);
+        }
+        double qe = 0.0, me = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) w[r] += __shfl_xor_sync(kFull, w[r], o);
+          qe = fma(w[r], w[r], qe);
+          me = fma(w[r], __ldg(py + r), me);
+        }
+        if (lane == src) {
+          q = qe;
+          m = me;
+        }
+      }
+      if (valid) {
+        double var = os - q + (p.include_noise ? noise : 0.0);
+        var = var > p.min_variance ? var : p.min_variance;
+        if (q != q) var = q;
+        mean[t * p.n_gp + g] = (T)(m * y_scale);
+        sd[t * p.n_gp + g] = (T)(sqrt(var) * y_scale);
+      }
+    }
+  }
+}
+
+template <int R, int DP, typename T>
+int launch_gp_farfield(const rcbf_gp_posterior& p, const T* test_x, int64_t n_test, T* mean, T* sd, cudaStream_t s) {
+  const int64_t tiles = (n_test + 31) / 32;
+  const int64_t want = (tiles + 3) / 4;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  k_gp_farfield<R, DP, T><<<grid, 128, 0, s>>>(p, test_x, n_test, mean, sd);
+  return (int)cudaGetLastError();
+}
+
 template <int RT, int DP, typename T>
 int launch_gp_one(const rcbf_gp_posterior& p, const T* test_x, int64_t n_test, T* mean, T* sd, cudaStream_t s) {
   static bool attr_done[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   constexpr bool kLowRank = RT <= 16;
+  if constexpr (kLowRank) {
+    if (p.ff_coef && p.ff_amax && p.max_tiles == 1) return launch_gp_farfield<RT, DP, T>(p, test_x, n_test, mean, sd, s);
+  }
   const int smem = kLowRank ? (int)sizeof(GpLrSmem<kLowRank ? RT : 16, DP>) : (int)sizeof(GpSmem<RT, DP>);
   if (dev >= 0 && dev < 64 && !attr_done[dev]) {
     cudaError_t e;

@@ -70,6 +70,8 @@ class DisturbanceGPBank:
         self.x_scale = torch.ones(self.d, **f64) if x_scale is None else torch.as_tensor(x_scale).to(**f64)
         self.y_scale = torch.ones(self.n_gp, **f64) if y_scale is None else torch.as_tensor(y_scale).to(**f64)
         self.include_noise = True
+        self.far_field = True       # allow the far-field polynomial path when the bank qualifies (build_posterior)
+        self.far_field_active = False
         self._post = None
 
     # ---------------------------------------------------------------------------------------------- hyper-parameters
@@ -176,7 +178,8 @@ class DisturbanceGPBank:
             f = q[:, :chosen].t() / torch.sqrt(lam[:chosen].clamp_min(0.0) + s2)[:, None]
             factors.append(f)
             projs.append(f @ y)
-        max_rank = max(f.shape[0] for f in factors)
+        self.ranks = [f.shape[0] for f in factors]
+        max_rank = max(self.ranks)
         tile_rows = 4 if max_rank <= 4 else 8 if max_rank <= 8 else 16 if max_rank <= 48 else 64
         max_tiles = (max_rank + tile_rows - 1) // tile_rows
         factor = torch.zeros(self.n_gp, max_tiles, n_pad, tile_rows, **f64)
@@ -196,14 +199,57 @@ class DisturbanceGPBank:
         inv_x = torch.zeros(dim_pad, **f64)
         inv_x[:self.d] = 1.0 / self.x_scale
         hyp = torch.stack([1.0 / (2.0 * self.lengthscale ** 2), self.outputscale, self.noise, self.y_scale], 1)
-        keep = (train_z, inv_x, hyp.contiguous(), r_tiles, factor.contiguous(), proj_y)
-        post = P.GpPosterior(train_z=keep[0].data_ptr(), inv_x_scale=keep[1].data_ptr(), hyp=keep[2].data_ptr(),
+        ff_coef, ff_amax, ff_zmax = self._far_field_tables(train_z, factor, proj_y, hyp, max_tiles, tile_rows, dim_pad)
+        keep = (train_z, inv_x, hyp.contiguous(), r_tiles, factor.contiguous(), proj_y, ff_coef, ff_amax)
+        post = P.GpPosterior(ff_coef=None if ff_coef is None else ff_coef.data_ptr(),
+                             ff_amax=None if ff_amax is None else ff_amax.data_ptr(), ff_zmax=ff_zmax,
+                             train_z=keep[0].data_ptr(), inv_x_scale=keep[1].data_ptr(), hyp=keep[2].data_ptr(),
                              r_tiles=keep[3].data_ptr(), factor=keep[4].data_ptr(), proj_y=keep[5].data_ptr(),
                              n_pad=n_pad, n_in=self.d, dim_pad=dim_pad, n_gp=self.n_gp, max_tiles=max_tiles,
                              tile_rows=tile_rows, include_noise=int(self.include_noise), min_variance=MIN_VARIANCE)
-        self.ranks = [f.shape[0] for f in factors]
         self._post = (post, keep)
         return self
+
+    def _far_field_tables(self, train_z, factor, proj_y, hyp, max_tiles, tile_rows, dim_pad, rel_tol=1e-9):
+        """Coefficients of the second-order far-field expansion (include/rcbf_b200.h, rcbf_gp_posterior::ff_coef) and
+        the per-GP validity bound.  With a_j = inv_2l2 (s - 2 z*.z_j + t_j), s = |z*|^2, t_j = |z_j|^2:
+            w_r = os sum_j F_rj (1 - a_j + a_j^2 / 2),  remainder <= os |F_r|_1 a_max^3 / 6.
+        Returns (None, None, 0) when the fast path is off or not even the training points would qualify."""
+        self.far_field_active = False
+        if not self.far_field or max_tiles != 1 or tile_rows > 16:
+            return None, None, 0.0
+        f64 = dict(dtype=torch.float64, device=self.device)
+        z = train_z                                            # (n_pad, dim_pad), zero rows beyond n
+        t = (z * z).sum(1)
+        zmax = float(t.max().sqrt())
+        nc = 3 + 2 * dim_pad + dim_pad * (dim_pad + 1) // 2
+        coef = torch.zeros(self.n_gp, tile_rows, nc, **f64)
+        amax = torch.zeros(self.n_gp, **f64)
+        iu = torch.triu_indices(dim_pad, dim_pad).to(self.device)
+        offdiag = (iu[0] != iu[1]).to(torch.float64) + 1.0     # symmetric matrix folded onto k <= l
+        for g in range(self.n_gp):
+            i2, os_, noise = hyp[g, 0], hyp[g, 1], hyp[g, 2]
+            f = factor[g, 0].t()                               # (tile_rows, n_pad)
+            s0, s1, s2 = f.sum(1), f @ t, f @ (t * t)
+            v0, v1 = f @ z, f @ (z * t[:, None])
+            mm = torch.einsum("rj,jk,jl->rkl", f, z, z)
+            coef[g, :, 0] = os_ * (s0 - i2 * s1 + 0.5 * i2 * i2 * s2)
+            coef[g, :, 1] = os_ * (-i2 * s0 + i2 * i2 * s1)
+            coef[g, :, 2] = os_ * 0.5 * i2 * i2 * s0
+            coef[g, :, 3:3 + dim_pad] = os_[None, None] * (2.0 * i2 * v0 - 2.0 * i2 * i2 * v1)
+            coef[g, :, 3 + dim_pad:3 + 2 * dim_pad] = os_ * (-2.0 * i2 * i2) * v0
+            coef[g, :, 3 + 2 * dim_pad:] = os_ * 2.0 * i2 * i2 * mm[:, iu[0], iu[1]] * offdiag
+            rows = max(1, self.ranks[g])
+            e_g = os_ * f.abs().sum(1).max()
+            y = self.train_y[:, g]
+            tol_w = rel_tol * torch.minimum(noise / (2.0 * os_.sqrt() * rows),
+                                            (y.abs().max() + 1e-300) / (proj_y[g].abs().sum() + 1e-300))
+            amax[g] = (6.0 * tol_w / (e_g + 1e-300)) ** (1.0 / 3.0)
+        a_train = (2.0 * zmax) ** 2 * hyp[:, 0]
+        if bool((a_train > amax).any()):
+            return None, None, 0.0
+        self.far_field_active = True
+        return coef.contiguous(), amax, zmax
 
     # ---------------------------------------------------------------------------------------------- prediction
     def predict(self, test_x):

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import gp_oracle as G
-from tests.gp_sim import eval_packed
+from tests.gp_sim import eval_far_field, eval_packed
 
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "gp_disturbance.npz"))
 MAX_STD = {"unicycle": [0.2] * 3, "simulatedcars": [0, 0.2] * 5}
@@ -88,6 +88,26 @@ def test_packed_posterior_matches_oracle(mode):
     assert np.allclose(std, GOLD[mode + "_std"], rtol=1e-7, atol=0)
 
 
+@pytest.mark.parametrize("mode", ["unicycle", "simulatedcars"])
+def test_far_field_tables_match_oracle_and_gate_distant_points(mode):
+    """The second-order far-field polynomial the host tabulates (what k_gp_farfield evaluates) reproduces the oracle on
+    the golden test points, all of which pass the validity bound; points 400x farther out must be refused by it."""
+    bank = _bank(mode, train=False)
+    bank.raw = torch.as_tensor(GOLD[mode + "_raw"]).clone()
+    bank.build_posterior()
+    assert bank.far_field_active
+    mean, std, ok = eval_far_field(bank, GOLD[mode + "_test_x"])
+    assert ok.all()
+    scale = np.abs(GOLD[mode + "_train_y"]).max(0) + 1e-300
+    assert np.all(np.abs(mean - GOLD[mode + "_mean"]) <= 1e-8 * scale)
+    assert np.allclose(std, GOLD[mode + "_std"], rtol=1e-9, atol=0)
+    _, _, ok_far = eval_far_field(bank, 400.0 * GOLD[mode + "_test_x"])
+    assert not ok_far[:, -1].any()      # (GPs with a ~zero outputscale keep a much wider bound: checked per GP)
+    bank.far_field = False
+    bank.build_posterior()
+    assert not bank.far_field_active and not bank._post[0].ff_coef
+
+
 def test_packed_posterior_moderate_lengthscale_keeps_enough_rank():
     """A kernel that is NOT low rank (lengthscale ~ data spread): the validated truncation must keep what the dense
     solve needs (here it ends up using most or all of the n rows) and still match the oracle."""
@@ -101,7 +121,7 @@ def test_packed_posterior_moderate_lengthscale_keeps_enough_rank():
     test = rng.uniform(-2.5, 2.5, (60, 3))
     p = gp.predict(test)
     mean, std = eval_packed(bank, test)
-    assert bank._post[0].tile_rows == 64 and bank.ranks[0] > 48
+    assert bank._post[0].tile_rows == 64 and bank.ranks[0] > 48 and not bank.far_field_active
     assert np.allclose(mean[:, 0], p["mean"], rtol=0, atol=1e-7 * np.abs(y).max())
     assert np.allclose(std[:, 0] ** 2, p["f_var"], rtol=1e-7)
 

@@ -43,6 +43,37 @@ def test_fit_and_predict_match_oracle_on_golden_history(mode):
     assert np.allclose(std32.cpu().numpy(), GOLD[mode + "_std"], rtol=2e-6, atol=0)
 
 
+@pytest.mark.parametrize("mode", ["unicycle", "simulatedcars"])
+def test_far_field_path_agrees_with_exact_kernels_and_falls_back_per_point(mode):
+    """At the reference's lengthscale the bank qualifies for the far-field polynomial (rcbf_gp_posterior::ff_coef).
+    (i) it must agree with the exact low-rank kernel (far_field = False) far below the parity tolerance;
+    (ii) points outside its validity bound (here: 50x farther out, interleaved with ordinary points so both kinds share
+    warps) are finished exactly inside the same launch."""
+    bank = _bank(mode)
+    bank.raw = torch.as_tensor(GOLD[mode + "_raw"]).cuda().clone()
+    bank.build_posterior()
+    assert bank.far_field_active and bank._post[0].ff_coef
+    exact = _bank(mode)
+    exact.raw = bank.raw.clone()
+    exact.far_field = False
+    exact.build_posterior()
+    assert not exact.far_field_active and not exact._post[0].ff_coef
+    test = np.repeat(GOLD[mode + "_test_x"], 3, axis=0)
+    test[1::3] *= 50.0
+    test[2::7] *= -400.0
+    x = torch.as_tensor(test).cuda()
+    (m_ff, s_ff), (m_ex, s_ex) = bank.predict(x), exact.predict(x)
+    scale = torch.as_tensor(np.abs(GOLD[mode + "_train_y"]).max(0) + 1e-300).cuda()
+    assert float(((m_ff - m_ex).abs() / scale).max()) <= 2e-9
+    assert float(((s_ff - s_ex).abs() / s_ex).max()) <= 2e-9
+    ora = G.DisturbanceGPs(GOLD[mode + "_train_x"], GOLD[mode + "_train_y"], MAX_STD[mode], training_iter=0)
+    for g, raw in zip(ora.gps, GOLD[mode + "_raw"]):
+        g.raw = raw.copy()
+    om, os_ = ora.predict_disturbance(test)
+    assert np.all(np.abs(m_ff.cpu().numpy() - om) <= 1e-7 * scale.cpu().numpy())
+    assert np.allclose(s_ff.cpu().numpy(), os_, rtol=1e-7, atol=0)
+
+
 @pytest.mark.parametrize("n_test", [1, 31, 33, 1000])
 def test_ragged_batches_and_unpadded_training_sets(n_test):
     """n = 117 training points (not a multiple of the 32-point chunk), batches that do not fill a 32-point tile."""
