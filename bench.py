@@ -348,6 +348,45 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     ms = _time_calls(lambda: layc.get_safe_action(stc[:b], acc[:b], muc[:b], sgc[:b]), 50, device)
     out["config2_cars_b512_fwd_us"] = 1e3 * ms
     layer.check_nan = True
+    # (d) SURVEY 8f row 1: disturbance-GP posterior in front of the same step.  History = 3000 transitions (the
+    # reference's --gp_model_size, main.py:247) of the Unicycle's true drag disturbance (unicycle_env.py:87) + noise;
+    # hyper-parameters = where the reference's 70 Adam steps end (lengthscale pinned at 1e5 by its prior, noise ~ 1 in
+    # normalised units; the fit itself is timed by scripts/gpu_gp.py, it is not on the per-step path).
+    import time as _time
+    from sac_rcbf_b200.gp_model import DisturbanceGPBank
+    rng = np.random.default_rng(12345)
+    nt = 3000
+    hx = np.stack([rng.uniform(-3, 3, nt), rng.uniform(-3, 3, nt), rng.uniform(-np.pi, np.pi, nt)], 1)
+    hy = np.stack([-0.1 * np.cos(hx[:, 2]) ** 2, -0.1 * np.sin(hx[:, 2]) * np.cos(hx[:, 2]), np.zeros(nt)], 1)
+    hy = hy + 1e-3 * rng.standard_normal(hy.shape)
+    xs, ys = hx.std(0), hy.std(0)
+    bank = DisturbanceGPBank(hx / (xs + 1e-8), hy / (ys + 1e-8), [0.2] * 3, device=device, x_scale=xs, y_scale=ys + 1e-8)
+    bank.set_hyperparameters(noise=[1.0, 1.0, 1.0])
+    t0 = _time.time()
+    bank.build_posterior()
+    torch.cuda.synchronize(device)
+    factor_s = _time.time() - t0
+    state_view = env._state4[:, :3]                     # float4 env state read in place (row stride 4)
+    ms_ff = _time_calls(lambda: bank.predict(state_view), 5, device)
+    gp_out = {}
+
+    def gp_step():
+        gp_out["m"], gp_out["s"] = bank.predict(state_view)
+        env.safe_step(layer, u, gp_out["m"], gp_out["s"])
+
+    ms_pipe = _time_calls(gp_step, 5, device)
+    ff_active, ranks = bank.far_field_active, list(bank.ranks)
+    bank.far_field = False
+    bank.build_posterior()
+    nsub = min(n, 1 << 18)
+    sub = state_view[:nsub]
+    ms_ex = _time_calls(lambda: bank.predict(sub), 3, device)
+    out["gp_posterior"] = {
+        "train_points": nt, "gps": 3, "ranks": ranks, "factor_build_s": factor_s, "far_field_active": bool(ff_active),
+        "far_field": {"value": n / (ms_ff * 1e-3), "unit": "test points/s", "instances": n, "ms": ms_ff},
+        "exact_lowrank": {"value": nsub / (ms_ex * 1e-3), "unit": "test points/s", "instances": nsub, "ms": ms_ex},
+        "safe_step_with_gp": {"value": n / (ms_pipe * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_pipe,
+                              "note": "GP posterior kernel (state -> mean, std) + fused safe step, 2 launches"}}
     return out
 
 

@@ -247,6 +247,8 @@ typedef struct {
   const double* ff_coef;
   const double* ff_amax;
   double ff_zmax; /* max_j |z_j| */
+  int64_t test_stride; /* elements between consecutive test_x rows; 0 = n_in (dense).  Lets the float4 env state
+                        * (x, y, theta, last_goal_dist) of rcbf_unicycle_env_step_f32 be read in place with stride 4 */
 } rcbf_gp_posterior;
 
 /* test_x (n_test, n_in) row-major -> mean, std (n_test, n_gp) row-major, same scalar type as test_x. */

@@ -41,6 +41,7 @@ class GpPosterior(C.Structure):  # rcbf_gp_posterior
         ("ff_coef", C.c_void_p),
         ("ff_amax", C.c_void_p),
         ("ff_zmax", C.c_double),
+        ("test_stride", C.c_int64),
     ]
 
 

@@ -48,6 +48,7 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_predict(rcbf_gp_posterior p, 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gp = blockIdx.y;
   const int64_t t0 = (int64_t)blockIdx.x * kGpTile;
+  const int64_t xs = p.test_stride ? p.test_stride : p.n_in;
 
   const double inv_2l2 = p.hyp[gp * 4 + 0], os = p.hyp[gp * 4 + 1], noise = p.hyp[gp * 4 + 2],
                y_scale = p.hyp[gp * 4 + 3];
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kGpThreads) k_gp_predict(rcbf_gp_posterior p, 
     const int64_t t = t0 + lane;
 #pragma unroll
     for (int k = 0; k < DP; ++k)
-      zt[k] = (k < p.n_in && t < n_test) ? (double)test_x[t * p.n_in + k] * p.inv_x_scale[k] : 0.0;
+      zt[k] = (k < p.n_in && t < n_test) ? (double)test_x[t * xs + k] * p.inv_x_scale[k] : 0.0;
   }
 
   const int tr = tid >> 3, tt = tid & 7;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) k_gp_predict_lowrank(rcbf_gp_po
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gp = blockIdx.y;
   const int64_t t0 = (int64_t)blockIdx.x * kGpTile;
+  const int64_t xs = p.test_stride ? p.test_stride : p.n_in;
   const double inv_2l2 = p.hyp[gp * 4 + 0], os = p.hyp[gp * 4 + 1], noise = p.hyp[gp * 4 + 2],
                y_scale = p.hyp[gp * 4 + 3];
   const int n_chunks = p.n_pad / kLrChunk;
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(kLrWarps * 32) k_gp_predict_lowrank(rcbf_gp_po
     const int64_t t = t0 + lane;
 #pragma unroll
     for (int k = 0; k < DP; ++k)
-      zt[k] = (k < p.n_in && t < n_test) ? (double)test_x[t * p.n_in + k] * p.inv_x_scale[k] : 0.0;
+      zt[k] = (k < p.n_in && t < n_test) ? (double)test_x[t * xs + k] * p.inv_x_scale[k] : 0.0;
   }
   double w[R];
   double q = 0.0, m = 0.0;  // meaningful in warp 0 only
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(128) k_gp_farfield(rcbf_gp_posterior p, const 
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int64_t n_tiles = (n_test + 31) / 32;
+  const int64_t xs = p.test_stride ? p.test_stride : p.n_in;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
     const int64_t t = tile * 32 + lane;
@@ -306,7 +309,7 @@ __global__ void __launch_bounds__(128) k_gp_farfield(rcbf_gp_posterior p, const 
     double s = 0.0;
 #pragma unroll
     for (int k = 0; k < DP; ++k) {
-      zt[k] = (k < p.n_in && valid) ? (double)test_x[t * p.n_in + k] * __ldg(p.inv_x_scale + k) : 0.0;
+      zt[k] = (k < p.n_in && valid) ? (double)test_x[t * xs + k] * __ldg(p.inv_x_scale + k) : 0.0;
       s = fma(zt[k], zt[k], s);
     }
     const double reach = sqrt(s) + p.ff_zmax;
@@ -414,10 +417,10 @@ int launch_gp_one(const rcbf_gp_posterior& p, const T* test_x, int64_t n_test, T
     dim3 grid((unsigned)now, (unsigned)p.n_gp);
     const int64_t off = done * kGpTile;
     if constexpr (kLowRank)
-      k_gp_predict_lowrank<RT, DP, T><<<grid, kLrWarps * 32, smem, s>>>(p, test_x + off * p.n_in, n_test - off,
+      k_gp_predict_lowrank<RT, DP, T><<<grid, kLrWarps * 32, smem, s>>>(p, test_x + off * (p.test_stride ? p.test_stride : p.n_in), n_test - off,
                                                                        mean + off * p.n_gp, sd + off * p.n_gp);
     else
-      k_gp_predict<RT, DP, T><<<grid, kGpThreads, smem, s>>>(p, test_x + off * p.n_in, n_test - off,
+      k_gp_predict<RT, DP, T><<<grid, kGpThreads, smem, s>>>(p, test_x + off * (p.test_stride ? p.test_stride : p.n_in), n_test - off,
                                                             mean + off * p.n_gp, sd + off * p.n_gp);
     done += now;
   }
@@ -429,7 +432,7 @@ int launch_gp(const rcbf_gp_posterior* ph, const T* test_x, int64_t n_test, T* m
   if (!ph || n_test < 0) return (int)cudaErrorInvalidValue;
   const rcbf_gp_posterior& p = *ph;
   if (p.n_pad <= 0 || p.n_pad % kLrChunk || p.n_in <= 0 || p.n_in > p.dim_pad || p.n_gp <= 0 || p.n_gp > 65535 ||
-      p.max_tiles <= 0)
+      p.max_tiles <= 0 || (p.test_stride != 0 && p.test_stride < p.n_in))
     return (int)cudaErrorInvalidValue;
   if (n_test == 0) return 0;
   cudaStream_t s = (cudaStream_t)stream;

@@ -253,7 +253,8 @@ class DisturbanceGPBank:
 
     # ---------------------------------------------------------------------------------------------- prediction
     def predict(self, test_x):
-        """test_x (B, d) float32 / float64 device tensor -> (mean, std), each (B, n_gp), same dtype, on the device."""
+        """test_x (B, d) float32 / float64 device tensor -> (mean, std), each (B, n_gp), same dtype, on the device.
+        A row-strided view with unit column stride (e.g. `env._state4[:, :3]`) is read in place."""
         if self.device.type != "cuda":
             raise _lib.RcbfLibraryError("GP prediction runs in the CUDA kernel only (no CPU fallback); bank is on %s"
                                         % self.device)
@@ -264,7 +265,10 @@ class DisturbanceGPBank:
         x = test_x.detach()
         if x.dtype not in (torch.float32, torch.float64):
             x = x.float()
-        x = x.to(self.device).reshape(-1, self.d).contiguous()
+        x = x.to(self.device)
+        if not (x.dim() == 2 and x.shape[1] == self.d and x.stride(1) == 1 and x.stride(0) >= self.d):
+            x = x.reshape(-1, self.d).contiguous()
+        post.test_stride = x.stride(0) if x.shape[0] > 1 else self.d
         mean = torch.empty(x.shape[0], self.n_gp, dtype=x.dtype, device=self.device)
         std = torch.empty_like(mean)
         fn = lib.rcbf_gp_predict_f64 if x.dtype == torch.float64 else lib.rcbf_gp_predict_f32

@@ -97,6 +97,21 @@ def test_ragged_batches_and_unpadded_training_sets(n_test):
         assert np.allclose(std[:, g].cpu().numpy() ** 2, p["f_var"], rtol=1e-7)
 
 
+def test_strided_test_points_are_read_in_place():
+    """`env._state4[:, :3]` (row stride 4) must give the same answer as a dense copy, for both kernel families."""
+    bank = _bank("unicycle")
+    bank.raw = torch.as_tensor(GOLD["unicycle_raw"]).cuda().clone()
+    st4 = torch.zeros(77, 4, device="cuda")
+    st4[:, :3] = torch.as_tensor(np.resize(GOLD["unicycle_test_x"], (77, 3)), dtype=torch.float32).cuda()
+    st4[:, 3] = 123.0
+    for ff in (True, False):
+        bank.far_field = ff
+        bank.build_posterior()
+        m0, s0 = bank.predict(st4[:, :3].contiguous())
+        m1, s1 = bank.predict(st4[:, :3])
+        assert torch.equal(m0, m1) and torch.equal(s0, s1)
+
+
 def test_full_rank_factor_path():
     """lengthscale ~ data spread in 3-D: the kernel matrix is far from low rank, the factor keeps (nearly) all n rows
     and the kernel walks several 64-row tiles."""
