@@ -197,3 +197,36 @@ def test_dynamics_model_fits_and_predicts_on_device(mode, tmp_path):
     dm2.load_disturbance_models(str(tmp_path))
     m2, s2 = dm2.predict_disturbance(test)
     assert np.array_equal(m2, m) and np.array_equal(s2, s)
+
+
+def test_model_rollout_transition_uses_the_fitted_gps_on_the_device():
+    """generate_rollouts.py:29-31 with fitted GPs: get_state -> predict_next_state (prior + dt * GP mean, dt * GP std)
+    -> Gaussian sample.  Device tensors in, device tensors out, against the oracle transition fed with the ORACLE's GP
+    posterior at the same states."""
+    import sac_rcbf_b200 as S
+    from oracle import rcbf_oracle as O
+    tx, ty = GOLD["unicycle_train_x"], GOLD["unicycle_train_y"]
+    env = S.build_env(types.SimpleNamespace(env_name="Unicycle"))
+    dm = S.DynamicsModel(env, types.SimpleNamespace(cuda=True, gp_model_size=3000, l_p=0.03))
+    dm._install_gp_bank(tx, ty)
+    dm._gp_bank.raw = torch.as_tensor(GOLD["unicycle_raw"]).cuda().clone()
+    dm._gp_bank.build_posterior()
+    rng = np.random.default_rng(11)
+    B = 300
+    state = GOLD["unicycle_test_x"][rng.integers(0, 40, B)] + 0.01 * rng.standard_normal((B, 3))
+    dist = np.linalg.norm(np.array([2.5, 2.5]) - state[:, :2], axis=1)
+    obs = np.concatenate([state[:, :2], np.cos(state[:, 2:3]), np.sin(state[:, 2:3]), np.zeros((B, 2)),
+                          np.exp(-dist)[:, None]], 1)
+    act = rng.uniform(-1, 1, (B, 2))
+    eps = rng.standard_normal((B, 3))
+    ora = G.DisturbanceGPs(tx, ty, MAX_STD["unicycle"], training_iter=0)
+    for g, raw in zip(ora.gps, GOLD["unicycle_raw"]):
+        g.raw = raw.copy()
+    om, os_ = ora.predict_disturbance(O.get_state("Unicycle", obs))
+    want = O.rollout_step("Unicycle", obs, act, None, eps, mean=om, std=os_)
+    dev = lambda a: torch.as_tensor(a, dtype=torch.float64).cuda()  # noqa: E731
+    got = S.rollout_transition(env, dm, dev(obs), dev(act), None, dev(eps))
+    assert got[0].is_cuda
+    assert np.allclose(got[0].cpu().numpy(), want[0], rtol=0, atol=1e-9)
+    assert np.allclose(got[1].cpu().numpy(), want[1], rtol=0, atol=1e-9)
+    assert np.array_equal(got[2].cpu().numpy(), want[2])
