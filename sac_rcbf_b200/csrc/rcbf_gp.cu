@@ -297,86 +297,117 @@ template <int R, int DP, typename T>
 __global__ void __launch_bounds__(128) k_gp_farfield(rcbf_gp_posterior p, const T* __restrict__ test_x, int64_t n_test,
                                                      T* __restrict__ mean, T* __restrict__ sd) {
   constexpr int NC = 3 + 2 * DP + DP * (DP + 1) / 2;
+  constexpr int P = DP <= 4 ? 4 : 2;  // test points per lane: every coefficient load feeds P FMAs
   constexpr unsigned kFull = 0xffffffffu;
   const int lane = threadIdx.x & 31;
-  const int64_t n_tiles = (n_test + 31) / 32;
+  const int64_t n_tiles = (n_test + 32 * P - 1) / (32 * P);
   const int64_t xs = p.test_stride ? p.test_stride : p.n_in;
   const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t tile = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile < n_tiles; tile += warps) {
-    const int64_t t = tile * 32 + lane;
-    const bool valid = t < n_test;
-    double zt[DP];
-    double s = 0.0;
+    int64_t t[P];
+    bool valid[P];
+    double zt[P][DP], s[P], reach[P];
 #pragma unroll
-    for (int k = 0; k < DP; ++k) {
-      zt[k] = (k < p.n_in && valid) ? (double)test_x[t * xs + k] * __ldg(p.inv_x_scale + k) : 0.0;
-      s = fma(zt[k], zt[k], s);
+    for (int i = 0; i < P; ++i) {
+      t[i] = (tile * P + i) * 32 + lane;
+      valid[i] = t[i] < n_test;
+      s[i] = 0.0;
+#pragma unroll
+      for (int k = 0; k < DP; ++k) {
+        zt[i][k] = (k < p.n_in && valid[i]) ? (double)test_x[t[i] * xs + k] * __ldg(p.inv_x_scale + k) : 0.0;
+        s[i] = fma(zt[i][k], zt[i][k], s[i]);
+      }
+      reach[i] = sqrt(s[i]) + p.ff_zmax;
     }
-    const double reach = sqrt(s) + p.ff_zmax;
     for (int g = 0; g < p.n_gp; ++g) {
       const double inv_2l2 = __ldg(p.hyp + g * 4 + 0), os = __ldg(p.hyp + g * 4 + 1), noise = __ldg(p.hyp + g * 4 + 2),
-                   y_scale = __ldg(p.hyp + g * 4 + 3);
+                   y_scale = __ldg(p.hyp + g * 4 + 3), amax = __ldg(p.ff_amax + g);
       const double* py = p.proj_y + (size_t)g * R;
-      const bool far = reach * reach * inv_2l2 <= __ldg(p.ff_amax + g);
-      double q = 0.0, m = 0.0;
       const double* cf = p.ff_coef + (size_t)g * R * NC;
+      double q[P], m[P];
+#pragma unroll
+      for (int i = 0; i < P; ++i) q[i] = m[i] = 0.0;
+#pragma unroll(R <= 4 ? R : 2)
       for (int r = 0; r < R; ++r) {
         const double* c = cf + r * NC;
-        double w = fma(s, fma(s, __ldg(c + 2), __ldg(c + 1)), __ldg(c));
+        double w[P];
+        {
+          const double c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
 #pragma unroll
-        for (int k = 0; k < DP; ++k) w = fma(zt[k], fma(s, __ldg(c + 3 + DP + k), __ldg(c + 3 + k)), w);
+          for (int i = 0; i < P; ++i) w[i] = fma(s[i], fma(s[i], c2, c1), c0);
+        }
+#pragma unroll
+        for (int k = 0; k < DP; ++k) {
+          const double lin = __ldg(c + 3 + k), slin = __ldg(c + 3 + DP + k);
+#pragma unroll
+          for (int i = 0; i < P; ++i) w[i] = fma(zt[i][k], fma(s[i], slin, lin), w[i]);
+        }
         int idx = 3 + 2 * DP;
 #pragma unroll
         for (int k = 0; k < DP; ++k) {
-          double row = 0.0;
+          double row[P];
 #pragma unroll
-          for (int l = k; l < DP; ++l) row = fma(zt[l], __ldg(c + idx++), row);
-          w = fma(zt[k], row, w);
-        }
-        q = fma(w, w, q);
-        m = fma(w, __ldg(py + r), m);
-      }
-      unsigned near = __ballot_sync(kFull, valid && !far);
-      while (near) {  // exact evaluation of one point by the whole warp
-        const int src = __ffs(near) - 1;
-        near &= near - 1;
-        double zs[DP];
+          for (int i = 0; i < P; ++i) row[i] = 0.0;
 #pragma unroll
-        for (int k = 0; k < DP; ++k) zs[k] = __shfl_sync(kFull, zt[k], src);
-        double w[R];
+          for (int l = k; l < DP; ++l) {
+            const double cq = __ldg(c + idx++);
 #pragma unroll
-        for (int r = 0; r < R; ++r) w[r] = 0.0;
-        const double* fac = p.factor + (size_t)g * p.max_tiles * p.n_pad * R;
-        for (int j = lane; j < p.n_pad; j += 32) {
-          double d2 = 0.0;
-#pragma unroll
-          for (int k = 0; k < DP; ++k) {
-            const double d = __ldg(p.train_z + (size_t)j * DP + k) - zs[k];
-            d2 = fma(d, d, d2);
+            for (int i = 0; i < P; ++i) row[i] = fma(zt[i][l], cq, row[i]);
           }
-          const double kv = os * exp(-d2 * inv_2l2);
 #pragma unroll
-          for (int r = 0; r < R; ++r) w[r] = fma(__ldg(fac + (size_t)j * R + r), kv, w[r]);
+          for (int i = 0; i < P; ++i) w[i] = fma(zt[i][k], row[i], w[i]);
         }
-        double qe = 0.0, me = 0.0;
+        const double pyr = __ldg(py + r);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) w[r] += __shfl_xor_sync(kFull, w[r], o);
-          qe = fma(w[r], w[r], qe);
-          me = fma(w[r], __ldg(py + r), me);
-        }
-        if (lane == src) {
-          q = qe;
-          m = me;
+        for (int i = 0; i < P; ++i) {
+          q[i] = fma(w[i], w[i], q[i]);
+          m[i] = fma(w[i], pyr, m[i]);
         }
       }
-      if (valid) {
-        double var = os - q + (p.include_noise ? noise : 0.0);
-        var = var > p.min_variance ? var : p.min_variance;
-        if (q != q) var = q;
-        mean[t * p.n_gp + g] = (T)(m * y_scale);
-        sd[t * p.n_gp + g] = (T)(sqrt(var) * y_scale);
+#pragma unroll
+      for (int i = 0; i < P; ++i) {
+        unsigned near = __ballot_sync(kFull, valid[i] && !(reach[i] * reach[i] * inv_2l2 <= amax));
+        while (near) {  // exact evaluation of one point by the whole warp
+          const int src = __ffs(near) - 1;
+          near &= near - 1;
+          double zs[DP];
+#pragma unroll
+          for (int k = 0; k < DP; ++k) zs[k] = __shfl_sync(kFull, zt[i][k], src);
+          double w[R];
+#pragma unroll
+          for (int r = 0; r < R; ++r) w[r] = 0.0;
+          const double* fac = p.factor + (size_t)g * p.max_tiles * p.n_pad * R;
+          for (int j = lane; j < p.n_pad; j += 32) {
+            double d2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < DP; ++k) {
+              const double d = __ldg(p.train_z + (size_t)j * DP + k) - zs[k];
+              d2 = fma(d, d, d2);
+            }
+            const double kv = os * exp(-d2 * inv_2l2);
+#pragma unroll
+            for (int r = 0; r < R; ++r) w[r] = fma(__ldg(fac + (size_t)j * R + r), kv, w[r]);
+          }
+          double qe = 0.0, me = 0.0;
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) w[r] += __shfl_xor_sync(kFull, w[r], o);
+            qe = fma(w[r], w[r], qe);
+            me = fma(w[r], __ldg(py + r), me);
+          }
+          if (lane == src) {
+            q[i] = qe;
+            m[i] = me;
+          }
+        }
+        if (valid[i]) {
+          double var = os - q[i] + (p.include_noise ? noise : 0.0);
+          var = var > p.min_variance ? var : p.min_variance;
+          if (q[i] != q[i]) var = q[i];
+          mean[t[i] * p.n_gp + g] = (T)(m[i] * y_scale);
+          sd[t[i] * p.n_gp + g] = (T)(sqrt(var) * y_scale);
+        }
       }
     }
   }
@@ -384,7 +415,8 @@ __global__ void __launch_bounds__(128) k_gp_farfield(rcbf_gp_posterior p, const 
 
 template <int R, int DP, typename T>
 int launch_gp_farfield(const rcbf_gp_posterior& p, const T* test_x, int64_t n_test, T* mean, T* sd, cudaStream_t s) {
-  const int64_t tiles = (n_test + 31) / 32;
+  constexpr int P = DP <= 4 ? 4 : 2;
+  const int64_t tiles = (n_test + 32 * P - 1) / (32 * P);
   const int64_t want = (tiles + 3) / 4;
   const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
   k_gp_farfield<R, DP, T><<<grid, 128, 0, s>>>(p, test_x, n_test, mean, sd);
