@@ -35,7 +35,7 @@ for f in {f for f, _ in per_line}:
     if os.path.exists(p):
         st = []
         for i, l in enumerate(open(p), 1):
-            m = pat.match(re.sub(r'__launch_bounds__\([^)]*\)', '', l))
+            m = pat.match(re.sub(r'__launch_bounds__\([^)]*\)', '', l)) or re.match(r'^(k_\w+)\(', l)
             if m and not l.rstrip().endswith(';'):
                 st.append((i, m.group(1)))
         funcs[f] = st
