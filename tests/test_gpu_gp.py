@@ -230,3 +230,26 @@ def test_model_rollout_transition_uses_the_fitted_gps_on_the_device():
     assert np.allclose(got[0].cpu().numpy(), want[0], rtol=0, atol=1e-9)
     assert np.allclose(got[1].cpu().numpy(), want[1], rtol=0, atol=1e-9)
     assert np.array_equal(got[2].cpu().numpy(), want[2])
+
+
+def test_reference_demo_shapes_one_dimensional_inputs_and_empty_batches():
+    """gp_model.py:117-134 (__main__ demo): 1-D train_x / test_x tensors, prior_std = 0, 50 training iterations."""
+    from sac_rcbf_b200.gp_model import GPyDisturbanceEstimator
+    gen = torch.Generator().manual_seed(0)
+    train_x = torch.linspace(0, 1, 100)
+    train_y = torch.sin(train_x * (2 * np.pi)) + torch.randn(train_x.size(), generator=gen) * 0.2
+    est = GPyDisturbanceEstimator(train_x, train_y, 0.0, device=torch.device("cuda"))
+    est.train(50)
+    test_x = torch.linspace(0, 1, 51)
+    pred = est.predict(test_x)
+    gp = G.ExactGP(train_x.numpy().astype(np.float64)[:, None], train_y.numpy().astype(np.float64), 0.0)
+    gp.train(50)
+    p = gp.predict(test_x.numpy().astype(np.float64)[:, None])
+    assert pred["mean"].shape == (51,) and pred["mean"].dtype == torch.float32
+    assert np.allclose(pred["mean"].numpy(), p["mean"], rtol=0, atol=2e-6 * np.abs(train_y.numpy()).max())
+    assert np.allclose(pred["f_var"].numpy(), p["f_var"], rtol=4e-6)
+    assert pred["f_covar"].shape == (51, 51)
+    empty = est.predict(torch.zeros(0))
+    assert empty["mean"].shape == (0,)
+    m, s = est.bank.predict(torch.zeros(0, 1, device="cuda"))
+    assert m.shape == (0, 1) and s.shape == (0, 1)
