@@ -138,6 +138,7 @@ class SimulatedCarsEnv:
                                                _lib.ptr(self._done), _lib.ptr(self._cost), _lib.ptr(status),
                                                _lib.ptr(self._counters), _lib.stream_ptr(dev))
         _lib.check(rc, "rcbf_cars_safe_step")
+        cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
         info = {'cost': self._cost, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
 

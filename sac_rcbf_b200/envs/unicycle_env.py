@@ -170,6 +170,7 @@ class UnicycleEnv:
                                                    _lib.ptr(self._goal), _lib.ptr(status), _lib.ptr(self._counters),
                                                    _lib.stream_ptr(dev))
         _lib.check(rc, "rcbf_unicycle_safe_step")
+        cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
         info = {'cost': self._cost, 'goal_met': self._goal, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
 
