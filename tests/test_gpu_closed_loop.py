@@ -56,3 +56,40 @@ def test_unicycle_closed_loop_tracks_oracle_for_60_steps():
     assert (d2.min(1) >= 0.6 ** 2).mean() > 0.97
     stats = layer.solver_stats()
     assert stats["nan"] == 0 and stats["uncertified"] == 0
+
+
+def test_cars_closed_loop_tracks_oracle_for_40_steps():
+    """Same for SimulatedCars (positions ~ 100 m in float32, so the comparison is relative to the gap scale; instances
+    that come within 1e-3 of a `< 6 / < 13` braking switch are dropped -- a discontinuity of the reference model)."""
+    import sac_rcbf_b200 as S
+    B, T = 160, 40
+    st0, _, _, sg, t0 = O.synth_cars(B, seed=77)
+    env = S.SimulatedCarsEnv(num_envs=B)
+    layer = S.CBFQPLayer(env, types.SimpleNamespace(cuda=True), gamma_b=20, k_d=3.0, l_p=0.03)
+    env.reset()
+    env.state = torch.as_tensor(st0).cuda()
+    env._t.copy_(torch.as_tensor(t0).cuda())
+    st = st0.astype(np.float64)
+    t = t0.astype(np.float64)
+    step = np.zeros(B, np.int64)
+    mu = np.zeros((B, 10), np.float32)
+    rng = np.random.default_rng(5)
+    tt = torch.from_numpy
+    keep = np.ones(B, bool)
+    for k in range(T):
+        keep &= O.cars_threshold_margin(st) > 1e-3
+        u = rng.uniform(-1, 1, (B, 1)).astype(np.float32)
+        env.safe_step(layer, tt(u).cuda(), tt(sg).cuda())
+        us = O.safe_action("SimulatedCars", tt(st.astype(np.float32)), tt(u), tt(mu), tt(sg), solver="exact",
+                           gamma_b=20.0).numpy()
+        out = O.cars_env_step(st, us.astype(np.float64), t, step)
+        st, t, step = out["state"], out["t"], out["episode_step"]
+    dev_st = env.state.cpu().numpy().astype(np.float64)
+    assert keep.sum() > 0.8 * B
+    err_pos = np.abs(dev_st[:, 0::2] - st[:, 0::2]).max(1)[keep]
+    err_vel = np.abs(dev_st[:, 1::2] - st[:, 1::2]).max(1)[keep]
+    # float32 positions near 200 m carry 1.5e-5 of rounding per step; velocities feed back through kp = 4, k_brake = 20
+    assert np.median(err_pos) < 2e-3 and np.median(err_vel) < 2e-3, (np.median(err_pos), np.median(err_vel))
+    assert (err_pos < 2e-2).mean() > 0.97 and (err_vel < 5e-2).mean() > 0.97
+    stats = layer.solver_stats()
+    assert stats["nan"] == 0 and stats["uncertified"] == 0
