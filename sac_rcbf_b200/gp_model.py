@@ -113,14 +113,40 @@ class DisturbanceGPBank:
         lp = lambda v, mu: -0.5 * ((v - mu) / PRIOR_SIGMA) ** 2 - math.log(PRIOR_SIGMA * math.sqrt(2.0 * math.pi))
         return -(logp + lp(ls, LENGTHSCALE_INIT) + lp(os_, self.prior_outputscale)) / n
 
+    def _neg_mll_and_grad(self, raw, d2):
+        """Same loss with its analytic gradient w.r.t. the raw parameters,
+        d logp / d theta = 1/2 tr((alpha alpha^T - Khat^-1) dKhat/dtheta): one Cholesky + one Cholesky inverse per
+        step instead of autograd's backward through the factorisation (about 3x less float64 work)."""
+        n = self.n
+        sp = torch.nn.functional.softplus
+        ls, os_, s2 = sp(raw[:, 0]), sp(raw[:, 1]), sp(raw[:, 2]) + NOISE_LOWER
+        e = torch.exp(-d2[None] / (2.0 * ls * ls)[:, None, None])
+        khat = os_[:, None, None] * e
+        khat.diagonal(dim1=1, dim2=2).add_(s2[:, None])
+        chol = torch.linalg.cholesky(khat)
+        kinv = torch.cholesky_inverse(chol)
+        y = self.train_y.t()                                                   # (n_gp, n)
+        alpha = torch.einsum("gij,gj->gi", kinv, y)
+        logp = -0.5 * (y * alpha).sum(1) - torch.log(torch.diagonal(chol, dim1=1, dim2=2)).sum(1) \
+            - 0.5 * n * math.log(2.0 * math.pi)
+        lp = lambda v, mu: -0.5 * ((v - mu) / PRIOR_SIGMA) ** 2 - math.log(PRIOR_SIGMA * math.sqrt(2.0 * math.pi))
+        loss = -(logp + lp(ls, LENGTHSCALE_INIT) + lp(os_, self.prior_outputscale)) / n
+        w = alpha[:, :, None] * alpha[:, None, :] - kinv                       # 2 dlogp / dKhat
+        we = w * e
+        g_ls = 0.5 * os_ / ls ** 3 * (we * d2[None]).sum((1, 2)) - (ls - LENGTHSCALE_INIT) / PRIOR_SIGMA ** 2
+        g_os = 0.5 * we.sum((1, 2)) - (os_ - self.prior_outputscale) / PRIOR_SIGMA ** 2
+        g_s2 = 0.5 * torch.diagonal(w, dim1=1, dim2=2).sum(1)
+        grad = -torch.stack([g_ls, g_os, g_s2], 1) * torch.sigmoid(raw) / n
+        return loss, grad
+
     def train(self, training_iter, verbose=False):
         d2 = _sq_dists(self.train_x, self.train_x)
         raw = self.raw.clone().requires_grad_(True)
         opt = torch.optim.Adam([raw], lr=0.1)                                  # gp_model.py:66
         for i in range(training_iter):
             opt.zero_grad()
-            loss = self._neg_mll(raw, d2)
-            loss.sum().backward()                                              # GPs are independent: sum == per-GP steps
+            with torch.no_grad():
+                loss, raw.grad = self._neg_mll_and_grad(raw, d2)              # GPs are independent: per-GP Adam steps
             if verbose:
                 sp = torch.nn.functional.softplus
                 print('\tIter %d/%d - Loss: %s   lengthscale: %s   noise: %s' % (

@@ -131,3 +131,20 @@ def test_predict_without_cuda_fails_loudly():
     bank = _bank("unicycle", train=False)
     with pytest.raises(RcbfLibraryError):
         bank.predict(torch.zeros(4, 3))
+
+
+def test_analytic_training_gradient_equals_autograd():
+    """train() uses the closed-form gradient (one Cholesky inverse per step); it must be the autograd gradient."""
+    from sac_rcbf_b200.gp_model import _sq_dists
+    bank = _bank("unicycle", train=False)
+    d2 = _sq_dists(bank.train_x, bank.train_x)
+    raw = bank.raw.clone()
+    raw[:, 0] = torch.log(torch.expm1(torch.tensor(1.7, dtype=torch.float64)))
+    raw[:, 2] = -1.0
+    raw.requires_grad_(True)
+    loss = bank._neg_mll(raw, d2)
+    loss.sum().backward()
+    with torch.no_grad():
+        loss2, grad2 = bank._neg_mll_and_grad(raw, d2)
+    assert torch.allclose(loss, loss2, rtol=1e-13, atol=0)
+    assert torch.allclose(raw.grad, grad2, rtol=1e-10, atol=0)
