@@ -590,6 +590,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       // ---- B-step: a full warp of queued problems (or whatever is left once the tiles are exhausted)
       const int take = (qn >= 32) ? 32 : (have_tile ? 0 : qn);
       if (take > 0) {
+#ifndef RCBF_EXP_NOSOLVE  // (experiment switch: phase-1-only cost model, results are WRONG when defined)
         if (lane < take) {
           const int slot = (head + lane) & (kRing - 1);
           float w[NWR];
@@ -612,6 +613,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
             c_iters += sol.iters;
           }
         }
+#endif
         head = (head + take) & (kRing - 1);
         qn -= take;
         __syncwarp();
