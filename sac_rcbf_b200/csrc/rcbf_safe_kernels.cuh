@@ -18,6 +18,8 @@
 // workspace, or when its queue overflows, pass 2 scans for the sentinel instead.
 #pragma once
 
+#include <cstdlib>
+
 #include <cuda_runtime.h>
 
 #include "rcbf_core.cuh"
@@ -74,6 +76,7 @@ struct UniArgs {
 template <bool kFused>
 struct UniEnv {
   static constexpr int NZ = kUniNZ, M = kUniM, NU = 2;
+  static constexpr bool kPdlPass1 = true;   // see launch_pdl: the presolve kernel fills the register file exactly
   using Pat = UniPat;
   using Args = UniArgs;
   using Params = UnicycleParams;
@@ -250,6 +253,7 @@ struct CarsArgs {
 template <bool kFused>
 struct CarsEnv {
   static constexpr int NZ = kCarsNZ, M = kCarsM, NU = 1;
+  static constexpr bool kPdlPass1 = false;  // measured: -16 % when pass 1 is launched as a dependent
   using Pat = CarsPat;
   using Args = CarsArgs;
   using Params = CarsParams;
@@ -439,6 +443,18 @@ struct WarpShared {
   uint64_t bar[2];
 };
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute has its
+// launch latency and block scheduling overlapped with the tail of the kernel before it.  `pdl_wait` blocks until the
+// preceding grid in the stream has completed and flushed (a no-op for an ordinary launch) and must come before the
+// first read of anything an earlier kernel wrote; `pdl_launch_dependents` lets the dependent grid start being
+// scheduled.  Pass 2 is always launched this way.  Pass 1 (as a dependent of the PREVIOUS call's pass 2) only where
+// A/B runs on B200 showed a gain: the Unicycle presolve kernel (128 registers x 4 blocks = the whole register file,
+// so its blocks can only be placed evenly as the old ones drain; +1.8 %).  The SimulatedCars kernel leaves room for
+// its blocks to be placed early and unevenly next to pass-2 blocks and the persistent grid then runs imbalanced
+// (-16 %), so it is launched normally.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 template <class E>
 __device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t i, rcbf_counters_t* ws) {
   a.out[i * E::NU] = __uint_as_float(kPendingBits);
@@ -474,6 +490,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
   float xsB[NU];
 #pragma unroll
   for (int c = 0; c < NU; ++c) xsB[c] = 0.f;
+  pdl_wait();
   if (kBulk) {
     if (lane == 0) {
       mbar_init(&sh.bar[0], 1);
@@ -693,6 +710,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
 
     if (!have_tile && qn == 0 && fn == 0 && !__any_sync(0xffffffffu, onB)) break;
   }
+  pdl_launch_dependents();  // pass 2 may be scheduled as soon as every block of this grid got here
 
   if (ws != nullptr) {
     c_nan = __reduce_add_sync(0xffffffffu, c_nan);
@@ -795,6 +813,8 @@ k_safe_fallback(typename E::Args a, int64_t n, typename E::Params p, typename E:
   const int lane = threadIdx.x & 31;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
   const int64_t gwarp = gtid >> 5, nwarp = gsz >> 5;
+  pdl_wait();
+  pdl_launch_dependents();
   unsigned long long cnt = (ws != nullptr) ? ws[kWsQueueCount] : ~0ULL;
   const bool scan = cnt > (unsigned long long)kWsQueueCap;  // no workspace, or overflow: sentinel scan
   if (!scan && cnt == 0ULL) goto done;
@@ -851,6 +871,28 @@ done:
   }
 }
 
+// kernel launch, optionally with the PDL attribute (RCBF_NO_PDL=1 in the environment forces plain launches)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t s,
+                              Args... args) {
+  static const bool env_off = [] {
+    const char* v = getenv("RCBF_NO_PDL");
+    return v != nullptr && v[0] == '1';
+  }();
+  const bool no_pdl = env_off || !pdl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 template <class E>
 inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::Params& p, const typename E::EnvParams& e,
                        rcbf_counters_t* ws, cudaStream_t s) {
@@ -876,7 +918,8 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
                            (int)smem);                                                               \
       configured[dev_ & 63] = true;                                                                  \
     }                                                                                                \
-    k_safe<E, MODE, BULK, SAVED><<<grid, kThreadsW, smem, s>>>(a, n, p, e, ws);                      \
+    launch_pdl(E::kPdlPass1 && MODE == 0 && !SAVED, k_safe<E, MODE, BULK, SAVED>, grid, kThreadsW, smem, s, a, n, \
+               p, e, ws);                                                                            \
   } while (0)
 #define RCBF_LAUNCH_SAFE(MODE)                                                                       \
   do {                                                                                               \
@@ -884,7 +927,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
     else if (bulk) RCBF_LAUNCH_ONE(MODE, true, false);                                               \
     else if (saved) RCBF_LAUNCH_ONE(MODE, false, true);                                              \
     else RCBF_LAUNCH_ONE(MODE, false, false);                                                        \
-    k_safe_fallback<E, MODE><<<fgrid, 128, 0, s>>>(a, n, p, e, ws);                                  \
+    launch_pdl(true, k_safe_fallback<E, MODE>, fgrid, 128, 0, s, a, n, p, e, ws);                    \
   } while (0)
   if (p.solver_mode == 0) RCBF_LAUNCH_SAFE(0);
   else RCBF_LAUNCH_SAFE(1);
