@@ -574,7 +574,7 @@ def main():
                        "l2": "inputs larger than L2 (%.0f MB read per step per GPU, 2 rotating input sets)"
                              % (52 * n / 1e6), "gamma_b": 20, "parallelism": "instances sharded by rank, no collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 2 * args.steps, "extra": extra,
+            "gpu_launches": args.steps, "extra": extra,   # one k_safe launch per step (its own tail drains the queue)
         }
         print(json.dumps(out))
     if dist is not None:

@@ -83,10 +83,11 @@ typedef struct {
 /* Solver workspace: RCBF_WS_WORDS 64-bit words owned by the caller, zero-initialised once, one per concurrent stream.
  *   [0]=#NaN  [1]=#uncertified(max-iter)  [2]=#float64 interior-point passes  [3]=#trivial
  *   [4]=sum over instances of pass-1 iterations (presolve rounds in mode 0, interior-point iterations in mode 1)
- *   [5]=#instances handed to the fallback pass  [6]=sum of fallback-pass interior-point iterations  [7] reserved
- *   [8..15] queue bookkeeping, [16..) indices of the instances queued for the fallback pass (reset by the library).
- * The counters [0..7] accumulate with atomics across calls; zero them when you want per-call numbers.  Nullable: the
- * fallback pass then scans safe_action for its pending sentinel instead of reading the queue (slower). */
+ *   [5]=#instances left pending by the fast path  [6]=sum of their interior-point iterations  [7] reserved
+ *   [8..15] queue bookkeeping, [16..) queue of pending instances (index + 1, 0 = empty; reset by the library).
+ * The counters [0..7] accumulate with atomics across calls; zero them when you want per-call numbers.  With a workspace
+ * the default solver mode finishes pending instances inside the same kernel (one launch per call).  Nullable: a second
+ * kernel then scans safe_action for the pending sentinel instead (slower, two launches). */
 #define RCBF_WS_WORDS 32768
 typedef unsigned long long rcbf_counters_t;
 

@@ -1004,6 +1004,31 @@ RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_d
       o.status = RCBF_OK_CERTIFIED;
       if (want_aux) lnp_expand_aux<Pat, NZ, M>(nrm.Gn, nrm.hn, pisd, Rg, rbg, mask, y, lk, o.lam, o.s);
     }
+    if (M <= 4 && o.status == RCBF_PENDING) {
+      // Few rows (SimulatedCars: 10 candidate active sets): when the greedy guess is not certified, enumerate right
+      // here with the same float64 certificate instead of queueing for pass 2 (about 1 instance in 1000).
+      const NormCert<NZ, M> cp{nrm, pisd};
+      double lam[M], sl[M];
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+      for (uint32_t m = 1; m < (1u << M); ++m) {
+        int pc = 0;
+        RCBF_UNROLL
+        for (int i = 0; i < M; ++i) pc += (m >> i) & 1u;
+        if (pc > NZ) continue;
+        if (lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, m, kTolSlack, kTolDual, y, lam, sl)) {
+          o.status = RCBF_OK_CERTIFIED;
+          o.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
+          RCBF_UNROLL
+          for (int i = 0; i < M; ++i) {
+            o.lam[i] = lam[i];
+            o.s[i] = sl[i];
+          }
+          break;
+        }
+      }
+    }
   } else {
     const NormCert<NZ, M> cp{nrm, pisd};
     LnpProblem<float, NZ, M> Pf;

@@ -9,13 +9,16 @@
 // active-set presolve + float64 KKT certificate, or the float32 interior point in "pdipm" mode), reload the 28 bytes
 // of instance inputs they need and finish that instance.  So the expensive phase always runs with full warps (without
 // compaction it ran at ~35 % lane utilisation), and there is no block-wide barrier anywhere: warps never wait for
-// each other.
+// each other (until the very end of the kernel).
 //
-// Instances a B-step cannot certify get a tagged-NaN sentinel in safe_action[i][0] and are queued in the caller's
-// workspace; pass 2 (k_safe_fallback_*) finishes them: one WARP per instance enumerates every active set of size
-// <= nz (129 / 10 candidates) with the same float64 certificate, the interior point being the last resort
-// ("presolve" mode), or one thread per instance runs the float64 interior point ("pdipm" mode).  Without a
-// workspace, or when its queue overflows, pass 2 scans for the sentinel instead.
+// Instances a B-step cannot certify (a constraint would have to be dropped, borderline degeneracy: ~1.5e-5 of the
+// Unicycle instances; SimulatedCars enumerates its 10 candidate active sets inline and leaves none) get a tagged-NaN
+// sentinel in safe_action[i][0] and are queued in the caller's workspace.  "presolve" mode with a workspace: a warp
+// that has run out of tiles drains that queue -- one WARP per instance enumerates every active set of size <= nz (129
+// candidates) with the same float64 certificate, the interior point being the last resort -- so the step is ONE
+// kernel launch; the last block to finish resets the queue (and, should it ever overflow, scans for the sentinel).
+// Pass 2 (k_safe_fallback) remains for the other cases: without a workspace it scans for the sentinel, and in "pdipm"
+// mode one thread per queued instance runs the float64 interior point.
 #pragma once
 
 #include <cstdlib>
@@ -31,8 +34,9 @@ namespace rcbf {
 constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
 constexpr int kWsCounters = 8;                 // workspace words [0, 8): counters
 constexpr int kWsQueueCount = 8;               // [8]: number of queued instances
-constexpr int kWsBlocksDone = 9;               // [9]: fallback blocks finished (last one resets the queue)
-constexpr int kWsQueueBase = 16;               // [16, RCBF_WS_WORDS): queued instance indices
+constexpr int kWsBlocksDone = 9;               // [9]: blocks finished (the last one resets the queue)
+constexpr int kWsClaim = 10;                   // [10]: queue entries claimed by a draining warp (presolve mode)
+constexpr int kWsQueueBase = 16;               // [16, RCBF_WS_WORDS): queued instance indices + 1 (0 = empty slot)
 constexpr int kWsQueueCap = RCBF_WS_WORDS - kWsQueueBase;
 
 template <int K>
@@ -459,8 +463,161 @@ template <class E>
 __device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t i, rcbf_counters_t* ws) {
   a.out[i * E::NU] = __uint_as_float(kPendingBits);
   if (ws != nullptr) {
+    __threadfence();  // the sentinel must be visible before whoever drains the queue writes the real result over it
     const unsigned long long slot = atomicAdd(&ws[kWsQueueCount], 1ULL);
-    if (slot < (unsigned long long)kWsQueueCap) ws[kWsQueueBase + slot] = (unsigned long long)i;
+    if (slot < (unsigned long long)kWsQueueCap) ws[kWsQueueBase + slot] = (unsigned long long)i + 1ULL;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pass 2: the queued (or sentinel-marked) instances
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fallback_counters(rcbf_counters_t* ws, int status, int iters) {
+  if (ws == nullptr) return;
+  if (status == RCBF_NAN) atomicAdd(&ws[0], 1ULL);
+  if (status == RCBF_MAXITER) atomicAdd(&ws[1], 1ULL);
+  if (iters >= 100) atomicAdd(&ws[2], 1ULL);
+  atomicAdd(&ws[6], (unsigned long long)(iters >= 100 ? iters - 100 : iters));
+}
+
+// thread-per-instance interior-point chain (float32 unless it already failed in pass 1, then float64)
+template <class E, bool kSkipF32>
+__device__ __forceinline__ void fallback_ipm(const typename E::Args& a, int64_t i, const typename E::Params& p,
+                                             const typename E::EnvParams& e, rcbf_counters_t* ws) {
+  constexpr int NZ = E::NZ, M = E::M, NU = E::NU;
+  typename E::Inst in;
+  E::load_inst(a, i, in);
+  Normalised<NZ, M> nrm;
+  E::assemble(a, p, i, in, nrm);
+  NormSolution<NZ, M> sol;
+  solve_normalised_full<typename E::Pat, NZ, M>(nrm, p.p_diag, kSkipF32, sol);
+  float xs[NU];
+#pragma unroll
+  for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
+  write_saved<E>(a, i, sol);
+  E::finish(a, p, e, i, in, xs, sol.status);
+  fallback_counters(ws, sol.status, sol.iters);
+}
+
+// warp-per-instance exhaustive active-set enumeration with the float64 certificate ("presolve" mode)
+template <class E>
+__device__ __forceinline__ void fallback_enum(const typename E::Args& a, int64_t i, const typename E::Params& p,
+                                              const typename E::EnvParams& e, rcbf_counters_t* ws,
+                                              const unsigned short* table, int ntable, int lane) {
+  constexpr int NZ = E::NZ, M = E::M, NU = E::NU;
+  typename E::Inst in;
+  E::load_inst(a, i, in);
+  Normalised<NZ, M> nrm;
+  E::assemble(a, p, i, in, nrm);  // every lane assembles the same instance: 32x redundant, a few hundred flops
+  double pisd[NZ];
+  float pisf[NZ];
+  pis_of<NZ, M>(p.p_diag, pisd, pisf);
+  const NormCert<NZ, M> cp{nrm, pisd};
+  NormSolution<NZ, M> sol;
+  bool found = false;
+  for (int base = 0; base < ntable && !__any_sync(0xffffffffu, found); base += 32) {
+    const int t = base + lane;
+    double y[NZ], lam[M], s[M];
+    const uint32_t mask = (t < ntable) ? table[t] : 0u;
+    const bool ok = (t < ntable) && lnp_certify<double, NormCert<NZ, M>, typename E::Pat, NZ, M>(cp, mask, kTolSlack,
+                                                                                                  kTolDual, y, lam, s);
+    if (ok && !found) {
+      found = true;
+#pragma unroll
+      for (int j = 0; j < NZ; ++j) sol.x[j] = y[j] * pisd[j];
+#pragma unroll
+      for (int r = 0; r < M; ++r) {
+        sol.lam[r] = lam[r];
+        sol.s[r] = s[r];
+      }
+      sol.status = RCBF_OK_CERTIFIED;
+      sol.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
+    }
+  }
+  const unsigned winners = __ballot_sync(0xffffffffu, found);
+  if (winners == 0u) {
+    if (lane == 0) fallback_ipm<E, false>(a, i, p, e, ws);  // degenerate to working precision: interior point
+    return;
+  }
+  if (lane == __ffs(winners) - 1) {
+    float xs[NU];
+#pragma unroll
+    for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
+    write_saved<E>(a, i, sol);
+    E::finish(a, p, e, i, in, xs, sol.status);
+    fallback_counters(ws, sol.status, 0);
+  }
+}
+
+
+// table of every active set with 1..NZ rows (129 for the Unicycle, 10 for SimulatedCars), lane-parallel build
+template <int NZ, int M>
+__device__ __forceinline__ int build_enum_table(unsigned short* table, int lane) {
+  int ntable = 0;
+  for (int m0 = 0; m0 < (1 << M); m0 += 32) {
+    const int m = m0 + lane;
+    const int pc = __popc(m);
+    const bool keep = (m < (1 << M)) && pc >= 1 && pc <= NZ;
+    const unsigned b = __ballot_sync(0xffffffffu, keep);
+    if (keep) table[ntable + __popc(b & ((1u << lane) - 1u))] = (unsigned short)m;
+    ntable += __popc(b);
+  }
+  __syncwarp();
+  return ntable;
+}
+
+// Tail of the presolve-mode kernel: a warp that has run out of tiles drains the queue of pending instances (one warp
+// per instance, exhaustive enumeration).  Entries are claimed with a CAS on ws[kWsClaim]; an entry is published by its
+// producer right after the counter increment, so the claimer spins the few cycles until the slot turns non-zero and
+// clears it again (the queue is all-zero between calls).  Whatever a warp enqueued during its own tiles exists before
+// that warp drains, so nothing is left when the last block finishes -- no second kernel launch is needed.
+template <class E>
+__device__ __noinline__ void tail_drain(const typename E::Args a, const typename E::Params p,
+                                        const typename E::EnvParams e, rcbf_counters_t* ws, unsigned short* table,
+                                        int lane) {  // by VALUE: taking the address of a kernel parameter would move it
+                                                     // (and every access in the hot loop) from the constant bank to the stack
+  volatile rcbf_counters_t* vws = ws;
+  int ntable = -1;
+  for (;;) {
+    unsigned long long v = 0ULL;
+    if (lane == 0) {
+      for (;;) {
+        const unsigned long long c = vws[kWsClaim];
+        unsigned long long cnt = vws[kWsQueueCount];
+        cnt = cnt < (unsigned long long)kWsQueueCap ? cnt : (unsigned long long)kWsQueueCap;
+        if (c >= cnt) break;
+        if (atomicCAS(&ws[kWsClaim], c, c + 1ULL) == c) {
+          do {
+            v = vws[kWsQueueBase + c];
+          } while (v == 0ULL);
+          vws[kWsQueueBase + c] = 0ULL;
+          break;
+        }
+      }
+    }
+    v = __shfl_sync(0xffffffffu, v, 0);
+    if (v == 0ULL) break;
+    if (ntable < 0) ntable = build_enum_table<E::NZ, E::M>(table, lane);
+    fallback_enum<E>(a, (int64_t)(v - 1ULL), p, e, ws, table, ntable, lane);
+  }
+}
+
+// Queue overflow (more than kWsQueueCap pending instances in one call: pathological inputs): the LAST block scans the
+// output for the pending sentinel.  Slow, but only there to stay correct.
+template <class E>
+__device__ __noinline__ void tail_scan(const typename E::Args a, int64_t n, const typename E::Params p,
+                                       const typename E::EnvParams e, rcbf_counters_t* ws, unsigned short* table,
+                                       int lane, int warp) {
+  const int ntable = build_enum_table<E::NZ, E::M>(table, lane);
+  for (int64_t i0 = (int64_t)warp * 32; i0 < n; i0 += kWarps * 32) {
+    const int64_t i = i0 + lane;
+    const bool pend = (i < n) && __float_as_uint(__ldcg(a.out + i * E::NU)) == kPendingBits;
+    unsigned b = __ballot_sync(0xffffffffu, pend);
+    while (b) {
+      const int src = __ffs(b) - 1;
+      b &= b - 1;
+      fallback_enum<E>(a, i0 + src, p, e, ws, table, ntable, lane);
+    }
   }
 }
 
@@ -710,7 +867,9 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
 
     if (!have_tile && qn == 0 && fn == 0 && !__any_sync(0xffffffffu, onB)) break;
   }
-  pdl_launch_dependents();  // pass 2 may be scheduled as soon as every block of this grid got here
+  pdl_launch_dependents();  // the next kernel may be scheduled as soon as every block of this grid got here
+  const bool own_tail = (kMode == 0) && (ws != nullptr);  // presolve mode with a workspace: no pass-2 kernel
+  if (own_tail) tail_drain<E>(a, p, e, ws, reinterpret_cast<unsigned short*>(&sh.w[0][0]), lane);
 
   if (ws != nullptr) {
     c_nan = __reduce_add_sync(0xffffffffu, c_nan);
@@ -724,88 +883,33 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       if (c_pend) atomicAdd(&ws[5], (unsigned long long)c_pend);
     }
   }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// pass 2: the queued (or sentinel-marked) instances
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fallback_counters(rcbf_counters_t* ws, int status, int iters) {
-  if (ws == nullptr) return;
-  if (status == RCBF_NAN) atomicAdd(&ws[0], 1ULL);
-  if (status == RCBF_MAXITER) atomicAdd(&ws[1], 1ULL);
-  if (iters >= 100) atomicAdd(&ws[2], 1ULL);
-  atomicAdd(&ws[6], (unsigned long long)(iters >= 100 ? iters - 100 : iters));
-}
-
-// thread-per-instance interior-point chain (float32 unless it already failed in pass 1, then float64)
-template <class E, bool kSkipF32>
-__device__ __forceinline__ void fallback_ipm(const typename E::Args& a, int64_t i, const typename E::Params& p,
-                                             const typename E::EnvParams& e, rcbf_counters_t* ws) {
-  constexpr int NZ = E::NZ, M = E::M, NU = E::NU;
-  typename E::Inst in;
-  E::load_inst(a, i, in);
-  Normalised<NZ, M> nrm;
-  E::assemble(a, p, i, in, nrm);
-  NormSolution<NZ, M> sol;
-  solve_normalised_full<typename E::Pat, NZ, M>(nrm, p.p_diag, kSkipF32, sol);
-  float xs[NU];
-#pragma unroll
-  for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
-  write_saved<E>(a, i, sol);
-  E::finish(a, p, e, i, in, xs, sol.status);
-  fallback_counters(ws, sol.status, sol.iters);
-}
-
-// warp-per-instance exhaustive active-set enumeration with the float64 certificate ("presolve" mode)
-template <class E>
-__device__ __forceinline__ void fallback_enum(const typename E::Args& a, int64_t i, const typename E::Params& p,
-                                              const typename E::EnvParams& e, rcbf_counters_t* ws,
-                                              const unsigned short* table, int ntable, int lane) {
-  constexpr int NZ = E::NZ, M = E::M, NU = E::NU;
-  typename E::Inst in;
-  E::load_inst(a, i, in);
-  Normalised<NZ, M> nrm;
-  E::assemble(a, p, i, in, nrm);  // every lane assembles the same instance: 32x redundant, a few hundred flops
-  double pisd[NZ];
-  float pisf[NZ];
-  pis_of<NZ, M>(p.p_diag, pisd, pisf);
-  const NormCert<NZ, M> cp{nrm, pisd};
-  NormSolution<NZ, M> sol;
-  bool found = false;
-  for (int base = 0; base < ntable && !__any_sync(0xffffffffu, found); base += 32) {
-    const int t = base + lane;
-    double y[NZ], lam[M], s[M];
-    const uint32_t mask = (t < ntable) ? table[t] : 0u;
-    const bool ok = (t < ntable) && lnp_certify<double, NormCert<NZ, M>, typename E::Pat, NZ, M>(cp, mask, kTolSlack,
-                                                                                                  kTolDual, y, lam, s);
-    if (ok && !found) {
-      found = true;
-#pragma unroll
-      for (int j = 0; j < NZ; ++j) sol.x[j] = y[j] * pisd[j];
-#pragma unroll
-      for (int r = 0; r < M; ++r) {
-        sol.lam[r] = lam[r];
-        sol.s[r] = s[r];
+  if (own_tail) {  // the last block to get here handles a queue overflow and resets the queue for the next call
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(&ws[kWsBlocksDone], 1ULL) == (unsigned long long)gridDim.x - 1ULL) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const unsigned long long cnt = *(volatile rcbf_counters_t*)&ws[kWsQueueCount];
+      if (cnt > (unsigned long long)kWsQueueCap)
+        tail_scan<E>(a, n, p, e, ws, reinterpret_cast<unsigned short*>(&sh.w[0][0]), lane, warp);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ws[kWsQueueCount] = 0ULL;
+        ws[kWsClaim] = 0ULL;
+        ws[kWsBlocksDone] = 0ULL;
+        __threadfence();
       }
-      sol.status = RCBF_OK_CERTIFIED;
-      sol.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
     }
   }
-  const unsigned winners = __ballot_sync(0xffffffffu, found);
-  if (winners == 0u) {
-    if (lane == 0) fallback_ipm<E, false>(a, i, p, e, ws);  // degenerate to working precision: interior point
-    return;
-  }
-  if (lane == __ffs(winners) - 1) {
-    float xs[NU];
-#pragma unroll
-    for (int c = 0; c < NU; ++c) xs[c] = (float)sol.x[c];
-    write_saved<E>(a, i, sol);
-    E::finish(a, p, e, i, in, xs, sol.status);
-    fallback_counters(ws, sol.status, 0);
-  }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// pass 2 kernel: sentinel scan when the caller gave no workspace, and the queue of the interior-point ("pdipm") mode
+// ---------------------------------------------------------------------------------------------------------------
 template <class E, int kMode>
 __global__ void __launch_bounds__(128)
 k_safe_fallback(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
@@ -820,22 +924,16 @@ k_safe_fallback(typename E::Args a, int64_t n, typename E::Params p, typename E:
   if (!scan && cnt == 0ULL) goto done;
 
   if (kMode == 0) {
-    // table of every active set with 1..NZ rows, built once per warp (lane-parallel, ballot-compacted)
     __shared__ unsigned short s_table[4][160];
     unsigned short* table = s_table[threadIdx.x >> 5];
-    int ntable = 0;
-    for (int m0 = 0; m0 < (1 << M); m0 += 32) {
-      const int m = m0 + lane;
-      const int pc = __popc(m);
-      const bool keep = (m < (1 << M)) && pc >= 1 && pc <= NZ;
-      const unsigned b = __ballot_sync(0xffffffffu, keep);
-      if (keep) table[ntable + __popc(b & ((1u << lane) - 1u))] = (unsigned short)m;
-      ntable += __popc(b);
-    }
-    __syncwarp();
+    const int ntable = build_enum_table<NZ, M>(table, lane);
     if (!scan) {
-      for (int64_t q = gwarp; q < (int64_t)cnt; q += nwarp)
-        fallback_enum<E>(a, (int64_t)ws[kWsQueueBase + q], p, e, ws, table, ntable, lane);
+      for (int64_t q = gwarp; q < (int64_t)cnt; q += nwarp) {
+        const unsigned long long v = ws[kWsQueueBase + q];
+        __syncwarp();
+        if (lane == 0) ws[kWsQueueBase + q] = 0ULL;
+        fallback_enum<E>(a, (int64_t)(v - 1ULL), p, e, ws, table, ntable, lane);
+      }
     } else {
       for (int64_t i0 = gwarp * 32; i0 < n; i0 += nwarp * 32) {
         const int64_t i = i0 + lane;
@@ -850,12 +948,18 @@ k_safe_fallback(typename E::Args a, int64_t n, typename E::Params p, typename E:
     }
   } else {
     if (!scan) {
-      for (int64_t q = gtid; q < (int64_t)cnt; q += gsz) fallback_ipm<E, true>(a, (int64_t)ws[kWsQueueBase + q], p, e, ws);
+      for (int64_t q = gtid; q < (int64_t)cnt; q += gsz) {
+        const unsigned long long v = ws[kWsQueueBase + q];
+        ws[kWsQueueBase + q] = 0ULL;
+        fallback_ipm<E, true>(a, (int64_t)(v - 1ULL), p, e, ws);
+      }
     } else {
       for (int64_t i = gtid; i < n; i += gsz)
         if (__float_as_uint(__ldcg(a.out + i * E::NU)) == kPendingBits) fallback_ipm<E, true>(a, i, p, e, ws);
     }
   }
+  if (scan && ws != nullptr)  // overflow: the stored part of the queue was not consumed entry by entry; clear it
+    for (int64_t q = gtid; q < kWsQueueCap; q += gsz) ws[kWsQueueBase + q] = 0ULL;
 done:
   if (ws != nullptr) {  // the last block to finish resets the queue for the next call
     __syncthreads();
@@ -927,7 +1031,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
     else if (bulk) RCBF_LAUNCH_ONE(MODE, true, false);                                               \
     else if (saved) RCBF_LAUNCH_ONE(MODE, false, true);                                              \
     else RCBF_LAUNCH_ONE(MODE, false, false);                                                        \
-    launch_pdl(true, k_safe_fallback<E, MODE>, fgrid, 128, 0, s, a, n, p, e, ws);                    \
+    if (ws == nullptr || MODE == 1) launch_pdl(true, k_safe_fallback<E, MODE>, fgrid, 128, 0, s, a, n, p, e, ws); \
   } while (0)
   if (p.solver_mode == 0) RCBF_LAUNCH_SAFE(0);
   else RCBF_LAUNCH_SAFE(1);

@@ -158,24 +158,48 @@ def test_pdipm_solver_mode_matches_presolve_mode(request, mode):
     assert stats["sum_iters"] > stats_ref["sum_iters"]
 
 
-def test_fallback_pass_without_workspace_scans_for_the_sentinel(cars):
-    """SimulatedCars leaves ~0.1 % of the QPs to pass 2 (a constraint has to be dropped, which the greedy presolve
-    does not do).  With a workspace pass 2 reads the queue; with workspace = NULL it must find the same instances by
-    scanning for the sentinel.  Both must give identical results."""
+def test_pending_instances_with_and_without_workspace(uni, cars):
+    """A few Unicycle QPs per 100k need a constraint dropped, which the greedy presolve does not do: they are queued
+    and finished by exhaustive enumeration -- by the draining warps of the same kernel when a workspace is given, by
+    the pass-2 kernel scanning for the pending sentinel when workspace = NULL.  Both must give identical results.
+    SimulatedCars (10 candidate active sets) enumerates inline and must leave nothing pending at all."""
     from sac_rcbf_b200 import _lib
-    env, layer = cars
+    env, layer = uni
     lib = _lib.load()
     B = 1 << 20
-    st, ac, mu, sg, _ = O.synth_cars(B, seed=5)
-    ref = _forward_with_aux(layer, st, ac, mu, sg)
-    stats = layer.solver_stats()
-    assert stats["fallback"] > 100 and stats["uncertified"] == 0 and (ref[4] <= 2).all()
-    d = [_cuda(a) for a in (st, ac, sg)]
-    out = torch.empty((B, 1), dtype=torch.float32, device="cuda")
-    rc = lib.rcbf_cars_safe_action(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), B, layer._params(), _lib.ptr(out),
-                                   None, None, None, None, None, None, _lib.stream_ptr(layer.device))
+    rng = np.random.default_rng(5)
+    hz = O.UNICYCLE["hazards_locations"]
+    idx = rng.integers(0, len(hz), B)
+    r, phi = rng.uniform(0.3, 1.1, B), rng.uniform(-np.pi, np.pi, B)
+    st = np.stack([hz[idx, 0] + r * np.cos(phi), hz[idx, 1] + r * np.sin(phi), rng.uniform(-np.pi, np.pi, B)],
+                  1).astype(np.float32)
+    _, ac, mu, sg = O.synth_unicycle(B, seed=5)
+    for _ in range(2):      # twice: the queue must come back empty for the next call
+        ref = _forward_with_aux(layer, st, ac, mu, sg)
+        stats = layer.solver_stats()
+        assert stats["fallback"] > 20 and stats["uncertified"] == 0 and stats["nan"] == 0 and (ref[4] <= 2).all()
+        assert not np.isnan(ref[0]).any()
+    ws = layer._workspace()
+    assert int(ws[8:16].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0     # queue bookkeeping reset, slots cleared
+    d = [_cuda(a) for a in (st, ac, mu, sg)]
+    out = torch.empty((B, 2), dtype=torch.float32, device="cuda")
+    rc = lib.rcbf_unicycle_safe_action(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), B,
+                                       layer._params(), _lib.ptr(out), None, None, None, None, None, None,
+                                       _lib.stream_ptr(layer.device))
     assert rc == 0
     np.testing.assert_array_equal(out.cpu().numpy(), ref[0])
+    # SimulatedCars: nothing is left pending
+    envc, layc = cars
+    stc, acc, muc, sgc, _ = O.synth_cars(B, seed=5)
+    refc = _forward_with_aux(layc, stc, acc, muc, sgc)
+    sc = layc.solver_stats()
+    assert sc["fallback"] == 0 and sc["uncertified"] == 0 and (refc[4] <= 2).all() and (refc[5] == 3).sum() > 100
+    outc = torch.empty((B, 1), dtype=torch.float32, device="cuda")
+    dc = [_cuda(a) for a in (stc, acc, sgc)]
+    rc = lib.rcbf_cars_safe_action(_lib.ptr(dc[0]), _lib.ptr(dc[1]), _lib.ptr(dc[2]), B, layc._params(), _lib.ptr(outc),
+                                   None, None, None, None, None, None, _lib.stream_ptr(layc.device))
+    assert rc == 0
+    np.testing.assert_array_equal(outc.cpu().numpy(), refc[0])
 
 
 @pytest.mark.parametrize("mode", ["Unicycle", "SimulatedCars"])
