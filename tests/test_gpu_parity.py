@@ -158,48 +158,89 @@ def test_pdipm_solver_mode_matches_presolve_mode(request, mode):
     assert stats["sum_iters"] > stats_ref["sum_iters"]
 
 
-def test_pending_instances_with_and_without_workspace(uni, cars):
-    """A few Unicycle QPs per 100k need a constraint dropped, which the greedy presolve does not do: they are queued
-    and finished by exhaustive enumeration -- by the draining warps of the same kernel when a workspace is given, by
-    the pass-2 kernel scanning for the pending sentinel when workspace = NULL.  Both must give identical results.
-    SimulatedCars (10 candidate active sets) enumerates inline and must leave nothing pending at all."""
-    from sac_rcbf_b200 import _lib
-    env, layer = uni
-    lib = _lib.load()
-    B = 1 << 20
-    rng = np.random.default_rng(5)
+def _extreme_unicycle(B, seed):
+    """Instances around the hazards with actions up to the actuator limits and disturbance std up to 3 (15x MAX_STD):
+    about 1 % of them need a constraint dropped, which the greedy presolve does not do."""
+    rng = np.random.default_rng(seed)
     hz = O.UNICYCLE["hazards_locations"]
     idx = rng.integers(0, len(hz), B)
-    r, phi = rng.uniform(0.3, 1.1, B), rng.uniform(-np.pi, np.pi, B)
-    st = np.stack([hz[idx, 0] + r * np.cos(phi), hz[idx, 1] + r * np.sin(phi), rng.uniform(-np.pi, np.pi, B)],
-                  1).astype(np.float32)
-    _, ac, mu, sg = O.synth_unicycle(B, seed=5)
-    for _ in range(2):      # twice: the queue must come back empty for the next call
-        ref = _forward_with_aux(layer, st, ac, mu, sg)
-        stats = layer.solver_stats()
-        assert stats["fallback"] > 20 and stats["uncertified"] == 0 and stats["nan"] == 0 and (ref[4] <= 2).all()
-        assert not np.isnan(ref[0]).any()
-    ws = layer._workspace()
-    assert int(ws[8:16].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0     # queue bookkeeping reset, slots cleared
+    r, phi = rng.uniform(0.3, 1.2, B), rng.uniform(-np.pi, np.pi, B)
+    st = np.stack([hz[idx, 0] + r * np.cos(phi), hz[idx, 1] + r * np.sin(phi), rng.uniform(-np.pi, np.pi, B)], 1)
+    ac = rng.uniform(-2.5, 2.5, (B, 2))
+    mu = rng.uniform(-0.5, 0.5, (B, 3))
+    sg = rng.uniform(0, 3.0, (B, 3))
+    return tuple(a.astype(np.float32) for a in (st, ac, mu, sg))
+
+
+def _unicycle_without_workspace(layer, st, ac, mu, sg):
+    from sac_rcbf_b200 import _lib
+    lib = _lib.load()
     d = [_cuda(a) for a in (st, ac, mu, sg)]
-    out = torch.empty((B, 2), dtype=torch.float32, device="cuda")
-    rc = lib.rcbf_unicycle_safe_action(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), B,
+    out = torch.empty((st.shape[0], 2), dtype=torch.float32, device="cuda")
+    rc = lib.rcbf_unicycle_safe_action(_lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]), _lib.ptr(d[3]), st.shape[0],
                                        layer._params(), _lib.ptr(out), None, None, None, None, None, None,
                                        _lib.stream_ptr(layer.device))
     assert rc == 0
-    np.testing.assert_array_equal(out.cpu().numpy(), ref[0])
+    return out.cpu().numpy()
+
+
+def test_pending_instances_with_and_without_workspace(uni, cars):
+    """Pending Unicycle instances are queued and finished by exhaustive enumeration -- by the draining warps of the same
+    kernel when a workspace is given, by the pass-2 kernel scanning for the pending sentinel when workspace = NULL.
+    Both must give identical results (and the oracle's).  SimulatedCars (10 candidate active sets) enumerates inline
+    and must leave nothing pending at all."""
+    from sac_rcbf_b200 import _lib
+    env, layer = uni
+    B = 1 << 18
+    st, ac, mu, sg = _extreme_unicycle(B, 5)
+    for _ in range(2):      # twice: the queue must come back empty for the next call
+        ref = _forward_with_aux(layer, st, ac, mu, sg)
+        stats = layer.solver_stats()
+        assert stats["fallback"] > 200 and stats["uncertified"] == 0 and stats["nan"] == 0 and (ref[4] <= 2).all()
+        assert not np.isnan(ref[0]).any()
+        ws = layer._ws
+        assert int(ws[8:16].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0   # bookkeeping reset, slots cleared
+    np.testing.assert_array_equal(_unicycle_without_workspace(layer, st, ac, mu, sg), ref[0])
+    pend = ref[5] == 4                                    # iters == nz + 1 marks "enumerated"
+    assert pend.sum() == stats["fallback"]
+    k = np.flatnonzero(pend)[:300]
+    fe = O.safe_action("Unicycle", tt(st[k]), tt(ac[k]), tt(mu[k]), tt(sg[k]), solver="exact", gamma_b=20.0).numpy()
+    f64 = O.safe_action("Unicycle", tt(st[k]), tt(ac[k]), tt(mu[k]), tt(sg[k]), solver="exact",
+                        assembly_dtype=torch.float64, gamma_b=20.0).numpy()
+    well = np.abs(fe - f64).max(1) <= 2e-5
+    assert well.mean() > 0.5 and np.abs(ref[0][k] - fe)[well].max() < 1e-4
     # SimulatedCars: nothing is left pending
+    lib = _lib.load()
     envc, layc = cars
-    stc, acc, muc, sgc, _ = O.synth_cars(B, seed=5)
+    Bc = 1 << 20
+    stc, acc, muc, sgc, _ = O.synth_cars(Bc, seed=5)
     refc = _forward_with_aux(layc, stc, acc, muc, sgc)
     sc = layc.solver_stats()
     assert sc["fallback"] == 0 and sc["uncertified"] == 0 and (refc[4] <= 2).all() and (refc[5] == 3).sum() > 100
-    outc = torch.empty((B, 1), dtype=torch.float32, device="cuda")
+    outc = torch.empty((Bc, 1), dtype=torch.float32, device="cuda")
     dc = [_cuda(a) for a in (stc, acc, sgc)]
-    rc = lib.rcbf_cars_safe_action(_lib.ptr(dc[0]), _lib.ptr(dc[1]), _lib.ptr(dc[2]), B, layc._params(), _lib.ptr(outc),
-                                   None, None, None, None, None, None, _lib.stream_ptr(layc.device))
+    rc = lib.rcbf_cars_safe_action(_lib.ptr(dc[0]), _lib.ptr(dc[1]), _lib.ptr(dc[2]), Bc, layc._params(),
+                                   _lib.ptr(outc), None, None, None, None, None, None, _lib.stream_ptr(layc.device))
     assert rc == 0
     np.testing.assert_array_equal(outc.cpu().numpy(), refc[0])
+
+
+def test_pending_queue_overflow_falls_back_to_the_sentinel_scan(uni):
+    """More pending instances in one call than the 32 752-slot queue holds: the stored part is drained as usual, the
+    rest is found by the last block scanning for the sentinel.  Same results as the workspace-free path, queue clean."""
+    env, layer = uni
+    B = 1 << 22
+    st, ac, mu, sg = _extreme_unicycle(B, 6)
+    out, _, _, _ = layer._forward_raw(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg))
+    stats = layer.solver_stats()
+    assert stats["fallback"] > 32752 and stats["uncertified"] == 0 and stats["nan"] == 0
+    ws = layer._ws
+    assert int(ws[8:16].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0
+    got = out.cpu().numpy()
+    assert not np.isnan(got).any()
+    np.testing.assert_array_equal(_unicycle_without_workspace(layer, st, ac, mu, sg), got)
+    out2, _, _, _ = layer._forward_raw(_cuda(st[:4096]), _cuda(ac[:4096]), _cuda(mu[:4096]), _cuda(sg[:4096]))
+    np.testing.assert_array_equal(out2.cpu().numpy(), got[:4096])     # the next call starts from a clean queue
 
 
 @pytest.mark.parametrize("mode", ["Unicycle", "SimulatedCars"])
