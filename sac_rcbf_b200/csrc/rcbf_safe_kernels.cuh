@@ -633,9 +633,11 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WS& sh = reinterpret_cast<WS*>(smem_raw)[warp];
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int64_t ntiles = (n + 31) >> 5;
-  const int64_t nw = (int64_t)gridDim.x * kWarps;
-  int64_t tile = (int64_t)blockIdx.x * kWarps + warp;
+  // 32-bit tile arithmetic (launch_safe refuses n > 2^31 - 1): the full-tile test is `tile < nfull`
+  const int ntiles = (int)((n + 31) >> 5);
+  const int nfull = (int)(n >> 5);
+  const int nw = (int)gridDim.x * kWarps;
+  int tile = (int)blockIdx.x * kWarps + warp;
   int head = 0, qn = 0;     // problem ring
   int fhead = 0, fn = 0;    // finish ring
   int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
@@ -655,7 +657,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    if (lane == 0 && ((tile << 5) + 32 <= n)) E::issue(a, tile, sh.stage[0], &sh.bar[0]);
+    if (lane == 0 && tile < nfull) E::issue(a, tile, sh.stage[0], &sh.bar[0]);
   }
 
   for (;;) {
@@ -668,22 +670,22 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
     int stA = RCBF_OK_TRIVIAL;
 
     if (have_tile) {  // ---- A-step: assemble, classify, queue
-      const int64_t i0 = (tile << 5) + lane;
+      const int64_t i0 = ((int64_t)tile << 5) + lane;
       const bool valid = i0 < n;
       iA = valid ? i0 : n - 1;
       typename E::Aux aux;
-      if (kBulk && (tile << 5) + 32 <= n) {
+      if (kBulk && tile < nfull) {
         // this tile's inputs were bulk-copied into shared memory one iteration ago; wait, read, then put the NEXT
         // tile in flight into the other buffer (its last reader finished before the previous __syncwarp)
         const int b = nbulk & 1;
         mbar_wait(&sh.bar[b], (nbulk >> 1) & 1);
         E::read_stage(sh.stage[b], lane, inA, aux);
         __syncwarp();
-        if (lane == 0 && (((tile + nw) << 5) + 32 <= n)) E::issue(a, tile + nw, sh.stage[b ^ 1], &sh.bar[b ^ 1]);
+        if (lane == 0 && tile + nw < nfull) E::issue(a, tile + nw, sh.stage[b ^ 1], &sh.bar[b ^ 1]);
         ++nbulk;
       } else {
         if (!kBulk && tile + nw < ntiles) {  // pull the NEXT tile's input lines towards L1 meanwhile
-          const int64_t j0 = ((tile + nw) << 5) + lane;
+          const int64_t j0 = ((int64_t)(tile + nw) << 5) + lane;
           E::prefetch(a, j0 < n ? j0 : n - 1);
         }
         E::load_inst(a, iA, inA);
