@@ -257,6 +257,48 @@ RCBF_HD bool lnp_certify(const CP& P, uint32_t mask, C tol_s, C tol_l, C y[NZ], 
   return ok;
 }
 
+// (R R') lam = -rb on the first K of NZ gathered rows, lam = 0 on the rest: the same arithmetic (same expressions,
+// same order) as factoring the NZ x NZ Gram matrix with a unit diagonal on the unused slots -- whose extra entries are
+// exact zeros -- minus the multiplications by those zeros.
+template <int NZ, int K>
+RCBF_HD void greedy_solve_rows(const float R[NZ][NZ], const float rbg[NZ], float lk[NZ]) {
+  float S[K][K];
+  RCBF_UNROLL
+  for (int k = 0; k < K; ++k) {
+    RCBF_UNROLL
+    for (int l = 0; l <= k; ++l) {
+      float acc = 0.f;
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = fmaf(R[k][j], R[l][j], acc);
+      S[k][l] = acc;
+    }
+  }
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) lk[k] = 0.f;
+  const float i00 = t_rsqrt(S[0][0]);
+  const float w0 = -rbg[0] * i00;
+  if (K == 1) {
+    lk[0] = w0 * i00;
+  } else if (K == 2) {
+    const float l10 = S[K > 1 ? 1 : 0][0] * i00;
+    const float i11 = t_rsqrt(S[K > 1 ? 1 : 0][K > 1 ? 1 : 0] - l10 * l10);
+    const float w1 = (-rbg[1] - l10 * w0) * i11;
+    lk[1] = w1 * i11;
+    lk[0] = (w0 - l10 * lk[1]) * i00;
+  } else {
+    const float l10 = S[K > 1 ? 1 : 0][0] * i00;
+    const float i11 = t_rsqrt(S[K > 1 ? 1 : 0][K > 1 ? 1 : 0] - l10 * l10);
+    const float l20 = S[K > 2 ? 2 : 0][0] * i00;
+    const float l21 = (S[K > 2 ? 2 : 0][K > 1 ? 1 : 0] - l20 * l10) * i11;
+    const float i22 = t_rsqrt(S[K > 2 ? 2 : 0][K > 2 ? 2 : 0] - l20 * l20 - l21 * l21);
+    const float w1 = (-rbg[1] - l10 * w0) * i11;
+    const float w2 = (-rbg[K > 2 ? 2 : 0] - l20 * w0 - l21 * w1) * i22;
+    lk[K > 2 ? 2 : 0] = w2 * i22;
+    lk[1] = (w1 - l21 * lk[K > 2 ? 2 : 0]) * i11;
+    lk[0] = (w0 - l10 * lk[1] - l20 * lk[K > 2 ? 2 : 0]) * i00;
+  }
+}
+
 // --- greedy dual active-set presolve -----------------------------------------------------------------------
 // Starting from y = 0 (the unconstrained optimum), repeatedly add the most violated row (violation measured in
 // units of the row norm) and re-solve the equality-constrained least-norm problem on the chosen rows, at most NZ
@@ -300,9 +342,11 @@ RCBF_HD bool lnp_greedy_active_set(const float Gn[M][NZ], const float hn[M], con
     RCBF_UNROLL
     for (int i = 0; i < M; ++i) {
       float acc = hn[i];
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j)
-        if (Pat::nz(i, j)) acc = fmaf(-A[i][j], y[j], acc);
+      if (r > 0) {  // (round 0 starts from y = 0: the products are exact zeros)
+        RCBF_UNROLL
+        for (int j = 0; j < NZ; ++j)
+          if (Pat::nz(i, j)) acc = fmaf(-A[i][j], y[j], acc);
+      }
       const float v = acc * inv_norm[i];
       const bool take = !((mask >> i) & 1u) && (v < worst);
       worst = take ? v : worst;
@@ -324,25 +368,11 @@ RCBF_HD bool lnp_greedy_active_set(const float Gn[M][NZ], const float hn[M], con
     }
     RCBF_UNROLL
     for (int j = 0; j < NZ; ++j) R[r][j] = Rg[r][j] * pis[j];
-    // (R R') lam = -rb on the first r+1 rows (unit diagonal on the unused slots)
-    float Gm[NZ][NZ];
-    RCBF_UNROLL
-    for (int k = 0; k < NZ; ++k) {
-      RCBF_UNROLL
-      for (int l = 0; l <= k; ++l) {
-        float acc = 0.f;
-        RCBF_UNROLL
-        for (int j = 0; j < NZ; ++j) acc = fmaf(R[k][j], R[l][j], acc);
-        Gm[k][l] = acc;
-      }
-      Gm[k][k] = (k <= r) ? Gm[k][k] : 1.f;
-    }
-    Chol<float, NZ> ch;
-    ch.factor(Gm);
-    float nrb[NZ], lk[NZ];
-    RCBF_UNROLL
-    for (int k = 0; k < NZ; ++k) nrb[k] = -rbg[k];
-    ch.solve(nrb, lk);
+    // (R R') lam = -rb on the first r+1 rows (r is a compile-time constant once the loop is unrolled)
+    float lk[NZ];
+    if (r == 0) greedy_solve_rows<NZ, 1>(R, rbg, lk);
+    else if (r == 1 || NZ == 2) greedy_solve_rows<NZ, (NZ < 2 ? NZ : 2)>(R, rbg, lk);
+    else greedy_solve_rows<NZ, NZ>(R, rbg, lk);
     RCBF_UNROLL
     for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -1e-6f);  // NaN (dependent rows) -> false
     if (!ok) break;
@@ -350,7 +380,8 @@ RCBF_HD bool lnp_greedy_active_set(const float Gn[M][NZ], const float hn[M], con
     for (int j = 0; j < NZ; ++j) {
       float acc = 0.f;
       RCBF_UNROLL
-      for (int k = 0; k < NZ; ++k) acc = fmaf(-R[k][j], lk[k], acc);
+      for (int k = 0; k < NZ; ++k)
+        if (k <= r) acc = fmaf(-R[k][j], lk[k], acc);  // (rows beyond r are zero and carry lam = 0)
       y[j] = acc;
     }
   }
