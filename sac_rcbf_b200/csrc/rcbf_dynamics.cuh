@@ -159,12 +159,17 @@ struct CarsEnvOut {
   int done;
 };
 
+// x / n for a compile-time n: float32 multiplies by the (correctly rounded) reciprocal and corrects the quotient once
+// with the exact residual -- the fast path of an IEEE division without its range checks (|x| <= 1e6 here)
+RCBF_HD float div_const(float x, float n, float r) { return div_by(x, n, r); }
+RCBF_HD double div_const(double x, double n, double) { return x / n; }
+
 template <typename T>
 RCBF_HD void cars_obs(const T st[10], T obs[10]) {  // simulated_cars_env.py:143-158
   RCBF_UNROLL
   for (int i = 0; i < 5; ++i) {
-    obs[2 * i] = st[2 * i] / T(100);
-    obs[2 * i + 1] = st[2 * i + 1] / T(30);
+    obs[2 * i] = div_const(st[2 * i], T(100), T(0.01));
+    obs[2 * i + 1] = div_const(st[2 * i + 1], T(30), T(1.0 / 30.0));
   }
 }
 

@@ -31,6 +31,13 @@
 
 namespace rcbf {
 
+#ifndef RCBF_MINB
+#define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (128 registers; A/B on B200: 4 > 3 > 5)
+#endif
+#ifndef RCBF_MINB_CARS
+#define RCBF_MINB_CARS RCBF_MINB
+#endif
+
 constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
 constexpr int kWsCounters = 8;                 // workspace words [0, 8): counters
 constexpr int kWsQueueCount = 8;               // [8]: number of queued instances
@@ -80,6 +87,7 @@ struct UniArgs {
 template <bool kFused>
 struct UniEnv {
   static constexpr int NZ = kUniNZ, M = kUniM, NU = 2;
+  static constexpr int kMinBlocks = RCBF_MINB;
   static constexpr bool kPdlPass1 = true;   // see launch_pdl: the presolve kernel fills the register file exactly
   using Pat = UniPat;
   using Args = UniArgs;
@@ -257,6 +265,7 @@ struct CarsArgs {
 template <bool kFused>
 struct CarsEnv {
   static constexpr int NZ = kCarsNZ, M = kCarsM, NU = 1;
+  static constexpr int kMinBlocks = RCBF_MINB_CARS;
   static constexpr bool kPdlPass1 = false;  // measured: -16 % when pass 1 is launched as a dependent
   using Pat = CarsPat;
   using Args = CarsArgs;
@@ -427,9 +436,6 @@ __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i
 // ---------------------------------------------------------------------------------------------------------------
 // pass 1: persistent warps, warp-private compaction ring
 // ---------------------------------------------------------------------------------------------------------------
-#ifndef RCBF_MINB
-#define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (128 registers; A/B on B200: 4 > 3 > 5)
-#endif
 constexpr int kWarps = 4;             // warps per block
 constexpr int kThreadsW = 32 * kWarps;
 // Per-warp shared memory.  Problem ring: raw rows + instance index of the QPs waiting for a solve.  Finish ring:
@@ -623,7 +629,7 @@ __device__ __noinline__ void tail_scan(const typename E::Args a, int64_t n, cons
 
 template <class E, int kMode /* 0 presolve, 1 pdipm */, bool kBulk /* TMA bulk-copy input staging */,
           bool kSaved /* also write x / lam / slack / iters (backward pass, diagnostics) */>
-__global__ void __launch_bounds__(kThreadsW, kMode == 0 ? RCBF_MINB : 2)
+__global__ void __launch_bounds__(kThreadsW, kMode == 0 ? E::kMinBlocks : 2)
 k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NWR = E::NWR;
   using Inst = typename E::Inst;
@@ -1006,7 +1012,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   if (n > 0x7fffffffLL) return -2;  // ring indices are 32-bit
   const int64_t ntiles = (n + 31) / 32;
   const int64_t want = (ntiles + kWarps - 1) / kWarps;
-  const int resident = 148 * (p.solver_mode == 0 ? RCBF_MINB : 2);  // persistent: one wave of resident blocks
+  const int resident = 148 * (p.solver_mode == 0 ? E::kMinBlocks : 2);  // persistent: one wave of resident blocks
   const int grid = (int)(want < resident ? want : resident);
   const int64_t fb = (n + 127) / 128;
   const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);

@@ -1,0 +1,23 @@
+"""SimulatedCars fused safe step, 4 Mi instances, a few launches (profiling target)."""
+import sys, types, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import sac_rcbf_b200 as S
+from oracle import rcbf_oracle as O   # synthetic inputs only
+dev = torch.device("cuda")
+nc = 1 << 22
+stc, acc, muc, sgc, tc = (torch.from_numpy(a).to(dev) for a in O.synth_cars(nc, seed=12345))
+env = S.SimulatedCarsEnv(num_envs=nc, device=dev)
+lay = S.CBFQPLayer(env, types.SimpleNamespace(cuda=True), gamma_b=20, k_d=3.0, l_p=0.03)
+lay.check_nan = False
+env.state = stc
+env._t.copy_(tc)
+for _ in range(6):
+    env.safe_step(lay, acc, sgc)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10):
+    env.safe_step(lay, acc, sgc)
+e1.record(); torch.cuda.synchronize()
+print("cars fused step: %.4f ms -> %.3e steps/s, stats %s" % (e0.elapsed_time(e1) / 10, nc / (e0.elapsed_time(e1) / 10) * 1e3, lay.solver_stats()))
