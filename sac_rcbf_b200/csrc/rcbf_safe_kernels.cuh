@@ -35,8 +35,9 @@ namespace rcbf {
 #define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (128 registers; A/B on B200: 4 > 3 > 5)
 #endif
 #ifndef RCBF_MINB_CARS
-#define RCBF_MINB_CARS RCBF_MINB
-#endif
+#define RCBF_MINB_CARS 3  // SimulatedCars: 3 (168 registers, no spills in the loop) > 2 > 4 > 5 > 6 on B200 -- that kernel is
+#endif                    // bound by memory-system requests (40-byte rows), not by latency hiding
+
 
 constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
 constexpr int kWsCounters = 8;                 // workspace words [0, 8): counters
