@@ -35,8 +35,8 @@ namespace rcbf {
 #define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (128 registers; A/B on B200: 4 > 3 > 5)
 #endif
 #ifndef RCBF_MINB_CARS
-#define RCBF_MINB_CARS 3  // SimulatedCars: 3 (168 registers, no spills in the loop) > 2 > 4 > 5 > 6 on B200 -- that kernel is
-#endif                    // bound by memory-system requests (40-byte rows), not by latency hiding
+#define RCBF_MINB_CARS 3  // SimulatedCars fused step: 3 (168 registers, no spills in the loop) > 2 > 4 > 5 > 6 on B200 --
+#endif                    // that kernel is bound by memory-system requests (40-byte rows), not by latency hiding
 
 
 constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
@@ -266,7 +266,7 @@ struct CarsArgs {
 template <bool kFused>
 struct CarsEnv {
   static constexpr int NZ = kCarsNZ, M = kCarsM, NU = 1;
-  static constexpr int kMinBlocks = RCBF_MINB_CARS;
+  static constexpr int kMinBlocks = kFused ? RCBF_MINB_CARS : RCBF_MINB;  // get_safe_action alone: 4 is faster (A/B)
   static constexpr bool kPdlPass1 = false;  // measured: -16 % when pass 1 is launched as a dependent
   using Pat = CarsPat;
   using Args = CarsArgs;
