@@ -307,9 +307,9 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     u, mu, sg = batches[0]
     ms = _time_calls(lambda: layer._forward_raw(st, u, mu, sg), 5, device)
     out["qp_solves_unicycle"] = {"value": n / (ms * 1e-3), "unit": "QP/s", "instances": n, "ms": ms}
-    from oracle import rcbf_oracle as O
+    from sac_rcbf_b200 import workloads
     nc = 1 << 22
-    stc, acc, muc, sgc, tc = (torch.from_numpy(a).to(device) for a in O.synth_cars(nc, seed=12345))
+    stc, acc, muc, sgc, tc = (torch.from_numpy(a).to(device) for a in workloads.synth_cars(nc, seed=12345))
     envc = S.SimulatedCarsEnv(num_envs=nc, device=device)
     layc = S.CBFQPLayer(envc, ns, gamma_b=20, k_d=3.0, l_p=0.03)
     layc.check_nan = False

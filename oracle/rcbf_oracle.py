@@ -444,37 +444,9 @@ def rollout_step(mode, obs, action, t, eps, mean=None, std=None):
 # --------------------------------------------------------------------------------------
 # Synthetic inputs
 # --------------------------------------------------------------------------------------
-def synth_unicycle(B, seed=12345, hazard_frac=0.2):
-    g = np.random.default_rng(seed)
-    st = np.stack([g.uniform(-3, 3, B), g.uniform(-3, 3, B), g.uniform(-math.pi, math.pi, B)], axis=1)
-    nh = int(B * hazard_frac)
-    if nh > 0:
-        hz = UNICYCLE["hazards_locations"][g.integers(0, 5, nh)]
-        r = g.uniform(0.3, 1.1, nh)
-        phi = g.uniform(-math.pi, math.pi, nh)
-        st[:nh, 0] = hz[:, 0] + r * np.cos(phi)
-        st[:nh, 1] = hz[:, 1] + r * np.sin(phi)
-    ac = g.uniform(-1, 1, (B, 2))
-    mu = g.uniform(-0.1, 0.1, (B, 3))
-    sg = g.uniform(0, 0.2, (B, 3))
-    perm = g.permutation(B)
-    return tuple(a[perm].astype(np.float32) for a in (st, ac, mu, sg))
-
-
-def synth_cars(B, seed=12345):
-    g = np.random.default_rng(seed)
-    t = g.uniform(0, 6, B)
-    pos = CARS["init_pos"][None, :] + 30.0 * t[:, None] + g.normal(0, 1.5, (B, 5))
-    vel = g.normal(30, 2, (B, 5))
-    vel[:, 3] += 3.0
-    st = np.zeros((B, 10))
-    st[:, 0::2] = pos
-    st[:, 1::2] = vel
-    ac = g.uniform(-1, 1, (B, 1))
-    mu = np.zeros((B, 10))
-    sg = np.zeros((B, 10))
-    sg[:, 1::2] = g.uniform(0, 0.2, (B, 5))
-    return tuple(a.astype(np.float32) for a in (st, ac, mu, sg)) + (t.astype(np.float32),)
+# The synthetic workloads are defined once, in the product package (they are workload definitions, not reference
+# arithmetic); re-exported here because every parity test draws its inputs through this module.
+from sac_rcbf_b200.workloads import synth_cars, synth_unicycle  # noqa: E402,F401
 
 
 def cars_threshold_margin(state):

@@ -3,7 +3,7 @@ import sys, types, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import sac_rcbf_b200 as S
-from oracle import rcbf_oracle as O   # synthetic inputs only
+from sac_rcbf_b200 import workloads as O
 dev = torch.device("cuda")
 nc = 1 << 22
 stc, acc, muc, sgc, tc = (torch.from_numpy(a).to(dev) for a in O.synth_cars(nc, seed=12345))
