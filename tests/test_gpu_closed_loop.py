@@ -93,3 +93,43 @@ def test_cars_closed_loop_tracks_oracle_for_40_steps():
     assert (err_pos < 2e-2).mean() > 0.97 and (err_vel < 5e-2).mean() > 0.97
     stats = layer.solver_stats()
     assert stats["nan"] == 0 and stats["uncertified"] == 0
+
+
+def test_fused_step_replays_from_a_cuda_graph():
+    """The C entry points allocate nothing and only enqueue work on the caller's stream, so a rollout loop can be
+    captured once and replayed (launch-bound small-batch loops: SURVEY 'CUDA streams and graphs').  Three replayed
+    steps must equal three eager steps bit for bit."""
+    import sac_rcbf_b200 as S
+    B = 4096
+    st, ac, mu, sg = O.synth_unicycle(B, seed=99)
+    dev = lambda a: torch.from_numpy(a).cuda()  # noqa: E731
+    layer_args = types.SimpleNamespace(cuda=True)
+    outs = []
+    for use_graph in (False, True):
+        env = S.UnicycleEnv(num_envs=B)
+        layer = S.CBFQPLayer(env, layer_args, gamma_b=20, k_d=3.0, l_p=0.03)
+        env.reset()
+        env.state = dev(st)
+        a_, m_, s_ = dev(ac), dev(mu), dev(sg)
+        if use_graph:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                env.safe_step(layer, a_, m_, s_)              # warm-up on the capture stream (buffers, attributes)
+            torch.cuda.current_stream().wait_stream(side)
+            env.reset()
+            env.state = dev(st)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                env.safe_step(layer, a_, m_, s_)
+            env.reset()
+            env.state = dev(st)
+            for _ in range(3):
+                g.replay()
+        else:
+            for _ in range(3):
+                env.safe_step(layer, a_, m_, s_)
+        torch.cuda.synchronize()
+        outs.append((env.state.clone(), env._safe_action.clone(), env._obs.clone(), env._reward.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
