@@ -347,6 +347,21 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     out["config3_unicycle_b512_fwd_bwd_us"] = 1e3 * ms
     ms = _time_calls(lambda: layc.get_safe_action(stc[:b], acc[:b], muc[:b], sgc[:b]), 50, device)
     out["config2_cars_b512_fwd_us"] = 1e3 * ms
+    # (c2) the same small batch as a captured CUDA graph of 16 fused steps (what a launch-bound rollout loop should do)
+    envs_ = S.UnicycleEnv(num_envs=b, device=device, auto_reset=True)
+    envs_.reset()
+    side = torch.cuda.Stream(device=device)
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        envs_.safe_step(layer, a5, m5, g5)
+    torch.cuda.current_stream(device).wait_stream(side)
+    ms_eager = _time_calls(lambda: envs_.safe_step(layer, a5, m5, g5), 50, device)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for _ in range(16):
+            envs_.safe_step(layer, a5, m5, g5)
+    ms_graph = _time_calls(graph.replay, 20, device) / 16
+    out["unicycle_b512_safe_step_us"] = {"eager": 1e3 * ms_eager, "cuda_graph_of_16": 1e3 * ms_graph}
     layer.check_nan = True
     # (d) SURVEY 8f row 1: disturbance-GP posterior in front of the same step.  History = 3000 transitions (the
     # reference's --gp_model_size, main.py:247) of the Unicycle's true drag disturbance (unicycle_env.py:87) + noise;
