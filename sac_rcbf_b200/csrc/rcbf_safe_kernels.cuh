@@ -88,6 +88,7 @@ struct UniArgs {
 template <bool kFused>
 struct UniEnv {
   static constexpr int NZ = kUniNZ, M = kUniM, NU = 2;
+  static constexpr bool kTileFinish = false;
   static constexpr int kMinBlocks = RCBF_MINB;
   static constexpr bool kPdlPass1 = true;   // see launch_pdl: the presolve kernel fills the register file exactly
   using Pat = UniPat;
@@ -266,6 +267,10 @@ struct CarsArgs {
 template <bool kFused>
 struct CarsEnv {
   static constexpr int NZ = kCarsNZ, M = kCarsM, NU = 1;
+#ifndef RCBF_CARS_TILE_FINISH
+#define RCBF_CARS_TILE_FINISH 1
+#endif
+  static constexpr bool kTileFinish = kFused && RCBF_CARS_TILE_FINISH;  // see finish_tile
   static constexpr int kMinBlocks = kFused ? RCBF_MINB_CARS : RCBF_MINB;  // get_safe_action alone: 4 is faster (A/B)
   static constexpr bool kPdlPass1 = false;  // measured: -16 % when pass 1 is launched as a dependent
   using Pat = CarsPat;
@@ -411,6 +416,59 @@ struct CarsEnv {
       a.t[i] = in.tt;
       a.step[i] = in.stp;
     }
+  }
+  // Warp-collective finish of the lanes that finish their OWN instance of a full, bulk-staged tile (job A).  The rows of
+  // `state` and `obs` are 40 bytes: a lane-per-row access pattern touches every 32-byte sector of the 1280-byte tile
+  // span five times (five 8-byte accesses at a 40-byte stride), and that request count -- not bytes, not latency --
+  // is what bounds this kernel.  Here the input row comes from the TMA landing buffer, the new state / observation
+  // rows go back into that buffer (the sigma half is free by now) and leave through ten fully coalesced, owner-masked
+  // 128-byte stores each: 1/5 of the sector requests.  `on` lanes only; all 32 lanes must call.
+  __device__ static __forceinline__ void finish_tile(const Args& a, const Params& p, const EnvParams& e, int64_t i0,
+                                                     int lane, bool on, Inst& in, const float xs[NU], int status,
+                                                     Stage& sg_) {
+    float s[10];
+    CarsEnvOut<float> o;
+    const int64_t i = i0 + lane;
+    if (on) {
+      const float us = clampf(in.u[0] + xs[0], p.u_min, p.u_max);  // diff_cbf_qp.py:77
+      a.out[i] = us;
+      if (a.status != nullptr) a.status[i] = status;
+      const float2* sp = reinterpret_cast<const float2*>(sg_.st) + lane * 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const float2 q = sp[k];
+        s[2 * k] = q.x; s[2 * k + 1] = q.y;
+      }
+      cars_env_step<float>(e, s, in.tt, in.stp, us, o);
+      a.reward[i] = o.reward;
+      a.done[i] = (uint8_t)o.done;
+      a.cost[i] = o.cost;
+      a.t[i] = in.tt;
+      a.step[i] = in.stp;
+      float2* wp = reinterpret_cast<float2*>(sg_.st) + lane * 5;   // own row: nobody else reads or writes it
+      float2* op = reinterpret_cast<float2*>(sg_.sg) + lane * 5;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        wp[k] = make_float2(s[2 * k], s[2 * k + 1]);
+        op[k] = make_float2(o.obs[2 * k], o.obs[2 * k + 1]);
+      }
+    }
+    const unsigned owners = __ballot_sync(0xffffffffu, on);
+    __syncwarp();
+    float* gs = a.state + i0 * 10;
+    float* go = a.obs + i0 * 10;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const int w = r * 32 + lane;
+      const int owner = (w * 205) >> 11;  // w / 10 for w < 1024
+      if ((owners >> owner) & 1u) {
+        gs[w] = sg_.st[w];
+        go[w] = sg_.sg[w];
+      }
+    }
+    // the buffer is handed back to the async proxy (next bulk copy) only after these generic-proxy accesses
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
   }
 };
 
@@ -675,6 +733,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
     Inst inA;
     float xsA[NU];
     int stA = RCBF_OK_TRIVIAL;
+    int stageA = -1;  // landing buffer that still holds this iteration's tile (bulk-staged full tiles only)
 
     if (have_tile) {  // ---- A-step: assemble, classify, queue
       const int64_t i0 = ((int64_t)tile << 5) + lane;
@@ -685,6 +744,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
         // this tile's inputs were bulk-copied into shared memory one iteration ago; wait, read, then put the NEXT
         // tile in flight into the other buffer (its last reader finished before the previous __syncwarp)
         const int b = nbulk & 1;
+        stageA = b;
         mbar_wait(&sh.bar[b], (nbulk >> 1) & 1);
         E::read_stage(sh.stage[b], lane, inA, aux);
         __syncwarp();
@@ -764,6 +824,12 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
         if (on) E::load_inst(a, i, in);
         fhead = (fhead + take) & (kFin - 1);
         fn -= take;
+      }
+      if constexpr (E::kTileFinish) {
+        if (j == 0 && stageA >= 0) {
+          E::finish_tile(a, p, e, iA - lane, lane, on, in, xs, stv, sh.stage[stageA]);
+          continue;
+        }
       }
       if (on) E::finish(a, p, e, i, in, xs, stv);
       __syncwarp();
