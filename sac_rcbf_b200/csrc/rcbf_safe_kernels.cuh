@@ -34,6 +34,9 @@ namespace rcbf {
 #ifndef RCBF_MINB
 #define RCBF_MINB 4  // resident blocks per SM the presolve-mode kernel is compiled for (128 registers; A/B on B200: 4 > 3 > 5)
 #endif
+#ifndef RCBF_MINB_PDIPM
+#define RCBF_MINB_PDIPM 2  // interior-point ("pdipm") mode: the iteration state wants the registers
+#endif
 #ifndef RCBF_MINB_CARS
 #define RCBF_MINB_CARS 3  // SimulatedCars fused step: 3 (168 registers, no spills in the loop) > 2 > 4 > 5 > 6 on B200 --
 #endif                    // that kernel is bound by memory-system requests (40-byte rows), not by latency hiding
@@ -688,7 +691,7 @@ __device__ __noinline__ void tail_scan(const typename E::Args a, int64_t n, cons
 
 template <class E, int kMode /* 0 presolve, 1 pdipm */, bool kBulk /* TMA bulk-copy input staging */,
           bool kSaved /* also write x / lam / slack / iters (backward pass, diagnostics) */>
-__global__ void __launch_bounds__(kThreadsW, kMode == 0 ? E::kMinBlocks : 2)
+__global__ void __launch_bounds__(kThreadsW, kMode == 0 ? E::kMinBlocks : RCBF_MINB_PDIPM)
 k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParams e, rcbf_counters_t* ws) {
   constexpr int NZ = E::NZ, M = E::M, NU = E::NU, NWR = E::NWR;
   using Inst = typename E::Inst;
@@ -1079,7 +1082,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   if (n > 0x7fffffffLL) return -2;  // ring indices are 32-bit
   const int64_t ntiles = (n + 31) / 32;
   const int64_t want = (ntiles + kWarps - 1) / kWarps;
-  const int resident = 148 * (p.solver_mode == 0 ? E::kMinBlocks : 2);  // persistent: one wave of resident blocks
+  const int resident = 148 * (p.solver_mode == 0 ? E::kMinBlocks : RCBF_MINB_PDIPM);  // persistent: one wave of resident blocks
   const int grid = (int)(want < resident ? want : resident);
   const int64_t fb = (n + 127) / 128;
   const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);
