@@ -67,3 +67,40 @@ def test_core_on_golden_batches(golden):
     g = golden("cars_layer_b512.npz")
     o = sim.cars_safe_action(g["state"], g["action"], g["sigma"], PR.cars_params(gamma_b=20.0))
     assert np.abs(o["out"] - g["safe_action"]).max() < 1e-4
+
+
+def test_core_kkt_conditions_on_extreme_inputs():
+    """Host build of the kernel source on the stress distribution of the GPU suite (actions up to the actuator limits,
+    disturbance std up to 15x MAX_STD, all instances around the hazards): whatever status the solver reports as solved
+    must BE the optimum of the normalised QP it was given -- stationarity, primal / dual feasibility, complementarity
+    in float64 -- including the instances the greedy presolve leaves pending (a drop is needed), which the host driver
+    hands to the full chain (float32 interior point + certificate, float64 interior point) like pass 2 does."""
+    B = 6000
+    rng = np.random.default_rng(11)
+    hz = O.UNICYCLE["hazards_locations"]
+    idx = rng.integers(0, len(hz), B)
+    r, phi = rng.uniform(0.3, 1.2, B), rng.uniform(-np.pi, np.pi, B)
+    st = np.stack([hz[idx, 0] + r * np.cos(phi), hz[idx, 1] + r * np.sin(phi), rng.uniform(-np.pi, np.pi, B)], 1)
+    ac, mu, sg = rng.uniform(-2.5, 2.5, (B, 2)), rng.uniform(-0.5, 0.5, (B, 3)), rng.uniform(0, 3.0, (B, 3))
+    params = PR.unicycle_params(gamma_b=20.0)
+    pdiag = np.array([1.0, 1e-2, 1e5])
+
+    def kkt(o, sel):
+        Gn, hn = o["Gn"][sel].astype(np.float64), o["hn"][sel].astype(np.float64)
+        x, lam = o["x"][sel], o["lam"][sel]
+        slack = hn - np.einsum("bmj,bj->bm", Gn, x)
+        stat = pdiag[None] * x + np.einsum("bmj,bm->bj", Gn, lam)
+        scale = 1.0 + np.abs(pdiag[None] * x).max(1)
+        return slack.min(), lam.min(), (np.abs(lam * slack) / (1.0 + lam)).max(), (np.abs(stat).max(1) / scale).max()
+
+    fast = sim.unicycle_safe_action(st, ac, mu, sg, params, mode=0)
+    assert (fast["status"] <= 2).all()
+    chained = fast["iters"] >= 1000           # the host driver ran the fallback chain for these (pending after pass 1)
+    assert 10 < chained.sum() < 0.03 * B
+    smin, lmin, comp, stat = kkt(fast, ~chained)
+    assert smin > -1e-8 and lmin >= 0.0 and comp < 1e-8 and stat < 1e-7, (smin, lmin, comp, stat)   # multipliers reach 1e5
+    smin, lmin, comp, stat = kkt(fast, chained)
+    assert smin > -1e-7 and lmin >= -1e-9 and comp < 1e-5 and stat < 1e-5, (smin, lmin, comp, stat)
+    # and the interior-point-only mode agrees with the presolve mode
+    ipm = sim.unicycle_safe_action(st, ac, mu, sg, params, mode=1)
+    assert (ipm["status"] <= 2).all() and np.abs(ipm["out"] - fast["out"]).max() < 1e-5
