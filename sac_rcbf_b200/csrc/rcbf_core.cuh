@@ -1084,17 +1084,44 @@ RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_d
   for (int j = 0; j < NZ; ++j) o.x[j] = y[j] * pisd[j];
 }
 
-// trivial test on the RAW rows (n_i > 0, so h~_i >= 0 <=> h_i >= 0): x = 0 is optimal iff every h_i >= 0
+// NaN-PROPAGATING 3-input min / max (one FMNMX3.NAN on sm_100): the result is NaN iff any input is
+RCBF_HD float nanmin3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("min.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+#else
+  return (a != a || b != b || c != c) ? NAN : fminf(fminf(a, b), c);
+#endif
+}
+RCBF_HD float nanmax3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("max.NaN.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+#else
+  return (a != a || b != b || c != c) ? NAN : fmaxf(fmaxf(a, b), c);
+#endif
+}
+// "is any of these K words NaN", K >= 1: a NaN-propagating max chain, (K + 1) / 2 instructions + one compare
+template <int K>
+RCBF_HD bool any_nan(const float* w) {
+  float m = w[0];
+  RCBF_UNROLL
+  for (int k = 1; k + 1 < K; k += 2) m = nanmax3(m, w[k], w[k + 1]);
+  if ((K & 1) == 0) m = nanmax3(m, w[K - 1], w[K - 1]);
+  return m != m;
+}
+
+// trivial test on the RAW rows (n_i > 0, so h~_i >= 0 <=> h_i >= 0): x = 0 is optimal iff every h_i >= 0.
+// One NaN-propagating min over the rows answers both questions: NaN -> some h_i is NaN, else trivial iff min >= 0.
 template <int M>
 RCBF_HD void classify_raw(const float h[M], bool& triv, bool& nan) {
-  // min over the rows (fminf skips NaN entries; `nan` reports those): 3-input FMNMX on sm_100, half the compares
   float m = h[0];
-  nan = (h[0] != h[0]);
   RCBF_UNROLL
-  for (int i = 1; i < M; ++i) {
-    m = fminf(m, h[i]);
-    nan = nan || (h[i] != h[i]);
-  }
+  for (int i = 1; i + 1 < M; i += 2) m = nanmin3(m, h[i], h[i + 1]);
+  if ((M & 1) == 0) m = nanmin3(m, h[M - 1], h[M - 1]);
+  nan = (m != m);
   triv = (m >= 0.f);
 }
 

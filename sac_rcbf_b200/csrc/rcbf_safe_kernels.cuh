@@ -192,8 +192,8 @@ struct UniEnv {
     for (int r = 0; r < kUniHaz; ++r) {
       w[2 * r] = raw.G[r][0];
       w[2 * r + 1] = raw.G[r][1];
-      nan = nan || (raw.G[r][0] != raw.G[r][0]) || (raw.G[r][1] != raw.G[r][1]);
     }
+    nan = nan || any_nan<2 * kUniHaz>(w);
 #pragma unroll
     for (int r = 0; r < M; ++r) w[10 + r] = raw.h[r];
   }
@@ -366,7 +366,7 @@ struct CarsEnv {
     classify_raw<M>(raw.h, triv, nan);
     w[0] = raw.G[0][0];
     w[1] = raw.G[1][0];
-    nan = nan || (w[0] != w[0]) || (w[1] != w[1]);
+    nan = nan || any_nan<2>(w);
 #pragma unroll
     for (int r = 0; r < M; ++r) w[2 + r] = raw.h[r];
   }
