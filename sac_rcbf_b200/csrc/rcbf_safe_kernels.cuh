@@ -1,13 +1,15 @@
 // rcbf_safe_kernels.cuh -- the hot kernels: get_safe_action forward (K2+K3) and the fused safe step (K5).
 //
 // One lane owns one instance; warps are persistent and walk 32-instance tiles (coalesced row-major loads).
-// Per tile ("A-step") every lane assembles the constraints in the reference's float32 op order, normalises the rows
-// and runs the trivial test (h~ >= 0 on every row  <=>  x = 0 is optimal, ~2/3 of the synthetic instances); trivial
-// lanes finish right there (clamp, env.step, outputs).  Lanes whose instance needs a solve push its packed problem
-// (28 words Unicycle / 10 words SimulatedCars + the instance index) into a WARP-PRIVATE ring in shared memory.
-// Whenever the ring holds >= 32 problems the warp runs a "B-step": all 32 lanes solve one problem each (greedy
-// active-set presolve + float64 KKT certificate, or the float32 interior point in "pdipm" mode), reload the 28 bytes
-// of instance inputs they need and finish that instance.  So the expensive phase always runs with full warps (without
+// The inputs of the NEXT tile arrive by TMA bulk copies (cp.async.bulk + mbarrier, double buffered) while the warp
+// works.  Per tile ("A-step") every lane assembles the constraints in the reference's float32 op order and runs the
+// trivial test on the raw rows (h >= 0 on every row  <=>  x = 0 is optimal, ~2/3 of the synthetic instances); trivial
+// lanes finish right there (clamp, env.step, outputs).  Lanes whose instance needs a solve push its raw rows (19 words
+// Unicycle / 6 words SimulatedCars, the constant entries are not stored, + the instance index) into a WARP-PRIVATE
+// ring in shared memory.  Whenever the ring holds >= 32 problems the warp runs a "B-step": all 32 lanes normalise and
+// solve one problem each (greedy active-set presolve + float64 KKT certificate, or the float32 interior point in
+// "pdipm" mode); after the next A-step they reload the 28 bytes of instance inputs they need and finish that instance
+// through the same (single) copy of the finish code.  So the expensive phase always runs with full warps (without
 // compaction it ran at ~35 % lane utilisation), and there is no block-wide barrier anywhere: warps never wait for
 // each other (until the very end of the kernel).
 //
