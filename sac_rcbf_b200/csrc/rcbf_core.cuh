@@ -66,21 +66,21 @@ RCBF_HD double t_rsqrt(double a) {
 
 // single-rounding float ops that the compiler may not contract into FMAs (reference-order assembly)
 RCBF_HD float mul_rn(float a, float b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(RCBF_EXP_CONTRACT)  // (experiment switch: let nvcc contract the assembly)
   return __fmul_rn(a, b);
 #else
   return a * b;  // host build uses -ffp-contract=off
 #endif
 }
 RCBF_HD float add_rn(float a, float b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(RCBF_EXP_CONTRACT)
   return __fadd_rn(a, b);
 #else
   return a + b;
 #endif
 }
 RCBF_HD float sub_rn(float a, float b) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(RCBF_EXP_CONTRACT)
   return __fsub_rn(a, b);
 #else
   return a - b;
