@@ -42,6 +42,36 @@ __device__ __forceinline__ void store_row(T* __restrict__ base, int64_t i, const
   for (int j = 0; j < K; ++j) base[i * K + j] = in[j];
 }
 
+// Rows of K words per instance, one instance per thread.  A lane-per-row access pattern makes each of a warp's K
+// load / store instructions touch EVERY 32-byte sector of the warp's span (K-fold request amplification on the L1 -> L2
+// path, the limiter of these streaming kernels on B200); staging the block's rows through shared memory makes every
+// global access fully coalesced.  All threads of the block must call (rows beyond n read as zero / are not written).
+template <typename T, int K>
+struct BlockRows {
+  T* buf;  // kThreads * K words of shared memory, reused by successive calls
+  __device__ explicit BlockRows(T* b) : buf(b) {}
+  __device__ __forceinline__ void load(const T* __restrict__ base, int64_t i0, int64_t n, T row[K]) {
+    const int cnt = (int)((n - i0) < (int64_t)kThreads ? (n - i0) : (int64_t)kThreads);
+    const T* __restrict__ src = base + i0 * K;
+    __syncthreads();
+    for (int w = threadIdx.x; w < cnt * K; w += kThreads) buf[w] = __ldg(src + w);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) row[k] = ((int)threadIdx.x < cnt) ? buf[threadIdx.x * K + k] : T(0);
+  }
+  __device__ __forceinline__ void store(T* __restrict__ base, int64_t i0, int64_t n, const T row[K]) {
+    const int cnt = (int)((n - i0) < (int64_t)kThreads ? (n - i0) : (int64_t)kThreads);
+    T* __restrict__ dst = base + i0 * K;
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) buf[threadIdx.x * K + k] = row[k];
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < cnt * K; w += kThreads) dst[w] = buf[w];
+  }
+};
+
 // block-level accumulation of the solver counters (rare events -> rare atomics)
 __device__ __forceinline__ void accumulate_counters(rcbf_counters_t* counters, bool valid, int status, int iters) {
   if (counters == nullptr) return;
@@ -209,28 +239,35 @@ __global__ void __launch_bounds__(kThreads)
 k_unicycle_env_step(T* __restrict__ state4, int32_t* __restrict__ step, const T* __restrict__ action, int64_t n,
                     UnicycleEnvParams e, T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done,
                     T* __restrict__ cost, uint8_t* __restrict__ goal_met) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
-  T v[4], a[2];
-  load_state4<T>(state4, i, v);
-  load_row<2>(action, i, a);
-  int stp = step[i];
+  __shared__ T s_rows[kThreads * 7];
+  BlockRows<T, 7> rows(s_rows);
+  const int64_t i0 = (int64_t)blockIdx.x * kThreads;
+  const int64_t i = i0 + threadIdx.x;
+  const bool valid = i < n;
   UniEnvOut<T> o;
-  if constexpr (sizeof(T) == 4) {
-    float s0, c0;
-    sincos_t(v[2], &s0, &c0);
-    unicycle_env_step_sc(e, v, v[3], stp, a, s0, c0, o);
-  } else {
-    unicycle_env_step<T>(e, v, v[3], stp, a, o);
+#pragma unroll
+  for (int k = 0; k < 7; ++k) o.obs[k] = T(0);
+  if (valid) {
+    T v[4], a[2];
+    load_state4<T>(state4, i, v);
+    load_row<2>(action, i, a);
+    int stp = step[i];
+    if constexpr (sizeof(T) == 4) {
+      float s0, c0;
+      sincos_t(v[2], &s0, &c0);
+      unicycle_env_step_sc(e, v, v[3], stp, a, s0, c0, o);
+    } else {
+      unicycle_env_step<T>(e, v, v[3], stp, a, o);
+    }
+    reward[i] = o.reward;
+    done[i] = (uint8_t)o.done;
+    cost[i] = o.cost;
+    goal_met[i] = (uint8_t)o.goal_met;
+    if (e.auto_reset && o.done) unicycle_reset<T>(e, v, v[3], stp);
+    store_state4<T>(state4, i, v);
+    step[i] = stp;
   }
-  store_row<7>(obs, i, o.obs);
-  reward[i] = o.reward;
-  done[i] = (uint8_t)o.done;
-  cost[i] = o.cost;
-  goal_met[i] = (uint8_t)o.goal_met;
-  if (e.auto_reset && o.done) unicycle_reset<T>(e, v, v[3], stp);
-  store_state4<T>(state4, i, v);
-  step[i] = stp;
+  rows.store(obs, i0, n, o.obs);
 }
 
 template <typename T>
@@ -262,21 +299,28 @@ __global__ void __launch_bounds__(kThreads)
 k_cars_env_step(T* __restrict__ state, T* __restrict__ t, int32_t* __restrict__ step, const T* __restrict__ action,
                 int64_t n, CarsEnvParams e, T* __restrict__ obs, T* __restrict__ reward, uint8_t* __restrict__ done,
                 T* __restrict__ cost) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
+  __shared__ T s_rows[kThreads * 10];
+  BlockRows<T, 10> rows(s_rows);
+  const int64_t i0 = (int64_t)blockIdx.x * kThreads;
+  const int64_t i = i0 + threadIdx.x;
+  const bool valid = i < n;
   T s[10];
-  load_row<10>(state, i, s);
-  T tt = t[i];
-  int stp = step[i];
+  rows.load(state, i0, n, s);
   CarsEnvOut<T> o;
-  cars_env_step<T>(e, s, tt, stp, action[i], o);
-  store_row<10>(obs, i, o.obs);
-  reward[i] = o.reward;
-  done[i] = (uint8_t)o.done;
-  cost[i] = o.cost;
-  store_row<10>(state, i, s);
-  t[i] = tt;
-  step[i] = stp;
+#pragma unroll
+  for (int k = 0; k < 10; ++k) o.obs[k] = T(0);
+  if (valid) {
+    T tt = t[i];
+    int stp = step[i];
+    cars_env_step<T>(e, s, tt, stp, action[i], o);
+    reward[i] = o.reward;
+    done[i] = (uint8_t)o.done;
+    cost[i] = o.cost;
+    t[i] = tt;
+    step[i] = stp;
+  }
+  rows.store(obs, i0, n, o.obs);
+  rows.store(state, i0, n, s);
 }
 
 template <typename T>
@@ -308,8 +352,8 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_unicycle_predict_next(const T* __restrict__ state, const T* __restrict__ action, const T* __restrict__ mean, int64_t n,
                         T dt, T* __restrict__ next) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;  // (3-word rows: staging through shared memory
+  if (i >= n) return;                                              //  measured slower than the direct accesses)
   T s[3], u[2], m[3] = {T(0), T(0), T(0)}, nx[3];
   load_row<3>(state, i, s);
   load_row<2>(action, i, u);
@@ -322,15 +366,18 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_cars_predict_next(const T* __restrict__ state, const T* __restrict__ action, const T* __restrict__ t,
                     const T* __restrict__ mean, int64_t n, T dt, T kp, T kb, T* __restrict__ next) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
+  __shared__ T s_rows[kThreads * 10];
+  BlockRows<T, 10> rows(s_rows);
+  const int64_t i0 = (int64_t)blockIdx.x * kThreads;
+  const int64_t i = i0 + threadIdx.x;
   T s[10], m[10], nx[10];
-  load_row<10>(state, i, s);
+  rows.load(state, i0, n, s);
 #pragma unroll
   for (int j = 0; j < 10; ++j) m[j] = T(0);
-  if (mean != nullptr) load_row<10>(mean, i, m);
-  cars_prior_next<T>(dt, kp, kb, s, action[i], t[i], m, nx);
-  store_row<10>(next, i, nx);
+  if (mean != nullptr) rows.load(mean, i0, n, m);
+  const T a = (i < n) ? action[i] : T(0), tt = (i < n) ? t[i] : T(0);
+  cars_prior_next<T>(dt, kp, kb, s, a, tt, m, nx);
+  rows.store(next, i0, n, nx);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -341,7 +388,7 @@ __global__ void __launch_bounds__(kThreads)
 k_unicycle_rollout_step(const T* __restrict__ obs, const T* __restrict__ action, const T* __restrict__ mean,
                         const T* __restrict__ std, const T* __restrict__ eps, int64_t n, T dt, T gx, T gy,
                         T* __restrict__ next_obs, T* __restrict__ reward, uint8_t* __restrict__ done) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;  // (short rows: direct accesses measured faster)
   if (i >= n) return;
   T o[7], a[2], m[3] = {T(0), T(0), T(0)}, sd[3] = {T(0), T(0), T(0)}, e[3] = {T(0), T(0), T(0)}, no[7], r;
   int d;
@@ -364,23 +411,28 @@ k_cars_rollout_step(const T* __restrict__ obs, const T* __restrict__ action, con
                     const T* __restrict__ mean, const T* __restrict__ std, const T* __restrict__ eps, int64_t n, T dt,
                     T kp, T kb, int max_steps, T* __restrict__ next_obs, T* __restrict__ reward,
                     uint8_t* __restrict__ done, T* __restrict__ next_t) {
-  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= n) return;
+  __shared__ T s_rows[kThreads * 10];
+  BlockRows<T, 10> rows(s_rows);
+  const int64_t i0 = (int64_t)blockIdx.x * kThreads;
+  const int64_t i = i0 + threadIdx.x;
   T o[10], m[10], sd[10], e[10], no[10], r, nt;
   int d;
-  load_row<10>(obs, i, o);
+  rows.load(obs, i0, n, o);
 #pragma unroll
   for (int j = 0; j < 10; ++j) m[j] = sd[j] = e[j] = T(0);
-  if (mean != nullptr) load_row<10>(mean, i, m);
+  if (mean != nullptr) rows.load(mean, i0, n, m);
   if (std != nullptr && eps != nullptr) {
-    load_row<10>(std, i, sd);
-    load_row<10>(eps, i, e);
+    rows.load(std, i0, n, sd);
+    rows.load(eps, i0, n, e);
   }
-  cars_rollout_step<T>(dt, kp, kb, max_steps, o, action[i], t[i], m, sd, e, no, r, d, nt);
-  store_row<10>(next_obs, i, no);
-  reward[i] = r;
-  done[i] = (uint8_t)d;
-  next_t[i] = nt;
+  const T a = (i < n) ? action[i] : T(0), tt = (i < n) ? t[i] : T(0);
+  cars_rollout_step<T>(dt, kp, kb, max_steps, o, a, tt, m, sd, e, no, r, d, nt);
+  rows.store(next_obs, i0, n, no);
+  if (i < n) {
+    reward[i] = r;
+    done[i] = (uint8_t)d;
+    next_t[i] = nt;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
