@@ -8,8 +8,12 @@
 // Unicycle / 6 words SimulatedCars, the constant entries are not stored, + the instance index) into a WARP-PRIVATE
 // ring in shared memory.  Whenever the ring holds >= 32 problems the warp runs a "B-step": all 32 lanes normalise and
 // solve one problem each (greedy active-set presolve + float64 KKT certificate, or the float32 interior point in
-// "pdipm" mode); after the next A-step they reload the 28 bytes of instance inputs they need and finish that instance
-// through the same (single) copy of the finish code.  So the expensive phase always runs with full warps (without
+// "pdipm" mode).  Unicycle, presolve mode ("merged finish"): the solving lane puts (index, correction, status, sin, cos)
+// into a warp-private finish ring and starts cp.async copies of the instance's 28 bytes of finish inputs into it; in
+// the finish pass of a LATER tile every lane whose own instance went to the problem ring takes one entry, so the
+// finish code runs with (nearly) full warps too.  SimulatedCars (whole-tile finish) and pdipm mode keep the earlier
+// scheme: the lanes reload their instance after the next A-step and run a second finish pass.
+// So the expensive phase always runs with full warps (without
 // compaction it ran at ~35 % lane utilisation), and there is no block-wide barrier anywhere: warps never wait for
 // each other (until the very end of the kernel).
 //
@@ -118,6 +122,57 @@ struct UniEnv {
     }
     ld_row<2>(a.ac, i, in.u);
     sincos_t(in.v[2], &in.sn, &in.cs);
+  }
+  // Merged finish (presolve mode): a solved instance is finished by a lane that is idle in a LATER tile's finish pass
+  // (a lane whose own instance went to the ring), so the finish code runs once per tile instead of 1.35 times.  The
+  // lane that solved it starts cp.async copies of the instance's finish inputs into the finish ring (they land during
+  // the next A-step: no register is held and nobody waits for the L2 round trip); the sin / cos of the heading travel
+  // with the problem through the rings instead of being recomputed.
+#ifndef RCBF_MERGE_FINISH
+#define RCBF_MERGE_FINISH 1
+#endif
+  static constexpr bool kMergeFinish = RCBF_MERGE_FINISH;
+  static constexpr int NSC = 2;
+  __device__ static __forceinline__ void stash(const Inst& in, float s[NSC]) {
+    s[0] = in.sn;
+    s[1] = in.cs;
+  }
+  template <int K>
+  struct alignas(16) FinRing {
+    float4 st[kFused ? K : 1];
+    float2 ac[K];
+    int step[kFused ? K : 1];
+    float sn[K], cs[K];
+  };
+  template <int K, bool kAc8>
+  __device__ static __forceinline__ void fin_fetch(const Args& a, int64_t i, FinRing<K>& f, int fs, const float s[NSC]) {
+    if (kFused) {
+      cp_async<16>(&f.st[fs], a.state4 + i * 4);
+      cp_async<4>(&f.step[fs], a.step + i);
+    }
+    if (kAc8) {
+      cp_async<8>(&f.ac[fs], a.ac + i * 2);
+    } else {
+      cp_async<4>(&f.ac[fs].x, a.ac + i * 2);
+      cp_async<4>(&f.ac[fs].y, a.ac + i * 2 + 1);
+    }
+    f.sn[fs] = s[0];
+    f.cs[fs] = s[1];
+  }
+  template <int K>
+  __device__ static __forceinline__ void fin_read(const FinRing<K>& f, int fs, Inst& in) {
+    if (kFused) {
+      const float4 q = f.st[fs];
+      in.v[0] = q.x; in.v[1] = q.y; in.v[2] = q.z; in.v[3] = q.w;
+      in.stp = f.step[fs];
+    } else {
+      in.v[0] = in.v[1] = in.v[2] = in.v[3] = 0.f;  // the layer's finish only clamps action + correction
+      in.stp = 0;
+    }
+    const float2 u2 = f.ac[fs];
+    in.u[0] = u2.x; in.u[1] = u2.y;
+    in.sn = f.sn[fs];
+    in.cs = f.cs[fs];
   }
   // raw rows in NWR = 19 words: (G[i][0], G[i][1]) of the 5 CBF rows + the 9 h; the rest of G is constant
   static constexpr int NWR = 19;
@@ -297,6 +352,17 @@ struct CarsEnv {
       in.stp = 0;
     }
   }
+  static constexpr bool kMergeFinish = false;  // the fused step finishes whole tiles (finish_tile)
+  static constexpr int NSC = 1;
+  __device__ static __forceinline__ void stash(const Inst&, float s[NSC]) { s[0] = 0.f; }
+  template <int K>
+  struct FinRing {
+    int unused;
+  };
+  template <int K, bool kAc8>
+  __device__ static __forceinline__ void fin_fetch(const Args&, int64_t, FinRing<K>&, int, const float[NSC]) {}
+  template <int K>
+  __device__ static __forceinline__ void fin_read(const FinRing<K>&, int, Inst&) {}
   static constexpr int NWR = 6;  // G[0][0], G[1][0] + the 4 h; the slack column and the actuator rows are constant
   struct Aux {
     float s[10], g[10];
@@ -507,12 +573,18 @@ constexpr int kThreadsW = 32 * kWarps;
 template <class E, int kMode>
 struct WarpShared {
   static constexpr int kRing = kMode == 0 ? 64 : 128;  // presolve: <= 31 left over + 32 new; pdipm: engine starts at 64
-  static constexpr int kFin = kMode == 0 ? 64 : 256;   // <= 31 left over + one solve phase's output
+  static constexpr bool kMerge = kMode == 0 && E::kMergeFinish;
+  // finish ring: pdipm <= 31 left over + one solve phase's output; merged presolve: 64 (a full-warp pass drains it
+  // whenever a B-step's output might not fit, see k_safe); plain presolve: unused
+  static constexpr int kFin = kMode == 0 ? (kMerge ? 64 : 32) : 256;
+  static constexpr int kScRing = kMerge ? kRing : 1;
   float w[E::NWR][kRing];
   int idx[kRing];
+  float sc[E::NSC][kScRing];   // merged finish: words that travel with the problem (Unicycle: sin, cos)
   float fx[E::NU][kFin];
   int fidx[kFin];
   int fst[kFin];
+  typename E::template FinRing<kMerge ? kFin : 1> fin;   // merged finish: the instance's finish inputs (cp.async)
   typename E::Stage stage[2];
   uint64_t bar[2];
 };
@@ -699,6 +771,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
   using Inst = typename E::Inst;
   using WS = WarpShared<E, kMode>;
   constexpr int kRing = WS::kRing, kFin = WS::kFin;
+  constexpr bool kMerge = WS::kMerge;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WS& sh = reinterpret_cast<WS*>(smem_raw)[warp];
@@ -773,6 +846,12 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
 #pragma unroll
         for (int k = 0; k < NWR; ++k) sh.w[k][slot] = w[k];
         sh.idx[slot] = (int)iA;
+        if constexpr (kMerge) {
+          float sc[E::NSC];
+          E::stash(inA, sc);
+#pragma unroll
+          for (int k = 0; k < E::NSC; ++k) sh.sc[k][slot] = sc[k];
+        }
       }
       onA = valid && !need;
       stA = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
@@ -790,6 +869,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       qn += __popc(ballot);
       tile += nw;
     }
+    if constexpr (kMerge) cp_async_wait_all();  // the finish inputs the previous B-step asked for have landed
     __syncwarp();
 
     // ---- finish (clamp, env.step, outputs): ONE copy of the code.  Pass 0 = job A; later passes = job B of the
@@ -801,7 +881,37 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       Inst in;
       float xs[NU];
       int stv;
-      if (j == 0) {
+      if constexpr (kMerge) {
+        // merged finish: pass 0 = job A, its idle lanes (own instance queued, or past the end) each take one solved
+        // instance from the finish ring.  A further pass with every lane idle runs while the ring could not take the
+        // next B-step's 32 results (such a pass is a full warp of useful work, so it costs no efficiency).
+        if (j > 0) {
+          if (fn <= kFin - 32) break;
+          onA = false;
+        }
+        on = onA;
+        i = iA;
+        in = inA;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) xs[c] = xsA[c];
+        stv = stA;
+        if (fn > 0) {
+          const unsigned idle = __ballot_sync(0xffffffffu, !onA);
+          const int r = __popc(idle & lt_mask);
+          if (!onA && r < fn) {
+            const int fs = (fhead + r) & (kFin - 1);
+            i = sh.fidx[fs];
+#pragma unroll
+            for (int c = 0; c < NU; ++c) xs[c] = sh.fx[c][fs];
+            stv = sh.fst[fs];
+            E::fin_read(sh.fin, fs, in);
+            on = true;
+          }
+          const int took = min(fn, __popc(idle));
+          fhead = (fhead + took) & (kFin - 1);
+          fn -= took;
+        }
+      } else if (j == 0) {
         on = onA;
         i = iA;
         in = inA;
@@ -845,8 +955,8 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       const int take = (qn >= 32) ? 32 : (have_tile ? 0 : qn);
       if (take > 0) {
 #ifndef RCBF_EXP_NOSOLVE  // (experiment switch: phase-1-only cost model, results are WRONG when defined)
+        const int slot = (head + lane) & (kRing - 1);
         if (lane < take) {
-          const int slot = (head + lane) & (kRing - 1);
           float w[NWR];
 #pragma unroll
           for (int k = 0; k < NWR; ++k) w[k] = sh.w[k][slot];
@@ -866,6 +976,22 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
             if (kSaved) write_saved<E>(a, iB, sol);
             c_iters += sol.iters;
           }
+        }
+        if constexpr (kMerge) {  // hand the solved instances to the finish ring (consumed by idle lanes of later finish passes)
+          const unsigned fb = __ballot_sync(0xffffffffu, onB);
+          if (onB) {
+            const int fs = (fhead + fn + __popc(fb & lt_mask)) & (kFin - 1);
+#pragma unroll
+            for (int c = 0; c < NU; ++c) sh.fx[c][fs] = xsB[c];
+            sh.fidx[fs] = iB;
+            sh.fst[fs] = stB;
+            float sc[E::NSC];
+#pragma unroll
+            for (int k = 0; k < E::NSC; ++k) sc[k] = sh.sc[k][slot];
+            E::template fin_fetch<kFin, kBulk>(a, iB, sh.fin, fs, sc);
+          }
+          fn += __popc(fb);
+          onB = false;
         }
 #endif
         head = (head + take) & (kRing - 1);

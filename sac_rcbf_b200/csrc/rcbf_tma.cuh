@@ -34,4 +34,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// ---- per-thread asynchronous copies (cp.async / LDGSTS, global -> shared): scattered rows a lane fetches for a later
+// consumer without holding registers or stalling on the L2 round trip
+template <int kBytes>
+__device__ __forceinline__ void cp_async(void* dst, const void* src) {
+  static_assert(kBytes == 4 || kBytes == 8 || kBytes == 16, "cp.async copies 4, 8 or 16 bytes");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(kBytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 }  // namespace rcbf
