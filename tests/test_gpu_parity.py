@@ -611,6 +611,61 @@ def test_fused_safe_step_equals_layer_then_env(S, uni, cars, B):
     assert torch.equal(us, us2) and torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(a.state, b.state)
 
 
+def test_fused_step_merged_finish_structured_need_patterns(S, uni):
+    """The Unicycle presolve kernel finishes a solved instance on a lane that is idle in a LATER tile (finish ring +
+    cp.async hand-over, `k_safe` merged finish).  Stress the hand-over with need/trivial patterns per tile ROUND (a
+    persistent warp walks tiles w, w + 2368, w + 2*2368 ...): rounds where every instance needs a solve, rounds where
+    none does, mixtures, and a ragged tail; then (i) the fused step must commute with a permutation of the instances
+    (another lane / ring slot finishes every instance), (ii) equal get_safe_action + env.step, (iii) agree with the
+    interior-point mode, whose finish path is the separate one."""
+    env, layer = uni
+    pool = 1 << 21
+    st, ac, mu, sg = O.synth_unicycle(pool, seed=4242)
+    status = _forward_with_aux(layer, st, ac, mu, sg)[4]
+    need_idx, triv_idx = np.flatnonzero(status != 0), np.flatnonzero(status == 0)
+    rng = np.random.default_rng(7)
+    rnd = 2368 * 32                                    # instances per round of the persistent grid (148 x 4 x 4 warps)
+    order, un, ut = [], 0, 0
+    for frac in (1.0, 1.0, 0.0, 0.97, 0.0, 0.5, 0.9, 0.0, 1.0, 0.35):
+        k = int(round(frac * rnd)) if frac < 1.0 else rnd
+        pick = np.concatenate([need_idx[un:un + k], triv_idx[ut:ut + rnd - k]])
+        un, ut = un + k, ut + rnd - k
+        order.append(rng.permutation(pick) if 0.0 < frac < 1.0 else pick)
+    order.append(np.concatenate([need_idx[un:un + 700], triv_idx[ut:ut + 301]]))   # ragged tail: 1001 instances
+    order = np.concatenate(order)
+    assert len(np.unique(order)) == len(order)
+    st, ac, mu, sg = st[order], ac[order], mu[order], sg[order]
+    B = len(order)
+
+    def fused(perm=None, solver="presolve"):
+        e = S.UnicycleEnv(num_envs=B)
+        sel = (lambda a: a) if perm is None else (lambda a: a[perm])
+        e.state = _cuda(sel(st))
+        layer.solver = solver
+        try:
+            us, obs, rew, done, info = e.safe_step(layer, _cuda(sel(ac)), _cuda(sel(mu)), _cuda(sel(sg)))
+            torch.cuda.synchronize()
+        finally:
+            layer.solver = "presolve"
+        return [t.cpu().numpy().copy() for t in (us, obs, rew, done, info["cost"], e.state)]
+
+    base = fused()
+    assert not np.isnan(base[0]).any() and np.isfinite(base[5]).all()
+    perm = rng.permutation(B)
+    for a, b in zip(fused(perm), base):
+        np.testing.assert_array_equal(a, b[perm])
+    e2 = S.UnicycleEnv(num_envs=B)
+    e2.state = _cuda(st)
+    us = layer.get_safe_action(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg))
+    o1, r1, d1, i1 = e2.step(us)
+    np.testing.assert_array_equal(us.cpu().numpy(), base[0])
+    np.testing.assert_array_equal(o1.cpu().numpy(), base[1])
+    np.testing.assert_array_equal(e2.state.cpu().numpy(), base[5])
+    alt = fused(solver="pdipm")
+    assert np.abs(alt[0] - base[0]).max() < 1e-5 and np.abs(alt[5] - base[5]).max() < 1e-5
+    assert (alt[0] == base[0]).all(1).mean() > 0.99
+
+
 # ----------------------------------------------------------------------------------------------------- full size
 def test_full_size_properties(uni):
     """BASELINE config 4 size (1M instances): size-independent properties instead of an oracle run."""
