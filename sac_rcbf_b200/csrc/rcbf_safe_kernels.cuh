@@ -138,29 +138,32 @@ struct UniEnv {
     s[1] = in.cs;
   }
   template <int K>
-  struct alignas(16) FinRing {
-    float4 st[kFused ? K : 1];
-    float2 ac[K];
-    int step[kFused ? K : 1];
-    float sn[K], cs[K];
+  struct alignas(16) FinRing {   // one entry = 3 x 128 bits + the step counter
+    float4 st[kFused ? K : 1];   // x, y, theta, last goal distance        (cp.async)
+    float4 res[K];               // correction x0, x1, instance index, status
+    float4 acsc[K];              // nominal action (cp.async), sin, cos
+    int step[kFused ? K : 1];    //                                        (cp.async)
   };
   template <int K, bool kAc8>
-  __device__ static __forceinline__ void fin_fetch(const Args& a, int64_t i, FinRing<K>& f, int fs, const float s[NSC]) {
+  __device__ static __forceinline__ void fin_fetch(const Args& a, int i, FinRing<K>& f, int fs, const float s[NSC],
+                                                   const float xs[NU], int status) {
     if (kFused) {
-      cp_async<16>(&f.st[fs], a.state4 + i * 4);
+      cp_async<16>(&f.st[fs], a.state4 + (int64_t)i * 4);
       cp_async<4>(&f.step[fs], a.step + i);
     }
+    float* acsc = reinterpret_cast<float*>(&f.acsc[fs]);
     if (kAc8) {
-      cp_async<8>(&f.ac[fs], a.ac + i * 2);
+      cp_async<8>(acsc, a.ac + (int64_t)i * 2);
     } else {
-      cp_async<4>(&f.ac[fs].x, a.ac + i * 2);
-      cp_async<4>(&f.ac[fs].y, a.ac + i * 2 + 1);
+      cp_async<4>(acsc, a.ac + (int64_t)i * 2);
+      cp_async<4>(acsc + 1, a.ac + (int64_t)i * 2 + 1);
     }
-    f.sn[fs] = s[0];
-    f.cs[fs] = s[1];
+    reinterpret_cast<float2*>(acsc)[1] = make_float2(s[0], s[1]);
+    f.res[fs] = make_float4(xs[0], xs[1], __int_as_float(i), __int_as_float(status));
   }
   template <int K>
-  __device__ static __forceinline__ void fin_read(const FinRing<K>& f, int fs, Inst& in) {
+  __device__ static __forceinline__ void fin_read(const FinRing<K>& f, int fs, Inst& in, float xs[NU], int64_t& i,
+                                                  int& status) {
     if (kFused) {
       const float4 q = f.st[fs];
       in.v[0] = q.x; in.v[1] = q.y; in.v[2] = q.z; in.v[3] = q.w;
@@ -169,10 +172,13 @@ struct UniEnv {
       in.v[0] = in.v[1] = in.v[2] = in.v[3] = 0.f;  // the layer's finish only clamps action + correction
       in.stp = 0;
     }
-    const float2 u2 = f.ac[fs];
-    in.u[0] = u2.x; in.u[1] = u2.y;
-    in.sn = f.sn[fs];
-    in.cs = f.cs[fs];
+    const float4 r = f.res[fs], c = f.acsc[fs];
+    xs[0] = r.x; xs[1] = r.y;
+    i = __float_as_int(r.z);
+    status = __float_as_int(r.w);
+    in.u[0] = c.x; in.u[1] = c.y;
+    in.sn = c.z;
+    in.cs = c.w;
   }
   // raw rows in NWR = 19 words: (G[i][0], G[i][1]) of the 5 CBF rows + the 9 h; the rest of G is constant
   static constexpr int NWR = 19;
@@ -194,7 +200,7 @@ struct UniEnv {
   __host__ __device__ static __forceinline__ bool aligned(const Args& a) {
     auto ok = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     return ok(kFused ? (const void*)a.state4 : (const void*)a.st) && ok(a.ac) && ok(a.mu) && ok(a.sg) &&
-           (!kFused || ok(a.step));
+           (!kFused || ok(a.step)) && (reinterpret_cast<uintptr_t>(a.out) & 7) == 0;
   }
   __device__ static __forceinline__ void issue(const Args& a, int64_t tile, Stage& sg_, uint64_t* bar) {
     const int64_t i0 = tile << 5;
@@ -283,12 +289,14 @@ struct UniEnv {
     assemble_raw(p, in, x, w, triv, nan);
     normalise_packed(w, p, nrm);
   }
+  template <bool kOut8 = false>  // kOut8: safe_action rows are 8-byte aligned (part of `aligned`), one 64-bit store
   __device__ static __forceinline__ void finish(const Args& a, const Params& p, const EnvParams& e, int64_t i, Inst& in,
                                                 const float xs[NU], int status) {
     float us[2];
 #pragma unroll
     for (int c = 0; c < 2; ++c) us[c] = clampf(in.u[c] + xs[c], p.u_min[c], p.u_max[c]);  // diff_cbf_qp.py:77
-    st_row<2>(a.out, i, us);
+    if (kOut8) reinterpret_cast<float2*>(a.out)[i] = make_float2(us[0], us[1]);
+    else st_row<2>(a.out, i, us);
     if (a.status != nullptr) a.status[i] = status;
     if (kFused) {
       UniEnvOut<float> o;
@@ -360,9 +368,10 @@ struct CarsEnv {
     int unused;
   };
   template <int K, bool kAc8>
-  __device__ static __forceinline__ void fin_fetch(const Args&, int64_t, FinRing<K>&, int, const float[NSC]) {}
+  __device__ static __forceinline__ void fin_fetch(const Args&, int, FinRing<K>&, int, const float[NSC], const float[NU],
+                                                   int) {}
   template <int K>
-  __device__ static __forceinline__ void fin_read(const FinRing<K>&, int, Inst&) {}
+  __device__ static __forceinline__ void fin_read(const FinRing<K>&, int, Inst&, float[NU], int64_t&, int&) {}
   static constexpr int NWR = 6;  // G[0][0], G[1][0] + the 4 h; the slack column and the actuator rows are constant
   struct Aux {
     float s[10], g[10];
@@ -459,6 +468,7 @@ struct CarsEnv {
     assemble_raw(p, in, x, w, triv, nan);
     normalise_packed(w, p, nrm);
   }
+  template <bool kOut8 = false>
   __device__ static __forceinline__ void finish(const Args& a, const Params& p, const EnvParams& e, int64_t i, Inst& in,
                                                 const float xs[NU], int status) {
     const float us = clampf(in.u[0] + xs[0], p.u_min, p.u_max);  // diff_cbf_qp.py:77
@@ -623,9 +633,10 @@ struct WarpShared {
   __device__ __forceinline__ unsigned short* scratch() { return reinterpret_cast<unsigned short*>(&w[0][0]); }
 #endif
   float sc[E::NSC][kScRing];   // merged finish: words that travel with the problem (Unicycle: sin, cos)
-  float fx[E::NU][kFin];
-  int fidx[kFin];
-  int fst[kFin];
+  static constexpr int kFinPlain = kMerge ? 1 : kFin;   // (index, correction, status) rings of the other modes
+  float fx[E::NU][kFinPlain];
+  int fidx[kFinPlain];
+  int fst[kFinPlain];
   typename E::template FinRing<kMerge ? kFin : 1> fin;   // merged finish: the instance's finish inputs (cp.async)
   typename E::Stage stage[2];
   uint64_t bar[2];
@@ -940,11 +951,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
           const int r = __popc(idle & lt_mask);
           if (!onA && r < fn) {
             const int fs = (fhead + r) & (kFin - 1);
-            i = sh.fidx[fs];
-#pragma unroll
-            for (int c = 0; c < NU; ++c) xs[c] = sh.fx[c][fs];
-            stv = sh.fst[fs];
-            E::fin_read(sh.fin, fs, in);
+            E::fin_read(sh.fin, fs, in, xs, i, stv);
             on = true;
           }
           const int took = min(fn, __popc(idle));
@@ -986,7 +993,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
           continue;
         }
       }
-      if (on) E::finish(a, p, e, i, in, xs, stv);
+      if (on) E::template finish<kBulk>(a, p, e, i, in, xs, stv);
       __syncwarp();
     }
 
@@ -1019,14 +1026,10 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
           const unsigned fb = __ballot_sync(0xffffffffu, onB);
           if (onB) {
             const int fs = (fhead + fn + __popc(fb & lt_mask)) & (kFin - 1);
-#pragma unroll
-            for (int c = 0; c < NU; ++c) sh.fx[c][fs] = xsB[c];
-            sh.fidx[fs] = iB;
-            sh.fst[fs] = stB;
             float sc[E::NSC];
 #pragma unroll
             for (int k = 0; k < E::NSC; ++k) sc[k] = sh.sc[k][slot];
-            E::template fin_fetch<kFin, kBulk>(a, iB, sh.fin, fs, sc);
+            E::template fin_fetch<kFin, kBulk>(a, iB, sh.fin, fs, sc, xsB, stB);
           }
           fn += __popc(fb);
           onB = false;
