@@ -17,6 +17,11 @@
 // compaction it ran at ~35 % lane utilisation), and there is no block-wide barrier anywhere: warps never wait for
 // each other (until the very end of the kernel).
 //
+// SimulatedCars fused step: no ring at all.  Its 2 x 4 QP is cheap and the kernel is bound by memory requests, so the
+// lanes that need a solve do it inline in the A-step (partial lane utilisation) and the whole tile -- every instance of
+// it -- is finished through the coalesced warp-collective path (`finish_tile`); measured +37 % over the ring version,
+// whose solved third came back in a second finish pass with lane-per-row 40-byte accesses.
+//
 // Instances a B-step cannot certify (a constraint would have to be dropped, borderline degeneracy: ~1.5e-5 of the
 // Unicycle instances; SimulatedCars enumerates its 10 candidate active sets inline and leaves none) get a tagged-NaN
 // sentinel in safe_action[i][0] and are queued in the caller's workspace.  "presolve" mode with a workspace: a warp
@@ -44,8 +49,8 @@ namespace rcbf {
 #define RCBF_MINB_PDIPM 2  // interior-point ("pdipm") mode: the iteration state wants the registers
 #endif
 #ifndef RCBF_MINB_CARS
-#define RCBF_MINB_CARS 3  // SimulatedCars fused step: 3 (168 registers, no spills in the loop) > 2 > 4 > 5 > 6 on B200 --
-#endif                    // that kernel is bound by memory-system requests (40-byte rows), not by latency hiding
+#define RCBF_MINB_CARS 4  // SimulatedCars fused step (inline solve, whole-tile finish): 4 (128 registers) > 5 > 3 >> 6 on B200
+#endif                    // (with the earlier problem-ring version of that kernel 3 was best: it was request-bound)
 
 
 constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
@@ -132,6 +137,7 @@ struct UniEnv {
 #define RCBF_MERGE_FINISH 1
 #endif
   static constexpr bool kMergeFinish = RCBF_MERGE_FINISH;
+  static constexpr bool kInlineSolve = false;
   static constexpr int NSC = 2;
   __device__ static __forceinline__ void stash(const Inst& in, float s[NSC]) {
     s[0] = in.sn;
@@ -361,6 +367,13 @@ struct CarsEnv {
     }
   }
   static constexpr bool kMergeFinish = false;  // the fused step finishes whole tiles (finish_tile)
+#ifndef RCBF_CARS_INLINE
+#define RCBF_CARS_INLINE 1
+#endif
+#ifndef RCBF_CARS_INLINE_ALL
+#define RCBF_CARS_INLINE_ALL 0
+#endif
+  static constexpr bool kInlineSolve = (kFused || RCBF_CARS_INLINE_ALL) && RCBF_CARS_INLINE;  // see k_safe: solve in the A-step, no ring
   static constexpr int NSC = 1;
   __device__ static __forceinline__ void stash(const Inst&, float s[NSC]) { s[0] = 0.f; }
   template <int K>
@@ -825,6 +838,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
   using WS = WarpShared<E, kMode>;
   constexpr int kRing = WS::kRing, kFin = WS::kFin;
   constexpr bool kMerge = WS::kMerge;
+  constexpr bool kInline = kMode == 0 && E::kInlineSolve;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WS& sh = reinterpret_cast<WS*>(smem_raw)[warp];
@@ -892,7 +906,28 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       float w[NWR];
       bool triv, nan;
       E::assemble_raw(p, inA, aux, w, triv, nan);
-      const bool need = valid && !triv && !nan;
+      bool need = valid && !triv && !nan;
+      bool solvedA = false;
+      NormSolution<NZ, M> solA;
+      if constexpr (kInline) {
+        // inline solve (SimulatedCars fused step): the 2 x 4 QP is cheap and the kernel is bound by memory requests,
+        // so the lanes that need a solve do it right here at partial lane utilisation; every instance of the tile is
+        // then finished by the coalesced whole-tile path (no second pass with lane-per-row 40-byte accesses)
+        if (need) {
+          Normalised<NZ, M> nrm;
+          E::normalise_packed(w, p, nrm);
+          solve_normalised_fast<typename E::Pat, NZ, M, true>(nrm, p.p_diag, kSaved, solA);
+          if (solA.status == RCBF_PENDING) {
+            mark_pending<E>(a, iA, ws);
+            c_pend += 1;
+          } else {
+            solvedA = true;
+            if (kSaved) write_saved<E>(a, iA, solA);
+            c_iters += solA.iters;
+          }
+        }
+        need = false;
+      }
       const unsigned ballot = __ballot_sync(0xffffffffu, need);
       if (need) {
         const int slot = (head + qn + __popc(ballot & lt_mask)) & (kRing - 1);
@@ -904,11 +939,16 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
           for (int k = 0; k < E::NSC; ++k) sh.sc[k][slot] = sc[k];
         }
       }
-      onA = valid && !need;
+      onA = kInline ? (valid && (triv || nan || solvedA)) : (valid && !need);
       stA = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
 #pragma unroll
       for (int c = 0; c < NU; ++c) xsA[c] = nan ? NAN : 0.f;
-      if (kSaved && onA) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
+      if (kInline && solvedA) {
+        stA = solA.status;
+#pragma unroll
+        for (int c = 0; c < NU; ++c) xsA[c] = (float)solA.x[c];
+      }
+      if (kSaved && onA && !solvedA) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
         Normalised<NZ, M> nrm;
         E::normalise_packed(w, p, nrm);
         NormSolution<NZ, M> sol;
@@ -916,7 +956,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
         write_saved<E>(a, iA, sol);
       }
       c_nan += (onA && nan) ? 1 : 0;
-      c_triv += (onA && !nan) ? 1 : 0;
+      c_triv += (onA && !nan && !solvedA) ? 1 : 0;
       qn += __popc(ballot);
       tile += nw;
     }
