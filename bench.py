@@ -319,7 +319,8 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     envc._t.copy_(tc)
     ms = _time_calls(lambda: envc.safe_step(layc, acc, sgc), 5, device)
     out["cars_safe_step"] = {"value": nc / (ms * 1e-3), "unit": "env-steps/s", "instances": nc, "ms": ms,
-                             "bytes_per_unit": 40 + 4 + 4 + 4 + 40 + 40 + 4 + 4 + 40 + 4 + 1 + 4 + 4}
+                             "bytes_per_unit": 40 + 4 + 4 + 4 + 40 + 40 + 4 + 4 + 40 + 4 + 1 + 4 + 4,
+                             "achieved_gbs": 193.0 * nc / (ms * 1e-3) / 1e9}
     # (b2) config 3 at scale: differentiable path, forward with saved tensors + implicit-KKT backward kernel
     go = torch.ones_like(u)
     saved = {}
