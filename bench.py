@@ -363,6 +363,24 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
             envs_.safe_step(layer, a5, m5, g5)
     ms_graph = _time_calls(graph.replay, 20, device) / 16
     out["unicycle_b512_safe_step_us"] = {"eager": 1e3 * ms_eager, "cuda_graph_of_16": 1e3 * ms_graph}
+    # (c3) BASELINE config 2 as written: SimulatedCars 5-car chain step + RCBF-QP forward, batch 512 (one fused launch)
+    envc_ = S.SimulatedCarsEnv(num_envs=b, device=device)
+    envc_.state = stc[:b].clone()
+    envc_._t.copy_(tc[:b])
+    ac5, sg5 = acc[:b].clone(), sgc[:b].clone()
+    layc.check_nan = False
+    side.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(side):
+        envc_.safe_step(layc, ac5, sg5)
+    torch.cuda.current_stream(device).wait_stream(side)
+    ms_eager = _time_calls(lambda: envc_.safe_step(layc, ac5, sg5), 50, device)
+    graph_c = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph_c):
+        for _ in range(16):
+            envc_.safe_step(layc, ac5, sg5)
+    ms_graph = _time_calls(graph_c.replay, 20, device) / 16
+    out["config2_cars_b512_safe_step_us"] = {"eager": 1e3 * ms_eager, "cuda_graph_of_16": 1e3 * ms_graph,
+                                             "env_steps_per_s_graph": b / (ms_graph * 1e-3)}
     layer.check_nan = True
     # (d) SURVEY 8f row 1: disturbance-GP posterior in front of the same step.  History = 3000 transitions (the
     # reference's --gp_model_size, main.py:247) of the Unicycle's true drag disturbance (unicycle_env.py:87) + noise;
