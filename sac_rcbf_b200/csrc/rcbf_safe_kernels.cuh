@@ -943,10 +943,12 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
       stA = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
 #pragma unroll
       for (int c = 0; c < NU; ++c) xsA[c] = nan ? NAN : 0.f;
-      if (kInline && solvedA) {
-        stA = solA.status;
+      if constexpr (kInline) {
+        if (solvedA) {
+          stA = solA.status;
 #pragma unroll
-        for (int c = 0; c < NU; ++c) xsA[c] = (float)solA.x[c];
+          for (int c = 0; c < NU; ++c) xsA[c] = (float)solA.x[c];
+        }
       }
       if (kSaved && onA && !solvedA) {  // trivial / NaN instance: x = 0 (NaN), lam = 0, slack = h~
         Normalised<NZ, M> nrm;
