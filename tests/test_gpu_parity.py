@@ -586,11 +586,13 @@ def test_predict_next_state_vs_golden(S, golden):
 
 
 # ----------------------------------------------------------------------------------------------------- fused step
-@pytest.mark.parametrize("B", [32768, 1000, 31])
+@pytest.mark.parametrize("B", [32768, 1000, 31, 400017])
 def test_fused_safe_step_equals_layer_then_env(S, uni, cars, B):
     """One fused launch == get_safe_action followed by env.step, bit for bit, also for ragged sizes (1000 = 31 bulk-staged
-    tiles + a partial one; 31 = no full tile at all) -- the fused SimulatedCars kernel finishes full tiles through its
-    coalesced warp-collective path and everything else through the per-lane path."""
+    tiles + a partial one; 31 = no full tile at all; 400017 = every persistent warp walks several tiles, the steady state
+    of the merged finish / inline solve) -- the fused SimulatedCars kernel solves inline and finishes full tiles through
+    its coalesced warp-collective path (the layer kernel goes through the problem ring: an independent path), everything
+    else through the per-lane path."""
     env_u, layer_u = uni
     st, ac, mu, sg = O.synth_unicycle(B, seed=9)
     a = S.UnicycleEnv(num_envs=B); b = S.UnicycleEnv(num_envs=B)
