@@ -53,6 +53,23 @@ namespace rcbf {
 #endif                    // (with the earlier problem-ring version of that kernel 3 was best: it was request-bound)
 
 
+// A/B switches (defaults = what measured best on B200; the alternatives are kept so the comparison can be re-run)
+#ifndef RCBF_MERGE_FINISH
+#define RCBF_MERGE_FINISH 1      // Unicycle presolve: solved instances are finished by idle lanes of later tiles
+#endif
+#ifndef RCBF_RING_VEC
+#define RCBF_RING_VEC 1          // slot-major float4 problem ring (0: word-major scalar ring)
+#endif
+#ifndef RCBF_CARS_TILE_FINISH
+#define RCBF_CARS_TILE_FINISH 1  // fused SimulatedCars step: coalesced whole-tile finish
+#endif
+#ifndef RCBF_CARS_INLINE
+#define RCBF_CARS_INLINE 1       // fused SimulatedCars step: solve inline in the A-step (no problem ring)
+#endif
+#ifndef RCBF_CARS_INLINE_ALL
+#define RCBF_CARS_INLINE_ALL 0   // ... also in the SimulatedCars layer-only kernel (measured: -27 %)
+#endif
+
 constexpr uint32_t kPendingBits = 0x7fc0dead;  // quiet NaN with a payload no arithmetic produces
 constexpr int kWsCounters = 8;                 // workspace words [0, 8): counters
 constexpr int kWsQueueCount = 8;               // [8]: number of queued instances
@@ -133,9 +150,6 @@ struct UniEnv {
   // lane that solved it starts cp.async copies of the instance's finish inputs into the finish ring (they land during
   // the next A-step: no register is held and nobody waits for the L2 round trip); the sin / cos of the heading travel
   // with the problem through the rings instead of being recomputed.
-#ifndef RCBF_MERGE_FINISH
-#define RCBF_MERGE_FINISH 1
-#endif
   static constexpr bool kMergeFinish = RCBF_MERGE_FINISH;
   static constexpr bool kInlineSolve = false;
   static constexpr int NSC = 2;
@@ -341,9 +355,6 @@ struct CarsArgs {
 template <bool kFused>
 struct CarsEnv {
   static constexpr int NZ = kCarsNZ, M = kCarsM, NU = 1;
-#ifndef RCBF_CARS_TILE_FINISH
-#define RCBF_CARS_TILE_FINISH 1
-#endif
   static constexpr bool kTileFinish = kFused && RCBF_CARS_TILE_FINISH;  // see finish_tile
   static constexpr int kMinBlocks = kFused ? RCBF_MINB_CARS : RCBF_MINB;  // get_safe_action alone: 4 is faster (A/B)
   static constexpr bool kPdlPass1 = false;  // measured: -16 % when pass 1 is launched as a dependent
@@ -367,12 +378,6 @@ struct CarsEnv {
     }
   }
   static constexpr bool kMergeFinish = false;  // the fused step finishes whole tiles (finish_tile)
-#ifndef RCBF_CARS_INLINE
-#define RCBF_CARS_INLINE 1
-#endif
-#ifndef RCBF_CARS_INLINE_ALL
-#define RCBF_CARS_INLINE_ALL 0
-#endif
   static constexpr bool kInlineSolve = (kFused || RCBF_CARS_INLINE_ALL) && RCBF_CARS_INLINE;  // see k_safe: solve in the A-step, no ring
   static constexpr int NSC = 1;
   __device__ static __forceinline__ void stash(const Inst&, float s[NSC]) { s[0] = 0.f; }
@@ -601,9 +606,6 @@ struct WarpShared {
   // whenever a B-step's output might not fit, see k_safe); plain presolve: unused
   static constexpr int kFin = kMode == 0 ? (kMerge ? 64 : 32) : 256;
   static constexpr int kScRing = kMerge ? kRing : 1;
-#ifndef RCBF_RING_VEC
-#define RCBF_RING_VEC 1
-#endif
 #if RCBF_RING_VEC
   // problem ring, slot-major: NWR raw words + the instance index, padded to float4s and moved by 128-bit shared-memory
   // accesses (Unicycle: 5 per problem instead of 20 scalar ones; the 80-byte slot stride is conflict-free per
