@@ -11,11 +11,10 @@
 // "pdipm" mode).  Unicycle, presolve mode ("merged finish"): the solving lane puts (index, correction, status, sin, cos)
 // into a warp-private finish ring and starts cp.async copies of the instance's 28 bytes of finish inputs into it; in
 // the finish pass of a LATER tile every lane whose own instance went to the problem ring takes one entry, so the
-// finish code runs with (nearly) full warps too.  SimulatedCars (whole-tile finish) and pdipm mode keep the earlier
-// scheme: the lanes reload their instance after the next A-step and run a second finish pass.
-// So the expensive phase always runs with full warps (without
-// compaction it ran at ~35 % lane utilisation), and there is no block-wide barrier anywhere: warps never wait for
-// each other (until the very end of the kernel).
+// finish code runs with (nearly) full warps too.  The SimulatedCars layer kernel and pdipm mode keep the earlier
+// scheme: the lanes reload their instance after the next A-step and run a second finish pass.  So the expensive phase
+// always runs with full warps (without compaction it ran at ~35 % lane utilisation), and there is no block-wide barrier
+// anywhere: warps never wait for each other (until the very end of the kernel).
 //
 // SimulatedCars fused step: no ring at all.  Its 2 x 4 QP is cheap and the kernel is bound by memory requests, so the
 // lanes that need a solve do it inline in the A-step (partial lane utilisation) and the whole tile -- every instance of
