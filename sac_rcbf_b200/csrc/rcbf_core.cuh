@@ -65,9 +65,15 @@ RCBF_HD double t_rsqrt(double a) {
 }
 
 // single-rounding float ops that the compiler may not contract into FMAs (reference-order assembly)
+// mul_rn flushes denormal products to zero (.ftz) while add_rn / sub_rn do not: ptxas 12.9 contracts a PACKED
+// `mul.rn.f32x2` feeding an `add.rn.f32x2` into one FFMA2 (single rounding!) despite the explicit .rn, unless the two
+// differ in their ftz mode -- and the scalar instruction uses the same mode so that T = float and T = f2 agree bit for
+// bit.  Products below 1.2e-38 do not occur in this path's data (metres, radians, m/s).
 RCBF_HD float mul_rn(float a, float b) {
 #if defined(__CUDA_ARCH__) && !defined(RCBF_EXP_CONTRACT)  // (experiment switch: let nvcc contract the assembly)
-  return __fmul_rn(a, b);
+  float r;
+  asm("mul.rn.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
 #else
   return a * b;  // host build uses -ffp-contract=off
 #endif
@@ -97,6 +103,31 @@ RCBF_HD float t_rcp_fast(float a) {
 #endif
 }
 RCBF_HD double t_rcp_fast(double a) { return 1.0 / a; }
+
+// a / n with r ~ 1/n: one multiply + one residual correction (the fast path of IEEE division; correctly rounded
+// whenever r is within an ulp of 1/n, i.e. outside the denormal/overflow corners that normalised rows never reach)
+RCBF_HD float div_by(float a, float n, float r) {
+#if defined(__CUDA_ARCH__)
+  const float q = a * r;
+  return fmaf(fmaf(-n, q, a), r, q);
+#else
+  (void)r;
+  return a / n;
+#endif
+}
+RCBF_HD float rcp_refined(float n) {
+#if defined(__CUDA_ARCH__)
+  float r;  // MUFU.RCP is within one ulp: enough for the single-correction quotient in div_by to round correctly
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
+  return r;
+#else
+  return 1.0f / n;
+#endif
+}
+
+}  // namespace rcbf
+#include "rcbf_f2.cuh"  // packed pairs of float32 + the op set shared by T = float and T = f2
+namespace rcbf {
 
 // per-instance status codes: RCBF_OK_TRIVIAL ... RCBF_NAN, see include/rcbf_b200.h
 
@@ -781,60 +812,80 @@ struct UniRaw {
 // most dt * 1 rad/s per step over 1000 steps).  Cody-Waite reduction by pi/2 in three float32 pieces + the classic
 // degree-7 / degree-8 minimax polynomials on [-pi/4, pi/4].  ~30 instructions, no slow path, no local memory (the
 // library sincosf carries a Payne-Hanek branch that costs code size and registers in every kernel that calls it).
-RCBF_HD void sincos_t(float x, float* sn, float* cs) {
-  const float j = rintf(x * 0.636619772f);             // nearest multiple of pi/2
-  float r = fmaf(j, -1.57079601e+00f, x);
-  r = fmaf(j, -3.13916473e-07f, r);
-  r = fmaf(j, -5.39030253e-15f, r);
-  const int q = (int)j;
-  const float z = r * r;
-  float ps = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
-  ps = fmaf(ps, z, -1.6666654611e-1f);
-  ps = fmaf(ps * z, r, r);                              // sin(r)
-  float pc = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
-  pc = fmaf(pc, z, 4.166664568298827e-2f);
-  pc = fmaf(pc * z, z, fmaf(z, -0.5f, 1.0f));           // cos(r)
-  const bool swap = q & 1;
-  float sv = swap ? pc : ps;
-  float cv = swap ? ps : pc;
-  sv = (q & 2) ? -sv : sv;
-  cv = ((q + 1) & 2) ? -cv : cv;
+template <typename T>
+RCBF_HD void sincos_v(T x, T* sn, T* cs) {  // T = float or f2 (two instances through the packed FP32 instructions)
+  const T j = t_rint(mul_rn(x, T(0.636619772f)));       // nearest multiple of pi/2
+  T r = t_fma(j, T(-1.57079601e+00f), x);
+  r = t_fma(j, T(-3.13916473e-07f), r);
+  r = t_fma(j, T(-5.39030253e-15f), r);
+  const typename VecOf<T>::ivec q = t_toint(j);
+  const T z = mul_rn(r, r);
+  T ps = t_fma(z, T(-1.9515295891e-4f), T(8.3321608736e-3f));
+  ps = t_fma(ps, z, T(-1.6666654611e-1f));
+  ps = t_fma(mul_rn(ps, z), r, r);                      // sin(r)
+  T pc = t_fma(z, T(2.443315711809948e-5f), T(-1.388731625493765e-3f));
+  pc = t_fma(pc, z, T(4.166664568298827e-2f));
+  pc = t_fma(mul_rn(pc, z), z, t_fma(z, T(-0.5f), T(1.0f)));  // cos(r)
+  const typename VecOf<T>::mask swap = t_bit(q, 1);
+  T sv = t_sel(swap, pc, ps);
+  T cv = t_sel(swap, ps, pc);
+  sv = t_sel(t_bit(q, 2), t_neg(sv), sv);
+  cv = t_sel(t_bit(t_iadd(q, 1), 2), t_neg(cv), cv);
   *sn = sv;
   *cs = cv;
 }
+RCBF_HD void sincos_t(float x, float* sn, float* cs) { sincos_v<float>(x, sn, cs); }
 
 // The assembly mirrors the reference's float32 operation ORDER (one rounding per torch op, no FMA contraction, the
 // k-ordered accumulation of torch.bmm's small-matrix path) so that the QP data agree with the reference's to the
 // last bit up to the ulp of cos/sin: near-degenerate instances amplify 1e-7 data noise into >1e-4 action noise.
-RCBF_HD void assemble_unicycle_sc(const UnicycleParams& p, const float st[3], float s, float c, const float u[2],
-                                  const float mu[3], const float sg[3], UniRaw& o) {
+// Written once for T = float (one instance) and T = f2 (two instances per lane, FMUL2 / FADD2): the packed
+// instructions round each half exactly like the scalar ones, so both instantiations give the same bits.
+// Output: Lg[i] = d h_i / d action (G[i][:2] = -Lg[i]) and the 9 right-hand sides.
+template <typename T>
+RCBF_HD void assemble_unicycle_v(const UnicycleParams& p, const T st[3], T s, T c, const T u[2], const T mu[3],
+                                 const T sg[3], T Lg[kUniHaz][2], T h[kUniM]) {
   // s, c = sin / cos of st[2]                              // :211-212
-  const float lp = p.l_p;
-  const float px = add_rn(st[0], mul_rn(lp, c));           // :216
-  const float py = add_rn(st[1], mul_rn(lp, s));           // :217
-  const float g01 = -mul_rn(s, lp), g11 = mul_rn(c, lp);   // g_p = R diag(1,l_p) = [[c, g01],[s, g11]]  :225-233
-  const float mpx = add_rn(mul_rn(g01, mu[2]), mu[0]);     // :236-238
-  const float mpy = add_rn(mul_rn(g11, mu[2]), mu[1]);
-  const float a01 = p.abs_sigma_map ? fabsf(g01) : g01;
-  const float a11 = p.abs_sigma_map ? fabsf(g11) : g11;
-  const float spx = mul_rn(p.sigma_scale, add_rn(mul_rn(a01, sg[2]), sg[0]));  // :239-241 (scale = 1 in this layer)
-  const float spy = mul_rn(p.sigma_scale, add_rn(mul_rn(a11, sg[2]), sg[1]));
+  const T lp = T(p.l_p);
+  const T px = add_rn(st[0], mul_rn(lp, c));               // :216
+  const T py = add_rn(st[1], mul_rn(lp, s));               // :217
+  const T g01 = t_neg(mul_rn(s, lp)), g11 = mul_rn(c, lp); // g_p = R diag(1,l_p) = [[c, g01],[s, g11]]  :225-233
+  const T mpx = add_rn(mul_rn(g01, mu[2]), mu[0]);         // :236-238
+  const T mpy = add_rn(mul_rn(g11, mu[2]), mu[1]);
+  const T a01 = p.abs_sigma_map ? t_fabs(g01) : g01;
+  const T a11 = p.abs_sigma_map ? t_fabs(g11) : g11;
+  const T spx = mul_rn(T(p.sigma_scale), add_rn(mul_rn(a01, sg[2]), sg[0]));  // :239-241 (scale = 1 in this layer)
+  const T spy = mul_rn(T(p.sigma_scale), add_rn(mul_rn(a11, sg[2]), sg[1]));
   RCBF_UNROLL
   for (int i = 0; i < kUniHaz; ++i) {
-    const float dx = sub_rn(px, p.hazards[i][0]);          // :248
-    const float dy = sub_rn(py, p.hazards[i][1]);
-    const float hc = mul_rn(0.5f, sub_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), p.collision_radius_sq));  // :246
-    const float L0 = add_rn(mul_rn(dx, c), mul_rn(dy, s));      // dhdp' g_p   :259
-    const float L1 = add_rn(mul_rn(dx, g01), mul_rn(dy, g11));
-    o.Lg[i][0] = L0;
-    o.Lg[i][1] = L1;
-    o.G[i][0] = -L0;
-    o.G[i][1] = -L1;
+    const T dx = sub_rn(px, T(p.hazards[i][0]));           // :248
+    const T dy = sub_rn(py, T(p.hazards[i][1]));
+    const T hc = mul_rn(T(0.5f), sub_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), T(p.collision_radius_sq)));  // :246
+    const T L0 = add_rn(mul_rn(dx, c), mul_rn(dy, s));     // dhdp' g_p   :259
+    const T L1 = add_rn(mul_rn(dx, g01), mul_rn(dy, g11));
+    Lg[i][0] = L0;
+    Lg[i][1] = L1;
+    const T t1 = add_rn(mul_rn(dx, mpx), mul_rn(dy, mpy));
+    const T t2 = add_rn(mul_rn(t_fabs(dx), spx), mul_rn(t_fabs(dy), spy));
+    const T t3 = add_rn(mul_rn(L0, u[0]), mul_rn(L1, u[1]));
+    h[i] = add_rn(mul_rn(T(p.gamma_b), mul_rn(mul_rn(hc, hc), hc)), add_rn(sub_rn(t1, t2), t3));  // :261
+  }
+  RCBF_UNROLL
+  for (int cc = 0; cc < 2; ++cc) {  // :365-377
+    const int r = kUniHaz + 2 * cc;
+    h[r] = sub_rn(T(p.u_max[cc]), u[cc]);
+    h[r + 1] = add_rn(T(-p.u_min[cc]), u[cc]);
+  }
+}
+
+RCBF_HD void assemble_unicycle_sc(const UnicycleParams& p, const float st[3], float s, float c, const float u[2],
+                                  const float mu[3], const float sg[3], UniRaw& o) {
+  assemble_unicycle_v<float>(p, st, s, c, u, mu, sg, o.Lg, o.h);
+  RCBF_UNROLL
+  for (int i = 0; i < kUniHaz; ++i) {
+    o.G[i][0] = -o.Lg[i][0];
+    o.G[i][1] = -o.Lg[i][1];
     o.G[i][2] = -1.0f;                                     // :260
-    const float t1 = add_rn(mul_rn(dx, mpx), mul_rn(dy, mpy));
-    const float t2 = add_rn(mul_rn(fabsf(dx), spx), mul_rn(fabsf(dy), spy));
-    const float t3 = add_rn(mul_rn(L0, u[0]), mul_rn(L1, u[1]));
-    o.h[i] = add_rn(mul_rn(p.gamma_b, mul_rn(mul_rn(hc, hc), hc)), add_rn(sub_rn(t1, t2), t3));  // :261
   }
   RCBF_UNROLL
   for (int cc = 0; cc < 2; ++cc) {  // :365-377
@@ -844,8 +895,6 @@ RCBF_HD void assemble_unicycle_sc(const UnicycleParams& p, const float st[3], fl
       o.G[r][j] = (j == cc) ? 1.0f : 0.0f;
       o.G[r + 1][j] = (j == cc) ? -1.0f : 0.0f;
     }
-    o.h[r] = sub_rn(p.u_max[cc], u[cc]);
-    o.h[r + 1] = add_rn(-p.u_min[cc], u[cc]);
   }
 }
 
@@ -933,27 +982,6 @@ struct Normalised {
   float n[M];
   uint32_t h_is_max;  // bit i: |h_i| is the (strict) row maximum  -> routes d n_i / d h_i in the backward
 };
-
-// a / n with r ~ 1/n: one multiply + one residual correction (the fast path of IEEE division; correctly rounded
-// whenever r is within an ulp of 1/n, i.e. outside the denormal/overflow corners that normalised rows never reach)
-RCBF_HD float div_by(float a, float n, float r) {
-#if defined(__CUDA_ARCH__)
-  const float q = a * r;
-  return fmaf(fmaf(-n, q, a), r, q);
-#else
-  (void)r;
-  return a / n;
-#endif
-}
-RCBF_HD float rcp_refined(float n) {
-#if defined(__CUDA_ARCH__)
-  float r;  // MUFU.RCP is within one ulp: enough for the single-correction quotient in div_by to round correctly
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
-  return r;
-#else
-  return 1.0f / n;
-#endif
-}
 
 template <typename Pat, int NZ, int M>
 RCBF_HD void normalise_rows(const float G[M][NZ], const float h[M], Normalised<NZ, M>& o) {

@@ -128,18 +128,140 @@ RCBF_HD void unicycle_env_step(const UnicycleEnvParams& p, T st[3], T& last_dist
   unicycle_env_finish<T>(p, st, last_dist, step, s, c, o);
 }
 
+// ---- float32 throughput path, written once for T = float (one instance per lane) and T = f2 (two instances per lane
+// through FMUL2 / FADD2 / FFMA2).  Every operation is spelled out (rcbf_f2.cuh): the compiler contracts nothing, so
+// both instantiations -- and therefore the scalar env.step kernel, the one-per-lane fused kernel and the two-per-lane
+// fused kernel -- produce the same bits.  unicycle_env.py:46-111,215-280.
+template <typename T>
+struct UniEnvOutV {
+  T obs[7];
+  T reward;
+  T cost;
+  typename VecOf<T>::mask done, goal_met;
+};
+
+// the env parameters as the float32 path uses them (converted once, on the host or at kernel entry: the double -> float
+// conversions and the two derived products are the same IEEE operations either way)
+struct UniEnvF {
+  float hz[kUniHaz][2];
+  float r2;            // hazards_radius^2
+  float dt, ndt, nk;   // dt, -dt, -(dt * 0.1)
+  float gx, gy, goal_size, reward_goal;
+  float init_x, init_y, init_th;
+  int max_steps, auto_reset;
+};
+RCBF_HD UniEnvF make_env_f(const UnicycleEnvParams& p) {
+  UniEnvF f;
+  RCBF_UNROLL
+  for (int i = 0; i < kUniHaz; ++i) {
+    f.hz[i][0] = (float)p.hazards[i][0];
+    f.hz[i][1] = (float)p.hazards[i][1];
+  }
+  const float hr = (float)p.hazards_radius;
+  f.r2 = mul_rn(hr, hr);
+  f.dt = (float)p.dt;
+  f.ndt = -f.dt;
+  f.nk = -mul_rn(f.dt, 0.1f);
+  f.gx = (float)p.goal_x;
+  f.gy = (float)p.goal_y;
+  f.goal_size = (float)p.goal_size;
+  f.reward_goal = (float)p.reward_goal;
+  f.init_x = (float)p.init_x;
+  f.init_y = (float)p.init_y;
+  f.init_th = (float)p.init_theta;
+  f.max_steps = p.max_episode_steps;
+  f.auto_reset = p.auto_reset;
+  return f;
+}
+
+template <typename T>
+RCBF_HD T unicycle_goal_dist_v(const UniEnvF& p, T x, T y, T* vx_out, T* vy_out) {
+  const T vx = sub_rn(T(p.gx), x), vy = sub_rn(T(p.gy), y);
+  *vx_out = vx;
+  *vy_out = vy;
+  return sqrt_pos(t_fma(vx, vx, mul_rn(vy, vy)));
+}
+
+// s, c = sin / cos of the CURRENT heading (the constraint assembly already has them); the updated heading's pair comes
+// from one plane rotation by the small per-step increment |delta| <= dt * 1 rad/s (Taylor to delta^5, relative error
+// < 1e-12 at |delta| = 0.02) instead of a second full sincos.
+template <typename T>
+RCBF_HD void unicycle_env_step_v(const UniEnvF& p, T st[3], T& last_dist, typename VecOf<T>::ivec& step,
+                                 const T a_in[2], T s, T c, UniEnvOutV<T>& o) {
+  const T dt = T(p.dt);
+  const T a0 = t_fmin(t_fmax(a_in[0], T(-1.f)), T(1.f));  // :62
+  const T a1 = t_fmin(t_fmax(a_in[1], T(-1.f)), T(1.f));
+  T x = t_fma(dt, mul_rn(c, a0), st[0]);                  // :86   state += dt * (f + g(state) @ action), f = 0
+  T y = t_fma(dt, mul_rn(s, a0), st[1]);
+  const T delta = mul_rn(dt, a1);
+  st[2] = add_rn(st[2], delta);
+  const T d2 = mul_rn(delta, delta);
+  const T sp = t_fma(d2, t_fma(d2, T(8.333333333e-3f), T(-1.666666667e-1f)), T(1.0f));
+  const T sd = mul_rn(delta, sp);
+  const T nsd = mul_rn(mul_rn(T(p.ndt), a1), sp);         // -sd (a packed multiply is cheaper than two sign flips)
+  const T cd = t_fma(d2, t_fma(d2, T(4.166666667e-2f), T(-0.5f)), T(1.0f));
+  const T s1 = t_fma(s, cd, mul_rn(c, sd));               // sin / cos of the UPDATED heading
+  const T c1 = t_fma(c, cd, mul_rn(s, nsd));
+  const T nk = T(p.nk);
+  x = t_fma(mul_rn(nk, c1), c1, x);                       // :87 uses g() and cos() of the UPDATED theta
+  y = t_fma(mul_rn(nk, s1), c1, y);
+  st[0] = x;
+  st[1] = y;
+  step = t_iadd(step, 1);                                 // :89
+  T vx, vy;
+  const T dist = unicycle_goal_dist_v<T>(p, x, y, &vx, &vy);
+  const T rw = sub_rn(last_dist, dist);                   // :93-95
+  last_dist = dist;
+  const typename VecOf<T>::mask goal = t_le(dist, T(p.goal_size));  // :97,113-123
+  o.reward = t_sel(goal, add_rn(rw, T(p.reward_goal)), rw);
+  o.done = t_or(goal, t_ige(step, p.max_steps));          // :100-102
+  o.goal_met = goal;
+  T d2min = T(3.0e38f);  // any(d2_i < r2) == (min_i d2_i < r2); a NaN position compares false either way   :106
+  RCBF_UNROLL
+  for (int i = 0; i < kUniHaz; ++i) {
+    const T dx = sub_rn(x, T(p.hz[i][0])), dy = sub_rn(y, T(p.hz[i][1]));
+    d2min = t_fmin(d2min, t_fma(dx, dx, mul_rn(dy, dy)));
+  }
+  o.cost = t_sel(t_lt(d2min, T(p.r2)), T(0.1f), T(0.f));
+  // obs = [x, y, cos th, sin th, compass_x, compass_y, exp(-dist)]     :215-231,260-277
+  const T cx = t_fma(vx, c1, mul_rn(vy, s1));             // row-vector times R(theta)    :272-274
+  const T cy = t_fma(vy, c1, mul_rn(sub_rn(x, T(p.gx)), s1));
+  const T nrm = add_rn(sqrt_pos(t_fma(cx, cx, mul_rn(cy, cy))), T(0.001f));  // :276
+  const T rn = rcp_refined(nrm);
+  o.obs[0] = x;
+  o.obs[1] = y;
+  o.obs[2] = c1;
+  o.obs[3] = s1;
+  o.obs[4] = div_by_v(cx, nrm, rn);
+  o.obs[5] = div_by_v(cy, nrm, rn);
+  // exp(-dist) = 2^(-dist log2 e): the product's rounding error enters as a first-order correction (<= ~2 ulp)
+#if defined(__CUDA_ARCH__)
+  const T nhi = mul_rn(dist, T(-1.44269502e+00f));
+  const T tl = t_fma(dist, T(1.92596299e-08f), t_fma(dist, T(1.44269502e+00f), nhi));
+  const T ev = ex2_approx(nhi);
+  o.obs[6] = t_fma(ev, mul_rn(tl, T(-6.93147182e-01f)), ev);
+#else
+  o.obs[6] = exp_neg(t_neg(dist));
+#endif
+}
+
+// reset values (:125-143); the goal distance of the initial pose is the same for every instance
+RCBF_HD float unicycle_reset_dist(const UniEnvF& p) {
+  float vx, vy;
+  return unicycle_goal_dist_v<float>(p, p.init_x, p.init_y, &vx, &vy);
+}
+
 RCBF_HD void unicycle_env_step_sc(const UnicycleEnvParams& p, float st[3], float& last_dist, int& step,
                                   const float a_in[2], float s, float c, UniEnvOut<float>& o) {
-  const float dt = (float)p.dt;
-  const float a0 = fminf(fmaxf(a_in[0], -1.f), 1.f);  // :62
-  const float a1 = fminf(fmaxf(a_in[1], -1.f), 1.f);
-  st[0] += dt * (c * a0);  // :86
-  st[1] += dt * (s * a0);
-  const float delta = dt * a1;
-  st[2] += delta;
-  float s1, c1;
-  rotate_small(s, c, delta, &s1, &c1);
-  unicycle_env_finish<float>(p, st, last_dist, step, s1, c1, o);
+  const UniEnvF pf = make_env_f(p);
+  UniEnvOutV<float> v;
+  unicycle_env_step_v<float>(pf, st, last_dist, step, a_in, s, c, v);
+  RCBF_UNROLL
+  for (int j = 0; j < 7; ++j) o.obs[j] = v.obs[j];
+  o.reward = v.reward;
+  o.cost = v.cost;
+  o.done = v.done;
+  o.goal_met = v.goal_met;
 }
 
 template <typename T>
@@ -149,6 +271,14 @@ RCBF_HD void unicycle_reset(const UnicycleEnvParams& p, T st[3], T& last_dist, i
   st[2] = T(p.init_theta);
   step = 0;
   last_dist = unicycle_goal_dist(p, st);
+}
+template <>
+RCBF_HD void unicycle_reset<float>(const UnicycleEnvParams& p, float st[3], float& last_dist, int& step) {  // float32: same
+  st[0] = (float)p.init_x;                                                               // bits as the packed kernel
+  st[1] = (float)p.init_y;
+  st[2] = (float)p.init_theta;
+  step = 0;
+  last_dist = unicycle_reset_dist(make_env_f(p));
 }
 
 template <typename T>

@@ -1,0 +1,475 @@
+// rcbf_safe2.cuh -- k_safe2: the Unicycle hot kernel, TWO instances per lane through the Blackwell packed-FP32
+// instructions (FMUL2 / FADD2 / FFMA2, rcbf_f2.cuh), TMA in AND out, whole-tile in-place finish.
+//
+// get_safe_action (diff_cbf_qp.py:44-79) and, fused, UnicycleEnv.step (unicycle_env.py:46-111) for 64-instance
+// tiles; a lane owns the adjacent instances (2*lane, 2*lane+1) of its warp's tile.  Per persistent-loop iteration k:
+//
+//   A-step(tile k)   inputs arrive by cp.async.bulk (TMA, mbarrier completion) one iteration ahead; sin/cos, the
+//                    reference-order constraint assembly and the trivial test run PACKED (one instruction = both
+//                    instances, each half rounded exactly like the scalar instruction); trivial / NaN instances get
+//                    their clamped action written in place of the nominal one in the tile's input slot; instances that
+//                    need a solve push 15 words (Lg 5x2, h 5; the actuator rows are rebuilt from u) + a tag into the
+//                    warp-private problem ring.
+//   B-step           whenever >= 32 problems wait: one problem per lane, greedy active-set presolve + float64 KKT
+//                    certificate (rcbf_core.cuh), the clamped safe action goes back into the owning tile's slot.
+//   finish(tile k-2) two iterations later every problem of that tile is solved (FIFO ring; if the stream is too
+//                    sparse in problems the oldest ones are flushed by a partial B-step), so the OWNING lanes finish
+//                    the whole tile in place: clamp result, packed env.step, observation, reward, cost, done.  All
+//                    outputs of the tile are staged in shared memory and leave through cp.async.bulk stores
+//                    (shared -> global, bulk_group completion): perfectly coalesced, a handful of instructions.
+//
+// Compared with k_safe (one instance per lane, rcbf_safe_kernels.cuh) this halves the issue slots of the arithmetic,
+// amortises the loop / ring / staging glue over 64 instances, removes the finish ring with its 28-byte re-read of
+// every solved instance, and turns 14 strided stores per instance pair into 8 bulk copies per tile.
+//
+// Instances the B-step cannot certify (~1.5e-5) keep their OLD state, get the pending sentinel in safe_action[i][0] and
+// are queued AFTER their tile's bulk stores completed; the kernel's tail (tail_drain of rcbf_safe_kernels.cuh: one
+// warp per instance, exhaustive enumeration) finishes them -- still one launch per step.
+//
+// Launch conditions (launch_safe2): solver_mode 0, no saved tensors, every array base 16-byte aligned; n is split
+// into full 64-instance tiles for this kernel and a ragged tail (< 64) for k_safe.
+#pragma once
+
+#include "rcbf_safe_kernels.cuh"
+
+namespace rcbf {
+
+#ifndef RCBF_S2_MINB
+#define RCBF_S2_MINB 3     // resident blocks per SM
+#endif
+#ifndef RCBF_S2_WARPS
+#define RCBF_S2_WARPS 4    // warps per block
+#endif
+#ifndef RCBF_S2_MIN_N
+#define RCBF_S2_MIN_N 4096  // below this the one-per-lane kernel spreads the few tiles over more warps
+#endif
+constexpr int kS2Warps = RCBF_S2_WARPS;
+constexpr int kS2Threads = 32 * kS2Warps;
+constexpr int kS2Ring = 96;  // <= 31 problems left over + 64 new ones
+
+// bulk stores (shared -> global) + their completion
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g_u32(void* dst, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <bool kFused>
+struct alignas(16) S2Warp {
+  struct alignas(16) In {   // TMA landing slot of one tile; after the A-/B-steps `ac` holds the clamped SAFE action,
+    float st[kFused ? 256 : 192];  // after the finish `st` / `step` hold the new state: all three leave from here
+    int step[kFused ? 64 : 4];
+    float ac[128];
+  };
+  In in[4];                 // tiles k-2 (finishing), k-1, k, k+1 (in flight)
+  float mu[192], sg[192];   // only the assembly reads them: single buffer, refilled right after the A-step's read
+  float sn[3][64], cs[3][64];  // sin / cos of the heading, kept from the assembly for env.step
+  float4 ring[kS2Ring][4];  // problem ring: Lg[5][2], h[5], tag
+  float obs[kFused ? 448 : 4];   // output staging of the tile being finished
+  float reward[kFused ? 64 : 4], cost[kFused ? 64 : 4];
+  uint8_t done[kFused ? 64 : 16], goal[kFused ? 64 : 16];
+  uint8_t cls[3][64];       // per instance: RCBF_OK_TRIVIAL / RCBF_OK_CERTIFIED / RCBF_NAN / RCBF_PENDING
+  uint64_t bar[2];
+};
+
+template <bool kFused>
+__global__ void __launch_bounds__(kS2Threads, RCBF_S2_MINB)
+k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnvParams e, UniEnvF ef /* = make_env_f(e) */,
+        rcbf_counters_t* ws) {
+  using E = UniEnv<kFused>;
+  using WS = S2Warp<kFused>;
+  constexpr int NZ = kUniNZ, M = kUniM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WS& sh = reinterpret_cast<WS*>(smem_raw)[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const int ntiles = (int)(n >> 6);
+  const int nw = (int)gridDim.x * kS2Warps;
+  int tile = (int)blockIdx.x * kS2Warps + warp;
+  int head = 0, qn = 0;          // problem ring
+  int pk = 0, pk1 = 0;           // problems pushed by tiles k, k-1 (the newest pk + pk1 entries of the ring)
+  int r3 = 0;                    // k % 3
+  int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
+  constexpr uint32_t kInBytes = (kFused ? 1024 + 256 : 768) + 512 + 768 + 768;
+
+  // Bulk-copy descriptors, one per lane: lanes 0..4 each own one INPUT array of a tile (state4, step, action, mean,
+  // sigma), lanes 8..15 one OUTPUT array (safe action, state4, step, obs, reward, cost, done, goal_met).  A tile's copies
+  // are then ONE predicated cp.async.bulk instruction executed by several lanes instead of a sequence issued by lane 0
+  // (each with its own 64-bit address arithmetic): ~60 fewer warp instructions per tile.
+  const uint32_t sh_base = smem_u32(&sh);
+  const char* d_g = nullptr;      // global base of this lane's array
+  uint32_t d_gstride = 0;         // bytes per tile
+  uint32_t d_soff = 0;            // shared-memory offset inside this warp's block (slot 0 for the slot-resident ones)
+  bool d_slot = false;            // lives in the tile's input slot (sh.in[k & 3])
+  {
+    const int l = lane;
+    if (kFused) {
+      if (l == 0) { d_g = (const char*)a.state4; d_gstride = 1024; d_soff = offsetof(WS, in) + offsetof(typename WS::In, st); d_slot = true; }
+      if (l == 1) { d_g = (const char*)a.step; d_gstride = 256; d_soff = offsetof(WS, in) + offsetof(typename WS::In, step); d_slot = true; }
+    } else {
+      if (l == 0) { d_g = (const char*)a.st; d_gstride = 768; d_soff = offsetof(WS, in) + offsetof(typename WS::In, st); d_slot = true; }
+    }
+    if (l == 2) { d_g = (const char*)a.ac; d_gstride = 512; d_soff = offsetof(WS, in) + offsetof(typename WS::In, ac); d_slot = true; }
+    if (l == 3) { d_g = (const char*)a.mu; d_gstride = 768; d_soff = offsetof(WS, mu); }
+    if (l == 4) { d_g = (const char*)a.sg; d_gstride = 768; d_soff = offsetof(WS, sg); }
+    if (l == 8) { d_g = (const char*)a.out; d_gstride = 512; d_soff = offsetof(WS, in) + offsetof(typename WS::In, ac); d_slot = true; }
+    if (kFused) {
+      if (l == 9) { d_g = (const char*)a.state4; d_gstride = 1024; d_soff = offsetof(WS, in) + offsetof(typename WS::In, st); d_slot = true; }
+      if (l == 10) { d_g = (const char*)a.step; d_gstride = 256; d_soff = offsetof(WS, in) + offsetof(typename WS::In, step); d_slot = true; }
+      if (l == 11) { d_g = (const char*)a.obs; d_gstride = 1792; d_soff = offsetof(WS, obs); }
+      if (l == 12) { d_g = (const char*)a.reward; d_gstride = 256; d_soff = offsetof(WS, reward); }
+      if (l == 13) { d_g = (const char*)a.cost; d_gstride = 256; d_soff = offsetof(WS, cost); }
+      if (l == 14) { d_g = (const char*)a.done; d_gstride = 64; d_soff = offsetof(WS, done); }
+      if (l == 15) { d_g = (const char*)a.goal_met; d_gstride = 64; d_soff = offsetof(WS, goal); }
+    }
+  }
+  const bool is_loader = d_g != nullptr && lane < 8;
+  const bool is_storer = d_g != nullptr && lane >= 8;
+  auto issue = [&](int t, int k) {  // all lanes: put tile t in flight into slot k & 3 (+ the mu / sigma buffer)
+    uint64_t* bar = &sh.bar[k & 1];
+    if (lane == 0) mbar_expect_tx(bar, kInBytes);
+    __syncwarp();
+    if (is_loader)
+      bulk_g2s_u32(sh_base + d_soff + (d_slot ? (uint32_t)(k & 3) * (uint32_t)sizeof(typename WS::In) : 0u),
+                   d_g + (int64_t)t * d_gstride, d_gstride, bar);
+  };
+
+  pdl_wait();
+  if (lane == 0) {
+    mbar_init(&sh.bar[0], 1);
+    mbar_init(&sh.bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (tile < ntiles) issue(tile, 0);
+
+  const float reset_dist = unicycle_reset_dist(ef);
+  int after = 0;  // iterations past this warp's last tile (the last two tiles are finished then)
+#pragma unroll 1
+  for (int k = 0;; ++k) {
+    const bool have_tile = tile < ntiles;
+    pk1 = pk;
+    pk = 0;
+    if (have_tile) {  // ---------------------------------------------------------------- A-step
+      typename WS::In& si = sh.in[k & 3];
+      mbar_wait(&sh.bar[k & 1], (k >> 1) & 1);
+      f2 st[3], u[2], mu[3], sg[3];
+      if (kFused) {
+        const float4 qa = reinterpret_cast<const float4*>(si.st)[2 * lane];
+        const float4 qb = reinterpret_cast<const float4*>(si.st)[2 * lane + 1];
+        st[0] = f2(qa.x, qb.x); st[1] = f2(qa.y, qb.y); st[2] = f2_pin(qa.z, qb.z);
+      } else {
+        const float2* sp = reinterpret_cast<const float2*>(si.st) + 3 * lane;
+        const float2 s0 = sp[0], s1 = sp[1], s2 = sp[2];
+        st[0] = f2(s0.x, s1.y); st[1] = f2(s0.y, s2.x); st[2] = f2_pin(s1.x, s2.y);
+      }
+      {
+        const float4 uu = reinterpret_cast<const float4*>(si.ac)[lane];
+        u[0] = f2_pin(uu.x, uu.z); u[1] = f2_pin(uu.y, uu.w);
+        const float2* mp = reinterpret_cast<const float2*>(sh.mu) + 3 * lane;
+        const float2 m0 = mp[0], m1 = mp[1], m2 = mp[2];
+        mu[0] = f2(m0.x, m1.y); mu[1] = f2(m0.y, m2.x); mu[2] = f2_pin(m1.x, m2.y);
+        const float2* gp = reinterpret_cast<const float2*>(sh.sg) + 3 * lane;
+        const float2 g0 = gp[0], g1 = gp[1], g2 = gp[2];
+        sg[0] = f2(g0.x, g1.y); sg[1] = f2(g0.y, g2.x); sg[2] = f2_pin(g1.x, g2.y);
+      }
+      __syncwarp();
+      if (tile + nw < ntiles) {
+        bulk_wait_read0();  // the stores of the tile that last used slot (k+1) & 3 have read it (issued an iteration ago)
+        issue(tile + nw, k + 1);
+      }
+      f2 sn, cs;
+      sincos_v<f2>(st[2], &sn, &cs);
+      if (kFused) {
+        reinterpret_cast<float2*>(sh.sn[r3])[lane] = make_float2(sn.lo(), sn.hi());
+        reinterpret_cast<float2*>(sh.cs[r3])[lane] = make_float2(cs.lo(), cs.hi());
+      }
+      f2 Lg[kUniHaz][2], h[M];
+      assemble_unicycle_v<f2>(p, st, sn, cs, u, mu, sg, Lg, h);
+      // trivial test on the raw rows (h >= 0 on every row <=> x = 0 optimal) and NaN screen, per half
+      bool triv[2], nan[2];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float hv[M], gv[2 * kUniHaz];
+#pragma unroll
+        for (int r = 0; r < M; ++r) hv[r] = hh ? h[r].hi() : h[r].lo();
+#pragma unroll
+        for (int r = 0; r < kUniHaz; ++r) {
+          gv[2 * r] = hh ? Lg[r][0].hi() : Lg[r][0].lo();
+          gv[2 * r + 1] = hh ? Lg[r][1].hi() : Lg[r][1].lo();
+        }
+        classify_raw<M>(hv, triv[hh], nan[hh]);
+        nan[hh] = nan[hh] || any_nan<2 * kUniHaz>(gv);
+      }
+      const bool need0 = !triv[0] && !nan[0], need1 = !triv[1] && !nan[1];
+      // trivial / NaN instances: the clamped action replaces the nominal one in the slot (diff_cbf_qp.py:77)
+      {
+        const float z0 = nan[0] ? NAN : 0.f, z1 = nan[1] ? NAN : 0.f;
+        float2* acp = reinterpret_cast<float2*>(si.ac) + 2 * lane;
+        if (!need0) acp[0] = make_float2(clampf(u[0].lo() + z0, p.u_min[0], p.u_max[0]), clampf(u[1].lo() + z0, p.u_min[1], p.u_max[1]));
+        if (!need1) acp[1] = make_float2(clampf(u[0].hi() + z1, p.u_min[0], p.u_max[0]), clampf(u[1].hi() + z1, p.u_min[1], p.u_max[1]));
+        uchar2 c2;
+        c2.x = (unsigned char)(nan[0] ? RCBF_NAN : (need0 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
+        c2.y = (unsigned char)(nan[1] ? RCBF_NAN : (need1 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
+        reinterpret_cast<uchar2*>(sh.cls[r3])[lane] = c2;
+      }
+      const unsigned b0 = __ballot_sync(0xffffffffu, need0), b1 = __ballot_sync(0xffffffffu, need1);
+      const int n0 = __popc(b0);
+      const int tagbase = ((k & 3) << 8) | (r3 << 6) | (2 * lane);
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (hh ? need1 : need0) {
+          int slot = head + qn + (hh ? n0 + __popc(b1 & lt_mask) : __popc(b0 & lt_mask));
+          slot -= slot >= kS2Ring ? kS2Ring : 0;
+          slot -= slot >= kS2Ring ? kS2Ring : 0;
+          float v[16];
+#pragma unroll
+          for (int r = 0; r < kUniHaz; ++r) {
+            v[2 * r] = hh ? Lg[r][0].hi() : Lg[r][0].lo();
+            v[2 * r + 1] = hh ? Lg[r][1].hi() : Lg[r][1].lo();
+            v[10 + r] = hh ? h[r].hi() : h[r].lo();
+          }
+          v[15] = __int_as_float(tagbase + hh);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sh.ring[slot][q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+      pk = n0 + __popc(b1);
+      qn += pk;
+      c_nan += (nan[0] ? 1 : 0) + (nan[1] ? 1 : 0);
+      c_triv += ((!need0 && !nan[0]) ? 1 : 0) + ((!need1 && !nan[1]) ? 1 : 0);
+    } else {
+      ++after;
+    }
+    __syncwarp();
+
+    // ---------------------------------------------------------------- B-steps
+    // full warps while >= 32 problems wait; then, if tile k-2 (finished below) still has problems in the ring (they are
+    // the oldest entries), flush exactly those
+    const bool fin_due = (k >= 2) && (after <= 2);
+#pragma unroll 1
+    for (;;) {
+      const int old = qn - pk - pk1;
+      const int take = qn >= 32 ? 32 : ((fin_due && old > 0) ? old : 0);
+      if (take == 0) break;
+      if (lane < take) {
+        int slot = head + lane;
+        slot -= slot >= kS2Ring ? kS2Ring : 0;
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 t = sh.ring[slot][q];
+          v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+        const int tag = __float_as_int(v[15]);
+        const int pos = tag & 63;
+        float2* up = reinterpret_cast<float2*>(sh.in[tag >> 8].ac) + pos;
+        const float2 uu = *up;
+        float w[E::NWR];
+#pragma unroll
+        for (int r = 0; r < 2 * kUniHaz; ++r) w[r] = -v[r];  // G[i][:2] = -Lg[i]   diff_cbf_qp.py:259
+#pragma unroll
+        for (int r = 0; r < kUniHaz; ++r) w[10 + r] = v[10 + r];
+        w[15] = sub_rn(p.u_max[0], uu.x);                    // actuator rows, :365-377 (same expressions as the assembly)
+        w[16] = add_rn(-p.u_min[0], uu.x);
+        w[17] = sub_rn(p.u_max[1], uu.y);
+        w[18] = add_rn(-p.u_min[1], uu.y);
+        Normalised<NZ, M> nrm;
+        E::normalise_packed(w, p, nrm);
+        NormSolution<NZ, M> sol;
+        solve_normalised_fast<UniPat, NZ, M, true>(nrm, p.p_diag, false, sol);
+        if (sol.status == RCBF_PENDING) {
+          *up = make_float2(__uint_as_float(kPendingBits), 0.f);
+          sh.cls[(tag >> 6) & 3][pos] = (unsigned char)RCBF_PENDING;
+          c_pend += 1;
+        } else {
+          *up = make_float2(clampf(uu.x + (float)sol.x[0], p.u_min[0], p.u_max[0]),
+                            clampf(uu.y + (float)sol.x[1], p.u_min[1], p.u_max[1]));  // :77
+          c_iters += sol.iters;
+        }
+      }
+      head += take;
+      head -= head >= kS2Ring ? kS2Ring : 0;
+      qn -= take;
+      __syncwarp();
+    }
+
+    // ---------------------------------------------------------------- finish(tile k-2): whole tile, in place, TMA out
+    if (fin_due) {
+      const int ft = tile - 2 * nw;                        // `tile` names iteration k's tile index
+      typename WS::In& sf = sh.in[(k + 2) & 3];
+      const int rf = r3 == 2 ? 0 : r3 + 1;                 // (k - 2) % 3 == (k + 1) % 3
+      const int64_t i0 = (int64_t)ft << 6;
+      bulk_wait_read0();   // (storer lanes) the output staging of the previous finish has been read
+      __syncwarp();
+      const uchar2 cl = reinterpret_cast<const uchar2*>(sh.cls[rf])[lane];
+      const bool pend0 = cl.x == RCBF_PENDING, pend1 = cl.y == RCBF_PENDING;
+      if (a.status != nullptr) reinterpret_cast<int2*>(a.status + i0)[lane] = make_int2(cl.x, cl.y);
+      if (kFused) {
+        const float4 qa = reinterpret_cast<const float4*>(sf.st)[2 * lane];
+        const float4 qb = reinterpret_cast<const float4*>(sf.st)[2 * lane + 1];
+        const int2 sp = reinterpret_cast<const int2*>(sf.step)[lane];
+        const float4 us4 = reinterpret_cast<const float4*>(sf.ac)[lane];
+        const float2 sn2 = reinterpret_cast<const float2*>(sh.sn[rf])[lane];
+        const float2 cs2 = reinterpret_cast<const float2*>(sh.cs[rf])[lane];
+        f2 v[3] = {f2(qa.x, qb.x), f2(qa.y, qb.y), f2(qa.z, qb.z)};
+        f2 last(qa.w, qb.w);
+        typename VecOf<f2>::ivec stp = {sp.x, sp.y};
+        const f2 us[2] = {f2(us4.x, us4.z), f2(us4.y, us4.w)};
+        UniEnvOutV<f2> o;
+        unicycle_env_step_v<f2>(ef, v, last, stp, us, f2_pin(sn2.x, sn2.y), f2_pin(cs2.x, cs2.y), o);
+        if (ef.auto_reset && __any_sync(0xffffffffu, o.done.x || o.done.y)) {  // (a finished episode is a rare event)
+          v[0] = t_sel(o.done, f2(ef.init_x), v[0]);
+          v[1] = t_sel(o.done, f2(ef.init_y), v[1]);
+          v[2] = t_sel(o.done, f2(ef.init_th), v[2]);
+          last = t_sel(o.done, f2(reset_dist), last);
+          stp.x = o.done.x ? 0 : stp.x;
+          stp.y = o.done.y ? 0 : stp.y;
+        }
+        // a pending instance keeps its OLD state: the kernel's tail redoes it from scratch
+        reinterpret_cast<float4*>(sf.st)[2 * lane] = pend0 ? qa : make_float4(v[0].lo(), v[1].lo(), v[2].lo(), last.lo());
+        reinterpret_cast<float4*>(sf.st)[2 * lane + 1] = pend1 ? qb : make_float4(v[0].hi(), v[1].hi(), v[2].hi(), last.hi());
+        reinterpret_cast<int2*>(sf.step)[lane] = make_int2(pend0 ? sp.x : stp.x, pend1 ? sp.y : stp.y);
+        float2* ob = reinterpret_cast<float2*>(sh.obs) + 7 * lane;
+        ob[0] = make_float2(o.obs[0].lo(), o.obs[1].lo());
+        ob[1] = make_float2(o.obs[2].lo(), o.obs[3].lo());
+        ob[2] = make_float2(o.obs[4].lo(), o.obs[5].lo());
+        ob[3] = make_float2(o.obs[6].lo(), o.obs[0].hi());
+        ob[4] = make_float2(o.obs[1].hi(), o.obs[2].hi());
+        ob[5] = make_float2(o.obs[3].hi(), o.obs[4].hi());
+        ob[6] = make_float2(o.obs[5].hi(), o.obs[6].hi());
+        reinterpret_cast<float2*>(sh.reward)[lane] = make_float2(o.reward.lo(), o.reward.hi());
+        reinterpret_cast<float2*>(sh.cost)[lane] = make_float2(o.cost.lo(), o.cost.hi());
+        uchar2 d2, g2;
+        d2.x = o.done.x; d2.y = o.done.y;
+        g2.x = o.goal_met.x; g2.y = o.goal_met.y;
+        reinterpret_cast<uchar2*>(sh.done)[lane] = d2;
+        reinterpret_cast<uchar2*>(sh.goal)[lane] = g2;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copies
+      __syncwarp();
+      if (is_storer)
+        bulk_s2g_u32(const_cast<char*>(d_g) + (int64_t)ft * d_gstride,
+                     sh_base + d_soff + (d_slot ? (uint32_t)((k + 2) & 3) * (uint32_t)sizeof(typename WS::In) : 0u), d_gstride);
+      bulk_commit();
+      if (__any_sync(0xffffffffu, pend0 || pend1)) {  // (rare) queue them once the tile's stores are complete
+        bulk_wait0();
+        __syncwarp();
+        if (ws != nullptr) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (hh ? pend1 : pend0) {
+              __threadfence();
+              const unsigned long long slot = atomicAdd(&ws[kWsQueueCount], 1ULL);
+              if (slot < (unsigned long long)kWsQueueCap)
+                ws[kWsQueueBase + slot] = (unsigned long long)(i0 + 2 * lane + hh) + 1ULL;
+            }
+          }
+        }
+      }
+    }
+    if (after >= 2) break;
+    r3 = r3 == 2 ? 0 : r3 + 1;
+    tile += nw;
+  }
+  bulk_wait0();  // shared memory stays valid until the last bulk stores have read it; results visible
+  __syncwarp();
+  pdl_launch_dependents();
+  const bool own_tail = ws != nullptr;
+  // (the counters go out BEFORE the tail: nothing of this function's state is live across the call)
+  if (ws != nullptr) {
+    c_nan = __reduce_add_sync(0xffffffffu, c_nan);
+    c_triv = __reduce_add_sync(0xffffffffu, c_triv);
+    c_pend = __reduce_add_sync(0xffffffffu, c_pend);
+    c_iters = __reduce_add_sync(0xffffffffu, c_iters);
+    if (lane == 0) {
+      if (c_nan) atomicAdd(&ws[0], (unsigned long long)c_nan);
+      if (c_triv) atomicAdd(&ws[3], (unsigned long long)c_triv);
+      if (c_iters) atomicAdd(&ws[4], (unsigned long long)c_iters);
+      if (c_pend) atomicAdd(&ws[5], (unsigned long long)c_pend);
+    }
+  }
+  if (own_tail) tail_drain<E>(a, p, e, ws, reinterpret_cast<unsigned short*>(&sh.ring[0][0]), lane);
+  if (own_tail) {  // the last block to get here handles a queue overflow and resets the queue for the next call
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(&ws[kWsBlocksDone], 1ULL) == (unsigned long long)gridDim.x - 1ULL) ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const unsigned long long cnt = *(volatile rcbf_counters_t*)&ws[kWsQueueCount];
+      if (cnt > (unsigned long long)kWsQueueCap)
+        tail_scan<E>(a, n, p, e, ws, reinterpret_cast<unsigned short*>(&sh.ring[0][0]), lane, warp, kS2Warps);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        ws[kWsQueueCount] = 0ULL;
+        ws[kWsClaim] = 0ULL;
+        ws[kWsBlocksDone] = 0ULL;
+        __threadfence();
+      }
+    }
+  }
+}
+
+// Launch the two-per-lane kernel on the full 64-instance tiles of the call.  *handled = number of leading instances it
+// covers (0: the call does not qualify); the caller runs the one-per-lane kernel (launch_safe) on the ragged rest.
+template <bool kFused>
+inline int launch_safe2_tiles(const UniArgs& a, int64_t n, const UnicycleParams& p, const UnicycleEnvParams& e,
+                              rcbf_counters_t* ws, cudaStream_t s, int64_t* handled) {
+  using E = UniEnv<kFused>;
+  *handled = 0;
+  static const bool env_off = [] {
+    const char* v = getenv("RCBF_NO_SAFE2");
+    return v != nullptr && v[0] == '1';
+  }();
+  if (env_off || n < RCBF_S2_MIN_N || n > 0x7fffffffLL || p.solver_mode != 0) return 0;
+  if (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr) return 0;
+  auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!(ok16(a.ac) && ok16(a.mu) && ok16(a.sg) && ok16(a.out) && (a.status == nullptr || ok16(a.status)))) return 0;
+  if (kFused) {
+    if (!(ok16(a.state4) && ok16(a.step) && ok16(a.obs) && ok16(a.reward) && ok16(a.cost) && ok16(a.done) &&
+          ok16(a.goal_met)))
+      return 0;
+  } else if (!ok16(a.st)) {
+    return 0;
+  }
+  const int64_t n2 = n & ~(int64_t)63;
+  const int64_t ntiles = n2 >> 6;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  static int sm_count[64] = {};
+  if (sm_count[dev & 63] == 0) {
+    cudaFuncSetAttribute(k_safe2<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)(sizeof(S2Warp<kFused>) * kS2Warps));
+    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int sms = sm_count[dev & 63];
+  const int64_t want = (ntiles + kS2Warps - 1) / kS2Warps;
+  const int resident = sms * RCBF_S2_MINB;
+  const int grid = (int)(want < resident ? want : resident);
+  cudaError_t err =
+      launch_pdl(true, k_safe2<kFused>, grid, kS2Threads, sizeof(S2Warp<kFused>) * kS2Warps, s, a, n2, p, e, make_env_f(e), ws);
+  if (err != cudaSuccess) return (int)err;
+  if (ws == nullptr) {  // no workspace: a second kernel scans safe_action for the pending sentinel
+    const int64_t fb = (n2 + 127) / 128;
+    err = launch_pdl(true, k_safe_fallback<E, 0>, (int)(fb < sms * 4 ? fb : sms * 4), 128, 0, s, a, n2, p, e, ws);
+    if (err != cudaSuccess) return (int)err;
+  }
+  *handled = n2;
+  return 0;
+}
+
+}  // namespace rcbf

@@ -816,9 +816,9 @@ __device__ __noinline__ void tail_drain(const typename E::Args a, const typename
 template <class E>
 __device__ __noinline__ void tail_scan(const typename E::Args a, int64_t n, const typename E::Params p,
                                        const typename E::EnvParams e, rcbf_counters_t* ws, unsigned short* table,
-                                       int lane, int warp) {
+                                       int lane, int warp, int nwarps = kWarps) {
   const int ntable = build_enum_table<E::NZ, E::M>(table, lane);
-  for (int64_t i0 = (int64_t)warp * 32; i0 < n; i0 += kWarps * 32) {
+  for (int64_t i0 = (int64_t)warp * 32; i0 < n; i0 += nwarps * 32) {
     const int64_t i = i0 + lane;
     const bool pend = (i < n) && __float_as_uint(__ldcg(a.out + i * E::NU)) == kPendingBits;
     unsigned b = __ballot_sync(0xffffffffu, pend);
