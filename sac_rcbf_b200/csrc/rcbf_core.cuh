@@ -1112,6 +1112,281 @@ RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_d
   for (int j = 0; j < NZ; ++j) o.x[j] = y[j] * pisd[j];
 }
 
+// ---- presolve on the rows AS ASSEMBLED ---------------------------------------------------------------------------
+// The violation of row i in units of its norm, (h_i - A_i y) / |A_i| with A = G P^-1/2, does not depend on the row
+// normalisation of diff_cbf_qp.py:103-106 (n_i cancels), so the greedy pass scores the raw rows and only the <= NZ rows
+// that enter the active set are normalised (correctly rounded quotients, the float32 data the reference's QP sees).
+// The float64 certificate then solves on those rows exactly as before; the rows OUTSIDE the active set are screened in
+// float32 first: the sign of a slack does not depend on n_i > 0 either, so a raw slack that is positive by more than
+// its own rounding-error bound is feasible, and only a row inside that band is normalised and checked in float64.
+// Decisions and results are those of the all-rows float64 test; a QP costs ~150 instructions less.
+RCBF_HD float key_of(float v, int i) {  // v with the row index in the 4 low mantissa bits: min over keys = arg min
+#if defined(__CUDA_ARCH__)
+  return __uint_as_float((__float_as_uint(v) & 0xfffffff0u) | (uint32_t)i);
+#else
+  union { float f; uint32_t u; } c;
+  c.f = v;
+  c.u = (c.u & 0xfffffff0u) | (uint32_t)i;
+  return c.f;
+#endif
+}
+RCBF_HD int key_index(float k) {
+#if defined(__CUDA_ARCH__)
+  return (int)(__float_as_uint(k) & 15u);
+#else
+  union { float f; uint32_t u; } c;
+  c.f = k;
+  return (int)(c.u & 15u);
+#endif
+}
+RCBF_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }  // NaN operands are ignored
+
+template <typename Pat, int NZ, int M>
+RCBF_HD bool lnp_greedy_raw(const float G[M][NZ], const float h[M], const float pis[NZ], float A[M][NZ],
+                            float Rg[NZ][NZ], float rbg[NZ], uint32_t& mask_out, int& rounds) {
+  static_assert(M <= 16, "the row index travels in 4 mantissa bits");
+  float inv_norm[M];
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    float acc = 0.f;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      A[i][j] = Pat::nz(i, j) ? G[i][j] * pis[j] : 0.f;
+      if (Pat::nz(i, j)) acc = fmaf(A[i][j], A[i][j], acc);
+    }
+    inv_norm[i] = t_rsqrt(acc);
+  }
+  float y[NZ], R[NZ][NZ];
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    y[j] = 0.f;
+    rbg[j] = 0.f;
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) {
+      R[j][k] = 0.f;
+      Rg[j][k] = 0.f;
+    }
+  }
+  uint32_t mask = 0;
+  bool ok = true, feasible = false;
+  int r = 0;
+  RCBF_UNROLL
+  for (; r <= NZ; ++r) {
+    // most violated row at the current y: a tree of 3-input minima over (violation, index) keys
+    float key[M];
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      float acc = h[i];
+      if (r > 0) {  // (round 0 starts from y = 0: the products are exact zeros)
+        RCBF_UNROLL
+        for (int j = 0; j < NZ; ++j)
+          if (Pat::nz(i, j)) acc = fmaf(-A[i][j], y[j], acc);
+      }
+      key[i] = key_of(acc * inv_norm[i], i);
+    }
+    float worst = -1e-6f;
+    RCBF_UNROLL
+    for (int i = 0; i + 2 < M; i += 3) worst = fminf(worst, min3f(key[i], key[i + 1], key[i + 2]));
+    RCBF_UNROLL
+    for (int i = M - M % 3; i < M; ++i) worst = fminf(worst, key[i]);
+    if (!(worst < -1e-6f)) {
+      feasible = true;
+      break;
+    }
+    if (r == NZ) break;  // NZ rows and still infeasible
+    const int wi = key_index(worst);
+    mask |= 1u << wi;
+    // gather the raw row and normalise it (diff_cbf_qp.py:103-106): these are the QP data of the reference
+    float g[NZ], hh = 0.f;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) g[j] = 0.f;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      const bool put = (i == wi);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) g[j] = put ? G[i][j] : g[j];
+      hh = put ? h[i] : hh;
+      inv_norm[i] = put ? 0.f : inv_norm[i];  // a row of the active set is never picked again (its raw slack is only
+    }                                         // zero up to the rounding of the normalised quotients)
+    {
+      float gm = 0.f;
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) gm = fmaxf(gm, fabsf(g[j]));
+      const float ha = fabsf(hh);
+      const float n = (ha != ha) ? ha : fmaxf(gm, ha);
+      const float rn = rcp_refined(n);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) Rg[r][j] = div_by(g[j], n, rn);
+      rbg[r] = div_by(hh, n, rn);
+    }
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) R[r][j] = Rg[r][j] * pis[j];
+    // (R R') lam = -rb on the first r+1 rows (r is a compile-time constant once the loop is unrolled)
+    float lk[NZ];
+    if (r == 0) greedy_solve_rows<NZ, 1>(R, rbg, lk);
+    else if (r == 1 || NZ == 2) greedy_solve_rows<NZ, (NZ < 2 ? NZ : 2)>(R, rbg, lk);
+    else greedy_solve_rows<NZ, NZ>(R, rbg, lk);
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -1e-6f);  // NaN (dependent rows) -> false
+    if (!ok) break;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) {
+      float acc = 0.f;
+      RCBF_UNROLL
+      for (int k = 0; k < NZ; ++k)
+        if (k <= r) acc = fmaf(-R[k][j], lk[k], acc);  // (rows beyond r are zero and carry lam = 0)
+      y[j] = acc;
+    }
+  }
+  mask_out = mask;
+  rounds = r;
+  return ok && feasible;
+}
+
+// row i of the normalised problem in float64 (the exact slack of the certificate): h~_i - sum_j (G~_ij P_j^-1/2) y_j
+template <typename Pat, int NZ, int M>
+RCBF_HD double exact_slack_of_raw_row(const float g[NZ], float hh, const double pis[NZ], const double y[NZ]) {
+  float gm = 0.f;
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) gm = fmaxf(gm, fabsf(g[j]));
+  const float ha = fabsf(hh);
+  const float n = (ha != ha) ? ha : fmaxf(gm, ha);
+  const float rn = rcp_refined(n);
+  double acc = (double)div_by(hh, n, rn);
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) acc = fma(-((double)div_by(g[j], n, rn) * pis[j]), y[j], acc);
+  return acc;
+}
+
+template <typename Pat, int NZ, int M>
+RCBF_HD bool lnp_certify_raw(const float G[M][NZ], const float h[M], const float A[M][NZ], const double pis[NZ],
+                             const float Rg[NZ][NZ], const float rbg[NZ], int cnt, uint32_t mask, double tol_s,
+                             double tol_l, double y[NZ], double lk[NZ]) {
+  double R[NZ][NZ], Gm[NZ][NZ], nrb[NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) R[k][j] = (double)Rg[k][j] * pis[j];
+    nrb[k] = -(double)rbg[k];
+  }
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int l = 0; l <= k; ++l) {
+      double acc = 0.0;
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = fma(R[k][j], R[l][j], acc);
+      Gm[k][l] = acc;
+    }
+    Gm[k][k] = (k < cnt) ? Gm[k][k] : 1.0;
+  }
+  Chol<double, NZ> ch;
+  ch.factor(Gm);
+  ch.solve(nrb, lk);
+  bool ok = true;
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -tol_l);
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    double acc = 0.0;
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) acc = fma(-R[k][j], lk[k], acc);
+    y[j] = acc;
+  }
+  // rows of the active set (the gathered, normalised slots): |slack| <= tol_s in float64
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    double acc = (double)rbg[k];
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) acc = fma(-R[k][j], y[j], acc);
+    ok = ok && (k >= cnt || (acc >= -tol_s && acc <= tol_s));
+  }
+  // the other rows: float32 screen on the raw rows, float64 only inside the rounding-error band
+  float yf[NZ], ya[NZ];
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) {
+    yf[j] = (float)y[j];
+    ya[j] = fabsf(yf[j]);
+  }
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    float sl = h[i], mag = fabsf(h[i]);
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j)
+      if (Pat::nz(i, j)) {
+        sl = fmaf(-A[i][j], yf[j], sl);
+        mag = fmaf(fabsf(A[i][j]), ya[j], mag);
+      }
+    const bool act = (mask >> i) & 1u;
+    // |float32 error of sl| <= (NZ + 2) * 2^-24 * mag (+ the float rounding of y and A: 3 * 2^-24 * mag): band = 1e-5 mag
+    if (!act && !(sl > 1e-5f * mag)) {
+      float g[NZ];
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) g[j] = Pat::nz(i, j) ? G[i][j] : 0.f;
+      const double acc = exact_slack_of_raw_row<Pat, NZ, M>(g, h[i], pis, y);
+      ok = ok && (acc >= -tol_s);
+    }
+  }
+  return ok;
+}
+
+// Fast path of one QP given its rows as assembled (presolve mode): greedy guess, float64 certificate, and -- for the
+// callers that save them -- the dense multipliers / slacks of the normalised problem.
+template <typename Pat, int NZ, int M>
+RCBF_HD void solve_raw_fast(const float G[M][NZ], const float h[M], const float p_diag[NZ], bool want_aux,
+                            NormSolution<NZ, M>& o) {
+  double pisd[NZ];
+  float pisf[NZ];
+  pis_of<NZ, M>(p_diag, pisd, pisf);
+  double y[NZ], lk[NZ];
+  uint32_t mask;
+  int rounds;
+  float A[M][NZ], Rg[NZ][NZ], rbg[NZ];
+  const bool guess = lnp_greedy_raw<Pat, NZ, M>(G, h, pisf, A, Rg, rbg, mask, rounds);
+  o.status = RCBF_PENDING;
+  o.iters = rounds;
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) y[j] = 0.0;
+  if (guess && lnp_certify_raw<Pat, NZ, M>(G, h, A, pisd, Rg, rbg, rounds, mask, kTolSlack, kTolDual, y, lk)) {
+    o.status = RCBF_OK_CERTIFIED;
+    if (want_aux) {
+      Normalised<NZ, M> nrm;
+      normalise_rows<Pat, NZ, M>(G, h, nrm);
+      lnp_expand_aux<Pat, NZ, M>(nrm.Gn, nrm.hn, pisd, Rg, rbg, mask, y, lk, o.lam, o.s);
+    }
+  }
+  if (M <= 4 && o.status == RCBF_PENDING) {
+    // Few rows (SimulatedCars: 10 candidate active sets): when the greedy guess is not certified, enumerate right
+    // here with the all-rows float64 certificate instead of queueing for pass 2 (about 1 instance in 1000).
+    Normalised<NZ, M> nrm;
+    normalise_rows<Pat, NZ, M>(G, h, nrm);
+    const NormCert<NZ, M> cp{nrm, pisd};
+    double lam[M], sl[M];
+#ifdef __CUDA_ARCH__
+#pragma unroll 1
+#endif
+    for (uint32_t m = 1; m < (1u << M); ++m) {
+      int pc = 0;
+      RCBF_UNROLL
+      for (int i = 0; i < M; ++i) pc += (m >> i) & 1u;
+      if (pc > NZ) continue;
+      if (lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, m, kTolSlack, kTolDual, y, lam, sl)) {
+        o.status = RCBF_OK_CERTIFIED;
+        o.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
+        RCBF_UNROLL
+        for (int i = 0; i < M; ++i) {
+          o.lam[i] = lam[i];
+          o.s[i] = sl[i];
+        }
+        break;
+      }
+    }
+  }
+  RCBF_UNROLL
+  for (int j = 0; j < NZ; ++j) o.x[j] = y[j] * pisd[j];
+}
+
 // NaN-PROPAGATING 3-input min / max (one FMNMX3.NAN on sm_100): the result is NaN iff any input is
 RCBF_HD float nanmin3(float a, float b, float c) {
 #if defined(__CUDA_ARCH__)
@@ -1229,7 +1504,7 @@ RCBF_HD void unicycle_safe_action(const UnicycleParams& p, const float st[3], co
   if (triv || nan) {
     trivial_solution<UniPat, kUniNZ, kUniM>(w.nrm, nan, w.sol);
   } else {
-    if (kMode == 0) solve_normalised_fast<UniPat, kUniNZ, kUniM, true>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode == 0) solve_raw_fast<UniPat, kUniNZ, kUniM>(w.raw.G, w.raw.h, p.p_diag, true, w.sol);
     if (kMode == 1) solve_normalised_fast<UniPat, kUniNZ, kUniM, false>(w.nrm, p.p_diag, true, w.sol);
     if (kMode >= 2) solve_normalised_full<UniPat, kUniNZ, kUniM>(w.nrm, p.p_diag, kMode == 3, w.sol);
   }
@@ -1254,7 +1529,7 @@ RCBF_HD void cars_safe_action(const CarsParams& p, const float st[10], float u, 
   if (triv || nan) {
     trivial_solution<CarsPat, kCarsNZ, kCarsM>(w.nrm, nan, w.sol);
   } else {
-    if (kMode == 0) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, true>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode == 0) solve_raw_fast<CarsPat, kCarsNZ, kCarsM>(w.raw.G, w.raw.h, p.p_diag, true, w.sol);
     if (kMode == 1) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, false>(w.nrm, p.p_diag, true, w.sol);
     if (kMode >= 2) solve_normalised_full<CarsPat, kCarsNZ, kCarsM>(w.nrm, p.p_diag, kMode == 3, w.sol);
   }

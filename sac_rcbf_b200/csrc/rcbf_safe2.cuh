@@ -75,9 +75,7 @@ struct alignas(16) S2Warp {
   float mu[192], sg[192];   // only the assembly reads them: single buffer, refilled right after the A-step's read
   float sn[3][64], cs[3][64];  // sin / cos of the heading, kept from the assembly for env.step
   float4 ring[kS2Ring][4];  // problem ring: Lg[5][2], h[5], tag
-  float obs[kFused ? 448 : 4];   // output staging of the tile being finished
-  float reward[kFused ? 64 : 4], cost[kFused ? 64 : 4];
-  uint8_t done[kFused ? 64 : 16], goal[kFused ? 64 : 16];
+  float obs[kFused ? 448 : 4];   // observation rows of the tile being finished (28-byte rows: leave by one bulk store)
   uint8_t cls[3][64];       // per instance: RCBF_OK_TRIVIAL / RCBF_OK_CERTIFIED / RCBF_NAN / RCBF_PENDING
   uint64_t bar[2];
 };
@@ -102,46 +100,22 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
   int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
   constexpr uint32_t kInBytes = (kFused ? 1024 + 256 : 768) + 512 + 768 + 768;
 
-  // Bulk-copy descriptors, one per lane: lanes 0..4 each own one INPUT array of a tile (state4, step, action, mean,
-  // sigma), lanes 8..15 one OUTPUT array (safe action, state4, step, obs, reward, cost, done, goal_met).  A tile's copies
-  // are then ONE predicated cp.async.bulk instruction executed by several lanes instead of a sequence issued by lane 0
-  // (each with its own 64-bit address arithmetic): ~60 fewer warp instructions per tile.
-  const uint32_t sh_base = smem_u32(&sh);
-  const char* d_g = nullptr;      // global base of this lane's array
-  uint32_t d_gstride = 0;         // bytes per tile
-  uint32_t d_soff = 0;            // shared-memory offset inside this warp's block (slot 0 for the slot-resident ones)
-  bool d_slot = false;            // lives in the tile's input slot (sh.in[k & 3])
-  {
-    const int l = lane;
-    if (kFused) {
-      if (l == 0) { d_g = (const char*)a.state4; d_gstride = 1024; d_soff = offsetof(WS, in) + offsetof(typename WS::In, st); d_slot = true; }
-      if (l == 1) { d_g = (const char*)a.step; d_gstride = 256; d_soff = offsetof(WS, in) + offsetof(typename WS::In, step); d_slot = true; }
-    } else {
-      if (l == 0) { d_g = (const char*)a.st; d_gstride = 768; d_soff = offsetof(WS, in) + offsetof(typename WS::In, st); d_slot = true; }
-    }
-    if (l == 2) { d_g = (const char*)a.ac; d_gstride = 512; d_soff = offsetof(WS, in) + offsetof(typename WS::In, ac); d_slot = true; }
-    if (l == 3) { d_g = (const char*)a.mu; d_gstride = 768; d_soff = offsetof(WS, mu); }
-    if (l == 4) { d_g = (const char*)a.sg; d_gstride = 768; d_soff = offsetof(WS, sg); }
-    if (l == 8) { d_g = (const char*)a.out; d_gstride = 512; d_soff = offsetof(WS, in) + offsetof(typename WS::In, ac); d_slot = true; }
-    if (kFused) {
-      if (l == 9) { d_g = (const char*)a.state4; d_gstride = 1024; d_soff = offsetof(WS, in) + offsetof(typename WS::In, st); d_slot = true; }
-      if (l == 10) { d_g = (const char*)a.step; d_gstride = 256; d_soff = offsetof(WS, in) + offsetof(typename WS::In, step); d_slot = true; }
-      if (l == 11) { d_g = (const char*)a.obs; d_gstride = 1792; d_soff = offsetof(WS, obs); }
-      if (l == 12) { d_g = (const char*)a.reward; d_gstride = 256; d_soff = offsetof(WS, reward); }
-      if (l == 13) { d_g = (const char*)a.cost; d_gstride = 256; d_soff = offsetof(WS, cost); }
-      if (l == 14) { d_g = (const char*)a.done; d_gstride = 64; d_soff = offsetof(WS, done); }
-      if (l == 15) { d_g = (const char*)a.goal_met; d_gstride = 64; d_soff = offsetof(WS, goal); }
-    }
-  }
-  const bool is_loader = d_g != nullptr && lane < 8;
-  const bool is_storer = d_g != nullptr && lane >= 8;
-  auto issue = [&](int t, int k) {  // all lanes: put tile t in flight into slot k & 3 (+ the mu / sigma buffer)
+  // lane 0 puts tile t in flight into slot k & 3 (+ the mu / sigma buffer).  cp.async.bulk is a uniform-datapath
+  // instruction (UBLKCP): one copy per execution, so per-lane descriptors would only turn into a loop over lanes.
+  auto issue = [&](int t, int k) {
+    typename WS::In& si = sh.in[k & 3];
     uint64_t* bar = &sh.bar[k & 1];
-    if (lane == 0) mbar_expect_tx(bar, kInBytes);
-    __syncwarp();
-    if (is_loader)
-      bulk_g2s_u32(sh_base + d_soff + (d_slot ? (uint32_t)(k & 3) * (uint32_t)sizeof(typename WS::In) : 0u),
-                   d_g + (int64_t)t * d_gstride, d_gstride, bar);
+    const int64_t i0 = (int64_t)t << 6;
+    mbar_expect_tx(bar, kInBytes);
+    if (kFused) {
+      bulk_g2s(si.st, a.state4 + i0 * 4, 1024, bar);
+      bulk_g2s(si.step, a.step + i0, 256, bar);
+    } else {
+      bulk_g2s(si.st, a.st + i0 * 3, 768, bar);
+    }
+    bulk_g2s(si.ac, a.ac + i0 * 2, 512, bar);
+    bulk_g2s(sh.mu, a.mu + i0 * 3, 768, bar);
+    bulk_g2s(sh.sg, a.sg + i0 * 3, 768, bar);
   };
 
   pdl_wait();
@@ -151,7 +125,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  if (tile < ntiles) issue(tile, 0);
+  if (lane == 0 && tile < ntiles) issue(tile, 0);
 
   const float reset_dist = unicycle_reset_dist(ef);
   int after = 0;  // iterations past this warp's last tile (the last two tiles are finished then)
@@ -184,10 +158,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         sg[0] = f2(g0.x, g1.y); sg[1] = f2(g0.y, g2.x); sg[2] = f2_pin(g1.x, g2.y);
       }
       __syncwarp();
-      if (tile + nw < ntiles) {
-        bulk_wait_read0();  // the stores of the tile that last used slot (k+1) & 3 have read it (issued an iteration ago)
-        issue(tile + nw, k + 1);
-      }
+      if (lane == 0 && tile + nw < ntiles) issue(tile + nw, k + 1);  // slot (k+1) & 3: its tile was finished an iteration ago
       f2 sn, cs;
       sincos_v<f2>(st[2], &sn, &cs);
       if (kFused) {
@@ -284,10 +255,10 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         w[16] = add_rn(-p.u_min[0], uu.x);
         w[17] = sub_rn(p.u_max[1], uu.y);
         w[18] = add_rn(-p.u_min[1], uu.y);
-        Normalised<NZ, M> nrm;
-        E::normalise_packed(w, p, nrm);
+        float Gr[M][NZ], hr[M];
+        E::unpack_raw(w, p, Gr, hr);
         NormSolution<NZ, M> sol;
-        solve_normalised_fast<UniPat, NZ, M, true>(nrm, p.p_diag, false, sol);
+        solve_raw_fast<UniPat, NZ, M>(Gr, hr, p.p_diag, false, sol);
         if (sol.status == RCBF_PENDING) {
           *up = make_float2(__uint_as_float(kPendingBits), 0.f);
           sh.cls[(tag >> 6) & 3][pos] = (unsigned char)RCBF_PENDING;
@@ -310,8 +281,10 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
       typename WS::In& sf = sh.in[(k + 2) & 3];
       const int rf = r3 == 2 ? 0 : r3 + 1;                 // (k - 2) % 3 == (k + 1) % 3
       const int64_t i0 = (int64_t)ft << 6;
-      bulk_wait_read0();   // (storer lanes) the output staging of the previous finish has been read
-      __syncwarp();
+      if (kFused) {
+        if (lane == 0) bulk_wait_read0();   // the observation staging of the previous finish has been read
+        __syncwarp();
+      }
       const uchar2 cl = reinterpret_cast<const uchar2*>(sh.cls[rf])[lane];
       const bool pend0 = cl.x == RCBF_PENDING, pend1 = cl.y == RCBF_PENDING;
       if (a.status != nullptr) reinterpret_cast<int2*>(a.status + i0)[lane] = make_int2(cl.x, cl.y);
@@ -336,10 +309,21 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
           stp.x = o.done.x ? 0 : stp.x;
           stp.y = o.done.y ? 0 : stp.y;
         }
-        // a pending instance keeps its OLD state: the kernel's tail redoes it from scratch
-        reinterpret_cast<float4*>(sf.st)[2 * lane] = pend0 ? qa : make_float4(v[0].lo(), v[1].lo(), v[2].lo(), last.lo());
-        reinterpret_cast<float4*>(sf.st)[2 * lane + 1] = pend1 ? qb : make_float4(v[0].hi(), v[1].hi(), v[2].hi(), last.hi());
-        reinterpret_cast<int2*>(sf.step)[lane] = make_int2(pend0 ? sp.x : stp.x, pend1 ? sp.y : stp.y);
+        // Outputs: every array except the 28-byte observation rows is a contiguous span per tile that the lanes cover
+        // with one (two for state4) fully coalesced vector store; a pending instance keeps its OLD state (the kernel's
+        // tail redoes it from scratch) and whatever else is written for it here is overwritten there.
+        reinterpret_cast<float4*>(a.out + i0 * 2)[lane] = us4;
+        float4* gs = reinterpret_cast<float4*>(a.state4 + i0 * 4) + 2 * lane;
+        gs[0] = pend0 ? qa : make_float4(v[0].lo(), v[1].lo(), v[2].lo(), last.lo());
+        gs[1] = pend1 ? qb : make_float4(v[0].hi(), v[1].hi(), v[2].hi(), last.hi());
+        reinterpret_cast<int2*>(a.step + i0)[lane] = make_int2(pend0 ? sp.x : stp.x, pend1 ? sp.y : stp.y);
+        reinterpret_cast<float2*>(a.reward + i0)[lane] = make_float2(o.reward.lo(), o.reward.hi());
+        reinterpret_cast<float2*>(a.cost + i0)[lane] = make_float2(o.cost.lo(), o.cost.hi());
+        uchar2 d2, g2;
+        d2.x = o.done.x; d2.y = o.done.y;
+        g2.x = o.goal_met.x; g2.y = o.goal_met.y;
+        reinterpret_cast<uchar2*>(a.done + i0)[lane] = d2;
+        reinterpret_cast<uchar2*>(a.goal_met + i0)[lane] = g2;
         float2* ob = reinterpret_cast<float2*>(sh.obs) + 7 * lane;
         ob[0] = make_float2(o.obs[0].lo(), o.obs[1].lo());
         ob[1] = make_float2(o.obs[2].lo(), o.obs[3].lo());
@@ -348,23 +332,20 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         ob[4] = make_float2(o.obs[1].hi(), o.obs[2].hi());
         ob[5] = make_float2(o.obs[3].hi(), o.obs[4].hi());
         ob[6] = make_float2(o.obs[5].hi(), o.obs[6].hi());
-        reinterpret_cast<float2*>(sh.reward)[lane] = make_float2(o.reward.lo(), o.reward.hi());
-        reinterpret_cast<float2*>(sh.cost)[lane] = make_float2(o.cost.lo(), o.cost.hi());
-        uchar2 d2, g2;
-        d2.x = o.done.x; d2.y = o.done.y;
-        g2.x = o.goal_met.x; g2.y = o.goal_met.y;
-        reinterpret_cast<uchar2*>(sh.done)[lane] = d2;
-        reinterpret_cast<uchar2*>(sh.goal)[lane] = g2;
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copies
-      __syncwarp();
-      if (is_storer)
-        bulk_s2g_u32(const_cast<char*>(d_g) + (int64_t)ft * d_gstride,
-                     sh_base + d_soff + (d_slot ? (uint32_t)((k + 2) & 3) * (uint32_t)sizeof(typename WS::In) : 0u), d_gstride);
-      bulk_commit();
-      if (__any_sync(0xffffffffu, pend0 || pend1)) {  // (rare) queue them once the tile's stores are complete
-        bulk_wait0();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
         __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(a.obs + i0 * 7, sh.obs, 1792);
+          bulk_commit();
+        }
+      } else {
+        reinterpret_cast<float4*>(a.out + i0 * 2)[lane] = reinterpret_cast<const float4*>(sf.ac)[lane];
+      }
+      if (__any_sync(0xffffffffu, pend0 || pend1)) {  // (rare) queue them once the tile's stores are complete
+        if (kFused) {
+          if (lane == 0) bulk_wait0();
+          __syncwarp();
+        }
         if (ws != nullptr) {
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -382,7 +363,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
     r3 = r3 == 2 ? 0 : r3 + 1;
     tile += nw;
   }
-  bulk_wait0();  // shared memory stays valid until the last bulk stores have read it; results visible
+  if (kFused && lane == 0) bulk_wait0();  // shared memory stays valid until the last bulk store has read it
   __syncwarp();
   pdl_launch_dependents();
   const bool own_tail = ws != nullptr;

@@ -279,8 +279,7 @@ struct UniEnv {
 #pragma unroll
     for (int r = 0; r < M; ++r) w[10 + r] = raw.h[r];
   }
-  __device__ static __forceinline__ void normalise_packed(const float w[NWR], const Params& p, Normalised<NZ, M>& nrm) {
-    float G[M][NZ], h[M];
+  __device__ static __forceinline__ void unpack_raw(const float w[NWR], const Params&, float G[M][NZ], float h[M]) {
 #pragma unroll
     for (int r = 0; r < kUniHaz; ++r) {
       G[r][0] = w[2 * r];
@@ -297,6 +296,10 @@ struct UniEnv {
     }
 #pragma unroll
     for (int r = 0; r < M; ++r) h[r] = w[10 + r];
+  }
+  __device__ static __forceinline__ void normalise_packed(const float w[NWR], const Params& p, Normalised<NZ, M>& nrm) {
+    float G[M][NZ], h[M];
+    unpack_raw(w, p, G, h);
     normalise_rows<Pat, NZ, M>(G, h, nrm);
   }
   __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
@@ -464,8 +467,7 @@ struct CarsEnv {
 #pragma unroll
     for (int r = 0; r < M; ++r) w[2 + r] = raw.h[r];
   }
-  __device__ static __forceinline__ void normalise_packed(const float w[NWR], const Params& p, Normalised<NZ, M>& nrm) {
-    float G[M][NZ], h[M];
+  __device__ static __forceinline__ void unpack_raw(const float w[NWR], const Params& p, float G[M][NZ], float h[M]) {
     G[0][0] = w[0];
     G[1][0] = w[1];
     G[0][1] = -p.slack_coeff;  // diff_cbf_qp.py:352
@@ -474,6 +476,10 @@ struct CarsEnv {
     G[3][0] = -1.0f; G[3][1] = 0.0f;   // :375-376
 #pragma unroll
     for (int r = 0; r < M; ++r) h[r] = w[2 + r];
+  }
+  __device__ static __forceinline__ void normalise_packed(const float w[NWR], const Params& p, Normalised<NZ, M>& nrm) {
+    float G[M][NZ], h[M];
+    unpack_raw(w, p, G, h);
     normalise_rows<Pat, NZ, M>(G, h, nrm);
   }
   __device__ static __forceinline__ void assemble(const Args& a, const Params& p, int64_t i, const Inst& in,
@@ -915,9 +921,9 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
         // so the lanes that need a solve do it right here at partial lane utilisation; every instance of the tile is
         // then finished by the coalesced whole-tile path (no second pass with lane-per-row 40-byte accesses)
         if (need) {
-          Normalised<NZ, M> nrm;
-          E::normalise_packed(w, p, nrm);
-          solve_normalised_fast<typename E::Pat, NZ, M, true>(nrm, p.p_diag, kSaved, solA);
+          float Gr[M][NZ], hr[M];
+          E::unpack_raw(w, p, Gr, hr);
+          solve_raw_fast<typename E::Pat, NZ, M>(Gr, hr, p.p_diag, kSaved, solA);
           if (solA.status == RCBF_PENDING) {
             mark_pending<E>(a, iA, ws);
             c_pend += 1;
@@ -1049,10 +1055,10 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
         if (lane < take) {
           float w[NWR];
           sh.pop(slot, w, iB);
-          Normalised<NZ, M> nrm;
-          E::normalise_packed(w, p, nrm);
+          float Gr[M][NZ], hr[M];
+          E::unpack_raw(w, p, Gr, hr);
           NormSolution<NZ, M> sol;
-          solve_normalised_fast<typename E::Pat, NZ, M, true>(nrm, p.p_diag, kSaved, sol);
+          solve_raw_fast<typename E::Pat, NZ, M>(Gr, hr, p.p_diag, kSaved, sol);
           if (sol.status == RCBF_PENDING) {
             mark_pending<E>(a, iB, ws);
             c_pend += 1;
