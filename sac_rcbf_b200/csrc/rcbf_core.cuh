@@ -1309,6 +1309,7 @@ RCBF_HD bool lnp_certify_raw(const float G[M][NZ], const float h[M], const float
     yf[j] = (float)y[j];
     ya[j] = fabsf(yf[j]);
   }
+  uint32_t amb = 0;
   RCBF_UNROLL
   for (int i = 0; i < M; ++i) {
     float sl = h[i], mag = fabsf(h[i]);
@@ -1320,13 +1321,29 @@ RCBF_HD bool lnp_certify_raw(const float G[M][NZ], const float h[M], const float
       }
     const bool act = (mask >> i) & 1u;
     // |float32 error of sl| <= (NZ + 2) * 2^-24 * mag (+ the float rounding of y and A: 3 * 2^-24 * mag): band = 1e-5 mag
-    if (!act && !(sl > 1e-5f * mag)) {
-      float g[NZ];
+    if (!act && !(sl > 1e-5f * mag)) amb |= 1u << i;
+  }
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+  for (; amb != 0u; amb &= amb - 1u) {  // (rare) one copy of the exact test: gather the row like the presolve does
+#if defined(__CUDA_ARCH__)
+    const int wi = __ffs((int)amb) - 1;
+#else
+    const int wi = __builtin_ffs((int)amb) - 1;
+#endif
+    float g[NZ], hh = 0.f;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) g[j] = 0.f;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      const bool put = (i == wi);
       RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) g[j] = Pat::nz(i, j) ? G[i][j] : 0.f;
-      const double acc = exact_slack_of_raw_row<Pat, NZ, M>(g, h[i], pis, y);
-      ok = ok && (acc >= -tol_s);
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) g[j] = put ? G[i][j] : g[j];
+      hh = put ? h[i] : hh;
     }
+    ok = ok && (exact_slack_of_raw_row<Pat, NZ, M>(g, hh, pis, y) >= -tol_s);
   }
   return ok;
 }

@@ -35,17 +35,17 @@
 namespace rcbf {
 
 #ifndef RCBF_S2_MINB
-#define RCBF_S2_MINB 3     // resident blocks per SM
+#define RCBF_S2_MINB 1     // resident blocks per SM (A/B on B200: 1 x 12 warps > 3 x 4 warps > 2 x 6 warps)
 #endif
 #ifndef RCBF_S2_WARPS
-#define RCBF_S2_WARPS 4    // warps per block
+#define RCBF_S2_WARPS 12   // warps per block
 #endif
 #ifndef RCBF_S2_MIN_N
 #define RCBF_S2_MIN_N 4096  // below this the one-per-lane kernel spreads the few tiles over more warps
 #endif
 constexpr int kS2Warps = RCBF_S2_WARPS;
 constexpr int kS2Threads = 32 * kS2Warps;
-constexpr int kS2Ring = 96;  // <= 31 problems left over + 64 new ones
+constexpr int kS2Ring = 95;  // <= 31 problems left over + 64 new ones
 
 // bulk stores (shared -> global) + their completion
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
@@ -75,13 +75,21 @@ struct alignas(16) S2Warp {
   float mu[192], sg[192];   // only the assembly reads them: single buffer, refilled right after the A-step's read
   float sn[3][64], cs[3][64];  // sin / cos of the heading, kept from the assembly for env.step
   float4 ring[kS2Ring][4];  // problem ring: Lg[5][2], h[5], tag
-  float obs[kFused ? 448 : 4];   // observation rows of the tile being finished (28-byte rows: leave by one bulk store)
+  // (the observation rows of the tile being finished, 64 x 28 B = exactly one In slot, are staged in that tile's own
+  //  slot once its state / step / action have been read, and leave from there by one bulk store)
   uint8_t cls[3][64];       // per instance: RCBF_OK_TRIVIAL / RCBF_OK_CERTIFIED / RCBF_NAN / RCBF_PENDING
   uint64_t bar[2];
 };
 
+static_assert(sizeof(S2Warp<true>::In) == 64 * 7 * 4, "a fused input slot doubles as the staging of the tile's observation rows");
+
+#ifdef RCBF_S2_MAXNREG
+#define RCBF_S2_BOUNDS __maxnreg__(RCBF_S2_MAXNREG)
+#else
+#define RCBF_S2_BOUNDS __launch_bounds__(kS2Threads, RCBF_S2_MINB)
+#endif
 template <bool kFused>
-__global__ void __launch_bounds__(kS2Threads, RCBF_S2_MINB)
+__global__ void RCBF_S2_BOUNDS
 k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnvParams e, UniEnvF ef /* = make_env_f(e) */,
         rcbf_counters_t* ws) {
   using E = UniEnv<kFused>;
@@ -93,7 +101,12 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
   const unsigned lt_mask = (1u << lane) - 1u;
   const int ntiles = (int)(n >> 6);
   const int nw = (int)gridDim.x * kS2Warps;
-  int tile = (int)blockIdx.x * kS2Warps + warp;
+  // Tiles are dealt round robin over the resident warps.  (Tried on B200: claiming every tile after the first from an
+  // atomic ticket in the workspace to even out the tail.  65 536 same-address atomics per launch serialise in L2 for
+  // about as long as the kernel runs: 0.153 ms against 0.137 ms with the static deal.)
+  int tile = (int)blockIdx.x * kS2Warps + warp;   // tile of iteration k
+  int tile1 = tile + nw;                          // tile of iteration k + 1
+  int tm1 = 0, tm2 = 0;                           // tiles of iterations k - 1, k - 2
   int head = 0, qn = 0;          // problem ring
   int pk = 0, pk1 = 0;           // problems pushed by tiles k, k-1 (the newest pk + pk1 entries of the ring)
   int r3 = 0;                    // k % 3
@@ -158,7 +171,6 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         sg[0] = f2(g0.x, g1.y); sg[1] = f2(g0.y, g2.x); sg[2] = f2_pin(g1.x, g2.y);
       }
       __syncwarp();
-      if (lane == 0 && tile + nw < ntiles) issue(tile + nw, k + 1);  // slot (k+1) & 3: its tile was finished an iteration ago
       f2 sn, cs;
       sincos_v<f2>(st[2], &sn, &cs);
       if (kFused) {
@@ -193,6 +205,12 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         c2.x = (unsigned char)(nan[0] ? RCBF_NAN : (need0 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
         c2.y = (unsigned char)(nan[1] ? RCBF_NAN : (need1 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
         reinterpret_cast<uchar2*>(sh.cls[r3])[lane] = c2;
+      }
+      if (lane == 0 && tile1 < ntiles) {
+        // slot (k+1) & 3 belonged to the tile finished in the previous iteration; the bulk store of its observation rows
+        // (staged in that slot) was issued then and has long read it
+        if (kFused) bulk_wait_read0();
+        issue(tile1, k + 1);
       }
       const unsigned b0 = __ballot_sync(0xffffffffu, need0), b1 = __ballot_sync(0xffffffffu, need1);
       const int n0 = __popc(b0);
@@ -277,14 +295,10 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
 
     // ---------------------------------------------------------------- finish(tile k-2): whole tile, in place, TMA out
     if (fin_due) {
-      const int ft = tile - 2 * nw;                        // `tile` names iteration k's tile index
+      const int ft = tm2;
       typename WS::In& sf = sh.in[(k + 2) & 3];
       const int rf = r3 == 2 ? 0 : r3 + 1;                 // (k - 2) % 3 == (k + 1) % 3
       const int64_t i0 = (int64_t)ft << 6;
-      if (kFused) {
-        if (lane == 0) bulk_wait_read0();   // the observation staging of the previous finish has been read
-        __syncwarp();
-      }
       const uchar2 cl = reinterpret_cast<const uchar2*>(sh.cls[rf])[lane];
       const bool pend0 = cl.x == RCBF_PENDING, pend1 = cl.y == RCBF_PENDING;
       if (a.status != nullptr) reinterpret_cast<int2*>(a.status + i0)[lane] = make_int2(cl.x, cl.y);
@@ -324,7 +338,8 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         g2.x = o.goal_met.x; g2.y = o.goal_met.y;
         reinterpret_cast<uchar2*>(a.done + i0)[lane] = d2;
         reinterpret_cast<uchar2*>(a.goal_met + i0)[lane] = g2;
-        float2* ob = reinterpret_cast<float2*>(sh.obs) + 7 * lane;
+        __syncwarp();  // every lane has read its part of the slot: it now stages the observation rows
+        float2* ob = reinterpret_cast<float2*>(&sf) + 7 * lane;
         ob[0] = make_float2(o.obs[0].lo(), o.obs[1].lo());
         ob[1] = make_float2(o.obs[2].lo(), o.obs[3].lo());
         ob[2] = make_float2(o.obs[4].lo(), o.obs[5].lo());
@@ -335,7 +350,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copy
         __syncwarp();
         if (lane == 0) {
-          bulk_s2g(a.obs + i0 * 7, sh.obs, 1792);
+          bulk_s2g(a.obs + i0 * 7, &sf, 1792);
           bulk_commit();
         }
       } else {
@@ -361,7 +376,10 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
     }
     if (after >= 2) break;
     r3 = r3 == 2 ? 0 : r3 + 1;
-    tile += nw;
+    tm2 = tm1;
+    tm1 = tile;
+    tile = tile1;
+    tile1 += nw;
   }
   if (kFused && lane == 0) bulk_wait0();  // shared memory stays valid until the last bulk store has read it
   __syncwarp();
