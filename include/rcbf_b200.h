@@ -115,8 +115,31 @@ int rcbf_cars_safe_action_bwd(const float* state, const float* action, const flo
                               const float* lam, const float* slack, const float* grad_out, int64_t n,
                               const rcbf_cars_params* p_host, float* grad_action, void* stream);
 
+/* ---- the differentiable path in compact form (what CBFQPLayer's autograd function uses) ---------------------------
+ * The forward saves ONE int32 per instance, meta = (status << 16) | active-set mask (bit i = row i of G~x <= h~ is
+ * active at the optimum; 0xffff: no vertex, interior-point result), instead of x / lam / slack (84 bytes).  The backward
+ * finishes a trivial instance (status RCBF_OK_TRIVIAL: x = 0, gradient = the clamp mask of diff_cbf_qp.py:77) from 28
+ * bytes; for the others it re-assembles the constraints, rebuilds x / lam / slack from the active set with the float64
+ * solve of the forward certificate and applies the same implicit-KKT backward as rcbf_*_safe_action_bwd. */
+int rcbf_unicycle_safe_action_saved(const float* state, const float* action, const float* mean, const float* sigma,
+                                    int64_t n, const rcbf_unicycle_params* p_host, float* safe_action /* n*2 */,
+                                    int32_t* meta /* n */, rcbf_counters_t* workspace, void* stream);
+int rcbf_cars_safe_action_saved(const float* state, const float* action, const float* sigma, int64_t n,
+                                const rcbf_cars_params* p_host, float* safe_action /* n */, int32_t* meta /* n */,
+                                rcbf_counters_t* workspace, void* stream);
+/* scratch: nullable device buffer of n + 4 int32.  With it, large batches run as two launches (classify + a dense
+ * list of the non-trivial instances of the whole batch, then the float64 part on full blocks); without it, or for
+ * small batches, as one launch that compacts inside each block. */
+int rcbf_unicycle_safe_action_bwd_meta(const float* state, const float* action, const float* mean, const float* sigma,
+                                       const int32_t* meta, const float* grad_out, int64_t n,
+                                       const rcbf_unicycle_params* p_host, float* grad_action, int32_t* scratch,
+                                       void* stream);
+int rcbf_cars_safe_action_bwd_meta(const float* state, const float* action, const float* sigma, const int32_t* meta,
+                                   const float* grad_out, int64_t n, const rcbf_cars_params* p_host, float* grad_action,
+                                   int32_t* scratch, void* stream);
+
 /* ---- generic small QP  min 1/2 x'Qx + p'x  s.t. Gx <= h  (cbf_layer / solve_qp), float64 tensors like qpth sees ---
- * (nz, m) in {(3,9), (2,4)}.  normalise != 0 applies the [G|h] row normalisation of solve_qp first. */
+ * (nz, m) in {(3,9), (2,4)}.  (solve_qp's [G|h] row normalisation is applied by the caller, diff_cbf_qp.py:103-106.) */
 int rcbf_qp_solve(const double* Q /* n*nz*nz */, const double* p /* n*nz */, const double* G /* n*m*nz */,
                   const double* h /* n*m */, int64_t n, int nz, int m, double* x /* n*nz */, double* lam /* n*m */,
                   double* slack /* n*m */, int32_t* status, int32_t* iters, rcbf_counters_t* counters, void* stream);
@@ -198,7 +221,11 @@ int rcbf_cars_safe_action_host(const float* state_host, const float* action_host
                                int device, int chunks);
 
 /* fused step with HOST inputs/outputs: the env state (state4/state, t, step) stays on the DEVICE, the per-step inputs
- * (u_rl, GP mean/std) come from host arrays and every per-step output goes back to host arrays.  Same pipeline. */
+ * (u_rl, GP mean/std) come from host arrays and the per-step outputs go back to host arrays.  Same pipeline.
+ * Every *_host OUTPUT pointer is nullable: an output the caller does not need on the host is not copied back (a caller
+ * that only wants safe_action / reward / done / cost moves 17 instead of 46 bytes per instance over PCIe).
+ * The library keeps its streams, staging buffers and workspaces per device; the entry points are thread safe
+ * (serialised by one lock). */
 int rcbf_unicycle_safe_step_host(float* state4, int32_t* step, const float* action_host, const float* mean_host,
                                  const float* sigma_host, int64_t n, const rcbf_unicycle_params* p_host,
                                  const rcbf_unicycle_env_params* e_host, float* safe_action_host, float* obs_host,
@@ -257,6 +284,17 @@ int rcbf_gp_predict_f32(const float* test_x, int64_t n_test, const rcbf_gp_poste
                         float* std, void* stream);
 int rcbf_gp_predict_f64(const double* test_x, int64_t n_test, const rcbf_gp_posterior* post_host, double* mean,
                         double* std, void* stream);
+
+/* fused step with the disturbance GP evaluated ON THE DEVICE from the resident state (what RCBF_SAC.get_safe_action does
+ * logically, rcbf_sac/sac_cbf.py:230-236: predict_disturbance(state) -> get_safe_action): per slice the posterior
+ * kernel reads the float4 state in place (test_stride = 4) and its mean / std feed the fused step without ever leaving
+ * the GPU, so the only host input is the nominal action (8 bytes per instance).  post_host->n_in and n_gp must be 3.
+ * Output pointers are nullable as above. */
+int rcbf_unicycle_safe_step_host_gp(float* state4, int32_t* step, const float* action_host,
+                                    const rcbf_gp_posterior* post_host, int64_t n, const rcbf_unicycle_params* p_host,
+                                    const rcbf_unicycle_env_params* e_host, float* safe_action_host, float* obs_host,
+                                    float* reward_host, uint8_t* done_host, float* cost_host, uint8_t* goal_met_host,
+                                    int32_t* n_failed_host, int device, int chunks);
 
 /* ---- measurement helpers --------------------------------------------------------------------------------------
  * FP32 FMA throughput probe: `iters` dependent-chain FMAs x 8 chains per thread; returns nothing, time it outside.

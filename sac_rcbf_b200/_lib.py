@@ -26,6 +26,11 @@ SIGNATURES = {
     "rcbf_unicycle_safe_action_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp,
                                       _vp],
     "rcbf_cars_safe_action_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, _vp],
+    "rcbf_unicycle_safe_action_saved": [_vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp, _vp, _vp, _vp],
+    "rcbf_cars_safe_action_saved": [_vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, _vp, _vp, _vp],
+    "rcbf_unicycle_safe_action_bwd_meta": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp, _vp,
+                                           _vp],
+    "rcbf_cars_safe_action_bwd_meta": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, _vp, _vp],
     "rcbf_qp_solve": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rcbf_qp_solve_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp],
     "rcbf_unicycle_safe_step": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams),
@@ -39,6 +44,9 @@ SIGNATURES = {
     "rcbf_unicycle_safe_step_host": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams),
                                      C.POINTER(P.UnicycleEnvParams), _vp, _vp, _vp, _vp, _vp, _vp,
                                      C.POINTER(C.c_int32), C.c_int, C.c_int],
+    "rcbf_unicycle_safe_step_host_gp": [_vp, _vp, _vp, C.POINTER(P.GpPosterior), _i64, C.POINTER(P.UnicycleParams),
+                                        C.POINTER(P.UnicycleEnvParams), _vp, _vp, _vp, _vp, _vp, _vp,
+                                        C.POINTER(C.c_int32), C.c_int, C.c_int],
     "rcbf_cars_safe_step_host": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), C.POINTER(P.CarsEnvParams),
                                  _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.c_int, C.c_int],
     "rcbf_fp32_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],

@@ -162,7 +162,9 @@ struct LnpSolution {
   T s[M];
   int status;
   int iters;
+  uint32_t mask;  // active set of a certified solution (0: trivial); kMaskUnknown when the point is not a vertex guess
 };
+constexpr uint32_t kMaskUnknown = 0xffffu;
 
 // --- tiny SPD solves (closed-form Cholesky), NZ in {1,2,3} -------------------------------------------
 template <typename T>
@@ -334,146 +336,6 @@ RCBF_HD void greedy_solve_rows(const float R[NZ][NZ], const float rbg[NZ], float
   }
 }
 
-// --- greedy dual active-set presolve -----------------------------------------------------------------------
-// Starting from y = 0 (the unconstrained optimum), repeatedly add the most violated row (violation measured in
-// units of the row norm) and re-solve the equality-constrained least-norm problem on the chosen rows, at most NZ
-// times.  This is Goldfarb-Idnani without constraint dropping: it stops with `false` as soon as a multiplier turns
-// negative (a drop would be needed) or NZ rows do not make the point feasible -- those instances go to the
-// interior-point solver.  The returned mask is only a GUESS; the float64 certificate decides.
-template <typename Pat, int NZ, int M>
-RCBF_HD bool lnp_greedy_active_set(const float Gn[M][NZ], const float hn[M], const float pis[NZ], float Rg[NZ][NZ],
-                                   float rbg[NZ], uint32_t& mask_out, int& rounds) {
-  // scaled problem A = G~ P^-1/2 and the reciprocal row norms (violations are compared in units of |a_i|)
-  float A[M][NZ], inv_norm[M];
-  RCBF_UNROLL
-  for (int i = 0; i < M; ++i) {
-    float acc = 0.f;
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) {
-      A[i][j] = Pat::nz(i, j) ? Gn[i][j] * pis[j] : 0.f;
-      if (Pat::nz(i, j)) acc = fmaf(A[i][j], A[i][j], acc);
-    }
-    inv_norm[i] = t_rsqrt(acc);
-  }
-  float y[NZ], R[NZ][NZ];
-  RCBF_UNROLL
-  for (int j = 0; j < NZ; ++j) {
-    y[j] = 0.f;
-    rbg[j] = 0.f;
-    RCBF_UNROLL
-    for (int k = 0; k < NZ; ++k) {
-      R[j][k] = 0.f;
-      Rg[j][k] = 0.f;
-    }
-  }
-  uint32_t mask = 0;
-  bool ok = true, feasible = false;
-  int r = 0;
-  RCBF_UNROLL
-  for (; r <= NZ; ++r) {
-    // most violated row at the current y
-    float worst = -1e-6f;
-    int wi = -1;
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      float acc = hn[i];
-      if (r > 0) {  // (round 0 starts from y = 0: the products are exact zeros)
-        RCBF_UNROLL
-        for (int j = 0; j < NZ; ++j)
-          if (Pat::nz(i, j)) acc = fmaf(-A[i][j], y[j], acc);
-      }
-      const float v = acc * inv_norm[i];
-      const bool take = !((mask >> i) & 1u) && (v < worst);
-      worst = take ? v : worst;
-      wi = take ? i : wi;
-    }
-    if (wi < 0) {
-      feasible = true;
-      break;
-    }
-    if (r == NZ) break;  // NZ rows and still infeasible
-    mask |= 1u << wi;
-    // gather the UNSCALED row (the float64 certificate rebuilds its data from it) and scale the NZ entries
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      const bool put = (i == wi);
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) Rg[r][j] = put ? (Pat::nz(i, j) ? Gn[i][j] : 0.f) : Rg[r][j];
-      rbg[r] = put ? hn[i] : rbg[r];
-    }
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) R[r][j] = Rg[r][j] * pis[j];
-    // (R R') lam = -rb on the first r+1 rows (r is a compile-time constant once the loop is unrolled)
-    float lk[NZ];
-    if (r == 0) greedy_solve_rows<NZ, 1>(R, rbg, lk);
-    else if (r == 1 || NZ == 2) greedy_solve_rows<NZ, (NZ < 2 ? NZ : 2)>(R, rbg, lk);
-    else greedy_solve_rows<NZ, NZ>(R, rbg, lk);
-    RCBF_UNROLL
-    for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -1e-6f);  // NaN (dependent rows) -> false
-    if (!ok) break;
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) {
-      float acc = 0.f;
-      RCBF_UNROLL
-      for (int k = 0; k < NZ; ++k)
-        if (k <= r) acc = fmaf(-R[k][j], lk[k], acc);  // (rows beyond r are zero and carry lam = 0)
-      y[j] = acc;
-    }
-  }
-  mask_out = mask;
-  rounds = r;
-  return ok && feasible;
-}
-
-// float64 KKT certificate on rows that are ALREADY gathered (Rg, rbg from the presolve; slot k <-> k-th set bit of
-// `mask` in selection order is irrelevant to the test).  Returns y and the compact multipliers lk.
-template <typename Pat, int NZ, int M>
-RCBF_HD bool lnp_certify_rows(const float Gn[M][NZ], const float hn[M], const double pis[NZ], const float Rg[NZ][NZ],
-                              const float rbg[NZ], int cnt, uint32_t mask, double tol_s, double tol_l, double y[NZ],
-                              double lk[NZ]) {
-  double R[NZ][NZ], Gm[NZ][NZ], nrb[NZ];
-  RCBF_UNROLL
-  for (int k = 0; k < NZ; ++k) {
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) R[k][j] = (double)Rg[k][j] * pis[j];
-    nrb[k] = -(double)rbg[k];
-  }
-  RCBF_UNROLL
-  for (int k = 0; k < NZ; ++k) {
-    RCBF_UNROLL
-    for (int l = 0; l <= k; ++l) {
-      double acc = 0.0;
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j) acc = fma(R[k][j], R[l][j], acc);
-      Gm[k][l] = acc;
-    }
-    Gm[k][k] = (k < cnt) ? Gm[k][k] : 1.0;
-  }
-  Chol<double, NZ> ch;
-  ch.factor(Gm);
-  ch.solve(nrb, lk);
-  bool ok = true;
-  RCBF_UNROLL
-  for (int k = 0; k < NZ; ++k) ok = ok && (lk[k] >= -tol_l);
-  RCBF_UNROLL
-  for (int j = 0; j < NZ; ++j) {
-    double acc = 0.0;
-    RCBF_UNROLL
-    for (int k = 0; k < NZ; ++k) acc = fma(-R[k][j], lk[k], acc);
-    y[j] = acc;
-  }
-  RCBF_UNROLL
-  for (int i = 0; i < M; ++i) {
-    double acc = (double)hn[i];
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j)
-      if (Pat::nz(i, j)) acc = fma(-((double)Gn[i][j] * pis[j]), y[j], acc);
-    const bool act = (mask >> i) & 1u;
-    ok = ok && (acc >= -tol_s) && (!act || acc <= tol_s);
-  }
-  return ok;
-}
-
 // multipliers / slacks in dense form, only when a caller wants them saved (backward pass, diagnostics)
 template <typename Pat, int NZ, int M>
 RCBF_HD void lnp_expand_aux(const float Gn[M][NZ], const float hn[M], const double pis[NZ], const float Rg[NZ][NZ],
@@ -541,6 +403,7 @@ RCBF_HD int ipm_finish_best(const IpmState<T, NZ, M>& st, LnpSolution<C, NZ, M>&
   }
   out.status = (st.best_res < T(1e30)) ? status : RCBF_NAN;
   out.iters = st.it;
+  out.mask = kMaskUnknown;
   return out.status;
 }
 
@@ -649,6 +512,7 @@ RCBF_HD int ipm_step(const LnpProblem<T, NZ, M>& P, const CP& cp, IpmState<T, NZ
     if (lnp_certify<C, CP, Pat, NZ, M>(cp, mask, tol_s, tol_l, out.y, out.lam, out.s)) {
       out.status = RCBF_OK_CERTIFIED;
       out.iters = st.it;
+      out.mask = mask;
       return RCBF_OK_CERTIFIED;
     }
   }
@@ -775,6 +639,7 @@ RCBF_HD void lnp_solve(const LnpProblem<T, NZ, M>& P, const CP& cp, LnpSolution<
       }
       out.status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
       out.iters = 0;
+      out.mask = 0u;
       return;
     }
   }
@@ -1034,6 +899,7 @@ template <int NZ, int M>
 struct NormSolution {
   double x[NZ], lam[M], s[M];
   int status, iters;
+  uint32_t mask;  // active set the certificate accepted (0: trivial; kMaskUnknown: interior-point iterate)
 };
 
 template <int NZ, int M>
@@ -1045,71 +911,29 @@ RCBF_HD void pis_of(const float p_diag[NZ], double pisd[NZ], float pisf[NZ]) {
   }
 }
 
-// Fast path of one normalised QP: trivial test, greedy active-set presolve (float32) and the float64 KKT
-// certificate.  kPresolve = false skips the presolve and runs the float32 interior point inline instead
-// ("pdipm" solver mode).  Leaves status = RCBF_PENDING when it cannot certify: the fallback pass takes over.
-template <typename Pat, int NZ, int M, bool kPresolve>
-RCBF_HD void solve_normalised_fast(const Normalised<NZ, M>& nrm, const float p_diag[NZ], bool want_aux,
-                                   NormSolution<NZ, M>& o) {
+// Fast path of one normalised QP in "pdipm" solver mode: the float32 interior point with the float64 KKT certificate
+// tried on its active-set prediction.  Leaves status = RCBF_PENDING when it cannot certify: the fallback pass takes
+// over.  (Presolve mode: solve_raw_fast below.)
+template <typename Pat, int NZ, int M>
+RCBF_HD void solve_normalised_ipm(const Normalised<NZ, M>& nrm, const float p_diag[NZ], NormSolution<NZ, M>& o) {
   double pisd[NZ];
   float pisf[NZ];
   pis_of<NZ, M>(p_diag, pisd, pisf);
-  double y[NZ];
-  if (kPresolve) {
-    uint32_t mask;
-    int rounds;
-    float Rg[NZ][NZ], rbg[NZ];
-    const bool guess = lnp_greedy_active_set<Pat, NZ, M>(nrm.Gn, nrm.hn, pisf, Rg, rbg, mask, rounds);
-    o.status = RCBF_PENDING;
-    o.iters = rounds;
-    double lk[NZ];
-    if (guess && lnp_certify_rows<Pat, NZ, M>(nrm.Gn, nrm.hn, pisd, Rg, rbg, rounds, mask, kTolSlack, kTolDual, y, lk)) {
-      o.status = RCBF_OK_CERTIFIED;
-      if (want_aux) lnp_expand_aux<Pat, NZ, M>(nrm.Gn, nrm.hn, pisd, Rg, rbg, mask, y, lk, o.lam, o.s);
-    }
-    if (M <= 4 && o.status == RCBF_PENDING) {
-      // Few rows (SimulatedCars: 10 candidate active sets): when the greedy guess is not certified, enumerate right
-      // here with the same float64 certificate instead of queueing for pass 2 (about 1 instance in 1000).
-      const NormCert<NZ, M> cp{nrm, pisd};
-      double lam[M], sl[M];
-#ifdef __CUDA_ARCH__
-#pragma unroll 1
-#endif
-      for (uint32_t m = 1; m < (1u << M); ++m) {
-        int pc = 0;
-        RCBF_UNROLL
-        for (int i = 0; i < M; ++i) pc += (m >> i) & 1u;
-        if (pc > NZ) continue;
-        if (lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, m, kTolSlack, kTolDual, y, lam, sl)) {
-          o.status = RCBF_OK_CERTIFIED;
-          o.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
-          RCBF_UNROLL
-          for (int i = 0; i < M; ++i) {
-            o.lam[i] = lam[i];
-            o.s[i] = sl[i];
-          }
-          break;
-        }
-      }
-    }
-  } else {
-    const NormCert<NZ, M> cp{nrm, pisd};
-    LnpProblem<float, NZ, M> Pf;
-    to_lnp<float, Pat, NZ, M>(nrm, pisf, Pf);
-    LnpSolution<double, NZ, M> sol;
-    lnp_solve<float, double, NormCert<NZ, M>, Pat, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
-    o.status = (sol.status >= RCBF_MAXITER) ? RCBF_PENDING : sol.status;
-    o.iters = sol.iters;
-    RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) y[j] = sol.y[j];
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      o.lam[i] = sol.lam[i];
-      o.s[i] = sol.s[i];
-    }
+  const NormCert<NZ, M> cp{nrm, pisd};
+  LnpProblem<float, NZ, M> Pf;
+  to_lnp<float, Pat, NZ, M>(nrm, pisf, Pf);
+  LnpSolution<double, NZ, M> sol;
+  lnp_solve<float, double, NormCert<NZ, M>, Pat, NZ, M>(Pf, cp, sol, kTolSlack, kTolDual);
+  o.status = (sol.status >= RCBF_MAXITER) ? RCBF_PENDING : sol.status;
+  o.iters = sol.iters;
+  o.mask = sol.mask;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    o.lam[i] = sol.lam[i];
+    o.s[i] = sol.s[i];
   }
   RCBF_UNROLL
-  for (int j = 0; j < NZ; ++j) o.x[j] = y[j] * pisd[j];
+  for (int j = 0; j < NZ; ++j) o.x[j] = sol.y[j] * pisd[j];
 }
 
 // ---- presolve on the rows AS ASSEMBLED ---------------------------------------------------------------------------
@@ -1141,6 +965,13 @@ RCBF_HD int key_index(float k) {
 }
 RCBF_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }  // NaN operands are ignored
 
+// --- greedy dual active-set presolve -----------------------------------------------------------------------
+// Starting from y = 0 (the unconstrained optimum), repeatedly add the most violated row (violation measured in
+// units of the row norm) and re-solve the equality-constrained least-norm problem on the chosen rows, at most NZ
+// times.  This is Goldfarb-Idnani without constraint dropping: it stops with `false` as soon as a multiplier turns
+// negative (a drop would be needed) or NZ rows do not make the point feasible -- those instances go to the
+// interior-point solver.  The returned mask is only a GUESS; the float64 certificate decides.
+// (Rows are scored as assembled, see above; a row that entered the active set is never picked again.)
 template <typename Pat, int NZ, int M>
 RCBF_HD bool lnp_greedy_raw(const float G[M][NZ], const float h[M], const float pis[NZ], float A[M][NZ],
                             float Rg[NZ][NZ], float rbg[NZ], uint32_t& mask_out, int& rounds) {
@@ -1363,6 +1194,7 @@ RCBF_HD void solve_raw_fast(const float G[M][NZ], const float h[M], const float 
   const bool guess = lnp_greedy_raw<Pat, NZ, M>(G, h, pisf, A, Rg, rbg, mask, rounds);
   o.status = RCBF_PENDING;
   o.iters = rounds;
+  o.mask = mask;
   RCBF_UNROLL
   for (int j = 0; j < NZ; ++j) y[j] = 0.0;
   if (guess && lnp_certify_raw<Pat, NZ, M>(G, h, A, pisd, Rg, rbg, rounds, mask, kTolSlack, kTolDual, y, lk)) {
@@ -1391,6 +1223,7 @@ RCBF_HD void solve_raw_fast(const float G[M][NZ], const float h[M], const float 
       if (lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, m, kTolSlack, kTolDual, y, lam, sl)) {
         o.status = RCBF_OK_CERTIFIED;
         o.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
+        o.mask = m;
         RCBF_UNROLL
         for (int i = 0; i < M; ++i) {
           o.lam[i] = lam[i];
@@ -1478,6 +1311,7 @@ RCBF_HD void solve_normalised_full(const Normalised<NZ, M>& nrm, const float p_d
   }
   o.status = sol.status;
   o.iters = sol.iters;
+  o.mask = sol.mask;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1503,6 +1337,7 @@ RCBF_HD void trivial_solution(const Normalised<NZ, M>& nrm, bool nan, NormSoluti
   }
   o.status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
   o.iters = 0;
+  o.mask = 0u;
 }
 
 // kMode: 0 = fast path with presolve, 1 = fast path with inline float32 IPM ("pdipm" mode), 2 = fallback pass,
@@ -1522,7 +1357,7 @@ RCBF_HD void unicycle_safe_action(const UnicycleParams& p, const float st[3], co
     trivial_solution<UniPat, kUniNZ, kUniM>(w.nrm, nan, w.sol);
   } else {
     if (kMode == 0) solve_raw_fast<UniPat, kUniNZ, kUniM>(w.raw.G, w.raw.h, p.p_diag, true, w.sol);
-    if (kMode == 1) solve_normalised_fast<UniPat, kUniNZ, kUniM, false>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode == 1) solve_normalised_ipm<UniPat, kUniNZ, kUniM>(w.nrm, p.p_diag, w.sol);
     if (kMode >= 2) solve_normalised_full<UniPat, kUniNZ, kUniM>(w.nrm, p.p_diag, kMode == 3, w.sol);
   }
   RCBF_UNROLL
@@ -1547,7 +1382,7 @@ RCBF_HD void cars_safe_action(const CarsParams& p, const float st[10], float u, 
     trivial_solution<CarsPat, kCarsNZ, kCarsM>(w.nrm, nan, w.sol);
   } else {
     if (kMode == 0) solve_raw_fast<CarsPat, kCarsNZ, kCarsM>(w.raw.G, w.raw.h, p.p_diag, true, w.sol);
-    if (kMode == 1) solve_normalised_fast<CarsPat, kCarsNZ, kCarsM, false>(w.nrm, p.p_diag, true, w.sol);
+    if (kMode == 1) solve_normalised_ipm<CarsPat, kCarsNZ, kCarsM>(w.nrm, p.p_diag, w.sol);
     if (kMode >= 2) solve_normalised_full<CarsPat, kCarsNZ, kCarsM>(w.nrm, p.p_diag, kMode == 3, w.sol);
   }
   *u_safe = clampf(u + (float)w.sol.x[0], p.u_min, p.u_max);  // :77

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "rcbf_backward.cuh"
 #include "rcbf_core.cuh"
 #include "rcbf_dynamics.cuh"
@@ -20,6 +22,14 @@ namespace {
 constexpr int kThreads = 128;
 
 inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
+inline int sm_count() {  // SMs of the current device (cached per device)
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c > 0 ? c : 148;
+}
 #define RCBF_LAUNCH_CHECK()                 \
   do {                                      \
     cudaError_t e_ = cudaGetLastError();    \
@@ -204,6 +214,212 @@ k_cars_safe_action_bwd(const float* __restrict__ st, const float* __restrict__ a
   const float uu[1] = {u}, lo[1] = {p.u_min}, hi[1] = {p.u_max}, gg[1] = {go};
   safe_action_bwd<kCarsNZ, kCarsM, 1>(nrm, raw.G, raw.h, r, p.p_diag, xs, ls, ss, uu, lo, hi, gg, ga);
   grad_a[i] = ga[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4, compact form: the forward saved ONE word per instance, (status << 16) | active set.  A trivial instance
+// (x = 0, no active row: ~2/3 of them) needs nothing but the clamp mask of diff_cbf_qp.py:77 -- 28 bytes of traffic,
+// a handful of instructions.  The others are compacted inside the block (so that the float64 part runs with full
+// warps), re-assembled, their multipliers / slacks rebuilt from the active set by the same float64 solve the
+// certificate ran, and pushed through the implicit-KKT backward (rcbf_backward.cuh).
+// (For a trivial instance qpth's clamped ratios d_i = 1e-8 / s_i also leak O(1e-8 / s_i) of the gradient through the
+// inactive rows; that term is dropped here.)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kBwdThreads = 128;
+
+template <typename Pat, int NZ, int M>
+__device__ __forceinline__ void rebuild_saved(const Normalised<NZ, M>& nrm, const float p_diag[NZ], int meta,
+                                              float xs[NZ], float ls[M], float ss[M]) {
+  const int status = meta >> 16;
+  const uint32_t mask = (uint32_t)meta & 0xffffu;
+  double pisd[NZ];
+  float pisf[NZ];
+  pis_of<NZ, M>(p_diag, pisd, pisf);
+  if (mask != kMaskUnknown && status == RCBF_OK_CERTIFIED) {
+    const NormCert<NZ, M> cp{nrm, pisd};
+    double y[NZ], lam[M], sl[M];
+    lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, mask, kTolSlack, kTolDual, y, lam, sl);
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) xs[j] = (float)(y[j] * pisd[j]);
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      ls[i] = (float)lam[i];
+      ss[i] = (float)sl[i];
+    }
+  } else {  // interior-point result (no vertex to rebuild from): redo the fallback solve -- practically never taken
+    NormSolution<NZ, M> sol;
+    solve_normalised_full<Pat, NZ, M>(nrm, p_diag, false, sol);
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) xs[j] = (float)sol.x[j];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      ls[i] = (float)sol.lam[i];
+      ss[i] = (float)sol.s[i];
+    }
+  }
+}
+
+// phase 1 of both kernels: trivial / NaN instances are finished, the others are listed (dense) in shared memory
+template <int NU>
+__device__ __forceinline__ int bwd_classify(const float* __restrict__ ac, const int32_t* __restrict__ meta,
+                                            const float* __restrict__ gout, int64_t n, const float* u_min,
+                                            const float* u_max, float* __restrict__ grad_a, int* list) {
+  __shared__ int s_count;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;
+  bool heavy = false;
+  if (i < n) {
+    const int status = __ldg(meta + i) >> 16;
+    if (status == RCBF_OK_TRIVIAL || status == RCBF_NAN) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const float v = __ldg(ac + i * NU + c) + 0.f;
+        const float g = __ldg(gout + i * NU + c);
+        grad_a[i * NU + c] = (status == RCBF_NAN) ? NAN : ((v >= u_min[c] && v <= u_max[c]) ? g : 0.f);
+      }
+    } else {
+      heavy = true;
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, heavy);
+  int base = 0;
+  if ((threadIdx.x & 31) == 0 && b) base = atomicAdd(&s_count, __popc(b));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (heavy) list[base + __popc(b & ((1u << (threadIdx.x & 31)) - 1u))] = threadIdx.x;
+  __syncthreads();
+  return s_count;
+}
+
+__device__ __forceinline__ void unicycle_bwd_heavy(const float* __restrict__ st, const float* __restrict__ ac,
+                                                   const float* __restrict__ mu, const float* __restrict__ sg,
+                                                   const int32_t* __restrict__ meta, const float* __restrict__ gout,
+                                                   int64_t i, const UnicycleParams& p, float* __restrict__ grad_a) {
+  float s[3], u[2], m[3], g[3], xs[3], ls[kUniM], ss[kUniM], go[2];
+  load_row<3>(st, i, s);
+  load_row<2>(ac, i, u);
+  load_row<3>(mu, i, m);
+  load_row<3>(sg, i, g);
+  load_row<2>(gout, i, go);
+  UniRaw raw;
+  assemble_unicycle(p, s, u, m, g, raw);
+  Normalised<kUniNZ, kUniM> nrm;
+  normalise_rows<UniPat, kUniNZ, kUniM>(raw.G, raw.h, nrm);
+  rebuild_saved<UniPat, kUniNZ, kUniM>(nrm, p.p_diag, __ldg(meta + i), xs, ls, ss);
+  float r[kUniM][2];
+#pragma unroll
+  for (int k = 0; k < kUniHaz; ++k) {
+    r[k][0] = raw.Lg[k][0];
+    r[k][1] = raw.Lg[k][1];
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {  // h = u_max - a_c ; h = -u_min + a_c
+    r[kUniHaz + 2 * c][0] = (c == 0) ? -1.f : 0.f;
+    r[kUniHaz + 2 * c][1] = (c == 1) ? -1.f : 0.f;
+    r[kUniHaz + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f;
+    r[kUniHaz + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
+  }
+  float ga[2];
+  safe_action_bwd<kUniNZ, kUniM, 2>(nrm, raw.G, raw.h, r, p.p_diag, xs, ls, ss, u, p.u_min, p.u_max, go, ga);
+  store_row<2>(grad_a, i, ga);
+}
+
+// one launch (small batches): the block's own non-trivial instances, compacted to its first threads
+__global__ void __launch_bounds__(kBwdThreads)
+k_unicycle_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
+                                const float* __restrict__ sg, const int32_t* __restrict__ meta,
+                                const float* __restrict__ gout, int64_t n, UnicycleParams p, float* __restrict__ grad_a) {
+  __shared__ int list[kBwdThreads];
+  const int count = bwd_classify<2>(ac, meta, gout, n, p.u_min, p.u_max, grad_a, list);
+  if ((int)threadIdx.x >= count) return;
+  unicycle_bwd_heavy(st, ac, mu, sg, meta, gout, (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x], p, grad_a);
+}
+
+// two launches (large batches): k_bwd_classify lists the non-trivial instances of the WHOLE batch in global memory
+// (one atomic per block), this kernel walks the list with full blocks
+__global__ void __launch_bounds__(kBwdThreads)
+k_unicycle_safe_action_bwd_list(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
+                                const float* __restrict__ sg, const int32_t* __restrict__ meta,
+                                const float* __restrict__ gout, UnicycleParams p, float* __restrict__ grad_a,
+                                const int32_t* __restrict__ list /* [0] = count, entries from [4] */) {
+  const int count = list[0];
+  for (int k = blockIdx.x * kBwdThreads + threadIdx.x; k < count; k += gridDim.x * kBwdThreads)
+    unicycle_bwd_heavy(st, ac, mu, sg, meta, gout, (int64_t)list[4 + k], p, grad_a);
+}
+
+__device__ __forceinline__ void cars_bwd_heavy(const float* __restrict__ st, const float* __restrict__ ac,
+                                               const float* __restrict__ sg, const int32_t* __restrict__ meta,
+                                               const float* __restrict__ gout, int64_t i, const CarsParams& p,
+                                               float* __restrict__ grad_a) {
+  float s[10], g[10], xs[2], ls[kCarsM], ss[kCarsM];
+  load_row<10>(st, i, s);
+  load_row<10>(sg, i, g);
+  const float u = __ldg(ac + i);
+  const float go = __ldg(gout + i);
+  CarsRaw raw;
+  assemble_cars(p, s, u, g, raw);
+  Normalised<kCarsNZ, kCarsM> nrm;
+  normalise_rows<CarsPat, kCarsNZ, kCarsM>(raw.G, raw.h, nrm);
+  rebuild_saved<CarsPat, kCarsNZ, kCarsM>(nrm, p.p_diag, __ldg(meta + i), xs, ls, ss);
+  float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
+  float ga[1];
+  const float uu[1] = {u}, gg[1] = {go}, lo[1] = {p.u_min}, hi[1] = {p.u_max};
+  safe_action_bwd<kCarsNZ, kCarsM, 1>(nrm, raw.G, raw.h, r, p.p_diag, xs, ls, ss, uu, lo, hi, gg, ga);
+  grad_a[i] = ga[0];
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
+k_cars_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg,
+                            const int32_t* __restrict__ meta, const float* __restrict__ gout, int64_t n, CarsParams p,
+                            float* __restrict__ grad_a) {
+  __shared__ int list[kBwdThreads];
+  const float lo[1] = {p.u_min}, hi[1] = {p.u_max};
+  const int count = bwd_classify<1>(ac, meta, gout, n, lo, hi, grad_a, list);
+  if ((int)threadIdx.x >= count) return;
+  cars_bwd_heavy(st, ac, sg, meta, gout, (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x], p, grad_a);
+}
+
+__global__ void __launch_bounds__(kBwdThreads)
+k_cars_safe_action_bwd_list(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg,
+                            const int32_t* __restrict__ meta, const float* __restrict__ gout, CarsParams p,
+                            float* __restrict__ grad_a, const int32_t* __restrict__ list) {
+  const int count = list[0];
+  for (int k = blockIdx.x * kBwdThreads + threadIdx.x; k < count; k += gridDim.x * kBwdThreads)
+    cars_bwd_heavy(st, ac, sg, meta, gout, (int64_t)list[4 + k], p, grad_a);
+}
+
+// phase 1 of the two-launch form: clamp-mask gradients of the trivial instances, global list of the others
+template <int NU>
+__global__ void __launch_bounds__(256)
+k_bwd_classify(const float* __restrict__ ac, const int32_t* __restrict__ meta, const float* __restrict__ gout, int64_t n,
+               float lo0, float hi0, float lo1, float hi1, float* __restrict__ grad_a, int32_t* __restrict__ list) {
+  __shared__ int s_count, s_base;
+  if (threadIdx.x == 0) s_count = 0;
+  __syncthreads();
+  const float u_min[2] = {lo0, lo1}, u_max[2] = {hi0, hi1};
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  bool heavy = false;
+  if (i < n) {
+    const int status = __ldg(meta + i) >> 16;
+    if (status == RCBF_OK_TRIVIAL || status == RCBF_NAN) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const float v = __ldg(ac + i * NU + c) + 0.f;
+        const float g = __ldg(gout + i * NU + c);
+        grad_a[i * NU + c] = (status == RCBF_NAN) ? NAN : ((v >= u_min[c] && v <= u_max[c]) ? g : 0.f);
+      }
+    } else {
+      heavy = true;
+    }
+  }
+  const unsigned b = __ballot_sync(0xffffffffu, heavy);
+  int base = 0;
+  if ((threadIdx.x & 31) == 0 && b) base = atomicAdd(&s_count, __popc(b));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) s_base = s_count ? atomicAdd(list, s_count) : 0;
+  __syncthreads();
+  if (heavy) list[4 + s_base + base + __popc(b & ((1u << (threadIdx.x & 31)) - 1u))] = (int32_t)i;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -534,6 +750,47 @@ int rcbf_cars_safe_action_bwd(const float* state, const float* action, const flo
   return 0;
 }
 
+constexpr int64_t kBwdTwoLaunchMin = 32768;  // below this the single launch wins (one launch less, blocks few anyway)
+
+int rcbf_unicycle_safe_action_bwd_meta(const float* state, const float* action, const float* mean, const float* sigma,
+                                       const int32_t* meta, const float* grad_out, int64_t n,
+                                       const rcbf_unicycle_params* p, float* grad_action, int32_t* scratch,
+                                       void* stream) {
+  if (n <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (scratch == nullptr || n < kBwdTwoLaunchMin || n > 0x7fffffffLL) {
+    k_unicycle_safe_action_bwd_meta<<<(int)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, s>>>(
+        state, action, mean, sigma, meta, grad_out, n, *p, grad_action);
+  } else {
+    cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), s);
+    k_bwd_classify<2><<<(int)((n + 255) / 256), 256, 0, s>>>(action, meta, grad_out, n, p->u_min[0], p->u_max[0],
+                                                            p->u_min[1], p->u_max[1], grad_action, scratch);
+    k_unicycle_safe_action_bwd_list<<<sm_count() * 4, kBwdThreads, 0, s>>>(state, action, mean, sigma, meta, grad_out, *p,
+                                                                           grad_action, scratch);
+  }
+  RCBF_LAUNCH_CHECK();
+  return 0;
+}
+
+int rcbf_cars_safe_action_bwd_meta(const float* state, const float* action, const float* sigma, const int32_t* meta,
+                                   const float* grad_out, int64_t n, const rcbf_cars_params* p, float* grad_action,
+                                   int32_t* scratch, void* stream) {
+  if (n <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (scratch == nullptr || n < kBwdTwoLaunchMin || n > 0x7fffffffLL) {
+    k_cars_safe_action_bwd_meta<<<(int)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, s>>>(
+        state, action, sigma, meta, grad_out, n, *p, grad_action);
+  } else {
+    cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), s);
+    k_bwd_classify<1><<<(int)((n + 255) / 256), 256, 0, s>>>(action, meta, grad_out, n, p->u_min, p->u_max, 0.f, 0.f,
+                                                            grad_action, scratch);
+    k_cars_safe_action_bwd_list<<<sm_count() * 4, kBwdThreads, 0, s>>>(state, action, sigma, meta, grad_out, *p,
+                                                                       grad_action, scratch);
+  }
+  RCBF_LAUNCH_CHECK();
+  return 0;
+}
+
 int rcbf_qp_solve(const double* Q, const double* p, const double* G, const double* h, int64_t n, int nz, int m,
                   double* x, double* lam, double* slack, int32_t* status, int32_t* iters, rcbf_counters_t* counters,
                   void* stream) {
@@ -654,126 +911,107 @@ int rcbf_fp32_fma_probe(float* sink, int blocks, int threads, int iters, void* s
 }  // extern "C"
 
 namespace {
+// Host-buffer pipelines.  State is kept PER DEVICE (streams, staging scratch and solver workspaces belong to the device
+// they were created on) and every entry point holds one process-wide lock: two Python threads may call the *_host
+// functions concurrently, they are simply serialised.
 struct HostPipe {
-  int device = -1;
+  bool ready = false;
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};
-  float* scratch = nullptr;
-  size_t scratch_floats = 0;
+  char* scratch = nullptr;
+  size_t scratch_bytes = 0;
   rcbf_counters_t* counters = nullptr;  // 3 workspaces of RCBF_WS_WORDS words, one per stream
-  int ensure(int dev, size_t floats) {
+  rcbf_counters_t* failed_host = nullptr;  // pinned: the 3 NaN counters come back with the last chunk, no extra sync
+  int ensure(int dev, size_t bytes) {
     cudaError_t e;
-    if (device != dev) {
-      if ((e = cudaSetDevice(dev)) != cudaSuccess) return (int)e;
+    if ((e = cudaSetDevice(dev)) != cudaSuccess) return (int)e;
+    if (!ready) {
       for (auto& s : streams)
         if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return (int)e;
-      if ((e = cudaMalloc(&counters, 3 * RCBF_WS_WORDS * sizeof(rcbf_counters_t))) != cudaSuccess) return (int)e;
-      device = dev;
+      const size_t wsb = 3 * RCBF_WS_WORDS * sizeof(rcbf_counters_t);
+      if ((e = cudaMalloc(&counters, wsb)) != cudaSuccess) return (int)e;
+      // "zero-initialised once" (rcbf_b200.h): queue bookkeeping and slots must start at zero; the kernels leave them
+      // at zero, the per-call code below only clears the 8 counter words
+      if ((e = cudaMemset(counters, 0, wsb)) != cudaSuccess) return (int)e;
+      if ((e = cudaMallocHost(&failed_host, 3 * sizeof(rcbf_counters_t))) != cudaSuccess) return (int)e;
+      ready = true;
     }
-    if (floats > scratch_floats) {
+    if (bytes > scratch_bytes) {
+      for (auto& s : streams) cudaStreamSynchronize(s);
       if (scratch) cudaFree(scratch);
-      if ((e = cudaMalloc(&scratch, floats * sizeof(float))) != cudaSuccess) return (int)e;
-      scratch_floats = floats;
+      scratch = nullptr;
+      scratch_bytes = 0;
+      if ((e = cudaMalloc(&scratch, bytes)) != cudaSuccess) return (int)e;
+      scratch_bytes = bytes;
     }
     return 0;
   }
 };
-HostPipe g_pipe;
+constexpr int kMaxDevices = 64;
+HostPipe g_pipes[kMaxDevices];
+std::mutex g_pipe_mutex;
 
+// Generic pipeline: `n_in` HOST input arrays, `n_tmp` device-only intermediates and `n_out` output arrays of the given
+// BYTE widths per instance.  An output whose host pointer is NULL is still produced on the device (the kernels write
+// every array) but is not copied back.  launch(dev_in[], dev_tmp[], dev_out[], lo, cnt, ws, stream) enqueues the work
+// of one slice.  Slices are multiples of 64 instances (tiles of the two-per-lane kernel, 16-byte aligned arrays).
 template <typename LaunchFn>
-int run_host_pipe(const float* const* in_host, const int* in_width, int n_in, float* out_host, int out_width, int64_t n,
-                  int device, int chunks, int32_t* n_failed_host, LaunchFn launch) {
-  if (n <= 0) return 0;
-  int tot_w = out_width;
-  for (int k = 0; k < n_in; ++k) tot_w += in_width[k];
-  int rc = g_pipe.ensure(device, (size_t)n * tot_w);
-  if (rc) return rc;
-  cudaSetDevice(device);
-  if (chunks < 1) chunks = 1;
-  cudaMemsetAsync(g_pipe.counters, 0, 3 * RCBF_WS_WORDS * sizeof(rcbf_counters_t), g_pipe.streams[0]);
-  cudaStreamSynchronize(g_pipe.streams[0]);
-  float* dev_in[8];
-  float* cur = g_pipe.scratch;
-  for (int k = 0; k < n_in; ++k) {
-    dev_in[k] = cur;
-    cur += (size_t)n * in_width[k];
+int run_pipe(const void* const* in_host, const int* in_bytes, int n_in, const int* tmp_bytes, int n_tmp,
+             void* const* out_host, const int* out_bytes, int n_out, int64_t n, int device, int chunks,
+             int32_t* n_failed_host, LaunchFn launch) {
+  if (n <= 0) {
+    if (n_failed_host) *n_failed_host = 0;
+    return 0;
   }
-  float* dev_out = cur;
-  const int64_t per = (((n + chunks - 1) / chunks) + 31) & ~(int64_t)31;  // tile multiple: chunks stay 16-byte aligned
-  for (int c = 0; c < chunks; ++c) {
-    const int64_t lo = (int64_t)c * per;
-    const int64_t cnt = (lo + per <= n) ? per : (n - lo);
-    if (cnt <= 0) break;
-    cudaStream_t s = g_pipe.streams[c % 3];
-    for (int k = 0; k < n_in; ++k)
-      cudaMemcpyAsync(dev_in[k] + lo * in_width[k], in_host[k] + lo * in_width[k], cnt * in_width[k] * sizeof(float),
-                      cudaMemcpyHostToDevice, s);
-    rc = launch(dev_in, dev_out, lo, cnt, g_pipe.counters + (c % 3) * RCBF_WS_WORDS, s);
-    if (rc) return rc;
-    cudaMemcpyAsync(out_host + lo * out_width, dev_out + lo * out_width, cnt * out_width * sizeof(float),
-                    cudaMemcpyDeviceToHost, s);
-  }
-  for (auto& s : g_pipe.streams) cudaStreamSynchronize(s);
-  rcbf_counters_t nan_count = 0;
-  for (int k = 0; k < 3; ++k) {
-    rcbf_counters_t v = 0;
-    cudaError_t e = cudaMemcpy(&v, g_pipe.counters + k * RCBF_WS_WORDS, sizeof(v), cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) return (int)e;
-    nan_count += v;
-  }
-  if (n_failed_host) *n_failed_host = (int32_t)nan_count;
-  return (int)cudaGetLastError();
-}
-// fused-step pipeline: `n_in` host input arrays and `n_out` host output arrays of given BYTE widths per instance; the
-// env state stays on the device.  launch(dev_in[], dev_out[], lo, cnt, ws, stream) runs the fused kernel on a slice.
-template <typename LaunchFn>
-int run_step_pipe(const void* const* in_host, const int* in_bytes, int n_in, void* const* out_host, const int* out_bytes,
-                  int n_out, int64_t n, int device, int chunks, int32_t* n_failed_host, LaunchFn launch) {
-  if (n <= 0) return 0;
+  if (device < 0 || device >= kMaxDevices) return (int)cudaErrorInvalidDevice;
+  std::lock_guard<std::mutex> lock(g_pipe_mutex);
+  HostPipe& pp = g_pipes[device];
   size_t total = 0;
-  size_t off_in[8], off_out[8];
-  for (int k = 0; k < n_in; ++k) {
-    off_in[k] = total;
-    total += (((size_t)n * in_bytes[k]) + 255) & ~(size_t)255;
-  }
-  for (int k = 0; k < n_out; ++k) {
-    off_out[k] = total;
-    total += (((size_t)n * out_bytes[k]) + 255) & ~(size_t)255;
-  }
-  int rc = g_pipe.ensure(device, (total + 3) / 4);
+  size_t off_in[8], off_tmp[8], off_out[8];
+  auto place = [&](size_t* off, const int* w, int cnt_) {
+    for (int k = 0; k < cnt_; ++k) {
+      off[k] = total;
+      total += (((size_t)n * w[k]) + 255) & ~(size_t)255;
+    }
+  };
+  place(off_in, in_bytes, n_in);
+  place(off_tmp, tmp_bytes, n_tmp);
+  place(off_out, out_bytes, n_out);
+  int rc = pp.ensure(device, total);
   if (rc) return rc;
-  cudaSetDevice(device);
   if (chunks < 1) chunks = 1;
-  for (int k = 0; k < 3; ++k) cudaMemsetAsync(g_pipe.counters + k * RCBF_WS_WORDS, 0, 8 * sizeof(rcbf_counters_t), g_pipe.streams[k]);
-  char* base = reinterpret_cast<char*>(g_pipe.scratch);
+  for (int k = 0; k < 3; ++k)
+    cudaMemsetAsync(pp.counters + k * RCBF_WS_WORDS, 0, 8 * sizeof(rcbf_counters_t), pp.streams[k]);
   void* dev_in[8];
+  void* dev_tmp[8];
   void* dev_out[8];
-  const int64_t per = (((n + chunks - 1) / chunks) + 31) & ~(int64_t)31;
+  const int64_t per = (((n + chunks - 1) / chunks) + 63) & ~(int64_t)63;
   for (int c = 0; c < chunks; ++c) {
     const int64_t lo = (int64_t)c * per;
     const int64_t cnt = (lo + per <= n) ? per : (n - lo);
     if (cnt <= 0) break;
-    cudaStream_t s = g_pipe.streams[c % 3];
+    cudaStream_t s = pp.streams[c % 3];
     for (int k = 0; k < n_in; ++k) {
-      dev_in[k] = base + off_in[k] + (size_t)lo * in_bytes[k];
+      dev_in[k] = pp.scratch + off_in[k] + (size_t)lo * in_bytes[k];
       cudaMemcpyAsync(dev_in[k], static_cast<const char*>(in_host[k]) + (size_t)lo * in_bytes[k], (size_t)cnt * in_bytes[k],
                       cudaMemcpyHostToDevice, s);
     }
-    for (int k = 0; k < n_out; ++k) dev_out[k] = base + off_out[k] + (size_t)lo * out_bytes[k];
-    rc = launch(dev_in, dev_out, lo, cnt, g_pipe.counters + (c % 3) * RCBF_WS_WORDS, s);
+    for (int k = 0; k < n_tmp; ++k) dev_tmp[k] = pp.scratch + off_tmp[k] + (size_t)lo * tmp_bytes[k];
+    for (int k = 0; k < n_out; ++k) dev_out[k] = pp.scratch + off_out[k] + (size_t)lo * out_bytes[k];
+    rc = launch(dev_in, dev_tmp, dev_out, lo, cnt, pp.counters + (c % 3) * RCBF_WS_WORDS, s);
     if (rc) return rc;
     for (int k = 0; k < n_out; ++k)
-      cudaMemcpyAsync(static_cast<char*>(out_host[k]) + (size_t)lo * out_bytes[k], dev_out[k], (size_t)cnt * out_bytes[k],
-                      cudaMemcpyDeviceToHost, s);
+      if (out_host[k] != nullptr)
+        cudaMemcpyAsync(static_cast<char*>(out_host[k]) + (size_t)lo * out_bytes[k], dev_out[k], (size_t)cnt * out_bytes[k],
+                        cudaMemcpyDeviceToHost, s);
   }
-  for (auto& s : g_pipe.streams) cudaStreamSynchronize(s);
-  rcbf_counters_t nan_count = 0;
-  for (int k = 0; k < 3; ++k) {
-    rcbf_counters_t v = 0;
-    cudaError_t e = cudaMemcpy(&v, g_pipe.counters + k * RCBF_WS_WORDS, sizeof(v), cudaMemcpyDeviceToHost);
+  for (int k = 0; k < 3; ++k)
+    cudaMemcpyAsync(pp.failed_host + k, pp.counters + k * RCBF_WS_WORDS, sizeof(rcbf_counters_t), cudaMemcpyDeviceToHost,
+                    pp.streams[k]);
+  for (auto& s : pp.streams) {
+    cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return (int)e;
-    nan_count += v;
   }
-  if (n_failed_host) *n_failed_host = (int32_t)nan_count;
+  if (n_failed_host) *n_failed_host = (int32_t)(pp.failed_host[0] + pp.failed_host[1] + pp.failed_host[2]);
   return (int)cudaGetLastError();
 }
 }  // namespace
@@ -789,13 +1027,37 @@ int rcbf_unicycle_safe_step_host(float* state4, int32_t* step, const float* acti
   const int inb[3] = {8, 12, 12};
   void* out[6] = {safe_action_host, obs_host, reward_host, done_host, cost_host, goal_met_host};
   const int outb[6] = {8, 28, 4, 1, 4, 1};
-  return run_step_pipe(in, inb, 3, out, outb, 6, n, device, chunks, n_failed_host,
-                       [&](void** di, void** d_o, int64_t lo, int64_t cnt, rcbf_counters_t* ws, cudaStream_t s) {
-                         return rcbf_unicycle_safe_step(state4 + lo * 4, step + lo, (const float*)di[0],
-                                                        (const float*)di[1], (const float*)di[2], cnt, p, e,
-                                                        (float*)d_o[0], (float*)d_o[1], (float*)d_o[2], (uint8_t*)d_o[3],
-                                                        (float*)d_o[4], (uint8_t*)d_o[5], nullptr, ws, (void*)s);
-                       });
+  return run_pipe(in, inb, 3, nullptr, 0, out, outb, 6, n, device, chunks, n_failed_host,
+                  [&](void** di, void**, void** d_o, int64_t lo, int64_t cnt, rcbf_counters_t* ws, cudaStream_t s) {
+                    return rcbf_unicycle_safe_step(state4 + lo * 4, step + lo, (const float*)di[0], (const float*)di[1],
+                                                   (const float*)di[2], cnt, p, e, (float*)d_o[0], (float*)d_o[1],
+                                                   (float*)d_o[2], (uint8_t*)d_o[3], (float*)d_o[4], (uint8_t*)d_o[5],
+                                                   nullptr, ws, (void*)s);
+                  });
+}
+
+int rcbf_unicycle_safe_step_host_gp(float* state4, int32_t* step, const float* action_host,
+                                    const rcbf_gp_posterior* post, int64_t n, const rcbf_unicycle_params* p,
+                                    const rcbf_unicycle_env_params* e, float* safe_action_host, float* obs_host,
+                                    float* reward_host, uint8_t* done_host, float* cost_host, uint8_t* goal_met_host,
+                                    int32_t* n_failed_host, int device, int chunks) {
+  if (post == nullptr || post->n_in != 3 || post->n_gp != 3) return (int)cudaErrorInvalidValue;
+  rcbf_gp_posterior pg = *post;
+  pg.test_stride = 4;  // the resident float4 state (x, y, theta, last_goal_dist) is the test point, read in place
+  const void* in[1] = {action_host};
+  const int inb[1] = {8};
+  const int tmpb[2] = {12, 12};  // disturbance mean / std: produced and consumed on the device
+  void* out[6] = {safe_action_host, obs_host, reward_host, done_host, cost_host, goal_met_host};
+  const int outb[6] = {8, 28, 4, 1, 4, 1};
+  return run_pipe(in, inb, 1, tmpb, 2, out, outb, 6, n, device, chunks, n_failed_host,
+                  [&](void** di, void** dt, void** d_o, int64_t lo, int64_t cnt, rcbf_counters_t* ws, cudaStream_t s) {
+                    int rc = rcbf_gp_predict_f32(state4 + lo * 4, cnt, &pg, (float*)dt[0], (float*)dt[1], (void*)s);
+                    if (rc) return rc;
+                    return rcbf_unicycle_safe_step(state4 + lo * 4, step + lo, (const float*)di[0], (const float*)dt[0],
+                                                   (const float*)dt[1], cnt, p, e, (float*)d_o[0], (float*)d_o[1],
+                                                   (float*)d_o[2], (uint8_t*)d_o[3], (float*)d_o[4], (uint8_t*)d_o[5],
+                                                   nullptr, ws, (void*)s);
+                  });
 }
 
 int rcbf_cars_safe_step_host(float* state, float* t, int32_t* step, const float* action_host, const float* sigma_host,
@@ -806,37 +1068,42 @@ int rcbf_cars_safe_step_host(float* state, float* t, int32_t* step, const float*
   const int inb[2] = {4, 40};
   void* out[5] = {safe_action_host, obs_host, reward_host, done_host, cost_host};
   const int outb[5] = {4, 40, 4, 1, 4};
-  return run_step_pipe(in, inb, 2, out, outb, 5, n, device, chunks, n_failed_host,
-                       [&](void** di, void** d_o, int64_t lo, int64_t cnt, rcbf_counters_t* ws, cudaStream_t s) {
-                         return rcbf_cars_safe_step(state + lo * 10, t + lo, step + lo, (const float*)di[0],
-                                                    (const float*)di[1], cnt, p, e, (float*)d_o[0], (float*)d_o[1],
-                                                    (float*)d_o[2], (uint8_t*)d_o[3], (float*)d_o[4], nullptr, ws, (void*)s);
-                       });
+  return run_pipe(in, inb, 2, nullptr, 0, out, outb, 5, n, device, chunks, n_failed_host,
+                  [&](void** di, void**, void** d_o, int64_t lo, int64_t cnt, rcbf_counters_t* ws, cudaStream_t s) {
+                    return rcbf_cars_safe_step(state + lo * 10, t + lo, step + lo, (const float*)di[0],
+                                               (const float*)di[1], cnt, p, e, (float*)d_o[0], (float*)d_o[1],
+                                               (float*)d_o[2], (uint8_t*)d_o[3], (float*)d_o[4], nullptr, ws, (void*)s);
+                  });
 }
 
 int rcbf_unicycle_safe_action_host(const float* state_host, const float* action_host, const float* mean_host,
                                    const float* sigma_host, int64_t n, const rcbf_unicycle_params* p,
                                    float* safe_action_host, int32_t* n_failed_host, int device, int chunks) {
-  const float* in[4] = {state_host, action_host, mean_host, sigma_host};
-  const int w[4] = {3, 2, 3, 3};
-  return run_host_pipe(in, w, 4, safe_action_host, 2, n, device, chunks, n_failed_host,
-                       [&](float** d, float* out, int64_t lo, int64_t cnt, rcbf_counters_t* ctr, cudaStream_t s) {
-                         return rcbf_unicycle_safe_action(d[0] + lo * 3, d[1] + lo * 2, d[2] + lo * 3, d[3] + lo * 3, cnt,
-                                                          p, out + lo * 2, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                          ctr, (void*)s);
-                       });
+  const void* in[4] = {state_host, action_host, mean_host, sigma_host};
+  const int inb[4] = {12, 8, 12, 12};
+  void* out[1] = {safe_action_host};
+  const int outb[1] = {8};
+  return run_pipe(in, inb, 4, nullptr, 0, out, outb, 1, n, device, chunks, n_failed_host,
+                  [&](void** d, void**, void** d_o, int64_t, int64_t cnt, rcbf_counters_t* ctr, cudaStream_t s) {
+                    return rcbf_unicycle_safe_action((const float*)d[0], (const float*)d[1], (const float*)d[2],
+                                                     (const float*)d[3], cnt, p, (float*)d_o[0], nullptr, nullptr,
+                                                     nullptr, nullptr, nullptr, ctr, (void*)s);
+                  });
 }
 
 int rcbf_cars_safe_action_host(const float* state_host, const float* action_host, const float* sigma_host, int64_t n,
                                const rcbf_cars_params* p, float* safe_action_host, int32_t* n_failed_host, int device,
                                int chunks) {
-  const float* in[3] = {state_host, action_host, sigma_host};
-  const int w[3] = {10, 1, 10};
-  return run_host_pipe(in, w, 3, safe_action_host, 1, n, device, chunks, n_failed_host,
-                       [&](float** d, float* out, int64_t lo, int64_t cnt, rcbf_counters_t* ctr, cudaStream_t s) {
-                         return rcbf_cars_safe_action(d[0] + lo * 10, d[1] + lo, d[2] + lo * 10, cnt, p, out + lo,
-                                                      nullptr, nullptr, nullptr, nullptr, nullptr, ctr, (void*)s);
-                       });
+  const void* in[3] = {state_host, action_host, sigma_host};
+  const int inb[3] = {40, 4, 40};
+  void* out[1] = {safe_action_host};
+  const int outb[1] = {4};
+  return run_pipe(in, inb, 3, nullptr, 0, out, outb, 1, n, device, chunks, n_failed_host,
+                  [&](void** d, void**, void** d_o, int64_t, int64_t cnt, rcbf_counters_t* ctr, cudaStream_t s) {
+                    return rcbf_cars_safe_action((const float*)d[0], (const float*)d[1], (const float*)d[2], cnt, p,
+                                                 (float*)d_o[0], nullptr, nullptr, nullptr, nullptr, nullptr, ctr,
+                                                 (void*)s);
+                  });
 }
 
 }  // extern "C"

@@ -78,6 +78,7 @@ struct alignas(16) S2Warp {
   // (the observation rows of the tile being finished, 64 x 28 B = exactly one In slot, are staged in that tile's own
   //  slot once its state / step / action have been read, and leave from there by one bulk store)
   uint8_t cls[3][64];       // per instance: RCBF_OK_TRIVIAL / RCBF_OK_CERTIFIED / RCBF_NAN / RCBF_PENDING
+  uint16_t amask[kFused ? 1 : 3][64];  // layer-only kernel: active set of the certified solution (saved for the backward)
   uint64_t bar[2];
 };
 
@@ -205,6 +206,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         c2.x = (unsigned char)(nan[0] ? RCBF_NAN : (need0 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
         c2.y = (unsigned char)(nan[1] ? RCBF_NAN : (need1 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
         reinterpret_cast<uchar2*>(sh.cls[r3])[lane] = c2;
+        if (!kFused) reinterpret_cast<uint32_t*>(sh.amask[r3])[lane] = 0u;
       }
       if (lane == 0 && tile1 < ntiles) {
         // slot (k+1) & 3 belonged to the tile finished in the previous iteration; the bulk store of its observation rows
@@ -284,6 +286,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         } else {
           *up = make_float2(clampf(uu.x + (float)sol.x[0], p.u_min[0], p.u_max[0]),
                             clampf(uu.y + (float)sol.x[1], p.u_min[1], p.u_max[1]));  // :77
+          if (!kFused) sh.amask[(tag >> 6) & 3][pos] = (uint16_t)sol.mask;
           c_iters += sol.iters;
         }
       }
@@ -302,6 +305,11 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
       const uchar2 cl = reinterpret_cast<const uchar2*>(sh.cls[rf])[lane];
       const bool pend0 = cl.x == RCBF_PENDING, pend1 = cl.y == RCBF_PENDING;
       if (a.status != nullptr) reinterpret_cast<int2*>(a.status + i0)[lane] = make_int2(cl.x, cl.y);
+      if (!kFused && a.meta != nullptr) {  // (status << 16) | active set: what the backward kernel needs
+        const uint32_t am = reinterpret_cast<const uint32_t*>(sh.amask[rf])[lane];
+        reinterpret_cast<int2*>(a.meta + i0)[lane] =
+            make_int2(((int)cl.x << 16) | (int)(am & 0xffffu), ((int)cl.y << 16) | (int)(am >> 16));
+      }
       if (kFused) {
         const float4 qa = reinterpret_cast<const float4*>(sf.st)[2 * lane];
         const float4 qb = reinterpret_cast<const float4*>(sf.st)[2 * lane + 1];
@@ -435,8 +443,9 @@ inline int launch_safe2_tiles(const UniArgs& a, int64_t n, const UnicycleParams&
     return v != nullptr && v[0] == '1';
   }();
   if (env_off || n < RCBF_S2_MIN_N || n > 0x7fffffffLL || p.solver_mode != 0) return 0;
-  if (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr) return 0;
   auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr) return 0;
+  if (a.meta != nullptr && (kFused || !ok16(a.meta))) return 0;
   if (!(ok16(a.ac) && ok16(a.mu) && ok16(a.sg) && ok16(a.out) && (a.status == nullptr || ok16(a.status)))) return 0;
   if (kFused) {
     if (!(ok16(a.state4) && ok16(a.step) && ok16(a.obs) && ok16(a.reward) && ok16(a.cost) && ok16(a.done) &&

@@ -18,6 +18,15 @@ int rcbf_cars_safe_action(const float* state, const float* action, const float* 
   return launch_safe<CarsEnv<false>>(a, n, *p, rcbf_cars_env_params{}, workspace, (cudaStream_t)stream);
 }
 
+int rcbf_cars_safe_action_saved(const float* state, const float* action, const float* sigma, int64_t n,
+                                const rcbf_cars_params* p, float* safe_action, int32_t* meta, rcbf_counters_t* workspace,
+                                void* stream) {
+  CarsArgs a{};
+  a.st = state; a.ac = action; a.sg = sigma;
+  a.out = safe_action; a.meta = meta;
+  return launch_safe<CarsEnv<false>>(a, n, *p, rcbf_cars_env_params{}, workspace, (cudaStream_t)stream);
+}
+
 int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* action_rl, const float* sigma, int64_t n,
                         const rcbf_cars_params* p, const rcbf_cars_env_params* e, float* safe_action, float* obs,
                         float* reward, uint8_t* done, float* cost, int32_t* status, rcbf_counters_t* workspace,

@@ -108,6 +108,7 @@ struct UniArgs {
   float* slack;      // (n,9) nullable
   int32_t* status;   // nullable
   int32_t* iters;    // nullable
+  int32_t* meta;     // nullable: (status << 16) | active-set mask -- all the backward pass needs saved
   float* obs;        // (n,7)  [safe_step]
   float* reward;
   uint8_t* done;
@@ -348,6 +349,7 @@ struct CarsArgs {
   float* slack;     // (n,4) nullable
   int32_t* status;
   int32_t* iters;
+  int32_t* meta;    // nullable: (status << 16) | active-set mask
   float* obs;       // (n,10)
   float* reward;
   uint8_t* done;
@@ -594,6 +596,7 @@ __device__ __forceinline__ void write_saved(const typename E::Args& a, int64_t i
     for (int r = 0; r < E::M; ++r) a.slack[i * E::M + r] = (float)sol.s[r];
   }
   if (a.iters != nullptr) a.iters[i] = sol.iters;
+  if (a.meta != nullptr) a.meta[i] = (sol.status << 16) | (int)(sol.mask & 0xffffu);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -747,6 +750,7 @@ __device__ __forceinline__ void fallback_enum(const typename E::Args& a, int64_t
       }
       sol.status = RCBF_OK_CERTIFIED;
       sol.iters = NZ + 1;  // marks "enumerated" in the iteration histogram
+      sol.mask = mask;
     }
   }
   const unsigned winners = __ballot_sync(0xffffffffu, found);
@@ -1146,6 +1150,8 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
                 sol.s[r] = lsol.s[r];
               }
               sol.iters = lsol.iters;
+              sol.status = status;
+              sol.mask = lsol.mask;
               write_saved<E>(a, my_idx, sol);
             }
             c_iters += lsol.iters;
@@ -1304,7 +1310,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);
   // TMA bulk staging needs 16-byte aligned array bases (row spans of a 32-instance tile are then 16-byte multiples)
   const bool bulk = E::aligned(a) && n >= 32;
-  const bool saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr);
+  const bool saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr || a.meta != nullptr);
 #define RCBF_LAUNCH_ONE(MODE, BULK, SAVED)                                                           \
   do {                                                                                               \
     constexpr size_t smem = sizeof(WarpShared<E, MODE>) * kWarps;                                    \

@@ -30,6 +30,7 @@ int launch_unicycle(UniArgs a, int64_t n, const rcbf_unicycle_params& p, const r
     }
     a.ac += done * 2; a.mu += done * 3; a.sg += done * 3; a.out += done * 2;
     if (a.status != nullptr) a.status += done;
+    if (a.meta != nullptr) a.meta += done;
   }
   return launch_safe<UniEnv<kFused>>(a, n - done, p, e, ws, s);
 }
@@ -43,6 +44,15 @@ int rcbf_unicycle_safe_action(const float* state, const float* action, const flo
   UniArgs a{};
   a.st = state; a.ac = action; a.mu = mean; a.sg = sigma;
   a.out = safe_action; a.x = x; a.lam = lam; a.slack = slack; a.status = status; a.iters = iters;
+  return launch_unicycle<false>(a, n, *p, rcbf_unicycle_env_params{}, workspace, (cudaStream_t)stream);
+}
+
+int rcbf_unicycle_safe_action_saved(const float* state, const float* action, const float* mean, const float* sigma,
+                                    int64_t n, const rcbf_unicycle_params* p, float* safe_action, int32_t* meta,
+                                    rcbf_counters_t* workspace, void* stream) {
+  UniArgs a{};
+  a.st = state; a.ac = action; a.mu = mean; a.sg = sigma;
+  a.out = safe_action; a.meta = meta;
   return launch_unicycle<false>(a, n, *p, rcbf_unicycle_env_params{}, workspace, (cudaStream_t)stream);
 }
 

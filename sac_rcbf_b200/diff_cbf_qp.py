@@ -14,33 +14,35 @@ DYNAMICS_MODE = {"Unicycle": {"n_s": 3, "n_u": 2}, "SimulatedCars": {"n_s": 10, 
 
 
 def _f32c(t, device):
+    """float32, contiguous, on `device`, detached -- returned as is when it already is all of that (the common case
+    costs no torch dispatch)."""
+    if t.dtype == torch.float32 and t.device == device and not t.requires_grad and t.is_contiguous():
+        return t
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
 class _SafeActionFn(torch.autograd.Function):
-    """final = clamp(a + QP(a)) with the implicit-KKT backward kernel (K4)."""
+    """final = clamp(a + QP(a)) with the implicit-KKT backward kernel (K4).  Only entered when the action carries grad;
+    the forward saves one int32 per instance (status + active set), the backward rebuilds the rest."""
 
     @staticmethod
     def forward(ctx, layer, state, action, mean, sigma):
         dev = layer.device
         st, ac, sg = _f32c(state, dev), _f32c(action, dev), _f32c(sigma, dev)
         mu = _f32c(mean, dev)
-        n = st.shape[0]
-        need_grad = bool(ctx.needs_input_grad[2])   # grad mode is off inside forward(); this is the reliable signal
-        out, x, lam, slack = layer._forward_raw(st, ac, mu, sg, save=need_grad)
+        out, meta = layer._forward_meta(st, ac, mu, sg)
         ctx.layer = layer
         ctx.in_device = action.device
         ctx.in_dtype = action.dtype
-        if need_grad:
-            ctx.save_for_backward(st, ac, mu, sg, x, lam, slack)
+        ctx.save_for_backward(st, ac, mu, sg, meta)
         return out.to(device=action.device, dtype=action.dtype) if (action.device != dev or action.dtype != torch.float32) else out
 
     @staticmethod
     def backward(ctx, grad_out):
         layer = ctx.layer
-        st, ac, mu, sg, x, lam, slack = ctx.saved_tensors
+        st, ac, mu, sg, meta = ctx.saved_tensors
         go = _f32c(grad_out, layer.device)
-        ga = layer._backward_raw(st, ac, mu, sg, x, lam, slack, go)
+        ga = layer._backward_meta(st, ac, mu, sg, meta, go)
         return None, None, ga.to(device=ctx.in_device, dtype=ctx.in_dtype), None, None
 
 
@@ -66,6 +68,7 @@ class _QPFn(torch.autograd.Function):
                                       % (nz, m))
         _lib.check(rc, "rcbf_qp_solve")
         layer._last_counters = counters
+        layer._last_stats = None
         ctx.layer = layer
         ctx.save_for_backward(Qd, Gd, x, lam, slack)
         ctx.in_devices = (Q.device, p.device, G.device, h.device)
@@ -109,9 +112,8 @@ class CBFQPLayer:
         _lib.load()
         dev_num = getattr(args, "device_num", None)
         self.device = torch.device("cuda", torch.cuda.current_device() if dev_num is None else int(dev_num))
-        # the reference computes on CPU when args.cuda is False; here the QP always runs on the GPU and results are
-        # returned on the caller's device
-        self.caller_device = self.device if getattr(args, "cuda", True) else torch.device("cpu")
+        # (the reference computes on the CPU when args.cuda is False; here the QP always runs on the GPU -- there is no
+        #  CPU path -- and results are returned on the device / dtype of the caller's action tensor)
 
         self.env = env
         self.u_min, self.u_max = self.get_control_bounds()
@@ -133,17 +135,51 @@ class CBFQPLayer:
         # "presolve": greedy active-set guess + float64 KKT certificate, interior point only as fallback (default);
         # "pdipm": every non-trivial QP runs the primal-dual interior point (the reference's algorithm family)
         self.solver = "presolve"
-        self._last_counters = None  # device tensor [nan, uncertified, f64 passes, trivial, sum iters, ...]
+        self._last_counters = None  # workspace of the last fused env step (device tensor, cumulative counters)
+        self._last_stats = None     # per-call counter increments of the last synchronised launch
         self._params_cache = None
 
     def _workspace(self):
-        """RCBF_WS_WORDS-word solver workspace (counters + fallback queue) with the counters zeroed for this call."""
+        """RCBF_WS_WORDS-word solver workspace (counters + fallback queue), zero-initialised ONCE.  The counters
+        accumulate on the device; per-call numbers are differences taken on the host (`_sync_counters`), so a call
+        costs no extra launch."""
         ws = getattr(self, "_ws", None)
         if ws is None or ws.device != self.device:
             ws = self._ws = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=self.device)
-        else:
-            ws[:8].zero_()
+            self._ws_base = [0] * 8
+            self._ws_pin = None
         return ws
+
+    def _sync_counters(self):
+        """ONE device->host read of the 8 counters (synchronises); returns this call's increments."""
+        pin = getattr(self, "_ws_pin", None)
+        if pin is None:
+            pin = self._ws_pin = torch.zeros(8, dtype=torch.int64).pin_memory()
+            self._ws_head = self._ws[:8]
+        pin.copy_(self._ws_head, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        cur = pin.tolist()
+        delta = [c - b for c, b in zip(cur, self._ws_base)]
+        self._ws_base = cur
+        self._last_stats = delta
+        self._last_counters = None
+        return delta
+
+    def _before_launch(self):
+        """Counters advanced by launches that were not read back (check_nan = False) must not be blamed on this call."""
+        if self.check_nan and getattr(self, "_unread", False):
+            self._sync_counters()
+            self._unread = False
+
+    def _after_launch(self):
+        self._last_stats = None
+        self._last_counters = None
+        if not self.check_nan:
+            self._unread = True
+            return
+        if self._sync_counters()[0] > 0:
+            print('\033[91m QP Failed to solve - result is nan == True!\033[00m')
+            raise Exception('QP Failed to solve')
 
     # ------------------------------------------------------------------------------------------------------ params
     def _solver_mode(self):
@@ -162,6 +198,15 @@ class CBFQPLayer:
     def _params(self):
         """C parameter struct, rebuilt when a public attribute the reference reads at call time has changed."""
         env = self.env
+        # fast path: nothing the struct depends on was re-assigned (identity / value of the scalars, identity of the
+        # arrays; an IN-PLACE edit of env.hazards_locations is caught by the bytes comparison every 256th call)
+        quick = (self.solver, self.gamma_b, getattr(self, "l_p", None), id(getattr(env, "hazards_locations", None)),
+                 getattr(env, "hazards_radius", None), getattr(env, "kp", None), getattr(env, "k_brake", None),
+                 self.u_min.data_ptr(), self.u_min._version, self.u_max.data_ptr(), self.u_max._version)
+        self._params_calls = getattr(self, "_params_calls", 0) + 1
+        if self._params_cache is not None and getattr(self, "_params_quick", None) == quick and self._params_calls & 255:
+            return self._params_cache[1]
+        self._params_quick = quick
         lo, hi = self._bounds_host()
         if env.dynamics_mode == 'Unicycle':
             hz = np.asarray(env.hazards_locations, np.float64)
@@ -180,8 +225,16 @@ class CBFQPLayer:
         return self._params_cache[1]
 
     # ------------------------------------------------------------------------------------------------- raw launches
+    def _launch_ctx(self):
+        """(lib, stream pointer) with the layer's device current (switching only when it is not already)."""
+        dev = self.device
+        if torch.cuda.current_device() != dev.index:
+            torch.cuda.set_device(dev)
+        return _lib.load(), _lib.stream_ptr(dev)
+
     def _forward_raw(self, st, ac, mu, sg, save=False, want_status=False):
-        lib = _lib.load()
+        """Forward launch with the optional DENSE saved tensors x / lam / slack (diagnostics and the legacy backward
+        entry); the autograd path uses `_forward_meta`."""
         dev = self.device
         n = st.shape[0]
         mode = self.env.dynamics_mode
@@ -196,26 +249,70 @@ class CBFQPLayer:
             status = torch.empty((n,), dtype=torch.int32, device=dev)
             iters = torch.empty((n,), dtype=torch.int32, device=dev)
         counters = self._workspace()
+        self._before_launch()
         p = self._params()
-        with torch.cuda.device(dev):
-            if mode == 'Unicycle':
-                rc = lib.rcbf_unicycle_safe_action(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
-                                                   _lib.ptr(out), _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack),
-                                                   _lib.ptr(status), _lib.ptr(iters), _lib.ptr(counters),
-                                                   _lib.stream_ptr(dev))
-            else:
-                rc = lib.rcbf_cars_safe_action(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), n, p, _lib.ptr(out),
-                                               _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack), _lib.ptr(status),
-                                               _lib.ptr(iters), _lib.ptr(counters), _lib.stream_ptr(dev))
+        prev = torch.cuda.current_device()
+        lib, stream = self._launch_ctx()
+        if mode == 'Unicycle':
+            rc = lib.rcbf_unicycle_safe_action(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
+                                               _lib.ptr(out), _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack),
+                                               _lib.ptr(status), _lib.ptr(iters), _lib.ptr(counters), stream)
+        else:
+            rc = lib.rcbf_cars_safe_action(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), n, p, _lib.ptr(out),
+                                           _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack), _lib.ptr(status),
+                                           _lib.ptr(iters), _lib.ptr(counters), stream)
+        if prev != dev.index:
+            torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_%s_safe_action" % mode)
-        self._last_counters = counters
         self._last_status, self._last_iters = status, iters
-        if self.check_nan and int(counters[0].item()) > 0:
-            print('\033[91m QP Failed to solve - result is nan == True!\033[00m')
-            raise Exception('QP Failed to solve')
+        self._after_launch()
         return out, x, lam, slack
 
+    def _forward_meta(self, st, ac, mu, sg):
+        """Forward launch of the differentiable path: safe action + one int32 per instance (status << 16 | active set)."""
+        dev = self.device
+        n = st.shape[0]
+        mode = self.env.dynamics_mode
+        out = torch.empty((n, 2 if mode == 'Unicycle' else 1), dtype=torch.float32, device=dev)
+        meta = torch.empty((n,), dtype=torch.int32, device=dev)
+        counters = self._workspace()
+        self._before_launch()
+        p = self._params()
+        prev = torch.cuda.current_device()
+        lib, stream = self._launch_ctx()
+        if mode == 'Unicycle':
+            rc = lib.rcbf_unicycle_safe_action_saved(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
+                                                     _lib.ptr(out), _lib.ptr(meta), _lib.ptr(counters), stream)
+        else:
+            rc = lib.rcbf_cars_safe_action_saved(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), n, p, _lib.ptr(out),
+                                                 _lib.ptr(meta), _lib.ptr(counters), stream)
+        if prev != dev.index:
+            torch.cuda.set_device(prev)
+        _lib.check(rc, "rcbf_%s_safe_action_saved" % mode)
+        self._after_launch()
+        return out, meta
+
+    def _backward_meta(self, st, ac, mu, sg, meta, go):
+        n = st.shape[0]
+        ga = torch.empty_like(ac)
+        scratch = torch.empty((n + 4,), dtype=torch.int32, device=self.device) if n >= 32768 else None
+        p = self._params()
+        prev = torch.cuda.current_device()
+        lib, stream = self._launch_ctx()
+        if self.env.dynamics_mode == 'Unicycle':
+            rc = lib.rcbf_unicycle_safe_action_bwd_meta(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg),
+                                                        _lib.ptr(meta), _lib.ptr(go), n, p, _lib.ptr(ga),
+                                                        _lib.ptr(scratch), stream)
+        else:
+            rc = lib.rcbf_cars_safe_action_bwd_meta(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), _lib.ptr(meta),
+                                                    _lib.ptr(go), n, p, _lib.ptr(ga), _lib.ptr(scratch), stream)
+        if prev != self.device.index:
+            torch.cuda.set_device(prev)
+        _lib.check(rc, "rcbf_safe_action_bwd_meta")
+        return ga
+
     def _backward_raw(self, st, ac, mu, sg, x, lam, slack, go):
+        """Legacy backward entry on the dense saved tensors of `_forward_raw(save=True)`."""
         lib = _lib.load()
         dev = self.device
         n = st.shape[0]
@@ -245,7 +342,14 @@ class CBFQPLayer:
         assert len(state_batch.shape) == 2 and len(action_batch.shape) == 2 and len(mean_pred_batch.shape) == 2 and \
             len(sigma_batch.shape) == 2, print(state_batch.shape, action_batch.shape, mean_pred_batch.shape,
                                                sigma_batch.shape)
-        final_action = _SafeActionFn.apply(self, state_batch, action_batch, mean_pred_batch, sigma_batch)
+        if torch.is_grad_enabled() and action_batch.requires_grad:
+            final_action = _SafeActionFn.apply(self, state_batch, action_batch, mean_pred_batch, sigma_batch)
+        else:  # nothing to differentiate (select_action, --no_diff_qp): straight to the kernel, no autograd node
+            dev = self.device
+            out, _, _, _ = self._forward_raw(_f32c(state_batch, dev), _f32c(action_batch, dev),
+                                             _f32c(mean_pred_batch, dev), _f32c(sigma_batch, dev))
+            final_action = out if (action_batch.device == dev and action_batch.dtype == torch.float32) else \
+                out.to(device=action_batch.device, dtype=action_batch.dtype)
         return final_action if not expand_dims else final_action.squeeze(0)
 
     def solve_qp(self, Ps, qs, Gs, hs):
@@ -314,10 +418,17 @@ class CBFQPLayer:
 
     # ---------------------------------------------------------------------------------------------- diagnostics
     def solver_stats(self):
-        """Counters of the last launch: dict(nan, uncertified, f64_passes, trivial, sum_iters)."""
-        if self._last_counters is None:
+        """Counters of the last launch: dict(nan, uncertified, f64_passes, trivial, sum_iters, fallback, ...).  After a
+        call made with `check_nan = False` (no sync) or a fused env step the numbers are read here: the increments
+        since the previous read of that workspace."""
+        if getattr(self, "_last_stats", None) is not None:
+            c = self._last_stats
+        elif self._last_counters is not None:           # workspace of a fused env step (cumulative)
+            c = self._last_counters[:8].cpu().tolist()
+        elif getattr(self, "_ws", None) is not None:
+            c = self._sync_counters()
+        else:
             return None
-        c = self._last_counters[:8].cpu().tolist()
         return dict(nan=c[0], uncertified=c[1], f64_passes=c[2], trivial=c[3], sum_iters=c[4], fallback=c[5],
                     fallback_iters=c[6])
 

@@ -38,10 +38,14 @@ class SimulatedCarsEnv:
         self._state = torch.zeros((n, 10), dtype=self._dtype, device=self.device)
         self._t = torch.zeros((n,), dtype=self._dtype, device=self.device)
         self._step = torch.zeros((n,), dtype=torch.int32, device=self.device)
-        self._obs = torch.empty((n, 10), dtype=self._dtype, device=self.device)
-        self._reward = torch.empty((n,), dtype=self._dtype, device=self.device)
-        self._cost = torch.empty((n,), dtype=self._dtype, device=self.device)
-        self._done = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        # step outputs: typed views into ONE device buffer (single-env step = one device->host copy)
+        isz = 8 if self._dtype == torch.float64 else 4
+        self._outbuf = torch.zeros(((12 * isz + 1) * n + 15) // 16 * 16, dtype=torch.uint8, device=self.device)
+        typed = self._outbuf[:12 * isz * n].view(self._dtype)
+        self._obs = typed[:10 * n].view(n, 10)
+        self._reward = typed[10 * n:11 * n]
+        self._cost = typed[11 * n:12 * n]
+        self._done = self._outbuf[12 * isz * n:12 * isz * n + n]
         self._gen = torch.Generator(device=self.device)
         if seed is not None:
             self._gen.manual_seed(int(seed))
@@ -113,9 +117,11 @@ class SimulatedCarsEnv:
                                   _lib.ptr(self._done), _lib.ptr(self._cost), _lib.stream_ptr(self.device))
         _lib.check(rc, "rcbf_cars_env_step")
         if self.num_envs == 1:
-            info = {'cost': float(self._cost[0].item()), 'goal_met': False}     # simulated_cars_env.py:85
-            return (self._obs[0].double().cpu().numpy(), float(self._reward[0].item()), bool(self._done[0].item()),
-                    info)
+            isz = 8 if self._dtype == torch.float64 else 4
+            host = self._outbuf.cpu()                      # ONE device->host copy (and the only synchronisation)
+            vals = host[:12 * isz].view(self._dtype).double().numpy()
+            info = {'cost': float(vals[11]), 'goal_met': False}                 # simulated_cars_env.py:85
+            return vals[:10].copy(), float(vals[10]), bool(host[12 * isz]), info
         info = {'cost': self._cost.clone(), 'goal_met': torch.zeros_like(self._done, dtype=torch.bool)}
         return self._obs.clone(), self._reward.clone(), self._done.bool(), info
 
@@ -139,6 +145,7 @@ class SimulatedCarsEnv:
                                                _lib.ptr(self._counters), _lib.stream_ptr(dev))
         _lib.check(rc, "rcbf_cars_safe_step")
         cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
+        cbf_layer._last_stats = None
         info = {'cost': self._cost, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
 

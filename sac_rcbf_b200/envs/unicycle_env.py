@@ -43,11 +43,16 @@ class UnicycleEnv:
         n = self.num_envs
         self._state4 = torch.zeros((n, 4), dtype=self._dtype, device=self.device)
         self._step = torch.zeros((n,), dtype=torch.int32, device=self.device)
-        self._obs = torch.empty((n, 7), dtype=self._dtype, device=self.device)
-        self._reward = torch.empty((n,), dtype=self._dtype, device=self.device)
-        self._cost = torch.empty((n,), dtype=self._dtype, device=self.device)
-        self._done = torch.empty((n,), dtype=torch.uint8, device=self.device)
-        self._goal = torch.empty((n,), dtype=torch.uint8, device=self.device)
+        # step outputs: typed views into ONE device buffer, so that the single-env gym contract (obs ndarray, float
+        # reward, bool done, info dict -- main.py:93-95) costs one device->host copy per step instead of five
+        isz = 8 if self._dtype == torch.float64 else 4
+        self._outbuf = torch.zeros(((9 * isz + 2) * n + 15) // 16 * 16, dtype=torch.uint8, device=self.device)
+        typed = self._outbuf[:9 * isz * n].view(self._dtype)
+        self._obs = typed[:7 * n].view(n, 7)
+        self._reward = typed[7 * n:8 * n]
+        self._cost = typed[8 * n:9 * n]
+        self._done = self._outbuf[9 * isz * n:9 * isz * n + n]
+        self._goal = self._outbuf[9 * isz * n + n:9 * isz * n + 2 * n]
         self.reset()
 
     # -------------------------------------------------------------------------------------------- helpers
@@ -137,14 +142,17 @@ class UnicycleEnv:
 
     def _pack_step_outputs(self):
         if self.num_envs == 1:
+            isz = 8 if self._dtype == torch.float64 else 4
+            host = self._outbuf.cpu()                      # ONE device->host copy (and the only synchronisation)
+            vals = host[:9 * isz].view(self._dtype).double().numpy()
+            done, goal = bool(host[9 * isz]), bool(host[9 * isz + 1])
             info = dict()
-            if bool(self._goal[0].item()):
+            if goal:
                 info['goal_met'] = True                    # only present when met (unicycle_env.py:98)
-            c = float(self._cost[0].item())
+            c = float(vals[8])
             if c != 0.0:
                 info['cost'] = c                           # only present inside a hazard (:106-110)
-            return (self._obs[0].double().cpu().numpy(), float(self._reward[0].item()), bool(self._done[0].item()),
-                    info)
+            return vals[:7].copy(), float(vals[7]), done, info
         info = {'cost': self._cost.clone(), 'goal_met': self._goal.bool()}
         return self._obs.clone(), self._reward.clone(), self._done.bool(), info
 
@@ -171,33 +179,59 @@ class UnicycleEnv:
                                                    _lib.stream_ptr(dev))
         _lib.check(rc, "rcbf_unicycle_safe_step")
         cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
+        cbf_layer._last_stats = None
         info = {'cost': self._cost, 'goal_met': self._goal, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
 
-    def safe_step_host(self, cbf_layer, action_rl, mean_pred, sigma_pred, out=None, chunks=8):
+    HOST_OUTPUTS = ("safe_action", "obs", "reward", "done", "cost", "goal_met")
+
+    def safe_step_host(self, cbf_layer, action_rl, mean_pred=None, sigma_pred=None, out=None, chunks=8, outputs=None,
+                       gp=None):
         """Fused safe step with HOST tensors in and out (the end-to-end path): `action_rl (n,2)`, `mean_pred (n,3)`,
         `sigma_pred (n,3)` float32 CPU tensors (pinned memory recommended); the env state stays on the GPU.  The C
         library pipelines H2D / kernel / D2H over `chunks` slices on its own streams and returns when `out` is valid.
-        Returns dict(safe_action, obs, reward, done, cost, goal_met) of pinned CPU tensors (reused when passed back)."""
+
+        `outputs`: the subset of HOST_OUTPUTS the caller wants on the host (default: all six); the others are produced
+        on the device but not copied back.  `gp`: a fitted `DisturbanceGPBank` (3 inputs, 3 outputs) -- the disturbance
+        mean / std are then evaluated ON THE DEVICE from the resident state (rcbf_sac/sac_cbf.py:230-236) and
+        `mean_pred` / `sigma_pred` must be None: the only host input is the action.
+        Returns a dict of pinned CPU tensors (reused when passed back as `out`)."""
         import ctypes as C
         if self.precision != "f32":
             raise ValueError("safe_step_host runs on the float32 env layout (precision='f32')")
         n = self.num_envs
+        names = self.HOST_OUTPUTS if outputs is None else tuple(outputs)
+        for k in names:
+            if k not in self.HOST_OUTPUTS:
+                raise ValueError("unknown host output %r" % (k,))
+        shapes = dict(safe_action=((n, 2), torch.float32), obs=((n, 7), torch.float32), reward=((n,), torch.float32),
+                      done=((n,), torch.uint8), cost=((n,), torch.float32), goal_met=((n,), torch.uint8))
         if out is None:
-            mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()  # noqa: E731
-            out = dict(safe_action=mk((n, 2), torch.float32), obs=mk((n, 7), torch.float32),
-                       reward=mk((n,), torch.float32), done=mk((n,), torch.uint8), cost=mk((n,), torch.float32),
-                       goal_met=mk((n,), torch.uint8))
-        for t in (action_rl, mean_pred, sigma_pred):
-            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+            out = {}
+        for k in names:
+            if k not in out:
+                out[k] = torch.empty(shapes[k][0], dtype=shapes[k][1]).pin_memory()
+        ins = (action_rl,) if gp is not None else (action_rl, mean_pred, sigma_pred)
+        if gp is not None and (mean_pred is not None or sigma_pred is not None):
+            raise ValueError("with gp= the disturbance is evaluated on the device: pass mean_pred = sigma_pred = None")
+        for t in ins:
+            if t is None or t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise ValueError("safe_step_host takes contiguous float32 CPU tensors")
         nf = C.c_int32(0)
         torch.cuda.current_stream(self.device).synchronize()      # the library uses its own streams
-        rc = self._lib.rcbf_unicycle_safe_step_host(
-            _lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(action_rl), _lib.ptr(mean_pred), _lib.ptr(sigma_pred),
-            n, cbf_layer._params(), self._env_params(), _lib.ptr(out["safe_action"]), _lib.ptr(out["obs"]),
-            _lib.ptr(out["reward"]), _lib.ptr(out["done"]), _lib.ptr(out["cost"]), _lib.ptr(out["goal_met"]),
-            C.byref(nf), self.device.index or 0, int(chunks))
+        o = [_lib.ptr(out[k]) if k in names else None for k in self.HOST_OUTPUTS]
+        if gp is None:
+            rc = self._lib.rcbf_unicycle_safe_step_host(
+                _lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(action_rl), _lib.ptr(mean_pred),
+                _lib.ptr(sigma_pred), n, cbf_layer._params(), self._env_params(), o[0], o[1], o[2], o[3], o[4], o[5],
+                C.byref(nf), self.device.index or 0, int(chunks))
+        else:
+            if gp._post is None:
+                gp.build_posterior()
+            rc = self._lib.rcbf_unicycle_safe_step_host_gp(
+                _lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(action_rl), C.byref(gp._post[0]), n,
+                cbf_layer._params(), self._env_params(), o[0], o[1], o[2], o[3], o[4], o[5], C.byref(nf),
+                self.device.index or 0, int(chunks))
         _lib.check(rc, "rcbf_unicycle_safe_step_host")
         if cbf_layer.check_nan and nf.value > 0:
             raise Exception('QP Failed to solve')
