@@ -119,24 +119,21 @@ int rcbf_cars_safe_action_bwd(const float* state, const float* action, const flo
  * The forward saves ONE int32 per instance, meta = (status << 16) | active-set mask (bit i = row i of G~x <= h~ is
  * active at the optimum; 0xffff: no vertex, interior-point result), instead of x / lam / slack (84 bytes).  The backward
  * finishes a trivial instance (status RCBF_OK_TRIVIAL: x = 0, gradient = the clamp mask of diff_cbf_qp.py:77) from 28
- * bytes; for the others it re-assembles the constraints, rebuilds x / lam / slack from the active set with the float64
- * solve of the forward certificate and applies the same implicit-KKT backward as rcbf_*_safe_action_bwd. */
+ * bytes; for the others it re-assembles the constraints and differentiates the closed-form solution on the <= nz active
+ * rows (the exact active-set form of the implicit-KKT backward: rcbf_*_safe_action_bwd with qpth's 1e-8 clamps taken to
+ * zero; the two agree to ~1e-5 of the batch gradient norm).  One launch, no scratch memory. */
 int rcbf_unicycle_safe_action_saved(const float* state, const float* action, const float* mean, const float* sigma,
                                     int64_t n, const rcbf_unicycle_params* p_host, float* safe_action /* n*2 */,
                                     int32_t* meta /* n */, rcbf_counters_t* workspace, void* stream);
 int rcbf_cars_safe_action_saved(const float* state, const float* action, const float* sigma, int64_t n,
                                 const rcbf_cars_params* p_host, float* safe_action /* n */, int32_t* meta /* n */,
                                 rcbf_counters_t* workspace, void* stream);
-/* scratch: nullable device buffer of n + 4 int32.  With it, large batches run as two launches (classify + a dense
- * list of the non-trivial instances of the whole batch, then the float64 part on full blocks); without it, or for
- * small batches, as one launch that compacts inside each block. */
 int rcbf_unicycle_safe_action_bwd_meta(const float* state, const float* action, const float* mean, const float* sigma,
                                        const int32_t* meta, const float* grad_out, int64_t n,
-                                       const rcbf_unicycle_params* p_host, float* grad_action, int32_t* scratch,
-                                       void* stream);
+                                       const rcbf_unicycle_params* p_host, float* grad_action, void* stream);
 int rcbf_cars_safe_action_bwd_meta(const float* state, const float* action, const float* sigma, const int32_t* meta,
                                    const float* grad_out, int64_t n, const rcbf_cars_params* p_host, float* grad_action,
-                                   int32_t* scratch, void* stream);
+                                   void* stream);
 
 /* ---- generic small QP  min 1/2 x'Qx + p'x  s.t. Gx <= h  (cbf_layer / solve_qp), float64 tensors like qpth sees ---
  * (nz, m) in {(3,9), (2,4)}.  (solve_qp's [G|h] row normalisation is applied by the caller, diff_cbf_qp.py:103-106.) */

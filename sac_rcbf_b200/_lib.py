@@ -28,9 +28,8 @@ SIGNATURES = {
     "rcbf_cars_safe_action_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, _vp],
     "rcbf_unicycle_safe_action_saved": [_vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp, _vp, _vp, _vp],
     "rcbf_cars_safe_action_saved": [_vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, _vp, _vp, _vp],
-    "rcbf_unicycle_safe_action_bwd_meta": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp, _vp,
-                                           _vp],
-    "rcbf_cars_safe_action_bwd_meta": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, _vp, _vp],
+    "rcbf_unicycle_safe_action_bwd_meta": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp, _vp],
+    "rcbf_cars_safe_action_bwd_meta": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), _vp, _vp],
     "rcbf_qp_solve": [_vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rcbf_qp_solve_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp],
     "rcbf_unicycle_safe_step": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams),

@@ -148,4 +148,107 @@ RCBF_HD void safe_action_bwd(const Normalised<NZ, M>& nrm, const float rawG[M][N
   for (int c = 0; c < NU; ++c) grad_a[c] = (float)ga[c];
 }
 
+// ---- exact active-set form (what the compact backward kernels run) ---------------------------------------------------
+// The forward certificate established WHICH rows S (|S| <= NZ) are active at the optimum, so the solution is the closed
+// form  y = A_S' Gm^-1 b_S  (A = G~ P^-1/2, b = h~, Gm = A_S A_S', x = P^-1/2 y) and its derivative is that of the
+// equality-constrained problem -- the limit of qpth's backward above as its clamps 1e-8 -> 0 (d -> inf on the active rows,
+// d -> 0 on the inactive ones; the terms dropped are O(1e-8 / slack_i) and O(1e-8 / lam_k), below the convergence noise
+// of qpth's own iterate):
+//     dL/db_S = v = Gm^-1 A_S gy          (gy = P^-1/2 dL/dx),      dL/dA_k = mu_k (gy - A_S'v) - v_k y,   mu = Gm^-1 b_S.
+// Chain through the row normalisation (diff_cbf_qp.py:103-106): b_k = h_k / n_k, A_k = G_k P^-1/2 / n_k with G independent
+// of the action.  If n_k does not depend on h_k:  dL/dh_k = v_k / n_k.  If n_k = |h_k| (h is the row maximum): b_k = +-1
+// is constant and A_k = G_k P^-1/2 / |h_k|, so dL/dh_k = -(sgn h_k / n_k) dL/dA_k . A_k = (sgn h_k / n_k) v_k b_k
+// (A_k is orthogonal to gy - A_S'v and A_k . y = b_k) = v_k / n_k again.  Hence, for every active row,
+//     dL/da_c = g_c + sum_{k in S} (v_k / n_k) r_k[c],                                  inactive rows contribute nothing:
+// only the <= NZ active rows are gathered and normalised (the same float32 quotients the forward certified), one
+// NZ x NZ float64 Cholesky serves both the re-solve for x (clamp mask of diff_cbf_qp.py:77) and the gradient.
+// pis = P^-1/2 in float64 (pis_of).
+template <typename Pat, int NZ, int M, int NU>
+RCBF_HD void safe_action_bwd_active(const float G[M][NZ], const float h[M], const float r[M][NU], const double pis[NZ],
+                                    uint32_t mask, const float a[NU], const float u_min[NU], const float u_max[NU],
+                                    const float gout[NU], float grad_a[NU]) {
+  float g[NZ][NZ], hh[NZ], rr[NZ][NU];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) g[k][j] = 0.f;
+    RCBF_UNROLL
+    for (int c = 0; c < NU; ++c) rr[k][c] = 0.f;
+    hh[k] = 0.f;
+  }
+  int cnt = 0;
+  RCBF_UNROLL
+  for (int i = 0; i < M; ++i) {
+    const bool act = (mask >> i) & 1u;
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) {
+      const bool put = act && (cnt == k);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) g[k][j] = put ? G[i][j] : g[k][j];
+      RCBF_UNROLL
+      for (int c = 0; c < NU; ++c) rr[k][c] = put ? r[i][c] : rr[k][c];
+      hh[k] = put ? h[i] : hh[k];
+    }
+    cnt += act ? 1 : 0;
+  }
+  double R[NZ][NZ], rb[NZ], ninv[NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {  // normalise the gathered row exactly like the forward (lnp_greedy_raw / normalise_rows)
+    float gm = 0.f;
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) gm = fmaxf(gm, fabsf(g[k][j]));
+    const float ha = fabsf(hh[k]);
+    const float n = (k < cnt) ? ((ha != ha) ? ha : fmaxf(gm, ha)) : 1.f;
+    const float rn = rcp_refined(n);
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) R[k][j] = (double)div_by(g[k][j], n, rn) * pis[j];
+    rb[k] = (double)div_by(hh[k], n, rn);
+    ninv[k] = (double)rn;
+  }
+  double Gm[NZ][NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    RCBF_UNROLL
+    for (int l = 0; l <= k; ++l) {
+      double acc = 0.0;
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j) acc = fma(R[k][j], R[l][j], acc);
+      Gm[k][l] = acc;
+    }
+    Gm[k][k] = (k < cnt) ? Gm[k][k] : 1.0;
+  }
+  Chol<double, NZ> ch;
+  ch.factor(Gm);
+  double mu[NZ];
+  ch.solve(rb, mu);
+  // x_c = P_c^-1/2 sum_k A_kc mu_k ; clamp mask (torch.clamp passes grad where min <= v <= max)
+  double gy[NU], gc[NU];
+  RCBF_UNROLL
+  for (int c = 0; c < NU; ++c) {
+    double y = 0.0;
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) y = fma(R[k][c], mu[k], y);
+    const float v = a[c] + (float)(y * pis[c]);
+    gc[c] = (v >= u_min[c] && v <= u_max[c]) ? (double)gout[c] : 0.0;
+    gy[c] = gc[c] * pis[c];
+  }
+  double w[NZ], v[NZ];
+  RCBF_UNROLL
+  for (int k = 0; k < NZ; ++k) {
+    double acc = 0.0;
+    RCBF_UNROLL
+    for (int c = 0; c < NU; ++c) acc = fma(R[k][c], gy[c], acc);
+    w[k] = acc;
+  }
+  ch.solve(w, v);
+  RCBF_UNROLL
+  for (int c = 0; c < NU; ++c) {
+    double acc = gc[c];
+    RCBF_UNROLL
+    for (int k = 0; k < NZ; ++k) acc = fma(v[k] * ninv[k], (double)rr[k][c], acc);
+    grad_a[c] = (float)acc;
+  }
+}
+
 }  // namespace rcbf

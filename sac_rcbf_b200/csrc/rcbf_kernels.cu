@@ -219,65 +219,61 @@ k_cars_safe_action_bwd(const float* __restrict__ st, const float* __restrict__ a
 // ------------------------------------------------------------------------------------------------------------
 // K4, compact form: the forward saved ONE word per instance, (status << 16) | active set.  A trivial instance
 // (x = 0, no active row: ~2/3 of them) needs nothing but the clamp mask of diff_cbf_qp.py:77 -- 28 bytes of traffic,
-// a handful of instructions.  The others are compacted inside the block (so that the float64 part runs with full
-// warps), re-assembled, their multipliers / slacks rebuilt from the active set by the same float64 solve the
-// certificate ran, and pushed through the implicit-KKT backward (rcbf_backward.cuh).
-// (For a trivial instance qpth's clamped ratios d_i = 1e-8 / s_i also leak O(1e-8 / s_i) of the gradient through the
-// inactive rows; that term is dropped here.)
+// a handful of instructions.  The others are compacted inside the block (so that the second phase runs with full
+// warps), their constraint rows re-assembled, and the gradient follows from the <= NZ ACTIVE rows alone through the
+// exact active-set form of the implicit-KKT backward (safe_action_bwd_active, rcbf_backward.cuh).
+// An instance the forward could not pin to a vertex (interior-point result accepted on its residual: status
+// RCBF_OK_IPM / RCBF_MAXITER, mask 0xffff -- not observed on any test distribution) re-runs the fallback solve and the
+// dense qpth-clamp backward in a separate, non-inlined function, so that its ~250 live values do not set the register
+// allocation of the path every other instance takes.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kBwdThreads = 128;
 
 template <typename Pat, int NZ, int M>
-__device__ __forceinline__ void rebuild_saved(const Normalised<NZ, M>& nrm, const float p_diag[NZ], int meta,
-                                              float xs[NZ], float ls[M], float ss[M]) {
-  const int status = meta >> 16;
-  const uint32_t mask = (uint32_t)meta & 0xffffu;
-  double pisd[NZ];
-  float pisf[NZ];
-  pis_of<NZ, M>(p_diag, pisd, pisf);
-  if (mask != kMaskUnknown && status == RCBF_OK_CERTIFIED) {
-    const NormCert<NZ, M> cp{nrm, pisd};
-    double y[NZ], lam[M], sl[M];
-    lnp_certify<double, NormCert<NZ, M>, Pat, NZ, M>(cp, mask, kTolSlack, kTolDual, y, lam, sl);
+__device__ __forceinline__ void rebuild_saved(const Normalised<NZ, M>& nrm, const float p_diag[NZ], float xs[NZ],
+                                              float ls[M], float ss[M]) {
+  NormSolution<NZ, M> sol;
+  solve_normalised_full<Pat, NZ, M>(nrm, p_diag, false, sol);
 #pragma unroll
-    for (int j = 0; j < NZ; ++j) xs[j] = (float)(y[j] * pisd[j]);
+  for (int j = 0; j < NZ; ++j) xs[j] = (float)sol.x[j];
 #pragma unroll
-    for (int i = 0; i < M; ++i) {
-      ls[i] = (float)lam[i];
-      ss[i] = (float)sl[i];
-    }
-  } else {  // interior-point result (no vertex to rebuild from): redo the fallback solve -- practically never taken
-    NormSolution<NZ, M> sol;
-    solve_normalised_full<Pat, NZ, M>(nrm, p_diag, false, sol);
-#pragma unroll
-    for (int j = 0; j < NZ; ++j) xs[j] = (float)sol.x[j];
-#pragma unroll
-    for (int i = 0; i < M; ++i) {
-      ls[i] = (float)sol.lam[i];
-      ss[i] = (float)sol.s[i];
-    }
+  for (int i = 0; i < M; ++i) {
+    ls[i] = (float)sol.lam[i];
+    ss[i] = (float)sol.s[i];
   }
 }
 
-// phase 1 of both kernels: trivial / NaN instances are finished, the others are listed (dense) in shared memory
-template <int NU>
+// phase 1 of both kernels: trivial / NaN instances are finished, the others are listed (dense) in shared memory;
+// P^-1/2 in float64 (two IEEE double operations per entry) is computed once per block
+template <int NU, int NZ>
 __device__ __forceinline__ int bwd_classify(const float* __restrict__ ac, const int32_t* __restrict__ meta,
                                             const float* __restrict__ gout, int64_t n, const float* u_min,
-                                            const float* u_max, float* __restrict__ grad_a, int* list) {
+                                            const float* u_max, const float* p_diag, float* __restrict__ grad_a,
+                                            int* list, double* s_pis) {
   __shared__ int s_count;
   if (threadIdx.x == 0) s_count = 0;
+  if (threadIdx.x >= 32 && threadIdx.x < 32 + NZ) s_pis[threadIdx.x - 32] = 1.0 / sqrt((double)p_diag[threadIdx.x - 32]);
   __syncthreads();
   const int64_t i = (int64_t)blockIdx.x * kBwdThreads + threadIdx.x;
   bool heavy = false;
   if (i < n) {
     const int status = __ldg(meta + i) >> 16;
     if (status == RCBF_OK_TRIVIAL || status == RCBF_NAN) {
+      float v[NU], g[NU];
+      if (NU == 2) {
+        const float2 a2 = __ldg(reinterpret_cast<const float2*>(ac) + i), g2 = __ldg(reinterpret_cast<const float2*>(gout) + i);
+        v[0] = a2.x; v[NU - 1] = a2.y; g[0] = g2.x; g[NU - 1] = g2.y;
+      } else {
+#pragma unroll
+        for (int c = 0; c < NU; ++c) { v[c] = __ldg(ac + i * NU + c); g[c] = __ldg(gout + i * NU + c); }
+      }
 #pragma unroll
       for (int c = 0; c < NU; ++c) {
-        const float v = __ldg(ac + i * NU + c) + 0.f;
-        const float g = __ldg(gout + i * NU + c);
-        grad_a[i * NU + c] = (status == RCBF_NAN) ? NAN : ((v >= u_min[c] && v <= u_max[c]) ? g : 0.f);
+        const float vv = v[c] + 0.f;
+        g[c] = (status == RCBF_NAN) ? NAN : ((vv >= u_min[c] && vv <= u_max[c]) ? g[c] : 0.f);
       }
+      if (NU == 2) reinterpret_cast<float2*>(grad_a)[i] = make_float2(g[0], g[NU - 1]);
+      else grad_a[i] = g[0];
     } else {
       heavy = true;
     }
@@ -291,10 +287,11 @@ __device__ __forceinline__ int bwd_classify(const float* __restrict__ ac, const 
   return s_count;
 }
 
-__device__ __forceinline__ void unicycle_bwd_heavy(const float* __restrict__ st, const float* __restrict__ ac,
-                                                   const float* __restrict__ mu, const float* __restrict__ sg,
-                                                   const int32_t* __restrict__ meta, const float* __restrict__ gout,
-                                                   int64_t i, const UnicycleParams& p, float* __restrict__ grad_a) {
+__device__ __noinline__ void unicycle_bwd_dense(const float* __restrict__ st, const float* __restrict__ ac,
+                                                const float* __restrict__ mu, const float* __restrict__ sg,
+                                                const float* __restrict__ gout, int64_t i, const UnicycleParams* pp,
+                                                float* __restrict__ grad_a) {
+  const UnicycleParams& p = *pp;
   float s[3], u[2], m[3], g[3], xs[3], ls[kUniM], ss[kUniM], go[2];
   load_row<3>(st, i, s);
   load_row<2>(ac, i, u);
@@ -305,7 +302,7 @@ __device__ __forceinline__ void unicycle_bwd_heavy(const float* __restrict__ st,
   assemble_unicycle(p, s, u, m, g, raw);
   Normalised<kUniNZ, kUniM> nrm;
   normalise_rows<UniPat, kUniNZ, kUniM>(raw.G, raw.h, nrm);
-  rebuild_saved<UniPat, kUniNZ, kUniM>(nrm, p.p_diag, __ldg(meta + i), xs, ls, ss);
+  rebuild_saved<UniPat, kUniNZ, kUniM>(nrm, p.p_diag, xs, ls, ss);
   float r[kUniM][2];
 #pragma unroll
   for (int k = 0; k < kUniHaz; ++k) {
@@ -324,33 +321,52 @@ __device__ __forceinline__ void unicycle_bwd_heavy(const float* __restrict__ st,
   store_row<2>(grad_a, i, ga);
 }
 
-// one launch (small batches): the block's own non-trivial instances, compacted to its first threads
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, 4)
 k_unicycle_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
                                 const float* __restrict__ sg, const int32_t* __restrict__ meta,
-                                const float* __restrict__ gout, int64_t n, UnicycleParams p, float* __restrict__ grad_a) {
+                                const float* __restrict__ gout, int64_t n, const __grid_constant__ UnicycleParams p,
+                                float* __restrict__ grad_a) {
   __shared__ int list[kBwdThreads];
-  const int count = bwd_classify<2>(ac, meta, gout, n, p.u_min, p.u_max, grad_a, list);
+  __shared__ double s_pis[kUniNZ];
+  const int count = bwd_classify<2, kUniNZ>(ac, meta, gout, n, p.u_min, p.u_max, p.p_diag, grad_a, list, s_pis);
   if ((int)threadIdx.x >= count) return;
-  unicycle_bwd_heavy(st, ac, mu, sg, meta, gout, (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x], p, grad_a);
+  const int64_t i = (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x];
+  const int mt = __ldg(meta + i);
+  if ((mt >> 16) != RCBF_OK_CERTIFIED || (mt & 0xffff) == (int)kMaskUnknown) {
+    unicycle_bwd_dense(st, ac, mu, sg, gout, i, &p, grad_a);
+    return;
+  }
+  float s[3], u[2], m[3], g[3], go[2];
+  load_row<3>(st, i, s);
+  load_row<2>(ac, i, u);
+  load_row<3>(mu, i, m);
+  load_row<3>(sg, i, g);
+  load_row<2>(gout, i, go);
+  UniRaw raw;
+  assemble_unicycle(p, s, u, m, g, raw);
+  float r[kUniM][2];
+#pragma unroll
+  for (int k = 0; k < kUniHaz; ++k) {
+    r[k][0] = raw.Lg[k][0];
+    r[k][1] = raw.Lg[k][1];
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {  // h = u_max - a_c ; h = -u_min + a_c
+    r[kUniHaz + 2 * c][0] = (c == 0) ? -1.f : 0.f;
+    r[kUniHaz + 2 * c][1] = (c == 1) ? -1.f : 0.f;
+    r[kUniHaz + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f;
+    r[kUniHaz + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
+  }
+  const double pis[kUniNZ] = {s_pis[0], s_pis[1], s_pis[2]};
+  float ga[2];
+  safe_action_bwd_active<UniPat, kUniNZ, kUniM, 2>(raw.G, raw.h, r, pis, (uint32_t)mt & 0xffffu, u, p.u_min, p.u_max, go, ga);
+  store_row<2>(grad_a, i, ga);
 }
 
-// two launches (large batches): k_bwd_classify lists the non-trivial instances of the WHOLE batch in global memory
-// (one atomic per block), this kernel walks the list with full blocks
-__global__ void __launch_bounds__(kBwdThreads)
-k_unicycle_safe_action_bwd_list(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
-                                const float* __restrict__ sg, const int32_t* __restrict__ meta,
-                                const float* __restrict__ gout, UnicycleParams p, float* __restrict__ grad_a,
-                                const int32_t* __restrict__ list /* [0] = count, entries from [4] */) {
-  const int count = list[0];
-  for (int k = blockIdx.x * kBwdThreads + threadIdx.x; k < count; k += gridDim.x * kBwdThreads)
-    unicycle_bwd_heavy(st, ac, mu, sg, meta, gout, (int64_t)list[4 + k], p, grad_a);
-}
-
-__device__ __forceinline__ void cars_bwd_heavy(const float* __restrict__ st, const float* __restrict__ ac,
-                                               const float* __restrict__ sg, const int32_t* __restrict__ meta,
-                                               const float* __restrict__ gout, int64_t i, const CarsParams& p,
-                                               float* __restrict__ grad_a) {
+__device__ __noinline__ void cars_bwd_dense(const float* __restrict__ st, const float* __restrict__ ac,
+                                            const float* __restrict__ sg, const float* __restrict__ gout, int64_t i,
+                                            const CarsParams* pp, float* __restrict__ grad_a) {
+  const CarsParams& p = *pp;
   float s[10], g[10], xs[2], ls[kCarsM], ss[kCarsM];
   load_row<10>(st, i, s);
   load_row<10>(sg, i, g);
@@ -360,7 +376,7 @@ __device__ __forceinline__ void cars_bwd_heavy(const float* __restrict__ st, con
   assemble_cars(p, s, u, g, raw);
   Normalised<kCarsNZ, kCarsM> nrm;
   normalise_rows<CarsPat, kCarsNZ, kCarsM>(raw.G, raw.h, nrm);
-  rebuild_saved<CarsPat, kCarsNZ, kCarsM>(nrm, p.p_diag, __ldg(meta + i), xs, ls, ss);
+  rebuild_saved<CarsPat, kCarsNZ, kCarsM>(nrm, p.p_diag, xs, ls, ss);
   float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
   float ga[1];
   const float uu[1] = {u}, gg[1] = {go}, lo[1] = {p.u_min}, hi[1] = {p.u_max};
@@ -368,58 +384,34 @@ __device__ __forceinline__ void cars_bwd_heavy(const float* __restrict__ st, con
   grad_a[i] = ga[0];
 }
 
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, 4)
 k_cars_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg,
-                            const int32_t* __restrict__ meta, const float* __restrict__ gout, int64_t n, CarsParams p,
-                            float* __restrict__ grad_a) {
+                            const int32_t* __restrict__ meta, const float* __restrict__ gout, int64_t n,
+                            const __grid_constant__ CarsParams p, float* __restrict__ grad_a) {
   __shared__ int list[kBwdThreads];
+  __shared__ double s_pis[kCarsNZ];
   const float lo[1] = {p.u_min}, hi[1] = {p.u_max};
-  const int count = bwd_classify<1>(ac, meta, gout, n, lo, hi, grad_a, list);
+  const int count = bwd_classify<1, kCarsNZ>(ac, meta, gout, n, lo, hi, p.p_diag, grad_a, list, s_pis);
   if ((int)threadIdx.x >= count) return;
-  cars_bwd_heavy(st, ac, sg, meta, gout, (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x], p, grad_a);
-}
-
-__global__ void __launch_bounds__(kBwdThreads)
-k_cars_safe_action_bwd_list(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg,
-                            const int32_t* __restrict__ meta, const float* __restrict__ gout, CarsParams p,
-                            float* __restrict__ grad_a, const int32_t* __restrict__ list) {
-  const int count = list[0];
-  for (int k = blockIdx.x * kBwdThreads + threadIdx.x; k < count; k += gridDim.x * kBwdThreads)
-    cars_bwd_heavy(st, ac, sg, meta, gout, (int64_t)list[4 + k], p, grad_a);
-}
-
-// phase 1 of the two-launch form: clamp-mask gradients of the trivial instances, global list of the others
-template <int NU>
-__global__ void __launch_bounds__(256)
-k_bwd_classify(const float* __restrict__ ac, const int32_t* __restrict__ meta, const float* __restrict__ gout, int64_t n,
-               float lo0, float hi0, float lo1, float hi1, float* __restrict__ grad_a, int32_t* __restrict__ list) {
-  __shared__ int s_count, s_base;
-  if (threadIdx.x == 0) s_count = 0;
-  __syncthreads();
-  const float u_min[2] = {lo0, lo1}, u_max[2] = {hi0, hi1};
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  bool heavy = false;
-  if (i < n) {
-    const int status = __ldg(meta + i) >> 16;
-    if (status == RCBF_OK_TRIVIAL || status == RCBF_NAN) {
-#pragma unroll
-      for (int c = 0; c < NU; ++c) {
-        const float v = __ldg(ac + i * NU + c) + 0.f;
-        const float g = __ldg(gout + i * NU + c);
-        grad_a[i * NU + c] = (status == RCBF_NAN) ? NAN : ((v >= u_min[c] && v <= u_max[c]) ? g : 0.f);
-      }
-    } else {
-      heavy = true;
-    }
+  const int64_t i = (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x];
+  const int mt = __ldg(meta + i);
+  if ((mt >> 16) != RCBF_OK_CERTIFIED || (mt & 0xffff) == (int)kMaskUnknown) {
+    cars_bwd_dense(st, ac, sg, gout, i, &p, grad_a);
+    return;
   }
-  const unsigned b = __ballot_sync(0xffffffffu, heavy);
-  int base = 0;
-  if ((threadIdx.x & 31) == 0 && b) base = atomicAdd(&s_count, __popc(b));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  __syncthreads();
-  if (threadIdx.x == 0) s_base = s_count ? atomicAdd(list, s_count) : 0;
-  __syncthreads();
-  if (heavy) list[4 + s_base + base + __popc(b & ((1u << (threadIdx.x & 31)) - 1u))] = (int32_t)i;
+  float s[10], g[10];
+  load_row<10>(st, i, s);
+  load_row<10>(sg, i, g);
+  const float u = __ldg(ac + i);
+  const float go = __ldg(gout + i);
+  CarsRaw raw;
+  assemble_cars(p, s, u, g, raw);
+  const float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
+  const double pis[kCarsNZ] = {s_pis[0], s_pis[1]};
+  float ga[1];
+  const float uu[1] = {u}, gg[1] = {go};
+  safe_action_bwd_active<CarsPat, kCarsNZ, kCarsM, 1>(raw.G, raw.h, r, pis, (uint32_t)mt & 0xffffu, uu, lo, hi, gg, ga);
+  grad_a[i] = ga[0];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -750,43 +742,22 @@ int rcbf_cars_safe_action_bwd(const float* state, const float* action, const flo
   return 0;
 }
 
-constexpr int64_t kBwdTwoLaunchMin = 32768;  // below this the single launch wins (one launch less, blocks few anyway)
-
 int rcbf_unicycle_safe_action_bwd_meta(const float* state, const float* action, const float* mean, const float* sigma,
                                        const int32_t* meta, const float* grad_out, int64_t n,
-                                       const rcbf_unicycle_params* p, float* grad_action, int32_t* scratch,
-                                       void* stream) {
+                                       const rcbf_unicycle_params* p, float* grad_action, void* stream) {
   if (n <= 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (scratch == nullptr || n < kBwdTwoLaunchMin || n > 0x7fffffffLL) {
-    k_unicycle_safe_action_bwd_meta<<<(int)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, s>>>(
-        state, action, mean, sigma, meta, grad_out, n, *p, grad_action);
-  } else {
-    cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), s);
-    k_bwd_classify<2><<<(int)((n + 255) / 256), 256, 0, s>>>(action, meta, grad_out, n, p->u_min[0], p->u_max[0],
-                                                            p->u_min[1], p->u_max[1], grad_action, scratch);
-    k_unicycle_safe_action_bwd_list<<<sm_count() * 4, kBwdThreads, 0, s>>>(state, action, mean, sigma, meta, grad_out, *p,
-                                                                           grad_action, scratch);
-  }
+  k_unicycle_safe_action_bwd_meta<<<(unsigned)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(
+      state, action, mean, sigma, meta, grad_out, n, *p, grad_action);
   RCBF_LAUNCH_CHECK();
   return 0;
 }
 
 int rcbf_cars_safe_action_bwd_meta(const float* state, const float* action, const float* sigma, const int32_t* meta,
                                    const float* grad_out, int64_t n, const rcbf_cars_params* p, float* grad_action,
-                                   int32_t* scratch, void* stream) {
+                                   void* stream) {
   if (n <= 0) return 0;
-  cudaStream_t s = (cudaStream_t)stream;
-  if (scratch == nullptr || n < kBwdTwoLaunchMin || n > 0x7fffffffLL) {
-    k_cars_safe_action_bwd_meta<<<(int)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, s>>>(
-        state, action, sigma, meta, grad_out, n, *p, grad_action);
-  } else {
-    cudaMemsetAsync(scratch, 0, 4 * sizeof(int32_t), s);
-    k_bwd_classify<1><<<(int)((n + 255) / 256), 256, 0, s>>>(action, meta, grad_out, n, p->u_min, p->u_max, 0.f, 0.f,
-                                                            grad_action, scratch);
-    k_cars_safe_action_bwd_list<<<sm_count() * 4, kBwdThreads, 0, s>>>(state, action, sigma, meta, grad_out, *p,
-                                                                       grad_action, scratch);
-  }
+  k_cars_safe_action_bwd_meta<<<(unsigned)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(
+      state, action, sigma, meta, grad_out, n, *p, grad_action);
   RCBF_LAUNCH_CHECK();
   return 0;
 }

@@ -295,17 +295,15 @@ class CBFQPLayer:
     def _backward_meta(self, st, ac, mu, sg, meta, go):
         n = st.shape[0]
         ga = torch.empty_like(ac)
-        scratch = torch.empty((n + 4,), dtype=torch.int32, device=self.device) if n >= 32768 else None
         p = self._params()
         prev = torch.cuda.current_device()
         lib, stream = self._launch_ctx()
         if self.env.dynamics_mode == 'Unicycle':
             rc = lib.rcbf_unicycle_safe_action_bwd_meta(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg),
-                                                        _lib.ptr(meta), _lib.ptr(go), n, p, _lib.ptr(ga),
-                                                        _lib.ptr(scratch), stream)
+                                                        _lib.ptr(meta), _lib.ptr(go), n, p, _lib.ptr(ga), stream)
         else:
             rc = lib.rcbf_cars_safe_action_bwd_meta(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(sg), _lib.ptr(meta),
-                                                    _lib.ptr(go), n, p, _lib.ptr(ga), _lib.ptr(scratch), stream)
+                                                    _lib.ptr(go), n, p, _lib.ptr(ga), stream)
         if prev != self.device.index:
             torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_safe_action_bwd_meta")

@@ -4,6 +4,7 @@
 // fallback: nothing in the product package loads this library, and the product fails loudly without the CUDA one.
 #include <stdint.h>
 #include "../../sac_rcbf_b200/csrc/rcbf_core.cuh"
+#include "../../sac_rcbf_b200/csrc/rcbf_backward.cuh"
 
 using namespace rcbf;
 
@@ -66,6 +67,57 @@ void hs_cars_safe_action(int64_t n, const float* st, const float* ac, const floa
     }
     status[i] = w.sol.status;
     iters[i] = w.sol.iters;
+  }
+}
+
+// gradient of get_safe_action w.r.t. the nominal action: the qpth-clamp form on the dense saved tensors (ga_dense) and the
+// exact active-set form on the certified mask alone (ga_active), both from the same forward solve
+void hs_unicycle_bwd(int64_t n, const float* st, const float* ac, const float* mu, const float* sg, const float* gout,
+                     const UnicycleParams* p, float* ga_dense, float* ga_active, int* status) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    UniSolve w;
+    float out[2];
+    unicycle_safe_action<0>(*p, st + 3 * i, ac + 2 * i, mu + 3 * i, sg + 3 * i, w, out);
+    if (w.sol.status == RCBF_PENDING) unicycle_safe_action<2>(*p, st + 3 * i, ac + 2 * i, mu + 3 * i, sg + 3 * i, w, out);
+    status[i] = (w.sol.status == RCBF_OK_CERTIFIED && w.sol.mask == kMaskUnknown) ? RCBF_OK_IPM : w.sol.status;
+    float r[kUniM][2], xs[3], ls[kUniM], ss[kUniM];
+    for (int k = 0; k < kUniHaz; ++k) { r[k][0] = w.raw.Lg[k][0]; r[k][1] = w.raw.Lg[k][1]; }
+    for (int c = 0; c < 2; ++c) {
+      r[kUniHaz + 2 * c][0] = (c == 0) ? -1.f : 0.f; r[kUniHaz + 2 * c][1] = (c == 1) ? -1.f : 0.f;
+      r[kUniHaz + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f; r[kUniHaz + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
+    }
+    for (int j = 0; j < 3; ++j) xs[j] = (float)w.sol.x[j];
+    for (int k = 0; k < kUniM; ++k) { ls[k] = (float)w.sol.lam[k]; ss[k] = (float)w.sol.s[k]; }
+    safe_action_bwd<kUniNZ, kUniM, 2>(w.nrm, w.raw.G, w.raw.h, r, p->p_diag, xs, ls, ss, ac + 2 * i, p->u_min, p->u_max,
+                                      gout + 2 * i, ga_dense + 2 * i);
+    double pisd[3]; float pisf[3];
+    pis_of<kUniNZ, kUniM>(p->p_diag, pisd, pisf);
+    safe_action_bwd_active<UniPat, kUniNZ, kUniM, 2>(w.raw.G, w.raw.h, r, pisd, w.sol.mask == kMaskUnknown ? 0u : w.sol.mask,
+                                                     ac + 2 * i, p->u_min, p->u_max, gout + 2 * i, ga_active + 2 * i);
+  }
+}
+
+void hs_cars_bwd(int64_t n, const float* st, const float* ac, const float* sg, const float* gout, const CarsParams* p,
+                 float* ga_dense, float* ga_active, int* status) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    CarsSolve w;
+    float out;
+    cars_safe_action<0>(*p, st + 10 * i, ac[i], sg + 10 * i, w, &out);
+    if (w.sol.status == RCBF_PENDING) cars_safe_action<2>(*p, st + 10 * i, ac[i], sg + 10 * i, w, &out);
+    status[i] = (w.sol.status == RCBF_OK_CERTIFIED && w.sol.mask == kMaskUnknown) ? RCBF_OK_IPM : w.sol.status;
+    float r[kCarsM][1] = {{w.raw.Lg[0]}, {w.raw.Lg[1]}, {-1.f}, {1.f}};
+    float xs[2], ls[kCarsM], ss[kCarsM];
+    for (int j = 0; j < 2; ++j) xs[j] = (float)w.sol.x[j];
+    for (int k = 0; k < kCarsM; ++k) { ls[k] = (float)w.sol.lam[k]; ss[k] = (float)w.sol.s[k]; }
+    const float lo[1] = {p->u_min}, hi[1] = {p->u_max};
+    safe_action_bwd<kCarsNZ, kCarsM, 1>(w.nrm, w.raw.G, w.raw.h, r, p->p_diag, xs, ls, ss, ac + i, lo, hi, gout + i,
+                                        ga_dense + i);
+    double pisd[2]; float pisf[2];
+    pis_of<kCarsNZ, kCarsM>(p->p_diag, pisd, pisf);
+    safe_action_bwd_active<CarsPat, kCarsNZ, kCarsM, 1>(w.raw.G, w.raw.h, r, pisd, w.sol.mask == kMaskUnknown ? 0u : w.sol.mask,
+                                                        ac + i, lo, hi, gout + i, ga_active + i);
   }
 }
 

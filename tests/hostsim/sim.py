@@ -12,8 +12,9 @@ _lib = None
 def build(force=False, contract="off"):
     so = os.path.join(HERE, "libhostsim.so")
     src = os.path.join(HERE, "hostsim.cpp")
-    core = os.path.join(HERE, "..", "..", "sac_rcbf_b200", "csrc", "rcbf_core.cuh")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(core)):
+    csrc = os.path.join(HERE, "..", "..", "sac_rcbf_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("rcbf_core.cuh", "rcbf_backward.cuh", "rcbf_f2.cuh")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-march=native", "-ffp-contract=" + contract, "-fopenmp", "-shared",
                                "-fPIC", "-x", "c++", src, "-o", so])
     return so
@@ -56,3 +57,22 @@ def cars_safe_action(st, ac, sg, params, mode=0):
                               _p(o["Gn"], C.c_float), _p(o["hn"], C.c_float), _p(o["G"], C.c_float),
                               _p(o["h"], C.c_float), C.c_int(mode))
     return o
+
+
+def unicycle_bwd(st, ac, mu, sg, gout, params):
+    """(grad_action of the qpth-clamp form on dense saved tensors, of the exact active-set form on the mask, status)."""
+    n = st.shape[0]
+    st, ac, mu, sg, gout = (np.ascontiguousarray(a, np.float32) for a in (st, ac, mu, sg, gout))
+    gd, ga, status = np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+    lib().hs_unicycle_bwd(C.c_int64(n), _p(st, C.c_float), _p(ac, C.c_float), _p(mu, C.c_float), _p(sg, C.c_float),
+                          _p(gout, C.c_float), C.byref(params), _p(gd, C.c_float), _p(ga, C.c_float), _p(status, C.c_int))
+    return gd, ga, status
+
+
+def cars_bwd(st, ac, sg, gout, params):
+    n = st.shape[0]
+    st, ac, sg, gout = (np.ascontiguousarray(a, np.float32) for a in (st, ac, sg, gout))
+    gd, ga, status = np.zeros((n, 1), np.float32), np.zeros((n, 1), np.float32), np.zeros(n, np.int32)
+    lib().hs_cars_bwd(C.c_int64(n), _p(st, C.c_float), _p(ac, C.c_float), _p(sg, C.c_float), _p(gout, C.c_float),
+                      C.byref(params), _p(gd, C.c_float), _p(ga, C.c_float), _p(status, C.c_int))
+    return gd, ga, status
