@@ -14,6 +14,7 @@
 #include "rcbf_core.cuh"
 #include "rcbf_dynamics.cuh"
 #include "rcbf_generic.cuh"
+#include "rcbf_tma.cuh"
 
 using namespace rcbf;
 
@@ -22,7 +23,7 @@ namespace {
 constexpr int kThreads = 128;
 
 inline int grid_for(int64_t n) { return (int)((n + kThreads - 1) / kThreads); }
-inline int sm_count() {  // SMs of the current device (cached per device)
+[[maybe_unused]] inline int sm_count() {  // SMs of the current device (cached per device)
   static int cached[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -287,131 +288,255 @@ __device__ __forceinline__ int bwd_classify(const float* __restrict__ ac, const 
   return s_count;
 }
 
-__device__ __noinline__ void unicycle_bwd_dense(const float* __restrict__ st, const float* __restrict__ ac,
-                                                const float* __restrict__ mu, const float* __restrict__ sg,
-                                                const float* __restrict__ gout, int64_t i, const UnicycleParams* pp,
-                                                float* __restrict__ grad_a) {
-  const UnicycleParams& p = *pp;
-  float s[3], u[2], m[3], g[3], xs[3], ls[kUniM], ss[kUniM], go[2];
-  load_row<3>(st, i, s);
-  load_row<2>(ac, i, u);
-  load_row<3>(mu, i, m);
-  load_row<3>(sg, i, g);
-  load_row<2>(gout, i, go);
-  UniRaw raw;
-  assemble_unicycle(p, s, u, m, g, raw);
-  Normalised<kUniNZ, kUniM> nrm;
-  normalise_rows<UniPat, kUniNZ, kUniM>(raw.G, raw.h, nrm);
-  rebuild_saved<UniPat, kUniNZ, kUniM>(nrm, p.p_diag, xs, ls, ss);
-  float r[kUniM][2];
+// per-environment pieces of the compact backward: row widths, the lean (active-set) gradient of one instance from its
+// input rows (global or shared memory) and the out-of-line dense fallback from global memory
+struct UniBwd {
+  using Params = UnicycleParams;
+  static constexpr int NU = 2, NZ = kUniNZ, SF = 3, MF = 3;  // action / state / mean row widths (sigma row = state row)
+  static __device__ __forceinline__ const float* u_min(const Params& p) { return p.u_min; }
+  static __device__ __forceinline__ const float* u_max(const Params& p) { return p.u_max; }
+  static __device__ __forceinline__ void lean(const float* __restrict__ sr, const float* __restrict__ ur,
+                                              const float* __restrict__ mr, const float* __restrict__ gr,
+                                              const float* __restrict__ gor, uint32_t mask, const Params& p,
+                                              const double* pis_s, float* ga) {
+    const float s[3] = {sr[0], sr[1], sr[2]}, u[2] = {ur[0], ur[1]}, m[3] = {mr[0], mr[1], mr[2]};
+    const float g[3] = {gr[0], gr[1], gr[2]}, go[2] = {gor[0], gor[1]};
+    UniRaw raw;
+    assemble_unicycle(p, s, u, m, g, raw);
+    float r[kUniM][2];
 #pragma unroll
-  for (int k = 0; k < kUniHaz; ++k) {
-    r[k][0] = raw.Lg[k][0];
-    r[k][1] = raw.Lg[k][1];
-  }
+    for (int k = 0; k < kUniHaz; ++k) {
+      r[k][0] = raw.Lg[k][0];
+      r[k][1] = raw.Lg[k][1];
+    }
 #pragma unroll
-  for (int c = 0; c < 2; ++c) {  // h = u_max - a_c ; h = -u_min + a_c
-    r[kUniHaz + 2 * c][0] = (c == 0) ? -1.f : 0.f;
-    r[kUniHaz + 2 * c][1] = (c == 1) ? -1.f : 0.f;
-    r[kUniHaz + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f;
-    r[kUniHaz + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
+    for (int c = 0; c < 2; ++c) {  // h = u_max - a_c ; h = -u_min + a_c
+      r[kUniHaz + 2 * c][0] = (c == 0) ? -1.f : 0.f;
+      r[kUniHaz + 2 * c][1] = (c == 1) ? -1.f : 0.f;
+      r[kUniHaz + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f;
+      r[kUniHaz + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
+    }
+    const double pis[kUniNZ] = {pis_s[0], pis_s[1], pis_s[2]};
+    safe_action_bwd_active<UniPat, kUniNZ, kUniM, 2>(raw.G, raw.h, r, pis, mask, u, p.u_min, p.u_max, go, ga);
   }
-  float ga[2];
-  safe_action_bwd<kUniNZ, kUniM, 2>(nrm, raw.G, raw.h, r, p.p_diag, xs, ls, ss, u, p.u_min, p.u_max, go, ga);
-  store_row<2>(grad_a, i, ga);
+  static __device__ __noinline__ void dense(const float* __restrict__ st, const float* __restrict__ ac,
+                                            const float* __restrict__ mu, const float* __restrict__ sg,
+                                            const float* __restrict__ gout, int64_t i, const Params* pp, float* ga) {
+    const Params& p = *pp;
+    float s[3], u[2], m[3], g[3], xs[3], ls[kUniM], ss[kUniM], go[2];
+    load_row<3>(st, i, s);
+    load_row<2>(ac, i, u);
+    load_row<3>(mu, i, m);
+    load_row<3>(sg, i, g);
+    load_row<2>(gout, i, go);
+    UniRaw raw;
+    assemble_unicycle(p, s, u, m, g, raw);
+    Normalised<kUniNZ, kUniM> nrm;
+    normalise_rows<UniPat, kUniNZ, kUniM>(raw.G, raw.h, nrm);
+    rebuild_saved<UniPat, kUniNZ, kUniM>(nrm, p.p_diag, xs, ls, ss);
+    float r[kUniM][2];
+#pragma unroll
+    for (int k = 0; k < kUniHaz; ++k) {
+      r[k][0] = raw.Lg[k][0];
+      r[k][1] = raw.Lg[k][1];
+    }
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      r[kUniHaz + 2 * c][0] = (c == 0) ? -1.f : 0.f;
+      r[kUniHaz + 2 * c][1] = (c == 1) ? -1.f : 0.f;
+      r[kUniHaz + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f;
+      r[kUniHaz + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
+    }
+    safe_action_bwd<kUniNZ, kUniM, 2>(nrm, raw.G, raw.h, r, p.p_diag, xs, ls, ss, u, p.u_min, p.u_max, go, ga);
+  }
+};
+
+struct CarsBwd {
+  using Params = CarsParams;
+  static constexpr int NU = 1, NZ = kCarsNZ, SF = 10, MF = 0;  // (the layer does not read the disturbance mean, :299)
+  static __device__ __forceinline__ const float* u_min(const Params& p) { return &p.u_min; }
+  static __device__ __forceinline__ const float* u_max(const Params& p) { return &p.u_max; }
+  static __device__ __forceinline__ void lean(const float* __restrict__ sr, const float* __restrict__ ur,
+                                              const float* __restrict__, const float* __restrict__ gr,
+                                              const float* __restrict__ gor, uint32_t mask, const Params& p,
+                                              const double* pis_s, float* ga) {
+    float s[10], g[10];
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      s[j] = sr[j];
+      g[j] = gr[j];
+    }
+    const float u = ur[0];
+    CarsRaw raw;
+    assemble_cars(p, s, u, g, raw);
+    const float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
+    const double pis[kCarsNZ] = {pis_s[0], pis_s[1]};
+    const float uu[1] = {u}, gg[1] = {gor[0]}, lo[1] = {p.u_min}, hi[1] = {p.u_max};
+    safe_action_bwd_active<CarsPat, kCarsNZ, kCarsM, 1>(raw.G, raw.h, r, pis, mask, uu, lo, hi, gg, ga);
+  }
+  static __device__ __noinline__ void dense(const float* __restrict__ st, const float* __restrict__ ac,
+                                            const float* __restrict__, const float* __restrict__ sg,
+                                            const float* __restrict__ gout, int64_t i, const Params* pp, float* ga) {
+    const Params& p = *pp;
+    float s[10], g[10], xs[2], ls[kCarsM], ss[kCarsM];
+    load_row<10>(st, i, s);
+    load_row<10>(sg, i, g);
+    const float u = __ldg(ac + i);
+    const float go = __ldg(gout + i);
+    CarsRaw raw;
+    assemble_cars(p, s, u, g, raw);
+    Normalised<kCarsNZ, kCarsM> nrm;
+    normalise_rows<CarsPat, kCarsNZ, kCarsM>(raw.G, raw.h, nrm);
+    rebuild_saved<CarsPat, kCarsNZ, kCarsM>(nrm, p.p_diag, xs, ls, ss);
+    const float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
+    const float uu[1] = {u}, gg[1] = {go}, lo[1] = {p.u_min}, hi[1] = {p.u_max};
+    safe_action_bwd<kCarsNZ, kCarsM, 1>(nrm, raw.G, raw.h, r, p.p_diag, xs, ls, ss, uu, lo, hi, gg, ga);
+  }
+};
+
+__device__ __forceinline__ bool bwd_is_vertex(int mt) {
+  return (mt >> 16) == RCBF_OK_CERTIFIED && (mt & 0xffff) != (int)kMaskUnknown;
 }
 
+// generic form (any alignment, any n): one instance per thread, rows read from global memory
+template <class B>
 __global__ void __launch_bounds__(kBwdThreads, 4)
-k_unicycle_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
-                                const float* __restrict__ sg, const int32_t* __restrict__ meta,
-                                const float* __restrict__ gout, int64_t n, const __grid_constant__ UnicycleParams p,
-                                float* __restrict__ grad_a) {
+k_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
+                       const float* __restrict__ sg, const int32_t* __restrict__ meta, const float* __restrict__ gout,
+                       int64_t n, const __grid_constant__ typename B::Params p, float* __restrict__ grad_a) {
   __shared__ int list[kBwdThreads];
-  __shared__ double s_pis[kUniNZ];
-  const int count = bwd_classify<2, kUniNZ>(ac, meta, gout, n, p.u_min, p.u_max, p.p_diag, grad_a, list, s_pis);
+  __shared__ double s_pis[B::NZ];
+  const int count = bwd_classify<B::NU, B::NZ>(ac, meta, gout, n, B::u_min(p), B::u_max(p), p.p_diag, grad_a, list, s_pis);
   if ((int)threadIdx.x >= count) return;
   const int64_t i = (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x];
   const int mt = __ldg(meta + i);
-  if ((mt >> 16) != RCBF_OK_CERTIFIED || (mt & 0xffff) == (int)kMaskUnknown) {
-    unicycle_bwd_dense(st, ac, mu, sg, gout, i, &p, grad_a);
-    return;
-  }
-  float s[3], u[2], m[3], g[3], go[2];
-  load_row<3>(st, i, s);
-  load_row<2>(ac, i, u);
-  load_row<3>(mu, i, m);
-  load_row<3>(sg, i, g);
-  load_row<2>(gout, i, go);
-  UniRaw raw;
-  assemble_unicycle(p, s, u, m, g, raw);
-  float r[kUniM][2];
-#pragma unroll
-  for (int k = 0; k < kUniHaz; ++k) {
-    r[k][0] = raw.Lg[k][0];
-    r[k][1] = raw.Lg[k][1];
-  }
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {  // h = u_max - a_c ; h = -u_min + a_c
-    r[kUniHaz + 2 * c][0] = (c == 0) ? -1.f : 0.f;
-    r[kUniHaz + 2 * c][1] = (c == 1) ? -1.f : 0.f;
-    r[kUniHaz + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f;
-    r[kUniHaz + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
-  }
-  const double pis[kUniNZ] = {s_pis[0], s_pis[1], s_pis[2]};
-  float ga[2];
-  safe_action_bwd_active<UniPat, kUniNZ, kUniM, 2>(raw.G, raw.h, r, pis, (uint32_t)mt & 0xffffu, u, p.u_min, p.u_max, go, ga);
-  store_row<2>(grad_a, i, ga);
+  float ga[B::NU];
+  if (bwd_is_vertex(mt))
+    B::lean(st + i * B::SF, ac + i * B::NU, mu + i * B::MF, sg + i * B::SF, gout + i * B::NU, (uint32_t)mt & 0xffffu, p, s_pis, ga);
+  else
+    B::dense(st, ac, mu, sg, gout, i, &p, ga);
+  store_row<B::NU>(grad_a, i, ga);
 }
 
-__device__ __noinline__ void cars_bwd_dense(const float* __restrict__ st, const float* __restrict__ ac,
-                                            const float* __restrict__ sg, const float* __restrict__ gout, int64_t i,
-                                            const CarsParams* pp, float* __restrict__ grad_a) {
-  const CarsParams& p = *pp;
-  float s[10], g[10], xs[2], ls[kCarsM], ss[kCarsM];
-  load_row<10>(st, i, s);
-  load_row<10>(sg, i, g);
-  const float u = __ldg(ac + i);
-  const float go = __ldg(gout + i);
-  CarsRaw raw;
-  assemble_cars(p, s, u, g, raw);
-  Normalised<kCarsNZ, kCarsM> nrm;
-  normalise_rows<CarsPat, kCarsNZ, kCarsM>(raw.G, raw.h, nrm);
-  rebuild_saved<CarsPat, kCarsNZ, kCarsM>(nrm, p.p_diag, xs, ls, ss);
-  float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
-  float ga[1];
-  const float uu[1] = {u}, gg[1] = {go}, lo[1] = {p.u_min}, hi[1] = {p.u_max};
-  safe_action_bwd<kCarsNZ, kCarsM, 1>(nrm, raw.G, raw.h, r, p.p_diag, xs, ls, ss, uu, lo, hi, gg, ga);
-  grad_a[i] = ga[0];
-}
+// tile form (every array base 16-byte aligned; full tiles of kBwdTile instances): the rows of a tile are contiguous
+// spans, so ONE thread fetches all of them with six cp.async.bulk copies (TMA, mbarrier completion) and nobody issues
+// a global load; several resident blocks per SM overlap one tile's fetch with another tile's arithmetic.  Phase 1
+// finishes the trivial instances in shared memory and lists the others; phase 2 runs the listed instances in chunks of
+// 32 per warp from their shared-memory rows; the gradient tile (written in place of grad_out's) leaves by coalesced
+// 128-bit stores.
+constexpr int kBwdTile = 512;
 
+template <class B>
+struct alignas(16) BwdTileSmem {
+  uint64_t bar;
+  int count;
+  int pad;
+  double pis[4];
+  int meta[kBwdTile];
+  int list[kBwdTile];
+  float ac[kBwdTile * B::NU];
+  float go[kBwdTile * B::NU];
+  float st[kBwdTile * B::SF];
+  float sg[kBwdTile * B::SF];
+  float mu[kBwdTile * (B::MF ? B::MF : 1)];
+};
+
+template <class B>
 __global__ void __launch_bounds__(kBwdThreads, 4)
-k_cars_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ sg,
-                            const int32_t* __restrict__ meta, const float* __restrict__ gout, int64_t n,
-                            const __grid_constant__ CarsParams p, float* __restrict__ grad_a) {
-  __shared__ int list[kBwdThreads];
-  __shared__ double s_pis[kCarsNZ];
-  const float lo[1] = {p.u_min}, hi[1] = {p.u_max};
-  const int count = bwd_classify<1, kCarsNZ>(ac, meta, gout, n, lo, hi, p.p_diag, grad_a, list, s_pis);
-  if ((int)threadIdx.x >= count) return;
-  const int64_t i = (int64_t)blockIdx.x * kBwdThreads + list[threadIdx.x];
-  const int mt = __ldg(meta + i);
-  if ((mt >> 16) != RCBF_OK_CERTIFIED || (mt & 0xffff) == (int)kMaskUnknown) {
-    cars_bwd_dense(st, ac, sg, gout, i, &p, grad_a);
-    return;
+k_safe_action_bwd_tile(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
+                       const float* __restrict__ sg, const int32_t* __restrict__ meta, const float* __restrict__ gout,
+                       const __grid_constant__ typename B::Params p, float* __restrict__ grad_a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  BwdTileSmem<B>& sh = *reinterpret_cast<BwdTileSmem<B>*>(smem_raw);
+  constexpr int NU = B::NU;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t i0 = (int64_t)blockIdx.x * kBwdTile;
+  if (tid == 0) {
+    mbar_init(&sh.bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    constexpr uint32_t kBytes = kBwdTile * 4u * (1 + 2 * NU + 2 * B::SF + B::MF);
+    mbar_expect_tx(&sh.bar, kBytes);
+    bulk_g2s(sh.meta, meta + i0, kBwdTile * 4, &sh.bar);
+    bulk_g2s(sh.ac, ac + i0 * NU, kBwdTile * 4 * NU, &sh.bar);
+    bulk_g2s(sh.go, gout + i0 * NU, kBwdTile * 4 * NU, &sh.bar);
+    bulk_g2s(sh.st, st + i0 * B::SF, kBwdTile * 4 * B::SF, &sh.bar);
+    bulk_g2s(sh.sg, sg + i0 * B::SF, kBwdTile * 4 * B::SF, &sh.bar);
+    if (B::MF) bulk_g2s(sh.mu, mu + i0 * B::MF, kBwdTile * 4 * B::MF, &sh.bar);
+    sh.count = 0;
   }
-  float s[10], g[10];
-  load_row<10>(st, i, s);
-  load_row<10>(sg, i, g);
-  const float u = __ldg(ac + i);
-  const float go = __ldg(gout + i);
-  CarsRaw raw;
-  assemble_cars(p, s, u, g, raw);
-  const float r[kCarsM][1] = {{raw.Lg[0]}, {raw.Lg[1]}, {-1.f}, {1.f}};
-  const double pis[kCarsNZ] = {s_pis[0], s_pis[1]};
-  float ga[1];
-  const float uu[1] = {u}, gg[1] = {go};
-  safe_action_bwd_active<CarsPat, kCarsNZ, kCarsM, 1>(raw.G, raw.h, r, pis, (uint32_t)mt & 0xffffu, uu, lo, hi, gg, ga);
-  grad_a[i] = ga[0];
+  if (tid >= 32 && tid < 32 + B::NZ) sh.pis[tid - 32] = 1.0 / sqrt((double)p.p_diag[tid - 32]);
+  __syncthreads();
+  mbar_wait(&sh.bar, 0);
+  const float* lo = B::u_min(p);
+  const float* hi = B::u_max(p);
+  // phase 1
+#pragma unroll
+  for (int q = 0; q < kBwdTile / kBwdThreads; ++q) {
+    const int idx = q * kBwdThreads + tid;
+    const int status = sh.meta[idx] >> 16;
+    const bool heavy = !(status == RCBF_OK_TRIVIAL || status == RCBF_NAN);
+    if (!heavy) {
+#pragma unroll
+      for (int c = 0; c < NU; ++c) {
+        const float vv = sh.ac[idx * NU + c] + 0.f;
+        const float g = sh.go[idx * NU + c];
+        sh.go[idx * NU + c] = (status == RCBF_NAN) ? NAN : ((vv >= lo[c] && vv <= hi[c]) ? g : 0.f);
+      }
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, heavy);
+    int base = 0;
+    if (lane == 0 && b) base = atomicAdd(&sh.count, __popc(b));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (heavy) sh.list[base + __popc(b & ((1u << lane) - 1u))] = idx;
+  }
+  __syncthreads();
+  // phase 2
+  const int count = sh.count;
+  for (int k = tid; k < count; k += kBwdThreads) {
+    const int idx = sh.list[k];
+    const int mt = sh.meta[idx];
+    float ga[NU];
+    if (bwd_is_vertex(mt))
+      B::lean(sh.st + idx * B::SF, sh.ac + idx * NU, sh.mu + idx * B::MF, sh.sg + idx * B::SF, sh.go + idx * NU,
+              (uint32_t)mt & 0xffffu, p, sh.pis, ga);
+    else
+      B::dense(st, ac, mu, sg, gout, i0 + idx, &p, ga);
+#pragma unroll
+    for (int c = 0; c < NU; ++c) sh.go[idx * NU + c] = ga[c];
+  }
+  __syncthreads();
+  float4* dst = reinterpret_cast<float4*>(grad_a + i0 * NU);
+  const float4* src = reinterpret_cast<const float4*>(sh.go);
+#pragma unroll
+  for (int w = tid; w < kBwdTile * NU / 4; w += kBwdThreads) dst[w] = src[w];
+}
+
+template <class B>
+int launch_bwd_meta(const float* st, const float* ac, const float* mu, const float* sg, const int32_t* meta,
+                    const float* gout, int64_t n, const typename B::Params& p, float* grad_a, cudaStream_t s) {
+  auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  int64_t done = 0;
+  if (n >= 4 * kBwdTile && ok16(st) && ok16(ac) && (B::MF == 0 || ok16(mu)) && ok16(sg) && ok16(meta) && ok16(gout) &&
+      ok16(grad_a)) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is per function AND per device
+    if (!attr_set[dev & 63]) {
+      cudaFuncSetAttribute(k_safe_action_bwd_tile<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdTileSmem<B>));
+      attr_set[dev & 63] = true;
+    }
+    const int64_t ntiles = n / kBwdTile;
+    k_safe_action_bwd_tile<B><<<(unsigned)ntiles, kBwdThreads, sizeof(BwdTileSmem<B>), s>>>(st, ac, mu, sg, meta, gout, p, grad_a);
+    done = ntiles * kBwdTile;
+  }
+  if (done < n) {
+    const int64_t m = n - done;
+    k_safe_action_bwd_meta<B><<<(unsigned)((m + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, s>>>(
+        st + done * B::SF, ac + done * B::NU, B::MF ? mu + done * B::MF : mu, sg + done * B::SF, meta + done,
+        gout + done * B::NU, m, p, grad_a + done * B::NU);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -746,20 +871,14 @@ int rcbf_unicycle_safe_action_bwd_meta(const float* state, const float* action, 
                                        const int32_t* meta, const float* grad_out, int64_t n,
                                        const rcbf_unicycle_params* p, float* grad_action, void* stream) {
   if (n <= 0) return 0;
-  k_unicycle_safe_action_bwd_meta<<<(unsigned)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(
-      state, action, mean, sigma, meta, grad_out, n, *p, grad_action);
-  RCBF_LAUNCH_CHECK();
-  return 0;
+  return launch_bwd_meta<UniBwd>(state, action, mean, sigma, meta, grad_out, n, *p, grad_action, (cudaStream_t)stream);
 }
 
 int rcbf_cars_safe_action_bwd_meta(const float* state, const float* action, const float* sigma, const int32_t* meta,
                                    const float* grad_out, int64_t n, const rcbf_cars_params* p, float* grad_action,
                                    void* stream) {
   if (n <= 0) return 0;
-  k_cars_safe_action_bwd_meta<<<(unsigned)((n + kBwdThreads - 1) / kBwdThreads), kBwdThreads, 0, (cudaStream_t)stream>>>(
-      state, action, sigma, meta, grad_out, n, *p, grad_action);
-  RCBF_LAUNCH_CHECK();
-  return 0;
+  return launch_bwd_meta<CarsBwd>(state, action, nullptr, sigma, meta, grad_out, n, *p, grad_action, (cudaStream_t)stream);
 }
 
 int rcbf_qp_solve(const double* Q, const double* p, const double* G, const double* h, int64_t n, int nz, int m,

@@ -424,6 +424,43 @@ def test_gradient_vs_oracle_autograd(request, mode):
     assert torch.equal(out2, out.detach())
 
 
+@pytest.mark.parametrize("mode", ["Unicycle", "SimulatedCars"])
+def test_gradient_tile_kernel_paths(request, mode):
+    """The compact backward at a size that takes the TMA tile kernel (full 512-instance tiles) plus a ragged tail:
+    bit-identical to the generic one-instance-per-thread kernel (reached through a 4-byte-misaligned view of the same
+    data), within GRAD_TOL of the dense qpth-clamp backward on saved x / lam / slack, and exactly the clamp mask on the
+    trivial instances."""
+    env, layer = request.getfixturevalue("uni" if mode == "Unicycle" else "cars")
+    B = 512 * 9 + 77
+    if mode == "Unicycle":
+        st, ac, mu, sg = O.synth_unicycle(B, seed=77, hazard_frac=0.5)
+    else:
+        st, ac, mu, sg, _ = O.synth_cars(B, seed=77)
+    w = np.random.default_rng(9).normal(size=ac.shape).astype(np.float32)
+    st, ac, mu, sg, w = (_cuda(a) for a in (st, ac, mu, sg, w))
+    out, meta = layer._forward_meta(st, ac, mu, sg)
+    ga = layer._backward_meta(st, ac, mu, sg, meta, w)
+
+    def shifted(t):  # same values at an address that is 4 bytes off a 16-byte boundary: the tile kernel does not qualify
+        buf = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+        v = buf[1:].view(t.shape)
+        v.copy_(t)
+        assert v.data_ptr() % 16 != 0
+        return v
+    gb = layer._backward_meta(shifted(st), ac, mu, sg, meta, w)
+    assert torch.equal(ga, gb)
+    out2, x, lam, slack = layer._forward_raw(st, ac, mu, sg, save=True)
+    assert torch.equal(out, out2)
+    gd = layer._backward_raw(st, ac, mu, sg, x, lam, slack, w)
+    rel = float((ga - gd).norm() / gd.norm())
+    assert rel < GRAD_TOL, rel
+    triv = (meta >> 16) == 0
+    assert 0.2 < float(triv.float().mean()) < 0.95
+    lo, hi = layer.u_min.to(ac.device), layer.u_max.to(ac.device)
+    mask = ((ac >= lo) & (ac <= hi)).float()
+    assert torch.equal(ga[triv], (w * mask)[triv])
+
+
 # ----------------------------------------------------------------------------------------------------- generic QP API
 @pytest.mark.parametrize("which,name", [("uni", "unicycle_layer_b256.npz"), ("cars", "cars_layer_b512.npz")])
 def test_solve_qp_api(request, golden, which, name):
