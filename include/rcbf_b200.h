@@ -293,6 +293,16 @@ int rcbf_unicycle_safe_step_host_gp(float* state4, int32_t* step, const float* a
                                     float* reward_host, uint8_t* done_host, float* cost_host, uint8_t* goal_met_host,
                                     int32_t* n_failed_host, int device, int chunks);
 
+/* ---- low-latency completion / counter read-back (small batches: the reference's B = 1 / 25 / 256 call shapes) ----------
+ * rcbf_counters_publish enqueues a one-warp kernel that copies the 8 counters of `workspace` into host_mirror[1..8] and
+ * then stores `token` into host_mirror[0].  host_mirror is 9 words of page-locked host memory (cudaHostAlloc / a pinned
+ * torch tensor: device-accessible under unified addressing).  A host thread that polls host_mirror[0] for its token knows
+ * that every launch enqueued on `stream` before this one has finished and holds the counters (counter 0 = NaN results:
+ * the check of rcbf_sac/diff_cbf_qp.py:141-143) -- about 10 us less than cudaMemcpyAsync + cudaStreamSynchronize. */
+int rcbf_counters_publish(const rcbf_counters_t* workspace, uint64_t* host_mirror /* 9 words, pinned */, uint64_t token,
+                          void* stream);
+int rcbf_stream_synchronize(void* stream); /* cudaStreamSynchronize (for hosts that hold no CUDA runtime binding) */
+
 /* ---- measurement helpers --------------------------------------------------------------------------------------
  * FP32 FMA throughput probe: `iters` dependent-chain FMAs x 8 chains per thread; returns nothing, time it outside.
  * flops per launch = 2 * 8 * iters * blocks * threads. */

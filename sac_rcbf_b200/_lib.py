@@ -48,6 +48,8 @@ SIGNATURES = {
                                         C.POINTER(C.c_int32), C.c_int, C.c_int],
     "rcbf_cars_safe_step_host": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), C.POINTER(P.CarsEnvParams),
                                  _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.c_int, C.c_int],
+    "rcbf_counters_publish": [_vp, _vp, C.c_uint64, _vp],
+    "rcbf_stream_synchronize": [_vp],
     "rcbf_fp32_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
     "rcbf_fp64_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
     "rcbf_gp_predict_f32": [_vp, _i64, C.POINTER(P.GpPosterior), _vp, _vp, _vp],
@@ -104,14 +106,27 @@ def check(rc, what):
 
 
 def ptr(t):
-    """data pointer of a torch tensor (or None -> NULL)."""
-    return None if t is None else C.c_void_p(t.data_ptr())
+    """data pointer of a torch tensor as a plain int (or None -> NULL); ctypes converts it for the `void*` argtypes."""
+    return None if t is None else t.data_ptr()
+
+
+_raw_stream = None
 
 
 def stream_ptr(device):
-    import torch
+    """cudaStream_t of torch's current stream on `device` as an int (0 -> None: the legacy default stream)."""
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
 
-    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+        _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None) or \
+            (lambda idx: torch.cuda.current_stream(idx).cuda_stream)
+    idx = device.index if hasattr(device, "index") else device
+    if idx is None:
+        import torch
+
+        idx = torch.cuda.current_device()
+    return _raw_stream(idx) or None
 
 
 def require_cuda():

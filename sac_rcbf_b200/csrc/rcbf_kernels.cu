@@ -807,6 +807,16 @@ k_qp_solve_bwd(const double* __restrict__ Q, const double* __restrict__ G, const
 // ------------------------------------------------------------------------------------------------------------
 // FP32 FMA probe (roofline denominator for an FP32-pipe-bound path): 8 independent chains per thread
 // ------------------------------------------------------------------------------------------------------------
+// counters -> a host-visible mirror, then the caller's token: a host thread that polls mirror[0] learns that everything
+// enqueued before this launch has finished AND reads the counters, without a cudaMemcpy / cudaStreamSynchronize pair
+__global__ void k_counters_publish(const rcbf_counters_t* __restrict__ ws, volatile unsigned long long* mirror,
+                                   unsigned long long token) {
+  if (threadIdx.x < 8) mirror[1 + threadIdx.x] = ws[threadIdx.x];
+  __syncwarp();
+  __threadfence_system();
+  if (threadIdx.x == 0) mirror[0] = token;
+}
+
 __global__ void k_fp32_fma_probe(float* sink, int iters) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
         a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -988,6 +998,15 @@ RCBF_ROLLOUT_FUNCS(f32, float)
 RCBF_ROLLOUT_FUNCS(f64, double)
 
 
+
+int rcbf_counters_publish(const rcbf_counters_t* workspace, uint64_t* host_mirror, uint64_t token, void* stream) {
+  k_counters_publish<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, reinterpret_cast<volatile unsigned long long*>(host_mirror),
+                                                        (unsigned long long)token);
+  RCBF_LAUNCH_CHECK();
+  return 0;
+}
+
+int rcbf_stream_synchronize(void* stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
 
 int rcbf_fp32_fma_probe(float* sink, int blocks, int threads, int iters, void* stream) {
   k_fp32_fma_probe<<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters);

@@ -147,18 +147,35 @@ class CBFQPLayer:
         if ws is None or ws.device != self.device:
             ws = self._ws = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=self.device)
             self._ws_base = [0] * 8
-            self._ws_pin = None
+            self._ws_mirror = None
         return ws
 
     def _sync_counters(self):
-        """ONE device->host read of the 8 counters (synchronises); returns this call's increments."""
-        pin = getattr(self, "_ws_pin", None)
-        if pin is None:
-            pin = self._ws_pin = torch.zeros(8, dtype=torch.int64).pin_memory()
-            self._ws_head = self._ws[:8]
-        pin.copy_(self._ws_head, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        cur = pin.tolist()
+        """Read the 8 counters after everything enqueued so far has finished; returns this call's increments.
+        Low-latency form: a one-warp kernel (rcbf_counters_publish) copies the counters into a pinned host mirror and then
+        stores a token there; this thread polls the token -- no cudaMemcpy, no cudaStreamSynchronize on the common
+        path (a stream that stays busy for more than ~20 ms falls back to the blocking wait)."""
+        mir = getattr(self, "_ws_mirror", None)
+        if mir is None:
+            self._ws_mirror_t = torch.zeros(9, dtype=torch.int64).pin_memory()
+            mir = self._ws_mirror = self._ws_mirror_t.numpy()
+            self._ws_token = 0
+        self._ws_token += 1
+        token = self._ws_token
+        dev = self.device
+        prev = torch.cuda.current_device()
+        lib, stream = self._launch_ctx()
+        rc = lib.rcbf_counters_publish(self._ws.data_ptr(), self._ws_mirror_t.data_ptr(), token, stream)
+        if prev != dev.index:
+            torch.cuda.set_device(prev)
+        _lib.check(rc, "rcbf_counters_publish")
+        spins = 0
+        while mir[0] != token:
+            spins += 1
+            if spins > 100000:
+                _lib.check(lib.rcbf_stream_synchronize(stream), "cudaStreamSynchronize")
+                spins = 0
+        cur = mir[1:9].tolist()
         delta = [c - b for c, b in zip(cur, self._ws_base)]
         self._ws_base = cur
         self._last_stats = delta

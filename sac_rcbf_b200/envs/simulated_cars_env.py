@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from .. import _lib, _params
+from ..diff_cbf_qp import _f32c
 from ..spaces import Box
 
 
@@ -39,8 +40,16 @@ class SimulatedCarsEnv:
         self._t = torch.zeros((n,), dtype=self._dtype, device=self.device)
         self._step = torch.zeros((n,), dtype=torch.int32, device=self.device)
         # step outputs: typed views into ONE device buffer (single-env step = one device->host copy)
+        # (single-instance float64 env: pinned HOST buffers the kernel reads / writes directly, like UnicycleEnv)
         isz = 8 if self._dtype == torch.float64 else 4
+        self._mapped = (n == 1 and self.precision == "f64")
         self._outbuf = torch.zeros(((12 * isz + 1) * n + 15) // 16 * 16, dtype=torch.uint8, device=self.device)
+        if self._mapped:
+            self._outbuf = torch.zeros_like(self._outbuf, device="cpu").pin_memory()
+            self._out_np = self._outbuf.numpy()
+            self._vals_np = self._out_np[:12 * isz].view(np.float64)
+            self._act_pin = torch.zeros((1,), dtype=torch.float64).pin_memory()
+            self._act_np = self._act_pin.numpy()
         typed = self._outbuf[:12 * isz * n].view(self._dtype)
         self._obs = typed[:10 * n].view(n, 10)
         self._reward = typed[10 * n:11 * n]
@@ -56,7 +65,21 @@ class SimulatedCarsEnv:
         return self
 
     def _env_params(self):
-        return _params.cars_env_params(self.dt, self.kp, self.k_brake, self.max_episode_steps, self.auto_reset)
+        key = (self.dt, self.kp, self.k_brake, self.max_episode_steps, self.auto_reset)
+        cache = getattr(self, "_ep_cache", None)
+        if cache is None or cache[0] != key:
+            cache = self._ep_cache = (key, _params.cars_env_params(*key))
+        return cache[1]
+
+    def _enter_device(self):
+        prev = torch.cuda.current_device()
+        if prev != self.device.index:
+            torch.cuda.set_device(self.device)
+            return prev
+        return None
+
+    def _wait(self):
+        _lib.check(self._lib.rcbf_stream_synchronize(_lib.stream_ptr(self.device)), "cudaStreamSynchronize")
 
     def _fn(self, name):
         return getattr(self._lib, "rcbf_cars_env_%s_%s" % (name, self.precision))
@@ -104,24 +127,38 @@ class SimulatedCarsEnv:
             rc = self._fn("reset")(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step), _lib.ptr(vn),
                                    _lib.ptr(m), n, _lib.ptr(self._obs), _lib.stream_ptr(self.device))
         _lib.check(rc, "rcbf_cars_env_reset")
+        if self._mapped:
+            self._wait()
+            return self._vals_np[:10].copy()
         return self._obs[0].double().cpu().numpy() if n == 1 else self._obs.clone()
 
     def step(self, action):
-        if torch.is_tensor(action):
+        if self._mapped:
+            if torch.is_tensor(action):
+                action = action.detach().cpu().numpy()
+            self._act_np[0] = np.asarray(action, np.float64).reshape(())
+            a = self._act_pin
+        elif torch.is_tensor(action):
             a = action.detach().to(self.device, self._dtype).reshape(self.num_envs).contiguous()
         else:
             a = torch.as_tensor(np.asarray(action, np.float64).reshape(self.num_envs)).to(self.device, self._dtype)
-        with torch.cuda.device(self.device):
-            rc = self._fn("step")(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step), _lib.ptr(a),
-                                  self.num_envs, self._env_params(), _lib.ptr(self._obs), _lib.ptr(self._reward),
-                                  _lib.ptr(self._done), _lib.ptr(self._cost), _lib.stream_ptr(self.device))
+        prev = self._enter_device()
+        rc = self._fn("step")(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step), _lib.ptr(a),
+                              self.num_envs, self._env_params(), _lib.ptr(self._obs), _lib.ptr(self._reward),
+                              _lib.ptr(self._done), _lib.ptr(self._cost), _lib.stream_ptr(self.device))
+        if prev is not None:
+            torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_cars_env_step")
         if self.num_envs == 1:
             isz = 8 if self._dtype == torch.float64 else 4
-            host = self._outbuf.cpu()                      # ONE device->host copy (and the only synchronisation)
-            vals = host[:12 * isz].view(self._dtype).double().numpy()
+            if self._mapped:
+                self._wait()                               # the kernel wrote straight into the pinned host buffer
+                vals, flags = self._vals_np, self._out_np
+            else:
+                host = self._outbuf.cpu()                  # ONE device->host copy (and the only synchronisation)
+                vals, flags = host[:12 * isz].view(self._dtype).double().numpy(), host.numpy()
             info = {'cost': float(vals[11]), 'goal_met': False}                 # simulated_cars_env.py:85
-            return vals[:10].copy(), float(vals[10]), bool(host[12 * isz]), info
+            return vals[:10].copy(), float(vals[10]), bool(flags[12 * isz]), info
         info = {'cost': self._cost.clone(), 'goal_met': torch.zeros_like(self._done, dtype=torch.bool)}
         return self._obs.clone(), self._reward.clone(), self._done.bool(), info
 
@@ -131,18 +168,20 @@ class SimulatedCarsEnv:
             raise ValueError("safe_step runs on the float32 env layout (precision='f32')")
         dev = self.device
         n = self.num_envs
-        ac = action_rl.detach().to(dev, torch.float32).reshape(n).contiguous()
-        sg = sigma_pred.detach().to(dev, torch.float32).contiguous()
+        ac, sg = _f32c(action_rl, dev), _f32c(sigma_pred, dev)
         if not hasattr(self, "_safe_action"):
             self._safe_action = torch.empty((n, 1), dtype=torch.float32, device=dev)
             self._counters = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=dev)
+            self._own_ptrs = tuple(t.data_ptr() for t in (self._state, self._t, self._step, self._safe_action, self._obs,
+                                                          self._reward, self._done, self._cost, self._counters))
         status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None
-        with torch.cuda.device(dev):
-            rc = self._lib.rcbf_cars_safe_step(_lib.ptr(self._state), _lib.ptr(self._t), _lib.ptr(self._step),
-                                               _lib.ptr(ac), _lib.ptr(sg), n, cbf_layer._params(), self._env_params(),
-                                               _lib.ptr(self._safe_action), _lib.ptr(self._obs), _lib.ptr(self._reward),
-                                               _lib.ptr(self._done), _lib.ptr(self._cost), _lib.ptr(status),
-                                               _lib.ptr(self._counters), _lib.stream_ptr(dev))
+        o = self._own_ptrs
+        prev = self._enter_device()
+        rc = self._lib.rcbf_cars_safe_step(o[0], o[1], o[2], ac.data_ptr(), sg.data_ptr(), n, cbf_layer._params(),
+                                           self._env_params(), o[3], o[4], o[5], o[6], o[7], _lib.ptr(status), o[8],
+                                           _lib.stream_ptr(dev))
+        if prev is not None:
+            torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_cars_safe_step")
         cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
         cbf_layer._last_stats = None

@@ -10,6 +10,7 @@ import numpy as np
 import torch
 
 from .. import _lib, _params
+from ..diff_cbf_qp import _f32c
 from ..spaces import Box
 
 
@@ -45,8 +46,18 @@ class UnicycleEnv:
         self._step = torch.zeros((n,), dtype=torch.int32, device=self.device)
         # step outputs: typed views into ONE device buffer, so that the single-env gym contract (obs ndarray, float
         # reward, bool done, info dict -- main.py:93-95) costs one device->host copy per step instead of five
+        # The single-instance float64 env (the reference's training loop, main.py:93-95) goes one step further: its
+        # action / output buffers are PINNED HOST memory the kernel reads and writes directly (page-locked memory is
+        # device-accessible under unified addressing), so a step is one launch + one stream wait, no copy at all.
         isz = 8 if self._dtype == torch.float64 else 4
+        self._mapped = (n == 1 and self.precision == "f64")
         self._outbuf = torch.zeros(((9 * isz + 2) * n + 15) // 16 * 16, dtype=torch.uint8, device=self.device)
+        if self._mapped:
+            self._outbuf = torch.zeros_like(self._outbuf, device="cpu").pin_memory()
+            self._out_np = self._outbuf.numpy()
+            self._vals_np = self._out_np[:9 * isz].view(np.float64)
+            self._act_pin = torch.zeros((1, 2), dtype=torch.float64).pin_memory()
+            self._act_np = self._act_pin.numpy()
         typed = self._outbuf[:9 * isz * n].view(self._dtype)
         self._obs = typed[:7 * n].view(n, 7)
         self._reward = typed[7 * n:8 * n]
@@ -61,9 +72,37 @@ class UnicycleEnv:
         return self
 
     def _env_params(self):
-        return _params.unicycle_env_params(self.hazards_locations, self.hazards_radius, self.dt, self.goal_pos,
-                                           self.goal_size, self.reward_goal, self.initial_state,
-                                           self.max_episode_steps, self.auto_reset)
+        """C parameter struct of the env, rebuilt only when an attribute it mirrors was re-assigned (identity of the
+        arrays, value of the scalars); an IN-PLACE edit of an array attribute is caught by a content comparison every
+        256th call."""
+        quick = (id(self.hazards_locations), self.hazards_radius, self.dt, id(self.goal_pos), self.goal_size,
+                 self.reward_goal, id(self.initial_state), self.max_episode_steps, self.auto_reset)
+        cache = getattr(self, "_ep_cache", None)
+        self._ep_calls = getattr(self, "_ep_calls", 0) + 1
+        if cache is not None and cache[0] == quick and self._ep_calls & 255:
+            return cache[2]
+        content = (np.asarray(self.hazards_locations, np.float64).tobytes(), np.asarray(self.goal_pos, np.float64).tobytes(),
+                   np.asarray(self.initial_state, np.float64).tobytes())
+        if cache is not None and cache[0] == quick and cache[1] == content:
+            return cache[2]
+        e = _params.unicycle_env_params(self.hazards_locations, self.hazards_radius, self.dt, self.goal_pos,
+                                        self.goal_size, self.reward_goal, self.initial_state,
+                                        self.max_episode_steps, self.auto_reset)
+        self._ep_cache = (quick, content, e)
+        return e
+
+    def _enter_device(self):
+        """Make the env's device current for a launch; returns the previous one when a switch was needed."""
+        prev = torch.cuda.current_device()
+        if prev != self.device.index:
+            torch.cuda.set_device(self.device)
+            return prev
+        return None
+
+    def _wait(self):
+        """Block until the launches on the current stream have finished (the mapped single-instance buffers are read by
+        the host right after)."""
+        _lib.check(self._lib.rcbf_stream_synchronize(_lib.stream_ptr(self.device)), "cudaStreamSynchronize")
 
     def _fn(self, name):
         return getattr(self._lib, "rcbf_unicycle_env_%s_%s" % (name, self.precision))
@@ -112,6 +151,9 @@ class UnicycleEnv:
         return self.get_obs_from_buffer()
 
     def get_obs_from_buffer(self):
+        if self._mapped:
+            self._wait()
+            return self._vals_np[:7].copy()
         if self.num_envs == 1:
             return self._obs[0].double().cpu().numpy()
         return self._obs.clone()
@@ -128,24 +170,35 @@ class UnicycleEnv:
 
     def step(self, action):
         """(obs, reward, done, info).  The action is clipped to [-1, 1] inside the kernel (unicycle_env.py:62)."""
-        if torch.is_tensor(action):
+        if self._mapped:
+            if torch.is_tensor(action):
+                action = action.detach().cpu().numpy()
+            self._act_np[0] = np.asarray(action, np.float64).reshape(2)
+            a = self._act_pin
+        elif torch.is_tensor(action):
             a = action.detach().to(self.device, self._dtype).reshape(self.num_envs, 2).contiguous()
         else:
             a = torch.as_tensor(np.asarray(action, np.float64).reshape(self.num_envs, 2)).to(self.device, self._dtype)
         e = self._env_params()
-        with torch.cuda.device(self.device):
-            rc = self._fn("step")(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(a), self.num_envs, e,
-                                  _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._done),
-                                  _lib.ptr(self._cost), _lib.ptr(self._goal), _lib.stream_ptr(self.device))
+        prev = self._enter_device()
+        rc = self._fn("step")(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(a), self.num_envs, e,
+                              _lib.ptr(self._obs), _lib.ptr(self._reward), _lib.ptr(self._done),
+                              _lib.ptr(self._cost), _lib.ptr(self._goal), _lib.stream_ptr(self.device))
+        if prev is not None:
+            torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_unicycle_env_step")
         return self._pack_step_outputs()
 
     def _pack_step_outputs(self):
         if self.num_envs == 1:
             isz = 8 if self._dtype == torch.float64 else 4
-            host = self._outbuf.cpu()                      # ONE device->host copy (and the only synchronisation)
-            vals = host[:9 * isz].view(self._dtype).double().numpy()
-            done, goal = bool(host[9 * isz]), bool(host[9 * isz + 1])
+            if self._mapped:
+                self._wait()                               # the kernel wrote straight into the pinned host buffer
+                vals, flags = self._vals_np, self._out_np
+            else:
+                host = self._outbuf.cpu()                  # ONE device->host copy (and the only synchronisation)
+                vals, flags = host[:9 * isz].view(self._dtype).double().numpy(), host.numpy()
+            done, goal = bool(flags[9 * isz]), bool(flags[9 * isz + 1])
             info = dict()
             if goal:
                 info['goal_met'] = True                    # only present when met (unicycle_env.py:98)
@@ -162,21 +215,23 @@ class UnicycleEnv:
         if self.precision != "f32":
             raise ValueError("safe_step runs on the float32 env layout (precision='f32')")
         dev = self.device
-        ac = action_rl.detach().to(dev, torch.float32).contiguous()
-        mu = mean_pred.detach().to(dev, torch.float32).contiguous()
-        sg = sigma_pred.detach().to(dev, torch.float32).contiguous()
+        ac, mu, sg = _f32c(action_rl, dev), _f32c(mean_pred, dev), _f32c(sigma_pred, dev)
         n = self.num_envs
         if not hasattr(self, "_safe_action"):
             self._safe_action = torch.empty((n, 2), dtype=torch.float32, device=dev)
             self._counters = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=dev)
+            # (pointers of the env-owned buffers never change: looked up once)
+            self._own_ptrs = tuple(t.data_ptr() for t in (self._state4, self._step, self._safe_action, self._obs,
+                                                          self._reward, self._done, self._cost, self._goal,
+                                                          self._counters))
         status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None
-        with torch.cuda.device(dev):
-            rc = self._lib.rcbf_unicycle_safe_step(_lib.ptr(self._state4), _lib.ptr(self._step), _lib.ptr(ac),
-                                                   _lib.ptr(mu), _lib.ptr(sg), n, cbf_layer._params(),
-                                                   self._env_params(), _lib.ptr(self._safe_action), _lib.ptr(self._obs),
-                                                   _lib.ptr(self._reward), _lib.ptr(self._done), _lib.ptr(self._cost),
-                                                   _lib.ptr(self._goal), _lib.ptr(status), _lib.ptr(self._counters),
-                                                   _lib.stream_ptr(dev))
+        o = self._own_ptrs
+        prev = self._enter_device()
+        rc = self._lib.rcbf_unicycle_safe_step(o[0], o[1], ac.data_ptr(), mu.data_ptr(), sg.data_ptr(), n,
+                                               cbf_layer._params(), self._env_params(), o[2], o[3], o[4], o[5], o[6],
+                                               o[7], _lib.ptr(status), o[8], _lib.stream_ptr(dev))
+        if prev is not None:
+            torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_unicycle_safe_step")
         cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
         cbf_layer._last_stats = None

@@ -17,6 +17,25 @@ def timeit(fn, iters=300, warm=30):
     torch.cuda.synchronize(); return (time.perf_counter() - t0) / iters * 1e6
 
 
+class _Identity(torch.autograd.Function):
+    """autograd floor: a custom Function whose forward / backward launch one elementwise kernel each"""
+    @staticmethod
+    def forward(ctx, a):
+        return a * 1.0
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * 1.0
+
+
+_a = torch.zeros(512, 2, device=dev, requires_grad=True)
+def _floor():
+    _a.grad = None
+    _Identity.apply(_a).sum().backward()
+print("torch autograd floor (identity Function + .sum().backward(), B = 512): %.1f us" % timeit(_floor))
+_e = torch.empty(512, 2, device=dev)
+print("torch.empty + one elementwise launch: %.1f us" % timeit(lambda: torch.empty(512, 2, device=dev).copy_(_e)))
+
 for check in (True, False):
     print("== check_nan =", check, "(True: one D2H sync per call, like the reference's NaN test)")
     for B in (1, 25, 256, 512, 4096):
