@@ -97,6 +97,15 @@ int rcbf_unicycle_assemble(const float* state, const float* action, const float*
 int rcbf_cars_assemble(const float* state, const float* action, const float* sigma, int64_t n,
                        const rcbf_cars_params* p_host, float* G /* n*4*2 */, float* h /* n*4 */, void* stream);
 
+/* float64 variants for the single-instance numpy layer (rcbf_sac/cbf_qp.py:84-240 works in float64): double in, double
+ * out; normalise != 0 also applies that file's [G|h] row normalisation (:262-265), so the result feeds rcbf_qp_solve. */
+int rcbf_unicycle_assemble_f64(const double* state, const double* action, const double* mean, const double* sigma,
+                               int64_t n, const rcbf_unicycle_params* p_host, int normalise, double* G /* n*9*3 */,
+                               double* h /* n*9 */, void* stream);
+int rcbf_cars_assemble_f64(const double* state, const double* action, const double* sigma, int64_t n,
+                           const rcbf_cars_params* p_host, int normalise, double* G /* n*4*2 */, double* h /* n*4 */,
+                           void* stream);
+
 /* ---- get_safe_action forward.  x/lam/slack (float32, saved for the backward), status, iters: nullable ---------- */
 int rcbf_unicycle_safe_action(const float* state, const float* action, const float* mean, const float* sigma,
                               int64_t n, const rcbf_unicycle_params* p_host, float* safe_action /* n*2 */,
@@ -133,6 +142,27 @@ int rcbf_unicycle_safe_action_bwd_meta(const float* state, const float* action, 
                                        const rcbf_unicycle_params* p_host, float* grad_action, void* stream);
 int rcbf_cars_safe_action_bwd_meta(const float* state, const float* action, const float* sigma, const int32_t* meta,
                                    const float* grad_out, int64_t n, const rcbf_cars_params* p_host, float* grad_action,
+                                   void* stream);
+
+/* ---- Unicycle layer on an arbitrary hazard set (the reference sizes its layer from len(env.hazards_locations),
+ * rcbf_sac/diff_cbf_qp.py:35,243-261).  hazards_xy_host: n_hazards x 2 floats on the HOST, 1 <= n_hazards <=
+ * RCBF_MAX_HAZARDS (p_host->hazards is ignored; every other field of p_host applies).  One instance per thread, same
+ * per-instance source as the 5-hazard hot kernels (rows: n_hazards CBF rows, then the 4 actuator rows; meta's active-set
+ * mask indexes rows of the PADDED problem: 8 or 12 CBF rows, then the actuator rows).  Returns -1 for an unsupported
+ * hazard count. */
+#define RCBF_MAX_HAZARDS 12
+int rcbf_unicycle_safe_action_general(const float* state, const float* action, const float* mean, const float* sigma,
+                                      int64_t n, const rcbf_unicycle_params* p_host, const float* hazards_xy_host,
+                                      int n_hazards, float* safe_action /* n*2 */, int32_t* meta /* n, nullable */,
+                                      int32_t* status /* n, nullable */, rcbf_counters_t* counters /* nullable */,
+                                      void* stream);
+int rcbf_unicycle_safe_action_bwd_general(const float* state, const float* action, const float* mean, const float* sigma,
+                                          const int32_t* meta, const float* grad_out, int64_t n,
+                                          const rcbf_unicycle_params* p_host, const float* hazards_xy_host, int n_hazards,
+                                          float* grad_action, void* stream);
+int rcbf_unicycle_assemble_general(const float* state, const float* action, const float* mean, const float* sigma,
+                                   int64_t n, const rcbf_unicycle_params* p_host, const float* hazards_xy_host,
+                                   int n_hazards, float* G /* n*(n_hazards+4)*3 */, float* h /* n*(n_hazards+4) */,
                                    void* stream);
 
 /* ---- generic small QP  min 1/2 x'Qx + p'x  s.t. Gx <= h  (cbf_layer / solve_qp), float64 tensors like qpth sees ---

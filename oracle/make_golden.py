@@ -28,12 +28,25 @@ OUT = os.path.join(ROOT, "tests", "golden")
 tt = torch.from_numpy
 
 
-def layer_fixture(ref, mode, B, gamma_b):
+HAZARDS_7 = np.array([[0.0, 0.0], [-1.5, 1.5], [-1.5, -1.5], [1.5, -1.5], [1.5, 1.5], [0.0, 1.8], [1.9, 0.2]])
+HAZARDS_11 = np.concatenate([HAZARDS_7, np.array([[-2.0, 0.1], [0.3, -2.1], [2.4, 2.2], [-0.8, 0.7]])], 0)
+
+
+def layer_fixture(ref, mode, B, gamma_b, hazards=None):
     args = ref_loader.make_args()
     env = ref.UnicycleEnv() if mode == "Unicycle" else ref.SimulatedCarsEnv()
+    if hazards is not None:                      # the layer sizes itself from len(env.hazards_locations), :35
+        env.hazards_locations = np.array(hazards, dtype=np.float64)
     layer = ref.CBFQPLayer(env, args, gamma_b=gamma_b, k_d=3.0, l_p=0.03)
     if mode == "Unicycle":
         st, ac, mu, sg = O.synth_unicycle(B, seed=12345)
+        if hazards is not None:                  # put the hazard-heavy stratum around THESE hazards
+            rng = np.random.default_rng(99)
+            nh = B // 3
+            hz = np.asarray(hazards)[rng.integers(0, len(hazards), nh)]
+            r, phi = rng.uniform(0.3, 1.1, nh), rng.uniform(-np.pi, np.pi, nh)
+            st[:nh, 0] = hz[:, 0] + r * np.cos(phi)
+            st[:nh, 1] = hz[:, 1] + r * np.sin(phi)
         t = np.zeros(B, np.float32)
     else:
         st, ac, mu, sg, t = O.synth_cars(B, seed=12345)
@@ -51,7 +64,8 @@ def layer_fixture(ref, mode, B, gamma_b):
                                               hn.double().numpy())
     # 1-D call contract (diff_cbf_qp.py:64-69,79)
     final_1d = layer.get_safe_action(tt(st[0]), tt(ac[0]), tt(mu[0]), tt(sg[0]))
-    return dict(state=st, action=ac, mean=mu, sigma=sg, t=t, gamma_b=np.float32(gamma_b),
+    extra = {} if hazards is None else {"hazards": np.asarray(hazards, np.float64)}
+    return dict(state=st, action=ac, mean=mu, sigma=sg, t=t, gamma_b=np.float32(gamma_b), **extra,
                 P=P.numpy(), q=q.numpy(), G=G.numpy(), h=h.numpy(), Gn=Gn.numpy(), hn=hn.numpy(),
                 safe_action=final.detach().numpy(), grad_w=w.numpy(), grad_action=a.grad.numpy(),
                 x_exact=xe, lam_exact=lam, active_exact=act, viol_exact=viol, safe_action_1d=final_1d.numpy())
@@ -234,8 +248,46 @@ def gp_fixture(ref, n_uni=120, n_cars=96, n_test=40):
     return out
 
 
+REPLAY_SCHEDULE = (5, 1, 20, 30, 3, 80, 0, 11)   # wraps, exact fill, a batch larger than the capacity, an empty batch
+
+
+def replay_inputs(cap=37, od=7, ad=2, seed=0):
+    """The push schedule of the replay fixture (regenerated identically by the tests)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for n in REPLAY_SCHEDULE:
+        s, a, r = rng.normal(size=(n, od)), rng.normal(size=(n, ad)), rng.normal(size=n)
+        s2, m, t = rng.normal(size=(n, od)), (rng.random(n) > 0.2).astype(np.float64), rng.random(n)
+        out.append((s, a, r, s2, m, t, t + 0.02))
+    return out
+
+
+def replay_fixture(ref, cap=37):
+    """rcbf_sac/replay_memory.py:4-35 driven through batch_push / push; the ring content after every batch."""
+    mem = ref.ReplayMemory(cap, 0)
+    out = {"capacity": np.int64(cap)}
+    for k, b in enumerate(replay_inputs(cap)):
+        mem.batch_push(*b)
+        items = [np.concatenate([np.ravel(x) for x in it]) for it in mem.buffer]
+        out["after_%d" % k] = np.stack(items) if items else np.zeros((0, 20))
+        out["position_%d" % k] = np.int64(mem.position)
+    mem.push(np.ones(7), np.ones(2), 1.0, np.ones(7), 1.0, 0.5, 0.52)
+    out["after_push"] = np.stack([np.concatenate([np.ravel(x) for x in it]) for it in mem.buffer])
+    out["position_push"] = np.int64(mem.position)
+    smp = mem.sample(16)                                    # shapes / dtypes of what sample returns (:28-33)
+    out["sample_shapes"] = np.array([np.asarray(x).ndim for x in smp])
+    return out
+
+
 def main():
     ref = ref_loader.load_reference()
+    if "--hazards-only" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "unicycle_layer_7haz_b256.npz"), **layer_fixture(ref, "Unicycle", 256, 20.0, HAZARDS_7))
+        np.savez_compressed(os.path.join(OUT, "unicycle_layer_11haz_b128.npz"), **layer_fixture(ref, "Unicycle", 128, 20.0, HAZARDS_11))
+        return
+    if "--replay-only" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "replay_memory.npz"), **replay_fixture(ref))
+        return
     if "--gp-only" in sys.argv:
         np.savez_compressed(os.path.join(OUT, "gp_disturbance.npz"), **gp_fixture(ref))
         return
@@ -243,12 +295,16 @@ def main():
     torch.manual_seed(12345)
     np.savez_compressed(os.path.join(OUT, "unicycle_layer_b256.npz"), **layer_fixture(ref, "Unicycle", 256, 20.0))
     np.savez_compressed(os.path.join(OUT, "cars_layer_b512.npz"), **layer_fixture(ref, "SimulatedCars", 512, 20.0))
+    torch.manual_seed(12345)
+    np.savez_compressed(os.path.join(OUT, "unicycle_layer_7haz_b256.npz"), **layer_fixture(ref, "Unicycle", 256, 20.0, HAZARDS_7))
+    np.savez_compressed(os.path.join(OUT, "unicycle_layer_11haz_b128.npz"), **layer_fixture(ref, "Unicycle", 128, 20.0, HAZARDS_11))
     np.savez_compressed(os.path.join(OUT, "unicycle_env_traj.npz"), **unicycle_traj(ref))
     np.savez_compressed(os.path.join(OUT, "cars_env_traj.npz"), **cars_traj(ref))
     np.savez_compressed(os.path.join(OUT, "dynamics_prior.npz"), **dynamics_fixture(ref))
     np.savez_compressed(os.path.join(OUT, "cascade_layer.npz"), **cascade_fixture(ref))
     np.savez_compressed(os.path.join(OUT, "model_rollouts.npz"), **rollouts_fixture(ref))
     np.savez_compressed(os.path.join(OUT, "gp_disturbance.npz"), **gp_fixture(ref))
+    np.savez_compressed(os.path.join(OUT, "replay_memory.npz"), **replay_fixture(ref))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

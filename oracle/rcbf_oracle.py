@@ -22,6 +22,18 @@ import torch
 
 from oracle import exact_qp, qpth_pdipm
 
+# The reference's own QP solver (qpth, unvendored / unpinned dependency: rcbf_sac/diff_cbf_qp.py:7,139) is preferred
+# whenever the image ships it; otherwise its restatement oracle/qpth_pdipm.py stands in ("parity unpinned").
+try:  # pragma: no cover -- absent from this image
+    import qpth as _real_qpth
+    if getattr(_real_qpth, "__rcbf_stub__", False):      # oracle/ref_loader.py's stand-in, not the package
+        raise ImportError("stub")
+    from qpth.qp import QPFunction as _RealQPFunction
+    QP_BACKEND = "qpth %s (the real package)" % getattr(_real_qpth, "__version__", "?")
+except Exception:  # noqa: BLE001
+    _RealQPFunction = None
+    QP_BACKEND = "oracle/qpth_pdipm.py (restated qpth; the package is absent from the image)"
+
 # envs/unicycle_env.py:24-32
 UNICYCLE = dict(
     hazards_locations=np.array([[0.0, 0.0], [-1.0, 1.0], [-1.0, -1.0], [1.0, -1.0], [1.0, 1.0]]) * 1.5,
@@ -186,10 +198,16 @@ def safe_action(mode, state, action, mean, sigma, solver="qpth", assembly_dtype=
     assembly_dtype   : torch.float32 reproduces the reference (assembly f32, solve f64, result .float());
                        torch.float64 is the "ideal arithmetic" variant.
     """
+    force_restatement = kw.pop("force_restatement", False)   # tests: compare the restatement with the real package
     st, ac, mu, sg = (t.to(assembly_dtype) for t in (state, action, mean, sigma))
     P, q, G, h = ASSEMBLE[mode](st, ac, mu, sg, **kw)
     Gn, hn, n = normalise_rows(G, h)
-    if solver == "qpth":
+    if solver == "qpth" and _RealQPFunction is not None and not force_restatement:
+        e = torch.empty(0, dtype=torch.float64)                             # :107,:139 verbatim
+        x = _RealQPFunction(verbose=0, check_Q_spd=False, maxIter=100000, notImprovedLim=10, eps=eps)(
+            P.double(), q.double(), Gn.double(), hn.double(), e, e).to(assembly_dtype)
+        aux = dict(info=None)
+    elif solver == "qpth":
         fn = qpth_pdipm.QPFunction(verbose=0, check_Q_spd=False, maxIter=100000, notImprovedLim=10, eps=eps)
         e = torch.empty(0, dtype=torch.float64)
         x = fn(P.double(), q.double(), Gn.double(), hn.double(), e, e).to(assembly_dtype)

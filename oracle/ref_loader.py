@@ -68,8 +68,33 @@ class _Env:
         pass
 
 
+def _missing(name):
+    """True when `name` is neither imported nor installed: only then is a stub put in its place (a real package -- should
+    a later image ship qpth / gpytorch / quadprog / gym -- is always preferred)."""
+    import importlib.util
+
+    if name in sys.modules:
+        return False
+    try:
+        return importlib.util.find_spec(name) is None
+    except (ImportError, ValueError):
+        return True
+
+
+def is_stub(module) -> bool:
+    return bool(getattr(module, "__rcbf_stub__", False))
+
+
 def _install_stubs():
-    if "gym" not in sys.modules:
+    _install_stub_modules()
+    for name in ("gym", "gym.spaces", "gym.error", "gpytorch", "gpytorch.models", "qpth", "qpth.qp", "quadprog"):
+        m = sys.modules.get(name)
+        if m is not None and getattr(m, "__file__", None) is None and getattr(m, "__path__", None) is None:
+            m.__rcbf_stub__ = True          # a types.ModuleType made below, not a package found on disk
+
+
+def _install_stub_modules():
+    if _missing("gym"):
         gym = types.ModuleType("gym")
         spaces = types.ModuleType("gym.spaces")
         error = types.ModuleType("gym.error")
@@ -80,7 +105,7 @@ def _install_stubs():
         sys.modules["gym"] = gym
         sys.modules["gym.spaces"] = spaces
         sys.modules["gym.error"] = error
-    if "gpytorch" not in sys.modules:
+    if _missing("gpytorch"):
         gpytorch = types.ModuleType("gpytorch")
         models = types.ModuleType("gpytorch.models")
 
@@ -91,7 +116,7 @@ def _install_stubs():
         gpytorch.models = models
         sys.modules["gpytorch"] = gpytorch
         sys.modules["gpytorch.models"] = models
-    if "qpth" not in sys.modules:
+    if _missing("qpth"):
         from oracle import qpth_pdipm
 
         qpth = types.ModuleType("qpth")
@@ -100,7 +125,7 @@ def _install_stubs():
         qpth.qp = qp
         sys.modules["qpth"] = qpth
         sys.modules["qpth.qp"] = qp
-    if "quadprog" not in sys.modules:
+    if _missing("quadprog"):
         from oracle import exact_qp
 
         quadprog = types.ModuleType("quadprog")
@@ -127,6 +152,7 @@ def load_reference():
     from rcbf_sac.diff_cbf_qp import CBFQPLayer
     from rcbf_sac.cbf_qp import CascadeCBFLayer
     from rcbf_sac import generate_rollouts
+    from rcbf_sac.replay_memory import ReplayMemory
 
     ns = types.SimpleNamespace(
         UnicycleEnv=UnicycleEnv,
@@ -137,6 +163,7 @@ def load_reference():
         CBFQPLayer=CBFQPLayer,
         CascadeCBFLayer=CascadeCBFLayer,
         generate_model_rollouts=generate_rollouts.generate_model_rollouts,
+        ReplayMemory=ReplayMemory,
     )
     _loaded = ns
     return ns

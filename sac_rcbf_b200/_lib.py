@@ -48,6 +48,14 @@ SIGNATURES = {
                                         C.POINTER(C.c_int32), C.c_int, C.c_int],
     "rcbf_cars_safe_step_host": [_vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), C.POINTER(P.CarsEnvParams),
                                  _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int32), C.c_int, C.c_int],
+    "rcbf_unicycle_assemble_f64": [_vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), C.c_int, _vp, _vp, _vp],
+    "rcbf_cars_assemble_f64": [_vp, _vp, _vp, _i64, C.POINTER(P.CarsParams), C.c_int, _vp, _vp, _vp],
+    "rcbf_unicycle_safe_action_general": [_vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp, C.c_int, _vp, _vp,
+                                          _vp, _vp, _vp],
+    "rcbf_unicycle_safe_action_bwd_general": [_vp, _vp, _vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp,
+                                              C.c_int, _vp, _vp],
+    "rcbf_unicycle_assemble_general": [_vp, _vp, _vp, _vp, _i64, C.POINTER(P.UnicycleParams), _vp, C.c_int, _vp, _vp,
+                                       _vp],
     "rcbf_counters_publish": [_vp, _vp, C.c_uint64, _vp],
     "rcbf_stream_synchronize": [_vp],
     "rcbf_fp32_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],

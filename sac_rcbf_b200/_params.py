@@ -3,7 +3,8 @@ import ctypes as C
 
 import numpy as np
 
-UNI_HAZ = 5
+UNI_HAZ = 5          # hazards of the specialised hot kernels (envs/unicycle_env.py:26)
+MAX_HAZARDS = 12     # RCBF_MAX_HAZARDS: general per-instance kernels (rcbf_general.cu)
 WS_WORDS = 32768  # RCBF_WS_WORDS: solver workspace (counters + fallback queue), 64-bit words
 
 

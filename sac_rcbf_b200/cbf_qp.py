@@ -2,8 +2,9 @@
 
 Same kernels as CBFQPLayer with that file's constants: k_d applied to the sigma term (cbf_qp.py:141), signed sigma map
 (:119), P = diag(10, 1e-4, 1e7) (:146), SimulatedCars ignores sigma (:210-211).  `get_u_safe` returns the unclamped
-correction only, like the reference (:46-53, :277).  Assembly runs in float32 on the GPU (the reference uses numpy
-float64), so results agree to ~1e-6 relative, not bitwise; the reference's per-solve print (:278) is dropped.
+correction only, like the reference (:46-53, :277).  The reference works in numpy float64, so this layer does too:
+float64 assembly + row normalisation kernel (rcbf_*_assemble_f64), then the generic float64 QP kernel (rcbf_qp_solve);
+the reference's per-solve print (:278) is dropped.
 """
 import numpy as np
 import torch
@@ -35,30 +36,48 @@ class CascadeCBFLayer:
                                    float(self.u_min[0]), float(self.u_max[0]), sigma_scale=0.0)
 
     def _dev(self, a, width):
-        return torch.as_tensor(np.asarray(a, np.float64).reshape(1, width)).to(self.device, torch.float32)
+        return torch.as_tensor(np.asarray(a, np.float64).reshape(1, width)).to(self.device)
 
-    def get_u_safe(self, u_nom, s, mean_pred, sigma):
-        """Correction to add to u_nom (cbf_qp.py:29-53).  NOTE the argument order (u_nom first)."""
+    def _assemble(self, u_nom, state, mean_pred, sigma_pred, normalise):
+        """float64 G (1,m,nz), h (1,m) on the device, optionally row-normalised like cbf_qp.py:262-265."""
         mode = self.env.dynamics_mode
         dev = self.device
         p = self._params()
         with torch.cuda.device(dev):
             if mode == 'Unicycle':
-                out = torch.empty((1, 2), dtype=torch.float32, device=dev)
-                x = torch.empty((1, 3), dtype=torch.float32, device=dev)
-                ts = (self._dev(s, 3), self._dev(u_nom, 2), self._dev(mean_pred, 3), self._dev(sigma, 3))  # keep alive
-                rc = self._lib.rcbf_unicycle_safe_action(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]),
-                                                         _lib.ptr(ts[3]), 1, p, _lib.ptr(out), _lib.ptr(x), None, None,
-                                                         None, None, None, _lib.stream_ptr(dev))
+                G = torch.empty((1, 9, 3), dtype=torch.float64, device=dev)
+                h = torch.empty((1, 9), dtype=torch.float64, device=dev)
+                ts = (self._dev(state, 3), self._dev(u_nom, 2), self._dev(mean_pred, 3), self._dev(sigma_pred, 3))
+                rc = self._lib.rcbf_unicycle_assemble_f64(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]),
+                                                          _lib.ptr(ts[3]), 1, p, int(normalise), _lib.ptr(G), _lib.ptr(h),
+                                                          _lib.stream_ptr(dev))
+                P = np.diag([1.e1, 1.e-4, 1e7])                                 # cbf_qp.py:146
             else:
-                out = torch.empty((1, 1), dtype=torch.float32, device=dev)
-                x = torch.empty((1, 2), dtype=torch.float32, device=dev)
-                ts = (self._dev(s, 10), self._dev(u_nom, 1), self._dev(sigma, 10))  # keep alive
-                rc = self._lib.rcbf_cars_safe_action(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]), 1, p,
-                                                     _lib.ptr(out), _lib.ptr(x), None, None, None, None, None,
-                                                     _lib.stream_ptr(dev))
-        _lib.check(rc, "rcbf_safe_action")
-        xs = x[0].double().cpu().numpy()
+                G = torch.empty((1, 4, 2), dtype=torch.float64, device=dev)
+                h = torch.empty((1, 4), dtype=torch.float64, device=dev)
+                ts = (self._dev(state, 10), self._dev(u_nom, 1), self._dev(sigma_pred, 10))
+                rc = self._lib.rcbf_cars_assemble_f64(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]), 1, p,
+                                                      int(normalise), _lib.ptr(G), _lib.ptr(h), _lib.stream_ptr(dev))
+                P = np.diag([0.1, 1e1])                                         # :218
+        _lib.check(rc, "rcbf_assemble_f64")
+        return P, G, h
+
+    def get_u_safe(self, u_nom, s, mean_pred, sigma):
+        """Correction to add to u_nom (cbf_qp.py:29-53).  NOTE the argument order (u_nom first).  float64 throughout,
+        like the reference: float64 assembly + normalisation kernel, then the generic float64 QP kernel."""
+        dev = self.device
+        P, G, h = self._assemble(u_nom, s, mean_pred, sigma, normalise=True)
+        nz, m = G.shape[2], G.shape[1]
+        Q = torch.as_tensor(P, dtype=torch.float64, device=dev).reshape(1, nz, nz).contiguous()
+        q = torch.zeros((1, nz), dtype=torch.float64, device=dev)
+        x = torch.empty((1, nz), dtype=torch.float64, device=dev)
+        lam = torch.empty((1, m), dtype=torch.float64, device=dev)
+        slack = torch.empty((1, m), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            rc = self._lib.rcbf_qp_solve(_lib.ptr(Q), _lib.ptr(q), _lib.ptr(G), _lib.ptr(h), 1, nz, m, _lib.ptr(x),
+                                         _lib.ptr(lam), _lib.ptr(slack), None, None, None, _lib.stream_ptr(dev))
+        _lib.check(rc, "rcbf_qp_solve")
+        xs = x[0].cpu().numpy()
         if np.any(np.isnan(xs)):
             raise ValueError("constraints are inconsistent, no solution")   # what quadprog raises (cbf_qp.py:279-281)
         if np.abs(xs[-1]) > 1e-1:
@@ -67,26 +86,8 @@ class CascadeCBFLayer:
 
     def get_cbf_qp_constraints(self, u_nom, state, mean_pred, sigma_pred):
         """P, q, G, h as float64 ndarrays (cbf_qp.py:55-240)."""
-        mode = self.env.dynamics_mode
-        dev = self.device
-        p = self._params()
-        with torch.cuda.device(dev):
-            if mode == 'Unicycle':
-                G = torch.empty((1, 9, 3), dtype=torch.float32, device=dev)
-                h = torch.empty((1, 9), dtype=torch.float32, device=dev)
-                ts = (self._dev(state, 3), self._dev(u_nom, 2), self._dev(mean_pred, 3), self._dev(sigma_pred, 3))
-                rc = self._lib.rcbf_unicycle_assemble(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]), _lib.ptr(ts[3]),
-                                                      1, p, _lib.ptr(G), _lib.ptr(h), _lib.stream_ptr(dev))
-                P = np.diag([1.e1, 1.e-4, 1e7])
-            else:
-                G = torch.empty((1, 4, 2), dtype=torch.float32, device=dev)
-                h = torch.empty((1, 4), dtype=torch.float32, device=dev)
-                ts = (self._dev(state, 10), self._dev(u_nom, 1), self._dev(sigma_pred, 10))
-                rc = self._lib.rcbf_cars_assemble(_lib.ptr(ts[0]), _lib.ptr(ts[1]), _lib.ptr(ts[2]), 1, p, _lib.ptr(G),
-                                                  _lib.ptr(h), _lib.stream_ptr(dev))
-                P = np.diag([0.1, 1e1])
-        _lib.check(rc, "rcbf_assemble")
-        return P, np.zeros(P.shape[0]), G[0].double().cpu().numpy(), h[0].double().cpu().numpy()
+        P, G, h = self._assemble(u_nom, state, mean_pred, sigma_pred, normalise=False)
+        return P, np.zeros(P.shape[0]), G[0].cpu().numpy(), h[0].cpu().numpy()
 
     def get_cbfs(self, hazards_locations, hazards_radius):
         """h(x) and dh/dx closures with the +0.07 buffer of cbf_qp.py:288-325 (host-side helper, not on the QP path)."""

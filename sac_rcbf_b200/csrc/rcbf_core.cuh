@@ -707,9 +707,12 @@ RCBF_HD void sincos_t(float x, float* sn, float* cs) { sincos_v<float>(x, sn, cs
 // Written once for T = float (one instance) and T = f2 (two instances per lane, FMUL2 / FADD2): the packed
 // instructions round each half exactly like the scalar ones, so both instantiations give the same bits.
 // Output: Lg[i] = d h_i / d action (G[i][:2] = -Lg[i]) and the 9 right-hand sides.
-template <typename T>
-RCBF_HD void assemble_unicycle_v(const UnicycleParams& p, const T st[3], T s, T c, const T u[2], const T mu[3],
-                                 const T sg[3], T Lg[kUniHaz][2], T h[kUniM]) {
+// NH = number of hazards (CBF rows); hz = their centres.  The hot kernels use NH = kUniHaz with p.hazards (the
+// reference env, unicycle_env.py:26); rcbf_general.cu instantiates larger NH for layers built on other hazard sets
+// (the reference sizes the layer from len(env.hazards_locations), diff_cbf_qp.py:35,243-261).
+template <typename T, int NH>
+RCBF_HD void assemble_unicycle_n(const UnicycleParams& p, const float (*hz)[2], const T st[3], T s, T c, const T u[2],
+                                 const T mu[3], const T sg[3], T Lg[NH][2], T h[NH + 4]) {
   // s, c = sin / cos of st[2]                              // :211-212
   const T lp = T(p.l_p);
   const T px = add_rn(st[0], mul_rn(lp, c));               // :216
@@ -722,9 +725,9 @@ RCBF_HD void assemble_unicycle_v(const UnicycleParams& p, const T st[3], T s, T 
   const T spx = mul_rn(T(p.sigma_scale), add_rn(mul_rn(a01, sg[2]), sg[0]));  // :239-241 (scale = 1 in this layer)
   const T spy = mul_rn(T(p.sigma_scale), add_rn(mul_rn(a11, sg[2]), sg[1]));
   RCBF_UNROLL
-  for (int i = 0; i < kUniHaz; ++i) {
-    const T dx = sub_rn(px, T(p.hazards[i][0]));           // :248
-    const T dy = sub_rn(py, T(p.hazards[i][1]));
+  for (int i = 0; i < NH; ++i) {
+    const T dx = sub_rn(px, T(hz[i][0]));                  // :248
+    const T dy = sub_rn(py, T(hz[i][1]));
     const T hc = mul_rn(T(0.5f), sub_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), T(p.collision_radius_sq)));  // :246
     const T L0 = add_rn(mul_rn(dx, c), mul_rn(dy, s));     // dhdp' g_p   :259
     const T L1 = add_rn(mul_rn(dx, g01), mul_rn(dy, g11));
@@ -737,10 +740,16 @@ RCBF_HD void assemble_unicycle_v(const UnicycleParams& p, const T st[3], T s, T 
   }
   RCBF_UNROLL
   for (int cc = 0; cc < 2; ++cc) {  // :365-377
-    const int r = kUniHaz + 2 * cc;
+    const int r = NH + 2 * cc;
     h[r] = sub_rn(T(p.u_max[cc]), u[cc]);
     h[r + 1] = add_rn(T(-p.u_min[cc]), u[cc]);
   }
+}
+
+template <typename T>
+RCBF_HD void assemble_unicycle_v(const UnicycleParams& p, const T st[3], T s, T c, const T u[2], const T mu[3],
+                                 const T sg[3], T Lg[kUniHaz][2], T h[kUniM]) {
+  assemble_unicycle_n<T, kUniHaz>(p, p.hazards, st, s, c, u, mu, sg, Lg, h);
 }
 
 RCBF_HD void assemble_unicycle_sc(const UnicycleParams& p, const float st[3], float s, float c, const float u[2],

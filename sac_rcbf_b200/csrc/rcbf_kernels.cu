@@ -151,6 +151,111 @@ __global__ void __launch_bounds__(kThreads) k_cars_assemble(const float* __restr
   }
 }
 
+// float64 assembly (+ optional row normalisation) -- the single-instance numpy layer CascadeCBFLayer works in float64
+// (rcbf_sac/cbf_qp.py:84-240, normalisation :262-265); its QP then goes through the generic float64 kernel (rcbf_qp_solve).
+// Same formulas as assemble_unicycle_v / assemble_cars, evaluated in double from double inputs (the float parameters of
+// the structs are exact for every reference constant except l_p = 0.03 and r_c^2, which carry a 1e-8 relative rounding).
+__device__ __forceinline__ void normalise_row_f64(double* g, int nz, double& h) {
+  double n = fabs(h);
+  for (int j = 0; j < nz; ++j) n = fmax(n, fabs(g[j]));
+  for (int j = 0; j < nz; ++j) g[j] /= n;
+  h /= n;
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_unicycle_assemble_f64(const double* __restrict__ st, const double* __restrict__ ac, const double* __restrict__ mu,
+                        const double* __restrict__ sg, int64_t n, UnicycleParams p, int normalise,
+                        double* __restrict__ G, double* __restrict__ h) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double s[3], u[2], m[3], g[3];
+  load_row<3>(st, i, s);
+  load_row<2>(ac, i, u);
+  load_row<3>(mu, i, m);
+  load_row<3>(sg, i, g);
+  const double lp = (double)p.l_p, c = cos(s[2]), sn = sin(s[2]);
+  const double px = s[0] + lp * c, py = s[1] + lp * sn;                       // cbf_qp.py:94
+  const double g01 = -lp * sn, g11 = lp * c;                                  // g_p = R diag(1, l_p)   :100-105
+  const double mpx = m[0] + g01 * m[2], mpy = m[1] + g11 * m[2];              // :117
+  const double a01 = p.abs_sigma_map ? fabs(g01) : g01, a11 = p.abs_sigma_map ? fabs(g11) : g11;
+  const double spx = (double)p.sigma_scale * (g[0] + a01 * g[2]);             // :119 (signed), k_d of :141
+  const double spy = (double)p.sigma_scale * (g[1] + a11 * g[2]);
+  double* Gi = G + i * kUniM * kUniNZ;
+  double* hi = h + i * kUniM;
+#pragma unroll
+  for (int k = 0; k < kUniHaz; ++k) {
+    const double dx = px - (double)p.hazards[k][0], dy = py - (double)p.hazards[k][1];   // :111
+    const double hc = 0.5 * (dx * dx + dy * dy - (double)p.collision_radius_sq);          // :108
+    const double L0 = dx * c + dy * sn, L1 = dx * g01 + dy * g11;
+    double row[3] = {-L0, -L1, -1.0};                                          // :136-137
+    double hh = (double)p.gamma_b * hc * hc * hc + (dx * mpx + dy * mpy) + (L0 * u[0] + L1 * u[1]) -
+                (fabs(dx) * spx + fabs(dy) * spy);                             // :138-141
+    if (normalise) normalise_row_f64(row, 3, hh);
+    Gi[3 * k] = row[0]; Gi[3 * k + 1] = row[1]; Gi[3 * k + 2] = row[2];
+    hi[k] = hh;
+  }
+#pragma unroll
+  for (int cc = 0; cc < 2; ++cc) {                                             // :226-238
+    double r0[3] = {cc == 0 ? 1.0 : 0.0, cc == 1 ? 1.0 : 0.0, 0.0}, h0 = (double)p.u_max[cc] - u[cc];
+    double r1[3] = {cc == 0 ? -1.0 : 0.0, cc == 1 ? -1.0 : 0.0, 0.0}, h1 = -(double)p.u_min[cc] + u[cc];
+    if (normalise) {
+      normalise_row_f64(r0, 3, h0);
+      normalise_row_f64(r1, 3, h1);
+    }
+    const int r = kUniHaz + 2 * cc;
+    for (int j = 0; j < 3; ++j) {
+      Gi[3 * r + j] = r0[j];
+      Gi[3 * (r + 1) + j] = r1[j];
+    }
+    hi[r] = h0;
+    hi[r + 1] = h1;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_cars_assemble_f64(const double* __restrict__ st, const double* __restrict__ ac, const double* __restrict__ sg, int64_t n,
+                    CarsParams p, int normalise, double* __restrict__ G, double* __restrict__ h) {
+  const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  double s[10], g[10];
+  load_row<10>(st, i, s);
+  load_row<10>(sg, i, g);
+  const double u = __ldg(ac + i);
+  double pos[5], vel[5], acc[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    pos[k] = s[2 * k];
+    vel[k] = s[2 * k + 1];
+    acc[k] = (double)p.kp * (30.0 - vel[k]);                                   // cbf_qp.py:162-163
+  }
+  const double d01 = pos[0] - pos[1], d12 = pos[1] - pos[2], d24 = pos[2] - pos[4];
+  acc[1] -= (d01 < 6.0) ? (double)p.k_brake * d01 : 0.0;                        // :164-167
+  acc[2] -= (d12 < 6.0) ? (double)p.k_brake * d12 : 0.0;
+  acc[4] -= (d24 < 13.0) ? (double)p.k_brake * d24 : 0.0;
+  const double d23 = pos[2] - pos[3], d43 = pos[4] - pos[3];
+  const double r2 = (double)p.collision_radius_sq;
+  const double h13 = 0.5 * (d23 * d23 - r2), h15 = 0.5 * (d43 * d43 - r2);    // :178-179
+  const double a7 = pos[3] - pos[2], b7 = pos[3] - pos[4], a6 = vel[3] - vel[2], b6 = vel[3] - vel[4];
+  const double h13d = a7 * a6, h15d = b7 * b6;                                 // :182-183
+  const double Lff13 = (vel[2] - vel[3]) * vel[2] + d23 * acc[2] + a6 * vel[3];        // :186-191 (acc[3] = 0)
+  const double Lff15 = b6 * vel[3] + (vel[4] - vel[3]) * vel[4] + d43 * acc[4];        // :194-199
+  const double ss = (double)p.sigma_scale;
+  const double LfD13 = ss * (fabs(d23) * g[5] + fabs(a7) * g[7]);              // (0 in the cascade layer: :210-211)
+  const double LfD15 = ss * (fabs(b7) * g[7] + fabs(d43) * g[9]);
+  const double Lg13 = a7 * 50.0, Lg15 = b7 * 50.0;                             // :202-203
+  double rows[4][2] = {{-Lg13, -(double)p.slack_coeff}, {-Lg15, -(double)p.slack_coeff}, {1.0, 0.0}, {-1.0, 0.0}};
+  double hh[4] = {Lff13 - LfD13 + (double)p.gamma_2 * h13d + (double)p.gamma_sq * h13 + Lg13 * u,
+                  Lff15 - LfD15 + (double)p.gamma_2 * h15d + (double)p.gamma_sq * h15 + Lg15 * u,
+                  (double)p.u_max - u, -(double)p.u_min + u};
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if (normalise) normalise_row_f64(rows[r], 2, hh[r]);
+    G[(i * 4 + r) * 2] = rows[r][0];
+    G[(i * 4 + r) * 2 + 1] = rows[r][1];
+    h[i * 4 + r] = hh[r];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K4: backward (recomputes the cheap assembly, reads the saved x / lam / slack)
 // ------------------------------------------------------------------------------------------------------------
@@ -843,6 +948,23 @@ int rcbf_unicycle_assemble(const float* state, const float* action, const float*
                            const rcbf_unicycle_params* p, float* G, float* h, void* stream) {
   if (n <= 0) return 0;
   k_unicycle_assemble<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, action, mean, sigma, n, *p, G, h);
+  RCBF_LAUNCH_CHECK();
+  return 0;
+}
+
+int rcbf_unicycle_assemble_f64(const double* state, const double* action, const double* mean, const double* sigma,
+                               int64_t n, const rcbf_unicycle_params* p, int normalise, double* G, double* h, void* stream) {
+  if (n <= 0) return 0;
+  k_unicycle_assemble_f64<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, action, mean, sigma, n, *p, normalise,
+                                                                              G, h);
+  RCBF_LAUNCH_CHECK();
+  return 0;
+}
+
+int rcbf_cars_assemble_f64(const double* state, const double* action, const double* sigma, int64_t n,
+                           const rcbf_cars_params* p, int normalise, double* G, double* h, void* stream) {
+  if (n <= 0) return 0;
+  k_cars_assemble_f64<<<grid_for(n), kThreads, 0, (cudaStream_t)stream>>>(state, action, sigma, n, *p, normalise, G, h);
   RCBF_LAUNCH_CHECK();
   return 0;
 }

@@ -138,6 +138,7 @@ class CBFQPLayer:
         self._last_counters = None  # workspace of the last fused env step (device tensor, cumulative counters)
         self._last_stats = None     # per-call counter increments of the last synchronised launch
         self._params_cache = None
+        self._general_hz = None     # (K, 2) float32 host table when the layer has more than 5 hazards
 
     def _workspace(self):
         """RCBF_WS_WORDS-word solver workspace (counters + fallback queue), zero-initialised ONCE.  The counters
@@ -230,8 +231,17 @@ class CBFQPLayer:
             key = ('U', self.solver, float(self.gamma_b), float(self.l_p), float(env.hazards_radius), hz.tobytes(),
                    self._bounds_tag)
             if self._params_cache is None or self._params_cache[0] != key:
-                p = _params.unicycle_params(hz, env.hazards_radius, float(self.gamma_b), float(self.l_p), lo, hi,
-                                            solver_mode=self._solver_mode())
+                # up to 5 hazards: the specialised hot kernels (fewer are padded with inert ones); 6 .. 12: the general
+                # per-instance kernels of rcbf_general.cu, which take the hazard table as a separate host array
+                general = hz.ndim == 2 and hz.shape[0] > _params.UNI_HAZ
+                if general and (hz.shape[1] != 2 or hz.shape[0] > _params.MAX_HAZARDS):
+                    raise ValueError("the sm_100a kernels support 1..%d hazards of shape (K, 2), got %r"
+                                     % (_params.MAX_HAZARDS, hz.shape))
+                if general and self.solver != "presolve":
+                    raise ValueError("solver = 'pdipm' is only built for the 5-hazard kernels")
+                p = _params.unicycle_params(None if general else hz, env.hazards_radius, float(self.gamma_b),
+                                            float(self.l_p), lo, hi, solver_mode=self._solver_mode())
+                self._general_hz = np.ascontiguousarray(hz, np.float32) if general else None
                 self._params_cache = (key, p)
         else:
             key = ('C', self.solver, float(self.gamma_b), float(env.kp), float(env.k_brake), self._bounds_tag)
@@ -270,7 +280,14 @@ class CBFQPLayer:
         p = self._params()
         prev = torch.cuda.current_device()
         lib, stream = self._launch_ctx()
-        if mode == 'Unicycle':
+        ghz = self._general_hz
+        if ghz is not None:
+            if save:
+                raise NotImplementedError("dense saved tensors are only produced by the 5-hazard kernels")
+            rc = lib.rcbf_unicycle_safe_action_general(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
+                                                       ghz.ctypes.data, ghz.shape[0], _lib.ptr(out), None,
+                                                       _lib.ptr(status), _lib.ptr(counters), stream)
+        elif mode == 'Unicycle':
             rc = lib.rcbf_unicycle_safe_action(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
                                                _lib.ptr(out), _lib.ptr(x), _lib.ptr(lam), _lib.ptr(slack),
                                                _lib.ptr(status), _lib.ptr(iters), _lib.ptr(counters), stream)
@@ -297,7 +314,12 @@ class CBFQPLayer:
         p = self._params()
         prev = torch.cuda.current_device()
         lib, stream = self._launch_ctx()
-        if mode == 'Unicycle':
+        ghz = self._general_hz
+        if ghz is not None:
+            rc = lib.rcbf_unicycle_safe_action_general(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
+                                                       ghz.ctypes.data, ghz.shape[0], _lib.ptr(out), _lib.ptr(meta), None,
+                                                       _lib.ptr(counters), stream)
+        elif mode == 'Unicycle':
             rc = lib.rcbf_unicycle_safe_action_saved(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
                                                      _lib.ptr(out), _lib.ptr(meta), _lib.ptr(counters), stream)
         else:
@@ -315,7 +337,12 @@ class CBFQPLayer:
         p = self._params()
         prev = torch.cuda.current_device()
         lib, stream = self._launch_ctx()
-        if self.env.dynamics_mode == 'Unicycle':
+        ghz = self._general_hz
+        if ghz is not None:
+            rc = lib.rcbf_unicycle_safe_action_bwd_general(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg),
+                                                           _lib.ptr(meta), _lib.ptr(go), n, p, ghz.ctypes.data,
+                                                           ghz.shape[0], _lib.ptr(ga), stream)
+        elif self.env.dynamics_mode == 'Unicycle':
             rc = lib.rcbf_unicycle_safe_action_bwd_meta(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg),
                                                         _lib.ptr(meta), _lib.ptr(go), n, p, _lib.ptr(ga), stream)
         else:
@@ -404,7 +431,15 @@ class CBFQPLayer:
         mode = self.env.dynamics_mode
         p = self._params()
         with torch.cuda.device(dev):
-            if mode == 'Unicycle':
+            if mode == 'Unicycle' and self._general_hz is not None:
+                ghz = self._general_hz
+                G = torch.empty((n, ghz.shape[0] + 4, 3), dtype=torch.float32, device=dev)
+                h = torch.empty((n, ghz.shape[0] + 4), dtype=torch.float32, device=dev)
+                rc = lib.rcbf_unicycle_assemble_general(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
+                                                        ghz.ctypes.data, ghz.shape[0], _lib.ptr(G), _lib.ptr(h),
+                                                        _lib.stream_ptr(dev))
+                P = torch.diag(torch.tensor([1.e0, 1.e-2, 1e5])).repeat(n, 1, 1).to(out_dev)
+            elif mode == 'Unicycle':
                 G = torch.empty((n, 9, 3), dtype=torch.float32, device=dev)
                 h = torch.empty((n, 9), dtype=torch.float32, device=dev)
                 rc = lib.rcbf_unicycle_assemble(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,

@@ -169,9 +169,12 @@ class SimulatedCarsEnv:
         dev = self.device
         n = self.num_envs
         ac, sg = _f32c(action_rl, dev), _f32c(sigma_pred, dev)
-        if not hasattr(self, "_safe_action"):
+        if getattr(self, "_safe_action", None) is None:
             self._safe_action = torch.empty((n, 1), dtype=torch.float32, device=dev)
+        if getattr(self, "_counters", None) is None:
             self._counters = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=dev)
+        if getattr(self, "_own_key", None) != (id(self._safe_action), id(self._counters)):
+            self._own_key = (id(self._safe_action), id(self._counters))
             self._own_ptrs = tuple(t.data_ptr() for t in (self._state, self._t, self._step, self._safe_action, self._obs,
                                                           self._reward, self._done, self._cost, self._counters))
         status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None

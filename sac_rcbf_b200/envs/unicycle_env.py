@@ -214,13 +214,20 @@ class UnicycleEnv:
         Returns (safe_action, obs, reward, done, info)."""
         if self.precision != "f32":
             raise ValueError("safe_step runs on the float32 env layout (precision='f32')")
+        lp = cbf_layer._params()
+        if cbf_layer._general_hz is not None:
+            raise ValueError("the fused step is specialised for up to 5 hazards (unicycle_env.py:26); with %d use "
+                             "cbf_layer.get_safe_action + env.step" % cbf_layer._general_hz.shape[0])
         dev = self.device
         ac, mu, sg = _f32c(action_rl, dev), _f32c(mean_pred, dev), _f32c(sigma_pred, dev)
         n = self.num_envs
-        if not hasattr(self, "_safe_action"):
+        if getattr(self, "_safe_action", None) is None:
             self._safe_action = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        if getattr(self, "_counters", None) is None:
             self._counters = torch.zeros(_params.WS_WORDS, dtype=torch.int64, device=dev)
-            # (pointers of the env-owned buffers never change: looked up once)
+        if getattr(self, "_own_key", None) != (id(self._safe_action), id(self._counters)):
+            # (pointers of the env-owned buffers only change when a buffer object is replaced: looked up once)
+            self._own_key = (id(self._safe_action), id(self._counters))
             self._own_ptrs = tuple(t.data_ptr() for t in (self._state4, self._step, self._safe_action, self._obs,
                                                           self._reward, self._done, self._cost, self._goal,
                                                           self._counters))
@@ -228,7 +235,7 @@ class UnicycleEnv:
         o = self._own_ptrs
         prev = self._enter_device()
         rc = self._lib.rcbf_unicycle_safe_step(o[0], o[1], ac.data_ptr(), mu.data_ptr(), sg.data_ptr(), n,
-                                               cbf_layer._params(), self._env_params(), o[2], o[3], o[4], o[5], o[6],
+                                               lp, self._env_params(), o[2], o[3], o[4], o[5], o[6],
                                                o[7], _lib.ptr(status), o[8], _lib.stream_ptr(dev))
         if prev is not None:
             torch.cuda.set_device(prev)

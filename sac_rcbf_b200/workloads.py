@@ -45,3 +45,30 @@ def synth_cars(B, seed=12345):
     sg = np.zeros((B, 10))
     sg[:, 1::2] = g.uniform(0, 0.2, (B, 5))
     return tuple(a.astype(np.float32) for a in (st, ac, mu, sg)) + (t.astype(np.float32),)
+
+
+def bench_unicycle(n, seed=12345, sets=2, first=None):
+    """The bench workload (BASELINE config 4 semantics) as HOST arrays, prefix-stable: instance i's data do not depend on
+    n -- every array is drawn from its own Philox stream in instance order -- so `first=m` returns exactly the first m
+    instances of the n-instance workload.  bench.py's GPU arm uploads all n; its CPU arm (`--impl reference`,
+    `cpu_baseline`) runs on the leading instances of the SAME arrays.
+    Returns (state (m,3), [(u_rl (m,2), mean (m,3), sigma (m,3))] * sets), float32."""
+    m = n if first is None else min(int(first), n)
+
+    def U(k, cols):
+        return np.random.Generator(np.random.Philox(key=[seed, k])).random((m, cols), dtype=np.float32)
+
+    a = U(0, 3)
+    st = np.stack([-3 + 6 * a[:, 0], -3 + 6 * a[:, 1], (2 * a[:, 2] - 1) * np.float32(math.pi)], 1).astype(np.float32)
+    b = U(1, 4)
+    heavy = b[:, 0] < 0.2                                   # hazard-heavy stratum: 0.3 .. 1.1 m from a hazard centre
+    hz = UNICYCLE["hazards_locations"][np.minimum((5 * b[:, 1]).astype(np.int64), 4)]
+    r, phi = 0.3 + 0.8 * b[:, 2], (2 * b[:, 3] - 1) * np.float32(math.pi)
+    st[heavy, 0] = (hz[:, 0] + r * np.cos(phi))[heavy]
+    st[heavy, 1] = (hz[:, 1] + r * np.sin(phi))[heavy]
+    batches = []
+    for q in range(sets):
+        batches.append(((2 * U(10 + 3 * q, 2) - 1).astype(np.float32),
+                        (0.2 * U(11 + 3 * q, 3) - 0.1).astype(np.float32),
+                        (0.2 * U(12 + 3 * q, 3)).astype(np.float32)))
+    return st, batches

@@ -1,41 +1,72 @@
-"""DeviceReplayMemory semantics vs rcbf_sac/replay_memory.py (restated inline), on CPU tensors (the class is plain
-torch indexing; the GPU test repeats a subset on the device)."""
+"""DeviceReplayMemory semantics vs the reference's ReplayMemory (rcbf_sac/replay_memory.py:4-35).
+
+The ring content after every batch of a push schedule (wraps, exact fill, a batch larger than the capacity, an empty
+batch, a single push) comes from the REAL class: tests/golden/replay_memory.npz is written by oracle/make_golden.py from
+the unmodified reference source, and where /root/reference is present the real class is also driven live, side by side.
+The same check runs on CPU tensors here and on the device under `-m gpu`."""
 import numpy as np
+import pytest
 import torch
 
+from oracle import make_golden, ref_loader
 from sac_rcbf_b200.replay_memory import DeviceReplayMemory
 
 
-class _RefMemory:                      # rcbf_sac/replay_memory.py:4-35, minus sampling
-    def __init__(self, capacity):
-        self.capacity, self.buffer, self.position = capacity, [], 0
-
-    def push(self, *item):
-        if len(self.buffer) < self.capacity:
-            self.buffer.append(None)
-        self.buffer[self.position] = item
-        self.position = (self.position + 1) % self.capacity
+def _rows(mem):
+    n = len(mem)
+    cols = [mem.state[:n], mem.action[:n], mem.reward[:n, None], mem.next_state[:n], mem.mask[:n, None], mem.t[:n, None],
+            mem.next_t[:n, None]]
+    return torch.cat([c.double().cpu() for c in cols], 1).numpy()
 
 
-def test_ring_semantics_match_reference():
-    cap, od, ad = 37, 7, 2
-    mem = DeviceReplayMemory(cap, seed=0, obs_dim=od, action_dim=ad, device="cpu", dtype=torch.float64)
-    ref = _RefMemory(cap)
-    rng = np.random.default_rng(0)
-    for n in (5, 1, 20, 30, 3, 80, 0, 11):          # wraps, exact fill, a batch larger than the capacity, empty
-        s, a, r = rng.normal(size=(n, od)), rng.normal(size=(n, ad)), rng.normal(size=n)
-        s2, m, t = rng.normal(size=(n, od)), (rng.random(n) > 0.2), rng.random(n)
-        mem.batch_push(s, a, r, s2, m, t, t + 0.02)
-        for i in range(n):
-            ref.push(s[i], a[i], r[i], s2[i], m[i], t[i], t[i] + 0.02)
-        assert len(mem) == len(ref.buffer) and mem.position == ref.position
-        for slot, item in enumerate(ref.buffer):
-            np.testing.assert_array_equal(mem.state[slot].numpy(), item[0])
-            np.testing.assert_array_equal(mem.action[slot].numpy(), item[1])
-            assert mem.reward[slot].item() == item[2] and mem.mask[slot].item() == float(item[4])
-            assert mem.t[slot].item() == item[5] and mem.next_t[slot].item() == item[6]
-    mem.push(np.ones(od), np.ones(ad), 1.0, np.ones(od), 1.0, t=0.5, next_t=0.52)
-    assert mem.reward[(mem.position - 1) % cap].item() == 1.0
+def _check_against_golden(g, device):
+    cap = int(g["capacity"])
+    mem = DeviceReplayMemory(cap, seed=0, obs_dim=7, action_dim=2, device=device, dtype=torch.float64)
+    for k, b in enumerate(make_golden.replay_inputs(cap)):
+        mem.batch_push(*b)
+        assert len(mem) == g["after_%d" % k].shape[0] and mem.position == int(g["position_%d" % k])
+        np.testing.assert_array_equal(_rows(mem), g["after_%d" % k])
+    mem.push(np.ones(7), np.ones(2), 1.0, np.ones(7), 1.0, t=0.5, next_t=0.52)
+    assert mem.position == int(g["position_push"])
+    np.testing.assert_array_equal(_rows(mem), g["after_push"])
+    smp = mem.sample(16)
+    assert [x.dim() for x in smp] == list(g["sample_shapes"])
+    return mem
+
+
+def test_ring_semantics_match_reference_golden(golden):
+    _check_against_golden(golden("replay_memory.npz"), "cpu")
+
+
+@pytest.mark.skipif(not ref_loader.reference_available(), reason="reference source not mounted")
+def test_ring_semantics_match_live_reference():
+    ref = ref_loader.load_reference()
+    cap = 23
+    real = ref.ReplayMemory(cap, 0)
+    mem = DeviceReplayMemory(cap, seed=0, obs_dim=7, action_dim=2, device="cpu", dtype=torch.float64)
+    for b in make_golden.replay_inputs(cap, seed=4):
+        real.batch_push(*b)
+        mem.batch_push(*b)
+        assert len(mem) == len(real) and mem.position == real.position
+        want = np.stack([np.concatenate([np.ravel(x) for x in it]) for it in real.buffer]) if len(real) else np.zeros((0, 20))
+        np.testing.assert_array_equal(_rows(mem), want)
+    # sampling: same return structure (7 stacked arrays, batch first), every drawn row is a stored transition
+    out_real, out_mine = real.sample(8), mem.sample(8)
+    assert [np.asarray(x).shape for x in out_real] == [tuple(x.shape) for x in out_mine]
+    stored = {tuple(np.round(r, 12)) for r in _rows(mem)}
+    mine = torch.cat([out_mine[0], out_mine[1], out_mine[2][:, None], out_mine[3], out_mine[4][:, None],
+                      out_mine[5][:, None], out_mine[6][:, None]], 1).numpy()
+    assert all(tuple(np.round(r, 12)) in stored for r in mine)
+    with pytest.raises(ValueError):
+        real.sample(cap + 1)
+    with pytest.raises(ValueError):
+        mem.sample(cap + 1)
+
+
+@pytest.mark.gpu
+def test_ring_semantics_match_reference_golden_on_device(golden):
+    mem = _check_against_golden(golden("replay_memory.npz"), "cuda")
+    assert mem.state.is_cuda and mem.sample(4)[0].is_cuda
 
 
 def test_sample_without_replacement_and_shapes():
