@@ -166,7 +166,8 @@ int rcbf_unicycle_assemble_general(const float* state, const float* action, cons
                                    void* stream);
 
 /* ---- generic small QP  min 1/2 x'Qx + p'x  s.t. Gx <= h  (cbf_layer / solve_qp), float64 tensors like qpth sees ---
- * (nz, m) in {(3,9), (2,4)}.  (solve_qp's [G|h] row normalisation is applied by the caller, diff_cbf_qp.py:103-106.) */
+ * (nz, m) in {(3,9), (3,12), (3,16), (2,4)}; a system with fewer rows is padded by the caller with copies of one of its
+ * rows (a duplicate constraint changes neither the feasible set nor the optimum).  (solve_qp's [G|h] row normalisation is applied by the caller, diff_cbf_qp.py:103-106.) */
 int rcbf_qp_solve(const double* Q /* n*nz*nz */, const double* p /* n*nz */, const double* G /* n*m*nz */,
                   const double* h /* n*m */, int64_t n, int nz, int m, double* x /* n*nz */, double* lam /* n*m */,
                   double* slack /* n*m */, int32_t* status, int32_t* iters, rcbf_counters_t* counters, void* stream);

@@ -418,7 +418,13 @@ int launch_gp_farfield(const rcbf_gp_posterior& p, const T* test_x, int64_t n_te
   constexpr int P = DP <= 4 ? 4 : 2;
   const int64_t tiles = (n_test + 32 * P - 1) / (32 * P);
   const int64_t want = (tiles + 3) / 4;
-  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  static int sms_cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& sms = sms_cached[dev & 63];
+  if (sms == 0) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int cap = (sms > 0 ? sms : 148) * 16;
+  const int grid = (int)(want < cap ? want : cap);
   k_gp_farfield<R, DP, T><<<grid, 128, 0, s>>>(p, test_x, n_test, mean, sd);
   return (int)cudaGetLastError();
 }

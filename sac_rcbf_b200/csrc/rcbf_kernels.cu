@@ -1020,6 +1020,10 @@ int rcbf_qp_solve(const double* Q, const double* p, const double* G, const doubl
   cudaStream_t s = (cudaStream_t)stream;
   if (nz == 3 && m == 9)
     k_qp_solve<3, 9><<<grid_for(n), kThreads, 0, s>>>(Q, p, G, h, n, x, lam, slack, status, iters, counters);
+  else if (nz == 3 && m == 12)   // layers on 6 .. 8 hazards (the caller pads smaller systems with duplicate rows)
+    k_qp_solve<3, 12><<<grid_for(n), kThreads, 0, s>>>(Q, p, G, h, n, x, lam, slack, status, iters, counters);
+  else if (nz == 3 && m == 16)   // ... 9 .. 12 hazards
+    k_qp_solve<3, 16><<<grid_for(n), kThreads, 0, s>>>(Q, p, G, h, n, x, lam, slack, status, iters, counters);
   else if (nz == 2 && m == 4)
     k_qp_solve<2, 4><<<grid_for(n), kThreads, 0, s>>>(Q, p, G, h, n, x, lam, slack, status, iters, counters);
   else
@@ -1035,6 +1039,10 @@ int rcbf_qp_solve_bwd(const double* Q, const double* G, const double* x, const d
   cudaStream_t s = (cudaStream_t)stream;
   if (nz == 3 && m == 9)
     k_qp_solve_bwd<3, 9><<<grid_for(n), kThreads, 0, s>>>(Q, G, x, lam, slack, grad_x, n, dQ, dp, dG, dh);
+  else if (nz == 3 && m == 12)
+    k_qp_solve_bwd<3, 12><<<grid_for(n), kThreads, 0, s>>>(Q, G, x, lam, slack, grad_x, n, dQ, dp, dG, dh);
+  else if (nz == 3 && m == 16)
+    k_qp_solve_bwd<3, 16><<<grid_for(n), kThreads, 0, s>>>(Q, G, x, lam, slack, grad_x, n, dQ, dp, dG, dh);
   else if (nz == 2 && m == 4)
     k_qp_solve_bwd<2, 4><<<grid_for(n), kThreads, 0, s>>>(Q, G, x, lam, slack, grad_x, n, dQ, dp, dG, dh);
   else

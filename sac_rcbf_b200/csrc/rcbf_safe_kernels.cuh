@@ -1297,6 +1297,16 @@ inline cudaError_t launch_pdl(bool pdl, void (*kern)(KArgs...), int grid, int bl
   return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
+// SMs of the current device (cached per device; the persistent grids are sized from it)
+inline int device_sm_count() {
+  static int cached[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& c = cached[dev & 63];
+  if (c == 0) cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev);
+  return c > 0 ? c : 148;
+}
+
 template <class E>
 inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::Params& p, const typename E::EnvParams& e,
                        rcbf_counters_t* ws, cudaStream_t s) {
@@ -1304,10 +1314,11 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   if (n > 0x7fffffffLL) return -2;  // ring indices are 32-bit
   const int64_t ntiles = (n + 31) / 32;
   const int64_t want = (ntiles + kWarps - 1) / kWarps;
-  const int resident = 148 * (p.solver_mode == 0 ? E::kMinBlocks : RCBF_MINB_PDIPM);  // persistent: one wave of resident blocks
+  const int sms = device_sm_count();
+  const int resident = sms * (p.solver_mode == 0 ? E::kMinBlocks : RCBF_MINB_PDIPM);  // persistent: one wave of resident blocks
   const int grid = (int)(want < resident ? want : resident);
   const int64_t fb = (n + 127) / 128;
-  const int fgrid = (int)(fb < 148 * 4 ? fb : 148 * 4);
+  const int fgrid = (int)(fb < sms * 4 ? fb : sms * 4);
   // TMA bulk staging needs 16-byte aligned array bases (row spans of a 32-instance tile are then 16-byte multiples)
   const bool bulk = E::aligned(a) && n >= 32;
   const bool saved = (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr || a.meta != nullptr);

@@ -46,6 +46,9 @@ class _SafeActionFn(torch.autograd.Function):
         return None, None, ga.to(device=ctx.in_device, dtype=ctx.in_dtype), None, None
 
 
+_QP_ROWS = {3: (9, 12, 16), 2: (4,)}     # row counts rcbf_qp_solve is instantiated for, per number of variables
+
+
 class _QPFn(torch.autograd.Function):
     """Generic batched QP (cbf_layer API): float64 in, float64 out, qpth-style gradients for Q, p, G, h."""
 
@@ -53,8 +56,14 @@ class _QPFn(torch.autograd.Function):
     def forward(ctx, layer, Q, p, G, h):
         lib = _lib.load()
         dev = layer.device
-        n, m, nz = G.shape
+        n, m_in, nz = G.shape
         Qd, pd, Gd, hd = (t.detach().to(device=dev, dtype=torch.float64).contiguous() for t in (Q, p, G, h))
+        # the kernel is instantiated for a few row counts; a smaller system (a layer on K != 5 hazards: m = K + 4) is
+        # padded with copies of its first row -- a duplicate constraint changes neither the feasible set nor the optimum
+        m = min([s_ for s_ in _QP_ROWS.get(nz, ()) if s_ >= m_in], default=m_in)
+        if m > m_in:
+            Gd = torch.cat((Gd, Gd[:, :1].expand(n, m - m_in, nz)), 1).contiguous()
+            hd = torch.cat((hd, hd[:, :1].expand(n, m - m_in)), 1).contiguous()
         x = torch.empty((n, nz), dtype=torch.float64, device=dev)
         lam = torch.empty((n, m), dtype=torch.float64, device=dev)
         slack = torch.empty((n, m), dtype=torch.float64, device=dev)
@@ -64,14 +73,15 @@ class _QPFn(torch.autograd.Function):
                                    _lib.ptr(lam), _lib.ptr(slack), None, None, _lib.ptr(counters),
                                    _lib.stream_ptr(dev))
         if rc == -1:
-            raise NotImplementedError("generic QP kernel is instantiated for (nz, m) in {(3, 9), (2, 4)}, got (%d, %d)"
-                                      % (nz, m))
+            raise NotImplementedError("generic QP kernel is instantiated for nz = 3 with up to 16 rows and (nz, m) = "
+                                      "(2, 4), got (%d, %d)" % (nz, m_in))
         _lib.check(rc, "rcbf_qp_solve")
         layer._last_counters = counters
         layer._last_stats = None
         ctx.layer = layer
         ctx.save_for_backward(Qd, Gd, x, lam, slack)
         ctx.in_devices = (Q.device, p.device, G.device, h.device)
+        ctx.m_in = m_in
         return x.to(G.device)
 
     @staticmethod
@@ -92,6 +102,10 @@ class _QPFn(torch.autograd.Function):
                                        _lib.stream_ptr(dev))
         _lib.check(rc, "rcbf_qp_solve_bwd")
         d = ctx.in_devices
+        if ctx.m_in < m:     # padding rows were copies of row 0: their (inactive-duplicate) gradient belongs to it
+            dG[:, 0] += dG[:, ctx.m_in:].sum(1)
+            dh[:, 0] += dh[:, ctx.m_in:].sum(1)
+            dG, dh = dG[:, :ctx.m_in].contiguous(), dh[:, :ctx.m_in].contiguous()
         return None, dQ.to(d[0]), dp.to(d[1]), dG.to(d[2]), dh.to(d[3])
 
 

@@ -148,7 +148,16 @@ class DynamicsModel:
         if expand_dims:
             test_x = test_x[None]
         if self.disturbance_fn is not None:
-            means, f_std = self.disturbance_fn(test_x)
+            # documented contract: disturbance_fn(state_batch ndarray) -> (mean, std).  It is called with an ndarray
+            # whatever the caller passed, and its outputs come back in the caller's kind (tensor -> same device / dtype)
+            xs = test_x.detach().cpu().numpy() if is_tensor else np.asarray(test_x)
+            means, f_std = self.disturbance_fn(xs)
+            if is_tensor:
+                means = torch.as_tensor(means).to(test_x.device, test_x.dtype)
+                f_std = torch.as_tensor(f_std).to(test_x.device, test_x.dtype)
+            else:
+                means = means.detach().cpu().numpy() if torch.is_tensor(means) else np.asarray(means)
+                f_std = f_std.detach().cpu().numpy() if torch.is_tensor(f_std) else np.asarray(f_std)
         elif self.disturb_estimators:
             # dynamics.py:371-379: x / std_x, every GP, mean * (std_y + 1e-8), sqrt(f_var) * (std_y + 1e-8) -- the
             # scalings live in the bank and are applied inside the kernel
@@ -219,7 +228,10 @@ class DynamicsModel:
         self.train_y = train_y
 
     def load_disturbance_models(self, output):
-        """dynamics.py:393-410.  Reads this class's own files and the reference's (a list of gpytorch state dicts)."""
+        """dynamics.py:393-410.  Reads this class's own files and the reference's (a list of gpytorch state dicts).
+        Deliberate difference: the reference rebuilds its GPs on the RAW saved history here (:403) although it fitted
+        them on the normalised one (:326-334) and keeps normalising the queries (:375), so its loaded models are not the
+        models it saved; this loader restores what was saved (normalised history, as at fit time)."""
         if output is None:
             return
         try:
@@ -227,17 +239,23 @@ class DynamicsModel:
             train_x = torch.load('{}/gp_models_train_x.pkl'.format(output), weights_only=False)
             train_y = torch.load('{}/gp_models_train_y.pkl'.format(output), weights_only=False)
             self._install_gp_bank(np.asarray(train_x, np.float64), np.asarray(train_y, np.float64))
+            import os
+            raw64 = '{}/gp_models_raw_f64.pkl'.format(output)
+            raw64 = torch.load(raw64, map_location='cpu') if os.path.exists(raw64) else None
             for i in range(self.n_s):
-                self.disturb_estimators[i].load_state_dict(weights[i])
+                self.disturb_estimators[i].load_state_dict(weights[i] if raw64 is None else {"raw_float64": raw64[i]})
             self._gp_bank.build_posterior()
         except Exception:
             raise Exception('Could not load GP models from {}'.format(output))
 
     def save_disturbance_models(self, output):
-        """dynamics.py:412-423 (same three files, same gpytorch parameter names)."""
+        """dynamics.py:412-423: the same three files; gp_models.pkl holds one gpytorch-keyed state dict per GP (float32,
+        see BankMember.state_dict).  A fourth file, gp_models_raw_f64.pkl, keeps the float64 raw parameters this class
+        trains in; the reference ignores it, this class prefers it on load."""
         if not self.disturb_estimators or self.train_x is None or self.train_y is None:
             return
         torch.save([est.state_dict() for est in self.disturb_estimators], '{}/gp_models.pkl'.format(output))
+        torch.save(self._gp_bank.raw.detach().cpu().clone(), '{}/gp_models_raw_f64.pkl'.format(output))
         torch.save(self.train_x, '{}/gp_models_train_x.pkl'.format(output))
         torch.save(self.train_y, '{}/gp_models_train_y.pkl'.format(output))
 

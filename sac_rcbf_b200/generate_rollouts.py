@@ -7,10 +7,12 @@ arithmetic) and with DeviceReplayMemory (everything stays on the GPU, float32 ke
 the caller's generator (numpy global RNG on the host path like generate_rollouts.py:31, torch generator on the device
 path) and handed to the kernel as standard-normal `eps`, so a transition is a deterministic function of its inputs.
 
-Reference quirks kept: `reward_goal` is added twice when the goal is reached (:50,:53); `predict_next_state` is always
-called with the ORIGINAL `t_batch`, not the rolled one (:30); done rows are dropped from the observation batch only
-(:78-79), so k_horizon > 1 with Unicycle `done`s mis-aligns in the reference too -- here the time batch is shrunk
-together with the observations.
+Reference quirk kept: `reward_goal` is added twice when the goal is reached (:50,:53).
+Deliberate deviation for k_horizon > 1 (identical for the reference's k_horizon = 1 call, main.py:53-57): the reference
+hands `predict_next_state` the ORIGINAL `t_batch` at every horizon step (:30) and drops done rows from the observation
+batch only (:78-79), so after the first dropped row its time and observation batches no longer have the same length;
+here the time batch is rolled (t <- next_t) and shrunk together with the observations, which is what the pushed
+`t_batch_` / `next_t_batch_` of :71-72 intend.  A memory that stores no times (t = None, Unicycle) is passed through.
 """
 from copy import deepcopy
 
@@ -80,7 +82,7 @@ def generate_model_rollouts(env, memory_model, memory, agent, dynamics_model, k_
         memory.sample(batch_size=batch_size)
     on_device = torch.is_tensor(obs_batch)
     obs_batch_ = obs_batch.clone() if on_device else deepcopy(obs_batch)
-    t_batch_ = t_batch.clone() if on_device else deepcopy(t_batch)
+    t_batch_ = None if t_batch is None else (t_batch.clone() if on_device and torch.is_tensor(t_batch) else deepcopy(t_batch))
     n_s = dynamics_model.n_s
 
     for k in range(k_horizon):
@@ -100,5 +102,5 @@ def generate_model_rollouts(env, memory_model, memory, agent, dynamics_model, k_
                                 next_t_batch_)
         keep = ~done_batch_
         obs_batch_ = next_obs_batch_[keep]
-        t_batch_ = next_t_batch_[keep]
+        t_batch_ = None if next_t_batch_ is None else next_t_batch_[keep]
     return memory_model

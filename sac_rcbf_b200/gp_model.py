@@ -329,12 +329,32 @@ class BankMember:
         self.likelihood = self
 
     def state_dict(self):
+        """The key set `BaseGPy.state_dict()` has under gpytorch (gp_model.py:11-27: the three raw parameters plus the
+        constraint bounds and prior buffers gpytorch registers next to them), so that the reference's strict
+        `model.load_state_dict(weights[i])` (dynamics.py:404) finds every key and no unexpected one.  gpytorch is absent
+        from this image: the list follows gpytorch 1.x and is unverified here.  The float64 raw parameters (the bank
+        trains in float64) travel separately, see DynamicsModel.save_disturbance_models."""
         r = self.bank.raw[self.index].cpu()
-        return {_SD_KEYS[0]: r[0].reshape(1, 1).float(), _SD_KEYS[1]: r[1].reshape(()).float(),
-                _SD_KEYS[2]: r[2].reshape(1).float(), "raw_float64": r.clone()}
+        f = lambda v: torch.tensor(float(v))  # noqa: E731
+        pos_inf, prior_os = float("inf"), float(self.bank.prior_outputscale[self.index])
+        return {
+            "likelihood.noise_covar.raw_noise": r[2].reshape(1).float(),
+            "likelihood.noise_covar.raw_noise_constraint.lower_bound": f(1e-4),
+            "likelihood.noise_covar.raw_noise_constraint.upper_bound": f(pos_inf),
+            "covar_module.raw_outputscale": r[1].reshape(()).float(),
+            "covar_module.base_kernel.raw_lengthscale": r[0].reshape(1, 1).float(),
+            "covar_module.base_kernel.lengthscale_prior.loc": f(1e5),
+            "covar_module.base_kernel.lengthscale_prior.scale": f(1e-5),
+            "covar_module.base_kernel.raw_lengthscale_constraint.lower_bound": f(0.0),
+            "covar_module.base_kernel.raw_lengthscale_constraint.upper_bound": f(pos_inf),
+            "covar_module.outputscale_prior.loc": f(prior_os),
+            "covar_module.outputscale_prior.scale": f(1e-5),
+            "covar_module.raw_outputscale_constraint.lower_bound": f(0.0),
+            "covar_module.raw_outputscale_constraint.upper_bound": f(pos_inf),
+        }
 
     def load_state_dict(self, sd, strict=False):
-        if "raw_float64" in sd:
+        if "raw_float64" in sd:     # files written by round-1 builds
             raw = sd["raw_float64"].to(torch.float64)
         else:
             raw = torch.stack([sd[k].reshape(-1)[0].to(torch.float64) for k in _SD_KEYS])

@@ -336,6 +336,9 @@ def test_fewer_than_five_hazards(S):
     f64 = O.safe_action("Unicycle", tt(st), tt(ac), tt(mu), tt(sg), solver="exact", assembly_dtype=torch.float64, **kw).numpy()
     ok = np.abs(fe - f64).max(1) <= 2e-5
     assert ok.mean() > 0.995 and np.abs(out - fe)[ok].max() < ACT_TOL
+    # the 7-row system of get_cbf_qp_constraints goes through solve_qp too (padded to 9 rows inside)
+    xq = layer.solve_qp(P[:512], q[:512], G[:512].clone(), h[:512]).cpu().numpy()
+    assert np.abs(np.clip(ac[:512] + xq, -2.5, 2.5) - fe[:512])[ok[:512]].max() < ACT_TOL
 
 
 def test_trivial_instances_pass_through(uni):
@@ -491,6 +494,13 @@ def test_general_hazard_count_vs_golden(S, golden, name):
     assert rel < GRAD_TOL, rel
     o1 = layer.get_safe_action(*(t[0] for t in ins))
     assert o1.shape == (2,) and torch.equal(o1, out[0])
+    # solve_qp / cbf_layer on the (K + 4)-row system (padded to the next instantiated row count inside)
+    xq = layer.solve_qp(_cuda(g["P"]), _cuda(g["q"]), _cuda(g["G"].copy()), _cuda(g["h"]))
+    assert xq.shape == (g["G"].shape[0], 2) and np.abs(xq.cpu().numpy() - g["x_exact"][:, :2]).max() < ACT_TOL
+    hq = _cuda(g["hn"]).double().requires_grad_(True)
+    xs = layer.cbf_layer(_cuda(g["P"]).double(), _cuda(g["q"]).double(), _cuda(g["Gn"]).double(), hq)
+    xs.sum().backward()
+    assert hq.grad.shape == hq.shape and torch.isfinite(hq.grad).all()
     bad = ins[0].clone()
     bad[3, 0] = float("nan")
     with pytest.raises(Exception, match="QP Failed to solve"):
