@@ -8,6 +8,56 @@
 
 using namespace rcbf;
 
+// The layer on an arbitrary hazard set (rcbf_general.cu composes the same templated pieces per thread): NH CBF rows,
+// hazards beyond K padded 1e4 m away.  Forward + exact active-set gradient.
+template <int NH>
+static void general_one(const UnicycleParams& p, const float* hz_xy, int K, const float* st, const float* ac,
+                        const float* mu, const float* sg, const float* gout, float* out, float* ga, int* status) {
+  constexpr int M = NH + 4;
+  using Pat = CbfPat<NH, 2>;
+  float hz[NH][2];
+  for (int k = 0; k < NH; ++k) {
+    hz[k][0] = k < K ? hz_xy[2 * k] : 1.0e4f;
+    hz[k][1] = k < K ? hz_xy[2 * k + 1] : 1.0e4f + 10.0f * (float)(k - K);
+  }
+  float sn, cs, Lg[NH][2], h[M], G[M][3];
+  sincos_t(st[2], &sn, &cs);
+  assemble_unicycle_n<float, NH>(p, hz, st, sn, cs, ac, mu, sg, Lg, h);
+  for (int k = 0; k < NH; ++k) { G[k][0] = -Lg[k][0]; G[k][1] = -Lg[k][1]; G[k][2] = -1.0f; }
+  for (int cc = 0; cc < 2; ++cc)
+    for (int j = 0; j < 3; ++j) { G[NH + 2 * cc][j] = (j == cc) ? 1.0f : 0.0f; G[NH + 2 * cc + 1][j] = (j == cc) ? -1.0f : 0.0f; }
+  bool triv, nan;
+  classify_raw<M>(h, triv, nan);
+  NormSolution<3, M> sol;
+  sol.x[0] = sol.x[1] = sol.x[2] = 0.0;
+  sol.status = nan ? RCBF_NAN : RCBF_OK_TRIVIAL;
+  sol.mask = 0u;
+  if (!triv && !nan) {
+    solve_raw_fast<Pat, 3, M>(G, h, p.p_diag, false, sol);
+    if (sol.status == RCBF_PENDING) {
+      Normalised<3, M> nrm;
+      normalise_rows<Pat, 3, M>(G, h, nrm);
+      solve_normalised_full<Pat, 3, M>(nrm, p.p_diag, false, sol);
+    }
+  }
+  *status = sol.status;
+  for (int c = 0; c < 2; ++c) out[c] = clampf(ac[c] + (float)sol.x[c], p.u_min[c], p.u_max[c]);
+  if (sol.status == RCBF_OK_TRIVIAL) {
+    for (int c = 0; c < 2; ++c) ga[c] = (ac[c] >= p.u_min[c] && ac[c] <= p.u_max[c]) ? gout[c] : 0.f;
+    return;
+  }
+  float r[M][2];
+  for (int k = 0; k < NH; ++k) { r[k][0] = Lg[k][0]; r[k][1] = Lg[k][1]; }
+  for (int c = 0; c < 2; ++c) {
+    r[NH + 2 * c][0] = (c == 0) ? -1.f : 0.f; r[NH + 2 * c][1] = (c == 1) ? -1.f : 0.f;
+    r[NH + 2 * c + 1][0] = (c == 0) ? 1.f : 0.f; r[NH + 2 * c + 1][1] = (c == 1) ? 1.f : 0.f;
+  }
+  double pisd[3]; float pisf[3];
+  pis_of<3, M>(p.p_diag, pisd, pisf);
+  safe_action_bwd_active<Pat, 3, M, 2>(G, h, r, pisd, sol.mask == kMaskUnknown ? 0u : sol.mask, ac, p.u_min, p.u_max, gout, ga);
+}
+
+
 extern "C" {
 
 void hs_unicycle_safe_action(int64_t n, const float* st, const float* ac, const float* mu, const float* sg,
@@ -118,6 +168,15 @@ void hs_cars_bwd(int64_t n, const float* st, const float* ac, const float* sg, c
     pis_of<kCarsNZ, kCarsM>(p->p_diag, pisd, pisf);
     safe_action_bwd_active<CarsPat, kCarsNZ, kCarsM, 1>(w.raw.G, w.raw.h, r, pisd, w.sol.mask == kMaskUnknown ? 0u : w.sol.mask,
                                                         ac + i, lo, hi, gout + i, ga_active + i);
+  }
+}
+
+void hs_unicycle_general(int64_t n, const float* st, const float* ac, const float* mu, const float* sg, const float* gout,
+                         const UnicycleParams* p, const float* hz_xy, int K, float* out, float* ga, int* status) {
+#pragma omp parallel for schedule(static)
+  for (int64_t i = 0; i < n; ++i) {
+    if (K <= 8) general_one<8>(*p, hz_xy, K, st + 3 * i, ac + 2 * i, mu + 3 * i, sg + 3 * i, gout + 2 * i, out + 2 * i, ga + 2 * i, status + i);
+    else general_one<12>(*p, hz_xy, K, st + 3 * i, ac + 2 * i, mu + 3 * i, sg + 3 * i, gout + 2 * i, out + 2 * i, ga + 2 * i, status + i);
   }
 }
 

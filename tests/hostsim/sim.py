@@ -76,3 +76,15 @@ def cars_bwd(st, ac, sg, gout, params):
     lib().hs_cars_bwd(C.c_int64(n), _p(st, C.c_float), _p(ac, C.c_float), _p(sg, C.c_float), _p(gout, C.c_float),
                       C.byref(params), _p(gd, C.c_float), _p(ga, C.c_float), _p(status, C.c_int))
     return gd, ga, status
+
+
+def unicycle_general(st, ac, mu, sg, gout, params, hazards):
+    """Layer on K = len(hazards) (1..12) hazards: (safe action, grad_action of the exact active-set form, status)."""
+    n = st.shape[0]
+    st, ac, mu, sg, gout = (np.ascontiguousarray(a, np.float32) for a in (st, ac, mu, sg, gout))
+    hz = np.ascontiguousarray(hazards, np.float32)
+    out, ga, status = np.zeros((n, 2), np.float32), np.zeros((n, 2), np.float32), np.zeros(n, np.int32)
+    lib().hs_unicycle_general(C.c_int64(n), _p(st, C.c_float), _p(ac, C.c_float), _p(mu, C.c_float), _p(sg, C.c_float),
+                              _p(gout, C.c_float), C.byref(params), _p(hz, C.c_float), C.c_int(hz.shape[0]),
+                              _p(out, C.c_float), _p(ga, C.c_float), _p(status, C.c_int))
+    return out, ga, status

@@ -104,3 +104,42 @@ def test_core_kkt_conditions_on_extreme_inputs():
     # and the interior-point-only mode agrees with the presolve mode
     ipm = sim.unicycle_safe_action(st, ac, mu, sg, params, mode=1)
     assert (ipm["status"] <= 2).all() and np.abs(ipm["out"] - fast["out"]).max() < 1e-5
+
+
+def test_backward_forms_on_host(golden):
+    """The two implicit-KKT backward forms of csrc/rcbf_backward.cuh on the host build: the dense qpth-clamp form on saved
+    x / lam / slack and the exact active-set form the compact kernels run (from the certified mask alone) agree with
+    each other and with the golden gradients (reference CBFQPLayer + restated qpth backward)."""
+    for mode, name in (("uni", "unicycle_layer_b256.npz"), ("cars", "cars_layer_b512.npz")):
+        g = golden(name)
+        gb = float(g["gamma_b"])
+        if mode == "uni":
+            gd, ga, status = sim.unicycle_bwd(g["state"], g["action"], g["mean"], g["sigma"], g["grad_w"],
+                                              PR.unicycle_params(gamma_b=gb))
+        else:
+            gd, ga, status = sim.cars_bwd(g["state"], g["action"], g["sigma"], g["grad_w"], PR.cars_params(gamma_b=gb))
+        ref = g["grad_action"]
+        assert (status <= 1).all()
+        assert np.linalg.norm(gd - ref) / np.linalg.norm(ref) < 1e-5
+        assert np.linalg.norm(ga - ref) / np.linalg.norm(ref) < 1e-5
+    B = 100000
+    st, ac, mu, sg = O.synth_unicycle(B, seed=4)
+    go = np.random.default_rng(4).standard_normal((B, 2)).astype(np.float32)
+    gd, ga, status = sim.unicycle_bwd(st, ac, mu, sg, go, PR.unicycle_params(gamma_b=20.0))
+    assert np.linalg.norm(gd - ga) / np.linalg.norm(gd) < 1e-4      # qpth's 1e-8 clamps vs their limit
+    triv = status == 0
+    assert 0.5 < triv.mean() < 0.8 and np.array_equal(ga[triv], go[triv])   # |u_rl| <= 1 < 2.5: the clamp mask is all-pass
+
+
+@pytest.mark.parametrize("name", ["unicycle_layer_7haz_b256.npz", "unicycle_layer_11haz_b128.npz"])
+def test_general_hazard_count_on_host(golden, name):
+    """The row-count-templated source (assemble_unicycle_n, raw-row presolve, certificate, exact active-set backward) at
+    NH = 8 / 12 CBF rows, composed like rcbf_general.cu does per thread, against the reference-generated fixtures."""
+    g = golden(name)
+    out, ga, status = sim.unicycle_general(g["state"], g["action"], g["mean"], g["sigma"], g["grad_w"],
+                                           PR.unicycle_params(gamma_b=float(g["gamma_b"])), g["hazards"])
+    assert (status <= 1).all() and 0 < (status == 1).sum() < len(status)
+    assert np.abs(out - g["safe_action"]).max() < 1e-4
+    ex = np.clip(g["action"] + g["x_exact"][:, :2].astype(np.float32), -2.5, 2.5)
+    assert np.abs(out - ex).max() < 1e-4
+    assert np.linalg.norm(ga - g["grad_action"]) / np.linalg.norm(g["grad_action"]) < 1e-3
