@@ -38,14 +38,23 @@ namespace rcbf {
 #define RCBF_S2_MINB 1     // resident blocks per SM (A/B on B200: 1 x 12 warps > 3 x 4 warps > 2 x 6 warps)
 #endif
 #ifndef RCBF_S2_WARPS
-#define RCBF_S2_WARPS 12   // warps per block
+#define RCBF_S2_WARPS 16   // warps per block
+#endif
+#ifndef RCBF_S2_CARRY_SINCOS
+#define RCBF_S2_CARRY_SINCOS 0  // 1: keep sin / cos of the heading from the assembly for env.step (1.5 KB of shared memory
+#endif                          //    per warp); 0: recompute them in the finish (same function, same input: same bits)
+#ifndef RCBF_S2_RING
+#define RCBF_S2_RING 86    // problem ring entries
 #endif
 #ifndef RCBF_S2_MIN_N
 #define RCBF_S2_MIN_N 4096  // below this the one-per-lane kernel spreads the few tiles over more warps
 #endif
 constexpr int kS2Warps = RCBF_S2_WARPS;
 constexpr int kS2Threads = 32 * kS2Warps;
-constexpr int kS2Ring = 95;  // <= 31 problems left over + 64 new ones
+constexpr int kS2Ring = RCBF_S2_RING;  // a tile pushes <= 64 problems on top of the < 32 the B-steps left over; what does
+                                       // not fit (<= 31 + 64 - kS2Ring) is parked in the landing slot of the next tile
+constexpr bool kS2CarrySinCos = RCBF_S2_CARRY_SINCOS != 0;
+static_assert(kS2Ring >= 75 && kS2Ring <= 95, "31 + 64 - kS2Ring parked problems must fit a landing slot (20 entries)");
 
 // bulk stores (shared -> global) + their completion
 __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
@@ -73,16 +82,20 @@ struct alignas(16) S2Warp {
   };
   In in[4];                 // tiles k-2 (finishing), k-1, k, k+1 (in flight)
   float mu[192], sg[192];   // only the assembly reads them: single buffer, refilled right after the A-step's read
-  float sn[3][64], cs[3][64];  // sin / cos of the heading, kept from the assembly for env.step
+  float sn[kS2CarrySinCos && kFused ? 3 : 1][kS2CarrySinCos && kFused ? 64 : 4];  // sin / cos of the heading, kept from
+  float cs[kS2CarrySinCos && kFused ? 3 : 1][kS2CarrySinCos && kFused ? 64 : 4];  // the assembly for env.step (optional)
   float4 ring[kS2Ring][4];  // problem ring: Lg[5][2], h[5], tag
   // (the observation rows of the tile being finished, 64 x 28 B = exactly one In slot, are staged in that tile's own
   //  slot once its state / step / action have been read, and leave from there by one bulk store)
   uint8_t cls[3][64];       // per instance: RCBF_OK_TRIVIAL / RCBF_OK_CERTIFIED / RCBF_NAN / RCBF_PENDING
-  uint16_t amask[kFused ? 1 : 3][64];  // layer-only kernel: active set of the certified solution (saved for the backward)
+  uint16_t amask[kFused ? 1 : 3][kFused ? 2 : 64];  // layer-only kernel: active set of the certified solution (saved for the backward)
   uint64_t bar[2];
 };
 
 static_assert(sizeof(S2Warp<true>::In) == 64 * 7 * 4, "a fused input slot doubles as the staging of the tile's observation rows");
+static_assert(sizeof(S2Warp<true>) * kS2Warps * RCBF_S2_MINB + 1024 * RCBF_S2_MINB <= 233472,
+              "shared memory of the resident blocks (+ 1 KB reserved per block) must fit the 228 KB of an SM");
+static_assert(sizeof(S2Warp<true>) * kS2Warps + 256 <= 232448, "dynamic + static shared memory of one block <= 227 KB");
 
 #ifdef RCBF_S2_MAXNREG
 #define RCBF_S2_BOUNDS __maxnreg__(RCBF_S2_MAXNREG)
@@ -148,6 +161,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
     const bool have_tile = tile < ntiles;
     pk1 = pk;
     pk = 0;
+    int n_aux = 0;  // problems of this tile parked outside the (full) ring
     if (have_tile) {  // ---------------------------------------------------------------- A-step
       typename WS::In& si = sh.in[k & 3];
       mbar_wait(&sh.bar[k & 1], (k >> 1) & 1);
@@ -174,7 +188,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
       __syncwarp();
       f2 sn, cs;
       sincos_v<f2>(st[2], &sn, &cs);
-      if (kFused) {
+      if (kFused && kS2CarrySinCos) {
         reinterpret_cast<float2*>(sh.sn[r3])[lane] = make_float2(sn.lo(), sn.hi());
         reinterpret_cast<float2*>(sh.cs[r3])[lane] = make_float2(cs.lo(), cs.hi());
       }
@@ -208,21 +222,31 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         reinterpret_cast<uchar2*>(sh.cls[r3])[lane] = c2;
         if (!kFused) reinterpret_cast<uint32_t*>(sh.amask[r3])[lane] = 0u;
       }
-      if (lane == 0 && tile1 < ntiles) {
-        // slot (k+1) & 3 belonged to the tile finished in the previous iteration; the bulk store of its observation rows
-        // (staged in that slot) was issued then and has long read it
-        if (kFused) bulk_wait_read0();
-        issue(tile1, k + 1);
-      }
       const unsigned b0 = __ballot_sync(0xffffffffu, need0), b1 = __ballot_sync(0xffffffffu, need1);
       const int n0 = __popc(b0);
+      pk = n0 + __popc(b1);
+      // The ring holds kS2Ring problems; the B-step loop leaves < 32, so a tile with more than kS2Ring - 31 problems may
+      // not fit (rare: > 55 of 64 instances need a solve).  The excess (<= 9) is parked in the landing slot of tile k + 1
+      // -- whose prefetch is then delayed until the first B-step below has made room -- and enters the ring there.
+      const int cap = kS2Ring - qn;
+      n_aux = pk > cap ? pk - cap : 0;
+      // slot (k+1) & 3 belonged to the tile finished in the previous iteration; the bulk store of its observation rows
+      // (staged in that slot) was issued then and has long read it
+      if (lane == 0) {
+        if (kFused && (n_aux != 0 || tile1 < ntiles)) bulk_wait_read0();
+        if (n_aux == 0 && tile1 < ntiles) issue(tile1, k + 1);
+      }
+      if (n_aux != 0) __syncwarp();
+      float4(*aux)[4] = reinterpret_cast<float4(*)[4]>(&sh.in[(k + 1) & 3]);
       const int tagbase = ((k & 3) << 8) | (r3 << 6) | (2 * lane);
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         if (hh ? need1 : need0) {
-          int slot = head + qn + (hh ? n0 + __popc(b1 & lt_mask) : __popc(b0 & lt_mask));
+          const int idx = hh ? n0 + __popc(b1 & lt_mask) : __popc(b0 & lt_mask);
+          int slot = head + qn + idx;
           slot -= slot >= kS2Ring ? kS2Ring : 0;
           slot -= slot >= kS2Ring ? kS2Ring : 0;
+          float4* dst = idx < cap ? sh.ring[slot] : aux[idx - cap];
           float v[16];
 #pragma unroll
           for (int r = 0; r < kUniHaz; ++r) {
@@ -232,11 +256,10 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
           }
           v[15] = __int_as_float(tagbase + hh);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) sh.ring[slot][q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
       }
-      pk = n0 + __popc(b1);
-      qn += pk;
+      qn += pk - n_aux;
       c_nan += (nan[0] ? 1 : 0) + (nan[1] ? 1 : 0);
       c_triv += ((!need0 && !nan[0]) ? 1 : 0) + ((!need1 && !nan[1]) ? 1 : 0);
     } else {
@@ -294,6 +317,20 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
       head -= head >= kS2Ring ? kS2Ring : 0;
       qn -= take;
       __syncwarp();
+      if (n_aux != 0) {  // (rare) the parked problems enter the ring, then the delayed prefetch of tile k + 1 goes out
+        const float4(*aux)[4] = reinterpret_cast<const float4(*)[4]>(&sh.in[(k + 1) & 3]);
+        if (lane < n_aux) {
+          int slot = head + qn + lane;
+          slot -= slot >= kS2Ring ? kS2Ring : 0;
+          slot -= slot >= kS2Ring ? kS2Ring : 0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) sh.ring[slot][q] = aux[lane][q];
+        }
+        qn += n_aux;
+        n_aux = 0;
+        __syncwarp();
+        if (lane == 0 && tile1 < ntiles) issue(tile1, k + 1);
+      }
     }
 
     // ---------------------------------------------------------------- finish(tile k-2): whole tile, in place, TMA out
@@ -315,14 +352,21 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         const float4 qb = reinterpret_cast<const float4*>(sf.st)[2 * lane + 1];
         const int2 sp = reinterpret_cast<const int2*>(sf.step)[lane];
         const float4 us4 = reinterpret_cast<const float4*>(sf.ac)[lane];
-        const float2 sn2 = reinterpret_cast<const float2*>(sh.sn[rf])[lane];
-        const float2 cs2 = reinterpret_cast<const float2*>(sh.cs[rf])[lane];
         f2 v[3] = {f2(qa.x, qb.x), f2(qa.y, qb.y), f2(qa.z, qb.z)};
+        f2 snf, csf;
+        if (kS2CarrySinCos) {
+          const float2 sn2 = reinterpret_cast<const float2*>(sh.sn[rf])[lane];
+          const float2 cs2 = reinterpret_cast<const float2*>(sh.cs[rf])[lane];
+          snf = f2_pin(sn2.x, sn2.y);
+          csf = f2_pin(cs2.x, cs2.y);
+        } else {
+          sincos_v<f2>(f2_pin(qa.z, qb.z), &snf, &csf);   // what the A-step computed from the same heading
+        }
         f2 last(qa.w, qb.w);
         typename VecOf<f2>::ivec stp = {sp.x, sp.y};
         const f2 us[2] = {f2(us4.x, us4.z), f2(us4.y, us4.w)};
         UniEnvOutV<f2> o;
-        unicycle_env_step_v<f2>(ef, v, last, stp, us, f2_pin(sn2.x, sn2.y), f2_pin(cs2.x, cs2.y), o);
+        unicycle_env_step_v<f2>(ef, v, last, stp, us, snf, csf, o);
         if (ef.auto_reset && __any_sync(0xffffffffu, o.done.x || o.done.y)) {  // (a finished episode is a rare event)
           v[0] = t_sel(o.done, f2(ef.init_x), v[0]);
           v[1] = t_sel(o.done, f2(ef.init_y), v[1]);
