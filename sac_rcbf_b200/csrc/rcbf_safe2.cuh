@@ -128,6 +128,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
   int pk = 0, pk1 = 0;           // problems pushed by tiles k, k-1 (the newest pk + pk1 entries of the ring)
   int r3 = 0;                    // k % 3
   int c_nan = 0, c_triv = 0, c_pend = 0, c_iters = 0;
+  int n_solve = 0, n_tiles = 0;  // (warp-uniform) problems pushed / tiles assembled by this warp
   constexpr uint32_t kInBytes = (kFused ? 1024 + 256 : 768) + 512 + 768 + 768;
 
   // lane 0 puts tile t in flight into slot k & 3 (+ the mu / sigma buffer).  cp.async.bulk is a uniform-datapath
@@ -166,6 +167,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
     pk = 0;
     int n_aux = 0;  // problems of this tile parked outside the (full) ring
     if (have_tile) {  // ---------------------------------------------------------------- A-step
+      ++n_tiles;
       typename WS::In& si = sh.in[k & 3];
       mbar_wait(&sh.bar[k & 1], (k >> 1) & 1);
       f2 st[3], u[2], mu[3], sg[3];
@@ -198,27 +200,29 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
       f2 Lg[kUniHaz][2], h[M];
       assemble_unicycle_v<f2>(p, st, sn, cs, u, mu, sg, Lg, h);
       // trivial test on the raw rows (h >= 0 on every row <=> x = 0 optimal) and NaN screen, per half
+      // (a NaN in Lg[i] reaches h[i] through the Lg . u term whatever u is, so screening the 9 right-hand sides covers
+      //  the 10 coefficients as well)
       bool triv[2], nan[2];
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
-        float hv[M], gv[2 * kUniHaz];
+        float hv[M];
 #pragma unroll
         for (int r = 0; r < M; ++r) hv[r] = hh ? h[r].hi() : h[r].lo();
-#pragma unroll
-        for (int r = 0; r < kUniHaz; ++r) {
-          gv[2 * r] = hh ? Lg[r][0].hi() : Lg[r][0].lo();
-          gv[2 * r + 1] = hh ? Lg[r][1].hi() : Lg[r][1].lo();
-        }
         classify_raw<M>(hv, triv[hh], nan[hh]);
-        nan[hh] = nan[hh] || any_nan<2 * kUniHaz>(gv);
       }
       const bool need0 = !triv[0] && !nan[0], need1 = !triv[1] && !nan[1];
       // trivial / NaN instances: the clamped action replaces the nominal one in the slot (diff_cbf_qp.py:77)
       {
-        const float z0 = nan[0] ? NAN : 0.f, z1 = nan[1] ? NAN : 0.f;
+        // clamp, then NaN for a NaN instance (torch.clamp propagates it; a NaN action makes its rows NaN, i.e. nan[hh])
         float2* acp = reinterpret_cast<float2*>(si.ac) + 2 * lane;
-        if (!need0) acp[0] = make_float2(clampf(u[0].lo() + z0, p.u_min[0], p.u_max[0]), clampf(u[1].lo() + z0, p.u_min[1], p.u_max[1]));
-        if (!need1) acp[1] = make_float2(clampf(u[0].hi() + z1, p.u_min[0], p.u_max[0]), clampf(u[1].hi() + z1, p.u_min[1], p.u_max[1]));
+        if (!need0) {
+          const float a0 = fminf(fmaxf(u[0].lo(), p.u_min[0]), p.u_max[0]), a1 = fminf(fmaxf(u[1].lo(), p.u_min[1]), p.u_max[1]);
+          acp[0] = make_float2(nan[0] ? NAN : a0, nan[0] ? NAN : a1);
+        }
+        if (!need1) {
+          const float a0 = fminf(fmaxf(u[0].hi(), p.u_min[0]), p.u_max[0]), a1 = fminf(fmaxf(u[1].hi(), p.u_min[1]), p.u_max[1]);
+          acp[1] = make_float2(nan[1] ? NAN : a0, nan[1] ? NAN : a1);
+        }
         uchar2 c2;
         c2.x = (unsigned char)(nan[0] ? RCBF_NAN : (need0 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
         c2.y = (unsigned char)(nan[1] ? RCBF_NAN : (need1 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
@@ -246,8 +250,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
       for (int hh = 0; hh < 2; ++hh) {
         if (hh ? need1 : need0) {
           const int idx = hh ? n0 + __popc(b1 & lt_mask) : __popc(b0 & lt_mask);
-          int slot = head + qn + idx;
-          slot -= slot >= kS2Ring ? kS2Ring : 0;
+          int slot = head + qn + idx;                        // head < kS2Ring and qn + idx < kS2Ring when it is used
           slot -= slot >= kS2Ring ? kS2Ring : 0;
           float4* dst = idx < cap ? sh.ring[slot] : aux[idx - cap];
           float v[16];
@@ -263,8 +266,8 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         }
       }
       qn += pk - n_aux;
-      c_nan += (nan[0] ? 1 : 0) + (nan[1] ? 1 : 0);
-      c_triv += ((!need0 && !nan[0]) ? 1 : 0) + ((!need1 && !nan[1]) ? 1 : 0);
+      if (__any_sync(0xffffffffu, nan[0] || nan[1])) c_nan += (nan[0] ? 1 : 0) + (nan[1] ? 1 : 0);   // (rare)
+      n_solve += pk;   // warp-uniform: trivial instances = 64 * tiles - solved - NaN, taken at the end
     } else {
       ++after;
     }
@@ -324,7 +327,6 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         const float4(*aux)[4] = reinterpret_cast<const float4(*)[4]>(&sh.in[(k + 1) & 3]);
         if (lane < n_aux) {
           int slot = head + qn + lane;
-          slot -= slot >= kS2Ring ? kS2Ring : 0;
           slot -= slot >= kS2Ring ? kS2Ring : 0;
 #pragma unroll
           for (int q = 0; q < 4; ++q) sh.ring[slot][q] = aux[lane][q];
@@ -443,7 +445,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
   // (the counters go out BEFORE the tail: nothing of this function's state is live across the call)
   if (ws != nullptr) {
     c_nan = __reduce_add_sync(0xffffffffu, c_nan);
-    c_triv = __reduce_add_sync(0xffffffffu, c_triv);
+    c_triv = 64 * n_tiles - n_solve - c_nan;
     c_pend = __reduce_add_sync(0xffffffffu, c_pend);
     c_iters = __reduce_add_sync(0xffffffffu, c_iters);
     if (lane == 0) {
