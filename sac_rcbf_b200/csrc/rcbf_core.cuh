@@ -981,9 +981,30 @@ RCBF_HD float min3f(float a, float b, float c) { return fminf(fminf(a, b), c); }
 // negative (a drop would be needed) or NZ rows do not make the point feasible -- those instances go to the
 // interior-point solver.  The returned mask is only a GUESS; the float64 certificate decides.
 // (Rows are scored as assembled, see above; a row that entered the active set is never picked again.)
+// How the presolve gets hold of the raw row it has just picked (index wi, a run-time value): by default a chain of
+// selects over the register-resident rows; a caller whose problem also sits in addressable memory (the shared-memory ring
+// of k_safe2) passes a fetcher that reads the row there instead -- same values, a fraction of the instructions.
 template <typename Pat, int NZ, int M>
+struct SelectRowFetch {
+  RCBF_HD void operator()(int wi, const float G[M][NZ], const float h[M], float g[NZ], float& hh) const {
+    RCBF_UNROLL
+    for (int j = 0; j < NZ; ++j) g[j] = 0.f;
+    hh = 0.f;
+    RCBF_UNROLL
+    for (int i = 0; i < M; ++i) {
+      const bool put = (i == wi);
+      RCBF_UNROLL
+      for (int j = 0; j < NZ; ++j)
+        if (Pat::nz(i, j)) g[j] = put ? G[i][j] : g[j];
+      hh = put ? h[i] : hh;
+    }
+  }
+};
+
+template <typename Pat, int NZ, int M, typename Fetch = SelectRowFetch<Pat, NZ, M>>
 RCBF_HD bool lnp_greedy_raw(const float G[M][NZ], const float h[M], const float pis[NZ], float A[M][NZ],
-                            float Rg[NZ][NZ], float rbg[NZ], uint32_t& mask_out, int& rounds) {
+                            float Rg[NZ][NZ], float rbg[NZ], uint32_t& mask_out, int& rounds,
+                            const Fetch& fetch = Fetch()) {
   static_assert(M <= 16, "the row index travels in 4 mantissa bits");
   float inv_norm[M];
   RCBF_UNROLL
@@ -1037,18 +1058,11 @@ RCBF_HD bool lnp_greedy_raw(const float G[M][NZ], const float h[M], const float 
     const int wi = key_index(worst);
     mask |= 1u << wi;
     // gather the raw row and normalise it (diff_cbf_qp.py:103-106): these are the QP data of the reference
-    float g[NZ], hh = 0.f;
+    float g[NZ], hh;
+    fetch(wi, G, h, g, hh);
     RCBF_UNROLL
-    for (int j = 0; j < NZ; ++j) g[j] = 0.f;
-    RCBF_UNROLL
-    for (int i = 0; i < M; ++i) {
-      const bool put = (i == wi);
-      RCBF_UNROLL
-      for (int j = 0; j < NZ; ++j)
-        if (Pat::nz(i, j)) g[j] = put ? G[i][j] : g[j];
-      hh = put ? h[i] : hh;
-      inv_norm[i] = put ? 0.f : inv_norm[i];  // a row of the active set is never picked again (its raw slack is only
-    }                                         // zero up to the rounding of the normalised quotients)
+    for (int i = 0; i < M; ++i)               // a row of the active set is never picked again (its raw slack is only
+      inv_norm[i] = (i == wi) ? 0.f : inv_norm[i];  // zero up to the rounding of the normalised quotients)
     {
       float gm = 0.f;
       RCBF_UNROLL
@@ -1190,9 +1204,9 @@ RCBF_HD bool lnp_certify_raw(const float G[M][NZ], const float h[M], const float
 
 // Fast path of one QP given its rows as assembled (presolve mode): greedy guess, float64 certificate, and -- for the
 // callers that save them -- the dense multipliers / slacks of the normalised problem.
-template <typename Pat, int NZ, int M>
+template <typename Pat, int NZ, int M, typename Fetch = SelectRowFetch<Pat, NZ, M>>
 RCBF_HD void solve_raw_fast(const float G[M][NZ], const float h[M], const float p_diag[NZ], bool want_aux,
-                            NormSolution<NZ, M>& o) {
+                            NormSolution<NZ, M>& o, const Fetch& fetch = Fetch()) {
   double pisd[NZ];
   float pisf[NZ];
   pis_of<NZ, M>(p_diag, pisd, pisf);
@@ -1200,7 +1214,7 @@ RCBF_HD void solve_raw_fast(const float G[M][NZ], const float h[M], const float 
   uint32_t mask;
   int rounds;
   float A[M][NZ], Rg[NZ][NZ], rbg[NZ];
-  const bool guess = lnp_greedy_raw<Pat, NZ, M>(G, h, pisf, A, Rg, rbg, mask, rounds);
+  const bool guess = lnp_greedy_raw<Pat, NZ, M, Fetch>(G, h, pisf, A, Rg, rbg, mask, rounds, fetch);
   o.status = RCBF_PENDING;
   o.iters = rounds;
   o.mask = mask;

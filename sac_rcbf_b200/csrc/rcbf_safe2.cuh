@@ -73,6 +73,29 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// The presolve's row fetch for a problem that sits in the ring (rcbf_core.cuh: SelectRowFetch): a CBF row is read back
+// from the slot (G[i][:2] = -Lg[i], G[i][2] = -1), an actuator row is rebuilt from its index.  Same values as the
+// register-resident copy the default fetch would pick through a 9-way select chain.
+struct S2RowFetch {
+  const float* slot;  // Lg[5][2], h[5], tag
+  __device__ __forceinline__ void operator()(int wi, const float G[kUniM][kUniNZ], const float h[kUniM], float g[kUniNZ],
+                                             float& hh) const {
+    if (wi < kUniHaz) {
+      const float2 l = *reinterpret_cast<const float2*>(slot + 2 * wi);
+      g[0] = -l.x;
+      g[1] = -l.y;
+      g[2] = -1.0f;
+      hh = slot[2 * kUniHaz + wi];
+    } else {  // rows 5..8 = +e_0, -e_0, +e_1, -e_1 on the controls (diff_cbf_qp.py:365-377)
+      const int a = wi - kUniHaz;
+      g[0] = a == 0 ? 1.0f : (a == 1 ? -1.0f : 0.0f);
+      g[1] = a == 2 ? 1.0f : (a == 3 ? -1.0f : 0.0f);
+      g[2] = 0.0f;
+      hh = a == 0 ? h[kUniHaz] : (a == 1 ? h[kUniHaz + 1] : (a == 2 ? h[kUniHaz + 2] : h[kUniHaz + 3]));
+    }
+  }
+};
+
 template <bool kFused>
 struct alignas(16) S2Warp {
   struct alignas(16) In {   // TMA landing slot of one tile; after the A-/B-steps `ac` holds the clamped SAFE action,
@@ -159,6 +182,8 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
   if (lane == 0 && tile < ntiles) issue(tile, 0);
 
   const float reset_dist = unicycle_reset_dist(ef);
+  // per-instance class bytes: only the layer kernel (meta) and callers that want a status array need them
+  const bool want_cls = !kFused || a.status != nullptr;
   int after = 0;  // iterations past this warp's last tile (the last two tiles are finished then)
 #pragma unroll 1
   for (int k = 0;; ++k) {
@@ -223,10 +248,12 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
           const float a0 = fminf(fmaxf(u[0].hi(), p.u_min[0]), p.u_max[0]), a1 = fminf(fmaxf(u[1].hi(), p.u_min[1]), p.u_max[1]);
           acp[1] = make_float2(nan[1] ? NAN : a0, nan[1] ? NAN : a1);
         }
-        uchar2 c2;
-        c2.x = (unsigned char)(nan[0] ? RCBF_NAN : (need0 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
-        c2.y = (unsigned char)(nan[1] ? RCBF_NAN : (need1 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
-        reinterpret_cast<uchar2*>(sh.cls[r3])[lane] = c2;
+        if (want_cls) {
+          uchar2 c2;
+          c2.x = (unsigned char)(nan[0] ? RCBF_NAN : (need0 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
+          c2.y = (unsigned char)(nan[1] ? RCBF_NAN : (need1 ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
+          reinterpret_cast<uchar2*>(sh.cls[r3])[lane] = c2;
+        }
         if (!kFused) reinterpret_cast<uint32_t*>(sh.amask[r3])[lane] = 0u;
       }
       const unsigned b0 = __ballot_sync(0xffffffffu, need0), b1 = __ballot_sync(0xffffffffu, need1);
@@ -307,10 +334,11 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         float Gr[M][NZ], hr[M];
         E::unpack_raw(w, p, Gr, hr);
         NormSolution<NZ, M> sol;
-        solve_raw_fast<UniPat, NZ, M>(Gr, hr, p.p_diag, false, sol);
+        solve_raw_fast<UniPat, NZ, M, S2RowFetch>(Gr, hr, p.p_diag, false, sol,
+                                                  S2RowFetch{reinterpret_cast<const float*>(sh.ring[slot])});
         if (sol.status == RCBF_PENDING) {
           *up = make_float2(__uint_as_float(kPendingBits), 0.f);
-          sh.cls[(tag >> 6) & 3][pos] = (unsigned char)RCBF_PENDING;
+          if (want_cls) sh.cls[(tag >> 6) & 3][pos] = (unsigned char)RCBF_PENDING;
           c_pend += 1;
         } else {
           *up = make_float2(clampf(uu.x + (float)sol.x[0], p.u_min[0], p.u_max[0]),
@@ -344,8 +372,17 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
       typename WS::In& sf = sh.in[(k + 2) & 3];
       const int rf = r3 == 2 ? 0 : r3 + 1;                 // (k - 2) % 3 == (k + 1) % 3
       const int64_t i0 = (int64_t)ft << 6;
-      const uchar2 cl = reinterpret_cast<const uchar2*>(sh.cls[rf])[lane];
-      const bool pend0 = cl.x == RCBF_PENDING, pend1 = cl.y == RCBF_PENDING;
+      uchar2 cl = make_uchar2(0, 0);
+      bool pend0, pend1;
+      if (want_cls) {
+        cl = reinterpret_cast<const uchar2*>(sh.cls[rf])[lane];
+        pend0 = cl.x == RCBF_PENDING;
+        pend1 = cl.y == RCBF_PENDING;
+      } else {  // fused step without a status output: a pending instance is recognised by its sentinel in the action slot
+        const float4 t4 = reinterpret_cast<const float4*>(sf.ac)[lane];
+        pend0 = __float_as_uint(t4.x) == kPendingBits;
+        pend1 = __float_as_uint(t4.z) == kPendingBits;
+      }
       if (a.status != nullptr) reinterpret_cast<int2*>(a.status + i0)[lane] = make_int2(cl.x, cl.y);
       if (!kFused && a.meta != nullptr) {  // (status << 16) | active set: what the backward kernel needs
         const uint32_t am = reinterpret_cast<const uint32_t*>(sh.amask[rf])[lane];

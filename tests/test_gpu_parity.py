@@ -697,6 +697,14 @@ def test_fused_safe_step_equals_layer_then_env(S, uni, cars, B):
     us2, o2, r2, d2, i2 = b.safe_step(layer_u, _cuda(ac), _cuda(mu), _cuda(sg))
     assert torch.equal(us, us2) and torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2.bool())
     assert torch.equal(a.state, b.state) and torch.equal(i1["cost"], i2["cost"])
+    # the status array is optional (the two-per-lane kernel keeps no per-instance class bytes without it): same results
+    # with it, and the classes are those of the layer kernel
+    c = S.UnicycleEnv(num_envs=B)
+    c.state = _cuda(st)
+    us3, o3, r3, d3, i3 = c.safe_step(layer_u, _cuda(ac), _cuda(mu), _cuda(sg), want_status=True)
+    assert torch.equal(us3, us2) and torch.equal(o3, o2) and torch.equal(c.state, b.state)
+    layer_u._forward_raw(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg), want_status=True)
+    assert torch.equal(i3["status"], layer_u._last_status) and int((i3["status"] == 1).sum()) > 0
     env_c, layer_c = cars
     stc, acc, muc, sgc, t = O.synth_cars(B, seed=9)
     a = S.SimulatedCarsEnv(num_envs=B); b = S.SimulatedCarsEnv(num_envs=B)
