@@ -143,7 +143,8 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
   // about as long as the kernel runs: 0.153 ms against 0.137 ms with the static deal.  Dealing warp-major -- tile =
   // warp * gridDim.x + blockIdx.x, so that the last, partial round spreads over all SMs instead of 100 of 148 -- loses
   // 2.4 %: the warps of a block then stream from 16 far-apart regions instead of one contiguous span; dealing only the
-  // last round that way loses 1.7 % (index arithmetic in a loop that sits exactly at its 128-register cap).)
+  // last round that way loses 1.7 %, and dealing the partial round FIRST and warp-major (initial values only, nothing added
+  // to the loop) still loses 1 %: the tile-count imbalance between SMs is not what the tail of this kernel waits for.)
   int tile = (int)blockIdx.x * kS2Warps + warp;   // tile of iteration k
   int tile1 = tile + nw;                          // tile of iteration k + 1
   int tm1 = 0, tm2 = 0;                           // tiles of iterations k - 1, k - 2
