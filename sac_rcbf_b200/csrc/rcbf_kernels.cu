@@ -395,9 +395,25 @@ __device__ __forceinline__ int bwd_classify(const float* __restrict__ ac, const 
 
 // per-environment pieces of the compact backward: row widths, the lean (active-set) gradient of one instance from its
 // input rows (global or shared memory) and the out-of-line dense fallback from global memory
+#ifndef RCBF_BWD_UNI_TILE
+#define RCBF_BWD_UNI_TILE 512
+#endif
+#ifndef RCBF_BWD_UNI_MINB
+#define RCBF_BWD_UNI_MINB 7
+#endif
+#ifndef RCBF_BWD_CARS_TILE
+#define RCBF_BWD_CARS_TILE 256   // (A/B: 512 x 4 blocks 0.0650 ms, 256 x 7 0.0636, 256 x 8 0.0641, 128 x 8 0.0718 per 4 Mi:
+#endif                           //  96 bytes per instance, i.e. 6.3 TB/s -- this one runs at the HBM roofline)
+#ifndef RCBF_BWD_CARS_MINB
+#define RCBF_BWD_CARS_MINB 7
+#endif
 struct UniBwd {
   using Params = UnicycleParams;
   static constexpr int NU = 2, NZ = kUniNZ, SF = 3, MF = 3;  // action / state / mean row widths (sigma row = state row)
+  // tile kernel: instances per block and resident blocks per SM (A/B on B200, 4 Mi instances: 512 x 4 / 5 / 6 / 7 blocks
+  // = 0.0862 / 0.0782 / 0.0739 / 0.0700 ms, 256 x 8 / 10 = 0.0745 / 0.0761 -- the lean path fits 72 registers, and more
+  // blocks in flight hide both the tile fetch and the phase barriers)
+  static constexpr int kTile = RCBF_BWD_UNI_TILE, kMinBlocks = RCBF_BWD_UNI_MINB;
   static __device__ __forceinline__ const float* u_min(const Params& p) { return p.u_min; }
   static __device__ __forceinline__ const float* u_max(const Params& p) { return p.u_max; }
   static __device__ __forceinline__ void lean(const float* __restrict__ sr, const float* __restrict__ ur,
@@ -459,6 +475,7 @@ struct UniBwd {
 struct CarsBwd {
   using Params = CarsParams;
   static constexpr int NU = 1, NZ = kCarsNZ, SF = 10, MF = 0;  // (the layer does not read the disturbance mean, :299)
+  static constexpr int kTile = RCBF_BWD_CARS_TILE, kMinBlocks = RCBF_BWD_CARS_MINB;
   static __device__ __forceinline__ const float* u_min(const Params& p) { return &p.u_min; }
   static __device__ __forceinline__ const float* u_max(const Params& p) { return &p.u_max; }
   static __device__ __forceinline__ void lean(const float* __restrict__ sr, const float* __restrict__ ur,
@@ -523,13 +540,12 @@ k_safe_action_bwd_meta(const float* __restrict__ st, const float* __restrict__ a
   store_row<B::NU>(grad_a, i, ga);
 }
 
-// tile form (every array base 16-byte aligned; full tiles of kBwdTile instances): the rows of a tile are contiguous
+// tile form (every array base 16-byte aligned; full tiles of B::kTile instances): the rows of a tile are contiguous
 // spans, so ONE thread fetches all of them with six cp.async.bulk copies (TMA, mbarrier completion) and nobody issues
 // a global load; several resident blocks per SM overlap one tile's fetch with another tile's arithmetic.  Phase 1
 // finishes the trivial instances in shared memory and lists the others; phase 2 runs the listed instances in chunks of
 // 32 per warp from their shared-memory rows; the gradient tile (written in place of grad_out's) leaves by coalesced
 // 128-bit stores.
-constexpr int kBwdTile = 512;
 
 template <class B>
 struct alignas(16) BwdTileSmem {
@@ -537,17 +553,17 @@ struct alignas(16) BwdTileSmem {
   int count;
   int pad;
   double pis[4];
-  int meta[kBwdTile];
-  int list[kBwdTile];
-  float ac[kBwdTile * B::NU];
-  float go[kBwdTile * B::NU];
-  float st[kBwdTile * B::SF];
-  float sg[kBwdTile * B::SF];
-  float mu[kBwdTile * (B::MF ? B::MF : 1)];
+  int meta[B::kTile];
+  int list[B::kTile];
+  float ac[B::kTile * B::NU];
+  float go[B::kTile * B::NU];
+  float st[B::kTile * B::SF];
+  float sg[B::kTile * B::SF];
+  float mu[B::kTile * (B::MF ? B::MF : 1)];
 };
 
 template <class B>
-__global__ void __launch_bounds__(kBwdThreads, 4)
+__global__ void __launch_bounds__(kBwdThreads, B::kMinBlocks)
 k_safe_action_bwd_tile(const float* __restrict__ st, const float* __restrict__ ac, const float* __restrict__ mu,
                        const float* __restrict__ sg, const int32_t* __restrict__ meta, const float* __restrict__ gout,
                        const __grid_constant__ typename B::Params p, float* __restrict__ grad_a) {
@@ -555,18 +571,18 @@ k_safe_action_bwd_tile(const float* __restrict__ st, const float* __restrict__ a
   BwdTileSmem<B>& sh = *reinterpret_cast<BwdTileSmem<B>*>(smem_raw);
   constexpr int NU = B::NU;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t i0 = (int64_t)blockIdx.x * kBwdTile;
+  const int64_t i0 = (int64_t)blockIdx.x * B::kTile;
   if (tid == 0) {
     mbar_init(&sh.bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    constexpr uint32_t kBytes = kBwdTile * 4u * (1 + 2 * NU + 2 * B::SF + B::MF);
+    constexpr uint32_t kBytes = B::kTile * 4u * (1 + 2 * NU + 2 * B::SF + B::MF);
     mbar_expect_tx(&sh.bar, kBytes);
-    bulk_g2s(sh.meta, meta + i0, kBwdTile * 4, &sh.bar);
-    bulk_g2s(sh.ac, ac + i0 * NU, kBwdTile * 4 * NU, &sh.bar);
-    bulk_g2s(sh.go, gout + i0 * NU, kBwdTile * 4 * NU, &sh.bar);
-    bulk_g2s(sh.st, st + i0 * B::SF, kBwdTile * 4 * B::SF, &sh.bar);
-    bulk_g2s(sh.sg, sg + i0 * B::SF, kBwdTile * 4 * B::SF, &sh.bar);
-    if (B::MF) bulk_g2s(sh.mu, mu + i0 * B::MF, kBwdTile * 4 * B::MF, &sh.bar);
+    bulk_g2s(sh.meta, meta + i0, B::kTile * 4, &sh.bar);
+    bulk_g2s(sh.ac, ac + i0 * NU, B::kTile * 4 * NU, &sh.bar);
+    bulk_g2s(sh.go, gout + i0 * NU, B::kTile * 4 * NU, &sh.bar);
+    bulk_g2s(sh.st, st + i0 * B::SF, B::kTile * 4 * B::SF, &sh.bar);
+    bulk_g2s(sh.sg, sg + i0 * B::SF, B::kTile * 4 * B::SF, &sh.bar);
+    if (B::MF) bulk_g2s(sh.mu, mu + i0 * B::MF, B::kTile * 4 * B::MF, &sh.bar);
     sh.count = 0;
   }
   if (tid >= 32 && tid < 32 + B::NZ) sh.pis[tid - 32] = 1.0 / sqrt((double)p.p_diag[tid - 32]);
@@ -576,7 +592,7 @@ k_safe_action_bwd_tile(const float* __restrict__ st, const float* __restrict__ a
   const float* hi = B::u_max(p);
   // phase 1
 #pragma unroll
-  for (int q = 0; q < kBwdTile / kBwdThreads; ++q) {
+  for (int q = 0; q < B::kTile / kBwdThreads; ++q) {
     const int idx = q * kBwdThreads + tid;
     const int status = sh.meta[idx] >> 16;
     const bool heavy = !(status == RCBF_OK_TRIVIAL || status == RCBF_NAN);
@@ -613,7 +629,7 @@ k_safe_action_bwd_tile(const float* __restrict__ st, const float* __restrict__ a
   float4* dst = reinterpret_cast<float4*>(grad_a + i0 * NU);
   const float4* src = reinterpret_cast<const float4*>(sh.go);
 #pragma unroll
-  for (int w = tid; w < kBwdTile * NU / 4; w += kBwdThreads) dst[w] = src[w];
+  for (int w = tid; w < B::kTile * NU / 4; w += kBwdThreads) dst[w] = src[w];
 }
 
 template <class B>
@@ -621,7 +637,7 @@ int launch_bwd_meta(const float* st, const float* ac, const float* mu, const flo
                     const float* gout, int64_t n, const typename B::Params& p, float* grad_a, cudaStream_t s) {
   auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   int64_t done = 0;
-  if (n >= 4 * kBwdTile && ok16(st) && ok16(ac) && (B::MF == 0 || ok16(mu)) && ok16(sg) && ok16(meta) && ok16(gout) &&
+  if (n >= 4 * B::kTile && ok16(st) && ok16(ac) && (B::MF == 0 || ok16(mu)) && ok16(sg) && ok16(meta) && ok16(gout) &&
       ok16(grad_a)) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -630,9 +646,9 @@ int launch_bwd_meta(const float* st, const float* ac, const float* mu, const flo
       cudaFuncSetAttribute(k_safe_action_bwd_tile<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BwdTileSmem<B>));
       attr_set[dev & 63] = true;
     }
-    const int64_t ntiles = n / kBwdTile;
+    const int64_t ntiles = n / B::kTile;
     k_safe_action_bwd_tile<B><<<(unsigned)ntiles, kBwdThreads, sizeof(BwdTileSmem<B>), s>>>(st, ac, mu, sg, meta, gout, p, grad_a);
-    done = ntiles * kBwdTile;
+    done = ntiles * B::kTile;
   }
   if (done < n) {
     const int64_t m = n - done;
