@@ -22,6 +22,8 @@ class UnicycleEnv:
         self._lib = _lib.load()
         self.num_envs = int(num_envs)
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if self.device.type == "cuda" and self.device.index is None:      # "cuda" -> the current device, explicitly
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.precision = precision or ("f64" if self.num_envs == 1 else "f32")
         self._dtype = torch.float64 if self.precision == "f64" else torch.float32
         self.auto_reset = bool(auto_reset)

@@ -871,6 +871,20 @@ def test_fused_step_host_entry_matches_device_entry(S, uni, cars):
     assert torch.equal(out["reward"], rew.cpu()) and torch.equal(a.state, b.state)
 
 
+def test_envs_accept_an_unindexed_cuda_device(S, uni, cars):
+    """`device="cuda"` / torch.device("cuda") (no index) means the current device, like everywhere in torch."""
+    for dev in ("cuda", torch.device("cuda")):
+        e = S.UnicycleEnv(num_envs=8, device=dev, auto_reset=True)
+        assert e.device.index == torch.cuda.current_device()
+        z = torch.zeros(8, 3, device="cuda")
+        e.safe_step(uni[1], torch.zeros(8, 2, device="cuda"), z, z)
+        e.step(torch.zeros(8, 2, device="cuda"))
+        c = S.SimulatedCarsEnv(num_envs=8, device=dev)
+        c.safe_step(cars[1], torch.zeros(8, 1, device="cuda"), torch.zeros(8, 10, device="cuda"))
+        c.step(torch.zeros(8, device="cuda"))
+    torch.cuda.synchronize()
+
+
 # ----------------------------------------------------------------------------------------------------- numpy layer shim
 def test_cascade_layer_vs_oracle(S, golden):
     g = golden("cascade_layer.npz")
