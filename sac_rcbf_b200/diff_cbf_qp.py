@@ -165,8 +165,8 @@ class CBFQPLayer:
             self._ws_mirror = None
         return ws
 
-    def _sync_counters(self):
-        """Read the 8 counters after everything enqueued so far has finished; returns this call's increments.
+    def _publish_read(self, ws):
+        """The 8 cumulative counters of workspace `ws` once everything enqueued so far on the current stream has finished.
         Low-latency form: a one-warp kernel (rcbf_counters_publish) copies the counters into a pinned host mirror and then
         stores a token there; this thread polls the token -- no cudaMemcpy, no cudaStreamSynchronize on the common
         path (a stream that stays busy for more than ~20 ms falls back to the blocking wait)."""
@@ -180,7 +180,7 @@ class CBFQPLayer:
         dev = self.device
         prev = torch.cuda.current_device()
         lib, stream = self._launch_ctx()
-        rc = lib.rcbf_counters_publish(self._ws.data_ptr(), self._ws_mirror_t.data_ptr(), token, stream)
+        rc = lib.rcbf_counters_publish(ws.data_ptr(), self._ws_mirror_t.data_ptr(), token, stream)
         if prev != dev.index:
             torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_counters_publish")
@@ -190,12 +190,31 @@ class CBFQPLayer:
             if spins > 100000:
                 _lib.check(lib.rcbf_stream_synchronize(stream), "cudaStreamSynchronize")
                 spins = 0
-        cur = mir[1:9].tolist()
+        return mir[1:9].tolist()
+
+    def _sync_counters(self):
+        """Read the layer's own workspace (synchronises); returns this call's increments of the 8 counters."""
+        cur = self._publish_read(self._ws)
         delta = [c - b for c, b in zip(cur, self._ws_base)]
         self._ws_base = cur
         self._last_stats = delta
         self._last_counters = None
         return delta
+
+    def _check_fused_step(self, env, counters):
+        """NaN test of a fused env step (the reference raises on any NaN safe action, diff_cbf_qp.py:141-143): reads the
+        env's workspace when `check_nan` is on (one host wait per step, like the reference's `.any()`); skipped while the
+        stream is being captured into a CUDA graph and when `check_nan` is False (read `solver_stats()` instead)."""
+        if not self.check_nan or torch.cuda.is_current_stream_capturing():
+            return
+        nan_now = self._publish_read(counters)[0]
+        seen = getattr(env, "_nan_seen", 0)
+        if nan_now < seen:          # the workspace was re-zeroed by its owner
+            env._nan_seen = seen = nan_now
+        if nan_now > seen:
+            env._nan_seen = nan_now
+            print('\033[91m QP Failed to solve - result is nan == True!\033[00m')
+            raise Exception('QP Failed to solve')
 
     def _before_launch(self):
         """Counters advanced by launches that were not read back (check_nan = False) must not be blamed on this call."""

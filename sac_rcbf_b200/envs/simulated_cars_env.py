@@ -190,6 +190,7 @@ class SimulatedCarsEnv:
         _lib.check(rc, "rcbf_cars_safe_step")
         cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
         cbf_layer._last_stats = None
+        cbf_layer._check_fused_step(self, self._counters)   # raises 'QP Failed to solve' like the reference (check_nan)
         info = {'cost': self._cost, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
 

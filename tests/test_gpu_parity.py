@@ -364,6 +364,38 @@ def test_nan_raises_like_reference(uni):
                                      torch.zeros(3, device="cuda"), torch.zeros(3, device="cuda"))
 
 
+@pytest.mark.parametrize("B", [4, 5000])
+def test_nan_raises_on_the_fused_step_too(S, uni, cars, B):
+    """The reference raises on ANY NaN safe action (diff_cbf_qp.py:141-143); so does the fused env step while
+    `check_nan` is on -- once per offending step, not for ever after -- and with `check_nan = False` the step goes
+    through and the counter is there to be read."""
+    _, layer = uni
+    st, ac, mu, sg = O.synth_unicycle(B, seed=12)
+    env = S.UnicycleEnv(num_envs=B)
+    env.state = _cuda(st)
+    bad = _cuda(mu).clone()
+    bad[B // 2, 1] = float("nan")
+    env.safe_step(layer, _cuda(ac), _cuda(mu), _cuda(sg))                       # clean step: no exception
+    with pytest.raises(Exception, match="QP Failed to solve"):
+        env.safe_step(layer, _cuda(ac), bad, _cuda(sg))
+    env.state = _cuda(st)
+    env.safe_step(layer, _cuda(ac), _cuda(mu), _cuda(sg))                       # clean again: the old NaN is not re-reported
+    layer.check_nan = False
+    try:
+        us, *_ = env.safe_step(layer, _cuda(ac), bad, _cuda(sg))
+        assert torch.isnan(us[B // 2]).all() and layer.solver_stats()["nan"] >= 1
+    finally:
+        layer.check_nan = True
+    _, layer_c = cars
+    stc, acc, muc, sgc, t = O.synth_cars(B, seed=12)
+    envc = S.SimulatedCarsEnv(num_envs=B)
+    envc.state = _cuda(stc)
+    badc = _cuda(sgc).clone()
+    badc[B // 2, 7] = float("nan")
+    with pytest.raises(Exception, match="QP Failed to solve"):
+        envc.safe_step(layer_c, _cuda(acc), badc)
+
+
 def test_unknown_dynamics_mode_raises(S):
     env = types.SimpleNamespace(dynamics_mode="Quadrotor", safe_action_space=types.SimpleNamespace(
         low=np.zeros(2, np.float32), high=np.ones(2, np.float32)), action_space=types.SimpleNamespace(shape=(2,)))
