@@ -534,6 +534,23 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
         "exact_lowrank": {"value": nsub / (ms_ex * 1e-3), "unit": "test points/s", "instances": nsub, "ms": ms_ex},
         "safe_step_with_gp": {"value": n / (ms_pipe * 1e-3), "unit": "env-steps/s", "ms_per_step": ms_pipe,
                               "note": "GP posterior kernel (state -> mean, std) + fused safe step, 2 launches"}}
+    # (e) SURVEY 8f row 3: the replay ring (rcbf_replay_push / rcbf_replay_sample): the reference's call shapes
+    # (sample(256) for one SAC update, sac_cbf.py:112-128; batch_push of one model-rollout batch) and a large draw
+    mem = S.DeviceReplayMemory(1 << 20, seed=0, obs_dim=7, action_dim=2, device=device)
+    nr = 1 << 20
+    rows = [torch.randn(nr, w, device=device) for w in (7, 2, 1, 7, 1, 1, 1)]
+    rows = [r if r.shape[1] > 1 else r[:, 0] for r in rows]
+    push5k = [r[:5000] for r in rows]
+    ms_push = _time_calls(lambda: mem.batch_push(*rows), 5, device)
+    ms_push5k = _time_calls(lambda: mem.batch_push(*push5k), 20, device)
+    ms_s256 = _time_calls(lambda: mem.sample(256), 50, device)
+    ms_s1m = _time_calls(lambda: mem.sample(nr), 5, device)
+    out["replay_ring"] = {
+        "layout": "row-major, 80-byte transition in a 96-byte row", "capacity": 1 << 20,
+        "sample_256_us": 1e3 * ms_s256, "batch_push_5000_us": 1e3 * ms_push5k,
+        "sample_1Mi": {"ms": ms_s1m, "payload_GBps": 2 * 80 * nr / (ms_s1m * 1e-3) / 1e9,
+                       "note": "index draw without replacement + gather of all seven fields, one launch"},
+        "batch_push_1Mi": {"ms": ms_push, "payload_GBps": 2 * 80 * nr / (ms_push * 1e-3) / 1e9}}
     layer.check_nan = True
     return out
 

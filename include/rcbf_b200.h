@@ -12,6 +12,7 @@
  *   rcbf_*_predict_next_*    DynamicsModel.predict_next_state (prior)   rcbf_sac/dynamics.py:60-105
  *   rcbf_*_safe_step         get_safe_action + env.step fused           rcbf_sac/sac_cbf.py:218-238 + main.py:93-95
  *   rcbf_*_rollout_step_*    one transition of generate_model_rollouts  rcbf_sac/generate_rollouts.py:29-66
+ *   rcbf_replay_push/sample  ReplayMemory.batch_push / .sample           rcbf_sac/replay_memory.py:12-32
  *   (CascadeCBFLayer.get_u_safe, rcbf_sac/cbf_qp.py:29-53, is rcbf_unicycle_safe_action with sigma_scale = k_d,
  *    abs_sigma_map = 0, p_diag = (10, 1e-4, 1e7) and the unclamped correction read from `x`.)
  *
@@ -323,6 +324,42 @@ int rcbf_unicycle_safe_step_host_gp(float* state4, int32_t* step, const float* a
                                     const rcbf_unicycle_env_params* e_host, float* safe_action_host, float* obs_host,
                                     float* reward_host, uint8_t* done_host, float* cost_host, uint8_t* goal_met_host,
                                     int32_t* n_failed_host, int device, int chunks);
+
+/* ---- device-resident replay ring ------------------------------------------------------------------
+ * Replaces ReplayMemory (rcbf_sac/replay_memory.py:4-35): the list of (state, action, reward, next_state, mask, t,
+ * next_t) tuples (:17) becomes seven caller-owned device arrays of `capacity` rows, field order as in the tuple:
+ *   field[0] state (capacity, obs_dim)   field[1] action (capacity, action_dim)   field[2] reward (capacity)
+ *   field[3] next_state (capacity, obs_dim)   field[4] mask   field[5] t   field[6] next_t   (capacity each)
+ * all of one scalar type (elem_bytes = 4: float32, 8: float64).  row_stride[f] = elements between consecutive rows of
+ * field f (0: the field's own width, i.e. a separate dense array).  The layout this library is built for is ROW-MAJOR:
+ * the seven fields of a transition adjacent in one (capacity, stride) matrix -- field[f] = base + (elements of the
+ * fields before f), every row_stride[f] = stride, base and stride * elem_bytes multiples of 16 (pad the stride to 32
+ * bytes), stride * elem_bytes <= 256 -- so that a drawn transition is three 32-byte sectors instead of nine; any other
+ * layout works through word-granular kernels.  The ring cursor (position, size) stays with the caller, as
+ * `self.position` / `len(self.buffer)` do in the reference. */
+#define RCBF_REPLAY_FIELDS 7
+typedef struct {
+  void* field[RCBF_REPLAY_FIELDS];
+  int64_t row_stride[RCBF_REPLAY_FIELDS];
+  int64_t capacity;
+  int32_t obs_dim, action_dim, elem_bytes;
+} rcbf_replay_ring;
+
+/* batch_push (replay_memory.py:20-26 = n x push, :12-18): row i of every src[f] (n rows, same layout and scalar type as
+ * the ring field) goes to ring row (position + i) % capacity.  0 <= position < capacity, 0 <= n <= capacity (of a longer
+ * batch only the newest `capacity` rows survive n pushes; the caller passes those).  src[5] / src[6] may be NULL
+ * (push without t / next_t, :26): those ring fields are left as they are.  One launch. */
+int rcbf_replay_push(const rcbf_replay_ring* ring_host, int64_t position, const void* const src[RCBF_REPLAY_FIELDS],
+                     int64_t n, void* stream);
+
+/* sample (replay_memory.py:28-32 = random.sample + seven np.stack): out[f] (batch rows, contiguous) receives ring rows
+ * perm(0), ..., perm(batch - 1), where perm is a bijection of [0, size) selected by `key` (Feistel network on
+ * ceil(log2 size) bits, cycle-walked into the range): `batch` DISTINCT rows, i.e. sampling without replacement, drawn
+ * and gathered in one launch.  1 <= size <= capacity, 0 <= batch <= size (random.sample raises ValueError beyond; the
+ * Python class does the same before calling).  out[f] may be NULL (field not wanted); idx_out (batch int64, nullable)
+ * receives the drawn row indices. */
+int rcbf_replay_sample(const rcbf_replay_ring* ring_host, int64_t size, int64_t batch, uint64_t key,
+                       void* const out[RCBF_REPLAY_FIELDS], int64_t* idx_out, void* stream);
 
 /* ---- low-latency completion / counter read-back (small batches: the reference's B = 1 / 25 / 256 call shapes) ----------
  * rcbf_counters_publish enqueues a one-warp kernel that copies the 8 counters of `workspace` into host_mirror[1..8] and

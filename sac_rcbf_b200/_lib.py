@@ -62,6 +62,8 @@ SIGNATURES = {
     "rcbf_fp64_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
     "rcbf_gp_predict_f32": [_vp, _i64, C.POINTER(P.GpPosterior), _vp, _vp, _vp],
     "rcbf_gp_predict_f64": [_vp, _i64, C.POINTER(P.GpPosterior), _vp, _vp, _vp],
+    "rcbf_replay_push": [C.POINTER(P.ReplayRing), _i64, C.POINTER(_vp * 7), _i64, _vp],
+    "rcbf_replay_sample": [C.POINTER(P.ReplayRing), _i64, _i64, C.c_uint64, C.POINTER(_vp * 7), _vp, _vp],
 }
 for _suf in ("f32", "f64"):
     SIGNATURES["rcbf_unicycle_env_reset_" + _suf] = [_vp, _vp, _vp, _i64, C.POINTER(P.UnicycleEnvParams), _vp, _vp]

@@ -46,6 +46,17 @@ class GpPosterior(C.Structure):  # rcbf_gp_posterior
     ]
 
 
+class ReplayRing(C.Structure):  # rcbf_replay_ring
+    _fields_ = [
+        ("field", C.c_void_p * 7),
+        ("row_stride", C.c_int64 * 7),
+        ("capacity", C.c_int64),
+        ("obs_dim", C.c_int32),
+        ("action_dim", C.c_int32),
+        ("elem_bytes", C.c_int32),
+    ]
+
+
 class CarsParams(C.Structure):
     _fields_ = [
         ("gamma_2", C.c_float),

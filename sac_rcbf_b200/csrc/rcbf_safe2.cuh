@@ -308,6 +308,8 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
 #pragma unroll 1
     for (;;) {
       const int old = qn - pk - pk1;
+      // (a forced flush that takes the whole ring instead of only tile k-2's leftovers saves 1.4 % of the B-steps in a
+      //  simulation of this deal and nothing measurable on B200: 0.12400 against 0.12394 ms, three interleaved runs each)
       const int take = qn >= 32 ? 32 : ((fin_due && old > 0) ? old : 0);
       if (take == 0) break;
       if (lane < take) {

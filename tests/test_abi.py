@@ -44,17 +44,18 @@ def test_library_exports_every_declared_symbol(lib):
 def test_ctypes_structs_match_c_layout(tmp_path):
     from sac_rcbf_b200 import _params as P
     prog = tmp_path / "sz.c"
-    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rcbf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "rcbf_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                     'sizeof(rcbf_unicycle_params),sizeof(rcbf_cars_params),sizeof(rcbf_unicycle_env_params),'
                     'sizeof(rcbf_cars_env_params),offsetof(rcbf_unicycle_params,p_diag),'
                     'offsetof(rcbf_unicycle_env_params,max_episode_steps),offsetof(rcbf_cars_params,slack_coeff),'
-                    'sizeof(rcbf_gp_posterior),offsetof(rcbf_gp_posterior,n_pad),offsetof(rcbf_gp_posterior,min_variance));return 0;}\n')
+                    'sizeof(rcbf_gp_posterior),offsetof(rcbf_gp_posterior,n_pad),offsetof(rcbf_gp_posterior,min_variance),sizeof(rcbf_replay_ring),offsetof(rcbf_replay_ring,obs_dim));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(v) for v in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(P.UnicycleParams), C.sizeof(P.CarsParams), C.sizeof(P.UnicycleEnvParams), C.sizeof(P.CarsEnvParams),
             P.UnicycleParams.p_diag.offset, P.UnicycleEnvParams.max_episode_steps.offset, P.CarsParams.slack_coeff.offset,
-            C.sizeof(P.GpPosterior), P.GpPosterior.n_pad.offset, P.GpPosterior.min_variance.offset]
+            C.sizeof(P.GpPosterior), P.GpPosterior.n_pad.offset, P.GpPosterior.min_variance.offset,
+            C.sizeof(P.ReplayRing), P.ReplayRing.obs_dim.offset]
     assert got == want
 
 
