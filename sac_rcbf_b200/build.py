@@ -7,8 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librcbf_b200.so")
-SOURCES = ["rcbf_kernels.cu", "rcbf_safe_unicycle.cu", "rcbf_safe2_unicycle.cu", "rcbf_safe_cars.cu", "rcbf_gp.cu", "rcbf_general.cu", "rcbf_replay.cu"]
-HEADERS = ["rcbf_core.cuh", "rcbf_dynamics.cuh", "rcbf_backward.cuh", "rcbf_generic.cuh", "rcbf_safe_kernels.cuh", "rcbf_safe2.cuh", "rcbf_f2.cuh", "rcbf_tma.cuh",
+SOURCES = ["rcbf_kernels.cu", "rcbf_safe_unicycle.cu", "rcbf_safe2_unicycle.cu", "rcbf_safe_cars.cu", "rcbf_cars2.cu", "rcbf_gp.cu", "rcbf_general.cu", "rcbf_replay.cu"]
+HEADERS = ["rcbf_core.cuh", "rcbf_dynamics.cuh", "rcbf_backward.cuh", "rcbf_generic.cuh", "rcbf_safe_kernels.cuh", "rcbf_safe2.cuh", "rcbf_cars2.cuh", "rcbf_f2.cuh", "rcbf_tma.cuh",
            os.path.join("..", "..", "include", "rcbf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 NVCC_FLAGS += os.environ.get("RCBF_NVCC_EXTRA", "").split()  # A/B switches (-DRCBF_S2_...=...) for scripts/gpu_ab.sh

@@ -56,23 +56,6 @@ constexpr int kS2Ring = RCBF_S2_RING;  // a tile pushes <= 64 problems on top of
 constexpr bool kS2CarrySinCos = RCBF_S2_CARRY_SINCOS != 0;
 static_assert(kS2Ring >= 75 && kS2Ring <= 95, "31 + 64 - kS2Ring parked problems must fit a landing slot (20 entries)");
 
-// bulk stores (shared -> global) + their completion
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void bulk_s2g_u32(void* dst, uint32_t src_smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s_u32(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // The presolve's row fetch for a problem that sits in the ring (rcbf_core.cuh: SelectRowFetch): a CBF row is read back
 // from the slot (G[i][:2] = -Lg[i], G[i][2] = -1), an actuator row is rebuilt from its index.  Same values as the
 // register-resident copy the default fetch would pick through a 9-way select chain.

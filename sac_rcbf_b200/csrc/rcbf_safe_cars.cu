@@ -7,6 +7,12 @@
 
 using namespace rcbf;
 
+namespace rcbf {
+// rcbf_cars2.cu: the ring-compacted fused-step kernel on the leading full 32-instance tiles (if the call qualifies)
+int launch_cars2(const CarsArgs& a, int64_t n, const CarsParams& p, const CarsEnvParams& e, rcbf_counters_t* ws,
+                 cudaStream_t s, int64_t* handled);
+}
+
 extern "C" {
 
 int rcbf_cars_safe_action(const float* state, const float* action, const float* sigma, int64_t n,
@@ -35,7 +41,16 @@ int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* acti
   a.state = state; a.t = t; a.step = step; a.ac = action_rl; a.sg = sigma;
   a.out = safe_action; a.status = status;
   a.obs = obs; a.reward = reward; a.done = done; a.cost = cost;
-  return launch_safe<CarsEnv<true>>(a, n, *p, *e, workspace, (cudaStream_t)stream);
+  int64_t handled = 0;
+  const int rc = launch_cars2(a, n, *p, *e, workspace, (cudaStream_t)stream, &handled);
+  if (rc != 0) return rc;
+  if (handled == n) return 0;
+  if (handled > 0) {  // ragged rest (< 32 instances) through the one-tile-at-a-time kernel
+    a.state += handled * 10; a.t += handled; a.step += handled; a.ac += handled; a.sg += handled * 10;
+    a.out += handled; a.obs += handled * 10; a.reward += handled; a.done += handled; a.cost += handled;
+    if (a.status != nullptr) a.status += handled;
+  }
+  return launch_safe<CarsEnv<true>>(a, n - handled, *p, *e, workspace, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -744,8 +744,18 @@ def test_fused_safe_step_equals_layer_then_env(S, uni, cars, B):
         e.state = _cuda(stc); e._t.copy_(_cuda(t))
     us = layer_c.get_safe_action(_cuda(stc), _cuda(acc), _cuda(muc), _cuda(sgc))
     o1, r1, d1, i1 = a.step(us)
-    us2, o2, r2, d2, i2 = b.safe_step(layer_c, _cuda(acc), _cuda(sgc))
+    us2, o2, r2, d2, i2 = b.safe_step(layer_c, _cuda(acc), _cuda(sgc), want_status=True)
     assert torch.equal(us, us2) and torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(a.state, b.state)
+    # (B >= 4096: the ring-compacted kernel k_cars2 on the full tiles, k_safe on the ragged rest)
+    assert torch.equal(d1, d2.bool()) and torch.equal(i1["cost"], i2["cost"]) and torch.equal(a._t, b._t)
+    assert torch.equal(a._step, b._step)
+    layer_c._forward_raw(_cuda(stc), _cuda(acc), _cuda(muc), _cuda(sgc), want_status=True)
+    assert torch.equal(i2["status"], layer_c._last_status) and int((i2["status"] == 1).sum()) > 0
+    # a second step from the stepped state (the in-place state rows the bulk stores wrote are what the next launch reads)
+    us = layer_c.get_safe_action(a.state, _cuda(acc), _cuda(muc), _cuda(sgc))
+    o1, r1, d1, i1 = a.step(us)
+    us2, o2, r2, d2, i2 = b.safe_step(layer_c, _cuda(acc), _cuda(sgc))
+    assert torch.equal(us, us2) and torch.equal(o1, o2) and torch.equal(a.state, b.state) and torch.equal(a._t, b._t)
 
 
 def test_fused_step_merged_finish_structured_need_patterns(S, uni):
