@@ -274,6 +274,13 @@ def hbm_peak_gbs():
         return 6650.0
 
 
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:  # noqa: BLE001
+        return 6650.0   # fallback of the profiling recipe
+
+
 def _time_calls(fn, iters, device):
     for _ in range(3):
         fn()
@@ -372,7 +379,10 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
     ms = _time_calls(lambda: envc.safe_step(layc, acc, sgc), 5, device)
     out["cars_safe_step"] = {"value": nc / (ms * 1e-3), "unit": "env-steps/s", "instances": nc, "ms": ms,
                              "bytes_per_unit": 40 + 4 + 4 + 4 + 40 + 40 + 4 + 4 + 40 + 4 + 1 + 4 + 4,
-                             "achieved_gbs": 193.0 * nc / (ms * 1e-3) / 1e9}
+                             "achieved_gbs": 193.0 * nc / (ms * 1e-3) / 1e9,
+                             "kernel": "k_cars2 (problem ring + finish lag, TMA in and out)",
+                             "roofline": {"bound": "hbm", "achieved": 193.0 * nc / (ms * 1e-3) / 1e9, "peak": _hbm_peak(),
+                                          "unit": "GB/s", "frac": 193.0 * nc / (ms * 1e-3) / 1e9 / _hbm_peak()}}
     # (b2) config 3 at scale: differentiable path = forward that saves one int32 per instance (status + active set) +
     # the compact implicit-KKT backward (TMA tile kernel).  Algorithmic bytes per instance: forward 12 + 8 + 12 + 12 in,
     # 8 + 4 out = 56; backward 4 + 8 + 8 + 12 + 12 + 12 in, 8 out = 64.

@@ -370,6 +370,17 @@ int rcbf_replay_sample(const rcbf_replay_ring* ring_host, int64_t size, int64_t 
 int rcbf_counters_publish(const rcbf_counters_t* workspace, uint64_t* host_mirror /* 9 words, pinned */, uint64_t token,
                           void* stream);
 int rcbf_stream_synchronize(void* stream); /* cudaStreamSynchronize (for hosts that hold no CUDA runtime binding) */
+/* In-kernel publication (saves the second launch): bind a 9-word page-locked host mirror to a workspace once
+ * (rcbf_counters_bind_mirror stores its address in workspace word 11), then OR
+ *     RCBF_SOLVER_PUBLISH | (token << RCBF_SOLVER_TOKEN_SHIFT)          (token < 2^22)
+ * into the `solver_mode` of the params passed to rcbf_*_safe_action / _saved / _safe_step (solver mode 0, workspace
+ * given): the last block of the call's LAST kernel copies the 8 counters into host_mirror[1..8] and then stores the
+ * token into host_mirror[0].  Bits 0..7 of solver_mode stay the solver mode.  Without a bound mirror the bits are
+ * ignored. */
+#define RCBF_SOLVER_PUBLISH 0x100
+#define RCBF_SOLVER_TOKEN_SHIFT 9
+int rcbf_counters_bind_mirror(rcbf_counters_t* workspace, uint64_t* host_mirror /* 9 words, pinned; NULL unbinds */,
+                              void* stream);
 
 /* ---- measurement helpers --------------------------------------------------------------------------------------
  * FP32 FMA throughput probe: `iters` dependent-chain FMAs x 8 chains per thread; returns nothing, time it outside.

@@ -58,6 +58,7 @@ SIGNATURES = {
                                        _vp],
     "rcbf_counters_publish": [_vp, _vp, C.c_uint64, _vp],
     "rcbf_stream_synchronize": [_vp],
+    "rcbf_counters_bind_mirror": [_vp, _vp, _vp],
     "rcbf_fp32_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
     "rcbf_fp64_fma_probe": [_vp, C.c_int, C.c_int, C.c_int, _vp],
     "rcbf_gp_predict_f32": [_vp, _i64, C.POINTER(P.GpPosterior), _vp, _vp, _vp],

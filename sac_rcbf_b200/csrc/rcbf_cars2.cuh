@@ -32,11 +32,13 @@
 
 namespace rcbf {
 
+// A/B on B200 (4 Mi instances, ms per step): 2 blocks x 8 warps 0.1385 (steadiest), 1 x 16 0.138-0.143, 1 x 12 0.151,
+// 1 x 20 (96 registers, spills) 0.160
 #ifndef RCBF_C2_WARPS
-#define RCBF_C2_WARPS 16
+#define RCBF_C2_WARPS 8
 #endif
 #ifndef RCBF_C2_MINB
-#define RCBF_C2_MINB 1
+#define RCBF_C2_MINB 2
 #endif
 #ifndef RCBF_C2_MIN_N
 #define RCBF_C2_MIN_N 4096   // below this the few tiles spread over more warps with k_safe's 4-warp blocks
@@ -294,6 +296,7 @@ k_cars2(CarsArgs a, int64_t n /* multiple of 32 */, CarsParams p, CarsEnvParams 
         ws[kWsClaim] = 0ULL;
         ws[kWsBlocksDone] = 0ULL;
         __threadfence();
+        publish_counters(ws, p.solver_mode);
       }
     }
   }
@@ -309,7 +312,7 @@ inline int launch_cars2_tiles(const CarsArgs& a, int64_t n, const CarsParams& p,
     const char* v = getenv("RCBF_NO_CARS2");
     return v != nullptr && v[0] == '1';
   }();
-  if (env_off || n < RCBF_C2_MIN_N || n > 0x7fffffffLL || p.solver_mode != 0) return 0;
+  if (env_off || n < RCBF_C2_MIN_N || n > 0x7fffffffLL || solver_mode_of(p) != 0) return 0;
   auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr || a.meta != nullptr) return 0;
   if (!(ok16(a.state) && ok16(a.t) && ok16(a.step) && ok16(a.ac) && ok16(a.sg) && ok16(a.obs))) return 0;
@@ -326,7 +329,9 @@ inline int launch_cars2_tiles(const CarsArgs& a, int64_t n, const CarsParams& p,
   const int64_t want = (ntiles + kC2Warps - 1) / kC2Warps;
   const int resident = sms * RCBF_C2_MINB;
   const int grid = (int)(want < resident ? want : resident);
-  cudaError_t err = launch_pdl(true, k_cars2, grid, kC2Threads, sizeof(C2Warp) * kC2Warps, s, a, n2, p, e, ws);
+  CarsParams pk = p;
+  if (n2 != n) pk.solver_mode = solver_mode_of(p);  // a ragged rest follows: that kernel publishes the counters
+  cudaError_t err = launch_pdl(true, k_cars2, grid, kC2Threads, sizeof(C2Warp) * kC2Warps, s, a, n2, pk, e, ws);
   if (err != cudaSuccess) return (int)err;
   if (ws == nullptr) {  // no workspace: a second kernel scans safe_action for the pending sentinel
     const int64_t fb = (n2 + 127) / 128;

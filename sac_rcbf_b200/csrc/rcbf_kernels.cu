@@ -938,6 +938,8 @@ __global__ void k_counters_publish(const rcbf_counters_t* __restrict__ ws, volat
   if (threadIdx.x == 0) mirror[0] = token;
 }
 
+__global__ void k_bind_mirror(rcbf_counters_t* ws, unsigned long long mirror) { ws[11] = mirror; }  // kWsMirror (rcbf_safe_kernels.cuh)
+
 __global__ void k_fp32_fma_probe(float* sink, int iters) {
   float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
         a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -1148,6 +1150,12 @@ RCBF_ROLLOUT_FUNCS(f64, double)
 int rcbf_counters_publish(const rcbf_counters_t* workspace, uint64_t* host_mirror, uint64_t token, void* stream) {
   k_counters_publish<<<1, 32, 0, (cudaStream_t)stream>>>(workspace, reinterpret_cast<volatile unsigned long long*>(host_mirror),
                                                         (unsigned long long)token);
+  RCBF_LAUNCH_CHECK();
+  return 0;
+}
+
+int rcbf_counters_bind_mirror(rcbf_counters_t* workspace, uint64_t* host_mirror, void* stream) {
+  k_bind_mirror<<<1, 1, 0, (cudaStream_t)stream>>>(workspace, (unsigned long long)reinterpret_cast<uintptr_t>(host_mirror));
   RCBF_LAUNCH_CHECK();
   return 0;
 }

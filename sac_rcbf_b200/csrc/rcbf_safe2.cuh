@@ -498,6 +498,7 @@ k_safe2(UniArgs a, int64_t n /* multiple of 64 */, UnicycleParams p, UnicycleEnv
         ws[kWsClaim] = 0ULL;
         ws[kWsBlocksDone] = 0ULL;
         __threadfence();
+        publish_counters(ws, p.solver_mode);
       }
     }
   }
@@ -514,7 +515,7 @@ inline int launch_safe2_tiles(const UniArgs& a, int64_t n, const UnicycleParams&
     const char* v = getenv("RCBF_NO_SAFE2");
     return v != nullptr && v[0] == '1';
   }();
-  if (env_off || n < RCBF_S2_MIN_N || n > 0x7fffffffLL || p.solver_mode != 0) return 0;
+  if (env_off || n < RCBF_S2_MIN_N || n > 0x7fffffffLL || solver_mode_of(p) != 0) return 0;
   auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr) return 0;
   if (a.meta != nullptr && (kFused || !ok16(a.meta))) return 0;
@@ -540,8 +541,10 @@ inline int launch_safe2_tiles(const UniArgs& a, int64_t n, const UnicycleParams&
   const int64_t want = (ntiles + kS2Warps - 1) / kS2Warps;
   const int resident = sms * RCBF_S2_MINB;
   const int grid = (int)(want < resident ? want : resident);
+  UnicycleParams pk = p;
+  if (n2 != n) pk.solver_mode = solver_mode_of(p);  // a ragged rest follows: that kernel publishes the counters
   cudaError_t err =
-      launch_pdl(true, k_safe2<kFused>, grid, kS2Threads, sizeof(S2Warp<kFused>) * kS2Warps, s, a, n2, p, e, make_env_f(e), ws);
+      launch_pdl(true, k_safe2<kFused>, grid, kS2Threads, sizeof(S2Warp<kFused>) * kS2Warps, s, a, n2, pk, e, make_env_f(e), ws);
   if (err != cudaSuccess) return (int)err;
   if (ws == nullptr) {  // no workspace: a second kernel scans safe_action for the pending sentinel
     const int64_t fb = (n2 + 127) / 128;

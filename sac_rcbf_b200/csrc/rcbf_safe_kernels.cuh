@@ -74,6 +74,7 @@ constexpr int kWsCounters = 8;                 // workspace words [0, 8): counte
 constexpr int kWsQueueCount = 8;               // [8]: number of queued instances
 constexpr int kWsBlocksDone = 9;               // [9]: blocks finished (the last one resets the queue)
 constexpr int kWsClaim = 10;                   // [10]: queue entries claimed by a draining warp (presolve mode)
+constexpr int kWsMirror = 11;                  // [11]: host mirror bound by rcbf_counters_bind_mirror (0: none)
 constexpr int kWsQueueBase = 16;               // [16, RCBF_WS_WORDS): queued instance indices + 1 (0 = empty slot)
 constexpr int kWsQueueCap = RCBF_WS_WORDS - kWsQueueBase;
 
@@ -677,6 +678,23 @@ struct WarpShared {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// solver mode proper (bits 0..7 of params.solver_mode; the rest is the publication request, include/rcbf_b200.h)
+template <class P>
+__host__ __device__ __forceinline__ int solver_mode_of(const P& p) { return p.solver_mode & 0xff; }
+
+// Last block of a call's last kernel, one thread, after every block's counter atomics (each block fences before it
+// arrives on ws[kWsBlocksDone]): counters -> the bound host mirror, then the caller's token.
+__device__ __forceinline__ void publish_counters(rcbf_counters_t* ws, int solver_mode) {
+  if ((solver_mode & RCBF_SOLVER_PUBLISH) == 0) return;
+  volatile rcbf_counters_t* vws = ws;
+  volatile unsigned long long* mirror = reinterpret_cast<volatile unsigned long long*>(vws[kWsMirror]);
+  if (mirror == nullptr) return;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) mirror[1 + c] = vws[c];
+  __threadfence_system();
+  mirror[0] = (unsigned long long)((unsigned)solver_mode >> RCBF_SOLVER_TOKEN_SHIFT);
+}
+
 template <class E>
 __device__ __forceinline__ void mark_pending(const typename E::Args& a, int64_t i, rcbf_counters_t* ws) {
   a.out[i * E::NU] = __uint_as_float(kPendingBits);
@@ -1202,6 +1220,7 @@ k_safe(typename E::Args a, int64_t n, typename E::Params p, typename E::EnvParam
         ws[kWsClaim] = 0ULL;
         ws[kWsBlocksDone] = 0ULL;
         __threadfence();
+        publish_counters(ws, p.solver_mode);
       }
     }
   }
@@ -1315,7 +1334,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
   const int64_t ntiles = (n + 31) / 32;
   const int64_t want = (ntiles + kWarps - 1) / kWarps;
   const int sms = device_sm_count();
-  const int resident = sms * (p.solver_mode == 0 ? E::kMinBlocks : RCBF_MINB_PDIPM);  // persistent: one wave of resident blocks
+  const int resident = sms * (solver_mode_of(p) == 0 ? E::kMinBlocks : RCBF_MINB_PDIPM);  // persistent: one wave of resident blocks
   const int grid = (int)(want < resident ? want : resident);
   const int64_t fb = (n + 127) / 128;
   const int fgrid = (int)(fb < sms * 4 ? fb : sms * 4);
@@ -1344,7 +1363,7 @@ inline int launch_safe(const typename E::Args& a, int64_t n, const typename E::P
     else RCBF_LAUNCH_ONE(MODE, false, false);                                                        \
     if (ws == nullptr || MODE == 1) launch_pdl(true, k_safe_fallback<E, MODE>, fgrid, 128, 0, s, a, n, p, e, ws); \
   } while (0)
-  if (p.solver_mode == 0) RCBF_LAUNCH_SAFE(0);
+  if (solver_mode_of(p) == 0) RCBF_LAUNCH_SAFE(0);
   else RCBF_LAUNCH_SAFE(1);
 #undef RCBF_LAUNCH_SAFE
 #undef RCBF_LAUNCH_ONE

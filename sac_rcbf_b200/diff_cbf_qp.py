@@ -192,22 +192,58 @@ class CBFQPLayer:
                 spins = 0
         return mir[1:9].tolist()
 
-    def _sync_counters(self):
+    # In-kernel publication (include/rcbf_b200.h: RCBF_SOLVER_PUBLISH): the last block of the step / layer kernel itself
+    # copies the counters into a pinned host mirror bound to the workspace and stores this call's token there, so the
+    # reference's per-call NaN test costs ONE launch + a poll instead of two launches.
+    def _publish_arm(self, ws, p):
+        """Request the publication for the launch that follows: -> token, or None when that launch cannot publish
+        (interior-point mode, the general-hazard kernels, CUDA-graph capture) and `_publish_read` has to be used."""
+        if self.solver != "presolve" or self._general_hz is not None or torch.cuda.is_current_stream_capturing():
+            return None
+        mirrors = self.__dict__.setdefault("_mirrors", {})
+        key = ws.data_ptr()
+        m = mirrors.get(key)
+        if m is None:
+            t = torch.zeros(9, dtype=torch.int64).pin_memory()
+            m = mirrors[key] = [t, t.numpy(), 0]
+            lib, stream = self._launch_ctx()
+            _lib.check(lib.rcbf_counters_bind_mirror(key, t.data_ptr(), stream), "rcbf_counters_bind_mirror")
+        m[2] = tok = (m[2] % 0x3fffff) + 1
+        p.solver_mode = (p.solver_mode & 0xff) | 0x100 | (tok << 9)
+        return tok
+
+    @staticmethod
+    def _publish_disarm(p):
+        p.solver_mode &= 0xff
+
+    def _publish_wait(self, ws, tok):
+        """The 8 cumulative counters once the armed launch has published them (falls back to `_publish_read`)."""
+        m = self._mirrors[ws.data_ptr()]
+        mir = m[1]
+        spins = 0
+        while mir[0] != tok:
+            spins += 1
+            if spins > 200000:      # not published (e.g. the workspace was re-created at the same address): re-bind
+                del self._mirrors[ws.data_ptr()]
+                return self._publish_read(ws)
+        return mir[1:9].tolist()
+
+    def _sync_counters(self, tok=None):
         """Read the layer's own workspace (synchronises); returns this call's increments of the 8 counters."""
-        cur = self._publish_read(self._ws)
+        cur = self._publish_read(self._ws) if tok is None else self._publish_wait(self._ws, tok)
         delta = [c - b for c, b in zip(cur, self._ws_base)]
         self._ws_base = cur
         self._last_stats = delta
         self._last_counters = None
         return delta
 
-    def _check_fused_step(self, env, counters):
+    def _check_fused_step(self, env, counters, tok=None):
         """NaN test of a fused env step (the reference raises on any NaN safe action, diff_cbf_qp.py:141-143): reads the
         env's workspace when `check_nan` is on (one host wait per step, like the reference's `.any()`); skipped while the
         stream is being captured into a CUDA graph and when `check_nan` is False (read `solver_stats()` instead)."""
         if not self.check_nan or torch.cuda.is_current_stream_capturing():
             return
-        nan_now = self._publish_read(counters)[0]
+        nan_now = (self._publish_read(counters) if tok is None else self._publish_wait(counters, tok))[0]
         seen = getattr(env, "_nan_seen", 0)
         if nan_now < seen:          # the workspace was re-zeroed by its owner
             env._nan_seen = seen = nan_now
@@ -222,13 +258,13 @@ class CBFQPLayer:
             self._sync_counters()
             self._unread = False
 
-    def _after_launch(self):
+    def _after_launch(self, tok=None):
         self._last_stats = None
         self._last_counters = None
         if not self.check_nan:
             self._unread = True
             return
-        if self._sync_counters()[0] > 0:
+        if self._sync_counters(tok)[0] > 0:
             print('\033[91m QP Failed to solve - result is nan == True!\033[00m')
             raise Exception('QP Failed to solve')
 
@@ -313,6 +349,7 @@ class CBFQPLayer:
         p = self._params()
         prev = torch.cuda.current_device()
         lib, stream = self._launch_ctx()
+        tok = self._publish_arm(counters, p) if self.check_nan else None
         ghz = self._general_hz
         if ghz is not None:
             if save:
@@ -330,9 +367,10 @@ class CBFQPLayer:
                                            _lib.ptr(iters), _lib.ptr(counters), stream)
         if prev != dev.index:
             torch.cuda.set_device(prev)
+        self._publish_disarm(p)
         _lib.check(rc, "rcbf_%s_safe_action" % mode)
         self._last_status, self._last_iters = status, iters
-        self._after_launch()
+        self._after_launch(tok)
         return out, x, lam, slack
 
     def _forward_meta(self, st, ac, mu, sg):
@@ -347,6 +385,7 @@ class CBFQPLayer:
         p = self._params()
         prev = torch.cuda.current_device()
         lib, stream = self._launch_ctx()
+        tok = self._publish_arm(counters, p) if self.check_nan else None
         ghz = self._general_hz
         if ghz is not None:
             rc = lib.rcbf_unicycle_safe_action_general(_lib.ptr(st), _lib.ptr(ac), _lib.ptr(mu), _lib.ptr(sg), n, p,
@@ -360,8 +399,9 @@ class CBFQPLayer:
                                                  _lib.ptr(meta), _lib.ptr(counters), stream)
         if prev != dev.index:
             torch.cuda.set_device(prev)
+        self._publish_disarm(p)
         _lib.check(rc, "rcbf_%s_safe_action_saved" % mode)
-        self._after_launch()
+        self._after_launch(tok)
         return out, meta
 
     def _backward_meta(self, st, ac, mu, sg, meta, go):

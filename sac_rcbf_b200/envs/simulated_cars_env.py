@@ -182,15 +182,18 @@ class SimulatedCarsEnv:
         status = torch.empty((n,), dtype=torch.int32, device=dev) if want_status else None
         o = self._own_ptrs
         prev = self._enter_device()
-        rc = self._lib.rcbf_cars_safe_step(o[0], o[1], o[2], ac.data_ptr(), sg.data_ptr(), n, cbf_layer._params(),
+        lp = cbf_layer._params()
+        tok = cbf_layer._publish_arm(self._counters, lp) if cbf_layer.check_nan else None   # kernel publishes the counters
+        rc = self._lib.rcbf_cars_safe_step(o[0], o[1], o[2], ac.data_ptr(), sg.data_ptr(), n, lp,
                                            self._env_params(), o[3], o[4], o[5], o[6], o[7], _lib.ptr(status), o[8],
                                            _lib.stream_ptr(dev))
+        cbf_layer._publish_disarm(lp)
         if prev is not None:
             torch.cuda.set_device(prev)
         _lib.check(rc, "rcbf_cars_safe_step")
         cbf_layer._last_counters = self._counters      # layer.solver_stats() also covers fused steps (cumulative)
         cbf_layer._last_stats = None
-        cbf_layer._check_fused_step(self, self._counters)   # raises 'QP Failed to solve' like the reference (check_nan)
+        cbf_layer._check_fused_step(self, self._counters, tok)   # raises 'QP Failed to solve' like the reference (check_nan)
         info = {'cost': self._cost, 'status': status}
         return self._safe_action, self._obs, self._reward, self._done, info
 

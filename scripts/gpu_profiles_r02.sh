@@ -11,3 +11,6 @@ PROFB="python scripts/gpu_bwd_prof.py"
 $PROFB > gpurun_out/bwd_plain.log 2>&1 && cat gpurun_out/bwd_plain.log && \
 ncu --set full --clock-control none --import-source on -k regex:bwd_tile -s 3 -c 1 -f -o gpurun_out/prof_bwd $PROFB > gpurun_out/ncu_bwd.log 2>&1; echo "ncu bwd rc=$?"
 python scripts/gpu_latency.py > gpurun_out/latency.log 2>&1; tail -16 gpurun_out/latency.log
+python scripts/gpu_cars_step.py > gpurun_out/cars_plain.log 2>&1 && cat gpurun_out/cars_plain.log | cut -c1-70 && \
+ncu --set full --clock-control none --import-source on -k regex:k_cars2 -s 6 -c 1 -f -o gpurun_out/prof_k_cars2 python scripts/gpu_cars_step.py > gpurun_out/ncu_cars.log 2>&1; echo "ncu cars rc=$?"
+python scripts/gpu_replay.py > gpurun_out/replay.log 2>&1; tail -10 gpurun_out/replay.log

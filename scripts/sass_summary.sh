@@ -13,7 +13,7 @@ cuobjdump -sass "$LIB" | awk '
   END { if (name != "") flush() }' | sed 's/_ZN[0-9]*_GLOBAL__N__[0-9a-f_]*cu_[0-9a-f]*//' | sort
 echo
 echo "# nvcc -Xptxas -v (registers, spills, shared memory) per entry function"
-for f in rcbf_kernels rcbf_safe_unicycle rcbf_safe2_unicycle rcbf_safe_cars rcbf_gp rcbf_general; do
+for f in rcbf_kernels rcbf_safe_unicycle rcbf_safe2_unicycle rcbf_safe_cars rcbf_cars2 rcbf_gp rcbf_general rcbf_replay; do
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v -c sac_rcbf_b200/csrc/$f.cu -o /tmp/sass_$f.o 2>&1 |
     awk -v tu=$f '/Compiling entry function/ { name=$0; sub(/.*entry function ./, "", name); sub(/. for .*/, "", name) }
          /bytes spill stores/ { if (!seen[name]) { spill=$0; sub(/^[[:space:]]+/, "", spill) } }

@@ -199,7 +199,7 @@ def test_pending_instances_with_and_without_workspace(uni, cars):
         assert stats["fallback"] > 200 and stats["uncertified"] == 0 and stats["nan"] == 0 and (ref[4] <= 2).all()
         assert not np.isnan(ref[0]).any()
         ws = layer._ws
-        assert int(ws[8:16].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0   # bookkeeping reset, slots cleared
+        assert int(ws[8:11].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0   # bookkeeping reset, slots cleared
     np.testing.assert_array_equal(_unicycle_without_workspace(layer, st, ac, mu, sg), ref[0])
     pend = ref[5] == 4                                    # iters == nz + 1 marks "enumerated"
     assert pend.sum() == stats["fallback"]
@@ -235,7 +235,7 @@ def test_pending_queue_overflow_falls_back_to_the_sentinel_scan(uni):
     stats = layer.solver_stats()
     assert stats["fallback"] > 32752 and stats["uncertified"] == 0 and stats["nan"] == 0
     ws = layer._ws
-    assert int(ws[8:16].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0
+    assert int(ws[8:11].abs().sum()) == 0 and int(ws[16:].abs().sum()) == 0
     got = out.cpu().numpy()
     assert not np.isnan(got).any()
     np.testing.assert_array_equal(_unicycle_without_workspace(layer, st, ac, mu, sg), got)
@@ -946,3 +946,39 @@ def test_cascade_layer_vs_oracle(S, golden):
         u = layc.get_u_safe(g["cars_action"][i], g["cars_state"][i], np.zeros(10), g["cars_sigma"][i])
         ue, _ = O.cascade_u_safe("SimulatedCars", g["cars_action"][i], g["cars_state"][i], np.zeros(10), g["cars_sigma"][i])
         assert u.shape == (1,) and np.abs(u - ue).max() < 1e-4 * max(1.0, np.abs(ue).max())
+
+
+@pytest.mark.parametrize("B", [1, 512, 4096, 4096 + 17, 65536 + 40])
+def test_counters_are_published_by_the_kernel_itself(S, uni, cars, B):
+    """check_nan = True (the reference's per-call NaN test): the last block of the call's last kernel writes the counters
+    and the call's token into the pinned mirror bound to the workspace -- one launch, no publish kernel.  Sizes cover
+    k_safe alone, k_safe2 / k_cars2 alone and either followed by a ragged rest (then the rest's kernel publishes)."""
+    env_u, layer_u = uni
+    st, ac, mu, sg = O.synth_unicycle(B, seed=21)
+    layer_u.check_nan = True
+    for _ in range(3):
+        out = layer_u.get_safe_action(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg))
+        m = layer_u._mirrors[layer_u._ws.data_ptr()]            # (a fallback to the publish kernel would have dropped it)
+        assert int(m[1][0]) == m[2] and layer_u._last_stats[0] == 0
+        assert sum(layer_u._last_stats[3:4]) + 0 <= B and m[1][1:9].tolist() == layer_u._ws[:8].tolist()
+    e = S.UnicycleEnv(num_envs=B, precision="f32")
+    e.state = _cuda(st)
+    for _ in range(2):
+        e.safe_step(layer_u, _cuda(ac), _cuda(mu), _cuda(sg))
+        m = layer_u._mirrors[e._counters.data_ptr()]
+        assert int(m[1][0]) == m[2] and m[1][1:9].tolist() == e._counters[:8].tolist()
+    ref = layer_u._forward_raw(_cuda(st), _cuda(ac), _cuda(mu), _cuda(sg))[0]
+    assert torch.equal(out.reshape(ref.shape), ref)
+    env_c, layer_c = cars
+    stc, acc, muc, sgc, t = O.synth_cars(B, seed=21)
+    layer_c.check_nan = True
+    ec = S.SimulatedCarsEnv(num_envs=B, precision="f32")
+    ec.state = _cuda(stc); ec._t.copy_(_cuda(t))
+    for _ in range(2):
+        ec.safe_step(layer_c, _cuda(acc), _cuda(sgc))
+        m = layer_c._mirrors[ec._counters.data_ptr()]
+        assert int(m[1][0]) == m[2] and m[1][1:9].tolist() == ec._counters[:8].tolist()
+    # a NaN input still raises, through the published counter
+    bad = ac.copy(); bad[B // 2, 0] = np.nan
+    with pytest.raises(Exception, match="QP Failed to solve"):
+        layer_u.get_safe_action(_cuda(st), _cuda(bad), _cuda(mu), _cuda(sg))
