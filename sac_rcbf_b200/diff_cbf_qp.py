@@ -5,6 +5,8 @@ Same constructor, attributes, method names, argument order, shapes, dtypes and e
 rcbf_sac/sac_cbf.py:233-236).  Compute always runs on the CUDA device; tensors that live elsewhere are copied in and
 the result is returned on the caller's device.  There is no CPU path.
 """
+import weakref
+
 import numpy as np
 import torch
 
@@ -203,9 +205,12 @@ class CBFQPLayer:
         mirrors = self.__dict__.setdefault("_mirrors", {})
         key = ws.data_ptr()
         m = mirrors.get(key)
-        if m is None:
+        if m is None or m[3]() is not ws:      # new workspace (possibly a fresh allocation at a recycled address)
+            if len(mirrors) > 64:
+                for k_ in [k_ for k_, v_ in mirrors.items() if v_[3]() is None]:
+                    del mirrors[k_]
             t = torch.zeros(9, dtype=torch.int64).pin_memory()
-            m = mirrors[key] = [t, t.numpy(), 0]
+            m = mirrors[key] = [t, t.numpy(), 0, weakref.ref(ws)]
             lib, stream = self._launch_ctx()
             _lib.check(lib.rcbf_counters_bind_mirror(key, t.data_ptr(), stream), "rcbf_counters_bind_mirror")
         m[2] = tok = (m[2] % 0x3fffff) + 1

@@ -25,7 +25,8 @@ for solver in ("presolve", "pdipm"):
     a = dev(acc).requires_grad_(True)
     layc.get_safe_action(dev(stc), a, dev(muc), dev(sgc)).sum().backward()
     envc.state = dev(stc); envc._t.copy_(dev(t))
-    envc.safe_step(layc, dev(acc), dev(sgc))
+    for _ in range(3):                    # presolve: k_cars2 on the 128 full tiles + k_safe on the ragged 3 instances
+        envc.safe_step(layc, dev(acc), dev(sgc))
 envc.step(dev(acc))
 P, q, G, h = layer.get_cbf_qp_constraints(dev(st), dev(ac), dev(mu), dev(sg))
 layer.solve_qp(P, q, G.clone(), h)
@@ -33,5 +34,13 @@ dm = S.DynamicsModel(env, args); dm.predict_next_state(st.astype(np.float64), ac
 S.rollout_transition(env, dm, O.unicycle_obs(st.astype(np.float64)), ac.astype(np.float64), np.zeros(B), np.zeros((B, 3)))
 pin = lambda x: torch.from_numpy(x).pin_memory()
 env.safe_step_host(layer, pin(ac), pin(mu), pin(sg), chunks=3)
+mem = S.DeviceReplayMemory(1000, seed=0, obs_dim=7, action_dim=2)            # row-major ring: tiled kernels
+for nb in (25, 700, 1300):
+    mem.batch_push(*[dev(x[:nb]) for x in (O.unicycle_obs(st.astype(np.float64)).astype(np.float32), ac,
+                                             st[:, 0], O.unicycle_obs(st.astype(np.float64)).astype(np.float32),
+                                             st[:, 1], st[:, 2], st[:, 2])])
+mem.sample(256); mem.sample(1000)
+mem.batch_push(dev(np.zeros((5, 7), np.float32)), dev(np.zeros((5, 2), np.float32)), dev(np.zeros(5, np.float32)),
+               dev(np.zeros((5, 7), np.float32)), dev(np.ones(5, np.float32)))    # no t / next_t: word-granular kernel
 torch.cuda.synchronize()
 print("sanitize workload done")
