@@ -7,9 +7,10 @@
 
 namespace rcbf {
 
-int launch_cars2(const CarsArgs& a, int64_t n, const CarsParams& p, const CarsEnvParams& e, rcbf_counters_t* ws,
-                 cudaStream_t s, int64_t* handled) {
-  return launch_cars2_tiles(a, n, p, e, ws, s, handled);
+int launch_cars2(bool fused, const CarsArgs& a, int64_t n, const CarsParams& p, const CarsEnvParams& e,
+                 rcbf_counters_t* ws, cudaStream_t s, int64_t* handled) {
+  return fused ? launch_cars2_tiles<true>(a, n, p, e, ws, s, handled)
+               : launch_cars2_tiles<false>(a, n, p, e, ws, s, handled);
 }
 
 }  // namespace rcbf

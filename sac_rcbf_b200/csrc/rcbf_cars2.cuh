@@ -24,8 +24,11 @@
 // are queued AFTER their tile's bulk stores completed; the kernel's tail (tail_drain) redoes them -- one launch per step.
 // Results are bit-identical to k_safe<CarsEnv<true>> (same per-instance functions, same operation order).
 //
-// Launch conditions (launch_cars2): solver_mode 0, no saved tensors, every array base 16-byte aligned; n is split into
-// full 32-instance tiles for this kernel and a ragged tail (< 32) for k_safe.
+// k_cars2<false> is the same loop for get_safe_action alone (read-only state; the finish stores the safe action and the
+// optional status / meta words): 0.100 -> see DESIGN 4.2b.
+//
+// Launch conditions (launch_cars2): solver_mode 0, no dense saved tensors, every array base 16-byte aligned; n is split
+// into full 32-instance tiles for this kernel and a ragged tail (< 32) for k_safe.
 #pragma once
 
 #include "rcbf_safe_kernels.cuh"
@@ -59,13 +62,17 @@ struct alignas(16) C2Warp {
   float obs[320];           // observation rows of the tile being finished (bulk-stored from here)
   float4 ring[kC2Ring][2];  // problem ring: Lgf[2], h[4], tag, -
   uint8_t cls[3][32];       // per instance: RCBF_OK_TRIVIAL / RCBF_OK_CERTIFIED / RCBF_NAN / RCBF_PENDING
+  uint16_t amask[3][32];    // layer-only kernel: active set of the certified solution (saved for the backward)
   uint64_t bar[2];
 };
 static_assert(sizeof(C2Warp) * kC2Warps * RCBF_C2_MINB + 1024 * RCBF_C2_MINB <= 233472, "shared memory of an SM");
 
+// kFused: the safe step (state in place, env outputs); !kFused: get_safe_action alone (state read-only, safe action +
+// optional status / meta out) -- same loop, the finish is then three lane-contiguous stores.
+template <bool kFused>
 __global__ void __launch_bounds__(kC2Threads, RCBF_C2_MINB)
 k_cars2(CarsArgs a, int64_t n /* multiple of 32 */, CarsParams p, CarsEnvParams e, rcbf_counters_t* ws) {
-  using E = CarsEnv<true>;
+  using E = CarsEnv<kFused>;
   constexpr int NZ = kCarsNZ, M = kCarsM, NWR = E::NWR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -80,17 +87,19 @@ k_cars2(CarsArgs a, int64_t n /* multiple of 32 */, CarsParams p, CarsEnvParams 
   int pk = 0, pk1 = 0;                           // problems pushed by tiles k, k-1 (the newest entries of the ring)
   int r3 = 0;                                    // k % 3
   int c_nan = 0, c_pend = 0, c_iters = 0, n_solve = 0, n_tiles = 0;
-  constexpr uint32_t kInBytes = 1280 + 128 + 128 + 128 + 1280;
+  constexpr uint32_t kInBytes = 1280 + 128 + (kFused ? 128 + 128 : 0) + 1280;
 
   auto issue = [&](int t, int k) {  // lane 0: tile t in flight into slot k & 3 (+ the sigma buffer)
     C2Warp::In& si = sh.in[k & 3];
     uint64_t* bar = &sh.bar[k & 1];
     const int64_t i0 = (int64_t)t << 5;
     mbar_expect_tx(bar, kInBytes);
-    bulk_g2s(si.st, a.state + i0 * 10, 1280, bar);
+    bulk_g2s(si.st, (kFused ? a.state : a.st) + i0 * 10, 1280, bar);
     bulk_g2s(si.ac, a.ac + i0, 128, bar);
-    bulk_g2s(si.t, a.t + i0, 128, bar);
-    bulk_g2s(si.step, a.step + i0, 128, bar);
+    if (kFused) {
+      bulk_g2s(si.t, a.t + i0, 128, bar);
+      bulk_g2s(si.step, a.step + i0, 128, bar);
+    }
     bulk_g2s(sh.sg, a.sg + i0 * 10, 1280, bar);
   };
 
@@ -141,6 +150,7 @@ k_cars2(CarsArgs a, int64_t n /* multiple of 32 */, CarsParams p, CarsEnvParams 
       const bool need = !triv && !nan;
       if (!need) si.ac[lane] = clampf(in.u[0] + (nan ? NAN : 0.f), p.u_min, p.u_max);   // diff_cbf_qp.py:77 (x = 0; NaN propagates)
       sh.cls[r3][lane] = (uint8_t)(nan ? RCBF_NAN : (need ? RCBF_OK_CERTIFIED : RCBF_OK_TRIVIAL));
+      if (!kFused) sh.amask[r3][lane] = 0;
       const unsigned b = __ballot_sync(0xffffffffu, need);
       pk = __popc(b);
       if (need) {
@@ -186,6 +196,7 @@ k_cars2(CarsArgs a, int64_t n /* multiple of 32 */, CarsParams p, CarsEnvParams 
         } else {
           *up = clampf(*up + (float)sol.x[0], p.u_min, p.u_max);   // :77
           sh.cls[(tag >> 6) & 3][pos] = (uint8_t)sol.status;
+          if (!kFused) sh.amask[(tag >> 6) & 3][pos] = (uint16_t)sol.mask;
           c_iters += sol.iters;
         }
       }
@@ -203,49 +214,55 @@ k_cars2(CarsArgs a, int64_t n /* multiple of 32 */, CarsParams p, CarsEnvParams 
       const int64_t i = i0 + lane;
       const float us = sf.ac[lane];
       const bool pend = __float_as_uint(us) == kPendingBits;
-      float s[10];
-      {
-        const float2* sp = reinterpret_cast<const float2*>(sf.st) + lane * 5;
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          const float2 s2 = sp[q];
-          s[2 * q] = s2.x; s[2 * q + 1] = s2.y;
-        }
-      }
-      float tt = sf.t[lane];
-      int stp = sf.step[lane];
-      CarsEnvOut<float> o;
-      cars_env_step<float>(e, s, tt, stp, us, o);
       a.out[i] = us;
       if (a.status != nullptr) a.status[i] = (int)sh.cls[rf][lane];
-      if (!pend) {   // a pending instance keeps its old state / t / step: the kernel's tail redoes it from scratch
-        a.reward[i] = o.reward;
-        a.done[i] = (uint8_t)o.done;
-        a.cost[i] = o.cost;
-        a.t[i] = tt;
-        a.step[i] = stp;
-      }
-      if (lane == 0) bulk_wait_read0();   // the previous tile's observation rows have left sh.obs
-      __syncwarp();
-      {
-        float2* wp = reinterpret_cast<float2*>(sf.st) + lane * 5;   // own row: nobody else reads or writes it
-        float2* op = reinterpret_cast<float2*>(sh.obs) + lane * 5;
+      if (!kFused && a.meta != nullptr)  // (status << 16) | active set: what the backward kernel needs
+        a.meta[i] = ((int)sh.cls[rf][lane] << 16) | (int)sh.amask[rf][lane];
+      if constexpr (kFused) {
+        float s[10];
+        {
+          const float2* sp = reinterpret_cast<const float2*>(sf.st) + lane * 5;
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-          if (!pend) wp[q] = make_float2(s[2 * q], s[2 * q + 1]);
-          op[q] = make_float2(o.obs[2 * q], o.obs[2 * q + 1]);
+          for (int q = 0; q < 5; ++q) {
+            const float2 s2 = sp[q];
+            s[2 * q] = s2.x; s[2 * q + 1] = s2.y;
+          }
+        }
+        float tt = sf.t[lane];
+        int stp = sf.step[lane];
+        CarsEnvOut<float> o;
+        cars_env_step<float>(e, s, tt, stp, us, o);
+        if (!pend) {   // a pending instance keeps its old state / t / step: the kernel's tail redoes it from scratch
+          a.reward[i] = o.reward;
+          a.done[i] = (uint8_t)o.done;
+          a.cost[i] = o.cost;
+          a.t[i] = tt;
+          a.step[i] = stp;
+        }
+        if (lane == 0) bulk_wait_read0();   // the previous tile's observation rows have left sh.obs
+        __syncwarp();
+        {
+          float2* wp = reinterpret_cast<float2*>(sf.st) + lane * 5;   // own row: nobody else reads or writes it
+          float2* op = reinterpret_cast<float2*>(sh.obs) + lane * 5;
+#pragma unroll
+          for (int q = 0; q < 5; ++q) {
+            if (!pend) wp[q] = make_float2(s[2 * q], s[2 * q + 1]);
+            op[q] = make_float2(o.obs[2 * q], o.obs[2 * q + 1]);
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copies
+        __syncwarp();
+        if (lane == 0) {
+          bulk_s2g(a.state + i0 * 10, sf.st, 1280);
+          bulk_s2g(a.obs + i0 * 10, sh.obs, 1280);
+          bulk_commit();
         }
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the bulk copies
-      __syncwarp();
-      if (lane == 0) {
-        bulk_s2g(a.state + i0 * 10, sf.st, 1280);
-        bulk_s2g(a.obs + i0 * 10, sh.obs, 1280);
-        bulk_commit();
-      }
       if (__any_sync(0xffffffffu, pend)) {  // (rare) queue them once the tile's stores are complete
-        if (lane == 0) bulk_wait0();
-        __syncwarp();
+        if (kFused) {
+          if (lane == 0) bulk_wait0();
+          __syncwarp();
+        }
         if (ws != nullptr && pend) {
           __threadfence();
           const unsigned long long slot = atomicAdd(&ws[kWsQueueCount], 1ULL);
@@ -302,11 +319,12 @@ k_cars2(CarsArgs a, int64_t n /* multiple of 32 */, CarsParams p, CarsEnvParams 
   }
 }
 
-// Launch k_cars2 on the full 32-instance tiles of the call.  *handled = number of leading instances it covers (0: the
+// Launch k_cars2<kFused> on the full 32-instance tiles of the call.  *handled = number of leading instances it covers (0: the
 // call does not qualify); the caller runs k_safe (launch_safe) on the ragged rest.
+template <bool kFused>
 inline int launch_cars2_tiles(const CarsArgs& a, int64_t n, const CarsParams& p, const CarsEnvParams& e,
                               rcbf_counters_t* ws, cudaStream_t s, int64_t* handled) {
-  using E = CarsEnv<true>;
+  using E = CarsEnv<kFused>;
   *handled = 0;
   static const bool env_off = [] {
     const char* v = getenv("RCBF_NO_CARS2");
@@ -314,15 +332,20 @@ inline int launch_cars2_tiles(const CarsArgs& a, int64_t n, const CarsParams& p,
   }();
   if (env_off || n < RCBF_C2_MIN_N || n > 0x7fffffffLL || solver_mode_of(p) != 0) return 0;
   auto ok16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr || a.meta != nullptr) return 0;
-  if (!(ok16(a.state) && ok16(a.t) && ok16(a.step) && ok16(a.ac) && ok16(a.sg) && ok16(a.obs))) return 0;
+  if (a.x != nullptr || a.lam != nullptr || a.slack != nullptr || a.iters != nullptr) return 0;
+  if (kFused) {
+    if (a.meta != nullptr || !(ok16(a.state) && ok16(a.t) && ok16(a.step) && ok16(a.ac) && ok16(a.sg) && ok16(a.obs)))
+      return 0;
+  } else if (!(ok16(a.st) && ok16(a.ac) && ok16(a.sg))) {
+    return 0;
+  }
   const int64_t n2 = n & ~(int64_t)31;
   const int64_t ntiles = n2 >> 5;
   int dev = 0;
   cudaGetDevice(&dev);
   static bool configured[64] = {};
   if (!configured[dev & 63]) {
-    cudaFuncSetAttribute(k_cars2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(C2Warp) * kC2Warps));
+    cudaFuncSetAttribute(k_cars2<kFused>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(C2Warp) * kC2Warps));
     configured[dev & 63] = true;
   }
   const int sms = device_sm_count();
@@ -331,7 +354,7 @@ inline int launch_cars2_tiles(const CarsArgs& a, int64_t n, const CarsParams& p,
   const int grid = (int)(want < resident ? want : resident);
   CarsParams pk = p;
   if (n2 != n) pk.solver_mode = solver_mode_of(p);  // a ragged rest follows: that kernel publishes the counters
-  cudaError_t err = launch_pdl(true, k_cars2, grid, kC2Threads, sizeof(C2Warp) * kC2Warps, s, a, n2, pk, e, ws);
+  cudaError_t err = launch_pdl(true, k_cars2<kFused>, grid, kC2Threads, sizeof(C2Warp) * kC2Warps, s, a, n2, pk, e, ws);
   if (err != cudaSuccess) return (int)err;
   if (ws == nullptr) {  // no workspace: a second kernel scans safe_action for the pending sentinel
     const int64_t fb = (n2 + 127) / 128;

@@ -9,9 +9,26 @@ using namespace rcbf;
 
 namespace rcbf {
 // rcbf_cars2.cu: the ring-compacted fused-step kernel on the leading full 32-instance tiles (if the call qualifies)
-int launch_cars2(const CarsArgs& a, int64_t n, const CarsParams& p, const CarsEnvParams& e, rcbf_counters_t* ws,
-                 cudaStream_t s, int64_t* handled);
+int launch_cars2(bool fused, const CarsArgs& a, int64_t n, const CarsParams& p, const CarsEnvParams& e,
+                 rcbf_counters_t* ws, cudaStream_t s, int64_t* handled);
 }
+
+namespace {
+// get_safe_action alone: k_cars2<false> on the full tiles, k_safe on the ragged rest (or on everything when the call
+// does not qualify: dense saved tensors, interior-point mode, unaligned arrays, small n)
+int launch_cars_layer(CarsArgs a, int64_t n, const rcbf_cars_params& p, rcbf_counters_t* ws, cudaStream_t s) {
+  int64_t handled = 0;
+  const int rc = launch_cars2(false, a, n, p, rcbf_cars_env_params{}, ws, s, &handled);
+  if (rc != 0) return rc;
+  if (handled == n) return 0;
+  if (handled > 0) {
+    a.st += handled * 10; a.ac += handled; a.sg += handled * 10; a.out += handled;
+    if (a.status != nullptr) a.status += handled;
+    if (a.meta != nullptr) a.meta += handled;
+  }
+  return launch_safe<CarsEnv<false>>(a, n - handled, p, rcbf_cars_env_params{}, ws, s);
+}
+}  // namespace
 
 extern "C" {
 
@@ -21,7 +38,7 @@ int rcbf_cars_safe_action(const float* state, const float* action, const float* 
   CarsArgs a{};
   a.st = state; a.ac = action; a.sg = sigma;
   a.out = safe_action; a.x = x; a.lam = lam; a.slack = slack; a.status = status; a.iters = iters;
-  return launch_safe<CarsEnv<false>>(a, n, *p, rcbf_cars_env_params{}, workspace, (cudaStream_t)stream);
+  return launch_cars_layer(a, n, *p, workspace, (cudaStream_t)stream);
 }
 
 int rcbf_cars_safe_action_saved(const float* state, const float* action, const float* sigma, int64_t n,
@@ -30,7 +47,7 @@ int rcbf_cars_safe_action_saved(const float* state, const float* action, const f
   CarsArgs a{};
   a.st = state; a.ac = action; a.sg = sigma;
   a.out = safe_action; a.meta = meta;
-  return launch_safe<CarsEnv<false>>(a, n, *p, rcbf_cars_env_params{}, workspace, (cudaStream_t)stream);
+  return launch_cars_layer(a, n, *p, workspace, (cudaStream_t)stream);
 }
 
 int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* action_rl, const float* sigma, int64_t n,
@@ -42,7 +59,7 @@ int rcbf_cars_safe_step(float* state, float* t, int32_t* step, const float* acti
   a.out = safe_action; a.status = status;
   a.obs = obs; a.reward = reward; a.done = done; a.cost = cost;
   int64_t handled = 0;
-  const int rc = launch_cars2(a, n, *p, *e, workspace, (cudaStream_t)stream, &handled);
+  const int rc = launch_cars2(true, a, n, *p, *e, workspace, (cudaStream_t)stream, &handled);
   if (rc != 0) return rc;
   if (handled == n) return 0;
   if (handled > 0) {  // ragged rest (< 32 instances) through the one-tile-at-a-time kernel

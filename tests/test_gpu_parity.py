@@ -982,3 +982,32 @@ def test_counters_are_published_by_the_kernel_itself(S, uni, cars, B):
     bad = ac.copy(); bad[B // 2, 0] = np.nan
     with pytest.raises(Exception, match="QP Failed to solve"):
         layer_u.get_safe_action(_cuda(st), _cuda(bad), _cuda(mu), _cuda(sg))
+
+
+@pytest.mark.parametrize("B", [4096, 50000 + 19])
+def test_cars_layer_ring_kernel_equals_the_one_tile_kernel(cars, B):
+    """get_safe_action for SimulatedCars at n >= 4096 runs k_cars2<false> (problem ring + finish lag) on the full tiles;
+    the same rows through arrays that are NOT 16-byte aligned take k_safe for every tile.  Safe action, status and the
+    meta word the backward reads must agree bit for bit, and so must the gradients computed from them."""
+    env_c, layer_c = cars
+    stc, acc, muc, sgc, _ = O.synth_cars(B + 1, seed=33)
+    d = [_cuda(x) for x in (stc, acc, muc, sgc)]
+    al = [x[1:].clone() for x in d]                  # fresh allocations: 16-byte aligned
+    un = [x[1:] for x in d]                          # views one row in: 40 / 4 bytes off
+    assert al[0].data_ptr() % 16 == 0 and un[0].data_ptr() % 16 != 0
+    out_a = layer_c._forward_raw(*al, want_status=True)[0]
+    st_a = layer_c._last_status.clone()
+    out_u = layer_c._forward_raw(*un, want_status=True)[0]
+    assert torch.equal(out_a, out_u) and torch.equal(st_a, layer_c._last_status) and int((st_a == 1).sum()) > B // 10
+    oa, ma = layer_c._forward_meta(*al)
+    ou, mu_ = layer_c._forward_meta(*un)
+    assert torch.equal(oa, out_a) and torch.equal(ou, out_a) and torch.equal(ma, mu_)
+    go = torch.randn_like(oa)
+    ga = layer_c._backward_meta(*al, ma, go)
+    gu = layer_c._backward_meta(*un, mu_, go)
+    assert torch.equal(ga, gu)
+    k = slice(0, 2000)
+    fe = O.safe_action("SimulatedCars", tt(stc[1:][k]), tt(acc[1:][k]), tt(muc[1:][k]), tt(sgc[1:][k]), solver="exact",
+                       gamma_b=20.0).numpy()
+    keep = O.cars_threshold_margin(stc[1:][k]) > 1e-4
+    assert np.abs(out_a[k].cpu().numpy() - fe)[keep].max() < 1e-4
