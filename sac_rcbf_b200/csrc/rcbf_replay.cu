@@ -39,7 +39,11 @@ struct RpDesc {
   int w[kRpFields];         // 4-byte words per row
   int64_t rs[kRpFields];    // 4-byte words between consecutive ring rows of the field
   int w0[kRpFields + 1];    // prefix sums: word j of the concatenated row belongs to field f with w0[f] <= j < w0[f+1]
+  uint32_t mw[kRpFields];   // floor(2^32 / w[f]) + 1: q / w[f] == __umulhi(q, mw[f]) for the q < 2^16 of a tile
+  uint32_t mv4;             // the same for the row stride in 16-byte vectors
 };
+
+__device__ __forceinline__ int rp_div(int q, uint32_t magic, int d) { return d == 1 ? q : (int)__umulhi((uint32_t)q, magic); }
 
 __device__ __forceinline__ uint32_t rp_mix(uint32_t x) {  // murmur3 finaliser
   x ^= x >> 16;
@@ -52,7 +56,15 @@ __device__ __forceinline__ uint32_t rp_mix(uint32_t x) {  // murmur3 finaliser
 
 // Keyed bijection of [0, size): balanced Feistel network over 2 * hb bits (2^(2 hb) >= size), 6 rounds, cycle-walked.
 // i < size, so walking the cycle that starts at i always comes back into the range.
-__device__ __forceinline__ int64_t rp_perm(int64_t i, int64_t size, int hb, uint64_t key) {
+__host__ __device__ __forceinline__ uint64_t rp_rotation(uint64_t key, int64_t size) {
+  uint64_t o = key * 0x9e3779b97f4a7c15ull;
+  o ^= o >> 29;
+  o *= 0xbf58476d1ce4e5b9ull;
+  o ^= o >> 32;
+  return o % (uint64_t)size;
+}
+
+__device__ __forceinline__ int64_t rp_perm(int64_t i, int64_t size, int hb, uint64_t key, uint64_t rot) {
   const uint32_t hm = (hb >= 32) ? 0xffffffffu : ((1u << hb) - 1u);
   const uint32_t k0 = (uint32_t)key, k1 = (uint32_t)(key >> 32);
   uint64_t v = (uint64_t)i;
@@ -67,13 +79,9 @@ __device__ __forceinline__ int64_t rp_perm(int64_t i, int64_t size, int hb, uint
     }
     v = ((uint64_t)l << hb) | (uint64_t)r;
   } while (v >= (uint64_t)size);
-  // a key-derived rotation on top: whatever structure a narrow network leaves (2-bit halves for a 7-row ring), every
-  // output slot is exactly uniform over the rows
-  uint64_t o = key * 0x9e3779b97f4a7c15ull;
-  o ^= o >> 29;
-  o *= 0xbf58476d1ce4e5b9ull;
-  o ^= o >> 32;
-  v += o % (uint64_t)size;
+  // a key-derived rotation on top (rot = rp_rotation(key, size), computed once on the host): whatever structure a
+  // narrow network leaves (2-bit halves for a 7-row ring), every output slot is exactly uniform over the rows
+  v += rot;
   v -= v >= (uint64_t)size ? (uint64_t)size : 0ull;
   return (int64_t)v;
 }
@@ -102,13 +110,13 @@ k_replay_push(RpDesc d, int64_t capacity, int64_t position, int64_t n) {
 }
 
 __global__ void __launch_bounds__(kRpThreads)
-k_replay_sample(RpDesc d, int64_t size, int64_t batch, int hb, uint64_t key, int64_t* idx_out) {
+k_replay_sample(RpDesc d, int64_t size, int64_t batch, int hb, uint64_t key, uint64_t rot, int64_t* idx_out) {
   __shared__ int64_t s_idx[kRpRows];
   const int W = d.w0[kRpFields];
   for (int64_t r0 = (int64_t)blockIdx.x * kRpRows; r0 < batch; r0 += (int64_t)gridDim.x * kRpRows) {
     const int rows = (int)(batch - r0 < kRpRows ? batch - r0 : kRpRows);
     if ((int)threadIdx.x < rows) {
-      const int64_t ix = rp_perm(r0 + threadIdx.x, size, hb, key);
+      const int64_t ix = rp_perm(r0 + threadIdx.x, size, hb, key, rot);
       s_idx[threadIdx.x] = ix;
       if (idx_out != nullptr) idx_out[r0 + threadIdx.x] = ix;
     }
@@ -137,20 +145,20 @@ constexpr int kRpMaxStride = 64;  // words (256 B) per ring row the tile is size
 // ring rows (sw words apart, 16-byte aligned) of the drawn indices -> tile -> the seven field-major outputs
 __global__ void __launch_bounds__(kRpThreads)
 k_replay_sample_rows(RpDesc d, const uint4* __restrict__ rows_base, int sw, int64_t size, int64_t batch, int hb,
-                     uint64_t key, int64_t* idx_out) {
+                     uint64_t key, uint64_t rot, int64_t* idx_out) {
   __shared__ int64_t s_idx[kRpRows];
   __shared__ __align__(16) uint32_t tile[kRpRows * kRpMaxStride];
   const int v4 = sw >> 2;
   for (int64_t r0 = (int64_t)blockIdx.x * kRpRows; r0 < batch; r0 += (int64_t)gridDim.x * kRpRows) {
     const int rows = (int)(batch - r0 < kRpRows ? batch - r0 : kRpRows);
     if ((int)threadIdx.x < rows) {
-      const int64_t ix = rp_perm(r0 + threadIdx.x, size, hb, key);
+      const int64_t ix = rp_perm(r0 + threadIdx.x, size, hb, key, rot);
       s_idx[threadIdx.x] = ix;
       if (idx_out != nullptr) idx_out[r0 + threadIdx.x] = ix;
     }
     __syncthreads();
     for (int q = threadIdx.x; q < rows * v4; q += kRpThreads) {
-      const int rr = q / v4, c = q - rr * v4;
+      const int rr = rp_div(q, d.mv4, v4), c = q - rr * v4;
       reinterpret_cast<uint4*>(tile)[q] = __ldg(rows_base + s_idx[rr] * v4 + c);
     }
     __syncthreads();
@@ -162,7 +170,7 @@ k_replay_sample_rows(RpDesc d, const uint4* __restrict__ rows_base, int sw, int6
       const int cnt = rows * w;
       const int nv = (reinterpret_cast<uintptr_t>(d.io[f]) & 15) == 0 ? cnt >> 2 : 0;   // 16-byte stores
       for (int q = threadIdx.x; q < nv; q += kRpThreads) {
-        int rr = (4 * q) / w, c = 4 * q - rr * w;
+        int rr = rp_div(4 * q, d.mw[f], w), c = 4 * q - rr * w;
         uint32_t v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -172,7 +180,7 @@ k_replay_sample_rows(RpDesc d, const uint4* __restrict__ rows_base, int sw, int6
         reinterpret_cast<uint4*>(out)[q] = make_uint4(v[0], v[1], v[2], v[3]);
       }
       for (int q = 4 * nv + threadIdx.x; q < cnt; q += kRpThreads) {
-        const int rr = q / w, c = q - rr * w;
+        const int rr = rp_div(q, d.mw[f], w), c = q - rr * w;
         out[q] = tile[rr * sw + off + c];
       }
     }
@@ -197,7 +205,7 @@ k_replay_push_rows(RpDesc d, uint4* __restrict__ rows_base, int sw, int64_t capa
       for (int q = threadIdx.x; q < nv; q += kRpThreads) {
         const uint4 t = __ldg(reinterpret_cast<const uint4*>(src) + q);
         const uint32_t v[4] = {t.x, t.y, t.z, t.w};
-        int rr = (4 * q) / w, c = 4 * q - rr * w;
+        int rr = rp_div(4 * q, d.mw[f], w), c = 4 * q - rr * w;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           tile[rr * sw + off + c] = v[j];
@@ -205,7 +213,7 @@ k_replay_push_rows(RpDesc d, uint4* __restrict__ rows_base, int sw, int64_t capa
         }
       }
       for (int q = 4 * nv + threadIdx.x; q < cnt; q += kRpThreads) {
-        const int rr = q / w, c = q - rr * w;
+        const int rr = rp_div(q, d.mw[f], w), c = q - rr * w;
         tile[rr * sw + off + c] = __ldg(src + q);
       }
     }
@@ -215,7 +223,7 @@ k_replay_push_rows(RpDesc d, uint4* __restrict__ rows_base, int sw, int64_t capa
     }
     __syncthreads();
     for (int q = threadIdx.x; q < rows * v4; q += kRpThreads) {
-      const int rr = q / v4, c = q - rr * v4;
+      const int rr = rp_div(q, d.mv4, v4), c = q - rr * v4;
       int64_t row = position + r0 + rr;
       row -= row >= capacity ? capacity : 0;
       rows_base[row * v4 + c] = reinterpret_cast<const uint4*>(tile)[q];
@@ -248,7 +256,10 @@ inline int rp_fill(RpDesc& d, const rcbf_replay_ring* r, void* const io[]) {
     d.rs[f] = r->row_stride[f] > 0 ? r->row_stride[f] * e : w[f];
     if (d.rs[f] < w[f]) return cudaErrorInvalidValue;
     d.w0[f + 1] = d.w0[f] + w[f];
+    d.mw[f] = (uint32_t)(0x100000000ull / (uint64_t)w[f]) + 1u;
   }
+  const int64_t sw4 = d.rs[0] >> 2;
+  d.mv4 = sw4 > 0 ? (uint32_t)(0x100000000ull / (uint64_t)sw4) + 1u : 0u;
   return 0;
 }
 
@@ -304,10 +315,10 @@ int rcbf_replay_sample(const rcbf_replay_ring* ring, int64_t size, int64_t batch
   const int64_t cap = (int64_t)rp_sms() * 8;
   if (const int sw = rp_row_major(d))
     k_replay_sample_rows<<<(int)(want < cap ? want : cap), kRpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        d, reinterpret_cast<const uint4*>(d.ring[0]), sw, size, batch, bits / 2, key, idx_out);
+        d, reinterpret_cast<const uint4*>(d.ring[0]), sw, size, batch, bits / 2, key, rp_rotation(key, size), idx_out);
   else
     k_replay_sample<<<(int)(want < cap ? want : cap), kRpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        d, size, batch, bits / 2, key, idx_out);
+        d, size, batch, bits / 2, key, rp_rotation(key, size), idx_out);
   return (int)cudaGetLastError();
 }
 
