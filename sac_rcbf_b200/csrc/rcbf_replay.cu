@@ -140,17 +140,26 @@ k_replay_sample(RpDesc d, int64_t size, int64_t batch, int hb, uint64_t key, uin
 
 
 // ---- row-major ring: whole rows through a shared-memory tile ---------------------------------------------------------
-constexpr int kRpMaxStride = 64;  // words (256 B) per ring row the tile is sized for
+constexpr int kRpMaxStride = 64;    // words (256 B) per ring row: the widest row the tile takes
+constexpr int kRpSampleTileWords = 4096;  // 16 KB: 168 rows of the Unicycle's 96-byte stride (64 of the widest one)
+constexpr int kRpPushTileWords = 6144;    // 24 KB: 256 rows
+constexpr int kRpMaxRows = 256;
+// Bytes in flight per barrier are what bounds these kernels.  4 Mi-row draw + gather on B200: 319 us with 64-row tiles,
+// 214 us with 168 rows, 270 us with 256 rows (the 24 KB tile leaves the random row fetches 20 KB of L1); 4 Mi-row push:
+// 317 / 200 / 179 us.
+// (Tried on B200: a barrier-free form -- G lanes per row, one 16-byte vector of the ring row per lane, the four words
+//  scattered to / gathered from the field arrays by 4-byte accesses.  440 us per 4 Mi rows against 319 us: the
+//  sector-partial accesses to seven arrays cost more than the barriers they remove.)
 
 // ring rows (sw words apart, 16-byte aligned) of the drawn indices -> tile -> the seven field-major outputs
 __global__ void __launch_bounds__(kRpThreads)
-k_replay_sample_rows(RpDesc d, const uint4* __restrict__ rows_base, int sw, int64_t size, int64_t batch, int hb,
-                     uint64_t key, uint64_t rot, int64_t* idx_out) {
-  __shared__ int64_t s_idx[kRpRows];
-  __shared__ __align__(16) uint32_t tile[kRpRows * kRpMaxStride];
+k_replay_sample_rows(RpDesc d, const uint4* __restrict__ rows_base, int sw, int R /* rows per tile */, int64_t size,
+                     int64_t batch, int hb, uint64_t key, uint64_t rot, int64_t* idx_out) {
+  __shared__ int64_t s_idx[kRpMaxRows];
+  __shared__ __align__(16) uint32_t tile[kRpSampleTileWords];
   const int v4 = sw >> 2;
-  for (int64_t r0 = (int64_t)blockIdx.x * kRpRows; r0 < batch; r0 += (int64_t)gridDim.x * kRpRows) {
-    const int rows = (int)(batch - r0 < kRpRows ? batch - r0 : kRpRows);
+  for (int64_t r0 = (int64_t)blockIdx.x * R; r0 < batch; r0 += (int64_t)gridDim.x * R) {
+    const int rows = (int)(batch - r0 < R ? batch - r0 : R);
     if ((int)threadIdx.x < rows) {
       const int64_t ix = rp_perm(r0 + threadIdx.x, size, hb, key, rot);
       s_idx[threadIdx.x] = ix;
@@ -166,7 +175,7 @@ k_replay_sample_rows(RpDesc d, const uint4* __restrict__ rows_base, int sw, int6
     for (int f = 0; f < kRpFields; ++f) {
       if (d.io[f] == nullptr) continue;
       const int w = d.w[f], off = d.w0[f];
-      uint32_t* out = d.io[f] + r0 * w;   // (r0 * w words = a multiple of 256 bytes past the array base)
+      uint32_t* out = d.io[f] + r0 * w;   // (R is a multiple of 4: r0 * w words = a multiple of 16 bytes past the base)
       const int cnt = rows * w;
       const int nv = (reinterpret_cast<uintptr_t>(d.io[f]) & 15) == 0 ? cnt >> 2 : 0;   // 16-byte stores
       for (int q = threadIdx.x; q < nv; q += kRpThreads) {
@@ -190,12 +199,13 @@ k_replay_sample_rows(RpDesc d, const uint4* __restrict__ rows_base, int sw, int6
 
 // the seven field-major sources (all present) -> tile -> ring rows (position + i) % capacity
 __global__ void __launch_bounds__(kRpThreads)
-k_replay_push_rows(RpDesc d, uint4* __restrict__ rows_base, int sw, int64_t capacity, int64_t position, int64_t n) {
-  __shared__ __align__(16) uint32_t tile[kRpRows * kRpMaxStride];
+k_replay_push_rows(RpDesc d, uint4* __restrict__ rows_base, int sw, int R /* rows per tile */, int64_t capacity,
+                   int64_t position, int64_t n) {
+  __shared__ __align__(16) uint32_t tile[kRpPushTileWords];
   const int v4 = sw >> 2;
   const int W = d.w0[kRpFields];
-  for (int64_t r0 = (int64_t)blockIdx.x * kRpRows; r0 < n; r0 += (int64_t)gridDim.x * kRpRows) {
-    const int rows = (int)(n - r0 < kRpRows ? n - r0 : kRpRows);
+  for (int64_t r0 = (int64_t)blockIdx.x * R; r0 < n; r0 += (int64_t)gridDim.x * R) {
+    const int rows = (int)(n - r0 < R ? n - r0 : R);
 #pragma unroll
     for (int f = 0; f < kRpFields; ++f) {
       const int w = d.w[f], off = d.w0[f];
@@ -230,6 +240,13 @@ k_replay_push_rows(RpDesc d, uint4* __restrict__ rows_base, int sw, int64_t capa
     }
     __syncthreads();
   }
+}
+
+// rows per tile for a stride of sw words: as many as the tile holds, a multiple of 4 (16-byte aligned field chunks)
+inline int rp_tile_rows(int sw, int tile_words) {
+  int r = tile_words / sw;
+  r = r > kRpMaxRows ? kRpMaxRows : r;
+  return r & ~3;
 }
 
 // Is the ring one row-major matrix the tiled kernels can move?  -> stride in words (0: no)
@@ -287,9 +304,10 @@ int rcbf_replay_push(const rcbf_replay_ring* ring, int64_t position, const void*
   bool all_src = true;
   for (int f = 0; f < kRpFields; ++f) all_src = all_src && src[f] != nullptr;
   if (const int sw = all_src ? rp_row_major(d) : 0) {
-    const int64_t want = (n + kRpRows - 1) / kRpRows;
+    const int R = rp_tile_rows(sw, kRpPushTileWords);
+    const int64_t want = (n + R - 1) / R;
     k_replay_push_rows<<<(int)(want < cap ? want : cap), kRpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        d, reinterpret_cast<uint4*>(d.ring[0]), sw, ring->capacity, position, n);
+        d, reinterpret_cast<uint4*>(d.ring[0]), sw, R, ring->capacity, position, n);
     return (int)cudaGetLastError();
   }
   const int64_t total = n * d.w0[kRpFields];
@@ -313,9 +331,12 @@ int rcbf_replay_sample(const rcbf_replay_ring* ring, int64_t size, int64_t batch
   bits += bits & 1;  // balanced halves
   const int64_t want = (batch + kRpRows - 1) / kRpRows;
   const int64_t cap = (int64_t)rp_sms() * 8;
-  if (const int sw = rp_row_major(d))
-    k_replay_sample_rows<<<(int)(want < cap ? want : cap), kRpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-        d, reinterpret_cast<const uint4*>(d.ring[0]), sw, size, batch, bits / 2, key, rp_rotation(key, size), idx_out);
+  if (const int sw = rp_row_major(d)) {
+    const int R = rp_tile_rows(sw, kRpSampleTileWords);
+    const int64_t wantr = (batch + R - 1) / R;
+    k_replay_sample_rows<<<(int)(wantr < cap ? wantr : cap), kRpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        d, reinterpret_cast<const uint4*>(d.ring[0]), sw, R, size, batch, bits / 2, key, rp_rotation(key, size), idx_out);
+  }
   else
     k_replay_sample<<<(int)(want < cap ? want : cap), kRpThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         d, size, batch, bits / 2, key, rp_rotation(key, size), idx_out);
