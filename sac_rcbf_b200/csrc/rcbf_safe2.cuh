@@ -35,7 +35,8 @@
 namespace rcbf {
 
 #ifndef RCBF_S2_MINB
-#define RCBF_S2_MINB 1     // resident blocks per SM (A/B on B200: 1 x 12 warps > 3 x 4 warps > 2 x 6 warps)
+#define RCBF_S2_MINB 1     // resident blocks per SM (A/B on B200: 1 x 12 warps > 3 x 4 warps > 2 x 6 warps; at 16 warps
+                           // per SM: 1 x 16 0.1272 ms, 2 x 8 (ring of 82 entries so that both fit) 0.1320 ms)
 #endif
 #ifndef RCBF_S2_WARPS
 #define RCBF_S2_WARPS 16   // warps per block
