@@ -158,6 +158,9 @@ def time_cpu_reference(seconds, n, batch=CPU_BATCH):
         el = time.perf_counter() - t0
         if el >= seconds:
             break
+    # the wall-clock GPU sections that follow are host-bound loops of a single thread: leave no 16-thread OpenMP team
+    # behind (its idle workers spin and slowed those loops 2-3x: replay sample(256) 42 us instead of 18 us)
+    torch.set_num_threads(1)
     return done / el, done, el
 
 
@@ -468,12 +471,14 @@ def secondary_workloads(S, lib, _lib, device, env, layer, batches, n, ns):
         layer.check_nan = False
         row["safe_step_us_nocheck"] = wall_us(lambda: env_b.safe_step(layer, a5, m5, g5))
         hs, ha, hm, hg = (x.cpu().numpy() for x in (s5, a5, m5, g5))
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
         t0 = _t.perf_counter()
         reps = 0
         while _t.perf_counter() - t0 < 0.5:
             O_.safe_action("Unicycle", tt_(hs), tt_(ha), tt_(hm), tt_(hg), gamma_b=20.0)
             reps += 1
         row["cpu_port_get_safe_action_us"] = (_t.perf_counter() - t0) / reps * 1e6
+        torch.set_num_threads(1)          # (see time_cpu_reference)
         lat["rows"].append(row)
     env1 = S.UnicycleEnv(device=device)
     lat["single_env_gym_step_us"] = wall_us(lambda: env1.step(np.array([0.3, 0.1])), iters=200)
