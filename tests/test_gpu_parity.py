@@ -1011,3 +1011,31 @@ def test_cars_layer_ring_kernel_equals_the_one_tile_kernel(cars, B):
                        gamma_b=20.0).numpy()
     keep = O.cars_threshold_margin(stc[1:][k]) > 1e-4
     assert np.abs(out_a[k].cpu().numpy() - fe)[keep].max() < 1e-4
+
+
+def test_cars_fused_step_full_size_properties(S, cars):
+    """BASELINE's 4 Mi-instance size for the fused SimulatedCars step (k_cars2): the result of an instance does not
+    depend on where it sits (permutation equivariance: other tile, other ring order, other B-step companions), and a
+    seeded sub-sample equals the same rows stepped in a launch small enough to take the one-tile-at-a-time kernel."""
+    env_c, layer_c = cars
+    B = 1 << 22
+    stc, acc, muc, sgc, t = O.synth_cars(B, seed=44)
+    d = [_cuda(x) for x in (stc, acc, sgc, t)]
+    g = torch.Generator(device="cuda").manual_seed(9)
+    perm = torch.randperm(B, generator=g, device="cuda")
+    outs = []
+    for sel in (None, perm):
+        st_, ac_, sg_, t_ = d if sel is None else [x[sel].contiguous() for x in d]
+        e = S.SimulatedCarsEnv(num_envs=B)
+        e.state = st_; e._t.copy_(t_)
+        us, obs, rew, done, info = e.safe_step(layer_c, ac_, sg_)
+        outs.append([x.clone() for x in (us, obs, rew, info["cost"], e.state, e._t)])
+    for a, b in zip(*outs):
+        assert torch.equal(a[perm], b)
+    assert float(outs[0][0].abs().max()) <= 10.0 and not bool(torch.isnan(outs[0][1]).any())
+    idx = torch.randperm(B, generator=g, device="cuda")[:3000]
+    e = S.SimulatedCarsEnv(num_envs=3000)
+    e.state = d[0][idx].contiguous(); e._t.copy_(d[3][idx])
+    us, obs, rew, done, info = e.safe_step(layer_c, d[1][idx].contiguous(), d[2][idx].contiguous())
+    for a, b in zip(outs[0], (us, obs, rew, info["cost"], e.state, e._t)):
+        assert torch.equal(a[idx], b)
