@@ -64,6 +64,8 @@ class DeviceReplayMemory:
         widths = (self.obs_dim, self.action_dim, 1, self.obs_dim, 1, 1, 1)
         self._widths = widths
         row = sum(widths)
+        # (a 128-byte stride -- one L2 line per row instead of 1.5 on average -- measured slower: 237 against 214 us per
+        #  4 Mi-row draw, 225 against 179 us per push; fewer rows fit a tile and the push writes a third more)
         stride = (row * eb + 31) // 32 * 32 // eb
         self._rows = torch.zeros((self.capacity, stride), dtype=dtype, device=self.device)
         offs = [sum(widths[:f]) for f in range(7)]
